@@ -1,0 +1,164 @@
+/* sos_b200.h -- C ABI of the B200-native Successive-Orders-of-Scattering engine.
+ *
+ * The reference (Guillaume-SOULIER/SOS-Radiative-Transfer) is pure Python/NumPy and has
+ * no FFI; its "operator interface" for the hot path is a set of Python call signatures
+ * (SURVEY.md 8b).  Every entry point below names the reference lines it replaces; the
+ * ctypes binding a reference maintainer would add is shown in INTEGRATION.md and is what
+ * sos-radiative-transfer_b200/_lib.py does.
+ *
+ * Conventions
+ *   - plain C: opaque plan handle, raw pointers, ints, doubles; no torch / C++ types.
+ *   - every function returns 0 on success or a negative sos_error; nothing throws.
+ *   - pointers named *_d are DEVICE pointers owned by the caller (e.g. torch tensors),
+ *     pointers named *_h are HOST pointers read during the call only.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - a "field" is a row-major double array [S*L rows][ld] (row = scenario*L + layer,
+ *     N = 2*nb_angles mu-columns used, ld >= N, ld even); S scenarios are stacked along
+ *     rows.  This is the reference's (L, 2*nb_angles) C-order array (SOS_Aer_I1_In.py:20)
+ *     with a batch dimension in front.
+ *   - one plan per (grid, batch); a plan owns its scratch and is not thread-safe; calls on
+ *     one plan must be issued on one stream at a time.
+ */
+#ifndef SOS_B200_H
+#define SOS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOS_ABI_VERSION 1
+
+typedef struct sos_plan sos_plan;
+
+typedef enum {
+  SOS_OK = 0,
+  SOS_ERR_INVALID = -1,      /* bad argument */
+  SOS_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed (see sos_last_cuda_error) */
+  SOS_ERR_NOMEM = -3,
+  SOS_ERR_UNSUPPORTED = -4,  /* e.g. not an sm_100 device */
+  SOS_ERR_STATE = -5         /* call order violated (e.g. source before set_phase) */
+} sos_error;
+
+typedef enum {
+  SOS_SURFACE_NONE = 0,      /* single homogeneous layer: In_NumInt (SOS_Aer_I1_In.py:77-130) */
+  SOS_SURFACE_SPECULAR = 1,  /* SOS_Aer_main_specular.py:397,399 */
+  SOS_SURFACE_LAMBERT = 2    /* Lambert-as-coded: SOS_Aer_main_lambertian.py:399,401 */
+} sos_surface;
+
+/* device-side status bits (OR-ed per scenario) */
+#define SOS_STATUS_BLEND_OVERRUN 1u /* reference would raise IndexError (SOS_Aer_I1_In.py:103) */
+#define SOS_STATUS_NONFINITE 2u     /* inf/nan met in a convergence ratio */
+
+/* Grid shared by all scenarios of a batch. */
+typedef struct {
+  int nb_layers;        /* L */
+  int nb_angles;        /* M; N = 2M columns: mu = [linspace(-1,0,M), linspace(0,1,M)] */
+  int n_scenarios;      /* S */
+  int n_regions;        /* 1 (single layer) or 3 (upper atm / aerosol / lower atm) */
+  int region_start[4];  /* first row of each region; region_start[n_regions] = L.
+                           3 regions: {0, idx_up, idx_down+1, L} (SOS_Aer_main_specular.py:330,349,368) */
+  int surface;          /* sos_surface */
+  int ld;               /* leading dimension of fields (elements) */
+  int chunk_rows;       /* rows per scan chunk; 0 = let the library choose */
+} sos_grid;
+
+/* Per-scenario scalars. */
+typedef struct {
+  double mu0;           /* SOS_Aer_main_specular.py:23 */
+  double grd_alb;       /* :47 */
+  double tauStar_tot;   /* :36  (tauStar_atm + tauStar_aer; single layer: tauStar) */
+  double coef_atm;      /* source-contraction scale on rows outside the aerosol region: alb_atm (:323);
+                           single layer: alb (SOS_Aer_I1_In.py:73) */
+  double coef_mix_atm;  /* aerosol rows: alb_atm * dtau_atm/(dtau_atm+dtau_aer)  (:321) */
+  double coef_mix_aer;  /* aerosol rows: alb_aer * dtau_aer/(dtau_atm+dtau_aer)  (:321) */
+  double threshold;     /* convergence threshold, 1e-4 (:309) */
+  int phase_atm;        /* index into the matrices registered with sos_plan_set_phase */
+  int phase_aer;
+  int extrap_width[3];  /* idx of improved_limit_mu_down per region (:342-345,361-364,380-383;
+                           single layer SOS_Aer_I1_In.py:124-127) */
+  int reserved;
+} sos_scenario;
+
+/* Per-scenario results of sos_solve / sos_converge (host copy). */
+typedef struct {
+  double ratio_toa;     /* max(In[0,M:]/I[0,M:])  (:309) */
+  double ratio_surf;    /* max(In[L-1,:M]/I[L-1,:M]) */
+  int n_orders;         /* the reference's `n` at loop exit */
+  int active;           /* 1 while the scenario has not converged */
+  unsigned status;      /* SOS_STATUS_* bits */
+  int reserved;
+} sos_result;
+
+int sos_abi_version(void);
+const char* sos_strerror(int err);
+const char* sos_last_cuda_error(void);
+
+/* mu-grid constants + per-scenario tau profiles (SOS_Aer_tau_profile.py:21-27) are uploaded
+ * once.  tau_h: [S][L]; mu_h: [N]; extrap_W_h: 4 extrapolation matrices for the widths
+ * int(0.005M), int(0.02M), int(0.04M), int(0.06M) -- see sos_extrap_layout(). */
+int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, const double* tau_h,
+                    const sos_scenario* scen_h, const double* extrap_W_h, int extrap_W_len);
+int sos_plan_destroy(sos_plan* plan);
+
+/* Extrapolation table layout: for width class c (0..3) the matrix W_c is [idx_c][ns_c] row-major
+ * at offset off_c in extrap_W_h, where ns_c = (idx_c<2 ? 2 : min(5, idx_c)) sources
+ * (SOS_Aer_In_limit.py:118-141).  Writes idx[4], ns[4], off[4] and returns the total length. */
+int sos_extrap_layout(int nb_angles, int* idx, int* ns, int* off);
+
+/* A[k][m] = 0.25 * w_k * P[m][N-1-k]  (the operand of Jn_NumInt as a GEMM, SOS_Aer_I1_In.py:73;
+ * w = composite-trapezoid weights of the mu grid).  P_d: [N][ldp], A_d: [N][lda]. */
+int sos_build_contraction(sos_plan* plan, const double* P_d, int ldp, double* A_d, int lda, void* stream);
+
+/* Register the contraction matrices (device, [N][lda] each) the scenarios index. */
+int sos_plan_set_phase(sos_plan* plan, const double* const* A_d, int n_matrices, int lda);
+
+/* First order.
+ *  n_regions == 3: inlined closed form of SOS_Aer_main_specular.py:104-292; C_h is [S][2][N]:
+ *     C_h[s][0][m] = alb_atm*P0_atm[m], C_h[s][1][m] = alb_atm*P0_atm[m]*f_atm + alb_aer*P0_aer[m]*f_aer
+ *  n_regions == 1: I1_NumInt (SOS_Aer_I1_In.py:13-58); C_h[s][0][m] = alb*P0[m] ([S][2][N], plane 1 unused) */
+int sos_first_order(sos_plan* plan, const double* C_h, double* I1_d, void* stream);
+
+/* Jn_NumInt (SOS_Aer_I1_In.py:62-74) / SOS_Aer_main_specular.py:315-323 as one FP64 GEMM. */
+int sos_source(sos_plan* plan, const double* In1_d, double* J_d, void* stream);
+
+/* In_NumInt (SOS_Aer_I1_In.py:77-130) / SOS_Aer_main_specular.py:327-449: down scan, mu->0
+ * columns, extrapolation, surface coupling, up scan, blend.  If I_d != NULL also I += I_n and
+ * the convergence ratios of :309 are refreshed (SOS_Aer_main_specular.py:454-456). */
+int sos_sweeps(sos_plan* plan, const double* J_d, double* In_d, double* I_d, void* stream);
+
+/* Convergence bookkeeping for the order that was just accumulated (`n` = its order number):
+ * scenarios whose ratio fell below threshold become inactive with n_orders = n. */
+int sos_converge(sos_plan* plan, int order, void* stream);
+
+/* Whole order loop (SOS_Aer_main_specular.py:302-458).  I_d holds I1 on entry and I on exit;
+ * In_d must hold I1 as well (it is the I_{n-1} operand of order 2) and holds the last order on
+ * exit; J_d is scratch.  orders_d (may be NULL) receives every order: [max_saved][S*L][ld]
+ * (I_saved, :304-305,458), order n>=2 at index n-2.  poll_every: orders enqueued between two
+ * non-blocking polls of the device "all converged" counter (>=1).  results_h: [S]. */
+int sos_solve(sos_plan* plan, double* I_d, double* In_d, double* J_d, double* orders_d, int max_saved,
+              int max_orders, int poll_every, sos_result* results_h, void* stream);
+
+/* Copy the per-scenario results to the host (synchronises the stream). */
+int sos_get_results(sos_plan* plan, sos_result* results_h, void* stream);
+/* Reset per-scenario state (active=1, n_orders=1, ratios from I1 with In := 1 as in :306-309). */
+int sos_reset(sos_plan* plan, const double* I1_d, void* stream);
+
+/* Quadratures of SOS_Aer_graphe.py: flux_up/flux_down (:154-158, direct beam scaled by
+ * direct_scale: 1 there, 1/(4 pi) in :77-78 and SOS_Aer_critical_albedo.py:380-381),
+ * net flux (:39-41), mean diffusivity (:8-10) and heating rate (:70-91; z_h: [L] altitudes).
+ * Outputs are device arrays [S][L]; any may be NULL. */
+int sos_quadratures(sos_plan* plan, const double* I_d, double direct_scale, const double* z_h,
+                    double* flux_up_d, double* flux_down_d, double* net_flux_d, double* diffusivity_d,
+                    double* heating_d, void* stream);
+
+/* Number of kernel launches issued through this plan so far (bench.py's gpu_launches). */
+long long sos_launch_count(const sos_plan* plan);
+
+/* FP64 throughput probe used for the roofline denominator (DFMA or DMMA loop, all SMs);
+ * returns TFLOP/s in *tflops.  kind: 0 = DFMA, 1 = DMMA m8n8k4. */
+int sos_fp64_peak(int kind, int repeats, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOS_B200_H */

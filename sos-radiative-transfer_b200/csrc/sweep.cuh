@@ -1,0 +1,513 @@
+// Layer integration of one scattering order: In_NumInt (SOS_Aer_I1_In.py:77-130) and its inlined
+// three-region form (SOS_Aer_main_specular.py:327-449; Lambert surface SOS_Aer_main_lambertian.py:399,401).
+//
+// The reference evaluates every (layer, mu) value as a trapezoid over the whole slice above/below it
+// (O(L^2 N)).  With a_t = exp(-dtau_t/|mu|) this is the linear recurrence
+//     down:  D_t = D_{t-1} a_t - dtau_t/(2 mu) (J_{t-1} a_t + J_t)
+//     up:    U_t = U_{t+1} a_t + s_t dtau_t/(2 mu) (J_t + J_{t+1} a_t)      (s_t = 0 on carry gaps)
+// which is evaluated here as a chunked scan in three launches:
+//   1. sweep_local   every (scenario, chunk, mu column) runs its chunk from a zero carry; because the
+//                    products of a_t telescope to exp((tau_t - tau_start)/mu) the chunk aggregate is
+//                    just the last local value.
+//   2. sweep_carry   one CTA per scenario chains the chunk carries (down), finishes the surface row
+//                    (mu->0 columns + extrapolation), applies the specular/Lambert coupling, chains the
+//                    up carries and re-seeds them from the *blended* boundary rows.
+//   3. sweep_finalize one CTA per (scenario, layer) adds carry*exp(...), evaluates the windowed /
+//                    Taylor columns (SOS_Aer_In_limit.py:70-109), the polynomial extrapolation
+//                    (:113-141, a fixed linear map W), the find-first second-difference blend
+//                    (SOS_Aer_I1_In.py:101-108), accumulates I += I_n (SOS_Aer_main_specular.py:454-456)
+//                    and reduces the convergence ratios of :309.
+#pragma once
+#include "common.cuh"
+
+namespace sossweep {
+
+constexpr int LOCAL_THREADS = 128;
+constexpr int ROW_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------
+// 1. chunk-local recurrences
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LOCAL_THREADS)
+sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
+                   double* __restrict__ aggD, double* __restrict__ aggU) {
+  const int s = blockIdx.z;
+  if (!g.state[s].active) return;
+  const int c = blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= g.N) return;
+  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
+  const int L = g.L, M = g.M, ld = g.ld;
+  const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
+  const double* __restrict__ Js = J + static_cast<size_t>(s) * L * ld;
+  double* __restrict__ Is = In + static_cast<size_t>(s) * L * ld;
+  const double mu = g.mu[m];
+  const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
+
+  if (m < M - 1) {
+    if (fabs(mu) < SOS_MU_THRESHOLD) return;  // windowed / Taylor columns are row-local (finalize)
+    double D = 0.0;
+    int t = t0;
+    double Jp;
+    if (t == 0) {
+      Jp = Js[m];
+      Is[m] = 0.0;  // trapezoid over a single point
+      t = 1;
+    } else {
+      Jp = Js[static_cast<size_t>(t - 1) * ld + m];
+    }
+    double tp = tau[t - 1 < 0 ? 0 : t - 1];
+    for (; t + 3 < t1; t += 4) {
+      // four independent loads / exps in flight, one dependent DFMA chain
+      const double tc0 = tau[t], tc1 = tau[t + 1], tc2 = tau[t + 2], tc3 = tau[t + 3];
+      const double j0 = Js[static_cast<size_t>(t) * ld + m];
+      const double j1 = Js[static_cast<size_t>(t + 1) * ld + m];
+      const double j2 = Js[static_cast<size_t>(t + 2) * ld + m];
+      const double j3 = Js[static_cast<size_t>(t + 3) * ld + m];
+      const double d0 = tc0 - tp, d1 = tc1 - tc0, d2 = tc2 - tc1, d3 = tc3 - tc2;
+      const double a0 = exp(d0 / mu), a1 = exp(d1 / mu), a2 = exp(d2 / mu), a3 = exp(d3 / mu);
+      const double b0 = (d0 * 0.5) * (Jp * a0 + j0) / mu;
+      const double b1 = (d1 * 0.5) * (j0 * a1 + j1) / mu;
+      const double b2 = (d2 * 0.5) * (j1 * a2 + j2) / mu;
+      const double b3 = (d3 * 0.5) * (j2 * a3 + j3) / mu;
+      D = D * a0 - b0;
+      Is[static_cast<size_t>(t) * ld + m] = D;
+      D = D * a1 - b1;
+      Is[static_cast<size_t>(t + 1) * ld + m] = D;
+      D = D * a2 - b2;
+      Is[static_cast<size_t>(t + 2) * ld + m] = D;
+      D = D * a3 - b3;
+      Is[static_cast<size_t>(t + 3) * ld + m] = D;
+      Jp = j3;
+      tp = tc3;
+    }
+    for (; t < t1; ++t) {
+      const double tc = tau[t];
+      const double jc = Js[static_cast<size_t>(t) * ld + m];
+      const double d = tc - tp;
+      const double a = exp(d / mu);
+      D = D * a - (d * 0.5) * (Jp * a + jc) / mu;
+      Is[static_cast<size_t>(t) * ld + m] = D;
+      Jp = jc;
+      tp = tc;
+    }
+    aggD[agg] = D;
+  } else if (m > M) {
+    double U = 0.0;
+    int t = t1 - 1;
+    double Jn, tn;
+    if (t == L - 1) {
+      Jn = Js[static_cast<size_t>(t) * ld + m];
+      tn = tau[t];
+      Is[static_cast<size_t>(t) * ld + m] = 0.0;  // zero-length integral; the surface seed is a carry
+      --t;
+    } else {
+      Jn = Js[static_cast<size_t>(t + 1) * ld + m];
+      tn = tau[t + 1];
+      // chunk ends at a region boundary: the slice stops one row short of the carry row
+      // (SOS_Aer_main_specular.py:413,433) -> pure attenuation, no source on this step
+      if (g.chunk_region[c + 1] != g.chunk_region[c]) {
+        Is[static_cast<size_t>(t) * ld + m] = 0.0;
+        Jn = Js[static_cast<size_t>(t) * ld + m];
+        tn = tau[t];
+        --t;
+      }
+    }
+    for (; t - 3 >= t0; t -= 4) {
+      const double tc0 = tau[t], tc1 = tau[t - 1], tc2 = tau[t - 2], tc3 = tau[t - 3];
+      const double j0 = Js[static_cast<size_t>(t) * ld + m];
+      const double j1 = Js[static_cast<size_t>(t - 1) * ld + m];
+      const double j2 = Js[static_cast<size_t>(t - 2) * ld + m];
+      const double j3 = Js[static_cast<size_t>(t - 3) * ld + m];
+      const double d0 = tn - tc0, d1 = tc0 - tc1, d2 = tc1 - tc2, d3 = tc2 - tc3;
+      const double a0 = exp(-d0 / mu), a1 = exp(-d1 / mu), a2 = exp(-d2 / mu), a3 = exp(-d3 / mu);
+      const double b0 = (d0 * 0.5) * (j0 + Jn * a0) / mu;
+      const double b1 = (d1 * 0.5) * (j1 + j0 * a1) / mu;
+      const double b2 = (d2 * 0.5) * (j2 + j1 * a2) / mu;
+      const double b3 = (d3 * 0.5) * (j3 + j2 * a3) / mu;
+      U = U * a0 + b0;
+      Is[static_cast<size_t>(t) * ld + m] = U;
+      U = U * a1 + b1;
+      Is[static_cast<size_t>(t - 1) * ld + m] = U;
+      U = U * a2 + b2;
+      Is[static_cast<size_t>(t - 2) * ld + m] = U;
+      U = U * a3 + b3;
+      Is[static_cast<size_t>(t - 3) * ld + m] = U;
+      Jn = j3;
+      tn = tc3;
+    }
+    for (; t >= t0; --t) {
+      const double tc = tau[t];
+      const double jc = Js[static_cast<size_t>(t) * ld + m];
+      const double d = tn - tc;
+      const double a = exp(-d / mu);
+      U = U * a + (d * 0.5) * (jc + Jn * a) / mu;
+      Is[static_cast<size_t>(t) * ld + m] = U;
+      Jn = jc;
+      tn = tc;
+    }
+    aggU[agg] = U;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// row-level helpers shared by sweep_carry and sweep_finalize (one CTA works on one row in smem)
+// ------------------------------------------------------------------------------------------
+
+// |mu| < MU_THRESHOLD downward column m at layer t (improved_asymptotic_downward_radiance,
+// SOS_Aer_In_limit.py:70-109).  One warp per call; every lane returns the value.
+__device__ __forceinline__ double asymptotic_column(const GridDev& g, const double* __restrict__ Js,
+                                                    const double* __restrict__ tau, int t, int r0, int m) {
+  const int lane = threadIdx.x & 31;
+  const int ld = g.ld;
+  const double mu = g.mu[m];
+  const double jt = Js[static_cast<size_t>(t) * ld + m];
+  if (fabs(mu) < SOS_MU_VERY_SMALL) {  // Taylor: -J + mu dJ/dtau (:79-93)
+    double slope = 0.0;
+    if (t > r0) slope = (jt - Js[static_cast<size_t>(t - 1) * ld + m]) / (tau[t] - tau[t - 1]);
+    return -jt + mu * slope;
+  }
+  // windowed trapezoid over tau' >= tau_t - 5|mu| inside the region slice (:96-107)
+  const double tt = tau[t];
+  const double lim = tt - 5.0 * fabs(mu);
+  int lo = r0, hi = t;  // first k in [r0, t] with tau[k] >= lim (tau is non-decreasing)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (tau[mid] >= lim) hi = mid; else lo = mid + 1;
+  }
+  const int k0 = lo;
+  double sum = 0.0;
+  bool bad = false;
+  // interval k..k+1 handled by lane (k-k0)%32; fixed order -> deterministic
+  for (int k = k0 + lane; k < t; k += 32) {
+    const double f0 = Js[static_cast<size_t>(k) * ld + m] * exp((tt - tau[k]) / mu);
+    const double f1 = Js[static_cast<size_t>(k + 1) * ld + m] * exp((tt - tau[k + 1]) / mu);
+    bad |= !isfinite(f0) || !isfinite(f1);
+    sum += (tau[k + 1] - tau[k]) * (f1 + f0) * 0.5;
+  }
+  if (t == k0) bad |= !isfinite(jt);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  bad = __any_sync(0xffffffffu, bad);
+  if (bad) return -jt;  // (:104-105)
+  return -sum / mu;
+}
+
+// Complete the downward half of a row held in smem `row[0..M-1]`:
+// windowed/Taylor columns that survive the extrapolation, then the extrapolation itself.
+// Must be called by all threads of the CTA; contains __syncthreads.
+__device__ __forceinline__ void finish_down_row(const GridDev& g, double* row, const double* __restrict__ Js,
+                                                const double* __restrict__ tau, int t, int region, int idx_width,
+                                                int wclass) {
+  const int M = g.M;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int r0 = g.rstart[region];
+  // columns first_small .. M-2 are non-standard; those >= M - idx are overwritten below -> skip them
+  const int hi = min(M - 1, M - idx_width);
+  for (int m = g.first_small + warp; m < hi; m += nwarps) {
+    const double v = asymptotic_column(g, Js, tau, t, r0, m);
+    if (lane == 0) row[m] = v;
+  }
+  __syncthreads();
+  if (idx_width > 0) {
+    // sources (columns < M - idx) and targets (columns >= M - idx) never overlap
+    const int ns = g.wns[wclass];
+    const int src0 = (idx_width < 2) ? (M - idx_width - 2) : (M - idx_width - ns);
+    const double* __restrict__ W = g.W + g.woff[wclass];
+    for (int i = threadIdx.x; i < idx_width; i += blockDim.x) {
+      double v = 0.0;
+      for (int j = 0; j < ns; ++j) v += W[i * ns + j] * row[src0 + j];
+      row[M - 1 - i] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// Blend of the upward half towards mu = 0+ (SOS_Aer_I1_In.py:101-108).  row[M] must already hold J[t,M].
+// `found` is a shared int.  All threads of the CTA must call; returns false on search overrun (Q11).
+__device__ __forceinline__ bool blend_up_row(const GridDev& g, double* row, int* found) {
+  const int M = g.M, N = g.N;
+  if (threadIdx.x == 0) *found = 0x7fffffff;
+  __syncthreads();
+  for (int base = M + 1; base + 2 <= N - 1; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    if (i + 2 <= N - 1) {
+      const double d = fabs((row[i] - row[i + 1]) - (row[i + 1] - row[i + 2]));
+      if (!(d > SOS_BLEND_THRESHOLD)) atomicMin(found, i);
+    }
+    __syncthreads();
+    const int f = *found;
+    __syncthreads();
+    if (f != 0x7fffffff) break;
+  }
+  const int f = *found;
+  if (f == 0x7fffffff) return false;
+  const int istar = f + 1;
+  const double v0 = row[M], v1 = row[istar], mus = g.mu[istar];
+  __syncthreads();
+  for (int m = M + 1 + threadIdx.x; m < istar; m += blockDim.x) {
+    const double w = g.mu[m] / mus;
+    row[m] = (1.0 - w) * v0 + w * v1;
+  }
+  __syncthreads();
+  return true;
+}
+
+__device__ __forceinline__ int width_class(const GridDev& g, int idx_width) {
+  // widths are one of the four classes of sos_extrap_layout (or 0)
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (g.widx[k] == idx_width) c = k;
+  return c;
+}
+
+// deterministic block sum (blockDim.x multiple of 32, <= 1024); result valid in all threads
+__device__ __forceinline__ double block_sum(double v, double* scratch /*[32]*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double tot = 0.0;
+  for (int w = 0; w < nwarps; ++w) tot += scratch[w];
+  __syncthreads();
+  return tot;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. carry chain (one CTA per scenario)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* __restrict__ aggD,
+                   const double* __restrict__ aggU, double* __restrict__ carryD, double* __restrict__ carryU) {
+  extern __shared__ double sm_row[];  // [N] + scratch[32]
+  __shared__ int found;
+  const int s = blockIdx.x;
+  if (!g.state[s].active) return;
+  const int L = g.L, M = g.M, N = g.N, ld = g.ld, nch = g.nchunks;
+  const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
+  const double* __restrict__ Js = J + static_cast<size_t>(s) * L * ld;
+  const sos_scenario sc = g.scen[s];
+  double* row = sm_row;
+  double* scratch = sm_row + N;
+  const size_t base = static_cast<size_t>(s) * nch * N;
+
+  // ---- down: chain the standard columns through the chunks ----
+  for (int m = threadIdx.x; m < M - 1; m += blockDim.x) {
+    const double mu = g.mu[m];
+    double cd = 0.0;
+    if (fabs(mu) >= SOS_MU_THRESHOLD) {
+      for (int c = 0; c < nch; ++c) {
+        carryD[base + static_cast<size_t>(c) * N + m] = cd;
+        const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
+        const double a = (t0 > 0) ? aggD[base + static_cast<size_t>(c) * N + m] + cd * exp((tau[t1 - 1] - tau[t0 - 1]) / mu)
+                                  : aggD[base + static_cast<size_t>(c) * N + m];
+        cd = a;
+      }
+    }
+    row[m] = cd;  // true D at the surface row for standard columns
+  }
+  if (threadIdx.x == 0) row[M - 1] = 0.0;
+  __syncthreads();
+
+  // ---- surface row: finish the downward half, then couple ----
+  const int last_region = g.nreg - 1;
+  if (g.surface != SOS_SURFACE_NONE) {
+    const int idxw = sc.extrap_width[last_region];
+    finish_down_row(g, row, Js, tau, L - 1, last_region, idxw, width_class(g, idxw));
+  }
+  double lambert = 0.0;
+  if (g.surface == SOS_SURFACE_LAMBERT) {
+    // -2 rho trapz(I[L-1,c] mu[c], mu[c]) over c = M-2 .. 0 (descending abscissa, column M-1 excluded)
+    double part = 0.0;
+    for (int j = threadIdx.x; j < M - 2; j += blockDim.x) {
+      const int c0 = M - 2 - j, c1 = c0 - 1;
+      part += (g.mu[c1] - g.mu[c0]) * (row[c1] * g.mu[c1] + row[c0] * g.mu[c0]) * 0.5;
+    }
+    lambert = -2.0 * sc.grd_alb * block_sum(part, scratch);
+  }
+  // seeds into the upper half of the row buffer
+  for (int m = M + 1 + threadIdx.x; m < N; m += blockDim.x) {
+    double seed = 0.0;
+    if (g.surface == SOS_SURFACE_SPECULAR) seed = sc.grd_alb * row[N - 1 - m];
+    else if (g.surface == SOS_SURFACE_LAMBERT) seed = lambert;
+    row[m] = seed;
+  }
+  __syncthreads();
+
+  // ---- up: chain from the surface, re-seeding from blended rows at region boundaries ----
+  for (int c = nch - 1; c >= 0; --c) {
+    const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
+    const double tref = tau[(t1 == L) ? L - 1 : t1];
+    for (int m = M + 1 + threadIdx.x; m < N; m += blockDim.x) {
+      const double cu = row[m];
+      carryU[base + static_cast<size_t>(c) * N + m] = cu;
+      row[m] = aggU[base + static_cast<size_t>(c) * N + m] + cu * exp(-(tref - tau[t0]) / g.mu[m]);  // raw U at row t0
+    }
+    if (c > 0 && g.chunk_region[c - 1] != g.chunk_region[c]) {
+      // row t0 is the carry row of the region above and is read after its blend (A.7)
+      if (threadIdx.x == 0) row[M] = Js[static_cast<size_t>(t0) * ld + M];
+      __syncthreads();
+      if (!blend_up_row(g, row, &found) && threadIdx.x == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. finalize rows
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
+                      const double* __restrict__ carryD, const double* __restrict__ carryU,
+                      double* __restrict__ I, double* __restrict__ saved) {
+  extern __shared__ double sm_row[];  // [N] + scratch[32]
+  __shared__ int found;
+  const int s = blockIdx.y, t = blockIdx.x;
+  if (!g.state[s].active) return;
+  const int L = g.L, M = g.M, N = g.N, ld = g.ld, nch = g.nchunks;
+  const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
+  const double* __restrict__ Js = J + static_cast<size_t>(s) * L * ld;
+  double* __restrict__ Is = In + static_cast<size_t>(s) * L * ld;
+  const sos_scenario sc = g.scen[s];
+  double* row = sm_row;
+  double* scratch = sm_row + N;
+  const int c = g.row_chunk[t];
+  const int region = g.chunk_region[c];
+  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
+  const size_t cbase = (static_cast<size_t>(s) * nch + c) * N;
+  const double tt = tau[t];
+  const double tdn = (t0 > 0) ? tau[t0 - 1] : 0.0;
+  const double tup = tau[(t1 == L) ? L - 1 : t1];
+  const size_t roff = static_cast<size_t>(t) * ld;
+
+  for (int m = threadIdx.x; m < N; m += blockDim.x) {
+    const double mu = g.mu[m];
+    double v = 0.0;
+    if (m < M - 1) {
+      if (fabs(mu) >= SOS_MU_THRESHOLD) {
+        v = Is[roff + m];
+        if (t0 > 0) v += carryD[cbase + m] * exp((tt - tdn) / mu);
+      }
+    } else if (m > M) {
+      v = Is[roff + m] + carryU[cbase + m] * exp(-(tup - tt) / mu);
+    } else if (m == M) {
+      v = Js[roff + M];  // I_n[t, mu=0+] = J[t, mu=0+]  (SOS_Aer_I1_In.py:100)
+    }
+    row[m] = v;
+  }
+  __syncthreads();
+
+  const int idxw = sc.extrap_width[region];
+  finish_down_row(g, row, Js, tau, t, region, idxw, width_class(g, idxw));
+  if (!blend_up_row(g, row, &found) && threadIdx.x == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
+
+  // ---- write I_n, accumulate, convergence ratios (SOS_Aer_main_specular.py:309,454-456) ----
+  const bool toa = (t == 0), surf = (t == L - 1);
+  double rmax = -INFINITY;
+  bool nonfinite = false;
+  double* __restrict__ Iacc = I ? I + static_cast<size_t>(s) * L * ld : nullptr;
+  double* __restrict__ sv = saved ? saved + static_cast<size_t>(s) * L * ld : nullptr;
+  for (int m = threadIdx.x; m < N; m += blockDim.x) {
+    const double v = row[m];
+    Is[roff + m] = v;
+    if (sv) sv[roff + m] = v;
+    if (Iacc) {
+      const double tot = Iacc[roff + m] + v;
+      Iacc[roff + m] = tot;
+      if ((toa && m >= M) || (surf && m < M)) {
+        const double r = v / tot;
+        if (isnan(r)) nonfinite = true; else rmax = fmax(rmax, r);
+      }
+    }
+  }
+  if (Iacc && (toa || surf)) {
+    // block max
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    nonfinite = __any_sync(0xffffffffu, nonfinite);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = nonfinite ? NAN : rmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = -INFINITY;
+      bool nf = false;
+      for (int w = 0; w < nwarps; ++w) {
+        if (isnan(scratch[w])) nf = true; else r = fmax(r, scratch[w]);
+      }
+      // a row can be both TOA and surface only if L == 1; not supported
+      if (toa) g.state[s].ratio_toa = r;
+      if (surf) g.state[s].ratio_surf = r;
+      if (nf || isinf(r)) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// convergence bookkeeping
+// ------------------------------------------------------------------------------------------
+__global__ void converge_kernel(const GridDev g, int order) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int s = threadIdx.x; s < g.S; s += blockDim.x) {
+    ScenState& st = g.state[s];
+    if (st.active) {
+      st.n_orders = order;
+      const double r = fmax(st.ratio_toa, st.ratio_surf);
+      if (!(r >= g.scen[s].threshold)) st.active = 0; else ++mine;
+    }
+  }
+  atomicAdd(&cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) *g.n_active = cnt;
+}
+
+// ratios with I_n := 1 (the reference initialises In = ones before the loop, :306-309)
+__global__ void reset_kernel(const GridDev g, const double* __restrict__ I1) {
+  const int s = blockIdx.x;
+  __shared__ double sc[32];
+  const int L = g.L, M = g.M, N = g.N, ld = g.ld;
+  const double* __restrict__ I = I1 + static_cast<size_t>(s) * L * ld;
+  double r0 = -INFINITY, r1 = -INFINITY;
+  for (int m = threadIdx.x; m < N; m += blockDim.x) {
+    if (m >= M) { const double r = 1.0 / I[m]; if (!isnan(r)) r0 = fmax(r0, r); }
+    else { const double r = 1.0 / I[static_cast<size_t>(L - 1) * ld + m]; if (!isnan(r)) r1 = fmax(r1, r); }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r0 = fmax(r0, __shfl_xor_sync(0xffffffffu, r0, o));
+    r1 = fmax(r1, __shfl_xor_sync(0xffffffffu, r1, o));
+  }
+  if (lane == 0) sc[warp] = r0;
+  __syncthreads();
+  if (threadIdx.x == 0) { double r = -INFINITY; for (int w = 0; w < nwarps; ++w) r = fmax(r, sc[w]); g.state[s].ratio_toa = r; }
+  __syncthreads();
+  if (lane == 0) sc[warp] = r1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = -INFINITY; for (int w = 0; w < nwarps; ++w) r = fmax(r, sc[w]);
+    ScenState& st = g.state[s];
+    st.ratio_surf = r;
+    st.n_orders = 1;
+    st.status = 0;
+    st.active = (fmax(st.ratio_toa, r) >= g.scen[s].threshold) ? 1 : 0;
+  }
+}
+
+__global__ void count_active_kernel(const GridDev g) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int s = threadIdx.x; s < g.S; s += blockDim.x) mine += g.state[s].active ? 1 : 0;
+  atomicAdd(&cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) *g.n_active = cnt;
+}
+
+}  // namespace sossweep
