@@ -1,0 +1,25 @@
+"""sos-radiative-transfer_b200 -- B200-native Successive-Orders-of-Scattering engine.
+
+Drop-in for the SOS_AER hot path of Guillaume-SOULIER/SOS-Radiative-Transfer: the reference's
+I1_NumInt / Jn_NumInt / In_NumInt signatures and SOS_Aer_main_specular / SOS_Aer_main_lambertian
+drivers, NumPy arrays in and out, computed by hand-written sm_100a CUDA kernels behind a C ABI
+(include/sos_b200.h).  There is no CPU fallback.
+
+The directory name is not a Python identifier; import it as `import sos_b200` (alias module at
+the repository root) or with importlib.import_module("sos-radiative-transfer_b200").
+"""
+from . import _lib
+from ._lib import SosError
+from .grid import mu_grid, tau_profile, extrapolation_width, aerosol_rows
+from .phase import phase_matrices
+from .engine import SosEngine, ScenarioCoefficients, SolveResult
+from .api import I1_NumInt, Jn_NumInt, In_NumInt, mu_approx_In, clear_cache
+from .drivers import (Scenario, DriverResult, BatchSolver, solve_scenarios, SOS_Aer_main_specular,
+                      SOS_Aer_main_lambertian, SOS_Aer_radiative_forcing, EVA, WILDFIRE)
+
+__all__ = [
+    "SosError", "mu_grid", "tau_profile", "extrapolation_width", "aerosol_rows", "phase_matrices",
+    "SosEngine", "ScenarioCoefficients", "SolveResult", "I1_NumInt", "Jn_NumInt", "In_NumInt",
+    "mu_approx_In", "clear_cache", "Scenario", "DriverResult", "BatchSolver", "solve_scenarios",
+    "SOS_Aer_main_specular", "SOS_Aer_main_lambertian", "SOS_Aer_radiative_forcing", "EVA", "WILDFIRE",
+]

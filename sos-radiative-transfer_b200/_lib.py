@@ -1,0 +1,117 @@
+"""ctypes binding of libsos_b200.so (the C ABI declared in include/sos_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, the
+package raises.  Build the library with `python -c "import __graft_entry__ as g; g.build()"`
+(or `make -C sos-radiative-transfer_b200/csrc`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsos_b200.so")
+
+
+class SosError(RuntimeError):
+    pass
+
+
+class sos_grid(C.Structure):
+    _fields_ = [
+        ("nb_layers", C.c_int),
+        ("nb_angles", C.c_int),
+        ("n_scenarios", C.c_int),
+        ("n_regions", C.c_int),
+        ("region_start", C.c_int * 4),
+        ("surface", C.c_int),
+        ("ld", C.c_int),
+        ("chunk_rows", C.c_int),
+    ]
+
+
+class sos_scenario(C.Structure):
+    _fields_ = [
+        ("mu0", C.c_double),
+        ("grd_alb", C.c_double),
+        ("tauStar_tot", C.c_double),
+        ("coef_atm", C.c_double),
+        ("coef_mix_atm", C.c_double),
+        ("coef_mix_aer", C.c_double),
+        ("threshold", C.c_double),
+        ("phase_atm", C.c_int),
+        ("phase_aer", C.c_int),
+        ("extrap_width", C.c_int * 3),
+        ("reserved", C.c_int),
+    ]
+
+
+class sos_result(C.Structure):
+    _fields_ = [
+        ("ratio_toa", C.c_double),
+        ("ratio_surf", C.c_double),
+        ("n_orders", C.c_int),
+        ("active", C.c_int),
+        ("status", C.c_uint),
+        ("reserved", C.c_int),
+    ]
+
+
+SURFACE_NONE, SURFACE_SPECULAR, SURFACE_LAMBERT = 0, 1, 2
+STATUS_BLEND_OVERRUN, STATUS_NONFINITE = 1, 2
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol of include/sos_b200.h
+SIGNATURES = {
+    "sos_abi_version": (C.c_int, []),
+    "sos_strerror": (C.c_char_p, [C.c_int]),
+    "sos_last_cuda_error": (C.c_char_p, []),
+    "sos_plan_create": (C.c_int, [C.POINTER(_vp), C.POINTER(sos_grid), _vp, _vp, C.POINTER(sos_scenario), _vp, C.c_int]),
+    "sos_plan_destroy": (C.c_int, [_vp]),
+    "sos_extrap_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sos_build_contraction": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
+    "sos_plan_set_phase": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int]),
+    "sos_first_order": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "sos_source": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "sos_sweeps": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "sos_converge": (C.c_int, [_vp, C.c_int, _vp]),
+    "sos_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(sos_result), _vp]),
+    "sos_get_results": (C.c_int, [_vp, C.POINTER(sos_result), _vp]),
+    "sos_reset": (C.c_int, [_vp, _vp, _vp]),
+    "sos_quadratures": (C.c_int, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sos_launch_count": (C.c_longlong, [_vp]),
+    "sos_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libsos_b200.so (once) and attach the prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise SosError(
+            f"{LIB_PATH} not found: the CUDA library has not been built "
+            "(run __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sos_abi_version() != 1:
+        raise SosError("libsos_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str = ""):
+    if code == 0:
+        return
+    lib = load()
+    msg = lib.sos_strerror(code).decode()
+    extra = lib.sos_last_cuda_error().decode()
+    raise SosError(f"{what or 'libsos_b200'}: {msg} ({code})" + (f": {extra}" if extra and code == -2 else ""))

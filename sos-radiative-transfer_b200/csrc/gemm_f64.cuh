@@ -78,7 +78,12 @@ struct Cfg {
   static constexpr int BM = 32 * WM;
   static constexpr int BN = 64 * WN;
   static constexpr int CONSUMER_WARPS = WM * WN;
-  static constexpr int THREADS = 32 * (CONSUMER_WARPS + 1);
+  // the producer gets a whole warpgroup (4 warps, one working lane) so that setmaxnreg can move its
+  // registers to the consumer warpgroups (register allocation is per warpgroup)
+  static constexpr int THREADS = 32 * (CONSUMER_WARPS + 4);
+  static constexpr bool REBALANCE = (THREADS > 256);
+  static constexpr int REGS_PRODUCER = 40;
+  static constexpr int REGS_CONSUMER = 232;
   static constexpr int A_BYTES = BM * BK * 8;   // I tile
   static constexpr int B_BYTES = BK * BN * 8;   // A tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -110,9 +115,10 @@ jn_gemm_kernel(const __grid_constant__ GemmParams p) {
   const int ksteps = (p.N + BK - 1) / BK;
   const int n_tiles = p.n_row_tiles * p.n_col_tiles;
 
-  if (warp == C::CONSUMER_WARPS) {
+  if (warp >= C::CONSUMER_WARPS) {
     // ===================== TMA producer (one elected lane) =====================
-    if (lane == 0) {
+    if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_PRODUCER));
+    if (warp == C::CONSUMER_WARPS && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -139,6 +145,7 @@ jn_gemm_kernel(const __grid_constant__ GemmParams p) {
   }
 
   // ===================== consumers: DFMA micro-kernels =====================
+  if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_CONSUMER));
   const int warp_m = warp / WN;
   const int warp_n = warp - warp_m * WN;
   const int ty = lane >> 3;  // 0..3

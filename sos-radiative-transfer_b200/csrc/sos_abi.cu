@@ -1,0 +1,642 @@
+// libsos_b200: C ABI over the sm_100a kernels (see include/sos_b200.h for the contract).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "first_order.cuh"
+#include "gemm_f64.cuh"
+#include "quadrature.cuh"
+#include "sweep.cuh"
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+
+#define SOS_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      g_last_cuda_error = std::string(#call) + ": " + cudaGetErrorString(_e);                   \
+      return SOS_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2D row-major double tensor [rows][cols] with row stride ld (elements)
+int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
+              uint32_t box_rows, CUtensorMapSwizzle swz) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    g_last_cuda_error = "cuTensorMapEncodeTiled entry point not available";
+    return SOS_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(double)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
+    return SOS_ERR_CUDA;
+  }
+  return SOS_OK;
+}
+
+}  // namespace
+
+struct sos_plan {
+  sos_grid grid;
+  GridDev dev;
+  int N;
+  int n_sms;
+  long long launches;
+  // device allocations
+  std::vector<void*> allocs;
+  double* d_aggD = nullptr;
+  double* d_aggU = nullptr;
+  double* d_carryD = nullptr;
+  double* d_carryU = nullptr;
+  double* d_C = nullptr;     // [S][2][N] first-order coefficients
+  double* d_sums = nullptr;  // [S][L][3]
+  double* d_z = nullptr;     // [L]
+  int* h_poll = nullptr;     // pinned
+  std::vector<sos_scenario> scen_h;
+  std::vector<int> chunk_start_h;
+  // GEMM
+  int gemm_bm = 0;  // rows per tile of the chosen config
+  std::vector<GemmTile> tiles_h;
+  GemmTile* d_tiles = nullptr;
+  const double* phase_ptr[SOS_MAX_PHASE];
+  int n_phase = 0;
+  int lda = 0;
+  sosgemm::GemmParams gp;
+  const double* gp_I = nullptr;  // operand the I tensor map was encoded for
+  std::map<const void*, CUtensorMap> map_cache;
+  bool maps_A_ready = false;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(sos_plan* p, T** out, size_t count) {
+  void* ptr = nullptr;
+  cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    g_last_cuda_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return SOS_ERR_NOMEM;
+  }
+  p->allocs.push_back(ptr);
+  *out = static_cast<T*>(ptr);
+  return SOS_OK;
+}
+
+template <typename T>
+int dev_upload(sos_plan* p, const T** out, const T* host, size_t count) {
+  T* d = nullptr;
+  int r = dev_alloc(p, &d, count);
+  if (r) return r;
+  SOS_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  *out = d;
+  return SOS_OK;
+}
+
+void build_tiles(sos_plan* p, int bm) {
+  p->tiles_h.clear();
+  const sos_grid& g = p->grid;
+  for (int s = 0; s < g.n_scenarios; ++s) {
+    for (int k = 0; k < g.n_regions; ++k) {
+      const int r0 = g.region_start[k], r1 = g.region_start[k + 1];
+      for (int r = r0; r < r1; r += bm) {
+        GemmTile t;
+        t.row0 = s * g.nb_layers + r;
+        t.nrows = std::min(bm, r1 - r);
+        t.scen = s;
+        t.mix = (g.n_regions == 3 && k == 1) ? 1 : 0;
+        p->tiles_h.push_back(t);
+      }
+    }
+  }
+}
+
+int launch_check(sos_plan* p) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = std::string("kernel launch: ") + cudaGetErrorString(e);
+    return SOS_ERR_CUDA;
+  }
+  p->launches++;
+  return SOS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sos_abi_version(void) { return SOS_ABI_VERSION; }
+
+const char* sos_strerror(int err) {
+  switch (err) {
+    case SOS_OK: return "ok";
+    case SOS_ERR_INVALID: return "invalid argument";
+    case SOS_ERR_CUDA: return "CUDA call failed";
+    case SOS_ERR_NOMEM: return "out of device memory";
+    case SOS_ERR_UNSUPPORTED: return "unsupported device or configuration";
+    case SOS_ERR_STATE: return "call order violated";
+    default: return "unknown error";
+  }
+}
+
+const char* sos_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+int sos_extrap_layout(int nb_angles, int* idx, int* ns, int* off) {
+  const double f[4] = {0.005, 0.02, 0.04, 0.06};
+  int total = 0;
+  for (int c = 0; c < 4; ++c) {
+    const int w = static_cast<int>(f[c] * nb_angles);
+    idx[c] = w;
+    ns[c] = (w <= 0) ? 0 : (w < 2 ? 2 : std::min(5, w));
+    off[c] = total;
+    total += idx[c] * ns[c];
+  }
+  return total;
+}
+
+int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, const double* tau_h,
+                    const sos_scenario* scen_h, const double* extrap_W_h, int extrap_W_len) {
+  if (!out || !grid || !mu_h || !tau_h || !scen_h) return SOS_ERR_INVALID;
+  const int L = grid->nb_layers, M = grid->nb_angles, S = grid->n_scenarios, N = 2 * M;
+  if (L < 2 || M < 4 || S < 1) return SOS_ERR_INVALID;
+  if (grid->n_regions != 1 && grid->n_regions != 3) return SOS_ERR_INVALID;
+  if (grid->ld < N || (grid->ld & 1)) return SOS_ERR_INVALID;
+  if (grid->region_start[0] != 0 || grid->region_start[grid->n_regions] != L) return SOS_ERR_INVALID;
+  for (int k = 0; k < grid->n_regions; ++k)
+    if (grid->region_start[k + 1] <= grid->region_start[k]) return SOS_ERR_INVALID;
+  if (grid->n_regions == 3 && (grid->region_start[1] < 2 || grid->region_start[2] < grid->region_start[1] + 1))
+    return SOS_ERR_INVALID;
+  if (grid->surface < 0 || grid->surface > 2) return SOS_ERR_INVALID;
+
+  int dev = 0;
+  SOS_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SOS_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    g_last_cuda_error = "libsos_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                        std::to_string(prop.minor);
+    return SOS_ERR_UNSUPPORTED;
+  }
+
+  sos_plan* p = new (std::nothrow) sos_plan();
+  if (!p) return SOS_ERR_NOMEM;
+  p->grid = *grid;
+  p->N = N;
+  p->n_sms = prop.multiProcessorCount;
+  p->launches = 0;
+  p->scen_h.assign(scen_h, scen_h + S);
+  std::memset(&p->gp, 0, sizeof(p->gp));
+
+  int widx[4], wns[4], woff[4];
+  const int wlen = sos_extrap_layout(M, widx, wns, woff);
+  if (wlen != extrap_W_len || (wlen > 0 && !extrap_W_h)) { delete p; return SOS_ERR_INVALID; }
+  for (int s = 0; s < S; ++s) {
+    for (int k = 0; k < grid->n_regions; ++k) {
+      const int w = scen_h[s].extrap_width[k];
+      if (w != widx[0] && w != widx[1] && w != widx[2] && w != widx[3]) { delete p; return SOS_ERR_INVALID; }
+      if (w + 5 > M - 1) { delete p; return SOS_ERR_INVALID; }
+    }
+    if (scen_h[s].phase_atm < 0 || scen_h[s].phase_atm >= SOS_MAX_PHASE || scen_h[s].phase_aer < 0 ||
+        scen_h[s].phase_aer >= SOS_MAX_PHASE) { delete p; return SOS_ERR_INVALID; }
+  }
+
+  // ---- chunks: never straddle a region ----
+  int chunk = grid->chunk_rows;
+  if (chunk <= 0) {
+    // enough (scenario x chunk x column) threads to fill the chip, but chunks not shorter than 16 rows
+    const long long want = 4LL * p->n_sms * 2048;
+    long long c = static_cast<long long>(S) * L * N / want;
+    chunk = static_cast<int>(std::max<long long>(16, std::min<long long>(128, c)));
+  }
+  std::vector<int> cstart, cregion, rowchunk(L);
+  for (int k = 0; k < grid->n_regions; ++k) {
+    const int r0 = grid->region_start[k], r1 = grid->region_start[k + 1];
+    const int len = r1 - r0;
+    const int nck = (len + chunk - 1) / chunk;
+    for (int i = 0; i < nck; ++i) {
+      // balanced split
+      const int a = r0 + static_cast<int>(static_cast<long long>(len) * i / nck);
+      cstart.push_back(a);
+      cregion.push_back(k);
+    }
+  }
+  cstart.push_back(L);
+  const int nch = static_cast<int>(cregion.size());
+  cregion.push_back(grid->n_regions);  // sentinel: chunk_region[nchunks] differs from the last region
+  for (int c = 0; c < nch; ++c)
+    for (int t = cstart[c]; t < cstart[c + 1]; ++t) rowchunk[t] = c;
+  p->chunk_start_h = cstart;
+
+  // ---- mu-grid constants ----
+  std::vector<double> w(N, 0.0);
+  for (int k = 0; k + 1 < N; ++k) {
+    const double d = mu_h[k + 1] - mu_h[k];
+    w[k] += d / 2;
+    w[k + 1] += d / 2;
+  }
+  int first_small = M - 1;
+  for (int m = 0; m < M - 1; ++m)
+    if (std::fabs(mu_h[m]) < SOS_MU_THRESHOLD) { first_small = m; break; }
+  // the standard/small split must be a prefix/suffix split (|mu| decreasing on the downward half)
+  for (int m = first_small; m < M - 1; ++m)
+    if (!(std::fabs(mu_h[m]) < SOS_MU_THRESHOLD)) { delete p; return SOS_ERR_INVALID; }
+
+  GridDev& d = p->dev;
+  std::memset(&d, 0, sizeof(d));
+  d.L = L; d.M = M; d.N = N; d.S = S; d.ld = grid->ld;
+  d.nreg = grid->n_regions;
+  for (int k = 0; k < 4; ++k) d.rstart[k] = grid->region_start[k];
+  d.surface = grid->surface;
+  d.nchunks = nch;
+  d.first_small = first_small;
+  for (int c = 0; c < 4; ++c) { d.widx[c] = widx[c]; d.wns[c] = wns[c]; d.woff[c] = woff[c]; }
+
+  int r = SOS_OK;
+#define TRY(x) do { r = (x); if (r) { sos_plan_destroy(p); return r; } } while (0)
+  TRY(dev_upload(p, &d.chunk_start, cstart.data(), cstart.size()));
+  TRY(dev_upload(p, &d.chunk_region, cregion.data(), cregion.size()));
+  TRY(dev_upload(p, &d.row_chunk, rowchunk.data(), rowchunk.size()));
+  TRY(dev_upload(p, &d.mu, mu_h, static_cast<size_t>(N)));
+  TRY(dev_upload(p, &d.wmu, w.data(), static_cast<size_t>(N)));
+  TRY(dev_upload(p, &d.tau, tau_h, static_cast<size_t>(S) * L));
+  TRY(dev_upload(p, &d.scen, scen_h, static_cast<size_t>(S)));
+  {
+    std::vector<double> Wtmp(std::max(wlen, 1), 0.0);
+    if (wlen > 0) std::memcpy(Wtmp.data(), extrap_W_h, sizeof(double) * wlen);
+    TRY(dev_upload(p, &d.W, Wtmp.data(), Wtmp.size()));
+  }
+  {
+    std::vector<ScenState> st(S);
+    for (int s = 0; s < S; ++s) { st[s].ratio_toa = 1; st[s].ratio_surf = 1; st[s].n_orders = 1; st[s].active = 1; st[s].status = 0; st[s].pad = 0; }
+    const ScenState* tmp = nullptr;
+    TRY(dev_upload(p, &tmp, st.data(), st.size()));
+    d.state = const_cast<ScenState*>(tmp);
+  }
+  TRY(dev_alloc(p, &d.n_active, 1));
+  {
+    cudaError_t e = cudaMemcpy(d.n_active, &S, sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { sos_plan_destroy(p); return SOS_ERR_CUDA; }
+  }
+  const size_t nagg = static_cast<size_t>(S) * nch * N;
+  TRY(dev_alloc(p, &p->d_aggD, nagg));
+  TRY(dev_alloc(p, &p->d_aggU, nagg));
+  TRY(dev_alloc(p, &p->d_carryD, nagg));
+  TRY(dev_alloc(p, &p->d_carryU, nagg));
+  TRY(dev_alloc(p, &p->d_C, static_cast<size_t>(S) * 2 * N));
+  TRY(dev_alloc(p, &p->d_sums, static_cast<size_t>(S) * L * 3));
+  TRY(dev_alloc(p, &p->d_z, static_cast<size_t>(L)));
+  {
+    cudaError_t e = cudaMemset(p->d_carryD, 0, nagg * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(p->d_carryU, 0, nagg * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&p->h_poll), 4096 * sizeof(int));
+    if (e != cudaSuccess) { g_last_cuda_error = cudaGetErrorString(e); sos_plan_destroy(p); return SOS_ERR_CUDA; }
+  }
+
+  // ---- GEMM tile list: 128-row tiles when they fill the chip, else 64-row tiles ----
+  {
+    const int ncol128 = (N + 127) / 128;
+    build_tiles(p, 128);
+    if (static_cast<long long>(p->tiles_h.size()) * ncol128 >= 2LL * p->n_sms) {
+      p->gemm_bm = 128;
+    } else {
+      p->gemm_bm = 64;
+      build_tiles(p, 64);
+    }
+    const GemmTile* tmp = nullptr;
+    TRY(dev_upload(p, &tmp, p->tiles_h.data(), p->tiles_h.size()));
+    p->d_tiles = const_cast<GemmTile*>(tmp);
+  }
+#undef TRY
+  // opt in to the large dynamic shared memory of the kernels used
+  cudaFuncSetAttribute(sosgemm::jn_gemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<4, 2>::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<2, 2>::SMEM);
+  if ((N + 32) * sizeof(double) > 48 * 1024) {
+    cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
+    cudaFuncSetAttribute(sossweep::sweep_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
+  }
+  *out = p;
+  return SOS_OK;
+}
+
+int sos_plan_destroy(sos_plan* p) {
+  if (!p) return SOS_OK;
+  for (void* a : p->allocs) cudaFree(a);
+  if (p->h_poll) cudaFreeHost(p->h_poll);
+  delete p;
+  return SOS_OK;
+}
+
+long long sos_launch_count(const sos_plan* p) { return p ? p->launches : 0; }
+
+int sos_build_contraction(sos_plan* p, const double* P_d, int ldp, double* A_d, int lda, void* stream) {
+  if (!p || !P_d || !A_d || ldp < p->N || lda < p->N) return SOS_ERR_INVALID;
+  const int N = p->N;
+  dim3 grid((N + 31) / 32, (N + 31) / 32);
+  sosquad::build_contraction_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P_d, ldp, A_d, lda, N, p->dev.wmu);
+  return launch_check(p);
+}
+
+int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
+  if (!p || !A_d || n < 1 || n > SOS_MAX_PHASE || lda < p->N || (lda & 1)) return SOS_ERR_INVALID;
+  for (const sos_scenario& sc : p->scen_h)
+    if (sc.phase_atm >= n || sc.phase_aer >= n) return SOS_ERR_INVALID;
+  const int bn = 128;
+  for (int i = 0; i < n; ++i) {
+    if (!A_d[i] || (reinterpret_cast<uintptr_t>(A_d[i]) & 15)) return SOS_ERR_INVALID;
+    p->phase_ptr[i] = A_d[i];
+    int r = encode_2d(&p->gp.map_A[i], A_d[i], p->N, p->N, lda, bn, sosgemm::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r) return r;
+  }
+  p->n_phase = n;
+  p->lda = lda;
+  p->maps_A_ready = true;
+  return SOS_OK;
+}
+
+int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) {
+  if (!p || !C_h || !I1_d) return SOS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GridDev& g = p->dev;
+  SOS_CUDA(cudaMemcpyAsync(p->d_C, C_h, sizeof(double) * g.S * 2 * g.N, cudaMemcpyHostToDevice, st));
+  // C_h may be pageable: make sure the copy has consumed it before we return
+  SOS_CUDA(cudaStreamSynchronize(st));
+  const int rows_per_block = 32;
+  dim3 grid((g.N + 127) / 128, (g.L + rows_per_block - 1) / rows_per_block, g.S);
+  if (g.nreg == 3)
+    sosfirst::first_order_regions_kernel<<<grid, 128, 0, st>>>(g, p->d_C, I1_d, rows_per_block);
+  else
+    sosfirst::first_order_single_kernel<<<grid, 128, 0, st>>>(g, p->d_C, I1_d, rows_per_block);
+  return launch_check(p);
+}
+
+int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
+  if (!p || !In1_d || !J_d) return SOS_ERR_INVALID;
+  if (!p->maps_A_ready) return SOS_ERR_STATE;
+  if ((reinterpret_cast<uintptr_t>(In1_d) & 15) || (reinterpret_cast<uintptr_t>(J_d) & 15)) return SOS_ERR_INVALID;
+  const GridDev& g = p->dev;
+  const int bm = p->gemm_bm;
+  auto it = p->map_cache.find(In1_d);
+  if (it == p->map_cache.end()) {
+    CUtensorMap m;
+    int r = encode_2d(&m, In1_d, g.N, static_cast<uint64_t>(g.S) * g.L, g.ld, sosgemm::BK, bm, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r) return r;
+    if (p->map_cache.size() > 64) p->map_cache.clear();
+    it = p->map_cache.emplace(In1_d, m).first;
+  }
+  p->gp.map_I = it->second;
+  p->gp.tiles = p->d_tiles;
+  p->gp.n_row_tiles = static_cast<int>(p->tiles_h.size());
+  p->gp.n_col_tiles = (g.N + 127) / 128;
+  p->gp.N = g.N;
+  p->gp.ld = g.ld;
+  p->gp.J = J_d;
+  p->gp.scen = g.scen;
+  p->gp.state = g.state;
+  const int n_tiles = p->gp.n_row_tiles * p->gp.n_col_tiles;
+  const int grid = std::min(n_tiles, p->n_sms);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bm == 128)
+    sosgemm::jn_gemm_kernel<4, 2><<<grid, sosgemm::Cfg<4, 2>::THREADS, sosgemm::Cfg<4, 2>::SMEM, st>>>(p->gp);
+  else
+    sosgemm::jn_gemm_kernel<2, 2><<<grid, sosgemm::Cfg<2, 2>::THREADS, sosgemm::Cfg<2, 2>::SMEM, st>>>(p->gp);
+  return launch_check(p);
+}
+
+static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st) {
+  const GridDev& g = p->dev;
+  {
+    dim3 grid((g.N + sossweep::LOCAL_THREADS - 1) / sossweep::LOCAL_THREADS, g.nchunks, g.S);
+    sossweep::sweep_local_kernel<<<grid, sossweep::LOCAL_THREADS, 0, st>>>(g, J_d, In_d, p->d_aggD, p->d_aggU);
+    int r = launch_check(p);
+    if (r) return r;
+  }
+  const size_t smem = (g.N + 32) * sizeof(double);
+  {
+    sossweep::sweep_carry_kernel<<<g.S, sossweep::ROW_THREADS, smem, st>>>(g, J_d, p->d_aggD, p->d_aggU, p->d_carryD, p->d_carryU);
+    int r = launch_check(p);
+    if (r) return r;
+  }
+  {
+    dim3 grid(g.L, g.S);
+    sossweep::sweep_finalize_kernel<<<grid, sossweep::ROW_THREADS, smem, st>>>(g, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
+    int r = launch_check(p);
+    if (r) return r;
+  }
+  return SOS_OK;
+}
+
+int sos_sweeps(sos_plan* p, const double* J_d, double* In_d, double* I_d, void* stream) {
+  if (!p || !J_d || !In_d) return SOS_ERR_INVALID;
+  return sweeps_impl(p, J_d, In_d, I_d, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int sos_converge(sos_plan* p, int order, void* stream) {
+  if (!p) return SOS_ERR_INVALID;
+  sossweep::converge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, order);
+  return launch_check(p);
+}
+
+int sos_reset(sos_plan* p, const double* I1_d, void* stream) {
+  if (!p || !I1_d) return SOS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  sossweep::reset_kernel<<<p->dev.S, 256, 0, st>>>(p->dev, I1_d);
+  int r = launch_check(p);
+  if (r) return r;
+  sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev);
+  return launch_check(p);
+}
+
+int sos_get_results(sos_plan* p, sos_result* results_h, void* stream) {
+  if (!p || !results_h) return SOS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<ScenState> tmp(p->dev.S);
+  SOS_CUDA(cudaMemcpyAsync(tmp.data(), p->dev.state, sizeof(ScenState) * p->dev.S, cudaMemcpyDeviceToHost, st));
+  SOS_CUDA(cudaStreamSynchronize(st));
+  for (int s = 0; s < p->dev.S; ++s) {
+    results_h[s].ratio_toa = tmp[s].ratio_toa;
+    results_h[s].ratio_surf = tmp[s].ratio_surf;
+    results_h[s].n_orders = tmp[s].n_orders;
+    results_h[s].active = tmp[s].active;
+    results_h[s].status = tmp[s].status;
+    results_h[s].reserved = 0;
+  }
+  return SOS_OK;
+}
+
+int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* orders_d, int max_saved, int max_orders,
+              int poll_every, sos_result* results_h, void* stream) {
+  if (!p || !I_d || !In_d || !J_d) return SOS_ERR_INVALID;
+  if (!p->maps_A_ready) return SOS_ERR_STATE;
+  if (poll_every < 1) poll_every = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GridDev& g = p->dev;
+  int r = sos_reset(p, I_d, stream);
+  if (r) return r;
+  const size_t field = static_cast<size_t>(g.S) * g.L * g.ld;
+  // The host never blocks inside the loop: after every order the device-side "still active" counter
+  // is copied to a pinned slot; the host looks at the newest slot that has already landed.  Kernels
+  // of converged scenarios exit immediately, so the few orders enqueued past convergence cost only
+  // their launch latency.
+  const int nslots = 4096;
+  cudaEvent_t ev[8];
+  for (auto& e : ev) SOS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  volatile int* poll = p->h_poll;
+  for (int i = 0; i < nslots; ++i) poll[i] = -1;
+  int rc = SOS_OK;
+  int issued = 0;
+  bool done = false;
+  int next_check = 0;  // slot index next to be examined
+  for (int n = 2; n <= max_orders && !done; ++n) {
+    rc = sos_source(p, In_d, J_d, stream);
+    if (rc) break;
+    double* saved = (orders_d && n - 2 < max_saved) ? orders_d + static_cast<size_t>(n - 2) * field : nullptr;
+    rc = sweeps_impl(p, J_d, In_d, I_d, saved, st);
+    if (rc) break;
+    rc = sos_converge(p, n, stream);
+    if (rc) break;
+    const int slot = issued % nslots;
+    cudaError_t e = cudaMemcpyAsync(const_cast<int*>(&poll[slot]), g.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { g_last_cuda_error = cudaGetErrorString(e); rc = SOS_ERR_CUDA; break; }
+    ++issued;
+    if (issued % poll_every == 0) {
+      // non-blocking look at the slots that have landed so far
+      while (next_check < issued && poll[next_check % nslots] >= 0) {
+        if (poll[next_check % nslots] == 0) done = true;
+        ++next_check;
+      }
+      // bound the run-ahead so a long tail of no-op orders cannot pile up
+      if (!done && issued - next_check >= 8) {
+        cudaStreamSynchronize(st);
+      }
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (rc) return rc;
+  if (results_h) return sos_get_results(p, results_h, stream);
+  return SOS_OK;
+}
+
+int sos_quadratures(sos_plan* p, const double* I_d, double direct_scale, const double* z_h, double* flux_up_d,
+                    double* flux_down_d, double* net_flux_d, double* diffusivity_d, double* heating_d, void* stream) {
+  if (!p || !I_d) return SOS_ERR_INVALID;
+  if (heating_d && (!z_h || p->dev.nreg != 3)) return SOS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GridDev& g = p->dev;
+  if (z_h) {
+    SOS_CUDA(cudaMemcpyAsync(p->d_z, z_h, sizeof(double) * g.L, cudaMemcpyHostToDevice, st));
+    SOS_CUDA(cudaStreamSynchronize(st));
+  }
+  {
+    dim3 grid(g.L, g.S);
+    sosquad::row_sums_kernel<<<grid, 256, 0, st>>>(g, I_d, p->d_sums);
+    int r = launch_check(p);
+    if (r) return r;
+  }
+  {
+    dim3 grid((g.L + 127) / 128, g.S);
+    sosquad::quadrature_outputs_kernel<<<grid, 128, 0, st>>>(g, p->d_sums, p->d_z, direct_scale, flux_up_d, flux_down_d,
+                                                            net_flux_d, diffusivity_d, heating_d);
+    return launch_check(p);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 throughput probes (roofline denominators; MEASURED_PEAKS.json has no FP64 entry)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) probe_dfma(double* out, int iters, double a, double b) {
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) probe_dmma(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-3; c[i][1] = i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+int sos_fp64_peak(int kind, int repeats, double* tflops) {
+  if (!tflops || repeats < 1) return SOS_ERR_INVALID;
+  int dev = 0;
+  SOS_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SOS_CUDA(cudaGetDeviceProperties(&prop, dev));
+  const int grid = prop.multiProcessorCount * 2, iters = 2048;
+  double* out = nullptr;
+  SOS_CUDA(cudaMalloc(&out, sizeof(double) * 256 * grid));
+  cudaEvent_t e0, e1;
+  SOS_CUDA(cudaEventCreate(&e0));
+  SOS_CUDA(cudaEventCreate(&e1));
+  double best = 0;
+  for (int r = 0; r < repeats + 2; ++r) {
+    SOS_CUDA(cudaEventRecord(e0));
+    if (kind == 0) probe_dfma<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+    else probe_dmma<<<grid, 256>>>(out, iters, 1.0000001, 1e-9);
+    SOS_CUDA(cudaEventRecord(e1));
+    SOS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    SOS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = (kind == 0) ? 2.0 * 64 * iters * 256.0 * grid : 512.0 * 32 * iters * 8.0 * grid;
+    if (r >= 2) best = std::max(best, fl / ms * 1e-9);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return SOS_OK;
+}
+
+}  // extern "C"

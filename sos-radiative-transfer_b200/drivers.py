@@ -1,0 +1,255 @@
+"""Three-region drivers: SOS_Aer_main_specular / SOS_Aer_main_lambertian / SOS_Aer_radiative_forcing.
+
+The reference drivers are zero-argument scripts whose parameters are literals inside SOS_Aer()
+and whose results are local variables (SOS_Aer_main_specular.py:19-94,478).  Here the same
+literals are keyword defaults of `Scenario`, the solve runs on the GPU through libsos_b200 and
+the arrays the reference only plots are returned.  Many scenarios that share the grid (layers,
+angles, aerosol rows, surface kind) are solved as ONE batch: their fields are stacked along
+rows, so the source contraction of every order is a single tall FP64 GEMM.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, replace
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import grid as G
+from . import phase as PH
+from .engine import ScenarioCoefficients, SosEngine
+
+PhaseSpec = Union[Tuple[str, float], Tuple[np.ndarray, np.ndarray]]
+
+
+@dataclass
+class Scenario:
+    """Parameters of SOS_Aer() with the shipped literals as defaults (SOS_Aer_main_specular.py:23-94)."""
+    mu0: float = 0.5
+    z0: float = 120.0
+    z_up: float = 25.0
+    z_down: float = 17.0
+    nb_layers: int = 800
+    tauStar_atm: float = 0.104
+    tauStar_aer: float = 0.120
+    grd_alb: float = 1.0
+    alb_atm: float = 1.0
+    alb_aer: float = 1.0
+    nb_angles: int = 501
+    atm_phase: PhaseSpec = ("rayleigh", 0.5)
+    # the shipped default is the log-normal Mie 'eva' aerosol, which needs miepython; pass explicit
+    # (P0, P) arrays for Mie, or an analytic stand-in such as ("hg", 0.5)
+    aer_phase: PhaseSpec = ("hg", 0.5)
+    surface: str = "specular"  # 'specular' | 'lambert' (Lambert-as-coded, SURVEY.md 8c "repair A")
+    threshold: float = 1e-4
+    max_orders: int = 10000
+
+
+# README scenarios (README.md:95-111) -- tau_atm 0.124, omega_aer 0.97, R_s 0.15
+EVA = dict(tauStar_atm=0.124, tauStar_aer=0.120, alb_aer=0.97, grd_alb=0.15, z_up=25.0, z_down=17.0)
+WILDFIRE = dict(tauStar_atm=0.124, tauStar_aer=0.0075, alb_aer=0.97, grd_alb=0.15, z_up=15.0, z_down=14.0)
+
+
+@dataclass
+class DriverResult:
+    I: np.ndarray
+    n: int
+    tau: np.ndarray
+    mu: np.ndarray
+    z_profile: np.ndarray
+    idx_up: int
+    idx_down: int
+    ratio: float
+    status: int
+    flux_up: Optional[np.ndarray] = None
+    flux_down: Optional[np.ndarray] = None
+    net_flux: Optional[np.ndarray] = None
+    diffusivity: Optional[np.ndarray] = None
+    heating_rate: Optional[np.ndarray] = None
+    I_saved: Optional[List[np.ndarray]] = None
+    toa_net_flux: Optional[float] = None
+
+
+class PhaseCache:
+    """P0/P per (family, g, M, mu0) on the host; P is independent of mu0 and shared."""
+
+    def __init__(self):
+        self._P: Dict[tuple, np.ndarray] = {}
+        self._P0: Dict[tuple, np.ndarray] = {}
+
+    def get(self, spec: PhaseSpec, M: int, mu: np.ndarray, mu0: float):
+        if isinstance(spec[0], str):
+            name, g = spec[0], float(spec[1])
+            kP, k0 = (name, g, M), (name, g, M, float(mu0))
+            if kP not in self._P or k0 not in self._P0:
+                P0, P = PH.phase_matrices(name, M, mu, mu0, g)
+                self._P.setdefault(kP, P)
+                self._P0[k0] = P0
+            return self._P0[k0], self._P[kP], kP
+        P0, P = spec
+        return np.asarray(P0, dtype=np.float64), np.asarray(P, dtype=np.float64), ("array", id(P))
+
+
+_PHASES = PhaseCache()
+
+
+def _group_key(sc: Scenario):
+    _, iu, idn = G.aerosol_rows(sc.z0, sc.z_up, sc.z_down, sc.nb_layers)
+    return (sc.nb_layers, sc.nb_angles, iu, idn, sc.surface)
+
+
+class BatchSolver:
+    """All scenarios of one group (same L, M, aerosol rows, surface) on one device."""
+
+    def __init__(self, scenarios: Sequence[Scenario], device=None, chunk_rows: int = 0, phases: Optional[PhaseCache] = None):
+        keys = {_group_key(s) for s in scenarios}
+        if len(keys) != 1:
+            raise ValueError("BatchSolver: scenarios must share nb_layers, nb_angles, aerosol rows and surface")
+        self.scenarios = list(scenarios)
+        L, M, self.idx_up, self.idx_down, surf = next(iter(keys))
+        self.L, self.M, self.N = L, M, 2 * M
+        self.mu = G.mu_grid(M)
+        phases = phases or _PHASES
+        S = len(scenarios)
+        tau = np.empty((S, L))
+        coefs = []
+        Ccoef = np.empty((S, 2, self.N))
+        mats, mat_index = [], {}
+        self.z = None
+        for i, sc in enumerate(scenarios):
+            z, _, _ = G.aerosol_rows(sc.z0, sc.z_up, sc.z_down, L)
+            self.z = z if self.z is None else self.z
+            zu, zd = (sc.z_up, sc.z_down) if sc.z_up >= sc.z_down else (sc.z_down, sc.z_up)
+            tau[i] = G.tau_profile(sc.tauStar_atm, sc.tauStar_aer, sc.z0, zu, zd, L)
+            P0a, Pa, ka = phases.get(sc.atm_phase, M, self.mu, sc.mu0)
+            P0e, Pe, ke = phases.get(sc.aer_phase, M, self.mu, sc.mu0)
+            for k, P in ((ka, Pa), (ke, Pe)):
+                if k not in mat_index:
+                    mat_index[k] = len(mats)
+                    mats.append(P)
+            # global mixing weights (SOS_Aer_main_specular.py:52-53; note dtau_atm = tauStar_atm / L, Q9)
+            dtau_aer = sc.tauStar_aer / (self.idx_down + 1 - self.idx_up)
+            dtau_atm = sc.tauStar_atm / L
+            f_atm = dtau_atm / (dtau_atm + dtau_aer)
+            f_aer = dtau_aer / (dtau_atm + dtau_aer)
+            Ccoef[i, 0] = sc.alb_atm * P0a
+            Ccoef[i, 1] = sc.alb_atm * P0a * f_atm + sc.alb_aer * P0e * f_aer
+            widths = (G.extrapolation_width(float(tau[i, self.idx_up - 1]), M),
+                      G.extrapolation_width(float(tau[i, self.idx_down]), M),
+                      G.extrapolation_width(float(tau[i, self.idx_down]), M))
+            coefs.append(ScenarioCoefficients(
+                mu0=sc.mu0, grd_alb=sc.grd_alb, tauStar_tot=sc.tauStar_atm + sc.tauStar_aer,
+                coef_atm=sc.alb_atm, coef_mix_atm=sc.alb_atm * f_atm, coef_mix_aer=sc.alb_aer * f_aer,
+                threshold=sc.threshold, phase_atm=mat_index[ka], phase_aer=mat_index[ke], extrap_width=widths))
+        self.tau = tau
+        self.Ccoef = Ccoef
+        surface = {"specular": _lib.SURFACE_SPECULAR, "lambert": _lib.SURFACE_LAMBERT}[surf]
+        self.engine = SosEngine(self.mu, tau, coefs, [0, self.idx_up, self.idx_down + 1, L], surface,
+                                device=device, chunk_rows=chunk_rows)
+        self.engine.set_phase(mats)
+        self.I1 = None
+
+    def first_order(self):
+        self.I1 = self.engine.first_order(self.Ccoef, out=self.I1)
+        return self.I1
+
+    def solve(self, keep_orders: int = 0, poll_every: int = 2, max_orders: Optional[int] = None):
+        I1 = self.first_order()
+        mo = max_orders if max_orders is not None else max(s.max_orders for s in self.scenarios)
+        return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every)
+
+    def results(self, res, quadratures=True, keep_orders=0) -> List[DriverResult]:
+        eng = self.engine
+        I = eng.to_host(res.I).reshape(eng.S, eng.L, eng.N)
+        q = q2 = None
+        if quadratures:
+            q = eng.quadratures(res.I, self.z, direct_scale=1.0)
+            q2 = eng.quadratures(res.I, None, direct_scale=1.0 / (4 * np.pi), heating=False)
+        orders = None
+        if keep_orders and res.orders is not None:
+            orders = res.orders[:, :, : eng.N].reshape(keep_orders, eng.S, eng.L, eng.N).cpu().numpy()
+        I1 = eng.to_host(self.I1).reshape(eng.S, eng.L, eng.N) if keep_orders else None
+        out = []
+        for i, sc in enumerate(self.scenarios):
+            r = DriverResult(I=I[i], n=int(res.n_orders[i]), tau=self.tau[i], mu=self.mu, z_profile=self.z,
+                             idx_up=self.idx_up, idx_down=self.idx_down,
+                             ratio=float(max(res.ratio_toa[i], res.ratio_surf[i])), status=int(res.status[i]))
+            if q is not None:
+                r.flux_up, r.flux_down, r.net_flux = q["flux_up"][i], q["flux_down"][i], q["net_flux"][i]
+                r.diffusivity, r.heating_rate = q["diffusivity"][i], q["heating_rate"][i]
+                # TOA net flux with the F0/(4 pi) direct scaling (SOS_Aer_critical_albedo.py:377-382)
+                r.toa_net_flux = float(-q2["flux_down"][i][0] - q2["flux_up"][i][0])
+            if orders is not None:
+                r.I_saved = [I1[i]] + [orders[k, i] for k in range(min(keep_orders, r.n - 1))]
+            if r.status & _lib.STATUS_BLEND_OVERRUN:
+                raise IndexError("mu->0 blend search ran off the row (reference: IndexError, "
+                                 "SOS_Aer_main_specular.py:404)")
+            out.append(r)
+        return out
+
+
+def solve_scenarios(scenarios: Sequence[Scenario], device=None, keep_orders: int = 0, quadratures: bool = True) -> List[DriverResult]:
+    """Solve any mix of scenarios; those sharing a grid are batched together."""
+    groups: Dict[tuple, List[int]] = {}
+    for i, sc in enumerate(scenarios):
+        groups.setdefault(_group_key(sc), []).append(i)
+    out: List[Optional[DriverResult]] = [None] * len(scenarios)
+    for key, idxs in groups.items():
+        bs = BatchSolver([scenarios[i] for i in idxs], device=device)
+        res = bs.solve(keep_orders=keep_orders)
+        for i, r in zip(idxs, bs.results(res, quadratures=quadratures, keep_orders=keep_orders)):
+            out[i] = r
+        bs.engine.close()
+    return out  # type: ignore
+
+
+def SOS_Aer_main_specular(keep_orders: int = 0, device=None, **params) -> DriverResult:
+    """SOS_Aer() of SOS_Aer_main_specular.py with keyword parameters; returns the arrays."""
+    sc = Scenario(**dict(params, surface="specular"))
+    return solve_scenarios([sc], device=device, keep_orders=keep_orders)[0]
+
+
+def SOS_Aer_main_lambertian(keep_orders: int = 0, device=None, **params) -> DriverResult:
+    """SOS_Aer() of SOS_Aer_main_lambertian.py (Lambert-as-coded, first order as in the specular driver)."""
+    sc = Scenario(**dict(params, surface="lambert"))
+    return solve_scenarios([sc], device=device, keep_orders=keep_orders)[0]
+
+
+def SOS_Aer_radiative_forcing(tauStar_aer, dtau_aer, tauStar_atm, dtau_atm, P_aer, P0_aer, alb_aer, P_atm, P0_atm,
+                              alb_atm, grd_alb, F0, mu, mu0, nb_angles, tau, nb_layers, idx_up, idx_down,
+                              tauStar_tot=None, baseline="reference", device=None):
+    """Drop-in for SOS_Aer_critical_albedo.py:20 (19 positional arguments).
+
+    The reference reads `tauStar_tot` from a module global (:39) -- pass it as a keyword (default:
+    tau[-1]).  Its baseline recursion (:385-389) reuses the same tau/dtau/P/omega, so the returned
+    forcing is identically 0 (Q19); baseline="reference" reproduces that, baseline="none" returns the
+    TOA net flux of this single solve (the quantity a corrected sweep needs).
+    """
+    tau = np.ascontiguousarray(tau, dtype=np.float64)
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    M, L = int(nb_angles), int(nb_layers)
+    T = float(tauStar_tot) if tauStar_tot is not None else float(tau[-1])
+    f_atm = dtau_atm / (dtau_atm + dtau_aer)
+    f_aer = dtau_aer / (dtau_atm + dtau_aer)
+    widths = (G.extrapolation_width(float(tau[idx_up - 1]), M), G.extrapolation_width(float(tau[idx_down]), M),
+              G.extrapolation_width(float(tau[idx_down]), M))
+    coef = ScenarioCoefficients(mu0=float(mu0), grd_alb=float(grd_alb), tauStar_tot=T, coef_atm=float(alb_atm),
+                                coef_mix_atm=float(alb_atm * f_atm), coef_mix_aer=float(alb_aer * f_aer),
+                                phase_atm=0, phase_aer=1, extrap_width=widths)
+    eng = SosEngine(mu, tau[None, :], [coef], [0, int(idx_up), int(idx_down) + 1, L], _lib.SURFACE_SPECULAR, device=device)
+    try:
+        eng.set_phase([P_atm, P_aer])
+        Cc = np.empty((1, 2, 2 * M))
+        Cc[0, 0] = alb_atm * np.asarray(P0_atm)
+        Cc[0, 1] = alb_atm * np.asarray(P0_atm) * f_atm + alb_aer * np.asarray(P0_aer) * f_aer
+        I1 = eng.first_order(Cc)
+        res = eng.solve(I1)
+        q = eng.quadratures(res.I, None, direct_scale=1.0 / (4 * np.pi), heating=False)
+        # the kernels use F0 = pi/mu0 (SOS_Aer_main_specular.py:105); the solve is linear in F0
+        net = float(-q["flux_down"][0][0] - q["flux_up"][0][0]) * (float(F0) * float(mu0) / np.pi)
+    finally:
+        eng.close()
+    if tauStar_aer == 0 or baseline == "none":
+        return net
+    return net - net  # the reference's recursion recomputes the identical solve (Q19)

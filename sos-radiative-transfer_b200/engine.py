@@ -1,0 +1,235 @@
+"""SosEngine: a batch of scenarios sharing one (layers x mu) grid, resident on one B200.
+
+Thin host object over the C ABI (include/sos_b200.h): it owns the torch device buffers
+(PyTorch is used for device memory and streams only), precomputes the once-per-grid tables
+(mu weights, chunking, extrapolation matrices) and exposes the per-order operators of the
+reference -- first order, source contraction, layer sweeps, accumulate/convergence -- plus the
+whole order loop and the quadratures.  No CPU fallback: every method raises if the CUDA
+library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import grid as G
+
+
+def _align(n: int, a: int) -> int:
+    return (n + a - 1) // a * a
+
+
+@dataclass
+class ScenarioCoefficients:
+    """Per-scenario scalars in the units the kernels want (see sos_scenario in sos_b200.h)."""
+    mu0: float
+    grd_alb: float
+    tauStar_tot: float
+    coef_atm: float
+    coef_mix_atm: float = 0.0
+    coef_mix_aer: float = 0.0
+    threshold: float = 1e-4
+    phase_atm: int = 0
+    phase_aer: int = 0
+    extrap_width: Sequence[int] = (0, 0, 0)
+
+
+class SolveResult:
+    """What the order loop returns: accumulated field + per-scenario bookkeeping."""
+
+    def __init__(self, I, n_orders, ratio_toa, ratio_surf, status, orders=None):
+        self.I = I
+        self.n_orders = n_orders
+        self.ratio_toa = ratio_toa
+        self.ratio_surf = ratio_surf
+        self.status = status
+        self.orders = orders
+
+
+class SosEngine:
+    def __init__(self, mu, tau, scenarios: Sequence[ScenarioCoefficients], region_start: Sequence[int],
+                 surface: int, device: Optional[torch.device] = None, chunk_rows: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SosError("no CUDA device: the SOS engine has no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        tau = np.ascontiguousarray(np.atleast_2d(tau), dtype=np.float64)
+        self.N = mu.shape[0]
+        self.M = self.N // 2
+        self.S, self.L = tau.shape
+        if len(scenarios) != self.S:
+            raise ValueError("one ScenarioCoefficients per tau row expected")
+        self.mu, self.tau = mu, tau
+        self.ld = _align(self.N, 16)  # 128-byte rows: TMA boxes of the contraction stay line-aligned
+        self.n_regions = len(region_start) - 1
+        self.region_start = list(region_start)
+        self.surface = surface
+        self.scenarios = list(scenarios)
+
+        g = _lib.sos_grid()
+        g.nb_layers, g.nb_angles, g.n_scenarios, g.n_regions = self.L, self.M, self.S, self.n_regions
+        for i in range(4):
+            g.region_start[i] = self.region_start[i] if i < len(self.region_start) else 0
+        g.surface, g.ld, g.chunk_rows = surface, self.ld, chunk_rows
+        sc = (_lib.sos_scenario * self.S)()
+        for i, s in enumerate(scenarios):
+            sc[i].mu0, sc[i].grd_alb, sc[i].tauStar_tot = s.mu0, s.grd_alb, s.tauStar_tot
+            sc[i].coef_atm, sc[i].coef_mix_atm, sc[i].coef_mix_aer = s.coef_atm, s.coef_mix_atm, s.coef_mix_aer
+            sc[i].threshold = s.threshold
+            sc[i].phase_atm, sc[i].phase_aer = s.phase_atm, s.phase_aer
+            for k in range(3):
+                sc[i].extrap_width[k] = int(s.extrap_width[k]) if k < len(s.extrap_width) else 0
+        W = np.ascontiguousarray(G.extrapolation_tables(mu, self.M), dtype=np.float64)
+        self._plan = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_plan_create(C.byref(self._plan), C.byref(g), mu.ctypes.data, tau.ctypes.data,
+                                                sc, W.ctypes.data if W.size else None, int(W.size)),
+                       "sos_plan_create")
+        self._A = []          # device contraction matrices (keep alive)
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_plan", None) is not None and self._plan.value:
+            self.lib.sos_plan_destroy(self._plan)
+            self._plan = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def new_field(self, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f((self.S * self.L, self.ld), dtype=torch.float64, device=self.device)
+
+    def _buf(self, name):
+        if name not in self._bufs:
+            self._bufs[name] = self.new_field(zero=True)
+        return self._bufs[name]
+
+    def to_field(self, arr) -> torch.Tensor:
+        """Host (S, L, N) / (L, N) array (or device tensor) -> padded device field."""
+        if isinstance(arr, torch.Tensor) and arr.is_cuda and arr.shape == (self.S * self.L, self.ld):
+            return arr
+        a = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)) if not isinstance(arr, torch.Tensor) else arr
+        a = a.reshape(self.S * self.L, self.N)
+        out = self.new_field(zero=True)
+        out[:, : self.N].copy_(a, non_blocking=False)
+        return out
+
+    def to_host(self, field: torch.Tensor) -> np.ndarray:
+        """Device field -> C-contiguous float64 (S, L, N) NumPy array (squeezed to (L, N) when S == 1)."""
+        a = field[:, : self.N].reshape(self.S, self.L, self.N).cpu().numpy()
+        a = np.ascontiguousarray(a)
+        return a[0] if self.S == 1 else a
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.sos_launch_count(self._plan))
+
+    # ------------------------------------------------------------------ phase operands
+    def set_phase(self, matrices: Sequence):
+        """Upload the phase matrices P (N, N) once and build A[k,m] = w_k/4 P[m, N-1-k] on device."""
+        self._A = []
+        lda = self.ld
+        with torch.cuda.device(self.device):
+            for P in matrices:
+                if isinstance(P, torch.Tensor):
+                    Pd = P.to(self.device, torch.float64).contiguous()
+                else:
+                    Pd = torch.as_tensor(np.ascontiguousarray(P, dtype=np.float64)).to(self.device)
+                if Pd.shape != (self.N, self.N):
+                    raise ValueError(f"phase matrix must be ({self.N}, {self.N})")
+                A = torch.zeros((self.N, lda), dtype=torch.float64, device=self.device)
+                _lib.check(self.lib.sos_build_contraction(self._plan, Pd.data_ptr(), self.N, A.data_ptr(), lda, self._stream),
+                           "sos_build_contraction")
+                self._A.append(A)
+            torch.cuda.current_stream(self.device).synchronize()  # Pd may be freed after this
+            ptrs = (C.c_void_p * len(self._A))(*[a.data_ptr() for a in self._A])
+            _lib.check(self.lib.sos_plan_set_phase(self._plan, ptrs, len(self._A), lda), "sos_plan_set_phase")
+
+    # ------------------------------------------------------------------ operators
+    def first_order(self, C_coef: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """C_coef: (S, 2, N) -- see sos_first_order in sos_b200.h."""
+        Cc = np.ascontiguousarray(C_coef, dtype=np.float64).reshape(self.S, 2, self.N)
+        out = self.new_field(zero=True) if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_first_order(self._plan, Cc.ctypes.data, out.data_ptr(), self._stream), "sos_first_order")
+        return out
+
+    def source(self, In1: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = self.new_field(zero=True) if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_source(self._plan, In1.data_ptr(), out.data_ptr(), self._stream), "sos_source")
+        return out
+
+    def sweeps(self, J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate_into: Optional[torch.Tensor] = None):
+        out = self.new_field(zero=True) if out is None else out
+        acc = accumulate_into.data_ptr() if accumulate_into is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_sweeps(self._plan, J.data_ptr(), out.data_ptr(), acc, self._stream), "sos_sweeps")
+        return out
+
+    def reset(self, I1: torch.Tensor):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_reset(self._plan, I1.data_ptr(), self._stream), "sos_reset")
+
+    def converge(self, order: int):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_converge(self._plan, int(order), self._stream), "sos_converge")
+
+    def results(self):
+        res = (_lib.sos_result * self.S)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_get_results(self._plan, res, self._stream), "sos_get_results")
+        return res
+
+    def solve(self, I1: torch.Tensor, max_orders: int = 10000, keep_orders: int = 0, poll_every: int = 1,
+              In: Optional[torch.Tensor] = None, J: Optional[torch.Tensor] = None, I: Optional[torch.Tensor] = None) -> SolveResult:
+        """The order loop of SOS_Aer() (SOS_Aer_main_specular.py:302-458) for the whole batch.
+
+        I1 is not modified.  keep_orders > 0 also returns the first `keep_orders` fields I_n (n >= 2).
+        """
+        I = self._buf("I") if I is None else I
+        In = self._buf("In") if In is None else In
+        J = self._buf("J") if J is None else J
+        I.copy_(I1)
+        In.copy_(I1)
+        orders = None
+        optr = None
+        if keep_orders > 0:
+            orders = torch.zeros((keep_orders, self.S * self.L, self.ld), dtype=torch.float64, device=self.device)
+            optr = orders.data_ptr()
+        res = (_lib.sos_result * self.S)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_solve(self._plan, I.data_ptr(), In.data_ptr(), J.data_ptr(), optr, keep_orders,
+                                          int(max_orders), int(poll_every), res, self._stream), "sos_solve")
+        n = np.array([r.n_orders for r in res])
+        return SolveResult(I, n, np.array([r.ratio_toa for r in res]), np.array([r.ratio_surf for r in res]),
+                           np.array([r.status for r in res], dtype=np.uint32), orders)
+
+    def quadratures(self, I: torch.Tensor, z: Optional[np.ndarray] = None, direct_scale: float = 1.0, heating: bool = True):
+        """flux_up, flux_down, net_flux, diffusivity, heating_rate -- each (S, L) on the host."""
+        outs = [torch.zeros((self.S, self.L), dtype=torch.float64, device=self.device) for _ in range(5)]
+        want_heat = heating and z is not None and self.n_regions == 3
+        zc = np.ascontiguousarray(z, dtype=np.float64) if z is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_quadratures(self._plan, I.data_ptr(), float(direct_scale),
+                                                zc.ctypes.data if zc is not None else None,
+                                                outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
+                                                outs[4].data_ptr() if want_heat else None, self._stream), "sos_quadratures")
+        host = [o.cpu().numpy() for o in outs]
+        return dict(flux_up=host[0], flux_down=host[1], net_flux=host[2], diffusivity=host[3],
+                    heating_rate=host[4] if want_heat else None)

@@ -1,0 +1,91 @@
+"""Azimuth-averaged phase functions P0(mu, mu0) and P(mu, mu') for the analytic / tabulated families.
+
+Input producer of the hot path.  Same quadrature as the
+reference builders -- 25 azimuth nodes on [0, pi], both half-rings, composite trapezoid, raw
+matrix symmetric, then every *column* normalised so that trapz(P[:, n], mu) = 4
+(SOS_Aer_phase_func.py:68-292) -- but evaluated as array expressions instead of the reference's
+triple Python loop (89-112 s per matrix at N = 1002 there, well under a second here).
+
+Mie / log-normal Mie (SOS_Aer_phase_func.py:299-753) need `miepython`, which the reference does
+not pin and which is not installed here; callers pass their own P0/P for those (north_star keeps
+Mie coefficients on the host).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+NB_PHI = 25  # SOS_Aer_phase_func.py:81
+
+_FWC = None
+
+
+def _fwc_table():
+    """The tabulated FWC cloud phase function (data of SOS_Aer_fwc_data.py:3,173)."""
+    global _FWC
+    if _FWC is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "fwc_table.npz")
+        d = np.load(path)
+        _FWC = (d["mu_fwc"], d["phase_func_FWC"])
+    return _FWC
+
+
+def _trapz(y, x, axis=-1):
+    y = np.asarray(y)
+    d = np.diff(x)
+    y = np.moveaxis(y, axis, -1)
+    return (d * (y[..., 1:] + y[..., :-1]) / 2.0).sum(-1)
+
+
+def _kernel(name, g):
+    if name == "rayleigh":
+        return lambda c: 0.75 * (1 + c * c)  # SOS_Aer_phase_func.py:97
+    if name == "hg":
+        return lambda c: (1 - g * g) / ((1 + g * g - 2 * g * c) ** 1.5)  # :158
+    if name == "fwc":
+        xs, ys = _fwc_table()
+
+        def interp(c):  # interpolate_fwc_phase, :202-236
+            c = np.clip(c, -1, 1)
+            i = np.searchsorted(xs, c)
+            lo = np.clip(i - 1, 0, len(xs) - 1)
+            hi = np.clip(i, 0, len(xs) - 1)
+            with np.errstate(all="ignore"):
+                w = (c - xs[lo]) / (xs[hi] - xs[lo])
+                v = ys[lo] + w * (ys[hi] - ys[lo])
+            v = np.where(i == 0, ys[0], v)
+            v = np.where(i >= len(xs), ys[-1], v)
+            return v
+        return interp
+    raise ValueError(f"unknown analytic phase function {name!r}")
+
+
+def phase_matrices(name: str, nb_angles: int, mu: np.ndarray, mu0: float, g: float = 0.5, block: int = 128):
+    """Return (P0 (N,), P (N, N)) for name in {'iso', 'rayleigh', 'hg', 'fwc'}."""
+    N = 2 * nb_angles
+    mu = np.asarray(mu, dtype=np.float64)
+    if name == "iso":
+        return np.ones(N), 2 * np.ones((N, N))  # :68-76
+    f = _kernel(name, g)
+    phi = np.linspace(0, np.pi, NB_PHI)
+    cphi = np.cos(0 - phi)
+    s = np.sqrt(1 - mu * mu)
+
+    # ---- P0(mu, mu0): :92-103 ----
+    cc = (mu * mu0)[:, None]
+    ss = (np.sqrt(1 - mu0 * mu0) * s)[:, None] * cphi[None, :]
+    P0 = _trapz(f(-(cc + ss)) + f(-(cc - ss)), phi) / (4 * np.pi)
+    P0 = P0 / _trapz(P0, mu) * 2
+
+    # ---- P(mu, mu'): :112-131, raw matrix is symmetric; normalise each column afterwards ----
+    P = np.empty((N, N))
+    for a in range(0, N, block):
+        b = min(N, a + block)
+        cmn = mu[:, None] * mu[None, a:b]                       # mu[m]*mu[n]
+        smn = (s[None, a:b] * s[:, None])                       # sqrt(1-mu[n]^2)*sqrt(1-mu[m]^2)
+        x = smn[:, :, None] * cphi[None, None, :]
+        raw = _trapz(f(-(cmn[:, :, None] + x)) + f(-(cmn[:, :, None] - x)), phi) / (2 * np.pi)
+        P[:, a:b] = raw
+    P = 4 * P / _trapz(P, mu, axis=0)[None, :]
+    return P0, P

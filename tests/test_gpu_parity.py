@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path, called through the reference-facing API / C ABI, against
+(a) golden fixtures produced by the unmodified reference and (b) the CPU oracle on the same inputs.
+
+FP64 tolerance stated by BASELINE.json north_star: 1e-10 relative on per-order radiances, fluxes
+and heating rates, same scattering order at convergence.  Metric (hard part 4):
+max|delta| / max|ref| per field, plus elementwise relative error where |ref| > 1e-6 max|ref|.
+"""
+import ast
+
+import numpy as np
+import pytest
+
+from conftest import relelem, relmax
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def sos():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import sos_b200
+    sos_b200._lib.load()  # fails loudly if the extension is missing
+    return sos_b200
+
+
+@pytest.fixture(scope="module")
+def so():
+    import sos_oracle
+    return sos_oracle
+
+
+def smooth_source(tau, mu, tauStar):
+    t, m = tau[:, None], mu[None, :]
+    return (1 + 0.5 * m + 0.3 * m * m) * np.exp(-t / 0.5) * (1 + 0.2 * np.sin(3 * t / tauStar)) + 0.01
+
+
+# ----------------------------------------------------------------------------------------------
+# single-layer drop-in functions
+# ----------------------------------------------------------------------------------------------
+def test_single_layer_vs_golden(sos, golden):
+    d = golden("single_layer.npz")
+    for ci in range(int(d["ncases"])):
+        L, M, ts, mu0, alb = d[f"c{ci}_params"]
+        L, M = int(L), int(M)
+        rows = d[f"c{ci}_rows"]
+        mu = sos.mu_grid(M)
+        tau = np.linspace(0, ts, L)
+        P0, P = sos.phase_matrices(str(d[f"c{ci}_phase"]), M, mu, mu0, 0.5)
+        I1 = sos.I1_NumInt(tau, mu, ts, mu0, P0, alb, M)
+        assert I1.shape == (L, 2 * M) and I1.dtype == np.float64 and I1.flags["C_CONTIGUOUS"]
+        assert relmax(I1[rows], d[f"c{ci}_I1"]) < TOL, ci
+        assert relelem(I1[rows], d[f"c{ci}_I1"]) < TOL, ci
+        J2 = sos.Jn_NumInt(2, I1, tau, mu, ts, mu0, P, alb, M)
+        assert relmax(J2[rows], d[f"c{ci}_J2"]) < TOL, ci
+        I2 = sos.In_NumInt(2, J2, I1, tau, mu, ts, mu0, P, alb, M, 0, 0)
+        assert relmax(I2[rows], d[f"c{ci}_I2"]) < TOL, ci
+        Is = sos.In_NumInt(2, smooth_source(tau, mu, ts), I1, tau, mu, ts, mu0, P, alb, M, 0, 0)
+        assert relmax(Is[rows], d[f"c{ci}_Is"]) < TOL, ci
+        assert tuple(d[f"c{ci}_mu12"]) == tuple(sos.mu_approx_In(mu, M))
+
+
+@pytest.mark.parametrize("L,M,ts", [(37, 64, 0.4), (130, 101, 3.0), (257, 333, 9.0), (64, 512, 30.0 * 64 / 10000)])
+def test_single_layer_vs_oracle_ragged(sos, so, L, M, ts):
+    """Ragged sizes (N not a multiple of any tile) and several tau* regimes against the oracle."""
+    mu = sos.mu_grid(M)
+    tau = np.linspace(0, ts, L) ** 1.0
+    tau[L // 2:] += 0.3 * ts / L  # a kink, as in SURVEY.md 8(d)
+    mu0, alb = 0.6, 0.93
+    P0, P = sos.phase_matrices("hg", M, mu, mu0, 0.7)
+    a = sos.I1_NumInt(tau, mu, ts, mu0, P0, alb, M)
+    b = so.I1_NumInt(tau, mu, ts, mu0, P0, alb, M)
+    assert relmax(a, b) < TOL
+    Ja = sos.Jn_NumInt(2, b, tau, mu, ts, mu0, P, alb, M)
+    Jb = b @ so.contraction_matrix(P, mu, alb)
+    assert relmax(Ja, Jb) < TOL
+    Js = smooth_source(tau, mu, ts)
+    Ia = sos.In_NumInt(2, Js, b, tau, mu, ts, mu0, P, alb, M, 0, 0)
+    Ib = so.In_NumInt(2, Js, b, tau, mu, ts, mu0, P, alb, M, method="recurrence")
+    assert relmax(Ia, Ib) < TOL
+
+
+def test_blend_overrun_raises_index_error(sos):
+    """Non-smooth input: the reference raises IndexError (SOS_Aer_I1_In.py:103); so do we."""
+    L, M, ts = 40, 64, 0.5
+    mu = sos.mu_grid(M)
+    tau = np.linspace(0, ts, L)
+    rng = np.random.default_rng(0)
+    J = rng.standard_normal((L, 2 * M)) * 10
+    with pytest.raises(IndexError):
+        sos.In_NumInt(2, J, J, tau, mu, ts, 0.5, None, 1.0, M, 0, 0)
+
+
+def test_inputs_not_mutated(sos):
+    L, M, ts = 50, 101, 0.5
+    mu = sos.mu_grid(M)
+    tau = np.linspace(0, ts, L)
+    P0, P = sos.phase_matrices("rayleigh", M, mu, 0.5)
+    I1 = sos.I1_NumInt(tau, mu, ts, 0.5, P0, 1.0, M)
+    keep = (I1.copy(), P.copy(), tau.copy(), mu.copy())
+    J = sos.Jn_NumInt(2, I1, tau, mu, ts, 0.5, P, 1.0, M)
+    Jk = J.copy()
+    sos.In_NumInt(2, J, I1, tau, mu, ts, 0.5, P, 1.0, M, 0, 0)
+    assert np.array_equal(I1, keep[0]) and np.array_equal(P, keep[1])
+    assert np.array_equal(tau, keep[2]) and np.array_equal(mu, keep[3]) and np.array_equal(J, Jk)
+
+
+# ----------------------------------------------------------------------------------------------
+# three-region drivers
+# ----------------------------------------------------------------------------------------------
+def _run_driver(sos, kind, kw, keep):
+    fn = sos.SOS_Aer_main_lambertian if kind == "lambertian" else sos.SOS_Aer_main_specular
+    return fn(keep_orders=keep, atm_phase=("rayleigh", 0.5), aer_phase=("hg", 0.5), **kw)
+
+
+@pytest.mark.parametrize("kind", ["specular", "lambertian"])
+@pytest.mark.parametrize("tag", ["thin", "thick", "mu0hit"])
+def test_small_drivers_vs_golden(sos, golden, kind, tag):
+    d = golden("drivers_small.npz")
+    key = f"{kind}_{tag}"
+    kw = ast.literal_eval(str(d[key + "_kw"]))
+    n_ref = int(d[key + "_n"])
+    r = _run_driver(sos, kind, kw, keep=n_ref)
+    assert r.n == n_ref
+    assert np.array_equal(r.tau, d[key + "_tau"])
+    assert [r.idx_up, r.idx_down] == list(d[key + "_idx"])
+    assert relmax(r.I, d[key + "_I"]) < TOL
+    for j, oid in enumerate(d[key + "_order_ids"]):
+        assert relmax(r.I_saved[oid], d[key + "_orders"][j]) < TOL, oid
+    assert relmax(r.flux_up, d[key + "_flux_up"]) < TOL
+    assert relmax(r.flux_down, d[key + "_flux_down"]) < TOL
+    assert relmax(r.net_flux, d[key + "_net_flux"]) < TOL
+    assert relmax(r.diffusivity, d[key + "_diffusivity"]) < TOL
+    # heating rate = difference of nearly equal fluxes / dz: compare against the flux scale
+    scale = np.max(np.abs(d[key + "_flux_down"])) / abs(r.z_profile[1] - r.z_profile[0]) / (1.225 * 1004)
+    assert np.max(np.abs(r.heating_rate - d[key + "_heating_rate"])) < TOL * scale
+
+
+@pytest.mark.parametrize("tag", ["eva_spec", "eva_lamb", "thin_spec", "mixed_spec", "tau2_lamb"])
+def test_n1002_drivers_vs_golden(sos, golden, tag):
+    d = golden("drivers_n1002.npz")
+    kw = ast.literal_eval(str(d[tag + "_kw"]))
+    kind = kw.pop("kind")
+    n_ref = int(d[tag + "_n"])
+    r = _run_driver(sos, kind, kw, keep=n_ref)
+    assert r.n == n_ref
+    rows = d[tag + "_rows"]
+    assert relmax(r.I[rows], d[tag + "_I_rows"]) < TOL
+    assert relmax(r.I[::10], d[tag + "_I_sub"]) < TOL
+    for j in range(n_ref):
+        assert relmax(r.I_saved[j][rows], d[tag + "_order_rows"][j]) < TOL, j
+        assert abs(np.sum(r.I_saved[j]) - d[tag + "_order_sum"][j]) < TOL * np.sum(np.abs(r.I_saved[j]))
+    assert relmax(r.flux_up, d[tag + "_flux_up"]) < TOL and relmax(r.flux_down, d[tag + "_flux_down"]) < TOL
+    assert relmax(r.net_flux, d[tag + "_net_flux"]) < TOL and relmax(r.diffusivity, d[tag + "_diffusivity"]) < TOL
+
+
+DEFAULT_RUNS = {
+    "eva_spec": ("specular", dict(tauStar_atm=0.124, grd_alb=0.15, alb_aer=0.97)),
+    "eva_lamb": ("lambertian", dict(tauStar_atm=0.124, grd_alb=0.15, alb_aer=0.97)),
+    "wildfire_lamb": ("lambertian", dict(tauStar_atm=0.124, tauStar_aer=0.0075, z_up=15, z_down=14, grd_alb=0.15, alb_aer=0.97)),
+    "shipped_spec": ("specular", {}),
+}
+
+
+@pytest.mark.parametrize("tag", list(DEFAULT_RUNS))
+def test_default_grid_vs_golden(sos, golden, tag):
+    """BASELINE configs 1-3 at the reference's 800 x 1002 grid (HG g=0.5 standing in for Mie)."""
+    d = golden(f"default_{tag}.npz")
+    kind, kw = DEFAULT_RUNS[tag]
+    n_ref = int(d["n"])
+    r = _run_driver(sos, kind, kw, keep=n_ref)
+    assert r.n == n_ref
+    assert [r.idx_up, r.idx_down] == list(d["idx"])
+    assert np.array_equal(r.tau, d["tau"])
+    rows = d["rows"]
+    assert relmax(r.I[rows], d["I_rows"]) < TOL and relelem(r.I[rows], d["I_rows"]) < 1e-9
+    assert relmax(r.I[::40], d["I_sub"]) < TOL
+    for j in range(n_ref):
+        assert relmax(r.I_saved[j][rows], d["order_rows"][j]) < TOL, j
+        assert abs(np.max(np.abs(r.I_saved[j])) - d["order_max"][j]) < TOL * d["order_max"][j]
+    assert relmax(r.flux_up, d["flux_up"]) < TOL and relmax(r.flux_down, d["flux_down"]) < TOL
+    assert relmax(r.net_flux, d["net_flux"]) < TOL and relmax(r.diffusivity, d["diffusivity"]) < TOL
+    scale = np.max(np.abs(d["flux_down"])) / abs(r.z_profile[1] - r.z_profile[0]) / (1.225 * 1004)
+    assert np.max(np.abs(r.heating_rate - d["heating_rate"])) < TOL * scale
+    if tag == "eva_spec":
+        assert abs(r.I[0, 751] - 0.24262858024159764) < 1e-12
+        assert abs(r.flux_up[0] - 0.45982557863744034) < 1e-11
+
+
+def test_thick_fwc_to_convergence(sos, golden):
+    """Config-4 stand-in on a reduced grid: 100+ orders, same order count as the reference."""
+    d = golden("thick_fwc.npz")
+    L, M, ts, mu0, alb = d["params"]
+    L, M = int(L), int(M)
+    mu = sos.mu_grid(M)
+    tau = np.linspace(0, ts, L)
+    P0, P = sos.phase_matrices("fwc", M, mu, mu0)
+    w = sos.extrapolation_width(ts, M)
+    coef = sos.ScenarioCoefficients(mu0=mu0, grd_alb=0.0, tauStar_tot=ts, coef_atm=alb, extrap_width=(w, w, w))
+    eng = sos.SosEngine(mu, tau[None], [coef], [0, L], sos._lib.SURFACE_NONE)
+    eng.set_phase([P])
+    Cc = np.zeros((1, 2, 2 * M))
+    Cc[0, 0] = alb * P0
+    I1 = eng.first_order(Cc)
+    res = eng.solve(I1, keep_orders=60)
+    assert int(res.n_orders[0]) == int(d["n"])
+    I = eng.to_host(res.I)
+    assert relmax(I[::25], d["I_sub"]) < TOL
+    assert relmax(I[0], d["I_toa"]) < TOL and relmax(I[L - 1], d["I_surf"]) < TOL
+    for n in (2, 3, 10, 50):
+        got = res.orders[n - 2][:, : 2 * M].cpu().numpy()
+        assert relmax(got[::50], d[f"order{n}_sub"]) < TOL, n
+    eng.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# size-independent properties at full size
+# ----------------------------------------------------------------------------------------------
+def test_batch_equals_single_and_chunking_is_invisible(sos):
+    """Scenario batching and the scan chunk length are implementation details: results must not move."""
+    base = dict(nb_layers=300, nb_angles=251, atm_phase=("rayleigh", 0.5), aer_phase=("hg", 0.6))
+    scs = [sos.Scenario(mu0=0.5, tauStar_aer=0.12, alb_aer=0.97, grd_alb=0.15, **base),
+           sos.Scenario(mu0=0.8, tauStar_aer=0.4, alb_aer=0.85, grd_alb=0.3, **base),
+           sos.Scenario(mu0=0.3, tauStar_aer=0.02, alb_aer=1.0, grd_alb=0.05, **base)]
+    batch = sos.solve_scenarios(scs)
+    for i, sc in enumerate(scs):
+        single = sos.solve_scenarios([sc])[0]
+        assert single.n == batch[i].n
+        assert relmax(batch[i].I, single.I) < 1e-13
+    for chunk in (16, 37, 128):
+        bs = sos.BatchSolver(scs, chunk_rows=chunk)
+        res = bs.solve()
+        out = bs.results(res)
+        for i in range(len(scs)):
+            assert out[i].n == batch[i].n
+            assert relmax(out[i].I, batch[i].I) < 1e-12, chunk
+        bs.engine.close()
+
+
+def test_source_contraction_linearity_full_size(sos):
+    """J is linear in I_{n-1} (config-4 width N = 1024, ragged rows): J(a x + b y) = a J(x) + b J(y)."""
+    import torch
+    L, M, ts = 1500, 512, 4.5
+    mu = sos.mu_grid(M)
+    tau = np.linspace(0, ts, L)
+    P0, P = sos.phase_matrices("hg", M, mu, 0.5, 0.8)
+    rng = np.random.default_rng(1)
+    x = rng.random((L, 2 * M))
+    y = rng.random((L, 2 * M))
+    Jx = sos.Jn_NumInt(2, x, tau, mu, ts, 0.5, P, 0.9, M)
+    Jy = sos.Jn_NumInt(2, y, tau, mu, ts, 0.5, P, 0.9, M)
+    Jz = sos.Jn_NumInt(2, 2.0 * x - 0.5 * y, tau, mu, ts, 0.5, P, 0.9, M)
+    assert relmax(Jz, 2.0 * Jx - 0.5 * Jy) < 1e-13
+    # and against a float64 matmul on the same device (torch is the checker here, not the product)
+    d = np.diff(mu)
+    w = np.zeros_like(mu)
+    w[:-1] += d / 2
+    w[1:] += d / 2
+    A = (0.9 / 4) * (w[:, None] * P[:, ::-1].T)
+    ref = (torch.as_tensor(x).cuda() @ torch.as_tensor(np.ascontiguousarray(A)).cuda()).cpu().numpy()
+    assert relmax(Jx, ref) < 1e-13
