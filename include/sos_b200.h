@@ -154,6 +154,13 @@ int sos_quadratures(sos_plan* plan, const double* I_d, double direct_scale, cons
 /* Number of kernel launches issued through this plan so far (bench.py's gpu_launches). */
 long long sos_launch_count(const sos_plan* plan);
 
+/* Optional timing of the two kernel classes with CUDA events on the launching stream:
+ * class 0 = source contraction (one launch per span), class 1 = layer sweeps (three launches per
+ * span).  sos_get_profile synchronises the stream, returns accumulated milliseconds and span counts
+ * in ms[2] / spans[2] and clears the accumulators. */
+int sos_set_profiling(sos_plan* plan, int enabled);
+int sos_get_profile(sos_plan* plan, double* ms, long long* spans, void* stream);
+
 /* FP64 throughput probe used for the roofline denominator (DFMA or DMMA loop, all SMs);
  * returns TFLOP/s in *tflops.  kind: 0 = DFMA, 1 = DMMA m8n8k4. */
 int sos_fp64_peak(int kind, int repeats, double* tflops);

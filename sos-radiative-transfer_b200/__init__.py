@@ -11,14 +11,14 @@ the repository root) or with importlib.import_module("sos-radiative-transfer_b20
 from . import _lib
 from ._lib import SosError
 from .grid import mu_grid, tau_profile, extrapolation_width, aerosol_rows
-from .phase import phase_matrices
+from .phase import phase_matrices, phase_P, phase_P0
 from .engine import SosEngine, ScenarioCoefficients, SolveResult
 from .api import I1_NumInt, Jn_NumInt, In_NumInt, mu_approx_In, clear_cache
 from .drivers import (Scenario, DriverResult, BatchSolver, solve_scenarios, SOS_Aer_main_specular,
                       SOS_Aer_main_lambertian, SOS_Aer_radiative_forcing, EVA, WILDFIRE)
 
 __all__ = [
-    "SosError", "mu_grid", "tau_profile", "extrapolation_width", "aerosol_rows", "phase_matrices",
+    "SosError", "mu_grid", "tau_profile", "extrapolation_width", "aerosol_rows", "phase_matrices", "phase_P", "phase_P0",
     "SosEngine", "ScenarioCoefficients", "SolveResult", "I1_NumInt", "Jn_NumInt", "In_NumInt",
     "mu_approx_In", "clear_cache", "Scenario", "DriverResult", "BatchSolver", "solve_scenarios",
     "SOS_Aer_main_specular", "SOS_Aer_main_lambertian", "SOS_Aer_radiative_forcing", "EVA", "WILDFIRE",

@@ -96,6 +96,11 @@ struct sos_plan {
   const double* gp_I = nullptr;  // operand the I tensor map was encoded for
   std::map<const void*, CUtensorMap> map_cache;
   bool maps_A_ready = false;
+  // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_spans;  // (class, (start, stop))
 };
 
 namespace {
@@ -140,6 +145,32 @@ void build_tiles(sos_plan* p, int bm) {
     }
   }
 }
+
+cudaEvent_t prof_event(sos_plan* p) {
+  if (p->ev_used == p->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    p->ev_pool.push_back(e);
+  }
+  return p->ev_pool[p->ev_used++];
+}
+
+struct ProfSpan {
+  sos_plan* p;
+  int cls;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr;
+  ProfSpan(sos_plan* plan, int c, cudaStream_t s) : p(plan), cls(c), st(s) {
+    if (p->profiling) { e0 = prof_event(p); cudaEventRecord(e0, st); }
+  }
+  ~ProfSpan() {
+    if (p->profiling && e0) {
+      cudaEvent_t e1 = prof_event(p);
+      cudaEventRecord(e1, st);
+      p->ev_spans.push_back({cls, {e0, e1}});
+    }
+  }
+};
 
 int launch_check(sos_plan* p) {
   cudaError_t e = cudaGetLastError();
@@ -350,6 +381,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
 
 int sos_plan_destroy(sos_plan* p) {
   if (!p) return SOS_OK;
+  for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   for (void* a : p->allocs) cudaFree(a);
   if (p->h_poll) cudaFreeHost(p->h_poll);
   delete p;
@@ -357,6 +389,28 @@ int sos_plan_destroy(sos_plan* p) {
 }
 
 long long sos_launch_count(const sos_plan* p) { return p ? p->launches : 0; }
+
+int sos_set_profiling(sos_plan* p, int enabled) {
+  if (!p) return SOS_ERR_INVALID;
+  p->profiling = enabled != 0;
+  return SOS_OK;
+}
+
+int sos_get_profile(sos_plan* p, double* ms, long long* spans, void* stream) {
+  if (!p || !ms || !spans) return SOS_ERR_INVALID;
+  SOS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  ms[0] = ms[1] = 0.0;
+  spans[0] = spans[1] = 0;
+  for (auto& sp : p->ev_spans) {
+    float t = 0.f;
+    SOS_CUDA(cudaEventElapsedTime(&t, sp.second.first, sp.second.second));
+    ms[sp.first] += t;
+    spans[sp.first] += 1;
+  }
+  p->ev_spans.clear();
+  p->ev_used = 0;
+  return SOS_OK;
+}
 
 int sos_build_contraction(sos_plan* p, const double* P_d, int ldp, double* A_d, int lda, void* stream) {
   if (!p || !P_d || !A_d || ldp < p->N || lda < p->N) return SOS_ERR_INVALID;
@@ -425,6 +479,7 @@ int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
   const int n_tiles = p->gp.n_row_tiles * p->gp.n_col_tiles;
   const int grid = std::min(n_tiles, p->n_sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfSpan span(p, 0, st);
   if (bm == 128)
     sosgemm::jn_gemm_kernel<4, 2><<<grid, sosgemm::Cfg<4, 2>::THREADS, sosgemm::Cfg<4, 2>::SMEM, st>>>(p->gp);
   else
@@ -434,6 +489,7 @@ int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
 
 static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st) {
   const GridDev& g = p->dev;
+  ProfSpan span(p, 1, st);
   {
     dim3 grid((g.N + sossweep::LOCAL_THREADS - 1) / sossweep::LOCAL_THREADS, g.nchunks, g.S);
     sossweep::sweep_local_kernel<<<grid, sossweep::LOCAL_THREADS, 0, st>>>(g, J_d, In_d, p->d_aggD, p->d_aggU);
@@ -508,8 +564,6 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
   // of converged scenarios exit immediately, so the few orders enqueued past convergence cost only
   // their launch latency.
   const int nslots = 4096;
-  cudaEvent_t ev[8];
-  for (auto& e : ev) SOS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   volatile int* poll = p->h_poll;
   for (int i = 0; i < nslots; ++i) poll[i] = -1;
   int rc = SOS_OK;
@@ -525,6 +579,7 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
     rc = sos_converge(p, n, stream);
     if (rc) break;
     const int slot = issued % nslots;
+    if (issued >= nslots) poll[slot] = -1;  // that copy finished long ago (run-ahead is bounded below)
     cudaError_t e = cudaMemcpyAsync(const_cast<int*>(&poll[slot]), g.n_active, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) { g_last_cuda_error = cudaGetErrorString(e); rc = SOS_ERR_CUDA; break; }
     ++issued;
@@ -540,7 +595,6 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
       }
     }
   }
-  for (auto& e : ev) cudaEventDestroy(e);
   if (rc) return rc;
   if (results_h) return sos_get_results(p, results_h, stream);
   return SOS_OK;

@@ -82,10 +82,10 @@ class PhaseCache:
         if isinstance(spec[0], str):
             name, g = spec[0], float(spec[1])
             kP, k0 = (name, g, M), (name, g, M, float(mu0))
-            if kP not in self._P or k0 not in self._P0:
-                P0, P = PH.phase_matrices(name, M, mu, mu0, g)
-                self._P.setdefault(kP, P)
-                self._P0[k0] = P0
+            if kP not in self._P:
+                self._P[kP] = PH.phase_P(name, M, mu, g)
+            if k0 not in self._P0:
+                self._P0[k0] = PH.phase_P0(name, M, mu, mu0, g)
             return self._P0[k0], self._P[kP], kP
         P0, P = spec
         return np.asarray(P0, dtype=np.float64), np.asarray(P, dtype=np.float64), ("array", id(P))

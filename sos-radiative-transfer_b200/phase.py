@@ -61,31 +61,42 @@ def _kernel(name, g):
     raise ValueError(f"unknown analytic phase function {name!r}")
 
 
-def phase_matrices(name: str, nb_angles: int, mu: np.ndarray, mu0: float, g: float = 0.5, block: int = 128):
-    """Return (P0 (N,), P (N, N)) for name in {'iso', 'rayleigh', 'hg', 'fwc'}."""
+def phase_P0(name: str, nb_angles: int, mu: np.ndarray, mu0: float, g: float = 0.5) -> np.ndarray:
+    """First-order phase function P0(mu, mu0), normalised to trapz(P0, mu) = 2 (:92-105)."""
     N = 2 * nb_angles
     mu = np.asarray(mu, dtype=np.float64)
     if name == "iso":
-        return np.ones(N), 2 * np.ones((N, N))  # :68-76
+        return np.ones(N)  # :71
     f = _kernel(name, g)
     phi = np.linspace(0, np.pi, NB_PHI)
     cphi = np.cos(0 - phi)
     s = np.sqrt(1 - mu * mu)
-
-    # ---- P0(mu, mu0): :92-103 ----
     cc = (mu * mu0)[:, None]
     ss = (np.sqrt(1 - mu0 * mu0) * s)[:, None] * cphi[None, :]
     P0 = _trapz(f(-(cc + ss)) + f(-(cc - ss)), phi) / (4 * np.pi)
-    P0 = P0 / _trapz(P0, mu) * 2
+    return P0 / _trapz(P0, mu) * 2
 
-    # ---- P(mu, mu'): :112-131, raw matrix is symmetric; normalise each column afterwards ----
+
+def phase_P(name: str, nb_angles: int, mu: np.ndarray, g: float = 0.5, block: int = 128) -> np.ndarray:
+    """P(mu, mu'): raw matrix symmetric, then every column normalised to trapz = 4 (:112-131)."""
+    N = 2 * nb_angles
+    mu = np.asarray(mu, dtype=np.float64)
+    if name == "iso":
+        return 2 * np.ones((N, N))  # :74
+    f = _kernel(name, g)
+    phi = np.linspace(0, np.pi, NB_PHI)
+    cphi = np.cos(0 - phi)
+    s = np.sqrt(1 - mu * mu)
     P = np.empty((N, N))
     for a in range(0, N, block):
         b = min(N, a + block)
         cmn = mu[:, None] * mu[None, a:b]                       # mu[m]*mu[n]
         smn = (s[None, a:b] * s[:, None])                       # sqrt(1-mu[n]^2)*sqrt(1-mu[m]^2)
         x = smn[:, :, None] * cphi[None, None, :]
-        raw = _trapz(f(-(cmn[:, :, None] + x)) + f(-(cmn[:, :, None] - x)), phi) / (2 * np.pi)
-        P[:, a:b] = raw
-    P = 4 * P / _trapz(P, mu, axis=0)[None, :]
-    return P0, P
+        P[:, a:b] = _trapz(f(-(cmn[:, :, None] + x)) + f(-(cmn[:, :, None] - x)), phi) / (2 * np.pi)
+    return 4 * P / _trapz(P, mu, axis=0)[None, :]
+
+
+def phase_matrices(name: str, nb_angles: int, mu: np.ndarray, mu0: float, g: float = 0.5):
+    """Return (P0 (N,), P (N, N)) for name in {'iso', 'rayleigh', 'hg', 'fwc'}."""
+    return phase_P0(name, nb_angles, mu, mu0, g), phase_P(name, nb_angles, mu, g)
