@@ -247,4 +247,184 @@ jn_gemm_kernel(const __grid_constant__ GemmParams p) {
   }
 }
 
+
+// =============================================================================================
+// DMMA variant: the same TMA/mbarrier pipeline, but the inner product runs on the FP64 tensor
+// path (mma.sync.aligned.m8n8k4.f64 -> SASS DMMA.8x8x4; measured 37.1 TFLOP/s on B200 against
+// 34.1 for a pure DFMA loop, profiles/r01_fp64_peak.json).  One DMMA keeps an SMSP's FP64 pipe
+// busy for 16 cycles, so issue slots and shared-memory bandwidth stop being the limiter.
+//
+// Warp tile 64 x 32 (8 x 4 mma blocks, 64 accumulator doubles per thread); fragments:
+//   A (8x4, row)  lane (g = lane/4, t = lane%4) holds I[r0+g][k0+t]   -- 128B-swizzled I tile:
+//                 8 rows x 32 B fall on 4 distinct chunk pairs -> 2 wavefronts (the minimum)
+//   B (4x8, col)  lane holds A[k0+t][n0+g]                            -- operand rows are padded to
+//                 BN+8 doubles by loading a wider TMA box, so the 4 k-rows of a fragment sit
+//                 64 B apart modulo 128 B -> 2 wavefronts (the minimum)
+//   C (8x8)       lane holds J[r0+g][n0+2t], J[r0+g][n0+2t+1]
+template <int WM, int WN>
+struct CfgT {
+  static constexpr int BM = 64 * WM;
+  static constexpr int BN = 32 * WN;
+  static constexpr int BN_PAD = BN + 8;
+  static constexpr int CONSUMER_WARPS = WM * WN;
+  static constexpr int THREADS = 32 * (CONSUMER_WARPS + 4);
+  static constexpr bool REBALANCE = (THREADS > 256);
+  static constexpr int REGS_PRODUCER = 40;
+  static constexpr int REGS_CONSUMER = 232;
+  static constexpr int A_BYTES = BM * BK * 8;
+  static constexpr int B_BYTES = BK * BN_PAD * 8;
+  static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int NSTAGES = 5;
+  static constexpr int SMEM = NSTAGES * STAGE_BYTES + 1024 + 2 * NSTAGES * 8;
+};
+
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int WM, int WN>
+__global__ void __launch_bounds__(CfgT<WM, WN>::THREADS, 1)
+jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
+  using C = CfgT<WM, WN>;
+  constexpr int NS = C::NSTAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NS;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], C::CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int ksteps = (p.N + BK - 1) / BK;
+  const int n_tiles = p.n_row_tiles * p.n_col_tiles;
+
+  if (warp >= C::CONSUMER_WARPS) {
+    if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_PRODUCER));
+    if (warp == C::CONSUMER_WARPS && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int rt = tile / p.n_col_tiles;
+        const int ct = tile - rt * p.n_col_tiles;
+        const GemmTile t = p.tiles[rt];
+        if (!p.state[t.scen].active) continue;
+        const sos_scenario sc = p.scen[t.scen];
+        const int passes = (t.mix && sc.coef_mix_aer != 0.0) ? 2 : 1;
+        for (int pass = 0; pass < passes; ++pass) {
+          const CUtensorMap* mapA = &p.map_A[pass == 0 ? sc.phase_atm : sc.phase_aer];
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* dst = smem + stage * C::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
+            tma_load_2d(dst, &p.map_I, &full_bar[stage], ks * BK, t.row0);
+            tma_load_2d(dst + C::A_BYTES, mapA, &full_bar[stage], ct * C::BN, ks * BK);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_CONSUMER));
+  const int warp_m = warp / WN;
+  const int warp_n = warp - warp_m * WN;
+  const int g = lane >> 2;  // 0..7
+  const int t4 = lane & 3;  // 0..3
+
+  // A fragment of m-block i, k-slab j: row r = warp_m*64 + 8 i + g (r & 7 == g), k = 4 j + t4
+  //   byte = r*128 + (((k >> 1) ^ g) << 4) + (k & 1)*8 ; ((4j + t4) >> 1) = 2j + (t4 >> 1)
+  uint32_t a_off[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    a_off[j] = static_cast<uint32_t>((warp_m * 64 + g) * 128 + ((((2 * j + (t4 >> 1)) ^ g) << 4) | ((t4 & 1) << 3)));
+  // B fragment of n-block q, k-slab j: row k = 4 j + t4, col n = warp_n*32 + 8 q + g
+  const uint32_t b_off = static_cast<uint32_t>(C::A_BYTES + (t4 * C::BN_PAD + warp_n * 32 + g) * 8);
+  const uint32_t smem_base = smem_u32(smem);
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int rt = tile / p.n_col_tiles;
+    const int ct = tile - rt * p.n_col_tiles;
+    const GemmTile t = p.tiles[rt];
+    if (!p.state[t.scen].active) continue;
+    const sos_scenario sc = p.scen[t.scen];
+    const int passes = (t.mix && sc.coef_mix_aer != 0.0) ? 2 : 1;
+    const double coef_first = t.mix ? sc.coef_mix_atm : sc.coef_atm;
+    const double coef_last = passes == 2 ? sc.coef_mix_aer : coef_first;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
+
+    for (int pass = 0; pass < passes; ++pass) {
+      if (pass == 1) {
+        const double r = coef_first / coef_last;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { acc[i][q][0] *= r; acc[i][q][1] *= r; }
+      }
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sB = sA + b_off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double fa[8], fb[4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) fa[i] = lds64(sA + a_off[j] + static_cast<uint32_t>(i * 8 * 128));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) fb[q] = lds64(sB + static_cast<uint32_t>((4 * j * C::BN_PAD + 8 * q) * 8));
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dmma884(acc[i][q][0], acc[i][q][1], fa[i], fb[q]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+    }
+
+    // ---- epilogue: lane owns J[r][c], J[r][c+1]; a quad writes 64 contiguous bytes ----
+    const int col_base = ct * C::BN + warp_n * 32 + 2 * t4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp_m * 64 + 8 * i + g;
+      if (r < t.nrows) {
+        double* out = p.J + static_cast<size_t>(t.row0 + r) * p.ld;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = col_base + 8 * q;
+          if (c + 1 < p.N) {
+            *reinterpret_cast<double2*>(out + c) = make_double2(coef_last * acc[i][q][0], coef_last * acc[i][q][1]);
+          } else if (c < p.N) {
+            out[c] = coef_last * acc[i][q][0];
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace sosgemm

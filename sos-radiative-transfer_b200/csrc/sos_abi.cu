@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -87,6 +88,7 @@ struct sos_plan {
   std::vector<int> chunk_start_h;
   // GEMM
   int gemm_bm = 0;  // rows per tile of the chosen config
+  int gemm_kind = 1;  // 0 = DFMA micro-kernel, 1 = DMMA (default; SOS_GEMM=dfma selects 0)
   std::vector<GemmTile> tiles_h;
   GemmTile* d_tiles = nullptr;
   const double* phase_ptr[SOS_MAX_PHASE];
@@ -371,6 +373,12 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   // opt in to the large dynamic shared memory of the kernels used
   cudaFuncSetAttribute(sosgemm::jn_gemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<4, 2>::SMEM);
   cudaFuncSetAttribute(sosgemm::jn_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<2, 2>::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_dmma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::CfgT<2, 4>::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_dmma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::CfgT<1, 4>::SMEM);
+  {
+    const char* e = getenv("SOS_GEMM");
+    p->gemm_kind = (e && std::string(e) == "dfma") ? 0 : 1;
+  }
   if ((N + 32) * sizeof(double) > 48 * 1024) {
     cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
     cudaFuncSetAttribute(sossweep::sweep_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
@@ -424,7 +432,7 @@ int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
   if (!p || !A_d || n < 1 || n > SOS_MAX_PHASE || lda < p->N || (lda & 1)) return SOS_ERR_INVALID;
   for (const sos_scenario& sc : p->scen_h)
     if (sc.phase_atm >= n || sc.phase_aer >= n) return SOS_ERR_INVALID;
-  const int bn = 128;
+  const int bn = p->gemm_kind == 1 ? sosgemm::CfgT<2, 4>::BN_PAD : 128;  // DMMA variant loads padded rows
   for (int i = 0; i < n; ++i) {
     if (!A_d[i] || (reinterpret_cast<uintptr_t>(A_d[i]) & 15)) return SOS_ERR_INVALID;
     p->phase_ptr[i] = A_d[i];
@@ -480,10 +488,17 @@ int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
   const int grid = std::min(n_tiles, p->n_sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfSpan span(p, 0, st);
-  if (bm == 128)
-    sosgemm::jn_gemm_kernel<4, 2><<<grid, sosgemm::Cfg<4, 2>::THREADS, sosgemm::Cfg<4, 2>::SMEM, st>>>(p->gp);
-  else
-    sosgemm::jn_gemm_kernel<2, 2><<<grid, sosgemm::Cfg<2, 2>::THREADS, sosgemm::Cfg<2, 2>::SMEM, st>>>(p->gp);
+  if (p->gemm_kind == 1) {
+    if (bm == 128)
+      sosgemm::jn_gemm_dmma_kernel<2, 4><<<grid, sosgemm::CfgT<2, 4>::THREADS, sosgemm::CfgT<2, 4>::SMEM, st>>>(p->gp);
+    else
+      sosgemm::jn_gemm_dmma_kernel<1, 4><<<grid, sosgemm::CfgT<1, 4>::THREADS, sosgemm::CfgT<1, 4>::SMEM, st>>>(p->gp);
+  } else {
+    if (bm == 128)
+      sosgemm::jn_gemm_kernel<4, 2><<<grid, sosgemm::Cfg<4, 2>::THREADS, sosgemm::Cfg<4, 2>::SMEM, st>>>(p->gp);
+    else
+      sosgemm::jn_gemm_kernel<2, 2><<<grid, sosgemm::Cfg<2, 2>::THREADS, sosgemm::Cfg<2, 2>::SMEM, st>>>(p->gp);
+  }
   return launch_check(p);
 }
 
