@@ -33,6 +33,9 @@ def _digest(a: np.ndarray) -> bytes:
 
 
 def _engine(tau, mu, tauStar, mu0, alb, nb_angles, P=None) -> SosEngine:
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.SosError("no CUDA device: the SOS engine has no CPU fallback")
     tau = np.ascontiguousarray(tau, dtype=np.float64)
     mu = np.ascontiguousarray(mu, dtype=np.float64)
     key = (int(nb_angles), float(tauStar), float(mu0), float(alb), _digest(tau), _digest(mu),

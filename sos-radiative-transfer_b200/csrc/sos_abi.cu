@@ -270,6 +270,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     const long long want = 4LL * p->n_sms * 2048;
     long long c = static_cast<long long>(S) * L * N / want;
     chunk = static_cast<int>(std::max<long long>(16, std::min<long long>(128, c)));
+    chunk = std::max(chunk, (L + 47) / 48);  // keep the serial carry chain short
   }
   std::vector<int> cstart, cregion, rowchunk(L);
   for (int k = 0; k < grid->n_regions; ++k) {
@@ -513,7 +514,7 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
   }
   const size_t smem = (g.N + 32) * sizeof(double);
   {
-    sossweep::sweep_carry_kernel<<<g.S, sossweep::ROW_THREADS, smem, st>>>(g, J_d, p->d_aggD, p->d_aggU, p->d_carryD, p->d_carryU);
+    sossweep::sweep_carry_kernel<<<g.S, sossweep::CARRY_THREADS, smem, st>>>(g, J_d, p->d_aggD, p->d_aggU, p->d_carryD, p->d_carryU);
     int r = launch_check(p);
     if (r) return r;
   }

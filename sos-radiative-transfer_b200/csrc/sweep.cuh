@@ -24,6 +24,7 @@ namespace sossweep {
 
 constexpr int LOCAL_THREADS = 128;
 constexpr int ROW_THREADS = 256;
+constexpr int CARRY_THREADS = 1024;
 
 // ------------------------------------------------------------------------------------------
 // 1. chunk-local recurrences
@@ -279,7 +280,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /*[32]*/) 
 // ------------------------------------------------------------------------------------------
 // 2. carry chain (one CTA per scenario)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(CARRY_THREADS)
 sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* __restrict__ aggD,
                    const double* __restrict__ aggU, double* __restrict__ carryD, double* __restrict__ carryU) {
   extern __shared__ double sm_row[];  // [N] + scratch[32]
@@ -295,16 +296,33 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
   const size_t base = static_cast<size_t>(s) * nch * N;
 
   // ---- down: chain the standard columns through the chunks ----
+  // (the loads of the chunk aggregates and the decay factors do not depend on the carry: fetch them
+  //  eight chunks at a time so that only the FMA chain is serial)
   for (int m = threadIdx.x; m < M - 1; m += blockDim.x) {
     const double mu = g.mu[m];
     double cd = 0.0;
     if (fabs(mu) >= SOS_MU_THRESHOLD) {
-      for (int c = 0; c < nch; ++c) {
-        carryD[base + static_cast<size_t>(c) * N + m] = cd;
-        const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
-        const double a = (t0 > 0) ? aggD[base + static_cast<size_t>(c) * N + m] + cd * exp((tau[t1 - 1] - tau[t0 - 1]) / mu)
-                                  : aggD[base + static_cast<size_t>(c) * N + m];
-        cd = a;
+      for (int c0 = 0; c0 < nch; c0 += 8) {
+        double ag[8], ex[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + u;
+          ag[u] = 0.0;
+          ex[u] = 0.0;
+          if (c < nch) {
+            ag[u] = aggD[base + static_cast<size_t>(c) * N + m];
+            const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
+            if (t0 > 0) ex[u] = exp((tau[t1 - 1] - tau[t0 - 1]) / mu);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + u;
+          if (c < nch) {
+            carryD[base + static_cast<size_t>(c) * N + m] = cd;
+            cd = ag[u] + cd * ex[u];
+          }
+        }
       }
     }
     row[m] = cd;  // true D at the surface row for standard columns
@@ -338,20 +356,43 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
   __syncthreads();
 
   // ---- up: chain from the surface, re-seeding from blended rows at region boundaries ----
-  for (int c = nch - 1; c >= 0; --c) {
-    const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
-    const double tref = tau[(t1 == L) ? L - 1 : t1];
+  int c = nch - 1;
+  while (c >= 0) {
+    // batch [ce, c]: at most 8 chunks, ending at the first chunk that starts a region
+    int ce = c, nb = 1;
+    while (nb < 8 && ce > 0 && g.chunk_region[ce - 1] == g.chunk_region[ce]) { --ce; ++nb; }
     for (int m = M + 1 + threadIdx.x; m < N; m += blockDim.x) {
-      const double cu = row[m];
-      carryU[base + static_cast<size_t>(c) * N + m] = cu;
-      row[m] = aggU[base + static_cast<size_t>(c) * N + m] + cu * exp(-(tref - tau[t0]) / g.mu[m]);  // raw U at row t0
+      const double mu = g.mu[m];
+      double ag[8], ex[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cc = c - u;
+        ag[u] = 0.0;
+        ex[u] = 0.0;
+        if (cc >= ce) {
+          const int t0 = g.chunk_start[cc], t1 = g.chunk_start[cc + 1];
+          ag[u] = aggU[base + static_cast<size_t>(cc) * N + m];
+          ex[u] = exp(-(tau[(t1 == L) ? L - 1 : t1] - tau[t0]) / mu);
+        }
+      }
+      double cu = row[m];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cc = c - u;
+        if (cc >= ce) {
+          carryU[base + static_cast<size_t>(cc) * N + m] = cu;
+          cu = ag[u] + cu * ex[u];  // raw U at the first row of chunk cc
+        }
+      }
+      row[m] = cu;
     }
-    if (c > 0 && g.chunk_region[c - 1] != g.chunk_region[c]) {
-      // row t0 is the carry row of the region above and is read after its blend (A.7)
-      if (threadIdx.x == 0) row[M] = Js[static_cast<size_t>(t0) * ld + M];
+    if (ce > 0 && g.chunk_region[ce - 1] != g.chunk_region[ce]) {
+      // row chunk_start[ce] is the carry row of the region above and is read after its blend (A.7)
+      if (threadIdx.x == 0) row[M] = Js[static_cast<size_t>(g.chunk_start[ce]) * ld + M];
       __syncthreads();
       if (!blend_up_row(g, row, &found) && threadIdx.x == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
     }
+    c = ce - 1;
   }
 }
 

@@ -1,0 +1,135 @@
+"""CPU-only checks of the host side: grid helpers, phase builders, the C-ABI surface."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sos_oracle as so
+from conftest import ROOT, relmax
+
+import sos_b200 as sos
+from importlib import import_module
+
+G = import_module("sos-radiative-transfer_b200.grid")
+
+
+def test_library_exports_every_declared_symbol():
+    """include/sos_b200.h <-> ctypes prototypes <-> symbols of libsos_b200.so."""
+    hdr = open(os.path.join(ROOT, "include", "sos_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sos_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(sos._lib.SIGNATURES), declared ^ set(sos._lib.SIGNATURES)
+    lib = sos._lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sos_abi_version() == 1
+
+
+def test_abi_host_only_entry_points():
+    lib = sos._lib.load()
+    assert lib.sos_strerror(0) == b"ok"
+    assert b"invalid" in lib.sos_strerror(-1)
+    idx, ns, off = (C.c_int * 4)(), (C.c_int * 4)(), (C.c_int * 4)()
+    total = lib.sos_extrap_layout(501, idx, ns, off)
+    assert list(idx) == [2, 10, 20, 30] and list(ns) == [2, 5, 5, 5]
+    assert total == 2 * 2 + 10 * 5 + 20 * 5 + 30 * 5
+    assert total == G.extrapolation_tables(sos.mu_grid(501), 501).size
+    total = lib.sos_extrap_layout(201, idx, ns, off)
+    assert list(idx) == [1, 4, 8, 12] and list(ns) == [2, 4, 5, 5]
+    assert total == G.extrapolation_tables(sos.mu_grid(201), 201).size
+    # invalid arguments are reported as error codes, never as exceptions or crashes
+    assert lib.sos_plan_create(None, None, None, None, None, None, 0) == -1
+    assert lib.sos_source(None, None, None, None) == -1
+    assert lib.sos_plan_destroy(None) == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sos.SosError):
+        sos.I1_NumInt(np.linspace(0, 1, 10), sos.mu_grid(8), 1.0, 0.5, np.ones(16), 1.0, 8)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "sos-radiative-transfer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "sos_oracle" not in text and "ref_harness" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+@pytest.mark.parametrize("kw", [dict(tauStar_atm=0.104, tauStar_aer=0.12, z0=120, z_up=25, z_down=17, nb_layers=800),
+                                dict(tauStar_atm=0.124, tauStar_aer=0.0075, z0=120, z_up=15, z_down=14, nb_layers=800),
+                                dict(tauStar_atm=0.5, tauStar_aer=1.5, z0=120, z_up=17, z_down=25, nb_layers=70)])
+def test_tau_profile_and_rows(kw, golden):
+    a = sos.tau_profile(**kw)
+    zu, zd = max(kw["z_up"], kw["z_down"]), min(kw["z_up"], kw["z_down"])
+    b = so.tau_profile(kw["tauStar_atm"], kw["tauStar_aer"], kw["z0"], zu, zd, kw["nb_layers"])
+    assert np.array_equal(a, b)
+    if kw["nb_layers"] == 800 and kw["z_up"] == 25:
+        d = golden("default_shipped_spec.npz")
+        assert np.array_equal(a, d["tau"])
+        _, iu, idn = sos.aerosol_rows(kw["z0"], kw["z_up"], kw["z_down"], 800)
+        assert [iu, idn] == list(d["idx"]) == [633, 686]
+        assert a[-1] == kw["tauStar_atm"] + kw["tauStar_aer"]
+
+
+def test_mu_grid_and_mu_approx():
+    for M in (64, 101, 501, 1201):
+        mu = sos.mu_grid(M)
+        assert np.array_equal(mu, so.mu_grid(M))
+        assert sos.mu_approx_In(mu, M) == so.mu_approx_In(mu, M)
+    with pytest.raises(IndexError):
+        sos.mu_approx_In(np.concatenate((np.linspace(-1, 0, 8), np.linspace(0, 0.005, 8))), 8)
+
+
+def test_extrapolation_tables_match_polyfit_semantics():
+    for M in (101, 201, 251, 501, 512, 1201):
+        mu = sos.mu_grid(M)
+        flat = G.extrapolation_tables(mu, M)
+        pos = 0
+        for f in (0.005, 0.02, 0.04, 0.06):
+            w = int(f * M)
+            W, src0, ns = so.extrapolation_matrix(mu[:M], w)
+            got = flat[pos: pos + W.size].reshape(W.shape)
+            pos += W.size
+            assert np.allclose(got, W, rtol=1e-12, atol=1e-12)
+        assert pos == flat.size
+    for tau_ref, M in ((0.05, 501), (0.0625, 501), (0.5, 501), (1.0, 501), (3.9, 501), (4.0, 501), (30, 512)):
+        assert sos.extrapolation_width(tau_ref, M) == so.extrapolation_width(tau_ref, M)
+
+
+def test_phase_builders_vs_reference(golden):
+    d = golden("phase_small.npz")
+    n = 0
+    for k in d.files:
+        if not k.endswith("_P"):
+            continue
+        name, M, mu0, g = k.split("_")[:4]
+        M, mu0, g = int(M[1:]), float(mu0[3:]), float(g[1:])
+        P0, P = sos.phase_matrices(name, M, sos.mu_grid(M), mu0, g)
+        assert relmax(P, d[k]) < 1e-13 and relmax(P0, d[k[:-2] + "_P0"]) < 1e-13
+        # the reference normalises every column to trapz = 4 (SOS_Aer_phase_func.py:131)
+        assert np.allclose(so.trapz(P, sos.mu_grid(M), axis=0), 4.0, rtol=1e-13)
+        n += 1
+    assert n >= 16
+    # full-size subsample pinned by the n1002 fixture
+    d2 = golden("drivers_n1002.npz")
+    M = 501
+    P0a, Pa = sos.phase_matrices("rayleigh", M, sos.mu_grid(M), 0.5)
+    P0h, Ph = sos.phase_matrices("hg", M, sos.mu_grid(M), 0.5, 0.5)
+    assert relmax(Pa[::25, ::25], d2["phase_sub_atm"]) < 1e-13 and relmax(Ph[::25, ::25], d2["phase_sub_aer"]) < 1e-13
+    assert relmax(P0a, d2["P0_atm"]) < 1e-13 and relmax(P0h, d2["P0_aer"]) < 1e-13
+
+
+def test_scenario_defaults_are_the_shipped_literals():
+    sc = sos.Scenario()
+    # SOS_Aer_main_specular.py:23-57
+    assert (sc.mu0, sc.z0, sc.z_up, sc.z_down, sc.nb_layers) == (0.5, 120, 25, 17, 800)
+    assert (sc.tauStar_atm, sc.tauStar_aer, sc.grd_alb, sc.alb_atm, sc.alb_aer, sc.nb_angles) == (0.104, 0.120, 1, 1.0, 1.0, 501)
