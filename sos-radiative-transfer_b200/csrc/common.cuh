@@ -12,6 +12,7 @@
 #define SOS_MU0_TOLERANCE 0.0001
 
 #define SOS_MAX_PHASE 16
+#define SOS_MAX_GROUPS 48
 
 // Per-scenario mutable state (device).
 struct ScenState {
@@ -44,10 +45,18 @@ struct GridDev {
   int first_small;          // first downward column with |mu| < MU_THRESHOLD (M-1 if none)
 };
 
-// One row-tile of the source contraction.
-struct GemmTile {
-  int row0;    // first stacked row
-  int nrows;   // valid rows (<= BM)
-  int scen;
-  int mix;     // 0: rows outside the aerosol region, 1: aerosol rows (two operands)
+// Row-tile layout of the source contraction, rebuilt on the device whenever the set of active
+// scenarios changes.  A group = scenarios sharing the contraction operand(s); class 1 groups
+// (aerosol rows, two operands) come first so that the dynamic scheduler hands out the heavy tiles
+// first.  Tile t of group g covers segments [t*SEGS, (t+1)*SEGS) of the concatenation
+// "active scenario 0: seg 0..nseg-1, active scenario 1: ...".
+struct TilePlan {
+  int n_row_tiles;
+  int n_groups;
+  int group_tile_start[SOS_MAX_GROUPS + 1];
+  int group_cls[SOS_MAX_GROUPS];
+  int group_nactive[SOS_MAX_GROUPS];
+  int group_list_off[SOS_MAX_GROUPS];
+  int group_phaseA[SOS_MAX_GROUPS];
+  int group_phaseB[SOS_MAX_GROUPS];
 };

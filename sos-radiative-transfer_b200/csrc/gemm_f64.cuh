@@ -1,25 +1,36 @@
-// Source contraction J = coef * (I_{n-1} . A)  -- Jn_NumInt (SOS_Aer_I1_In.py:62-74) and the
-// inlined two-operand version for aerosol rows (SOS_Aer_main_specular.py:315-323) as ONE FP64
-// GEMM over all stacked scenario rows.
+// Source contraction J = coef * (I_{n-1} . A)  -- Jn_NumInt (SOS_Aer_I1_In.py:62-74) and the inlined
+// two-operand version for aerosol rows (SOS_Aer_main_specular.py:315-323) as ONE FP64 GEMM over the
+// stacked rows of all scenarios that are still iterating.
 //
-// tcgen05.mma has no f64 kind, so the FP64 pipe is driven with register-tiled DFMA micro-kernels;
-// everything around them is Blackwell-native: operand tiles arrive by TMA
-// (cp.async.bulk.tensor.2d, 128B-swizzled I tile, OOB zero-fill handles the ragged N=1002 edge),
-// a dedicated producer warp runs a 4-stage full/empty mbarrier ring, CTAs are persistent
-// (one per SM) and walk a host-built tile list that never straddles a region or a scenario.
+// tcgen05.mma has no f64 kind, so the FP64 tensor path is mma.sync.aligned.m8n8k4.f64 (SASS
+// DMMA.8x8x4; measured 37.1 TFLOP/s on B200 against 34.1 for a pure DFMA loop,
+// profiles/r01_fp64_peak.json -- and a register-tiled DFMA version of this kernel reached 19.6
+// TFLOP/s where the DMMA version reached 24.7 on the same tiles, profiles/r01_gemm_variants.md).
+// Everything around the DMMA is Blackwell-native:
+//   * operand tiles arrive by TMA (cp.async.bulk.tensor.2d) into a 5-stage full/empty mbarrier ring
+//     fed by a dedicated producer warp; OOB zero-fill handles the ragged N = 1002 edge in k and n;
+//   * the I operand is fetched in 8-row SEGMENTS (one 1 KB, 128B-swizzled box each).  A row tile is
+//     any 8 or 16 segments taken from a device-built list of the ACTIVE scenarios' segments, so
+//     tiles are always full (no padding at region or scenario boundaries), aerosol rows of different
+//     scenarios share two-operand tiles, and converged scenarios cost nothing;
+//   * CTAs are persistent (one per SM); the producer draws tiles from a global atomic counter and
+//     hands the tile index to the consumers through the stage ring (heavy two-operand tiles first);
+//   * setmaxnreg moves the producer warpgroup's registers to the consumer warpgroups.
 //
-// Tile: BM = 32*WM rows x BN = 64*WN columns, BK = 16.  Consumer warp = 4 (rows) x 8 (cols)
-// threads, thread tile 8 x 8:
-//   rows  warp_m*32 + i*4 + ty      (i = 0..7)  -> the 4 ty's of a warp hit 4 different 16-byte
-//                                                 chunks of the swizzled I tile (no bank conflict)
-//   cols  warp_n*64 + j*16 + 2*tx   (j = 0..3)  -> 8 tx's read/write 128 contiguous bytes
+// Warp tile 64 x 32 = 8 x 4 mma blocks (64 accumulator doubles per thread); fragments:
+//   A (8x4, row)  lane (g = lane/4, t = lane%4) holds I[r0+g][k0+t]; in the swizzled segment the
+//                 8 rows x 32 B fall on 4 distinct chunk pairs -> 2 wavefronts (the minimum)
+//   B (4x8, col)  lane holds A[k0+t][n0+g]; operand rows are padded to BN+8 doubles by loading a
+//                 wider TMA box, so the 4 k-rows sit 64 B apart modulo 128 B -> 2 wavefronts
+//   C (8x8)       lane holds J[r0+g][n0+2t], J[r0+g][n0+2t+1]
 #pragma once
 #include "common.cuh"
 
 namespace sosgemm {
 
 constexpr int BK = 16;
-constexpr int STAGES = 4;
+constexpr int NSTAGES = 5;
+constexpr int SEG_ROWS = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -47,237 +58,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
+          smem_dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ double2 lds128(uint32_t addr) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-
-struct GemmParams {
-  CUtensorMap map_I;                  // [rows_total][N] (stride ld), box {BK, BM}, 128B swizzle
-  CUtensorMap map_A[SOS_MAX_PHASE];   // [N][N] (stride lda), box {BN, BK}, no swizzle
-  const GemmTile* tiles;              // row tiles
-  int n_row_tiles;
-  int n_col_tiles;
-  int N;
-  int ld;                             // leading dimension of J
-  double* J;
-  const sos_scenario* scen;
-  const ScenState* state;
-};
-
-template <int WM, int WN>
-struct Cfg {
-  static constexpr int BM = 32 * WM;
-  static constexpr int BN = 64 * WN;
-  static constexpr int CONSUMER_WARPS = WM * WN;
-  // the producer gets a whole warpgroup (4 warps, one working lane) so that setmaxnreg can move its
-  // registers to the consumer warpgroups (register allocation is per warpgroup)
-  static constexpr int THREADS = 32 * (CONSUMER_WARPS + 4);
-  static constexpr bool REBALANCE = (THREADS > 256);
-  static constexpr int REGS_PRODUCER = 40;
-  static constexpr int REGS_CONSUMER = 232;
-  static constexpr int A_BYTES = BM * BK * 8;   // I tile
-  static constexpr int B_BYTES = BK * BN * 8;   // A tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 2 * STAGES * 8;
-};
-
-template <int WM, int WN>
-__global__ void __launch_bounds__(Cfg<WM, WN>::THREADS, 1)
-jn_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<WM, WN>;
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for the 128B-swizzled TMA destination
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], C::CONSUMER_WARPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int ksteps = (p.N + BK - 1) / BK;
-  const int n_tiles = p.n_row_tiles * p.n_col_tiles;
-
-  if (warp >= C::CONSUMER_WARPS) {
-    // ===================== TMA producer (one elected lane) =====================
-    if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_PRODUCER));
-    if (warp == C::CONSUMER_WARPS && lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int rt = tile / p.n_col_tiles;
-        const int ct = tile - rt * p.n_col_tiles;
-        const GemmTile t = p.tiles[rt];
-        if (!p.state[t.scen].active) continue;
-        const sos_scenario sc = p.scen[t.scen];
-        const int passes = (t.mix && sc.coef_mix_aer != 0.0) ? 2 : 1;
-        for (int pass = 0; pass < passes; ++pass) {
-          const CUtensorMap* mapA = &p.map_A[pass == 0 ? sc.phase_atm : sc.phase_aer];
-          for (int ks = 0; ks < ksteps; ++ks) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* dst = smem + stage * C::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            tma_load_2d(dst, &p.map_I, &full_bar[stage], ks * BK, t.row0);
-            tma_load_2d(dst + C::A_BYTES, mapA, &full_bar[stage], ct * C::BN, ks * BK);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===================== consumers: DFMA micro-kernels =====================
-  if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_CONSUMER));
-  const int warp_m = warp / WN;
-  const int warp_n = warp - warp_m * WN;
-  const int ty = lane >> 3;  // 0..3
-  const int tx = lane & 7;   // 0..7
-
-  // byte offsets inside the I tile: row r at r*128, 16-byte chunk c of row r at (c ^ (r & 7)) * 16
-  uint32_t a_pre[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = warp_m * 32 + i * 4 + ty;
-    a_pre[i] = static_cast<uint32_t>(r * 128 + ((r & 7) << 4));
-  }
-  const uint32_t b_off = static_cast<uint32_t>((warp_n * 64 + 2 * tx) * 8);
-  const uint32_t smem_base = smem_u32(smem);
-
-  int stage = 0;
-  uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int rt = tile / p.n_col_tiles;
-    const int ct = tile - rt * p.n_col_tiles;
-    const GemmTile t = p.tiles[rt];
-    if (!p.state[t.scen].active) continue;
-    const sos_scenario sc = p.scen[t.scen];
-    const int passes = (t.mix && sc.coef_mix_aer != 0.0) ? 2 : 1;
-    const double coef_first = t.mix ? sc.coef_mix_atm : sc.coef_atm;
-    const double coef_last = passes == 2 ? sc.coef_mix_aer : coef_first;
-
-    double acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-
-    for (int pass = 0; pass < passes; ++pass) {
-      if (pass == 1) {
-        // J = c1*(I.A1) + c2*(I.A2) = c2 * ((c1/c2)*(I.A1) + I.A2): rescale once, keep one accumulator
-        const double r = coef_first / coef_last;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] *= r;
-      }
-      for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
-        const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
-        const uint32_t sB = sA + C::A_BYTES + b_off;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 2) {
-          double2 ra[8];
-          double2 rb0[4], rb1[4];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ra[i] = lds128(sA + (a_pre[i] ^ static_cast<uint32_t>((kk >> 1) << 4)));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            rb0[j] = lds128(sB + static_cast<uint32_t>((kk * C::BN + 16 * j) * 8));
-            rb1[j] = lds128(sB + static_cast<uint32_t>(((kk + 1) * C::BN + 16 * j) * 8));
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[i][2 * j] = fma(ra[i].x, rb0[j].x, acc[i][2 * j]);
-              acc[i][2 * j + 1] = fma(ra[i].x, rb0[j].y, acc[i][2 * j + 1]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[i][2 * j] = fma(ra[i].y, rb1[j].x, acc[i][2 * j]);
-              acc[i][2 * j + 1] = fma(ra[i].y, rb1[j].y, acc[i][2 * j + 1]);
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-
-    // ---- epilogue: scale and store (8 tx's -> 128 contiguous bytes per row) ----
-    const int col_base = ct * C::BN + warp_n * 64 + 2 * tx;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = warp_m * 32 + i * 4 + ty;
-      if (r < t.nrows) {
-        double* out = p.J + static_cast<size_t>(t.row0 + r) * p.ld;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = col_base + 16 * j;
-          if (c + 1 < p.N) {
-            *reinterpret_cast<double2*>(out + c) = make_double2(coef_last * acc[i][2 * j], coef_last * acc[i][2 * j + 1]);
-          } else if (c < p.N) {
-            out[c] = coef_last * acc[i][2 * j];
-          }
-        }
-      }
-    }
-  }
-}
-
-
-// =============================================================================================
-// DMMA variant: the same TMA/mbarrier pipeline, but the inner product runs on the FP64 tensor
-// path (mma.sync.aligned.m8n8k4.f64 -> SASS DMMA.8x8x4; measured 37.1 TFLOP/s on B200 against
-// 34.1 for a pure DFMA loop, profiles/r01_fp64_peak.json).  One DMMA keeps an SMSP's FP64 pipe
-// busy for 16 cycles, so issue slots and shared-memory bandwidth stop being the limiter.
-//
-// Warp tile 64 x 32 (8 x 4 mma blocks, 64 accumulator doubles per thread); fragments:
-//   A (8x4, row)  lane (g = lane/4, t = lane%4) holds I[r0+g][k0+t]   -- 128B-swizzled I tile:
-//                 8 rows x 32 B fall on 4 distinct chunk pairs -> 2 wavefronts (the minimum)
-//   B (4x8, col)  lane holds A[k0+t][n0+g]                            -- operand rows are padded to
-//                 BN+8 doubles by loading a wider TMA box, so the 4 k-rows of a fragment sit
-//                 64 B apart modulo 128 B -> 2 wavefronts (the minimum)
-//   C (8x8)       lane holds J[r0+g][n0+2t], J[r0+g][n0+2t+1]
-template <int WM, int WN>
-struct CfgT {
-  static constexpr int BM = 64 * WM;
-  static constexpr int BN = 32 * WN;
-  static constexpr int BN_PAD = BN + 8;
-  static constexpr int CONSUMER_WARPS = WM * WN;
-  static constexpr int THREADS = 32 * (CONSUMER_WARPS + 4);
-  static constexpr bool REBALANCE = (THREADS > 256);
-  static constexpr int REGS_PRODUCER = 40;
-  static constexpr int REGS_CONSUMER = 232;
-  static constexpr int A_BYTES = BM * BK * 8;
-  static constexpr int B_BYTES = BK * BN_PAD * 8;
-  static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 1023) / 1024) * 1024;
-  static constexpr int NSTAGES = 5;
-  static constexpr int SMEM = NSTAGES * STAGE_BYTES + 1024 + 2 * NSTAGES * 8;
-};
-
 __device__ __forceinline__ double lds64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -289,21 +76,102 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-template <int WM, int WN>
-__global__ void __launch_bounds__(CfgT<WM, WN>::THREADS, 1)
+struct GemmParams {
+  CUtensorMap map_I;                 // [rows_total][N] (stride ld), box {BK, SEG_ROWS}, 128B swizzle
+  CUtensorMap map_A[SOS_MAX_PHASE];  // [N][N] (stride lda), box {BN+8, BK}, no swizzle
+  const TilePlan* plan;              // device, rebuilt after every convergence update
+  int* work_counter;                 // device, zeroed before every launch
+  const int* active_list;            // compacted scenario ids per group
+  const int* seg_row[2];             // local first row of each segment, per class
+  const int* seg_valid[2];           // valid rows (1..8) of each segment, per class
+  int nseg[2];
+  int n_col_tiles;
+  int L, N, ld;
+  double* J;
+  const sos_scenario* scen;
+};
+
+// What the consumers need to know about a tile; written once by the producer warp into shared memory
+// so that the consumer warps never touch global memory except for their J stores.
+template <int SEGS>
+struct TileInfo {
+  double coef[SEGS];     // final scale of each segment's rows
+  double rescale[SEGS];  // accumulator rescale between the two passes of a class-1 tile
+  int row[SEGS];         // stacked first row of the segment
+  int valid[SEGS];       // valid rows (0 = empty segment)
+  int ct;                // column tile
+  int passes;            // 1 or 2
+  int pad[2];
+};
+
+template <int WM, int WN, int MB>
+struct Cfg {
+  // warp tile = (8*MB rows) x 32 columns, MB in {4, 8} mma blocks along m
+  static constexpr int BM = 8 * MB * WM;
+  static constexpr int BN = 32 * WN;
+  static constexpr int BN_PAD = BN + 8;
+  static constexpr int SEGS = BM / SEG_ROWS;
+  static constexpr int CONSUMER_WARPS = WM * WN;
+  // the producer gets a whole warpgroup (one working warp) so that setmaxnreg can move its registers
+  // to the consumer warpgroups (register allocation is per warpgroup)
+  static constexpr int THREADS = 32 * (CONSUMER_WARPS + 4);
+  static constexpr bool REBALANCE = (THREADS > 256);
+  // setmaxnreg can only redistribute the registers the CTA was launched with: the kernel is compiled
+  // for LAUNCH_REGS per thread (what __launch_bounds__(THREADS, 1) allows), the producer warpgroup
+  // drops to REGS_PRODUCER and the consumer warpgroups share what that frees.  Asking for more than
+  // the launch pool holds would block forever.
+  static constexpr int LAUNCH_REGS = (65536 / THREADS) / 8 * 8 > 255 ? 248 : (65536 / THREADS) / 8 * 8;
+  static constexpr int REGS_PRODUCER = 40;
+  static constexpr int REGS_CONSUMER_RAW = ((THREADS * LAUNCH_REGS - 128 * REGS_PRODUCER) / (32 * CONSUMER_WARPS)) / 8 * 8;
+  static constexpr int REGS_CONSUMER = REGS_CONSUMER_RAW > 232 ? 232 : REGS_CONSUMER_RAW;
+  static constexpr int A_BYTES = BM * BK * 8;
+  static constexpr int B_BYTES = BK * BN_PAD * 8;
+  static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int INFO_SLOTS = NSTAGES + 2;  // producer runs at most NSTAGES stages ahead and a stage is released before the epilogue
+  static constexpr int SMEM = NSTAGES * STAGE_BYTES + 1024 /*align*/ + 2 * NSTAGES * 8 + NSTAGES * 8 +
+                              INFO_SLOTS * static_cast<int>(sizeof(TileInfo<SEGS>));
+};
+
+// segment q of tile `lt` of a group -> (scenario, stacked first row, valid rows); valid = 0 if none
+struct SegRef {
+  int scen, row, valid;
+};
+__device__ __forceinline__ SegRef seg_lookup(const GemmParams& p, int cls, int nactive, int list_off, int q) {
+  SegRef r;
+  const int nseg = p.nseg[cls];
+  const int rank = q / nseg;
+  if (rank >= nactive) { r.scen = -1; r.row = 0; r.valid = 0; return r; }
+  const int j = q - rank * nseg;
+  r.scen = p.active_list[list_off + rank];
+  r.row = r.scen * p.L + p.seg_row[cls][j];
+  r.valid = p.seg_valid[cls][j];
+  return r;
+}
+
+__device__ __forceinline__ int find_group(const TilePlan* plan, int rt) {
+  int g = 0;
+  while (g + 1 < plan->n_groups && rt >= plan->group_tile_start[g + 1]) ++g;
+  return g;
+}
+
+template <int WM, int WN, int MB>
+__global__ void __launch_bounds__(Cfg<WM, WN, MB>::THREADS, 1)
 jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
-  using C = CfgT<WM, WN>;
-  constexpr int NS = C::NSTAGES;
+  using C = Cfg<WM, WN, MB>;
   extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: every 8-row segment is one swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * C::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NSTAGES;
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(empty_bar + NSTAGES);  // [NSTAGES] (+pad)
+  using Info = TileInfo<C::SEGS>;
+  Info* tile_info = reinterpret_cast<Info*>(const_cast<int*>(tile_ring) + 2 * NSTAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < NSTAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], C::CONSUMER_WARPS);
     }
@@ -311,119 +179,239 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
   }
   __syncthreads();
 
+  const TilePlan* plan = p.plan;
   const int ksteps = (p.N + BK - 1) / BK;
-  const int n_tiles = p.n_row_tiles * p.n_col_tiles;
+  const int n_tiles = plan->n_row_tiles * p.n_col_tiles;
+  const uint32_t smem_base = smem_u32(smem);
 
   if (warp >= C::CONSUMER_WARPS) {
+    // ===================== TMA producer warp =====================
     if constexpr (C::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_PRODUCER));
-    if (warp == C::CONSUMER_WARPS && lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int rt = tile / p.n_col_tiles;
-        const int ct = tile - rt * p.n_col_tiles;
-        const GemmTile t = p.tiles[rt];
-        if (!p.state[t.scen].active) continue;
-        const sos_scenario sc = p.scen[t.scen];
-        const int passes = (t.mix && sc.coef_mix_aer != 0.0) ? 2 : 1;
-        for (int pass = 0; pass < passes; ++pass) {
-          const CUtensorMap* mapA = &p.map_A[pass == 0 ? sc.phase_atm : sc.phase_aer];
-          for (int ks = 0; ks < ksteps; ++ks) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* dst = smem + stage * C::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
-            tma_load_2d(dst, &p.map_I, &full_bar[stage], ks * BK, t.row0);
-            tma_load_2d(dst + C::A_BYTES, mapA, &full_bar[stage], ct * C::BN, ks * BK);
-            if (++stage == NS) { stage = 0; phase ^= 1; }
+    if (warp != C::CONSUMER_WARPS) return;
+    int stage = 0;
+    uint32_t phase = 0;
+    int seq = 0;
+    while (true) {
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(p.work_counter, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (tile >= n_tiles) {
+        // sentinel stage: tells the consumers to stop
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          tile_ring[stage] = -1;
+          mbar_arrive(&full_bar[stage]);
+        }
+        break;
+      }
+      const int rt = tile / p.n_col_tiles;
+      const int ct = tile - rt * p.n_col_tiles;
+      const int g = find_group(plan, rt);
+      const int cls = plan->group_cls[g];
+      const int lt = rt - plan->group_tile_start[g];
+      // lanes 0..SEGS-1 own one I segment each, lane SEGS owns the operand tile
+      SegRef sr;
+      sr.scen = -1; sr.row = 0; sr.valid = 0;
+      if (lane < C::SEGS) sr = seg_lookup(p, cls, plan->group_nactive[g], plan->group_list_off[g], lt * C::SEGS + lane);
+      const unsigned have = __ballot_sync(0xffffffffu, sr.valid > 0);
+      const uint32_t tx = static_cast<uint32_t>(__popc(have)) * (SEG_ROWS * BK * 8) + C::B_BYTES;
+      // tile info for the consumers (slot reuse is safe: see INFO_SLOTS)
+      Info* info = &tile_info[seq % C::INFO_SLOTS];
+      if (lane < C::SEGS) {
+        double coef = 0.0, resc = 0.0;
+        if (sr.scen >= 0) {
+          const sos_scenario& sc = p.scen[sr.scen];
+          if (cls == 1) { coef = sc.coef_mix_aer; resc = sc.coef_mix_atm / sc.coef_mix_aer; }
+          else coef = sc.coef_atm;
+        }
+        info->coef[lane] = coef;
+        info->rescale[lane] = resc;
+        info->row[lane] = sr.row;
+        info->valid[lane] = sr.valid;
+      }
+      if (lane == 0) { info->ct = ct; info->passes = cls == 1 ? 2 : 1; }
+      __syncwarp();
+      ++seq;
+      const int passes = cls == 1 ? 2 : 1;
+      for (int pass = 0; pass < passes; ++pass) {
+        const CUtensorMap* mapA = &p.map_A[pass == 0 ? plan->group_phaseA[g] : plan->group_phaseB[g]];
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t dst = smem_base + stage * C::STAGE_BYTES;
+          if (lane == 0) {
+            if (pass == 0 && ks == 0) tile_ring[stage] = tile;
+            mbar_expect_tx(&full_bar[stage], tx);
           }
+          if (sr.valid > 0) tma_load_2d(dst + lane * (SEG_ROWS * BK * 8), &p.map_I, &full_bar[stage], ks * BK, sr.row);
+          if (lane == C::SEGS) tma_load_2d(dst + C::A_BYTES, mapA, &full_bar[stage], ct * C::BN, ks * BK);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     return;
   }
 
+  // ===================== consumers: DMMA =====================
   if constexpr (C::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_CONSUMER));
   const int warp_m = warp / WN;
   const int warp_n = warp - warp_m * WN;
-  const int g = lane >> 2;  // 0..7
-  const int t4 = lane & 3;  // 0..3
+  const int g8 = lane >> 2;  // 0..7
+  const int t4 = lane & 3;   // 0..3
 
-  // A fragment of m-block i, k-slab j: row r = warp_m*64 + 8 i + g (r & 7 == g), k = 4 j + t4
-  //   byte = r*128 + (((k >> 1) ^ g) << 4) + (k & 1)*8 ; ((4j + t4) >> 1) = 2j + (t4 >> 1)
+  // A fragment of m-block i (= segment warp_m*8 + i), k-slab j: row g8 of the segment, k = 4 j + t4
+  //   byte = seg*1024 + g8*128 + (((k >> 1) ^ g8) << 4) + (k & 1)*8 ; (4j + t4) >> 1 = 2j + (t4 >> 1)
   uint32_t a_off[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    a_off[j] = static_cast<uint32_t>((warp_m * 64 + g) * 128 + ((((2 * j + (t4 >> 1)) ^ g) << 4) | ((t4 & 1) << 3)));
-  // B fragment of n-block q, k-slab j: row k = 4 j + t4, col n = warp_n*32 + 8 q + g
-  const uint32_t b_off = static_cast<uint32_t>(C::A_BYTES + (t4 * C::BN_PAD + warp_n * 32 + g) * 8);
-  const uint32_t smem_base = smem_u32(smem);
+    a_off[j] = static_cast<uint32_t>((warp_m * 8 * MB + g8) * 128 + ((((2 * j + (t4 >> 1)) ^ g8) << 4) | ((t4 & 1) << 3)));
+  // B fragment of n-block q, k-slab j: row k = 4 j + t4, col n = warp_n*32 + 8 q + g8
+  const uint32_t b_off = static_cast<uint32_t>(C::A_BYTES + (t4 * C::BN_PAD + warp_n * 32 + g8) * 8);
 
   int stage = 0;
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int rt = tile / p.n_col_tiles;
-    const int ct = tile - rt * p.n_col_tiles;
-    const GemmTile t = p.tiles[rt];
-    if (!p.state[t.scen].active) continue;
-    const sos_scenario sc = p.scen[t.scen];
-    const int passes = (t.mix && sc.coef_mix_aer != 0.0) ? 2 : 1;
-    const double coef_first = t.mix ? sc.coef_mix_atm : sc.coef_atm;
-    const double coef_last = passes == 2 ? sc.coef_mix_aer : coef_first;
+  int seq = 0;
+  while (true) {
+    mbar_wait(&full_bar[stage], phase);
+    const int tile = tile_ring[stage];
+    if (tile < 0) break;
+    const Info* info = &tile_info[seq % C::INFO_SLOTS];
+    ++seq;
+    const int ct = info->ct;
+    const int passes = info->passes;
 
-    double acc[8][4][2];
+    double acc[MB][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MB; ++i)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
 
     for (int pass = 0; pass < passes; ++pass) {
       if (pass == 1) {
-        const double r = coef_first / coef_last;
+        // J = c1*(I.A1) + c2*(I.A2) = c2 * ((c1/c2)*(I.A1) + I.A2): rescale once per segment, one accumulator
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MB; ++i) {
+          const double r = info->rescale[warp_m * MB + i];
 #pragma unroll
           for (int q = 0; q < 4; ++q) { acc[i][q][0] *= r; acc[i][q][1] *= r; }
+        }
       }
       for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
+        if (pass != 0 || ks != 0) mbar_wait(&full_bar[stage], phase);
         const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
         const uint32_t sB = sA + b_off;
+        if constexpr (MB == 8) {
+          // 2 warps per SMSP: prefetch the next k-slab's fragments while this slab's DMMAs issue
+          double fa[2][MB], fb[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          double fa[8], fb[4];
+          for (int i = 0; i < MB; ++i) fa[0][i] = lds64(sA + a_off[0] + static_cast<uint32_t>(i * 1024));
 #pragma unroll
-          for (int i = 0; i < 8; ++i) fa[i] = lds64(sA + a_off[j] + static_cast<uint32_t>(i * 8 * 128));
+          for (int q = 0; q < 4; ++q) fb[0][q] = lds64(sB + static_cast<uint32_t>(8 * q * 8));
 #pragma unroll
-          for (int q = 0; q < 4; ++q) fb[q] = lds64(sB + static_cast<uint32_t>((4 * j * C::BN_PAD + 8 * q) * 8));
+          for (int j = 0; j < 4; ++j) {
+            const int cur = j & 1, nxt = cur ^ 1;
+            if (j + 1 < 4) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < MB; ++i) fa[nxt][i] = lds64(sA + a_off[j + 1] + static_cast<uint32_t>(i * 1024));
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dmma884(acc[i][q][0], acc[i][q][1], fa[i], fb[q]);
+              for (int q = 0; q < 4; ++q)
+                fb[nxt][q] = lds64(sB + static_cast<uint32_t>((4 * (j + 1) * C::BN_PAD + 8 * q) * 8));
+            }
+#pragma unroll
+            for (int i = 0; i < MB; ++i)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dmma884(acc[i][q][0], acc[i][q][1], fa[cur][i], fb[cur][q]);
+          }
+        } else {
+          // 4 warps per SMSP hide the fragment-load latency; registers are the scarce resource
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double fa[MB], fb[4];
+#pragma unroll
+            for (int i = 0; i < MB; ++i) fa[i] = lds64(sA + a_off[j] + static_cast<uint32_t>(i * 1024));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) fb[q] = lds64(sB + static_cast<uint32_t>((4 * j * C::BN_PAD + 8 * q) * 8));
+#pragma unroll
+            for (int i = 0; i < MB; ++i)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dmma884(acc[i][q][0], acc[i][q][1], fa[i], fb[q]);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
-        if (++stage == NS) { stage = 0; phase ^= 1; }
+        if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
       }
     }
 
     // ---- epilogue: lane owns J[r][c], J[r][c+1]; a quad writes 64 contiguous bytes ----
     const int col_base = ct * C::BN + warp_n * 32 + 2 * t4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = warp_m * 64 + 8 * i + g;
-      if (r < t.nrows) {
-        double* out = p.J + static_cast<size_t>(t.row0 + r) * p.ld;
+    for (int i = 0; i < MB; ++i) {
+      const int sg = warp_m * MB + i;
+      if (g8 < info->valid[sg]) {
+        const double coef = info->coef[sg];
+        double* out = p.J + static_cast<size_t>(info->row[sg] + g8) * p.ld;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = col_base + 8 * q;
           if (c + 1 < p.N) {
-            *reinterpret_cast<double2*>(out + c) = make_double2(coef_last * acc[i][q][0], coef_last * acc[i][q][1]);
+            *reinterpret_cast<double2*>(out + c) = make_double2(coef * acc[i][q][0], coef * acc[i][q][1]);
           } else if (c < p.N) {
-            out[c] = coef_last * acc[i][q][0];
+            out[c] = coef * acc[i][q][0];
           }
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile planning: compact the active scenarios of every group and lay the row tiles out.
+// One CTA; called after every convergence update (and at plan creation / reset).
+// ---------------------------------------------------------------------------------------------
+struct GroupTable {
+  int n_groups;
+  int cls[SOS_MAX_GROUPS];
+  int phaseA[SOS_MAX_GROUPS];
+  int phaseB[SOS_MAX_GROUPS];
+  int member_off[SOS_MAX_GROUPS + 1];  // into `members`
+};
+
+__device__ __forceinline__ void plan_tiles_block(const GroupTable& gt, const int* __restrict__ members,
+                                                 const ScenState* __restrict__ state, int* __restrict__ active_list,
+                                                 TilePlan* plan, const int nseg0, const int nseg1, const int segs_per_tile) {
+  // warp w handles groups w, w + nwarps, ...
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __shared__ int nact[SOS_MAX_GROUPS];
+  for (int g = warp; g < gt.n_groups; g += nwarps) {
+    const int off = gt.member_off[g], cnt = gt.member_off[g + 1] - off;
+    int total = 0;
+    for (int base = 0; base < cnt; base += 32) {
+      const int i = base + lane;
+      int s = -1;
+      bool on = false;
+      if (i < cnt) { s = members[off + i]; on = state[s].active != 0; }
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (on) active_list[off + total + __popc(m & ((1u << lane) - 1))] = s;
+      total += __popc(m);
+    }
+    if (lane == 0) nact[g] = total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int g = 0; g < gt.n_groups; ++g) {
+      plan->group_tile_start[g] = t;
+      plan->group_cls[g] = gt.cls[g];
+      plan->group_nactive[g] = nact[g];
+      plan->group_list_off[g] = gt.member_off[g];
+      plan->group_phaseA[g] = gt.phaseA[g];
+      plan->group_phaseB[g] = gt.phaseB[g];
+      const int segs = nact[g] * (gt.cls[g] == 1 ? nseg1 : nseg0);
+      t += (segs + segs_per_tile - 1) / segs_per_tile;
+    }
+    plan->group_tile_start[gt.n_groups] = t;
+    plan->n_groups = gt.n_groups;
+    plan->n_row_tiles = t;
   }
 }
 

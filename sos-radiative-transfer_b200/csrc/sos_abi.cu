@@ -87,10 +87,14 @@ struct sos_plan {
   std::vector<sos_scenario> scen_h;
   std::vector<int> chunk_start_h;
   // GEMM
-  int gemm_bm = 0;  // rows per tile of the chosen config
-  int gemm_kind = 1;  // 0 = DFMA micro-kernel, 1 = DMMA (default; SOS_GEMM=dfma selects 0)
-  std::vector<GemmTile> tiles_h;
-  GemmTile* d_tiles = nullptr;
+  int gemm_bm = 0;  // rows per tile
+  sosgemm::GroupTable groups;
+  int* d_members = nullptr;      // scenario ids per group (static)
+  int* d_active_list = nullptr;  // compacted per group (device-built)
+  TilePlan* d_tile_plan = nullptr;
+  int* d_work_counter = nullptr;
+  int nseg[2] = {0, 0};
+  long long max_row_tiles = 0;
   const double* phase_ptr[SOS_MAX_PHASE];
   int n_phase = 0;
   int lda = 0;
@@ -130,22 +134,9 @@ int dev_upload(sos_plan* p, const T** out, const T* host, size_t count) {
   return SOS_OK;
 }
 
-void build_tiles(sos_plan* p, int bm) {
-  p->tiles_h.clear();
-  const sos_grid& g = p->grid;
-  for (int s = 0; s < g.n_scenarios; ++s) {
-    for (int k = 0; k < g.n_regions; ++k) {
-      const int r0 = g.region_start[k], r1 = g.region_start[k + 1];
-      for (int r = r0; r < r1; r += bm) {
-        GemmTile t;
-        t.row0 = s * g.nb_layers + r;
-        t.nrows = std::min(bm, r1 - r);
-        t.scen = s;
-        t.mix = (g.n_regions == 3 && k == 1) ? 1 : 0;
-        p->tiles_h.push_back(t);
-      }
-    }
-  }
+__global__ void plan_tiles_kernel(sosgemm::GroupTable gt, const int* members, const ScenState* state, int* active_list,
+                                  TilePlan* plan, int nseg0, int nseg1, int segs_per_tile) {
+  sosgemm::plan_tiles_block(gt, members, state, active_list, plan, nseg0, nseg1, segs_per_tile);
 }
 
 cudaEvent_t prof_event(sos_plan* p) {
@@ -182,6 +173,12 @@ int launch_check(sos_plan* p) {
   }
   p->launches++;
   return SOS_OK;
+}
+
+int plan_tiles(sos_plan* p, cudaStream_t st) {
+  plan_tiles_kernel<<<1, 256, 0, st>>>(p->groups, p->d_members, p->dev.state, p->d_active_list, p->d_tile_plan,
+                                       p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS);
+  return launch_check(p);
 }
 
 }  // namespace
@@ -356,29 +353,83 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     if (e != cudaSuccess) { g_last_cuda_error = cudaGetErrorString(e); sos_plan_destroy(p); return SOS_ERR_CUDA; }
   }
 
-  // ---- GEMM tile list: 128-row tiles when they fill the chip, else 64-row tiles ----
+  // ---- source contraction: operand groups, 8-row segments, device tile plan ----
   {
-    const int ncol128 = (N + 127) / 128;
-    build_tiles(p, 128);
-    if (static_cast<long long>(p->tiles_h.size()) * ncol128 >= 2LL * p->n_sms) {
-      p->gemm_bm = 128;
-    } else {
-      p->gemm_bm = 64;
-      build_tiles(p, 64);
+    // aerosol rows with a vanishing second coefficient: split the first one in two equal halves on
+    // the same operand (exact in binary floating point) so that every class-1 tile runs two passes
+    std::vector<sos_scenario> patched(scen_h, scen_h + S);
+    if (grid->n_regions == 3) {
+      for (auto& sc : patched) {
+        if (sc.coef_mix_aer == 0.0) {
+          sc.phase_aer = sc.phase_atm;
+          sc.coef_mix_atm *= 0.5;
+          sc.coef_mix_aer = sc.coef_mix_atm;
+        }
+      }
+      SOS_CUDA(cudaMemcpy(const_cast<sos_scenario*>(d.scen), patched.data(), sizeof(sos_scenario) * S, cudaMemcpyHostToDevice));
+      p->scen_h = patched;
     }
-    const GemmTile* tmp = nullptr;
-    TRY(dev_upload(p, &tmp, p->tiles_h.data(), p->tiles_h.size()));
-    p->d_tiles = const_cast<GemmTile*>(tmp);
+    // groups: class 1 (two operands) first, then class 0
+    std::vector<std::vector<int>> members;
+    std::memset(&p->groups, 0, sizeof(p->groups));
+    auto add_groups = [&](int cls) -> int {
+      std::map<std::pair<int, int>, int> index;
+      for (int s = 0; s < S; ++s) {
+        const std::pair<int, int> key = cls == 1 ? std::make_pair(patched[s].phase_atm, patched[s].phase_aer)
+                                                 : std::make_pair(patched[s].phase_atm, -1);
+        auto it = index.find(key);
+        if (it == index.end()) {
+          if (p->groups.n_groups >= SOS_MAX_GROUPS) return SOS_ERR_UNSUPPORTED;
+          const int g = p->groups.n_groups++;
+          p->groups.cls[g] = cls;
+          p->groups.phaseA[g] = key.first;
+          p->groups.phaseB[g] = cls == 1 ? key.second : key.first;
+          members.emplace_back();
+          it = index.emplace(key, g).first;
+        }
+        members[it->second].push_back(s);
+      }
+      return SOS_OK;
+    };
+    if (grid->n_regions == 3) TRY(add_groups(1));
+    TRY(add_groups(0));
+    std::vector<int> flat;
+    for (int g = 0; g < p->groups.n_groups; ++g) {
+      p->groups.member_off[g] = static_cast<int>(flat.size());
+      flat.insert(flat.end(), members[g].begin(), members[g].end());
+    }
+    p->groups.member_off[p->groups.n_groups] = static_cast<int>(flat.size());
+    // segments: regions cut into 8-row pieces; class 1 = aerosol region, class 0 = the rest
+    std::vector<int> srow[2], sval[2];
+    for (int k = 0; k < grid->n_regions; ++k) {
+      const int cls = (grid->n_regions == 3 && k == 1) ? 1 : 0;
+      for (int r = grid->region_start[k]; r < grid->region_start[k + 1]; r += sosgemm::SEG_ROWS) {
+        srow[cls].push_back(r);
+        sval[cls].push_back(std::min(sosgemm::SEG_ROWS, grid->region_start[k + 1] - r));
+      }
+    }
+    for (int c = 0; c < 2; ++c) {
+      if (srow[c].empty()) { srow[c].push_back(0); sval[c].push_back(0); p->nseg[c] = 0; }
+      else p->nseg[c] = static_cast<int>(srow[c].size());
+      TRY(dev_upload(p, &p->gp.seg_row[c], srow[c].data(), srow[c].size()));
+      TRY(dev_upload(p, &p->gp.seg_valid[c], sval[c].data(), sval[c].size()));
+      p->gp.nseg[c] = std::max(p->nseg[c], 1);
+    }
+    const int* tmpi = nullptr;
+    TRY(dev_upload(p, &tmpi, flat.data(), flat.size()));
+    p->d_members = const_cast<int*>(tmpi);
+    TRY(dev_alloc(p, &p->d_active_list, flat.size()));
+    TRY(dev_alloc(p, &p->d_tile_plan, 1));
+    TRY(dev_alloc(p, &p->d_work_counter, 1));
+    p->gemm_bm = sosgemm::Cfg<2, 4, 4>::BM;
   }
 #undef TRY
   // opt in to the large dynamic shared memory of the kernels used
-  cudaFuncSetAttribute(sosgemm::jn_gemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<4, 2>::SMEM);
-  cudaFuncSetAttribute(sosgemm::jn_gemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<2, 2>::SMEM);
-  cudaFuncSetAttribute(sosgemm::jn_gemm_dmma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::CfgT<2, 4>::SMEM);
-  cudaFuncSetAttribute(sosgemm::jn_gemm_dmma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::CfgT<1, 4>::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_dmma_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<2, 4, 4>::SMEM);
   {
-    const char* e = getenv("SOS_GEMM");
-    p->gemm_kind = (e && std::string(e) == "dfma") ? 0 : 1;
+    int r2 = plan_tiles(p, nullptr);  // all scenarios active
+    if (r2) { sos_plan_destroy(p); return r2; }
+    cudaDeviceSynchronize();
   }
   if ((N + 32) * sizeof(double) > 48 * 1024) {
     cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
@@ -433,7 +484,7 @@ int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
   if (!p || !A_d || n < 1 || n > SOS_MAX_PHASE || lda < p->N || (lda & 1)) return SOS_ERR_INVALID;
   for (const sos_scenario& sc : p->scen_h)
     if (sc.phase_atm >= n || sc.phase_aer >= n) return SOS_ERR_INVALID;
-  const int bn = p->gemm_kind == 1 ? sosgemm::CfgT<2, 4>::BN_PAD : 128;  // DMMA variant loads padded rows
+  const int bn = sosgemm::Cfg<2, 4, 4>::BN_PAD;  // rows are loaded 8 columns wider than the tile (bank layout)
   for (int i = 0; i < n; ++i) {
     if (!A_d[i] || (reinterpret_cast<uintptr_t>(A_d[i]) & 15)) return SOS_ERR_INVALID;
     p->phase_ptr[i] = A_d[i];
@@ -467,39 +518,30 @@ int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
   if (!p->maps_A_ready) return SOS_ERR_STATE;
   if ((reinterpret_cast<uintptr_t>(In1_d) & 15) || (reinterpret_cast<uintptr_t>(J_d) & 15)) return SOS_ERR_INVALID;
   const GridDev& g = p->dev;
-  const int bm = p->gemm_bm;
   auto it = p->map_cache.find(In1_d);
   if (it == p->map_cache.end()) {
     CUtensorMap m;
-    int r = encode_2d(&m, In1_d, g.N, static_cast<uint64_t>(g.S) * g.L, g.ld, sosgemm::BK, bm, CU_TENSOR_MAP_SWIZZLE_128B);
+    int r = encode_2d(&m, In1_d, g.N, static_cast<uint64_t>(g.S) * g.L, g.ld, sosgemm::BK, sosgemm::SEG_ROWS,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (r) return r;
     if (p->map_cache.size() > 64) p->map_cache.clear();
     it = p->map_cache.emplace(In1_d, m).first;
   }
   p->gp.map_I = it->second;
-  p->gp.tiles = p->d_tiles;
-  p->gp.n_row_tiles = static_cast<int>(p->tiles_h.size());
+  p->gp.plan = p->d_tile_plan;
+  p->gp.work_counter = p->d_work_counter;
+  p->gp.active_list = p->d_active_list;
   p->gp.n_col_tiles = (g.N + 127) / 128;
+  p->gp.L = g.L;
   p->gp.N = g.N;
   p->gp.ld = g.ld;
   p->gp.J = J_d;
   p->gp.scen = g.scen;
-  p->gp.state = g.state;
-  const int n_tiles = p->gp.n_row_tiles * p->gp.n_col_tiles;
-  const int grid = std::min(n_tiles, p->n_sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SOS_CUDA(cudaMemsetAsync(p->d_work_counter, 0, sizeof(int), st));
   ProfSpan span(p, 0, st);
-  if (p->gemm_kind == 1) {
-    if (bm == 128)
-      sosgemm::jn_gemm_dmma_kernel<2, 4><<<grid, sosgemm::CfgT<2, 4>::THREADS, sosgemm::CfgT<2, 4>::SMEM, st>>>(p->gp);
-    else
-      sosgemm::jn_gemm_dmma_kernel<1, 4><<<grid, sosgemm::CfgT<1, 4>::THREADS, sosgemm::CfgT<1, 4>::SMEM, st>>>(p->gp);
-  } else {
-    if (bm == 128)
-      sosgemm::jn_gemm_kernel<4, 2><<<grid, sosgemm::Cfg<4, 2>::THREADS, sosgemm::Cfg<4, 2>::SMEM, st>>>(p->gp);
-    else
-      sosgemm::jn_gemm_kernel<2, 2><<<grid, sosgemm::Cfg<2, 2>::THREADS, sosgemm::Cfg<2, 2>::SMEM, st>>>(p->gp);
-  }
+  // 64 x 128 tiles, 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md: best of the four shapes tried)
+  sosgemm::jn_gemm_dmma_kernel<2, 4, 4><<<p->n_sms, sosgemm::Cfg<2, 4, 4>::THREADS, sosgemm::Cfg<2, 4, 4>::SMEM, st>>>(p->gp);
   return launch_check(p);
 }
 
@@ -535,7 +577,9 @@ int sos_sweeps(sos_plan* p, const double* J_d, double* In_d, double* I_d, void* 
 int sos_converge(sos_plan* p, int order, void* stream) {
   if (!p) return SOS_ERR_INVALID;
   sossweep::converge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, order);
-  return launch_check(p);
+  int r = launch_check(p);
+  if (r) return r;
+  return plan_tiles(p, static_cast<cudaStream_t>(stream));
 }
 
 int sos_reset(sos_plan* p, const double* I1_d, void* stream) {
@@ -545,7 +589,9 @@ int sos_reset(sos_plan* p, const double* I1_d, void* stream) {
   int r = launch_check(p);
   if (r) return r;
   sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev);
-  return launch_check(p);
+  r = launch_check(p);
+  if (r) return r;
+  return plan_tiles(p, st);
 }
 
 int sos_get_results(sos_plan* p, sos_result* results_h, void* stream) {
