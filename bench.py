@@ -12,8 +12,10 @@ closed-form first order + the order loop to In/I < 1e-4 for every scenario.
 
   metric  = sum over scenarios and orders n >= 2 of L*N^2  /  time     
   value   : inputs already resident in HBM (plan, phase operands, coefficients uploaded before)
-  e2e     : the public API call with HOST arrays in / NumPy out (plan creation, H2D of tau,
-            coefficients and phase matrices, D2H of every accumulated field + fluxes) per step
+  e2e     : the public API call with HOST arrays in / NumPy out per step: plan creation, H2D of tau,
+            coefficients and phase matrices, solve, D2H of the flux / diffusivity / heating-rate
+            profiles, order counts and TOA net flux of every scenario (what a forcing sweep returns;
+            the reference's SOS_Aer_radiative_forcing returns one float per solve)
   roofline: dominant kernel = the FP64 source contraction (jn_gemm), timed with CUDA events on the
             launching stream inside the timed steps; peak = FP64 DMMA/DFMA throughput measured on
             this GPU in the same run (MEASURED_PEAKS.json has no FP64 entry)
@@ -58,7 +60,10 @@ def make_scenarios(sos, S, rank=0, L=L_DEFAULT, M=M_DEFAULT):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    nvidia-smi takes a few hundred ms to start, so the sampler is started before the warm-up and
+    every line is stamped on arrival; stop(t0, t1) keeps the samples that fall inside [t0, t1]."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -69,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -77,14 +82,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)  # let the last in-window sample arrive
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except (ValueError, IndexError):
@@ -96,21 +104,34 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_CPU_CACHE = {}
+
+
+def cpu_port_inputs(L, M, seed_rank):
+    """Inputs of one workload scenario for the NumPy port (built once per process, untimed)."""
+    key = (L, M, seed_rank)
+    if key not in _CPU_CACHE:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import sos_oracle as so
+        import sos_b200 as sos
+        scen = make_scenarios(sos, 1, seed_rank, L, M)[0]
+        mu = so.mu_grid(M)
+        P0a, Pa = sos.phase_matrices("rayleigh", M, mu, scen.mu0)
+        P0e, Pe = sos.phase_matrices(scen.aer_phase[0], M, mu, scen.mu0, scen.aer_phase[1])
+        sc = so.Scenario(mu0=scen.mu0, nb_layers=L, nb_angles=M, tauStar_atm=scen.tauStar_atm,
+                         tauStar_aer=scen.tauStar_aer, grd_alb=scen.grd_alb, alb_aer=scen.alb_aer, surface="specular")
+        tau, z, iu, idn = sc.geometry()
+        I1 = so.first_order_regions(sc, tau, mu, iu, idn, P0a, P0e)
+        lay = so.driver_layout(sc, tau, mu, iu, idn)
+        _CPU_CACHE[key] = (so, sc, mu, iu, idn, Pa, Pe, lay, I1)
+    return _CPU_CACHE[key]
+
+
 def cpu_port_sample(orders=2, L=L_DEFAULT, M=M_DEFAULT, seed_rank=0):
     """One scenario of the workload through the NumPy port ("slices" = the reference's O(L^2 N)
-    scheme): first order untimed, `orders` scattering orders timed.  Returns (units, seconds)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import sos_oracle as so
-    import sos_b200 as sos
-    scen = make_scenarios(sos, 1, seed_rank, L, M)[0]
-    mu = so.mu_grid(M)
-    P0a, Pa = sos.phase_matrices("rayleigh", M, mu, scen.mu0)
-    P0e, Pe = sos.phase_matrices(scen.aer_phase[0], M, mu, scen.mu0, scen.aer_phase[1])
-    sc = so.Scenario(mu0=scen.mu0, nb_layers=L, nb_angles=M, tauStar_atm=scen.tauStar_atm, tauStar_aer=scen.tauStar_aer,
-                     grd_alb=scen.grd_alb, alb_aer=scen.alb_aer, surface="specular")
-    tau, z, iu, idn = sc.geometry()
-    I1 = so.first_order_regions(sc, tau, mu, iu, idn, P0a, P0e)
-    lay = so.driver_layout(sc, tau, mu, iu, idn)
+    scheme): phase matrices and first order untimed, `orders` scattering orders timed.
+    orders == 0 only builds the inputs.  Returns (units, seconds)."""
+    so, sc, mu, iu, idn, Pa, Pe, lay, I1 = cpu_port_inputs(L, M, seed_rank)
     In = I1
     t0 = time.perf_counter()
     for _ in range(orders):
@@ -121,7 +142,12 @@ def cpu_port_sample(orders=2, L=L_DEFAULT, M=M_DEFAULT, seed_rank=0):
 
 
 def _cpu_worker(args):
-    return cpu_port_sample(*args)
+    # every pool worker keeps ONE scenario of the workload (chosen by its worker index), so the inputs
+    # built in the untimed first round are the ones the timed rounds reuse
+    import multiprocessing as mp
+    ident = mp.current_process()._identity
+    orders, L, M, _ = args
+    return cpu_port_sample(orders, L, M, ident[0] - 1 if ident else 0)
 
 
 def run_reference(args):
@@ -135,13 +161,14 @@ def run_reference(args):
     orders = 1
     L = args.cpu_layers
     with mp.get_context("spawn").Pool(procs) as pool:
-        for _ in range(args.warmup if args.warmup < 1 else 1):
-            pool.map(_cpu_worker, [(1, 100, 101, i) for i in range(procs)])  # page-in / import warm-up
+        # untimed: imports, phase matrices and first order of every worker's scenario (chunksize 1 and as
+        # many tasks as workers: each worker builds, and later reuses, its own scenario)
+        pool.map(_cpu_worker, [(0, L, M_DEFAULT, i) for i in range(procs)], chunksize=1)
         times = []
         units = 0
         for _ in range(args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(orders, L, M_DEFAULT, i) for i in range(procs)])
+            res = pool.map(_cpu_worker, [(orders, L, M_DEFAULT, i) for i in range(procs)], chunksize=1)
             times.append(time.perf_counter() - t0)
             units = sum(r[0] for r in res)
     ms = 1e3 * float(np.mean(times))
@@ -162,7 +189,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--scenarios", type=int, default=96, help="scenarios per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -214,26 +241,28 @@ def main():
         return res
 
     # ---------------- device-resident timing ----------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(W):
         res = step_resident()
     units_per_step = int(np.sum(res.n_orders - 1)) * L * N * N
     n_orders = res.n_orders.copy()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     lib.sos_set_profiling(eng._plan, 1)
     l0 = eng.launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
     barrier()
-    t_wall = time.perf_counter()
+    t_begin = time.perf_counter()
+    t_wall = t_begin
     for k in range(args.steps):
         flush.zero_()                                  # L2 flush between timed iterations (untimed)
         ev[2 * k].record()
         step_resident()
         ev[2 * k + 1].record()
     barrier()
-    t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop()
+    t_end = time.perf_counter()
+    t_wall = t_end - t_wall
+    clocks = sampler.stop(t_begin, t_end)
     launches = eng.launches - l0
     import ctypes as C
     ms2 = (C.c_double * 2)()
@@ -290,9 +319,9 @@ def main():
         nonlocal h2d, d2h
         b = sos.BatchSolver(scen, device=dev)          # plan creation + H2D of tau, coefficients, P
         r = b.solve(poll_every=2)
-        out = b.results(r, quadratures=True)           # D2H of every accumulated field + fluxes
+        out = b.results(r, quadratures=True, fields=False)   # D2H: flux/diffusivity/heating profiles, n, TOA net flux
         h2d = (b.tau.nbytes + b.Ccoef.nbytes + len(b.engine._A) * N * N * 8 + b.mu.nbytes)
-        d2h = sum(o.I.nbytes + 5 * o.flux_up.nbytes for o in out)
+        d2h = sum(5 * o.flux_up.nbytes for o in out) + 40 * len(out)
         cnt = b.engine.launches
         b.engine.close()
         return cnt

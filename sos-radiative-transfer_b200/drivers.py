@@ -159,27 +159,34 @@ class BatchSolver:
         mo = max_orders if max_orders is not None else max(s.max_orders for s in self.scenarios)
         return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every)
 
-    def results(self, res, quadratures=True, keep_orders=0) -> List[DriverResult]:
+    def results(self, res, quadratures=True, keep_orders=0, fields=True) -> List[DriverResult]:
+        """Per-scenario results on the host.  fields=False skips the D2H copy of the radiance fields
+        (what a flux / forcing sweep needs: SOS_Aer_radiative_forcing returns one float)."""
         eng = self.engine
-        I = eng.to_host(res.I).reshape(eng.S, eng.L, eng.N)
-        q = q2 = None
+        I = eng.to_host(res.I).reshape(eng.S, eng.L, eng.N) if fields else None
+        q = None
         if quadratures:
             q = eng.quadratures(res.I, self.z, direct_scale=1.0)
-            q2 = eng.quadratures(res.I, None, direct_scale=1.0 / (4 * np.pi), heating=False)
         orders = None
         if keep_orders and res.orders is not None:
             orders = res.orders[:, :, : eng.N].reshape(keep_orders, eng.S, eng.L, eng.N).cpu().numpy()
         I1 = eng.to_host(self.I1).reshape(eng.S, eng.L, eng.N) if keep_orders else None
         out = []
         for i, sc in enumerate(self.scenarios):
-            r = DriverResult(I=I[i], n=int(res.n_orders[i]), tau=self.tau[i], mu=self.mu, z_profile=self.z,
-                             idx_up=self.idx_up, idx_down=self.idx_down,
+            r = DriverResult(I=I[i] if fields else None, n=int(res.n_orders[i]), tau=self.tau[i], mu=self.mu,
+                             z_profile=self.z, idx_up=self.idx_up, idx_down=self.idx_down,
                              ratio=float(max(res.ratio_toa[i], res.ratio_surf[i])), status=int(res.status[i]))
             if q is not None:
                 r.flux_up, r.flux_down, r.net_flux = q["flux_up"][i], q["flux_down"][i], q["net_flux"][i]
                 r.diffusivity, r.heating_rate = q["diffusivity"][i], q["heating_rate"][i]
-                # TOA net flux with the F0/(4 pi) direct scaling (SOS_Aer_critical_albedo.py:377-382)
-                r.toa_net_flux = float(-q2["flux_down"][i][0] - q2["flux_up"][i][0])
+                # TOA net flux with the F0/(4 pi) direct scaling (SOS_Aer_critical_albedo.py:377-382):
+                # same quadrature sums, direct terms rescaled from F0 to F0/(4 pi)
+                F0 = np.pi / sc.mu0
+                k = F0 * (1.0 - 1.0 / (4 * np.pi))
+                t0, tl = self.tau[i][0], self.tau[i][-1]
+                fd = r.flux_down[0] + k * np.exp(-t0 / sc.mu0)
+                fu = r.flux_up[0] - k * sc.grd_alb * np.exp(-(2 * tl - t0) / sc.mu0)
+                r.toa_net_flux = float(-fd - fu)
             if orders is not None:
                 r.I_saved = [I1[i]] + [orders[k, i] for k in range(min(keep_orders, r.n - 1))]
             if r.status & _lib.STATUS_BLEND_OVERRUN:
