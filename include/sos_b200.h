@@ -154,6 +154,16 @@ int sos_quadratures(sos_plan* plan, const double* I_d, double direct_scale, cons
 /* Number of kernel launches issued through this plan so far (bench.py's gpu_launches). */
 long long sos_launch_count(const sos_plan* plan);
 
+/* mu-block sharding of one large grid (BASELINE config 4): this plan computes only the mu columns
+ * [col0, col1) of J and I_n (and accumulates only those columns of I); the caller all-gathers the
+ * I_n blocks of all ranks before the next sos_source.  col0 and col1 must be multiples of 128 (or 0 /
+ * N); only grids without surface coupling (n_regions == 1, SOS_SURFACE_NONE) can be sharded, and a
+ * block boundary must not cut the mu -> 0 zones (SOS_ERR_UNSUPPORTED otherwise). */
+int sos_plan_set_columns(sos_plan* plan, int col0, int col1);
+/* Copy the per-scenario convergence ratios {ratio_toa, ratio_surf} to (set = 0) or from (set = 1) a
+ * device buffer [S][2]: sharded ranks MAX-all-reduce them between sos_sweeps and sos_converge. */
+int sos_state_ratios(sos_plan* plan, double* buf_d, int set, void* stream);
+
 /* Optional timing of the two kernel classes with CUDA events on the launching stream:
  * class 0 = source contraction (one launch per span), class 1 = layer sweeps (three launches per
  * span).  sos_get_profile synchronises the stream, returns accumulated milliseconds and span counts

@@ -82,6 +82,8 @@ SIGNATURES = {
     "sos_reset": (C.c_int, [_vp, _vp, _vp]),
     "sos_quadratures": (C.c_int, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sos_launch_count": (C.c_longlong, [_vp]),
+    "sos_plan_set_columns": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "sos_state_ratios": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "sos_set_profiling": (C.c_int, [_vp, C.c_int]),
     "sos_get_profile": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), _vp]),
     "sos_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),

@@ -43,6 +43,7 @@ struct GridDev {
   const double* W;          // extrapolation matrices
   int widx[4], wns[4], woff[4];
   int first_small;          // first downward column with |mu| < MU_THRESHOLD (M-1 if none)
+  int col0, col1;           // mu columns this plan owns (mu-block sharding); [0, N) by default
 };
 
 // Row-tile layout of the source contraction, rebuilt on the device whenever the set of active

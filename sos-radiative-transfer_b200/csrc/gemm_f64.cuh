@@ -85,7 +85,8 @@ struct GemmParams {
   const int* seg_row[2];             // local first row of each segment, per class
   const int* seg_valid[2];           // valid rows (1..8) of each segment, per class
   int nseg[2];
-  int n_col_tiles;
+  int n_col_tiles;                   // column tiles this plan computes ...
+  int ct0;                           // ... starting at this one (mu-block sharding)
   int L, N, ld;
   double* J;
   const sos_scenario* scen;
@@ -205,7 +206,7 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
         break;
       }
       const int rt = tile / p.n_col_tiles;
-      const int ct = tile - rt * p.n_col_tiles;
+      const int ct = p.ct0 + tile - rt * p.n_col_tiles;
       const int g = find_group(plan, rt);
       const int cls = plan->group_cls[g];
       const int lt = rt - plan->group_tile_start[g];

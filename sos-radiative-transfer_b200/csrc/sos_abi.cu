@@ -310,6 +310,8 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   d.surface = grid->surface;
   d.nchunks = nch;
   d.first_small = first_small;
+  d.col0 = 0;
+  d.col1 = N;
   for (int c = 0; c < 4; ++c) { d.widx[c] = widx[c]; d.wns[c] = wns[c]; d.woff[c] = woff[c]; }
 
   int r = SOS_OK;
@@ -450,6 +452,32 @@ int sos_plan_destroy(sos_plan* p) {
 
 long long sos_launch_count(const sos_plan* p) { return p ? p->launches : 0; }
 
+int sos_plan_set_columns(sos_plan* p, int col0, int col1) {
+  if (!p) return SOS_ERR_INVALID;
+  GridDev& g = p->dev;
+  if (col0 < 0 || col1 > g.N || col0 >= col1) return SOS_ERR_INVALID;
+  if (col0 == 0 && col1 == g.N) { g.col0 = 0; g.col1 = g.N; return SOS_OK; }
+  // mu-block sharding: only grids without a surface coupling (the coupling mixes mirror columns)
+  if (g.surface != SOS_SURFACE_NONE || g.nreg != 1) return SOS_ERR_UNSUPPORTED;
+  if ((col0 % 128) != 0 || (col1 != g.N && (col1 % 128) != 0)) return SOS_ERR_INVALID;
+  // the mu -> 0 zones must not straddle a block boundary
+  int wmax = 0;
+  for (const sos_scenario& sc : p->scen_h) wmax = std::max(wmax, sc.extrap_width[0]);
+  const int zlo = std::min(g.first_small, g.M - wmax - 5);
+  const bool cuts_down = (col0 > zlo && col0 < g.M) || (col1 > zlo && col1 < g.M);
+  const bool cuts_up = (col0 == g.M + 1) || (col1 == g.M + 1);
+  if (cuts_down || cuts_up) return SOS_ERR_UNSUPPORTED;
+  g.col0 = col0;
+  g.col1 = col1;
+  return SOS_OK;
+}
+
+int sos_state_ratios(sos_plan* p, double* buf_d, int set, void* stream) {
+  if (!p || !buf_d) return SOS_ERR_INVALID;
+  sossweep::ratios_kernel<<<(p->dev.S + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, buf_d, set);
+  return launch_check(p);
+}
+
 int sos_set_profiling(sos_plan* p, int enabled) {
   if (!p) return SOS_ERR_INVALID;
   p->profiling = enabled != 0;
@@ -531,7 +559,8 @@ int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
   p->gp.plan = p->d_tile_plan;
   p->gp.work_counter = p->d_work_counter;
   p->gp.active_list = p->d_active_list;
-  p->gp.n_col_tiles = (g.N + 127) / 128;
+  p->gp.ct0 = g.col0 / 128;
+  p->gp.n_col_tiles = (g.col1 + 127) / 128 - p->gp.ct0;
   p->gp.L = g.L;
   p->gp.N = g.N;
   p->gp.ld = g.ld;

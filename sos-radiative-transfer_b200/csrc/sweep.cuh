@@ -36,7 +36,7 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
   if (!g.state[s].active) return;
   const int c = blockIdx.y;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= g.N) return;
+  if (m >= g.N || m < g.col0 || m >= g.col1) return;
   const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
   const int L = g.L, M = g.M, ld = g.ld;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
@@ -227,7 +227,7 @@ __device__ __forceinline__ void finish_down_row(const GridDev& g, double* row, c
 // Blend of the upward half towards mu = 0+ (SOS_Aer_I1_In.py:101-108).  row[M] must already hold J[t,M].
 // `found` is a shared int.  All threads of the CTA must call; returns false on search overrun (Q11).
 __device__ __forceinline__ bool blend_up_row(const GridDev& g, double* row, int* found) {
-  const int M = g.M, N = g.N;
+  const int M = g.M, N = g.col1;  // the search never leaves the owned columns
   if (threadIdx.x == 0) *found = 0x7fffffff;
   __syncthreads();
   for (int base = M + 1; base + 2 <= N - 1; base += blockDim.x) {
@@ -301,7 +301,7 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
   for (int m = threadIdx.x; m < M - 1; m += blockDim.x) {
     const double mu = g.mu[m];
     double cd = 0.0;
-    if (fabs(mu) >= SOS_MU_THRESHOLD) {
+    if (fabs(mu) >= SOS_MU_THRESHOLD && m >= g.col0 && m < g.col1) {
       for (int c0 = 0; c0 < nch; c0 += 8) {
         double ag[8], ex[8];
 #pragma unroll
@@ -362,6 +362,7 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
     int ce = c, nb = 1;
     while (nb < 8 && ce > 0 && g.chunk_region[ce - 1] == g.chunk_region[ce]) { --ce; ++nb; }
     for (int m = M + 1 + threadIdx.x; m < N; m += blockDim.x) {
+      if (m < g.col0 || m >= g.col1) continue;
       const double mu = g.mu[m];
       double ag[8], ex[8];
 #pragma unroll
@@ -423,10 +424,15 @@ sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __r
   const double tup = tau[(t1 == L) ? L - 1 : t1];
   const size_t roff = static_cast<size_t>(t) * ld;
 
+  const int c_lo = g.col0, c_hi = g.col1;
+  const bool own_down_zone = (c_lo < M && c_hi >= M);   // columns next to mu = 0- (validated at plan time)
+  const bool own_up_zone = (c_lo <= M && c_hi > M + 1);  // columns next to mu = 0+
   for (int m = threadIdx.x; m < N; m += blockDim.x) {
     const double mu = g.mu[m];
     double v = 0.0;
-    if (m < M - 1) {
+    if (m < c_lo || m >= c_hi) {
+      v = 0.0;
+    } else if (m < M - 1) {
       if (fabs(mu) >= SOS_MU_THRESHOLD) {
         v = Is[roff + m];
         if (t0 > 0) v += carryD[cbase + m] * exp((tt - tdn) / mu);
@@ -441,8 +447,9 @@ sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __r
   __syncthreads();
 
   const int idxw = sc.extrap_width[region];
-  finish_down_row(g, row, Js, tau, t, region, idxw, width_class(g, idxw));
-  if (!blend_up_row(g, row, &found) && threadIdx.x == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
+  if (own_down_zone) finish_down_row(g, row, Js, tau, t, region, idxw, width_class(g, idxw));
+  if (own_up_zone && !blend_up_row(g, row, &found) && threadIdx.x == 0)
+    atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
 
   // ---- write I_n, accumulate, convergence ratios (SOS_Aer_main_specular.py:309,454-456) ----
   const bool toa = (t == 0), surf = (t == L - 1);
@@ -450,7 +457,7 @@ sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __r
   bool nonfinite = false;
   double* __restrict__ Iacc = I ? I + static_cast<size_t>(s) * L * ld : nullptr;
   double* __restrict__ sv = saved ? saved + static_cast<size_t>(s) * L * ld : nullptr;
-  for (int m = threadIdx.x; m < N; m += blockDim.x) {
+  for (int m = c_lo + threadIdx.x; m < c_hi; m += blockDim.x) {
     const double v = row[m];
     Is[roff + m] = v;
     if (sv) sv[roff + m] = v;
@@ -538,6 +545,14 @@ __global__ void reset_kernel(const GridDev g, const double* __restrict__ I1) {
     st.status = 0;
     st.active = (fmax(st.ratio_toa, r) >= g.scen[s].threshold) ? 1 : 0;
   }
+}
+
+// ratios <-> caller buffer [S][2] (mu-block sharding reduces them across ranks with a MAX all-reduce)
+__global__ void ratios_kernel(const GridDev g, double* buf, int set) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= g.S) return;
+  if (set) { g.state[s].ratio_toa = buf[2 * s]; g.state[s].ratio_surf = buf[2 * s + 1]; }
+  else { buf[2 * s] = g.state[s].ratio_toa; buf[2 * s + 1] = g.state[s].ratio_surf; }
 }
 
 __global__ void count_active_kernel(const GridDev g) {

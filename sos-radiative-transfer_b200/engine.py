@@ -219,6 +219,19 @@ class SosEngine:
             _lib.check(self.lib.sos_sweeps(self._plan, J.data_ptr(), out.data_ptr(), acc, self._stream), "sos_sweeps")
         return out
 
+    def set_columns(self, col0: int, col1: int):
+        """Own only the mu columns [col0, col1) (mu-block sharding, see sos_plan_set_columns)."""
+        _lib.check(self.lib.sos_plan_set_columns(self._plan, int(col0), int(col1)), "sos_plan_set_columns")
+        self.col0, self.col1 = int(col0), int(col1)
+
+    def ratios(self, buf: Optional[torch.Tensor] = None, set: bool = False) -> torch.Tensor:
+        """Device tensor (S, 2) of {ratio_toa, ratio_surf}; set=True writes `buf` back into the plan."""
+        if buf is None:
+            buf = torch.empty((self.S, 2), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_state_ratios(self._plan, buf.data_ptr(), 1 if set else 0, self._stream), "sos_state_ratios")
+        return buf
+
     def reset(self, I1: torch.Tensor):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sos_reset(self._plan, I1.data_ptr(), self._stream), "sos_reset")

@@ -261,3 +261,51 @@ def test_source_contraction_linearity_full_size(sos):
     A = (0.9 / 4) * (w[:, None] * P[:, ::-1].T)
     ref = (torch.as_tensor(x).cuda() @ torch.as_tensor(np.ascontiguousarray(A)).cuda()).cpu().numpy()
     assert relmax(Jx, ref) < 1e-13
+
+
+def test_mu_block_sharding_matches_unsharded_single_gpu(sos):
+    """mu-block sharding (config 4): four plans on one GPU, each owning a 256-column block, must
+    reproduce the unsharded order bit for bit (same arithmetic per column) -- the NCCL all-gather
+    between them is covered by the gloo test and tools/mu_shard_check.py."""
+    import torch
+    L, M, ts, mu0, alb = 400, 512, 1.2, 0.5, 0.9
+    N = 2 * M
+    mu = sos.mu_grid(M)
+    tau = np.linspace(0, ts, L)
+    P0, P = sos.phase_matrices("hg", M, mu, mu0, 0.8)
+    w = sos.extrapolation_width(ts, M)
+    coef = [sos.ScenarioCoefficients(mu0=mu0, grd_alb=0.0, tauStar_tot=ts, coef_atm=alb, extrap_width=(w, w, w))]
+    Cc = np.zeros((1, 2, N))
+    Cc[0, 0] = alb * P0
+
+    def one_order(cols=None):
+        eng = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE)
+        eng.set_phase([P])
+        if cols is not None:
+            eng.set_columns(*cols)
+        I1 = eng.first_order(Cc)
+        eng.reset(I1)
+        I = I1.clone()
+        J = eng.source(I1)
+        In = eng.sweeps(J, accumulate_into=I)
+        torch.cuda.synchronize()
+        out = (J[:, :N].cpu().numpy(), In[:, :N].cpu().numpy(), I[:, :N].cpu().numpy(), eng.ratios().cpu().numpy())
+        eng.close()
+        return out
+
+    Jf, Inf, If, rf = one_order()
+    zone_lo = M - w - 5
+    blocks = sos.mu_blocks(N, M, 4, zone_lo)
+    rmax = np.full_like(rf, -np.inf)
+    for c0, c1 in blocks:
+        Jb, Inb, Ib, rb = one_order((c0, c1))
+        assert np.array_equal(Jb[:, c0:c1], Jf[:, c0:c1])
+        assert np.array_equal(Inb[:, c0:c1], Inf[:, c0:c1])
+        assert np.array_equal(Ib[:, c0:c1], If[:, c0:c1])
+        rmax = np.maximum(rmax, rb)
+    assert np.array_equal(rmax, rf)
+    # a boundary inside the mu -> 0 zone is refused
+    eng = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE)
+    with pytest.raises(sos.SosError):
+        eng.set_columns(0, 500)
+    eng.close()
