@@ -190,3 +190,26 @@ def phase_matrices(name, nb_angles, mu, mu0, g=0.5):
         if name == "fwc":
             return pf.fwc(nb_angles, mu, mu0)
     raise ValueError(name)
+
+
+def critical_albedo_functions(tauStar_tot):
+    """The two functions of SOS_Aer_critical_albedo.py (:20-410) without its module-level script.
+
+    The file is a script that runs a whole sweep at import (:414-503); only the source above the
+    "MAIN SCRIPT" banner is exec'd.  SOS_Aer_radiative_forcing reads `tauStar_tot` as a module global
+    (:39), so it is planted in the namespace."""
+    load_reference()
+    path = os.path.join(REFERENCE_DIR, "SOS_Aer_critical_albedo.py")
+    with open(path, encoding="utf-8") as f:
+        lines = f.read().split("\n")
+    cut = next(i for i, l in enumerate(lines) if "MAIN SCRIPT" in l) - 1
+    src = "\n".join(lines[:cut])
+    ns = {"__name__": "sos_ref_critical", "tauStar_tot": tauStar_tot}
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(src, path, "exec"), ns)
+    def quiet(fn):
+        def call(*a, **k):
+            with contextlib.redirect_stdout(io.StringIO()):
+                return fn(*a, **k)
+        return call
+    return quiet(ns["SOS_Aer_radiative_forcing"]), quiet(ns["SOS_Aer_critical_albedo"])

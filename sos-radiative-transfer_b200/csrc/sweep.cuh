@@ -488,7 +488,7 @@ sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __r
       // a row can be both TOA and surface only if L == 1; not supported
       if (toa) g.state[s].ratio_toa = r;
       if (surf) g.state[s].ratio_surf = r;
-      if (nf || isinf(r)) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);
+      if (nf || r == INFINITY) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);  // -inf: no owned column
     }
   }
 }

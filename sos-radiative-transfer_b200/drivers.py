@@ -260,3 +260,66 @@ def SOS_Aer_radiative_forcing(tauStar_aer, dtau_aer, tauStar_atm, dtau_atm, P_ae
     if tauStar_aer == 0 or baseline == "none":
         return net
     return net - net  # the reference's recursion recomputes the identical solve (Q19)
+
+
+def SOS_Aer_critical_albedo(tauStar_aer, dtau_aer, tauStar_atm, dtau_atm, P_aer, P0_aer, P_atm, P0_atm, alb_atm, grd_alb,
+                            F0, mu, mu0, nb_angles, tau, nb_layers, idx_up, idx_down, tauStar_tot=None, device=None):
+    """Drop-in for SOS_Aer_critical_albedo.py:394-410: bisection on the aerosol single-scattering albedo.
+
+    As shipped the forcing it bisects on is identically zero (its baseline recursion repeats the same
+    solve, Q19), so the first tested value 0.5 is returned after one solve; that behaviour is reproduced.
+    `critical_albedo_sweep` below is the corrected, batched version.
+    """
+    lo, hi = 0.0, 1.0
+    while (hi - lo) > 0.1:
+        mid = (hi + lo) / 2
+        f = SOS_Aer_radiative_forcing(tauStar_aer, dtau_aer, tauStar_atm, dtau_atm, P_aer, P0_aer, mid, P_atm, P0_atm,
+                                      alb_atm, grd_alb, F0, mu, mu0, nb_angles, tau, nb_layers, idx_up, idx_down,
+                                      tauStar_tot=tauStar_tot, baseline="reference", device=device)
+        if abs(f) < 0.001:
+            return mid
+        if f > 0:
+            lo = mid
+        else:
+            hi = mid
+    return (hi + lo) / 2
+
+
+def critical_albedo_sweep(points: Sequence[Scenario], width: float = 0.1, forcing_tol: float = 1e-3, device=None,
+                          max_iter: int = 20):
+    """Critical aerosol single-scattering albedo for many sweep points at once (config 5's real caller).
+
+    For every point (a Scenario; its alb_aer is ignored) bisect omega_aer in [0, 1] on the radiative
+    forcing  dF = F_net_TOA(tau_aer, omega) - F_net_TOA(tau_aer = 0)  with a GENUINE aerosol-free
+    baseline (documented deviation from SOS_Aer_critical_albedo.py:385-389, whose baseline repeats the
+    same solve).  Stopping rule as in :397,402: interval width <= `width` or |dF| < `forcing_tol`.
+    Every bisection step is ONE batched GPU solve over all still-open points.
+    Returns (omega_critical, forcing_at_omega, n_solves).
+    """
+    pts = list(points)
+    base = solve_scenarios([replace(p, tauStar_aer=0.0, alb_aer=1.0) for p in pts], device=device)
+    f0 = np.array([r.toa_net_flux for r in base])
+    lo = np.zeros(len(pts))
+    hi = np.ones(len(pts))
+    omega = np.full(len(pts), 0.5)
+    forcing = np.full(len(pts), np.nan)
+    open_ = np.ones(len(pts), dtype=bool)
+    n_solves = len(pts)
+    for _ in range(max_iter):
+        open_ &= (hi - lo) > width
+        idx = np.nonzero(open_)[0]
+        if idx.size == 0:
+            break
+        mid = (hi[idx] + lo[idx]) / 2
+        res = solve_scenarios([replace(pts[i], alb_aer=float(m)) for i, m in zip(idx, mid)], device=device)
+        n_solves += idx.size
+        f = np.array([r.toa_net_flux for r in res]) - f0[idx]
+        omega[idx], forcing[idx] = mid, f
+        close = np.abs(f) < forcing_tol
+        open_[idx[close]] = False
+        up = (f > 0) & ~close
+        lo[idx[up]] = mid[up]
+        hi[idx[~up & ~close]] = mid[~up & ~close]
+    still = (hi - lo) <= width
+    final = np.where(np.isnan(forcing) | (still & (np.abs(np.nan_to_num(forcing)) >= forcing_tol)), (hi + lo) / 2, omega)
+    return final, forcing, n_solves

@@ -6,6 +6,7 @@ Only usable where /root/reference exists (the build container):
     python tests/golden/make_golden.py n1002      # ~10 min: M=501 grids, reduced L
     python tests/golden/make_golden.py default    # ~25 min: the 800 x 1002 scenarios
     python tests/golden/make_golden.py thick      # ~10 min: thick single-layer FWC
+    python tests/golden/make_golden.py forcing    # SOS_Aer_radiative_forcing / critical albedo, small grids
     python tests/golden/make_golden.py fwc_table  # the FWC data table (input data)
 
 Every array written here is an output of reference code (imported from where it
@@ -284,6 +285,37 @@ def stage_thick():
     print("thick done n =", n)
 
 
+def stage_forcing():
+    """SOS_Aer_radiative_forcing / SOS_Aer_critical_albedo (SOS_Aer_critical_albedo.py:20-410)."""
+    ref = rh.load_reference()
+    tp = ref["tau_profile"].tau_profile
+    import contextlib, io
+    rec = {}
+    cases = [("a", dict(L=60, M=41, mu0=0.5, ta=0.124, te=0.12, alb_aer=0.97, rho=0.15, z_up=25, z_down=17)),
+             ("b", dict(L=80, M=41, mu0=0.8, ta=0.2, te=0.4, alb_aer=0.8, rho=0.3, z_up=30, z_down=10))]
+    for tag, c in cases:
+        L, M, mu0 = c["L"], c["M"], c["mu0"]
+        mu = mu_grid(M)
+        P0a, Pa = rh.phase_matrices("rayleigh", M, mu, mu0)
+        P0h, Ph = rh.phase_matrices("hg", M, mu, mu0, 0.5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tau = tp(c["ta"], c["te"], 120, c["z_up"], c["z_down"], L)
+        z = np.linspace(120, 0, L)
+        iu, idn = int(np.argmin(np.abs(z - c["z_up"]))), int(np.argmin(np.abs(z - c["z_down"])))
+        dtau_aer = c["te"] / (idn + 1 - iu)
+        dtau_atm = c["ta"] / L
+        F0 = np.pi / mu0
+        forcing, critical = rh.critical_albedo_functions(c["ta"] + c["te"])
+        args = (dtau_aer, c["ta"], dtau_atm, Ph, P0h, c["alb_aer"], Pa, P0a, 1.0, c["rho"], F0, mu, mu0, M, tau, L, iu, idn)
+        rec[tag + "_toa_net_flux"] = np.array(forcing(0, *args))          # tauStar_aer == 0 -> returns the TOA net flux
+        rec[tag + "_forcing"] = np.array(forcing(c["te"], *args))          # Q19: identically 0
+        rec[tag + "_critical"] = np.array(critical(c["te"], dtau_aer, c["ta"], dtau_atm, Ph, P0h, Pa, P0a, 1.0, c["rho"],
+                                                   F0, mu, mu0, M, tau, L, iu, idn))
+        rec[tag + "_case"] = np.array(repr(c))
+        print(tag, rec[tag + "_toa_net_flux"], rec[tag + "_forcing"], rec[tag + "_critical"], flush=True)
+    np.savez_compressed(os.path.join(HERE, "forcing.npz"), **rec)
+
+
 def stage_fwc_table():
     fw = rh.load_reference()["fwc_data"]
     out = os.path.join(ROOT, "sos-radiative-transfer_b200", "data")
@@ -303,6 +335,8 @@ if __name__ == "__main__":
         stage_default(sys.argv[2:] or None)
     elif stage == "thick":
         stage_thick()
+    elif stage == "forcing":
+        stage_forcing()
     elif stage == "fwc_table":
         stage_fwc_table()
     else:

@@ -145,3 +145,21 @@ def test_thick_fwc_first_orders(golden):
         if f"order{n}_sub" in d.files:
             assert relmax(In[::50], d[f"order{n}_sub"]) < TOL, n
     assert np.allclose(ratios, d["ratios"][: len(ratios)], rtol=1e-11, atol=0)
+
+
+def test_toa_net_flux_vs_reference_forcing(golden):
+    """SOS_Aer_radiative_forcing (SOS_Aer_critical_albedo.py:20-389): TOA net flux of the solve; the
+    shipped forcing is identically 0 and the shipped bisection returns 0.5 (Q19)."""
+    d = golden("forcing.npz")
+    for tag in ("a", "b"):
+        c = ast.literal_eval(str(d[tag + "_case"]))
+        M = c["M"]
+        mu = so.mu_grid(M)
+        P0a, Pa = _phase("rayleigh", M, mu, c["mu0"])
+        P0h, Ph = _phase("hg", M, mu, c["mu0"], 0.5)
+        sc = so.Scenario(mu0=c["mu0"], nb_layers=c["L"], nb_angles=M, tauStar_atm=c["ta"], tauStar_aer=c["te"],
+                         grd_alb=c["rho"], alb_aer=c["alb_aer"], z_up=c["z_up"], z_down=c["z_down"])
+        res = so.solve(sc, P0a, Pa, P0h, Ph, method="recurrence", use_gemm=True)
+        got = so.toa_net_flux(res["I"], mu, M, res["tau"], c["mu0"], np.pi / c["mu0"], c["rho"])
+        assert abs(got - float(d[tag + "_toa_net_flux"])) < 1e-12 * abs(float(d[tag + "_toa_net_flux"]))
+        assert float(d[tag + "_forcing"]) == 0.0 and float(d[tag + "_critical"]) == 0.5
