@@ -320,7 +320,7 @@ def main():
         b = sos.BatchSolver(scen, device=dev)          # plan creation + H2D of tau, coefficients, P
         r = b.solve(poll_every=2)
         out = b.results(r, quadratures=True, fields=False)   # D2H: flux/diffusivity/heating profiles, n, TOA net flux
-        h2d = (b.tau.nbytes + b.Ccoef.nbytes + len(b.engine._A) * N * N * 8 + b.mu.nbytes)
+        h2d = (b.tau.nbytes + b.Ccoef.nbytes + b.engine.h2d_phase_bytes + b.mu.nbytes)   # phase operands are uploaded once and stay resident
         d2h = sum(5 * o.flux_up.nbytes for o in out) + 40 * len(out)
         cnt = b.engine.launches
         b.engine.close()

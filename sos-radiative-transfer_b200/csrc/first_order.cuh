@@ -21,52 +21,72 @@ struct Col {
   bool down, special;
 };
 
-// value of the closed form at optical depth tt for region parameters (carry, tau_b, tau_d, tau_s)
-__device__ __forceinline__ double i1_value(const Col& c, bool mix, double tt, double carry, double tau_b, double tau_d,
-                                           double tau_s) {
+// Region-dependent constants of the closed form (column independent).
+struct RegionK {
+  double tau_d, tau_s;  // tau_b == tau_d for every region
+  double ed;            // exp(-tau_d / mu0)
+  double esr;           // exp(-(T - tau_s) / mu0)
+};
+__device__ __forceinline__ RegionK region_consts(double tau_d, double tau_s, double T, double mu0) {
+  RegionK r;
+  r.tau_d = tau_d; r.tau_s = tau_s;
+  r.ed = exp(-tau_d / mu0);
+  r.esr = exp(-(T - tau_s) / mu0);
+  return r;
+}
+
+// value of the closed form at optical depth tt; e0 = exp(-tt/mu0) and es = exp(-(T-tt)/mu0) depend on
+// the row only and are shared by all columns (2 column-dependent exps per element instead of 7)
+__device__ __forceinline__ double i1_value(const Col& c, bool mix, double tt, double e0, double es, double carry,
+                                           const RegionK& rk) {
   const double Cm = mix ? c.Cm_mix : c.Cm_atm;
   const double Cr = mix ? c.Cmir_mix : c.Cmir_atm;
-  const double e0 = exp(-tt / c.mu0);
-  const double es = exp(-(c.T - tt) / c.mu0);
   double direct, surf;
+  double xd = 0.0;
+  bool have_xd = false;
   if (c.down && c.special) {  // |mu + mu0| < 1e-4 (:133-140)
-    direct = Cm * c.F0q * e0 * (tt - tau_d) / c.mu0;
+    direct = Cm * c.F0q * e0 * (tt - rk.tau_d) / c.mu0;
   } else {
-    direct = (c.mu0 / (c.mu0 + c.mu)) * Cm * c.F0q * (e0 - exp(-tau_d / c.mu0) * exp((tt - tau_d) / c.mu));
+    xd = exp((tt - rk.tau_d) / c.mu);
+    have_xd = true;
+    direct = (c.mu0 / (c.mu0 + c.mu)) * Cm * c.F0q * (e0 - rk.ed * xd);
   }
   if (!c.down && c.special) {  // |mu - mu0| < 1e-4 (:225-233)
-    surf = Cr * c.Sq * es * (tau_s - tt) / c.mu0;
+    surf = Cr * c.Sq * es * (rk.tau_s - tt) / c.mu0;
   } else {
-    surf = (c.mu0 / (c.mu0 - c.mu)) * Cr * c.Sq * (es - exp(-(c.T - tau_s) / c.mu0) * exp((tt - tau_s) / c.mu));
+    surf = (c.mu0 / (c.mu0 - c.mu)) * Cr * c.Sq * (es - rk.esr * exp((tt - rk.tau_s) / c.mu));
   }
   double v = direct + surf;
-  if (carry != 0.0) v = carry * exp((tt - tau_b) / c.mu) + v;
+  if (carry != 0.0) {
+    if (!have_xd) xd = exp((tt - rk.tau_d) / c.mu);
+    v = carry * xd + v;
+  }
   return v;
 }
 
-// downward column value at row t (3 regions), chaining the carries from the top
-__device__ double i1_down(const GridDev& g, const Col& c, const double* __restrict__ tau, int t, int* cached_region,
-                          double* cached_carry) {
-  // region of row t
+__device__ __forceinline__ int region_of(const GridDev& g, int t) {
   int k = 0;
   while (k + 1 < g.nreg && t >= g.rstart[k + 1]) ++k;
+  return k;
+}
+
+// downward regions: region 0 starts at the top (tau_d = tau_s = 0, no carry); region k >= 1 carries row
+// rstart[k]-1 with tau_d = tau[rstart[k]-1], tau_s = tau[rstart[k]]   (:113-198)
+__device__ __forceinline__ RegionK down_region(const GridDev& g, const double* __restrict__ tau, int k, double T, double mu0) {
+  if (k == 0) return region_consts(0.0, 0.0, T, mu0);
+  return region_consts(tau[g.rstart[k] - 1], tau[g.rstart[k]], T, mu0);
+}
+
+// carry into region k of a downward column = value at row rstart[k]-1, chained from the top
+__device__ double down_carry(const GridDev& g, const Col& c, const double* __restrict__ tau, int k, double T) {
   double carry = 0.0;
-  if (*cached_region == k) {
-    carry = *cached_carry;
-  } else {
-    for (int r = 1; r <= k; ++r) {
-      const int cb = g.rstart[r] - 1;  // carry row of region r
-      const int rp = r - 1;
-      const double tb = rp == 0 ? 0.0 : tau[g.rstart[rp] - 1];
-      const double ts = rp == 0 ? 0.0 : tau[g.rstart[rp]];
-      carry = i1_value(c, rp == 1, tau[cb], carry, tb, tb, ts);
-    }
-    *cached_region = k;
-    *cached_carry = carry;
+  for (int r = 1; r <= k; ++r) {
+    const int cb = g.rstart[r] - 1;  // carry row of region r, lies in region r-1
+    const RegionK rk = down_region(g, tau, r - 1, T, c.mu0);
+    const double tt = tau[cb];
+    carry = i1_value(c, (r - 1) == 1, tt, exp(-tt / c.mu0), exp(-(T - tt) / c.mu0), carry, rk);
   }
-  const double tb = k == 0 ? 0.0 : tau[g.rstart[k] - 1];
-  const double ts = k == 0 ? 0.0 : tau[g.rstart[k]];
-  return i1_value(c, k == 1, tau[t], carry, tb, tb, ts);
+  return carry;
 }
 
 __global__ void __launch_bounds__(128)
@@ -74,7 +94,6 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
                            int rows_per_block) {
   const int s = blockIdx.z;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= g.N) return;
   const int L = g.L, M = g.M, N = g.N, ld = g.ld;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
   const sos_scenario sc = g.scen[s];
@@ -90,6 +109,16 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
   const double q = 1.0 / (4.0 * PI);
   const double S = F0 * sc.grd_alb * exp(-T / mu0);
 
+  // row-only exponentials, shared by the 128 columns of the block
+  __shared__ double sh_e0[64], sh_es[64];
+  if (threadIdx.x < tb - ta) {
+    const double tt = tau[ta + threadIdx.x];
+    sh_e0[threadIdx.x] = exp(-tt / mu0);
+    sh_es[threadIdx.x] = exp(-(T - tt) / mu0);
+  }
+  __syncthreads();
+  if (m >= g.N) return;
+
   if (m == M - 1 || m == M) {
     // mu = 0-: C[M-1] F0/(4pi) e^{-tau/mu0} + C[M] S/(4pi) e^{-(T-tau)/mu0}   (:124-131); mu = 0+ mirrored (:217-224)
     const int mir = N - 1 - m;
@@ -98,8 +127,8 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
       while (k + 1 < g.nreg && t >= g.rstart[k + 1]) ++k;
       const double* C = (k == 1) ? Cmix : Catm;
       const double tt = tau[t];
-      out[static_cast<size_t>(t) * ld + m] = (mu0 / (mu0 + g.mu[m])) * C[m] * (F0 * q) * exp(-tt / mu0) +
-                                             (mu0 / (mu0 - g.mu[m])) * C[mir] * (S * q) * exp(-(T - tt) / mu0);
+      out[static_cast<size_t>(t) * ld + m] = (mu0 / (mu0 + g.mu[m])) * C[m] * (F0 * q) * sh_e0[t - ta] +
+                                             (mu0 / (mu0 - g.mu[m])) * C[mir] * (S * q) * sh_es[t - ta];
     }
     return;
   }
@@ -112,8 +141,14 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
     c.special = fabs(c.mu + mu0) < SOS_MU0_TOLERANCE;
     c.Cm_atm = Catm[m]; c.Cmir_atm = Catm[N - 1 - m];
     c.Cm_mix = Cmix[m]; c.Cmir_mix = Cmix[N - 1 - m];
-    int creg = -1; double ccar = 0.0;
-    for (int t = ta; t < tb; ++t) out[static_cast<size_t>(t) * ld + m] = i1_down(g, c, tau, t, &creg, &ccar);
+    int kcur = -1;
+    double carry = 0.0;
+    RegionK rk;
+    for (int t = ta; t < tb; ++t) {
+      const int k = region_of(g, t);
+      if (k != kcur) { kcur = k; carry = down_carry(g, c, tau, k, T); rk = down_region(g, tau, k, T, mu0); }
+      out[static_cast<size_t>(t) * ld + m] = i1_value(c, k == 1, tau[t], sh_e0[t - ta], sh_es[t - ta], carry, rk);
+    }
     return;
   }
 
@@ -126,8 +161,13 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
   d.special = fabs(d.mu + mu0) < SOS_MU0_TOLERANCE;
   d.Cm_atm = Catm[mir]; d.Cmir_atm = Catm[m];
   d.Cm_mix = Cmix[mir]; d.Cmir_mix = Cmix[m];
-  int creg = -1; double ccar = 0.0;
-  const double surf_down = i1_down(g, d, tau, L - 1, &creg, &ccar);
+  const int R = g.nreg;
+  double surf_down;
+  {
+    const double tt = tau[L - 1];
+    surf_down = i1_value(d, (R - 1) == 1, tt, exp(-tt / mu0), exp(-(T - tt) / mu0), down_carry(g, d, tau, R - 1, T),
+                         down_region(g, tau, R - 1, T, mu0));
+  }
 
   c.mu = g.mu[m];
   c.down = false;
@@ -135,25 +175,21 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
   c.Cm_atm = Catm[m]; c.Cmir_atm = Catm[mir];
   c.Cm_mix = Cmix[m]; c.Cmir_mix = Cmix[mir];
 
-  // carries of the upward chain, bottom region first:
-  //   last region : carry = rho * I1[L-1, mirror], tau_b = tau_d = tau[L-1], tau_s = T   (:206-216)
-  //   region k    : carry = I1[rstart[k+1], m],    tau_b = tau_d = tau[rstart[k+1]], tau_s = tau[rstart[k+1]-1]
-  const int R = g.nreg;
+  // upward regions, bottom first:
+  //   last region : carry = rho * I1[L-1, mirror], tau_d = tau[L-1], tau_s = T                      (:206-216)
+  //   region k    : carry = I1[rstart[k+1], m],    tau_d = tau[rstart[k+1]], tau_s = tau[rstart[k+1]-1]
+  RegionK rks[3];
   double carry_k[3];
+  for (int k = 0; k < R; ++k)
+    rks[k] = (k == R - 1) ? region_consts(tau[L - 1], T, T, mu0) : region_consts(tau[g.rstart[k + 1]], tau[g.rstart[k + 1] - 1], T, mu0);
   carry_k[R - 1] = sc.grd_alb * surf_down;
   for (int k = R - 2; k >= 0; --k) {
-    const int row = g.rstart[k + 1];  // first row of the region below = carry row
-    const int kb = k + 1;
-    const double tbb = (kb == R - 1) ? tau[L - 1] : tau[g.rstart[kb + 1]];
-    const double tss = (kb == R - 1) ? T : tau[g.rstart[kb + 1] - 1];
-    carry_k[k] = i1_value(c, kb == 1, tau[row], carry_k[kb], tbb, tbb, tss);
+    const double tt = tau[g.rstart[k + 1]];  // first row of the region below = carry row
+    carry_k[k] = i1_value(c, (k + 1) == 1, tt, exp(-tt / mu0), exp(-(T - tt) / mu0), carry_k[k + 1], rks[k + 1]);
   }
   for (int t = ta; t < tb; ++t) {
-    int k = 0;
-    while (k + 1 < R && t >= g.rstart[k + 1]) ++k;
-    const double tbb = (k == R - 1) ? tau[L - 1] : tau[g.rstart[k + 1]];
-    const double tss = (k == R - 1) ? T : tau[g.rstart[k + 1] - 1];
-    out[static_cast<size_t>(t) * ld + m] = i1_value(c, k == 1, tau[t], carry_k[k], tbb, tbb, tss);
+    const int k = region_of(g, t);
+    out[static_cast<size_t>(t) * ld + m] = i1_value(c, k == 1, tau[t], sh_e0[t - ta], sh_es[t - ta], carry_k[k], rks[k]);
   }
 }
 

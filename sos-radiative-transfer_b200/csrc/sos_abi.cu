@@ -111,12 +111,34 @@ struct sos_plan {
 
 namespace {
 
+void pool_setup() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ULL;  // keep freed blocks cached instead of returning them to the OS
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done = true;
+}
+
+// pinned poll buffers are recycled across plans (cudaMallocHost is slow)
+std::vector<int*>& pinned_free_list() {
+  static std::vector<int*> v;
+  return v;
+}
+constexpr int kPollSlots = 4096;
+
 template <typename T>
 int dev_alloc(sos_plan* p, T** out, size_t count) {
+  // stream-ordered pool allocation on the legacy default stream: plans are created and destroyed once
+  // per batch in the end-to-end path, and cudaMalloc/cudaFree would each cost a device-wide sync
   void* ptr = nullptr;
-  cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(T));
+  pool_setup();
+  cudaError_t e = cudaMallocAsync(&ptr, std::max<size_t>(count, 1) * sizeof(T), nullptr);
   if (e != cudaSuccess) {
-    g_last_cuda_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    g_last_cuda_error = std::string("cudaMallocAsync: ") + cudaGetErrorString(e);
     return SOS_ERR_NOMEM;
   }
   p->allocs.push_back(ptr);
@@ -351,7 +373,11 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   {
     cudaError_t e = cudaMemset(p->d_carryD, 0, nagg * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(p->d_carryU, 0, nagg * sizeof(double));
-    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&p->h_poll), 4096 * sizeof(int));
+    if (e == cudaSuccess) {
+      auto& fl = pinned_free_list();
+      if (!fl.empty()) { p->h_poll = fl.back(); fl.pop_back(); }
+      else e = cudaMallocHost(reinterpret_cast<void**>(&p->h_poll), kPollSlots * sizeof(int));
+    }
     if (e != cudaSuccess) { g_last_cuda_error = cudaGetErrorString(e); sos_plan_destroy(p); return SOS_ERR_CUDA; }
   }
 
@@ -444,8 +470,9 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
 int sos_plan_destroy(sos_plan* p) {
   if (!p) return SOS_OK;
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
-  for (void* a : p->allocs) cudaFree(a);
-  if (p->h_poll) cudaFreeHost(p->h_poll);
+  cudaDeviceSynchronize();  // nothing of this plan may still be running on any stream
+  for (void* a : p->allocs) cudaFreeAsync(a, nullptr);
+  if (p->h_poll) pinned_free_list().push_back(p->h_poll);
   delete p;
   return SOS_OK;
 }
@@ -654,7 +681,7 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
   // is copied to a pinned slot; the host looks at the newest slot that has already landed.  Kernels
   // of converged scenarios exit immediately, so the few orders enqueued past convergence cost only
   // their launch latency.
-  const int nslots = 4096;
+  const int nslots = kPollSlots;
   volatile int* poll = p->h_poll;
   for (int i = 0; i < nslots; ++i) poll[i] = -1;
   int rc = SOS_OK;

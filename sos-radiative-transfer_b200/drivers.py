@@ -115,7 +115,7 @@ class BatchSolver:
         tau = np.empty((S, L))
         coefs = []
         Ccoef = np.empty((S, 2, self.N))
-        mats, mat_index = [], {}
+        mats, mat_index, mat_keys = [], {}, []
         self.z = None
         for i, sc in enumerate(scenarios):
             z, _, _ = G.aerosol_rows(sc.z0, sc.z_up, sc.z_down, L)
@@ -128,6 +128,7 @@ class BatchSolver:
                 if k not in mat_index:
                     mat_index[k] = len(mats)
                     mats.append(P)
+                    mat_keys.append(k if k[0] != "array" else None)  # analytic families are immutable: cache on device
             # global mixing weights (SOS_Aer_main_specular.py:52-53; note dtau_atm = tauStar_atm / L, Q9)
             dtau_aer = sc.tauStar_aer / (self.idx_down + 1 - self.idx_up)
             dtau_atm = sc.tauStar_atm / L
@@ -147,7 +148,7 @@ class BatchSolver:
         surface = {"specular": _lib.SURFACE_SPECULAR, "lambert": _lib.SURFACE_LAMBERT}[surf]
         self.engine = SosEngine(self.mu, tau, coefs, [0, self.idx_up, self.idx_down + 1, L], surface,
                                 device=device, chunk_rows=chunk_rows)
-        self.engine.set_phase(mats)
+        self.engine.set_phase(mats, keys=mat_keys)
         self.I1 = None
 
     def first_order(self):

@@ -25,6 +25,7 @@ def _align(n: int, a: int) -> int:
 
 
 _PINNED = {}
+_OPERANDS = {}  # device-resident contraction operands shared between engines (see SosEngine.set_phase)
 
 
 def _pinned_pair(elems: int):
@@ -177,23 +178,38 @@ class SosEngine:
         return int(self.lib.sos_launch_count(self._plan))
 
     # ------------------------------------------------------------------ phase operands
-    def set_phase(self, matrices: Sequence):
-        """Upload the phase matrices P (N, N) once and build A[k,m] = w_k/4 P[m, N-1-k] on device."""
+    def set_phase(self, matrices: Sequence, keys: Optional[Sequence] = None):
+        """Upload the phase matrices P (N, N) once and build A[k,m] = w_k/4 P[m, N-1-k] on device.
+
+        keys: optional hashable identity per matrix (e.g. ("hg", 0.5, M)); operands built for a key are
+        kept on the device and shared by later engines of the same grid ("uploaded once", north_star).
+        Only pass keys for matrices that are never modified in place."""
         self._A = []
         lda = self.ld
+        self.h2d_phase_bytes = 0
         with torch.cuda.device(self.device):
-            for P in matrices:
+            for i, P in enumerate(matrices):
+                ck = None
+                if keys is not None and keys[i] is not None:
+                    ck = (keys[i], self.device.index, self.N, lda, self.mu.tobytes())
+                    hit = _OPERANDS.get(ck)
+                    if hit is not None:
+                        self._A.append(hit)
+                        continue
                 if isinstance(P, torch.Tensor):
                     Pd = P.to(self.device, torch.float64).contiguous()
                 else:
                     Pd = torch.as_tensor(np.ascontiguousarray(P, dtype=np.float64)).to(self.device)
+                    self.h2d_phase_bytes += Pd.numel() * 8
                 if Pd.shape != (self.N, self.N):
                     raise ValueError(f"phase matrix must be ({self.N}, {self.N})")
                 A = torch.zeros((self.N, lda), dtype=torch.float64, device=self.device)
                 _lib.check(self.lib.sos_build_contraction(self._plan, Pd.data_ptr(), self.N, A.data_ptr(), lda, self._stream),
                            "sos_build_contraction")
+                torch.cuda.current_stream(self.device).synchronize()  # Pd may be freed after this
+                if ck is not None:
+                    _OPERANDS[ck] = A
                 self._A.append(A)
-            torch.cuda.current_stream(self.device).synchronize()  # Pd may be freed after this
             ptrs = (C.c_void_p * len(self._A))(*[a.data_ptr() for a in self._A])
             _lib.check(self.lib.sos_plan_set_phase(self._plan, ptrs, len(self._A), lda), "sos_plan_set_phase")
 
