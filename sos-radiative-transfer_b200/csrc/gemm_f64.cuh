@@ -121,7 +121,10 @@ struct Cfg {
   // for LAUNCH_REGS per thread (what __launch_bounds__(THREADS, 1) allows), the producer warpgroup
   // drops to REGS_PRODUCER and the consumer warpgroups share what that frees.  Asking for more than
   // the launch pool holds would block forever.
-  static constexpr int LAUNCH_REGS = (65536 / THREADS) / 8 * 8 > 255 ? 248 : (65536 / THREADS) / 8 * 8;
+  // (capping the kernel at half of the register file so that another stream's HBM-bound sweeps can be
+  //  co-resident was tried: the kernels co-run but contend for L2/HBM, 5 % net gain at best -- not shipped)
+  static constexpr int MIN_CTAS = 1;
+  static constexpr int LAUNCH_REGS = (65536 / (THREADS * MIN_CTAS)) / 8 * 8 > 255 ? 248 : (65536 / (THREADS * MIN_CTAS)) / 8 * 8;
   static constexpr int REGS_PRODUCER = 40;
   static constexpr int REGS_CONSUMER_RAW = ((THREADS * LAUNCH_REGS - 128 * REGS_PRODUCER) / (32 * CONSUMER_WARPS)) / 8 * 8;
   static constexpr int REGS_CONSUMER = REGS_CONSUMER_RAW > 232 ? 232 : REGS_CONSUMER_RAW;
@@ -156,7 +159,7 @@ __device__ __forceinline__ int find_group(const TilePlan* plan, int rt) {
 }
 
 template <int WM, int WN, int MB>
-__global__ void __launch_bounds__(Cfg<WM, WN, MB>::THREADS, 1)
+__global__ void __launch_bounds__(Cfg<WM, WN, MB>::THREADS, Cfg<WM, WN, MB>::MIN_CTAS)
 jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<WM, WN, MB>;
   extern __shared__ uint8_t smem_raw[];

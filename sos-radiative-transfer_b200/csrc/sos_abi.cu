@@ -252,11 +252,14 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
 
   int dev = 0;
   SOS_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  SOS_CUDA(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) {
-    g_last_cuda_error = "libsos_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
-                        std::to_string(prop.minor);
+  // (cudaGetDeviceProperties costs milliseconds; two attribute queries do)
+  int cc_major = 0, cc_minor = 0, n_sms = 0;
+  SOS_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  SOS_CUDA(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  SOS_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major != 10) {
+    g_last_cuda_error = "libsos_b200 is built for sm_100a only; device is sm_" + std::to_string(cc_major) +
+                        std::to_string(cc_minor);
     return SOS_ERR_UNSUPPORTED;
   }
 
@@ -264,7 +267,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   if (!p) return SOS_ERR_NOMEM;
   p->grid = *grid;
   p->N = N;
-  p->n_sms = prop.multiProcessorCount;
+  p->n_sms = n_sms;
   p->launches = 0;
   p->scen_h.assign(scen_h, scen_h + S);
   std::memset(&p->gp, 0, sizeof(p->gp));
