@@ -121,6 +121,27 @@ int sos_first_order(sos_plan* plan, const double* C_h, double* I1_d, void* strea
 /* Jn_NumInt (SOS_Aer_I1_In.py:62-74) / SOS_Aer_main_specular.py:315-323 as one FP64 GEMM. */
 int sos_source(sos_plan* plan, const double* In1_d, double* J_d, void* stream);
 
+/* The same contraction restricted to layers [row0, row1) (row0 a multiple of 64; single-scenario,
+ * single-region plans only): lets a mu-sharded solve start the contraction of the rows whose I_{n-1}
+ * has already been all-gathered while the remaining rows are still in flight over NVLink. */
+int sos_source_rows(sos_plan* plan, const double* In1_d, double* J_d, int row0, int row1, void* stream);
+
+/* Fused all-gather + contraction for mu-block sharding: In1_peers_d[r] is the SAME field layout
+ * [S*L][ld] in the memory of the GPU that owns mu columns [peer_col[r], peer_col[r+1]) (peer memory
+ * mapped with sos_ipc_open, or this GPU's own buffer); the kernel fetches every k-range of I_{n-1}
+ * straight from its owner by TMA over NVLink, so no separate all-gather is needed.  The caller
+ * guarantees (e.g. with the MAX all-reduce of the convergence ratios) that every owner has finished
+ * writing its columns.  peer_col: [n_peers + 1], multiples of 16, peer_col[0] = 0, peer_col[n_peers] = N. */
+int sos_source_peers(sos_plan* plan, const double* const* In1_peers_d, int n_peers, const int* peer_col, double* J_d,
+                     void* stream);
+/* CUDA IPC plumbing for the above (one process per GPU): allocate a shareable device buffer and export
+ * its 64-byte handle / map a peer's buffer / unmap / free; plus a stream-ordered device copy. */
+int sos_ipc_alloc(size_t bytes, void** ptr_d, unsigned char* handle64);
+int sos_ipc_open(const unsigned char* handle64, void** ptr_d);
+int sos_ipc_close(void* ptr_d);
+int sos_ipc_free(void* ptr_d);
+int sos_copy_d2d(void* dst_d, const void* src_d, size_t bytes, void* stream);
+
 /* In_NumInt (SOS_Aer_I1_In.py:77-130) / SOS_Aer_main_specular.py:327-449: down scan, mu->0
  * columns, extrapolation, surface coupling, up scan, blend.  If I_d != NULL also I += I_n and
  * the convergence ratios of :309 are refreshed (SOS_Aer_main_specular.py:454-456). */

@@ -75,6 +75,13 @@ SIGNATURES = {
     "sos_plan_set_phase": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int]),
     "sos_first_order": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "sos_source_rows": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "sos_source_peers": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.POINTER(C.c_int), _vp, _vp]),
+    "sos_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), C.c_char_p]),
+    "sos_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "sos_ipc_close": (C.c_int, [_vp]),
+    "sos_ipc_free": (C.c_int, [_vp]),
+    "sos_copy_d2d": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "sos_sweeps": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "sos_converge": (C.c_int, [_vp, C.c_int, _vp]),
     "sos_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(sos_result), _vp]),

@@ -13,6 +13,7 @@
 
 #define SOS_MAX_PHASE 16
 #define SOS_MAX_GROUPS 48
+#define SOS_MAX_PEERS 8
 
 // Per-scenario mutable state (device).
 struct ScenState {

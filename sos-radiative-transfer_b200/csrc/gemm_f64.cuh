@@ -78,6 +78,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 struct GemmParams {
   CUtensorMap map_I;                 // [rows_total][N] (stride ld), box {BK, SEG_ROWS}, 128B swizzle
+  CUtensorMap map_peer[SOS_MAX_PEERS];  // same field on every mu-block owner (peer GPU memory over NVLink)
+  int n_peers;                       // 0: single-GPU operand (map_I); G: columns [peer_col[r], peer_col[r+1]) live on peer r
+  int peer_col[SOS_MAX_PEERS + 1];
   CUtensorMap map_A[SOS_MAX_PHASE];  // [N][N] (stride lda), box {BN+8, BK}, no swizzle
   const TilePlan* plan;              // device, rebuilt after every convergence update
   int* work_counter;                 // device, zeroed before every launch
@@ -87,6 +90,8 @@ struct GemmParams {
   int nseg[2];
   int n_col_tiles;                   // column tiles this plan computes ...
   int ct0;                           // ... starting at this one (mu-block sharding)
+  int seg_begin, seg_end;            // restrict every group to these segments of its list (row-chunked launches
+                                     // that overlap the all-gather of the other chunks); [0, INT_MAX) = all
   int L, N, ld;
   double* J;
   const sos_scenario* scen;
@@ -144,7 +149,7 @@ __device__ __forceinline__ SegRef seg_lookup(const GemmParams& p, int cls, int n
   SegRef r;
   const int nseg = p.nseg[cls];
   const int rank = q / nseg;
-  if (rank >= nactive) { r.scen = -1; r.row = 0; r.valid = 0; return r; }
+  if (rank >= nactive || q >= p.seg_end) { r.scen = -1; r.row = 0; r.valid = 0; return r; }
   const int j = q - rank * nseg;
   r.scen = p.active_list[list_off + rank];
   r.row = r.scen * p.L + p.seg_row[cls][j];
@@ -185,7 +190,11 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
 
   const TilePlan* plan = p.plan;
   const int ksteps = (p.N + BK - 1) / BK;
-  const int n_tiles = plan->n_row_tiles * p.n_col_tiles;
+  // row-restricted launch (single group only): tiles cover segments [seg_begin, seg_end)
+  const bool restricted = p.seg_begin > 0 || p.seg_end != 0x7fffffff;
+  const int n_row_tiles = restricted ? (min(p.seg_end, plan->group_nactive[0] * p.nseg[plan->group_cls[0]]) - p.seg_begin + C::SEGS - 1) / C::SEGS
+                                     : plan->n_row_tiles;
+  const int n_tiles = max(n_row_tiles, 0) * p.n_col_tiles;
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp >= C::CONSUMER_WARPS) {
@@ -210,9 +219,9 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
       }
       const int rt = tile / p.n_col_tiles;
       const int ct = p.ct0 + tile - rt * p.n_col_tiles;
-      const int g = find_group(plan, rt);
+      const int g = restricted ? 0 : find_group(plan, rt);
       const int cls = plan->group_cls[g];
-      const int lt = rt - plan->group_tile_start[g];
+      const int lt = restricted ? rt + p.seg_begin / C::SEGS : rt - plan->group_tile_start[g];
       // lanes 0..SEGS-1 own one I segment each, lane SEGS owns the operand tile
       SegRef sr;
       sr.scen = -1; sr.row = 0; sr.valid = 0;
@@ -239,14 +248,22 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
       const int passes = cls == 1 ? 2 : 1;
       for (int pass = 0; pass < passes; ++pass) {
         const CUtensorMap* mapA = &p.map_A[pass == 0 ? plan->group_phaseA[g] : plan->group_phaseB[g]];
+        int owner = 0;
         for (int ks = 0; ks < ksteps; ++ks) {
+          // fused all-gather: the k-range of this step is fetched straight from the GPU that owns those mu
+          // columns (TMA over NVLink peer memory), so the exchange overlaps the DMMA work tile by tile
+          const CUtensorMap* mapI = &p.map_I;
+          if (p.n_peers > 0) {
+            while (owner + 1 < p.n_peers && ks * BK >= p.peer_col[owner + 1]) ++owner;
+            mapI = &p.map_peer[owner];
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t dst = smem_base + stage * C::STAGE_BYTES;
           if (lane == 0) {
             if (pass == 0 && ks == 0) tile_ring[stage] = tile;
             mbar_expect_tx(&full_bar[stage], tx);
           }
-          if (sr.valid > 0) tma_load_2d(dst + lane * (SEG_ROWS * BK * 8), &p.map_I, &full_bar[stage], ks * BK, sr.row);
+          if (sr.valid > 0) tma_load_2d(dst + lane * (SEG_ROWS * BK * 8), mapI, &full_bar[stage], ks * BK, sr.row);
           if (lane == C::SEGS) tma_load_2d(dst + C::A_BYTES, mapA, &full_bar[stage], ct * C::BN, ks * BK);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }

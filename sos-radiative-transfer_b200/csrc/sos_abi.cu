@@ -571,7 +571,67 @@ int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) 
   return launch_check(p);
 }
 
+static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_begin, int seg_end, void* stream,
+                       const double* const* peers = nullptr, int n_peers = 0, const int* peer_col = nullptr);
+
 int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
+  return source_impl(p, In1_d, J_d, 0, 0x7fffffff, stream);
+}
+
+int sos_source_rows(sos_plan* p, const double* In1_d, double* J_d, int row0, int row1, void* stream) {
+  if (!p) return SOS_ERR_INVALID;
+  // row-chunked contraction: single scenario, single region (the mu-sharded large grid), 64-row granularity
+  if (p->dev.S != 1 || p->dev.nreg != 1) return SOS_ERR_UNSUPPORTED;
+  if (row0 < 0 || row1 > p->dev.L || row0 >= row1 || (row0 % p->gemm_bm) != 0) return SOS_ERR_INVALID;
+  const int seg0 = row0 / sosgemm::SEG_ROWS;
+  const int seg1 = (row1 + sosgemm::SEG_ROWS - 1) / sosgemm::SEG_ROWS;
+  return source_impl(p, In1_d, J_d, seg0, seg1, stream);
+}
+
+int sos_source_peers(sos_plan* p, const double* const* In1_peers_d, int n_peers, const int* peer_col, double* J_d, void* stream) {
+  if (!p || !In1_peers_d || !peer_col || n_peers < 1 || n_peers > SOS_MAX_PEERS) return SOS_ERR_INVALID;
+  if (peer_col[0] != 0 || peer_col[n_peers] != p->dev.N) return SOS_ERR_INVALID;
+  for (int r = 0; r < n_peers; ++r)
+    if (!In1_peers_d[r] || peer_col[r + 1] <= peer_col[r] || (peer_col[r] % sosgemm::BK) != 0) return SOS_ERR_INVALID;
+  return source_impl(p, In1_peers_d[0], J_d, 0, 0x7fffffff, stream, In1_peers_d, n_peers, peer_col);
+}
+
+// ---- CUDA IPC helpers: buffers that peer ranks (one process per GPU) map into their address space ----
+int sos_ipc_alloc(size_t bytes, void** ptr_d, unsigned char* handle64) {
+  if (!ptr_d || !handle64 || bytes == 0) return SOS_ERR_INVALID;
+  SOS_CUDA(cudaMalloc(ptr_d, bytes));
+  SOS_CUDA(cudaMemset(*ptr_d, 0, bytes));
+  cudaIpcMemHandle_t h;
+  SOS_CUDA(cudaIpcGetMemHandle(&h, *ptr_d));
+  static_assert(sizeof(h) == 64, "IPC handle size");
+  std::memcpy(handle64, &h, 64);
+  return SOS_OK;
+}
+int sos_ipc_open(const unsigned char* handle64, void** ptr_d) {
+  if (!ptr_d || !handle64) return SOS_ERR_INVALID;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  SOS_CUDA(cudaIpcOpenMemHandle(ptr_d, h, cudaIpcMemLazyEnablePeerAccess));
+  return SOS_OK;
+}
+int sos_ipc_close(void* ptr_d) {
+  if (!ptr_d) return SOS_OK;
+  SOS_CUDA(cudaIpcCloseMemHandle(ptr_d));
+  return SOS_OK;
+}
+int sos_ipc_free(void* ptr_d) {
+  if (!ptr_d) return SOS_OK;
+  SOS_CUDA(cudaFree(ptr_d));
+  return SOS_OK;
+}
+int sos_copy_d2d(void* dst_d, const void* src_d, size_t bytes, void* stream) {
+  if (!dst_d || !src_d) return SOS_ERR_INVALID;
+  SOS_CUDA(cudaMemcpyAsync(dst_d, src_d, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return SOS_OK;
+}
+
+static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_begin, int seg_end, void* stream,
+                       const double* const* peers, int n_peers, const int* peer_col) {
   if (!p || !In1_d || !J_d) return SOS_ERR_INVALID;
   if (!p->maps_A_ready) return SOS_ERR_STATE;
   if ((reinterpret_cast<uintptr_t>(In1_d) & 15) || (reinterpret_cast<uintptr_t>(J_d) & 15)) return SOS_ERR_INVALID;
@@ -586,11 +646,30 @@ int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
     it = p->map_cache.emplace(In1_d, m).first;
   }
   p->gp.map_I = it->second;
+  p->gp.n_peers = 0;
+  if (peers) {
+    for (int r = 0; r < n_peers; ++r) {
+      auto ip = p->map_cache.find(peers[r]);
+      if (ip == p->map_cache.end()) {
+        CUtensorMap m;
+        int rr = encode_2d(&m, peers[r], g.N, static_cast<uint64_t>(g.S) * g.L, g.ld, sosgemm::BK, sosgemm::SEG_ROWS,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rr) return rr;
+        ip = p->map_cache.emplace(peers[r], m).first;
+      }
+      p->gp.map_peer[r] = ip->second;
+      p->gp.peer_col[r] = peer_col[r];
+    }
+    p->gp.peer_col[n_peers] = peer_col[n_peers];
+    p->gp.n_peers = n_peers;
+  }
   p->gp.plan = p->d_tile_plan;
   p->gp.work_counter = p->d_work_counter;
   p->gp.active_list = p->d_active_list;
   p->gp.ct0 = g.col0 / 128;
   p->gp.n_col_tiles = (g.col1 + 127) / 128 - p->gp.ct0;
+  p->gp.seg_begin = seg_begin;
+  p->gp.seg_end = seg_end;
   p->gp.L = g.L;
   p->gp.N = g.N;
   p->gp.ld = g.ld;

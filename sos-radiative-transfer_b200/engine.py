@@ -228,6 +228,13 @@ class SosEngine:
             _lib.check(self.lib.sos_source(self._plan, In1.data_ptr(), out.data_ptr(), self._stream), "sos_source")
         return out
 
+    def source_rows(self, In1: torch.Tensor, out: torch.Tensor, row0: int, row1: int) -> torch.Tensor:
+        """Source contraction of layers [row0, row1) only (see sos_source_rows)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_source_rows(self._plan, In1.data_ptr(), out.data_ptr(), int(row0), int(row1), self._stream),
+                       "sos_source_rows")
+        return out
+
     def sweeps(self, J: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate_into: Optional[torch.Tensor] = None):
         out = self.new_field(zero=True) if out is None else out
         acc = accumulate_into.data_ptr() if accumulate_into is not None else None

@@ -69,24 +69,105 @@ def mu_blocks(N: int, M: int, world: int, zone_lo: int) -> List[Tuple[int, int]]
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+class ColumnGather:
+    """Preallocated buffers for repeated column all-gathers of equally shaped row slabs (keeps the
+    per-call host work to three tensor ops: pack, ncclAllGather, unpack)."""
+
+    def __init__(self, rows: int, blocks: Sequence[Tuple[int, int]], rank: int, dtype, device, group=None):
+        self.blocks, self.rank, self.group = list(blocks), rank, group
+        self.world = len(self.blocks)
+        self.width = max(c1 - c0 for c0, c1 in self.blocks)
+        self.uniform = all(c1 - c0 == self.width for c0, c1 in self.blocks) and \
+            all(self.blocks[r][0] == r * self.width for r in range(self.world))
+        self.send = torch.zeros((rows, self.width), dtype=dtype, device=device)
+        self.recv = torch.empty((self.world, rows, self.width), dtype=dtype, device=device)
+        self.nccl = self.world > 1 and dist.get_backend(group) == "nccl"
+
+    def __call__(self, field: torch.Tensor) -> None:
+        if self.world == 1:
+            return
+        rows = field.shape[0]
+        c0, c1 = self.blocks[self.rank]
+        send, recv = self.send[:rows], self.recv[:, :rows]
+        send[:, : c1 - c0].copy_(field[:, c0:c1])
+        if rows != self.send.shape[0]:
+            send, recv = send.contiguous(), torch.empty((self.world, rows, self.width), dtype=field.dtype, device=field.device)
+        if self.nccl:
+            dist.all_gather_into_tensor(recv, send, group=self.group)   # one ncclAllGather, no staging copies
+        else:
+            dist.all_gather([recv[r] for r in range(self.world)], send, group=self.group)
+        if self.uniform:
+            field[:, : self.world * self.width].view(rows, self.world, self.width).copy_(recv.permute(1, 0, 2))
+        else:
+            for r, (a, b) in enumerate(self.blocks):
+                if r != self.rank:
+                    field[:, a:b].copy_(recv[r, :, : b - a])
+
+
 def allgather_columns(field: torch.Tensor, blocks: Sequence[Tuple[int, int]], rank: int, group=None) -> None:
     """In place: every rank contributes field[:, c0:c1] of its own block and receives all others."""
-    world = len(blocks)
-    if world == 1:
+    if len(blocks) == 1:
         return
-    width = max(c1 - c0 for c0, c1 in blocks)
-    rows = field.shape[0]
-    send = torch.zeros((rows, width), dtype=field.dtype, device=field.device)
-    c0, c1 = blocks[rank]
-    send[:, : c1 - c0].copy_(field[:, c0:c1])
-    recv = torch.empty((world, rows, width), dtype=field.dtype, device=field.device)
-    if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(recv, send, group=group)   # one ncclAllGather, no staging copies
-    else:
-        dist.all_gather([recv[r] for r in range(world)], send, group=group)
-    for r, (a, b) in enumerate(blocks):
-        if r != rank:
-            field[:, a:b].copy_(recv[r, :, : b - a])
+    ColumnGather(field.shape[0], blocks, rank, field.dtype, field.device, group)(field)
+
+
+class RawField:
+    """A device buffer that is not a torch tensor (CUDA-IPC shareable allocation); quacks like one for
+    the engine calls, which only need data_ptr()."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = int(ptr), int(nbytes)
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+
+class PeerFields:
+    """Two ping-pong I_n buffers per rank, mapped into every rank's address space with CUDA IPC, so that
+    the source contraction can read each mu block from the GPU that owns it (sos_source_peers)."""
+
+    def __init__(self, engine, rank: int, world: int, group=None):
+        import ctypes as C
+        from . import _lib
+        self.lib, self.C, self._lib = _lib.load(), C, _lib
+        self.rank, self.world = rank, world
+        nbytes = engine.S * engine.L * engine.ld * 8
+        self.nbytes = nbytes
+        self.local, handles = [], []
+        with torch.cuda.device(engine.device):
+            for _ in range(2):
+                ptr = C.c_void_p()
+                h = C.create_string_buffer(64)
+                _lib.check(self.lib.sos_ipc_alloc(nbytes, C.byref(ptr), h), "sos_ipc_alloc")
+                self.local.append(RawField(ptr.value, nbytes))
+                handles.append(h.raw)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, handles, group=group)
+            self.ptrs = []          # [buffer][rank] -> device pointer valid in THIS process
+            self._opened = []
+            for b in range(2):
+                row = []
+                for r in range(world):
+                    if r == rank:
+                        row.append(self.local[b].ptr)
+                    else:
+                        ptr = C.c_void_p()
+                        _lib.check(self.lib.sos_ipc_open(everyone[r][b], C.byref(ptr)), "sos_ipc_open")
+                        self._opened.append(ptr.value)
+                        row.append(ptr.value)
+                self.ptrs.append(row)
+
+    def ptr_array(self, b: int):
+        C = self.C
+        return (C.c_void_p * self.world)(*self.ptrs[b])
+
+    def close(self):
+        for p in self._opened:
+            self.lib.sos_ipc_close(self.C.c_void_p(p))
+        self._opened = []
+        for f in self.local:
+            self.lib.sos_ipc_free(self.C.c_void_p(f.ptr))
+        self.local = []
 
 
 class MuShardedSolver:
@@ -99,37 +180,96 @@ class MuShardedSolver:
         engine.set_columns(c0, c1)
         self.comm_ms = 0.0
 
-    def solve(self, I1: torch.Tensor, max_orders: int = 10000, poll_every: int = 4, time_comm: bool = False):
-        eng = self.eng
+    def solve_p2p(self, I1: torch.Tensor, peers: "PeerFields", max_orders: int = 10000, poll_every: int = 4):
+        """Order loop with the all-gather FUSED into the contraction: every rank keeps its I_n block in
+        a CUDA-IPC buffer and the contraction kernel of order n+1 pulls each k-range from its owner by TMA
+        over NVLink (sos_source_peers).  The only collective left per order is the MAX all-reduce of the
+        two convergence ratios, which doubles as the cross-GPU barrier that orders writers and readers of
+        the ping-pong buffers."""
+        import ctypes as C
+        from . import _lib
+        eng, lib = self.eng, self.eng.lib
+        dev = eng.device
         I = I1.clone()
-        In = I1.clone()
         J = eng.new_field(zero=True)
         eng.reset(I1)
-        ratios = torch.empty((eng.S, 2), dtype=torch.float64, device=eng.device)
+        ratios = torch.empty((eng.S, 2), dtype=torch.float64, device=dev)
+        cols = (C.c_int * (self.world + 1))(*([b[0] for b in self.blocks] + [self.blocks[-1][1]]))
+        cur = 0
+        with torch.cuda.device(dev):
+            _lib.check(lib.sos_copy_d2d(C.c_void_p(peers.local[cur].ptr), C.c_void_p(I1.data_ptr()), peers.nbytes, eng._stream), "sos_copy_d2d")
+        torch.cuda.current_stream(dev).synchronize()
+        dist.barrier(group=self.group)             # every rank's I1 block is in place
         n = 1
         done = False
-        ev = []
         while n < max_orders and not done:
             n += 1
-            eng.source(In, out=J)
-            eng.sweeps(J, out=In, accumulate_into=I)
-            if time_comm:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            allgather_columns(In, self.blocks, self.rank, self.group)
-            if self.world > 1:
-                eng.ratios(ratios)
-                dist.all_reduce(ratios, op=dist.ReduceOp.MAX, group=self.group)
-                eng.ratios(ratios, set=True)
-            if time_comm:
-                e1.record()
-                ev.append((e0, e1))
+            with torch.cuda.device(dev):
+                _lib.check(lib.sos_source_peers(eng._plan, peers.ptr_array(cur), self.world, cols, J.data_ptr(), eng._stream),
+                           "sos_source_peers")
+            eng.sweeps(J, out=peers.local[cur ^ 1], accumulate_into=I)
+            eng.ratios(ratios)
+            dist.all_reduce(ratios, op=dist.ReduceOp.MAX, group=self.group)
+            eng.ratios(ratios, set=True)
             eng.converge(n)
+            cur ^= 1
             if (n - 1) % poll_every == 0:
                 done = not any(r.active for r in eng.results())
         res = eng.results()
         allgather_columns(I, self.blocks, self.rank, self.group)
-        if time_comm:
+        return I, res
+
+    def solve(self, I1: torch.Tensor, max_orders: int = 10000, poll_every: int = 4, time_comm: bool = False,
+              row_chunks: int = 4):
+        """Order loop.  After the sweeps of order n the I_n blocks are all-gathered in `row_chunks` slabs of
+        layers on a side stream; the contraction of order n+1 is launched slab by slab as soon as its
+        slab has arrived, so NVLink traffic overlaps the FP64 work."""
+        eng = self.eng
+        dev = eng.device
+        I = I1.clone()
+        In = I1.clone()
+        J = eng.new_field(zero=True)
+        eng.reset(I1)
+        ratios = torch.empty((eng.S, 2), dtype=torch.float64, device=dev)
+        L = eng.L
+        step = max(64, -(-L // max(row_chunks, 1) // 64) * 64) if self.world > 1 else L
+        slabs = [(r, min(L, r + step)) for r in range(0, L, step)]
+        gather = ColumnGather(step, self.blocks, self.rank, In.dtype, dev, self.group)
+        compute = torch.cuda.current_stream(dev)
+        comm = torch.cuda.Stream(device=dev) if self.world > 1 else compute
+        n = 1
+        done = False
+        ev = []
+        eng.source(In, out=J)                      # order 2 needs no exchange: every rank holds the full I1
+        while n < max_orders and not done:
+            n += 1
+            eng.sweeps(J, out=In, accumulate_into=I)
+            if self.world == 1:
+                eng.converge(n)
+                eng.source(In, out=J)
+            else:
+                swept = torch.cuda.Event(enable_timing=time_comm)
+                swept.record(compute)
+                comm.wait_event(swept)
+                with torch.cuda.stream(comm):
+                    eng.ratios(ratios)
+                    dist.all_reduce(ratios, op=dist.ReduceOp.MAX, group=self.group)
+                    eng.ratios(ratios, set=True)
+                    eng.converge(n)
+                for r0, r1 in slabs:
+                    with torch.cuda.stream(comm):
+                        gather(In[r0:r1])
+                        arrived = torch.cuda.Event(enable_timing=time_comm)
+                        arrived.record(comm)
+                    compute.wait_event(arrived)
+                    eng.source_rows(In, J, r0, r1)   # contraction of the next order on the slab that has landed
+                if time_comm:
+                    ev.append((swept, arrived))
+            if (n - 1) % poll_every == 0:
+                done = not any(r.active for r in eng.results())
+        res = eng.results()
+        allgather_columns(I, self.blocks, self.rank, self.group)
+        if time_comm and ev:
             torch.cuda.synchronize()
             self.comm_ms = sum(a.elapsed_time(b) for a, b in ev)
         return I, res

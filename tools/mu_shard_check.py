@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--orders", type=int, default=24)
     ap.add_argument("--phase", default="hg")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--slabs", type=int, default=1)
+    ap.add_argument("--p2p", action="store_true", help="fused all-gather: contraction reads peer memory over NVLink")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -56,21 +58,28 @@ def main():
     I1 = eng.first_order(Cc)
     blocks = sos.mu_blocks(N, M, world, M - w - 5)
     solver = sos.MuShardedSolver(eng, blocks, rank)
+    peers = sos.PeerFields(eng, rank, world) if (args.p2p and world > 1) else None
+
+    def run(max_orders, timed=False):
+        if peers is not None:
+            return solver.solve_p2p(I1, peers, max_orders=max_orders)
+        return solver.solve(I1, max_orders=max_orders, time_comm=timed, row_chunks=args.slabs)
+
     for _ in range(2):
-        solver.solve(I1, max_orders=4)
+        run(4)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    I, res = solver.solve(I1, max_orders=args.orders + 1, time_comm=True)
+    I, res = run(args.orders + 1, timed=True)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1), solver.comm_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     n_done = res[0].n_orders - 1
-    out = {"world": world, "L": L, "N": N, "orders": int(n_done), "ms_total": float(ms[0]), "ms_per_order": float(ms[0]) / max(n_done, 1),
+    out = {"world": world, "p2p": bool(peers is not None), "slabs": args.slabs, "L": L, "N": N, "orders": int(n_done), "ms_total": float(ms[0]), "ms_per_order": float(ms[0]) / max(n_done, 1),
            "allgather_ms_per_order": float(ms[1]) / max(n_done, 1), "status": int(res[0].status),
            "updates_per_s": n_done * L * N * N / (float(ms[0]) * 1e-3)}
     if args.check:
@@ -84,6 +93,10 @@ def main():
             out["orders_unsharded"] = int(r.n_orders[0]) - 1
     if rank == 0:
         print(json.dumps(out))
+    if peers is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        peers.close()
     if world > 1:
         dist.destroy_process_group()
 
