@@ -109,6 +109,16 @@ int sos_extrap_layout(int nb_angles, int* idx, int* ns, int* off);
  * w = composite-trapezoid weights of the mu grid).  P_d: [N][ldp], A_d: [N][lda]. */
 int sos_build_contraction(sos_plan* plan, const double* P_d, int ldp, double* A_d, int lda, void* stream);
 
+/* Azimuth-averaged phase functions built on the device (SOS_Aer_phase_func.py:68-292): family 0 =
+ * Rayleigh (:79-133), 1 = Henyey-Greenstein with asymmetry g (:141-195), 2 = tabulated (FWC: :202-292;
+ * tab_x_d ascending cos(scattering angle), tab_y_d values, device arrays).  phi_h / cphi_h: the 25
+ * azimuth nodes linspace(0, pi, 25) and their cosines as the host computed them.  Writes P_d [N][ldp]
+ * (every column normalised to trapz = 4, :131) and/or P0_d [N] for the solar direction mu0 (normalised
+ * to trapz = 2, :105); either may be NULL. */
+int sos_build_phase(sos_plan* plan, int family, double g, double mu0, const double* phi_h, const double* cphi_h,
+                    const double* tab_x_d, const double* tab_y_d, int tab_n, double* P_d, int ldp, double* P0_d,
+                    void* stream);
+
 /* Register the contraction matrices (device, [N][lda] each) the scenarios index. */
 int sos_plan_set_phase(sos_plan* plan, const double* const* A_d, int n_matrices, int lda);
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "sos_plan_destroy": (C.c_int, [_vp]),
     "sos_extrap_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sos_build_contraction": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
+    "sos_build_phase": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "sos_plan_set_phase": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int]),
     "sos_first_order": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source": (C.c_int, [_vp, _vp, _vp, _vp]),

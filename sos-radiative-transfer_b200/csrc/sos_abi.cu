@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "first_order.cuh"
 #include "gemm_f64.cuh"
+#include "phase.cuh"
 #include "quadrature.cuh"
 #include "sweep.cuh"
 
@@ -536,6 +537,38 @@ int sos_build_contraction(sos_plan* p, const double* P_d, int ldp, double* A_d, 
   dim3 grid((N + 31) / 32, (N + 31) / 32);
   sosquad::build_contraction_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P_d, ldp, A_d, lda, N, p->dev.wmu);
   return launch_check(p);
+}
+
+int sos_build_phase(sos_plan* p, int family, double g, double mu0, const double* phi_h, const double* cphi_h,
+                    const double* tab_x_d, const double* tab_y_d, int tab_n, double* P_d, int ldp, double* P0_d,
+                    void* stream) {
+  if (!p || !phi_h || !cphi_h || (!P_d && !P0_d)) return SOS_ERR_INVALID;
+  if (family < 0 || family > 2 || (family == 2 && (!tab_x_d || !tab_y_d || tab_n < 2))) return SOS_ERR_INVALID;
+  if (P_d && ldp < p->N) return SOS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  sosphase::PhaseArgs a;
+  a.family = family; a.g = g; a.tab_x = tab_x_d; a.tab_y = tab_y_d; a.tab_n = tab_n;
+  for (int k = 0; k < sosphase::NPHI; ++k) { a.phi[k] = phi_h[k]; a.cphi[k] = cphi_h[k]; }
+  const int N = p->N;
+  if (P_d) {
+    dim3 grid((N + 31) / 32, (N + 7) / 8);
+    sosphase::phase_raw_kernel<<<grid, 256, 0, st>>>(a, p->dev.mu, N, P_d, ldp);
+    int r = launch_check(p);
+    if (r) return r;
+    double* colint = p->d_sums;  // scratch of S*L*3 doubles; N <= that for every sensible grid
+    if (static_cast<size_t>(N) > static_cast<size_t>(p->dev.S) * p->dev.L * 3) return SOS_ERR_UNSUPPORTED;
+    sosphase::phase_colint_kernel<<<(N + 127) / 128, 128, 0, st>>>(p->dev.mu, N, P_d, ldp, colint);
+    r = launch_check(p);
+    if (r) return r;
+    sosphase::phase_normalise_kernel<<<grid, 256, 0, st>>>(N, P_d, ldp, colint);
+    r = launch_check(p);
+    if (r) return r;
+  }
+  if (P0_d) {
+    sosphase::phase_p0_kernel<<<1, 256, 0, st>>>(a, p->dev.mu, N, mu0, P0_d);
+    return launch_check(p);
+  }
+  return SOS_OK;
 }
 
 int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {

@@ -78,20 +78,33 @@ class PhaseCache:
         self._P: Dict[tuple, np.ndarray] = {}
         self._P0: Dict[tuple, np.ndarray] = {}
 
-    def get(self, spec: PhaseSpec, M: int, mu: np.ndarray, mu0: float):
+    def get(self, spec: PhaseSpec, M: int, mu: np.ndarray, mu0: float, need_P: bool = True):
+        """(P0, P or None, key).  need_P=False skips the host build of the N x N matrix (the caller builds
+        it on the device or already holds the operand)."""
         if isinstance(spec[0], str):
             name, g = spec[0], float(spec[1])
             kP, k0 = (name, g, M), (name, g, M, float(mu0))
-            if kP not in self._P:
+            if need_P and kP not in self._P:
                 self._P[kP] = PH.phase_P(name, M, mu, g)
             if k0 not in self._P0:
                 self._P0[k0] = PH.phase_P0(name, M, mu, mu0, g)
-            return self._P0[k0], self._P[kP], kP
+            return self._P0[k0], self._P.get(kP), kP
         P0, P = spec
         return np.asarray(P0, dtype=np.float64), np.asarray(P, dtype=np.float64), ("array", id(P))
 
 
 _PHASES = PhaseCache()
+
+
+class _DeviceBuilt:
+    """Placeholder for a phase matrix that SosEngine.set_phase builds on the device when (and only
+    when) the operand cache misses."""
+
+    def __init__(self, engine, name, g):
+        self.engine, self.name, self.g = engine, name, g
+
+    def build(self):
+        return self.engine.build_phase_matrix(self.name, self.g)[0]
 
 
 def _group_key(sc: Scenario):
@@ -102,7 +115,8 @@ def _group_key(sc: Scenario):
 class BatchSolver:
     """All scenarios of one group (same L, M, aerosol rows, surface) on one device."""
 
-    def __init__(self, scenarios: Sequence[Scenario], device=None, chunk_rows: int = 0, phases: Optional[PhaseCache] = None):
+    def __init__(self, scenarios: Sequence[Scenario], device=None, chunk_rows: int = 0, phases: Optional[PhaseCache] = None,
+                 device_phase: bool = True):
         keys = {_group_key(s) for s in scenarios}
         if len(keys) != 1:
             raise ValueError("BatchSolver: scenarios must share nb_layers, nb_angles, aerosol rows and surface")
@@ -122,8 +136,8 @@ class BatchSolver:
             self.z = z if self.z is None else self.z
             zu, zd = (sc.z_up, sc.z_down) if sc.z_up >= sc.z_down else (sc.z_down, sc.z_up)
             tau[i] = G.tau_profile(sc.tauStar_atm, sc.tauStar_aer, sc.z0, zu, zd, L)
-            P0a, Pa, ka = phases.get(sc.atm_phase, M, self.mu, sc.mu0)
-            P0e, Pe, ke = phases.get(sc.aer_phase, M, self.mu, sc.mu0)
+            P0a, Pa, ka = phases.get(sc.atm_phase, M, self.mu, sc.mu0, need_P=not device_phase)
+            P0e, Pe, ke = phases.get(sc.aer_phase, M, self.mu, sc.mu0, need_P=not device_phase)
             for k, P in ((ka, Pa), (ke, Pe)):
                 if k not in mat_index:
                     mat_index[k] = len(mats)
@@ -148,6 +162,13 @@ class BatchSolver:
         surface = {"specular": _lib.SURFACE_SPECULAR, "lambert": _lib.SURFACE_LAMBERT}[surf]
         self.engine = SosEngine(self.mu, tau, coefs, [0, self.idx_up, self.idx_down + 1, L], surface,
                                 device=device, chunk_rows=chunk_rows)
+        if device_phase:
+            # analytic families: the N x N matrix is built on the device (sos_build_phase) unless its
+            # contraction operand is already resident; only the cheap P0 vectors were built on the host
+            for i, k in enumerate(mat_keys):
+                if k is not None and mats[i] is None:
+                    name, g = k[0], k[1]
+                    mats[i] = _DeviceBuilt(self.engine, name, g)
         self.engine.set_phase(mats, keys=mat_keys)
         self.I1 = None
 

@@ -196,7 +196,9 @@ class SosEngine:
                     if hit is not None:
                         self._A.append(hit)
                         continue
-                if isinstance(P, torch.Tensor):
+                if hasattr(P, "build"):
+                    Pd = P.build()            # built on the device (drivers._DeviceBuilt)
+                elif isinstance(P, torch.Tensor):
                     Pd = P.to(self.device, torch.float64).contiguous()
                 else:
                     Pd = torch.as_tensor(np.ascontiguousarray(P, dtype=np.float64)).to(self.device)
@@ -212,6 +214,40 @@ class SosEngine:
                 self._A.append(A)
             ptrs = (C.c_void_p * len(self._A))(*[a.data_ptr() for a in self._A])
             _lib.check(self.lib.sos_plan_set_phase(self._plan, ptrs, len(self._A), lda), "sos_plan_set_phase")
+
+    def build_phase_matrix(self, name: str, g: float = 0.5, mu0: Optional[float] = None):
+        """P(mu, mu') (and P0(mu, mu0) when mu0 is given) of an analytic family, built ON THE DEVICE
+        (sos_build_phase): 'rayleigh', 'hg', 'fwc', 'iso'.  Returns (P (N, N) tensor, P0 (N,) tensor or None)."""
+        from . import phase as PH
+        N = self.N
+        P = torch.empty((N, N), dtype=torch.float64, device=self.device)
+        P0 = torch.empty(N, dtype=torch.float64, device=self.device) if mu0 is not None else None
+        if name == "iso":
+            P.fill_(2.0)
+            if P0 is not None:
+                P0.fill_(1.0)
+            return P, P0
+        fam = {"rayleigh": 0, "hg": 1, "fwc": 2}[name]
+        phi = np.linspace(0, np.pi, PH.NB_PHI)
+        cphi = np.ascontiguousarray(np.cos(0 - phi))
+        tx = ty = None
+        tn = 0
+        if fam == 2:
+            key = ("fwc_table", self.device.index)
+            if key not in _OPERANDS:
+                xs, ys = PH._fwc_table()
+                _OPERANDS[key] = (torch.as_tensor(np.ascontiguousarray(xs)).to(self.device),
+                                  torch.as_tensor(np.ascontiguousarray(ys)).to(self.device))
+            tx, ty = _OPERANDS[key]
+            tn = tx.numel()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_build_phase(self._plan, fam, float(g), float(mu0 if mu0 is not None else 0.5),
+                                                phi.ctypes.data, cphi.ctypes.data,
+                                                tx.data_ptr() if tx is not None else None,
+                                                ty.data_ptr() if ty is not None else None, int(tn),
+                                                P.data_ptr(), N, P0.data_ptr() if P0 is not None else None, self._stream),
+                       "sos_build_phase")
+        return P, P0
 
     # ------------------------------------------------------------------ operators
     def first_order(self, C_coef: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:

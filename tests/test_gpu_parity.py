@@ -354,3 +354,30 @@ def test_radiative_forcing_and_critical_albedo(sos, golden):
         if f_lo * f_hi < 0:  # a sign change exists: the returned omega brackets it within the width
             a, b = forcing_at(i, max(omega[i] - 0.06, 0.0)), forcing_at(i, min(omega[i] + 0.06, 1.0))
             assert a * b <= 0 or min(abs(a), abs(b)) < 2e-3
+
+
+@pytest.mark.parametrize("name,g", [("rayleigh", 0.0), ("hg", 0.5), ("hg", 0.75), ("fwc", 0.0)])
+def test_device_phase_builder_vs_reference(sos, golden, name, g):
+    """sos_build_phase against the reference's own builders (fixtures) and the host builder."""
+    d = golden("phase_small.npz")
+    for M in (21, 41):
+        for mu0 in (0.5, 0.8):
+            mu = sos.mu_grid(M)
+            coef = [sos.ScenarioCoefficients(mu0=mu0, grd_alb=0.0, tauStar_tot=1.0, coef_atm=1.0)]
+            eng = sos.SosEngine(mu, np.linspace(0, 1, 8)[None], coef, [0, 8], sos._lib.SURFACE_NONE)
+            P, P0 = eng.build_phase_matrix(name, g, mu0=mu0)
+            P, P0 = P.cpu().numpy(), P0.cpu().numpy()
+            eng.close()
+            key = f"{name}_M{M}_mu0{mu0}_g{g}"
+            assert relmax(P, d[key + "_P"]) < 1e-12 and relmax(P0, d[key + "_P0"]) < 1e-12
+    # full size against the host builder (itself pinned on the reference at M = 501 by the n1002 fixture)
+    M = 501
+    mu = sos.mu_grid(M)
+    coef = [sos.ScenarioCoefficients(mu0=0.5, grd_alb=0.0, tauStar_tot=1.0, coef_atm=1.0)]
+    eng = sos.SosEngine(mu, np.linspace(0, 1, 8)[None], coef, [0, 8], sos._lib.SURFACE_NONE)
+    P, P0 = eng.build_phase_matrix(name, g, mu0=0.5)
+    Ph = sos.phase_P(name, M, mu, g) if name != "fwc" else None
+    if Ph is not None:
+        assert relmax(P.cpu().numpy(), Ph) < 1e-12
+    assert relmax(P0.cpu().numpy(), sos.phase_P0(name, M, mu, 0.5, g)) < 1e-12
+    eng.close()
