@@ -84,6 +84,7 @@ struct sos_plan {
   double* d_C = nullptr;     // [S][2][N] first-order coefficients
   double* d_sums = nullptr;  // [S][L][3]
   double* d_z = nullptr;     // [L]
+  double* d_colint = nullptr;  // [N] column integrals of the device phase builder
   int* h_poll = nullptr;     // pinned
   std::vector<sos_scenario> scen_h;
   std::vector<int> chunk_start_h;
@@ -374,6 +375,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   TRY(dev_alloc(p, &p->d_C, static_cast<size_t>(S) * 2 * N));
   TRY(dev_alloc(p, &p->d_sums, static_cast<size_t>(S) * L * 3));
   TRY(dev_alloc(p, &p->d_z, static_cast<size_t>(L)));
+  TRY(dev_alloc(p, &p->d_colint, static_cast<size_t>(N)));
   {
     cudaError_t e = cudaMemset(p->d_carryD, 0, nagg * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(p->d_carryU, 0, nagg * sizeof(double));
@@ -555,8 +557,7 @@ int sos_build_phase(sos_plan* p, int family, double g, double mu0, const double*
     sosphase::phase_raw_kernel<<<grid, 256, 0, st>>>(a, p->dev.mu, N, P_d, ldp);
     int r = launch_check(p);
     if (r) return r;
-    double* colint = p->d_sums;  // scratch of S*L*3 doubles; N <= that for every sensible grid
-    if (static_cast<size_t>(N) > static_cast<size_t>(p->dev.S) * p->dev.L * 3) return SOS_ERR_UNSUPPORTED;
+    double* colint = p->d_colint;
     sosphase::phase_colint_kernel<<<(N + 127) / 128, 128, 0, st>>>(p->dev.mu, N, P_d, ldp, colint);
     r = launch_check(p);
     if (r) return r;

@@ -373,7 +373,8 @@ def test_device_phase_builder_vs_reference(sos, golden, name, g):
     # full size against the host builder (itself pinned on the reference at M = 501 by the n1002 fixture)
     M = 501
     mu = sos.mu_grid(M)
-    coef = [sos.ScenarioCoefficients(mu0=0.5, grd_alb=0.0, tauStar_tot=1.0, coef_atm=1.0)]
+    w = sos.extrapolation_width(1.0, M)
+    coef = [sos.ScenarioCoefficients(mu0=0.5, grd_alb=0.0, tauStar_tot=1.0, coef_atm=1.0, extrap_width=(w, w, w))]
     eng = sos.SosEngine(mu, np.linspace(0, 1, 8)[None], coef, [0, 8], sos._lib.SURFACE_NONE)
     P, P0 = eng.build_phase_matrix(name, g, mu0=0.5)
     Ph = sos.phase_P(name, M, mu, g) if name != "fwc" else None
