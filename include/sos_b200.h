@@ -158,7 +158,8 @@ int sos_copy_d2d(void* dst_d, const void* src_d, size_t bytes, void* stream);
 int sos_sweeps(sos_plan* plan, const double* J_d, double* In_d, double* I_d, void* stream);
 
 /* Convergence bookkeeping for the order that was just accumulated (`n` = its order number):
- * scenarios whose ratio fell below threshold become inactive with n_orders = n. */
+ * scenarios whose ratio fell below threshold become inactive with n_orders = n.  order < 0: use the
+ * plan's device-side order counter + 1 (reset to 1 by sos_reset) -- for CUDA-graph replays. */
 int sos_converge(sos_plan* plan, int order, void* stream);
 
 /* Whole order loop (SOS_Aer_main_specular.py:302-458).  I_d holds I1 on entry and I on exit;

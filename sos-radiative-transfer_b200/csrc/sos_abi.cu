@@ -95,6 +95,7 @@ struct sos_plan {
   int* d_active_list = nullptr;  // compacted per group (device-built)
   TilePlan* d_tile_plan = nullptr;
   int* d_work_counter = nullptr;
+  int* d_order = nullptr;        // device-side order counter (sos_converge with order < 0)
   int nseg[2] = {0, 0};
   long long max_row_tiles = 0;
   const double* phase_ptr[SOS_MAX_PHASE];
@@ -455,6 +456,8 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     TRY(dev_alloc(p, &p->d_active_list, flat.size()));
     TRY(dev_alloc(p, &p->d_tile_plan, 1));
     TRY(dev_alloc(p, &p->d_work_counter, 1));
+    TRY(dev_alloc(p, &p->d_order, 1));
+    { const int one = 1; SOS_CUDA(cudaMemcpy(p->d_order, &one, sizeof(int), cudaMemcpyHostToDevice)); }
     p->gemm_bm = sosgemm::Cfg<2, 4, 4>::BM;
   }
 #undef TRY
@@ -748,7 +751,7 @@ int sos_sweeps(sos_plan* p, const double* J_d, double* In_d, double* I_d, void* 
 
 int sos_converge(sos_plan* p, int order, void* stream) {
   if (!p) return SOS_ERR_INVALID;
-  sossweep::converge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, order);
+  sossweep::converge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, order, p->d_order);
   int r = launch_check(p);
   if (r) return r;
   return plan_tiles(p, static_cast<cudaStream_t>(stream));
@@ -757,7 +760,7 @@ int sos_converge(sos_plan* p, int order, void* stream) {
 int sos_reset(sos_plan* p, const double* I1_d, void* stream) {
   if (!p || !I1_d) return SOS_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  sossweep::reset_kernel<<<p->dev.S, 256, 0, st>>>(p->dev, I1_d);
+  sossweep::reset_kernel<<<p->dev.S, 256, 0, st>>>(p->dev, I1_d, p->d_order);
   int r = launch_check(p);
   if (r) return r;
   sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev);

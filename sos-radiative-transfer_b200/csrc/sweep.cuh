@@ -496,10 +496,18 @@ sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __r
 // ------------------------------------------------------------------------------------------
 // convergence bookkeeping
 // ------------------------------------------------------------------------------------------
-__global__ void converge_kernel(const GridDev g, int order) {
+__global__ void converge_kernel(const GridDev g, int order_arg, int* order_counter) {
   __shared__ int cnt;
-  if (threadIdx.x == 0) cnt = 0;
+  __shared__ int order_s;
+  if (threadIdx.x == 0) {
+    cnt = 0;
+    // order_arg < 0: take the order number from the device-side counter (CUDA-graph replays cannot
+    // change kernel arguments); the counter always tracks the last order handled
+    order_s = order_arg >= 0 ? order_arg : *order_counter + 1;
+    *order_counter = order_s;
+  }
   __syncthreads();
+  const int order = order_s;
   int mine = 0;
   for (int s = threadIdx.x; s < g.S; s += blockDim.x) {
     ScenState& st = g.state[s];
@@ -515,7 +523,7 @@ __global__ void converge_kernel(const GridDev g, int order) {
 }
 
 // ratios with I_n := 1 (the reference initialises In = ones before the loop, :306-309)
-__global__ void reset_kernel(const GridDev g, const double* __restrict__ I1) {
+__global__ void reset_kernel(const GridDev g, const double* __restrict__ I1, int* order_counter) {
   const int s = blockIdx.x;
   __shared__ double sc[32];
   const int L = g.L, M = g.M, N = g.N, ld = g.ld;
@@ -543,6 +551,7 @@ __global__ void reset_kernel(const GridDev g, const double* __restrict__ I1) {
     st.ratio_surf = r;
     st.n_orders = 1;
     st.status = 0;
+    if (s == 0) *order_counter = 1;
     st.active = (fmax(st.ratio_toa, r) >= g.scen[s].threshold) ? 1 : 0;
   }
 }

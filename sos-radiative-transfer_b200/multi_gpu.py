@@ -180,7 +180,7 @@ class MuShardedSolver:
         engine.set_columns(c0, c1)
         self.comm_ms = 0.0
 
-    def solve_p2p(self, I1: torch.Tensor, peers: "PeerFields", max_orders: int = 10000, poll_every: int = 4):
+    def solve_p2p(self, I1: torch.Tensor, peers: "PeerFields", max_orders: int = 10000, poll_every: int = 8):
         """Order loop with the all-gather FUSED into the contraction: every rank keeps its I_n block in
         a CUDA-IPC buffer and the contraction kernel of order n+1 pulls each k-range from its owner by TMA
         over NVLink (sos_source_peers).  The only collective left per order is the MAX all-reduce of the
@@ -190,28 +190,34 @@ class MuShardedSolver:
         from . import _lib
         eng, lib = self.eng, self.eng.lib
         dev = eng.device
-        I = I1.clone()
-        J = eng.new_field(zero=True)
+        if getattr(self, "_p2p_bufs", None) is None:   # work buffers are kept between solves
+            self._p2p_bufs = (torch.empty_like(I1), eng.new_field(zero=True),
+                              torch.empty((eng.S, 2), dtype=torch.float64, device=dev))
+        I, J, ratios = self._p2p_bufs
+        I.copy_(I1)
         eng.reset(I1)
-        ratios = torch.empty((eng.S, 2), dtype=torch.float64, device=dev)
         cols = (C.c_int * (self.world + 1))(*([b[0] for b in self.blocks] + [self.blocks[-1][1]]))
         cur = 0
         with torch.cuda.device(dev):
             _lib.check(lib.sos_copy_d2d(C.c_void_p(peers.local[cur].ptr), C.c_void_p(I1.data_ptr()), peers.nbytes, eng._stream), "sos_copy_d2d")
         torch.cuda.current_stream(dev).synchronize()
         dist.barrier(group=self.group)             # every rank's I1 block is in place
+
+        def one_order(b, order):
+            with torch.cuda.device(dev):
+                _lib.check(lib.sos_source_peers(eng._plan, peers.ptr_array(b), self.world, cols, J.data_ptr(), eng._stream),
+                           "sos_source_peers")
+            eng.sweeps(J, out=peers.local[b ^ 1], accumulate_into=I)
+            eng.ratios(ratios)
+            dist.all_reduce(ratios, op=dist.ReduceOp.MAX, group=self.group)
+            eng.ratios(ratios, set=True)
+            eng.converge(order)
+
         n = 1
         done = False
         while n < max_orders and not done:
             n += 1
-            with torch.cuda.device(dev):
-                _lib.check(lib.sos_source_peers(eng._plan, peers.ptr_array(cur), self.world, cols, J.data_ptr(), eng._stream),
-                           "sos_source_peers")
-            eng.sweeps(J, out=peers.local[cur ^ 1], accumulate_into=I)
-            eng.ratios(ratios)
-            dist.all_reduce(ratios, op=dist.ReduceOp.MAX, group=self.group)
-            eng.ratios(ratios, set=True)
-            eng.converge(n)
+            one_order(cur, n)
             cur ^= 1
             if (n - 1) % poll_every == 0:
                 done = not any(r.active for r in eng.results())

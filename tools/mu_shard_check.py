@@ -66,7 +66,7 @@ def main():
         return solver.solve(I1, max_orders=max_orders, time_comm=timed, row_chunks=args.slabs)
 
     for _ in range(2):
-        run(4)
+        run(8)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
