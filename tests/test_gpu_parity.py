@@ -382,3 +382,50 @@ def test_device_phase_builder_vs_reference(sos, golden, name, g):
         assert relmax(P.cpu().numpy(), Ph) < 1e-12
     assert relmax(P0.cpu().numpy(), sos.phase_P0(name, M, mu, 0.5, g)) < 1e-12
     eng.close()
+
+
+def _oracle_solve(so, sos, sc, atm=("rayleigh", 0.0), aer=("hg", 0.5)):
+    M = sc.nb_angles
+    mu = so.mu_grid(M)
+    P0a, Pa = sos.phase_matrices(atm[0], M, mu, sc.mu0, atm[1])
+    P0e, Pe = sos.phase_matrices(aer[0], M, mu, sc.mu0, aer[1])
+    osc = so.Scenario(mu0=sc.mu0, z0=sc.z0, z_up=sc.z_up, z_down=sc.z_down, nb_layers=sc.nb_layers,
+                      tauStar_atm=sc.tauStar_atm, tauStar_aer=sc.tauStar_aer, grd_alb=sc.grd_alb, alb_atm=sc.alb_atm,
+                      alb_aer=sc.alb_aer, nb_angles=M, surface=sc.surface, threshold=sc.threshold)
+    return so.solve(osc, P0a, Pa, P0e, Pe, method="recurrence", use_gemm=True, keep_orders=False)
+
+
+def test_edge_scenarios_vs_oracle(sos, so):
+    """Edge cases the fixtures do not reach, one mixed batch per surface kind, against the oracle:
+    no aerosol at all (second contraction coefficient exactly 0), absorbing gas (omega_atm < 1), black and
+    mirror surfaces, mu0 off the grid; then an optically thick column (tau_ref > 4: extrapolation width
+    class 0.06 M in the lower regions, 0.02 M above; 33 orders)."""
+    base = dict(nb_layers=96, nb_angles=251, atm_phase=("rayleigh", 0.0), aer_phase=("hg", 0.5))
+    for surface in ("specular", "lambert"):
+        scs = [sos.Scenario(mu0=0.5, tauStar_atm=0.124, tauStar_aer=0.0, grd_alb=0.15, surface=surface, **base),
+               sos.Scenario(mu0=0.37, tauStar_atm=0.6, tauStar_aer=0.9, alb_aer=0.8, alb_atm=0.9, grd_alb=0.3, surface=surface, **base),
+               sos.Scenario(mu0=0.9, tauStar_atm=0.3, tauStar_aer=0.2, alb_aer=1.0, grd_alb=0.0, surface=surface, **base),
+               sos.Scenario(mu0=0.2, tauStar_atm=0.05, tauStar_aer=0.01, alb_aer=0.95, grd_alb=1.0, surface=surface,
+                            z_up=60.0, z_down=30.0, **base)]
+        # scenarios 0-2 share the aerosol rows, scenario 3 has its own geometry -> two batches inside
+        got = sos.solve_scenarios(scs)
+        for sc, r in zip(scs, got):
+            ref = _oracle_solve(so, sos, sc)
+            assert r.n == ref["n"], (surface, sc.mu0, r.n, ref["n"])
+            assert relmax(r.I, ref["I"]) < TOL, (surface, sc.mu0)
+    thick = sos.Scenario(nb_layers=400, nb_angles=151, mu0=0.37, tauStar_atm=0.8, tauStar_aer=3.6, alb_aer=0.8, alb_atm=0.9,
+                         grd_alb=0.3, z_up=100.0, z_down=10.0, surface="specular", atm_phase=("rayleigh", 0.0),
+                         aer_phase=("hg", 0.5))
+    r = sos.solve_scenarios([thick])[0]
+    ref = _oracle_solve(so, sos, thick)
+    assert r.n == ref["n"] and relmax(r.I, ref["I"]) < TOL
+
+
+def test_taylor_columns_three_regions_vs_oracle(sos, so):
+    """M = 1201: |mu| = 1/1200 < 1e-3 is a Taylor column, ten windowed columns (SOS_Aer_In_limit.py:79-107)."""
+    sc = sos.Scenario(nb_layers=64, nb_angles=1201, mu0=0.5, tauStar_atm=0.03, tauStar_aer=0.02, grd_alb=0.4, alb_aer=0.9,
+                      atm_phase=("iso", 0.0), aer_phase=("iso", 0.0), surface="specular")
+    r = sos.solve_scenarios([sc])[0]
+    ref = _oracle_solve(so, sos, sc, atm=("iso", 0.0), aer=("iso", 0.0))
+    assert r.n == ref["n"]
+    assert relmax(r.I, ref["I"]) < TOL
