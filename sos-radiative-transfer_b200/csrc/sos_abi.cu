@@ -87,7 +87,6 @@ struct sos_plan {
   double* d_colint = nullptr;  // [N] column integrals of the device phase builder
   int* h_poll = nullptr;     // pinned
   std::vector<sos_scenario> scen_h;
-  std::vector<int> chunk_start_h;
   // GEMM
   int gemm_bm = 0;  // rows per tile
   sosgemm::GroupTable groups;
@@ -97,12 +96,8 @@ struct sos_plan {
   int* d_work_counter = nullptr;
   int* d_order = nullptr;        // device-side order counter (sos_converge with order < 0)
   int nseg[2] = {0, 0};
-  long long max_row_tiles = 0;
-  const double* phase_ptr[SOS_MAX_PHASE];
-  int n_phase = 0;
   int lda = 0;
   sosgemm::GemmParams gp;
-  const double* gp_I = nullptr;  // operand the I tensor map was encoded for
   std::map<const void*, CUtensorMap> map_cache;
   bool maps_A_ready = false;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
@@ -314,7 +309,6 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   cregion.push_back(grid->n_regions);  // sentinel: chunk_region[nchunks] differs from the last region
   for (int c = 0; c < nch; ++c)
     for (int t = cstart[c]; t < cstart[c + 1]; ++t) rowchunk[t] = c;
-  p->chunk_start_h = cstart;
 
   // ---- mu-grid constants ----
   std::vector<double> w(N, 0.0);
@@ -582,11 +576,9 @@ int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
   const int bn = sosgemm::Cfg<2, 4, 4>::BN_PAD;  // rows are loaded 8 columns wider than the tile (bank layout)
   for (int i = 0; i < n; ++i) {
     if (!A_d[i] || (reinterpret_cast<uintptr_t>(A_d[i]) & 15)) return SOS_ERR_INVALID;
-    p->phase_ptr[i] = A_d[i];
     int r = encode_2d(&p->gp.map_A[i], A_d[i], p->N, p->N, lda, bn, sosgemm::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r) return r;
   }
-  p->n_phase = n;
   p->lda = lda;
   p->maps_A_ready = true;
   return SOS_OK;
