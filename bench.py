@@ -289,10 +289,25 @@ def main():
     lib.sos_fp64_peak(0, 3, C.byref(pk_dfma))
     peak = max(pk.value, pk_dfma.value)
     sweep_bytes = 32.0 * float(np.sum(n_orders - 1)) * L * N * args.steps
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (all 96 scenarios
+    # active: one launch of order 2), scaled to the average number of active scenarios per timed launch
+    traffic = None
+    traffic_note = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")) as f:
+            tj = json.load(f)
+        active_per_launch = float(np.sum(n_orders - 1)) * args.steps / max(gemm_launches, 1)
+        traffic = tj["dram_bytes_per_active_scenario"] * active_per_launch
+        traffic_note = ("dram__bytes_read+write per launch from profiles/r01_ncu_gemm_traffic.json (%.3e B at %d active "
+                        "scenarios; algorithmic %.3e B) scaled to %.1f active scenarios per timed launch"
+                        % (tj["dram_bytes_per_launch"], tj["scenarios"], tj["algorithmic_bytes_per_launch"], active_per_launch))
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
-        "bound": "tensor", "kernel": "jn_gemm_kernel (FP64 source contraction)",
+        "bound": "tensor", "kernel": "jn_gemm_dmma_kernel (FP64 source contraction, DMMA m8n8k4)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_note,
+        "algorithmic_flops_per_launch": flops / max(gemm_launches, 1),
         "peak_source": "FP64 DMMA m8n8k4 loop measured on this GPU in this run (sos_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 entry; DFMA loop measured %.1f TFLOP/s" % pk_dfma.value,
         "gemm_ms_per_launch": gemm_ms / max(gemm_launches, 1), "gemm_launches": gemm_launches,
