@@ -464,7 +464,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   }
   if ((N + 32) * sizeof(double) > 48 * 1024) {
     cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
-    cudaFuncSetAttribute(sossweep::sweep_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
+    cudaFuncSetAttribute(sossweep::sweep_zone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
   }
   *out = p;
   return SOS_OK;
@@ -715,21 +715,28 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
 static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st) {
   const GridDev& g = p->dev;
   ProfSpan span(p, 1, st);
+  dim3 cgrid((g.N + sossweep::LOCAL_THREADS - 1) / sossweep::LOCAL_THREADS, g.nchunks, g.S);
   {
-    dim3 grid((g.N + sossweep::LOCAL_THREADS - 1) / sossweep::LOCAL_THREADS, g.nchunks, g.S);
-    sossweep::sweep_local_kernel<<<grid, sossweep::LOCAL_THREADS, 0, st>>>(g, J_d, In_d, p->d_aggD, p->d_aggU);
+    sossweep::sweep_local_kernel<<<cgrid, sossweep::LOCAL_THREADS, 0, st>>>(g, J_d, p->d_aggD, p->d_aggU);
     int r = launch_check(p);
     if (r) return r;
   }
-  const size_t smem = (g.N + 32) * sizeof(double);
   {
+    const size_t smem = (g.N + 32) * sizeof(double);
     sossweep::sweep_carry_kernel<<<g.S, sossweep::CARRY_THREADS, smem, st>>>(g, J_d, p->d_aggD, p->d_aggU, p->d_carryD, p->d_carryU);
     int r = launch_check(p);
     if (r) return r;
   }
   {
+    sossweep::sweep_apply_kernel<<<cgrid, sossweep::LOCAL_THREADS, 0, st>>>(g, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
+    int r = launch_check(p);
+    if (r) return r;
+  }
+  {
+    // zone buffer: at most (M - zone_lo) + ZONE_UP + 3 doubles; M is a safe bound for the first term
+    const size_t smem = (static_cast<size_t>(g.M) + sossweep::ZONE_UP + 3 + 32) * sizeof(double);
     dim3 grid(g.L, g.S);
-    sossweep::sweep_finalize_kernel<<<grid, sossweep::ROW_THREADS, smem, st>>>(g, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
+    sossweep::sweep_zone_kernel<<<grid, sossweep::ZONE_THREADS, smem, st>>>(g, J_d, In_d, I_d, saved_d);
     int r = launch_check(p);
     if (r) return r;
   }

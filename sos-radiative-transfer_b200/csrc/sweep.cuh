@@ -6,17 +6,19 @@
 //     down:  D_t = D_{t-1} a_t - dtau_t/(2 mu) (J_{t-1} a_t + J_t)
 //     up:    U_t = U_{t+1} a_t + s_t dtau_t/(2 mu) (J_t + J_{t+1} a_t)      (s_t = 0 on carry gaps)
 // which is evaluated here as a chunked scan in three launches:
-//   1. sweep_local   every (scenario, chunk, mu column) runs its chunk from a zero carry; because the
-//                    products of a_t telescope to exp((tau_t - tau_start)/mu) the chunk aggregate is
-//                    just the last local value.
+//   1. sweep_local   every (scenario, chunk, mu column) runs its chunk from a zero carry and keeps only
+//                    the chunk aggregate = the last local value (the products of a_t telescope to
+//                    exp((tau_t - tau_start)/mu), so no separate "a" aggregate is needed); reads J once.
 //   2. sweep_carry   one CTA per scenario chains the chunk carries (down), finishes the surface row
 //                    (mu->0 columns + extrapolation), applies the specular/Lambert coupling, chains the
 //                    up carries and re-seeds them from the *blended* boundary rows.
-//   3. sweep_finalize one CTA per (scenario, layer) adds carry*exp(...), evaluates the windowed /
-//                    Taylor columns (SOS_Aer_In_limit.py:70-109), the polynomial extrapolation
-//                    (:113-141, a fixed linear map W), the find-first second-difference blend
-//                    (SOS_Aer_I1_In.py:101-108), accumulates I += I_n (SOS_Aer_main_specular.py:454-456)
-//                    and reduces the convergence ratios of :309.
+//   3. sweep_apply   the same (scenario, chunk, column) threads rerun the recurrence from the TRUE carry,
+//                    write I_n and accumulate I += I_n (SOS_Aer_main_specular.py:454-456) in one pass;
+//      sweep_zone    one small CTA per (scenario, layer) finishes the ~160 columns next to mu = 0:
+//                    windowed / Taylor columns (SOS_Aer_In_limit.py:70-109), the polynomial
+//                    extrapolation (:113-141, a fixed linear map W), the find-first second-difference
+//                    blend (SOS_Aer_I1_In.py:101-108) and the convergence ratios of :309.
+//   Traffic: J 8 (pass 1) + J 8 + I_n 8 + I 16 (pass 3) = 40 B per element (32 B is the algorithmic minimum).
 #pragma once
 #include "common.cuh"
 
@@ -30,8 +32,7 @@ constexpr int CARRY_THREADS = 1024;
 // 1. chunk-local recurrences
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LOCAL_THREADS)
-sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
-                   double* __restrict__ aggD, double* __restrict__ aggU) {
+sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ aggD, double* __restrict__ aggU) {
   const int s = blockIdx.z;
   if (!g.state[s].active) return;
   const int c = blockIdx.y;
@@ -41,7 +42,6 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
   const int L = g.L, M = g.M, ld = g.ld;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
   const double* __restrict__ Js = J + static_cast<size_t>(s) * L * ld;
-  double* __restrict__ Is = In + static_cast<size_t>(s) * L * ld;
   const double mu = g.mu[m];
   const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
 
@@ -52,7 +52,6 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
     double Jp;
     if (t == 0) {
       Jp = Js[m];
-      Is[m] = 0.0;  // trapezoid over a single point
       t = 1;
     } else {
       Jp = Js[static_cast<size_t>(t - 1) * ld + m];
@@ -72,13 +71,9 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double b2 = (d2 * 0.5) * (j1 * a2 + j2) / mu;
       const double b3 = (d3 * 0.5) * (j2 * a3 + j3) / mu;
       D = D * a0 - b0;
-      Is[static_cast<size_t>(t) * ld + m] = D;
       D = D * a1 - b1;
-      Is[static_cast<size_t>(t + 1) * ld + m] = D;
       D = D * a2 - b2;
-      Is[static_cast<size_t>(t + 2) * ld + m] = D;
       D = D * a3 - b3;
-      Is[static_cast<size_t>(t + 3) * ld + m] = D;
       Jp = j3;
       tp = tc3;
     }
@@ -88,7 +83,6 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double d = tc - tp;
       const double a = exp(d / mu);
       D = D * a - (d * 0.5) * (Jp * a + jc) / mu;
-      Is[static_cast<size_t>(t) * ld + m] = D;
       Jp = jc;
       tp = tc;
     }
@@ -100,7 +94,6 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
     if (t == L - 1) {
       Jn = Js[static_cast<size_t>(t) * ld + m];
       tn = tau[t];
-      Is[static_cast<size_t>(t) * ld + m] = 0.0;  // zero-length integral; the surface seed is a carry
       --t;
     } else {
       Jn = Js[static_cast<size_t>(t + 1) * ld + m];
@@ -108,7 +101,6 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       // chunk ends at a region boundary: the slice stops one row short of the carry row
       // (SOS_Aer_main_specular.py:413,433) -> pure attenuation, no source on this step
       if (g.chunk_region[c + 1] != g.chunk_region[c]) {
-        Is[static_cast<size_t>(t) * ld + m] = 0.0;
         Jn = Js[static_cast<size_t>(t) * ld + m];
         tn = tau[t];
         --t;
@@ -127,13 +119,9 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double b2 = (d2 * 0.5) * (j2 + j1 * a2) / mu;
       const double b3 = (d3 * 0.5) * (j3 + j2 * a3) / mu;
       U = U * a0 + b0;
-      Is[static_cast<size_t>(t) * ld + m] = U;
       U = U * a1 + b1;
-      Is[static_cast<size_t>(t - 1) * ld + m] = U;
       U = U * a2 + b2;
-      Is[static_cast<size_t>(t - 2) * ld + m] = U;
       U = U * a3 + b3;
-      Is[static_cast<size_t>(t - 3) * ld + m] = U;
       Jn = j3;
       tn = tc3;
     }
@@ -143,7 +131,6 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double d = tn - tc;
       const double a = exp(-d / mu);
       U = U * a + (d * 0.5) * (jc + Jn * a) / mu;
-      Is[static_cast<size_t>(t) * ld + m] = U;
       Jn = jc;
       tn = tc;
     }
@@ -398,49 +385,193 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
 }
 
 // ------------------------------------------------------------------------------------------
-// 3. finalize rows
+// 3. apply the carries (chunk x column threads) and finish the mu -> 0 zone (row CTAs)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS)
-sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
-                      const double* __restrict__ carryD, const double* __restrict__ carryU,
-                      double* __restrict__ I, double* __restrict__ saved) {
-  extern __shared__ double sm_row[];  // [N] + scratch[32]
+constexpr int ZONE_UP = 128;    // upward columns [M, M + ZONE_UP) are finished row-wise by sweep_zone_kernel
+constexpr int ZONE_THREADS = 128;
+
+// first downward column of the row-wise zone: all non-standard columns, the extrapolation targets and
+// their sources (largest width of the scenario)
+__device__ __forceinline__ int zone_lo(const GridDev& g, const sos_scenario& sc) {
+  int w = 0;
+  for (int k = 0; k < g.nreg; ++k) w = max(w, sc.extrap_width[k]);
+  const int ns = (w <= 0) ? 0 : (w < 2 ? 2 : min(5, w));
+  return max(0, min(g.first_small, g.M - w - ns));
+}
+
+// Second sweep pass: the same recurrences as sweep_local_kernel, now started from the TRUE carry of the
+// chunk, writing the final I_n and accumulating I += I_n in the same pass (J 8 + I_n 8 + I 16 bytes per
+// element).  Columns of the mu -> 0 zone only get their raw value stored; sweep_zone_kernel finishes them.
+__global__ void __launch_bounds__(LOCAL_THREADS)
+sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
+                   const double* __restrict__ carryD, const double* __restrict__ carryU,
+                   double* __restrict__ I, double* __restrict__ saved) {
+  const int s = blockIdx.z;
+  if (!g.state[s].active) return;
+  const int c = blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= g.N || m < g.col0 || m >= g.col1) return;
+  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
+  const int L = g.L, M = g.M, ld = g.ld;
+  const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
+  const size_t fbase = static_cast<size_t>(s) * L * ld;
+  const double* __restrict__ Js = J + fbase;
+  double* __restrict__ Is = In + fbase;
+  double* __restrict__ Ia = I ? I + fbase : nullptr;
+  double* __restrict__ Sv = saved ? saved + fbase : nullptr;
+  const double mu = g.mu[m];
+  const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
+  const sos_scenario& sc = g.scen[s];
+
+#define SOS_EMIT(T_, V_)                                             \
+  do {                                                               \
+    const size_t o_ = static_cast<size_t>(T_) * ld + m;              \
+    const double v_ = (V_);                                          \
+    Is[o_] = v_;                                                     \
+    if (!zone) {                                                     \
+      if (Sv) Sv[o_] = v_;                                           \
+      if (Ia) Ia[o_] += v_;                                          \
+    }                                                                \
+  } while (0)
+
+  if (m < M - 1) {
+    if (fabs(mu) < SOS_MU_THRESHOLD) return;
+    const bool zone = m >= zone_lo(g, sc);
+    double D = (t0 > 0) ? carryD[agg] : 0.0;
+    int t = t0;
+    double Jp;
+    if (t == 0) {
+      Jp = Js[m];
+      SOS_EMIT(0, 0.0);
+      t = 1;
+    } else {
+      Jp = Js[static_cast<size_t>(t - 1) * ld + m];
+    }
+    double tp = tau[t - 1 < 0 ? 0 : t - 1];
+    for (; t + 3 < t1; t += 4) {
+      const double tc0 = tau[t], tc1 = tau[t + 1], tc2 = tau[t + 2], tc3 = tau[t + 3];
+      const double j0 = Js[static_cast<size_t>(t) * ld + m];
+      const double j1 = Js[static_cast<size_t>(t + 1) * ld + m];
+      const double j2 = Js[static_cast<size_t>(t + 2) * ld + m];
+      const double j3 = Js[static_cast<size_t>(t + 3) * ld + m];
+      const double d0 = tc0 - tp, d1 = tc1 - tc0, d2 = tc2 - tc1, d3 = tc3 - tc2;
+      const double a0 = exp(d0 / mu), a1 = exp(d1 / mu), a2 = exp(d2 / mu), a3 = exp(d3 / mu);
+      const double b0 = (d0 * 0.5) * (Jp * a0 + j0) / mu;
+      const double b1 = (d1 * 0.5) * (j0 * a1 + j1) / mu;
+      const double b2 = (d2 * 0.5) * (j1 * a2 + j2) / mu;
+      const double b3 = (d3 * 0.5) * (j2 * a3 + j3) / mu;
+      D = D * a0 - b0; SOS_EMIT(t, D);
+      D = D * a1 - b1; SOS_EMIT(t + 1, D);
+      D = D * a2 - b2; SOS_EMIT(t + 2, D);
+      D = D * a3 - b3; SOS_EMIT(t + 3, D);
+      Jp = j3;
+      tp = tc3;
+    }
+    for (; t < t1; ++t) {
+      const double tc = tau[t];
+      const double jc = Js[static_cast<size_t>(t) * ld + m];
+      const double d = tc - tp;
+      const double a = exp(d / mu);
+      D = D * a - (d * 0.5) * (Jp * a + jc) / mu;
+      SOS_EMIT(t, D);
+      Jp = jc;
+      tp = tc;
+    }
+  } else if (m > M) {
+    const bool zone = m < M + ZONE_UP;
+    double U = carryU[agg];  // value at the carry row (t1, or the surface seed for the last chunk)
+    int t = t1 - 1;
+    double Jn, tn;
+    if (t == L - 1) {
+      Jn = Js[static_cast<size_t>(t) * ld + m];
+      tn = tau[t];
+      SOS_EMIT(t, U);  // zero-length integral: the surface row is the seed itself
+      --t;
+    } else {
+      Jn = Js[static_cast<size_t>(t + 1) * ld + m];
+      tn = tau[t + 1];
+      if (g.chunk_region[c + 1] != g.chunk_region[c]) {  // carry gap: pure attenuation on this step
+        const double tc = tau[t];
+        U = U * exp(-(tn - tc) / mu);
+        SOS_EMIT(t, U);
+        Jn = Js[static_cast<size_t>(t) * ld + m];
+        tn = tc;
+        --t;
+      }
+    }
+    for (; t - 3 >= t0; t -= 4) {
+      const double tc0 = tau[t], tc1 = tau[t - 1], tc2 = tau[t - 2], tc3 = tau[t - 3];
+      const double j0 = Js[static_cast<size_t>(t) * ld + m];
+      const double j1 = Js[static_cast<size_t>(t - 1) * ld + m];
+      const double j2 = Js[static_cast<size_t>(t - 2) * ld + m];
+      const double j3 = Js[static_cast<size_t>(t - 3) * ld + m];
+      const double d0 = tn - tc0, d1 = tc0 - tc1, d2 = tc1 - tc2, d3 = tc2 - tc3;
+      const double a0 = exp(-d0 / mu), a1 = exp(-d1 / mu), a2 = exp(-d2 / mu), a3 = exp(-d3 / mu);
+      const double b0 = (d0 * 0.5) * (j0 + Jn * a0) / mu;
+      const double b1 = (d1 * 0.5) * (j1 + j0 * a1) / mu;
+      const double b2 = (d2 * 0.5) * (j2 + j1 * a2) / mu;
+      const double b3 = (d3 * 0.5) * (j3 + j2 * a3) / mu;
+      U = U * a0 + b0; SOS_EMIT(t, U);
+      U = U * a1 + b1; SOS_EMIT(t - 1, U);
+      U = U * a2 + b2; SOS_EMIT(t - 2, U);
+      U = U * a3 + b3; SOS_EMIT(t - 3, U);
+      Jn = j3;
+      tn = tc3;
+    }
+    for (; t >= t0; --t) {
+      const double tc = tau[t];
+      const double jc = Js[static_cast<size_t>(t) * ld + m];
+      const double d = tn - tc;
+      const double a = exp(-d / mu);
+      U = U * a + (d * 0.5) * (jc + Jn * a) / mu;
+      SOS_EMIT(t, U);
+      Jn = jc;
+      tn = tc;
+    }
+  }
+#undef SOS_EMIT
+}
+
+// Row-wise finish of the mu -> 0 zone: windowed / Taylor columns (SOS_Aer_In_limit.py:70-109), the
+// extrapolation W (:113-141), I_n[t, mu=0+] = J (SOS_Aer_I1_In.py:100), the find-first second-difference
+// blend (:101-108), accumulation of the zone columns and, on the TOA / surface rows, the convergence
+// ratios of SOS_Aer_main_specular.py:309.  One CTA per (layer, scenario); it touches ~160 columns.
+__global__ void __launch_bounds__(ZONE_THREADS)
+sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
+                  double* __restrict__ I, double* __restrict__ saved) {
+  extern __shared__ double sm_zone[];  // [zone columns + 3] + scratch[32]
   __shared__ int found;
   const int s = blockIdx.y, t = blockIdx.x;
   if (!g.state[s].active) return;
-  const int L = g.L, M = g.M, N = g.N, ld = g.ld, nch = g.nchunks;
+  const int L = g.L, M = g.M, N = g.N, ld = g.ld;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
-  const double* __restrict__ Js = J + static_cast<size_t>(s) * L * ld;
-  double* __restrict__ Is = In + static_cast<size_t>(s) * L * ld;
+  const size_t fbase = static_cast<size_t>(s) * L * ld;
+  const double* __restrict__ Js = J + fbase;
+  double* __restrict__ Is = In + fbase;
+  double* __restrict__ Ia = I ? I + fbase : nullptr;
+  double* __restrict__ Sv = saved ? saved + fbase : nullptr;
   const sos_scenario sc = g.scen[s];
-  double* row = sm_row;
-  double* scratch = sm_row + N;
-  const int c = g.row_chunk[t];
-  const int region = g.chunk_region[c];
-  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
-  const size_t cbase = (static_cast<size_t>(s) * nch + c) * N;
-  const double tt = tau[t];
-  const double tdn = (t0 > 0) ? tau[t0 - 1] : 0.0;
-  const double tup = tau[(t1 == L) ? L - 1 : t1];
+  const int zl = zone_lo(g, sc);
+  const int zu = min(N, M + ZONE_UP);       // end of the row-wise upward zone
+  const int hib = min(N, zu + 3);           // raw values kept in shared memory: [zl, hib)
+  double* row = sm_zone - zl;               // row[m] is valid for m in [zl, hib)
+  double* scratch = sm_zone + (hib - zl);
+  const int region = g.chunk_region[g.row_chunk[t]];
   const size_t roff = static_cast<size_t>(t) * ld;
-
   const int c_lo = g.col0, c_hi = g.col1;
-  const bool own_down_zone = (c_lo < M && c_hi >= M);   // columns next to mu = 0- (validated at plan time)
-  const bool own_up_zone = (c_lo <= M && c_hi > M + 1);  // columns next to mu = 0+
-  for (int m = threadIdx.x; m < N; m += blockDim.x) {
-    const double mu = g.mu[m];
+  const bool own_down_zone = (c_lo < M && c_hi >= M);
+  const bool own_up_zone = (c_lo <= M && c_hi > M + 1);
+
+  for (int m = zl + threadIdx.x; m < hib; m += blockDim.x) {
     double v = 0.0;
-    if (m < c_lo || m >= c_hi) {
-      v = 0.0;
-    } else if (m < M - 1) {
-      if (fabs(mu) >= SOS_MU_THRESHOLD) {
+    if (m >= c_lo && m < c_hi) {
+      if (m < M - 1) {
+        if (fabs(g.mu[m]) >= SOS_MU_THRESHOLD) v = Is[roff + m];
+      } else if (m == M) {
+        v = Js[roff + M];
+      } else if (m > M) {
         v = Is[roff + m];
-        if (t0 > 0) v += carryD[cbase + m] * exp((tt - tdn) / mu);
       }
-    } else if (m > M) {
-      v = Is[roff + m] + carryU[cbase + m] * exp(-(tup - tt) / mu);
-    } else if (m == M) {
-      v = Js[roff + M];  // I_n[t, mu=0+] = J[t, mu=0+]  (SOS_Aer_I1_In.py:100)
     }
     row[m] = v;
   }
@@ -448,35 +579,76 @@ sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __r
 
   const int idxw = sc.extrap_width[region];
   if (own_down_zone) finish_down_row(g, row, Js, tau, t, region, idxw, width_class(g, idxw));
-  if (own_up_zone && !blend_up_row(g, row, &found) && threadIdx.x == 0)
-    atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
 
-  // ---- write I_n, accumulate, convergence ratios (SOS_Aer_main_specular.py:309,454-456) ----
-  const bool toa = (t == 0), surf = (t == L - 1);
-  double rmax = -INFINITY;
-  bool nonfinite = false;
-  double* __restrict__ Iacc = I ? I + static_cast<size_t>(s) * L * ld : nullptr;
-  double* __restrict__ sv = saved ? saved + static_cast<size_t>(s) * L * ld : nullptr;
-  for (int m = c_lo + threadIdx.x; m < c_hi; m += blockDim.x) {
-    const double v = row[m];
-    Is[roff + m] = v;
-    if (sv) sv[roff + m] = v;
-    if (Iacc) {
-      const double tot = Iacc[roff + m] + v;
-      Iacc[roff + m] = tot;
-      if ((toa && m >= M) || (surf && m < M)) {
-        const double r = v / tot;
-        if (isnan(r)) nonfinite = true; else rmax = fmax(rmax, r);
+  if (own_up_zone) {
+    // find-first over raw values: shared memory inside the zone, global memory (final = raw there) beyond
+    const int lim = c_hi;  // the search never leaves the owned columns
+    if (threadIdx.x == 0) found = 0x7fffffff;
+    __syncthreads();
+    for (int base = M + 1; base + 2 <= lim - 1; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      if (i + 2 <= lim - 1) {
+        const double a = (i < hib) ? row[i] : Is[roff + i];
+        const double b = (i + 1 < hib) ? row[i + 1] : Is[roff + i + 1];
+        const double cc = (i + 2 < hib) ? row[i + 2] : Is[roff + i + 2];
+        if (!(fabs((a - b) - (b - cc)) > SOS_BLEND_THRESHOLD)) atomicMin(&found, i);
+      }
+      __syncthreads();
+      const int f = found;
+      __syncthreads();
+      if (f != 0x7fffffff) break;
+    }
+    const int f = found;
+    if (f == 0x7fffffff) {
+      if (threadIdx.x == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
+    } else {
+      const int istar = f + 1;
+      const double v0 = row[M];
+      const double v1 = (istar < hib) ? row[istar] : Is[roff + istar];
+      const double mus = g.mu[istar];
+      __syncthreads();
+      for (int m = M + 1 + threadIdx.x; m < istar; m += blockDim.x) {
+        const double w = g.mu[m] / mus;
+        const double val = (1.0 - w) * v0 + w * v1;
+        if (m < zu) {
+          row[m] = val;
+        } else {
+          // beyond the zone the apply pass already stored and accumulated the raw value: replace it
+          const double old = Is[roff + m];
+          Is[roff + m] = val;
+          if (Sv) Sv[roff + m] = val;
+          if (Ia) Ia[roff + m] += (val - old);
+        }
       }
     }
+    __syncthreads();
   }
-  if (Iacc && (toa || surf)) {
-    // block max
+
+  // ---- store the zone columns, accumulate them ----
+  for (int m = max(zl, c_lo) + threadIdx.x; m < min(zu, c_hi); m += blockDim.x) {
+    const double v = row[m];
+    Is[roff + m] = v;
+    if (Sv) Sv[roff + m] = v;
+    if (Ia) Ia[roff + m] += v;
+  }
+
+  // ---- convergence ratios on the TOA / surface rows (whole half-row, read back from global) ----
+  const bool toa = (t == 0), surf = (t == L - 1);
+  if (Ia && (toa || surf)) {
+    __threadfence_block();
+    __syncthreads();
+    double rmax = -INFINITY;
+    bool nonfinite = false;
+    const int a0 = toa ? max(M, c_lo) : c_lo;
+    const int a1 = toa ? c_hi : min(M, c_hi);
+    for (int m = a0 + threadIdx.x; m < a1; m += blockDim.x) {
+      const double r = Is[roff + m] / Ia[roff + m];
+      if (isnan(r)) nonfinite = true; else rmax = fmax(rmax, r);
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
     nonfinite = __any_sync(0xffffffffu, nonfinite);
-    __syncthreads();
     if (lane == 0) scratch[warp] = nonfinite ? NAN : rmax;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -485,7 +657,6 @@ sweep_finalize_kernel(const GridDev g, const double* __restrict__ J, double* __r
       for (int w = 0; w < nwarps; ++w) {
         if (isnan(scratch[w])) nf = true; else r = fmax(r, scratch[w]);
       }
-      // a row can be both TOA and surface only if L == 1; not supported
       if (toa) g.state[s].ratio_toa = r;
       if (surf) g.state[s].ratio_surf = r;
       if (nf || r == INFINITY) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);  // -inf: no owned column

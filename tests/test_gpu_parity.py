@@ -429,3 +429,18 @@ def test_taylor_columns_three_regions_vs_oracle(sos, so):
     ref = _oracle_solve(so, sos, sc, atm=("iso", 0.0), aer=("iso", 0.0))
     assert r.n == ref["n"]
     assert relmax(r.I, ref["I"]) < TOL
+
+
+def test_long_blend_beyond_the_row_zone(sos, so):
+    """The find-first threshold is absolute (SOS_Aer_I1_In.py:103): a large source pushes the blend index
+    far from mu = 0+, past the 128 columns the row-wise kernel keeps in shared memory."""
+    L, M, ts = 48, 801, 0.3
+    mu = sos.mu_grid(M)
+    tau = np.linspace(0, ts, L)
+    Js = 100.0 * smooth_source(tau, mu, ts)
+    ref_idx = np.zeros(L, dtype=int)
+    lay = so.Layout(tau=tau, mu=mu, nb_angles=M, regions=[(0, L)], tau_ref=[ts], thick=False, surface="none", grd_alb=0.0)
+    ref = so.order_sweeps(lay, Js, method="recurrence", blend_index_out=ref_idx)
+    assert ref_idx.max() > M + 140, ref_idx.max()      # the case really leaves the zone
+    got = sos.In_NumInt(2, Js, Js, tau, mu, ts, 0.5, None, 1.0, M, 0, 0)
+    assert relmax(got, ref) < TOL
