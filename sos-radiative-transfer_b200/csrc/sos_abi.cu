@@ -464,7 +464,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   }
   if ((N + 32) * sizeof(double) > 48 * 1024) {
     cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
-    cudaFuncSetAttribute(sossweep::sweep_zone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
+
   }
   *out = p;
   return SOS_OK;
@@ -733,10 +733,13 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     if (r) return r;
   }
   {
-    // zone buffer: at most (M - zone_lo) + ZONE_UP + 3 doubles; M is a safe bound for the first term
-    const size_t smem = (static_cast<size_t>(g.M) + sossweep::ZONE_UP + 3 + 32) * sizeof(double);
-    dim3 grid(g.L, g.S);
-    sossweep::sweep_zone_kernel<<<grid, sossweep::ZONE_THREADS, smem, st>>>(g, J_d, In_d, I_d, saved_d);
+    // per-warp zone buffer: (M - zone_lo) + ZONE_UP + 3 doubles; the widest class (0.06 M) + 5 sources and
+    // the non-standard columns bound the first term
+    const int down = std::max(g.M - g.first_small, g.widx[3] + 6) + 1;
+    const int zone_buf = std::min(g.M, down) + sossweep::ZONE_UP + 3;
+    const size_t smem = static_cast<size_t>(zone_buf) * sossweep::ZONE_ROWS * sizeof(double);
+    dim3 grid((g.L + sossweep::ZONE_ROWS - 1) / sossweep::ZONE_ROWS, g.S);
+    sossweep::sweep_zone_kernel<<<grid, 32 * sossweep::ZONE_ROWS, smem, st>>>(g, J_d, In_d, I_d, saved_d, zone_buf);
     int r = launch_check(p);
     if (r) return r;
   }

@@ -24,6 +24,25 @@
 
 namespace sossweep {
 
+// exp(x) for the attenuation factors a_t = exp(-dtau/|mu|): almost every argument is tiny (dtau ~ 1e-4 ..
+// 3e-3 per layer), where a degree-8 Taylor polynomial is exact to < 1e-19 relative (|x| <= 2^-5:
+// x^9/9! < 1e-19) and costs 8 DFMA instead of the ~30 instructions of the general routine.  The two
+// scan passes are FP64-pipe bound, not HBM bound, without this.
+__device__ __forceinline__ double exp_small(double x) {
+  if (fabs(x) <= 0.03125) {
+    double p = 1.0 / 40320.0;
+    p = fma(p, x, 1.0 / 5040.0);
+    p = fma(p, x, 1.0 / 720.0);
+    p = fma(p, x, 1.0 / 120.0);
+    p = fma(p, x, 1.0 / 24.0);
+    p = fma(p, x, 1.0 / 6.0);
+    p = fma(p, x, 0.5);
+    p = fma(p, x, 1.0);
+    return fma(p, x, 1.0);
+  }
+  return exp(x);
+}
+
 constexpr int LOCAL_THREADS = 128;
 constexpr int ROW_THREADS = 256;
 constexpr int CARRY_THREADS = 1024;
@@ -43,6 +62,7 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
   const double* __restrict__ Js = J + static_cast<size_t>(s) * L * ld;
   const double mu = g.mu[m];
+  const double imu = 1.0 / mu;  // one division per thread; the scan steps multiply
   const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
 
   if (m < M - 1) {
@@ -65,11 +85,11 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double j2 = Js[static_cast<size_t>(t + 2) * ld + m];
       const double j3 = Js[static_cast<size_t>(t + 3) * ld + m];
       const double d0 = tc0 - tp, d1 = tc1 - tc0, d2 = tc2 - tc1, d3 = tc3 - tc2;
-      const double a0 = exp(d0 / mu), a1 = exp(d1 / mu), a2 = exp(d2 / mu), a3 = exp(d3 / mu);
-      const double b0 = (d0 * 0.5) * (Jp * a0 + j0) / mu;
-      const double b1 = (d1 * 0.5) * (j0 * a1 + j1) / mu;
-      const double b2 = (d2 * 0.5) * (j1 * a2 + j2) / mu;
-      const double b3 = (d3 * 0.5) * (j2 * a3 + j3) / mu;
+      const double a0 = exp_small(d0 * imu), a1 = exp_small(d1 * imu), a2 = exp_small(d2 * imu), a3 = exp_small(d3 * imu);
+      const double b0 = (d0 * 0.5) * (Jp * a0 + j0) * imu;
+      const double b1 = (d1 * 0.5) * (j0 * a1 + j1) * imu;
+      const double b2 = (d2 * 0.5) * (j1 * a2 + j2) * imu;
+      const double b3 = (d3 * 0.5) * (j2 * a3 + j3) * imu;
       D = D * a0 - b0;
       D = D * a1 - b1;
       D = D * a2 - b2;
@@ -81,8 +101,8 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double tc = tau[t];
       const double jc = Js[static_cast<size_t>(t) * ld + m];
       const double d = tc - tp;
-      const double a = exp(d / mu);
-      D = D * a - (d * 0.5) * (Jp * a + jc) / mu;
+      const double a = exp_small(d * imu);
+      D = D * a - (d * 0.5) * (Jp * a + jc) * imu;
       Jp = jc;
       tp = tc;
     }
@@ -113,11 +133,11 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double j2 = Js[static_cast<size_t>(t - 2) * ld + m];
       const double j3 = Js[static_cast<size_t>(t - 3) * ld + m];
       const double d0 = tn - tc0, d1 = tc0 - tc1, d2 = tc1 - tc2, d3 = tc2 - tc3;
-      const double a0 = exp(-d0 / mu), a1 = exp(-d1 / mu), a2 = exp(-d2 / mu), a3 = exp(-d3 / mu);
-      const double b0 = (d0 * 0.5) * (j0 + Jn * a0) / mu;
-      const double b1 = (d1 * 0.5) * (j1 + j0 * a1) / mu;
-      const double b2 = (d2 * 0.5) * (j2 + j1 * a2) / mu;
-      const double b3 = (d3 * 0.5) * (j3 + j2 * a3) / mu;
+      const double a0 = exp_small(-d0 * imu), a1 = exp_small(-d1 * imu), a2 = exp_small(-d2 * imu), a3 = exp_small(-d3 * imu);
+      const double b0 = (d0 * 0.5) * (j0 + Jn * a0) * imu;
+      const double b1 = (d1 * 0.5) * (j1 + j0 * a1) * imu;
+      const double b2 = (d2 * 0.5) * (j2 + j1 * a2) * imu;
+      const double b3 = (d3 * 0.5) * (j3 + j2 * a3) * imu;
       U = U * a0 + b0;
       U = U * a1 + b1;
       U = U * a2 + b2;
@@ -129,8 +149,8 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double tc = tau[t];
       const double jc = Js[static_cast<size_t>(t) * ld + m];
       const double d = tn - tc;
-      const double a = exp(-d / mu);
-      U = U * a + (d * 0.5) * (jc + Jn * a) / mu;
+      const double a = exp_small(-d * imu);
+      U = U * a + (d * 0.5) * (jc + Jn * a) * imu;
       Jn = jc;
       tn = tc;
     }
@@ -388,7 +408,6 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
 // 3. apply the carries (chunk x column threads) and finish the mu -> 0 zone (row CTAs)
 // ------------------------------------------------------------------------------------------
 constexpr int ZONE_UP = 128;    // upward columns [M, M + ZONE_UP) are finished row-wise by sweep_zone_kernel
-constexpr int ZONE_THREADS = 128;
 
 // first downward column of the row-wise zone: all non-standard columns, the extrapolation targets and
 // their sources (largest width of the scenario)
@@ -420,19 +439,22 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
   double* __restrict__ Ia = I ? I + fbase : nullptr;
   double* __restrict__ Sv = saved ? saved + fbase : nullptr;
   const double mu = g.mu[m];
+  const double imu = 1.0 / mu;  // one division per thread; the scan steps multiply
   const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
   const sos_scenario& sc = g.scen[s];
 
-#define SOS_EMIT(T_, V_)                                             \
+// store I_n (and I_saved); accumulate with the I value that was prefetched together with J
+#define SOS_EMIT(T_, V_, IOLD_)                                      \
   do {                                                               \
     const size_t o_ = static_cast<size_t>(T_) * ld + m;              \
     const double v_ = (V_);                                          \
     Is[o_] = v_;                                                     \
     if (!zone) {                                                     \
       if (Sv) Sv[o_] = v_;                                           \
-      if (Ia) Ia[o_] += v_;                                          \
+      if (Ia) Ia[o_] = (IOLD_) + v_;                                 \
     }                                                                \
   } while (0)
+#define SOS_IOLD(T_) ((Ia && !zone) ? Ia[static_cast<size_t>(T_) * ld + m] : 0.0)
 
   if (m < M - 1) {
     if (fabs(mu) < SOS_MU_THRESHOLD) return;
@@ -442,7 +464,7 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
     double Jp;
     if (t == 0) {
       Jp = Js[m];
-      SOS_EMIT(0, 0.0);
+      SOS_EMIT(0, 0.0, SOS_IOLD(0));
       t = 1;
     } else {
       Jp = Js[static_cast<size_t>(t - 1) * ld + m];
@@ -454,26 +476,28 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double j1 = Js[static_cast<size_t>(t + 1) * ld + m];
       const double j2 = Js[static_cast<size_t>(t + 2) * ld + m];
       const double j3 = Js[static_cast<size_t>(t + 3) * ld + m];
+      const double i0 = SOS_IOLD(t), i1 = SOS_IOLD(t + 1), i2 = SOS_IOLD(t + 2), i3 = SOS_IOLD(t + 3);
       const double d0 = tc0 - tp, d1 = tc1 - tc0, d2 = tc2 - tc1, d3 = tc3 - tc2;
-      const double a0 = exp(d0 / mu), a1 = exp(d1 / mu), a2 = exp(d2 / mu), a3 = exp(d3 / mu);
-      const double b0 = (d0 * 0.5) * (Jp * a0 + j0) / mu;
-      const double b1 = (d1 * 0.5) * (j0 * a1 + j1) / mu;
-      const double b2 = (d2 * 0.5) * (j1 * a2 + j2) / mu;
-      const double b3 = (d3 * 0.5) * (j2 * a3 + j3) / mu;
-      D = D * a0 - b0; SOS_EMIT(t, D);
-      D = D * a1 - b1; SOS_EMIT(t + 1, D);
-      D = D * a2 - b2; SOS_EMIT(t + 2, D);
-      D = D * a3 - b3; SOS_EMIT(t + 3, D);
+      const double a0 = exp_small(d0 * imu), a1 = exp_small(d1 * imu), a2 = exp_small(d2 * imu), a3 = exp_small(d3 * imu);
+      const double b0 = (d0 * 0.5) * (Jp * a0 + j0) * imu;
+      const double b1 = (d1 * 0.5) * (j0 * a1 + j1) * imu;
+      const double b2 = (d2 * 0.5) * (j1 * a2 + j2) * imu;
+      const double b3 = (d3 * 0.5) * (j2 * a3 + j3) * imu;
+      D = D * a0 - b0; SOS_EMIT(t, D, i0);
+      D = D * a1 - b1; SOS_EMIT(t + 1, D, i1);
+      D = D * a2 - b2; SOS_EMIT(t + 2, D, i2);
+      D = D * a3 - b3; SOS_EMIT(t + 3, D, i3);
       Jp = j3;
       tp = tc3;
     }
     for (; t < t1; ++t) {
       const double tc = tau[t];
       const double jc = Js[static_cast<size_t>(t) * ld + m];
+      const double io = SOS_IOLD(t);
       const double d = tc - tp;
-      const double a = exp(d / mu);
-      D = D * a - (d * 0.5) * (Jp * a + jc) / mu;
-      SOS_EMIT(t, D);
+      const double a = exp_small(d * imu);
+      D = D * a - (d * 0.5) * (Jp * a + jc) * imu;
+      SOS_EMIT(t, D, io);
       Jp = jc;
       tp = tc;
     }
@@ -485,7 +509,7 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
     if (t == L - 1) {
       Jn = Js[static_cast<size_t>(t) * ld + m];
       tn = tau[t];
-      SOS_EMIT(t, U);  // zero-length integral: the surface row is the seed itself
+      SOS_EMIT(t, U, SOS_IOLD(t));  // zero-length integral: the surface row is the seed itself
       --t;
     } else {
       Jn = Js[static_cast<size_t>(t + 1) * ld + m];
@@ -493,7 +517,7 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       if (g.chunk_region[c + 1] != g.chunk_region[c]) {  // carry gap: pure attenuation on this step
         const double tc = tau[t];
         U = U * exp(-(tn - tc) / mu);
-        SOS_EMIT(t, U);
+        SOS_EMIT(t, U, SOS_IOLD(t));
         Jn = Js[static_cast<size_t>(t) * ld + m];
         tn = tc;
         --t;
@@ -505,45 +529,51 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       const double j1 = Js[static_cast<size_t>(t - 1) * ld + m];
       const double j2 = Js[static_cast<size_t>(t - 2) * ld + m];
       const double j3 = Js[static_cast<size_t>(t - 3) * ld + m];
+      const double i0 = SOS_IOLD(t), i1 = SOS_IOLD(t - 1), i2 = SOS_IOLD(t - 2), i3 = SOS_IOLD(t - 3);
       const double d0 = tn - tc0, d1 = tc0 - tc1, d2 = tc1 - tc2, d3 = tc2 - tc3;
-      const double a0 = exp(-d0 / mu), a1 = exp(-d1 / mu), a2 = exp(-d2 / mu), a3 = exp(-d3 / mu);
-      const double b0 = (d0 * 0.5) * (j0 + Jn * a0) / mu;
-      const double b1 = (d1 * 0.5) * (j1 + j0 * a1) / mu;
-      const double b2 = (d2 * 0.5) * (j2 + j1 * a2) / mu;
-      const double b3 = (d3 * 0.5) * (j3 + j2 * a3) / mu;
-      U = U * a0 + b0; SOS_EMIT(t, U);
-      U = U * a1 + b1; SOS_EMIT(t - 1, U);
-      U = U * a2 + b2; SOS_EMIT(t - 2, U);
-      U = U * a3 + b3; SOS_EMIT(t - 3, U);
+      const double a0 = exp_small(-d0 * imu), a1 = exp_small(-d1 * imu), a2 = exp_small(-d2 * imu), a3 = exp_small(-d3 * imu);
+      const double b0 = (d0 * 0.5) * (j0 + Jn * a0) * imu;
+      const double b1 = (d1 * 0.5) * (j1 + j0 * a1) * imu;
+      const double b2 = (d2 * 0.5) * (j2 + j1 * a2) * imu;
+      const double b3 = (d3 * 0.5) * (j3 + j2 * a3) * imu;
+      U = U * a0 + b0; SOS_EMIT(t, U, i0);
+      U = U * a1 + b1; SOS_EMIT(t - 1, U, i1);
+      U = U * a2 + b2; SOS_EMIT(t - 2, U, i2);
+      U = U * a3 + b3; SOS_EMIT(t - 3, U, i3);
       Jn = j3;
       tn = tc3;
     }
     for (; t >= t0; --t) {
       const double tc = tau[t];
       const double jc = Js[static_cast<size_t>(t) * ld + m];
+      const double io = SOS_IOLD(t);
       const double d = tn - tc;
-      const double a = exp(-d / mu);
-      U = U * a + (d * 0.5) * (jc + Jn * a) / mu;
-      SOS_EMIT(t, U);
+      const double a = exp_small(-d * imu);
+      U = U * a + (d * 0.5) * (jc + Jn * a) * imu;
+      SOS_EMIT(t, U, io);
       Jn = jc;
       tn = tc;
     }
   }
+#undef SOS_IOLD
 #undef SOS_EMIT
 }
 
 // Row-wise finish of the mu -> 0 zone: windowed / Taylor columns (SOS_Aer_In_limit.py:70-109), the
 // extrapolation W (:113-141), I_n[t, mu=0+] = J (SOS_Aer_I1_In.py:100), the find-first second-difference
 // blend (:101-108), accumulation of the zone columns and, on the TOA / surface rows, the convergence
-// ratios of SOS_Aer_main_specular.py:309.  One CTA per (layer, scenario); it touches ~160 columns.
-__global__ void __launch_bounds__(ZONE_THREADS)
+// ratios of SOS_Aer_main_specular.py:309.  ONE WARP per (layer, scenario) -- the zone is ~160 columns, so
+// warp shuffles / ballots replace every block-level barrier; ZONE_ROWS warps share a CTA.
+constexpr int ZONE_ROWS = 8;
+
+__global__ void __launch_bounds__(32 * ZONE_ROWS)
 sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
-                  double* __restrict__ I, double* __restrict__ saved) {
-  extern __shared__ double sm_zone[];  // [zone columns + 3] + scratch[32]
-  __shared__ int found;
-  const int s = blockIdx.y, t = blockIdx.x;
-  if (!g.state[s].active) return;
+                  double* __restrict__ I, double* __restrict__ saved, int zone_buf) {
+  extern __shared__ double sm_zone[];  // ZONE_ROWS x zone_buf
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.y, t = blockIdx.x * ZONE_ROWS + warp;
   const int L = g.L, M = g.M, N = g.N, ld = g.ld;
+  if (t >= L || !g.state[s].active) return;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
   const size_t fbase = static_cast<size_t>(s) * L * ld;
   const double* __restrict__ Js = J + fbase;
@@ -554,15 +584,14 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
   const int zl = zone_lo(g, sc);
   const int zu = min(N, M + ZONE_UP);       // end of the row-wise upward zone
   const int hib = min(N, zu + 3);           // raw values kept in shared memory: [zl, hib)
-  double* row = sm_zone - zl;               // row[m] is valid for m in [zl, hib)
-  double* scratch = sm_zone + (hib - zl);
+  double* row = sm_zone + static_cast<size_t>(warp) * zone_buf - zl;  // row[m] valid for m in [zl, hib)
   const int region = g.chunk_region[g.row_chunk[t]];
   const size_t roff = static_cast<size_t>(t) * ld;
   const int c_lo = g.col0, c_hi = g.col1;
   const bool own_down_zone = (c_lo < M && c_hi >= M);
   const bool own_up_zone = (c_lo <= M && c_hi > M + 1);
 
-  for (int m = zl + threadIdx.x; m < hib; m += blockDim.x) {
+  for (int m = zl + lane; m < hib; m += 32) {
     double v = 0.0;
     if (m >= c_lo && m < c_hi) {
       if (m < M - 1) {
@@ -575,39 +604,56 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
     }
     row[m] = v;
   }
-  __syncthreads();
+  __syncwarp();
 
-  const int idxw = sc.extrap_width[region];
-  if (own_down_zone) finish_down_row(g, row, Js, tau, t, region, idxw, width_class(g, idxw));
+  if (own_down_zone) {
+    const int idxw = sc.extrap_width[region];
+    const int r0 = g.rstart[region];
+    // non-standard columns that survive the extrapolation (those >= M - idx are overwritten below)
+    const int hi = min(M - 1, M - idxw);
+    for (int m = g.first_small; m < hi; ++m) {
+      const double v = asymptotic_column(g, Js, tau, t, r0, m);
+      if (lane == 0) row[m] = v;
+    }
+    __syncwarp();
+    if (idxw > 0) {
+      const int wclass = width_class(g, idxw);
+      const int ns = g.wns[wclass];
+      const int src0 = (idxw < 2) ? (M - idxw - 2) : (M - idxw - ns);
+      const double* __restrict__ W = g.W + g.woff[wclass];
+      for (int i = lane; i < idxw; i += 32) {
+        double v = 0.0;
+        for (int k = 0; k < ns; ++k) v += W[i * ns + k] * row[src0 + k];
+        row[M - 1 - i] = v;  // sources (< M - idx) and targets (>= M - idx) never overlap
+      }
+    }
+    __syncwarp();
+  }
 
   if (own_up_zone) {
     // find-first over raw values: shared memory inside the zone, global memory (final = raw there) beyond
     const int lim = c_hi;  // the search never leaves the owned columns
-    if (threadIdx.x == 0) found = 0x7fffffff;
-    __syncthreads();
-    for (int base = M + 1; base + 2 <= lim - 1; base += blockDim.x) {
-      const int i = base + threadIdx.x;
+    int istar = -1;
+    for (int base = M + 1; base + 2 <= lim - 1 && istar < 0; base += 32) {
+      const int i = base + lane;
+      bool hit = false;
       if (i + 2 <= lim - 1) {
         const double a = (i < hib) ? row[i] : Is[roff + i];
         const double b = (i + 1 < hib) ? row[i + 1] : Is[roff + i + 1];
         const double cc = (i + 2 < hib) ? row[i + 2] : Is[roff + i + 2];
-        if (!(fabs((a - b) - (b - cc)) > SOS_BLEND_THRESHOLD)) atomicMin(&found, i);
+        hit = !(fabs((a - b) - (b - cc)) > SOS_BLEND_THRESHOLD);
       }
-      __syncthreads();
-      const int f = found;
-      __syncthreads();
-      if (f != 0x7fffffff) break;
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (mask) istar = base + __ffs(mask) - 1 + 1;
     }
-    const int f = found;
-    if (f == 0x7fffffff) {
-      if (threadIdx.x == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
+    if (istar < 0) {
+      if (lane == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
     } else {
-      const int istar = f + 1;
       const double v0 = row[M];
       const double v1 = (istar < hib) ? row[istar] : Is[roff + istar];
       const double mus = g.mu[istar];
-      __syncthreads();
-      for (int m = M + 1 + threadIdx.x; m < istar; m += blockDim.x) {
+      __syncwarp();
+      for (int m = M + 1 + lane; m < istar; m += 32) {
         const double w = g.mu[m] / mus;
         const double val = (1.0 - w) * v0 + w * v1;
         if (m < zu) {
@@ -621,11 +667,11 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 
   // ---- store the zone columns, accumulate them ----
-  for (int m = max(zl, c_lo) + threadIdx.x; m < min(zu, c_hi); m += blockDim.x) {
+  for (int m = max(zl, c_lo) + lane; m < min(zu, c_hi); m += 32) {
     const double v = row[m];
     Is[roff + m] = v;
     if (Sv) Sv[roff + m] = v;
@@ -636,30 +682,22 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
   const bool toa = (t == 0), surf = (t == L - 1);
   if (Ia && (toa || surf)) {
     __threadfence_block();
-    __syncthreads();
+    __syncwarp();
     double rmax = -INFINITY;
     bool nonfinite = false;
     const int a0 = toa ? max(M, c_lo) : c_lo;
     const int a1 = toa ? c_hi : min(M, c_hi);
-    for (int m = a0 + threadIdx.x; m < a1; m += blockDim.x) {
+    for (int m = a0 + lane; m < a1; m += 32) {
       const double r = Is[roff + m] / Ia[roff + m];
       if (isnan(r)) nonfinite = true; else rmax = fmax(rmax, r);
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
     nonfinite = __any_sync(0xffffffffu, nonfinite);
-    if (lane == 0) scratch[warp] = nonfinite ? NAN : rmax;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double r = -INFINITY;
-      bool nf = false;
-      for (int w = 0; w < nwarps; ++w) {
-        if (isnan(scratch[w])) nf = true; else r = fmax(r, scratch[w]);
-      }
-      if (toa) g.state[s].ratio_toa = r;
-      if (surf) g.state[s].ratio_surf = r;
-      if (nf || r == INFINITY) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);  // -inf: no owned column
+    if (lane == 0) {
+      if (toa) g.state[s].ratio_toa = rmax;
+      if (surf) g.state[s].ratio_surf = rmax;
+      if (nonfinite || rmax == INFINITY) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);  // -inf: no owned column
     }
   }
 }
