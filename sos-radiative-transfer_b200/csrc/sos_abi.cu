@@ -733,10 +733,10 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     if (r) return r;
   }
   {
-    // per-warp zone buffer: (M - zone_lo) + ZONE_UP + 3 doubles; the widest class (0.06 M) + 5 sources and
-    // the non-standard columns bound the first term
+    // per-warp buffer of the raw downward values next to mu = 0-: the widest extrapolation class (0.06 M) + 5
+    // sources, or all non-standard columns, whichever is more
     const int down = std::max(g.M - g.first_small, g.widx[3] + 6) + 1;
-    const int zone_buf = std::min(g.M, down) + sossweep::ZONE_UP + 3;
+    const int zone_buf = std::min(g.M, down);
     const size_t smem = static_cast<size_t>(zone_buf) * sossweep::ZONE_ROWS * sizeof(double);
     dim3 grid((g.L + sossweep::ZONE_ROWS - 1) / sossweep::ZONE_ROWS, g.S);
     sossweep::sweep_zone_kernel<<<grid, 32 * sossweep::ZONE_ROWS, smem, st>>>(g, J_d, In_d, I_d, saved_d, zone_buf);

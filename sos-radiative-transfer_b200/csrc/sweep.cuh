@@ -407,7 +407,6 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
 // ------------------------------------------------------------------------------------------
 // 3. apply the carries (chunk x column threads) and finish the mu -> 0 zone (row CTAs)
 // ------------------------------------------------------------------------------------------
-constexpr int ZONE_UP = 128;    // upward columns [M, M + ZONE_UP) are finished row-wise by sweep_zone_kernel
 
 // first downward column of the row-wise zone: all non-standard columns, the extrapolation targets and
 // their sources (largest width of the scenario)
@@ -420,7 +419,8 @@ __device__ __forceinline__ int zone_lo(const GridDev& g, const sos_scenario& sc)
 
 // Second sweep pass: the same recurrences as sweep_local_kernel, now started from the TRUE carry of the
 // chunk, writing the final I_n and accumulating I += I_n in the same pass (J 8 + I_n 8 + I 16 bytes per
-// element).  Columns of the mu -> 0 zone only get their raw value stored; sweep_zone_kernel finishes them.
+// element).  The few columns next to mu = 0 that the reference post-processes are corrected afterwards by
+// sweep_zone_kernel (it replaces the raw value in I_n and adds the difference to I).
 __global__ void __launch_bounds__(LOCAL_THREADS)
 sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
                    const double* __restrict__ carryD, const double* __restrict__ carryU,
@@ -441,7 +441,6 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
   const double mu = g.mu[m];
   const double imu = 1.0 / mu;  // one division per thread; the scan steps multiply
   const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
-  const sos_scenario& sc = g.scen[s];
 
 // store I_n (and I_saved); accumulate with the I value that was prefetched together with J
 #define SOS_EMIT(T_, V_, IOLD_)                                      \
@@ -449,16 +448,13 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
     const size_t o_ = static_cast<size_t>(T_) * ld + m;              \
     const double v_ = (V_);                                          \
     Is[o_] = v_;                                                     \
-    if (!zone) {                                                     \
-      if (Sv) Sv[o_] = v_;                                           \
-      if (Ia) Ia[o_] = (IOLD_) + v_;                                 \
-    }                                                                \
+    if (Sv) Sv[o_] = v_;                                             \
+    if (Ia) Ia[o_] = (IOLD_) + v_;                                   \
   } while (0)
-#define SOS_IOLD(T_) ((Ia && !zone) ? Ia[static_cast<size_t>(T_) * ld + m] : 0.0)
+#define SOS_IOLD(T_) (Ia ? Ia[static_cast<size_t>(T_) * ld + m] : 0.0)
 
   if (m < M - 1) {
     if (fabs(mu) < SOS_MU_THRESHOLD) return;
-    const bool zone = m >= zone_lo(g, sc);
     double D = (t0 > 0) ? carryD[agg] : 0.0;
     int t = t0;
     double Jp;
@@ -502,7 +498,6 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
       tp = tc;
     }
   } else if (m > M) {
-    const bool zone = m < M + ZONE_UP;
     double U = carryU[agg];  // value at the carry row (t1, or the surface seed for the last chunk)
     int t = t1 - 1;
     double Jn, tn;
@@ -559,20 +554,21 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
 #undef SOS_EMIT
 }
 
-// Row-wise finish of the mu -> 0 zone: windowed / Taylor columns (SOS_Aer_In_limit.py:70-109), the
-// extrapolation W (:113-141), I_n[t, mu=0+] = J (SOS_Aer_I1_In.py:100), the find-first second-difference
-// blend (:101-108), accumulation of the zone columns and, on the TOA / surface rows, the convergence
-// ratios of SOS_Aer_main_specular.py:309.  ONE WARP per (layer, scenario) -- the zone is ~160 columns, so
-// warp shuffles / ballots replace every block-level barrier; ZONE_ROWS warps share a CTA.
+// Row-wise post-processing of the columns next to mu = 0: windowed / Taylor columns
+// (SOS_Aer_In_limit.py:70-109), the extrapolation W (:113-141), I_n[t, mu=0+] = J (SOS_Aer_I1_In.py:100),
+// the find-first second-difference blend (:101-108) and, on the TOA / surface rows, the convergence
+// ratios of SOS_Aer_main_specular.py:309.  ONE WARP per (layer, scenario): it reads the ~40 raw values
+// it needs, rewrites only the columns that change and corrects I by (new - raw) for those the apply
+// pass had already accumulated.
 constexpr int ZONE_ROWS = 8;
 
 __global__ void __launch_bounds__(32 * ZONE_ROWS)
 sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
                   double* __restrict__ I, double* __restrict__ saved, int zone_buf) {
-  extern __shared__ double sm_zone[];  // ZONE_ROWS x zone_buf
+  extern __shared__ double sm_zone[];  // ZONE_ROWS x zone_buf: raw downward values of columns [zl, M)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.y, t = blockIdx.x * ZONE_ROWS + warp;
-  const int L = g.L, M = g.M, N = g.N, ld = g.ld;
+  const int L = g.L, M = g.M, ld = g.ld;
   if (t >= L || !g.state[s].active) return;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
   const size_t fbase = static_cast<size_t>(s) * L * ld;
@@ -581,39 +577,32 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
   double* __restrict__ Ia = I ? I + fbase : nullptr;
   double* __restrict__ Sv = saved ? saved + fbase : nullptr;
   const sos_scenario sc = g.scen[s];
-  const int zl = zone_lo(g, sc);
-  const int zu = min(N, M + ZONE_UP);       // end of the row-wise upward zone
-  const int hib = min(N, zu + 3);           // raw values kept in shared memory: [zl, hib)
-  double* row = sm_zone + static_cast<size_t>(warp) * zone_buf - zl;  // row[m] valid for m in [zl, hib)
   const int region = g.chunk_region[g.row_chunk[t]];
   const size_t roff = static_cast<size_t>(t) * ld;
   const int c_lo = g.col0, c_hi = g.col1;
   const bool own_down_zone = (c_lo < M && c_hi >= M);
   const bool own_up_zone = (c_lo <= M && c_hi > M + 1);
 
-  for (int m = zl + lane; m < hib; m += 32) {
-    double v = 0.0;
-    if (m >= c_lo && m < c_hi) {
-      if (m < M - 1) {
-        if (fabs(g.mu[m]) >= SOS_MU_THRESHOLD) v = Is[roff + m];
-      } else if (m == M) {
-        v = Js[roff + M];
-      } else if (m > M) {
-        v = Is[roff + m];
-      }
-    }
-    row[m] = v;
-  }
-  __syncwarp();
-
   if (own_down_zone) {
+    const int zl = zone_lo(g, sc);
+    double* row = sm_zone + static_cast<size_t>(warp) * zone_buf - zl;  // row[m] valid for m in [zl, M)
+    for (int m = zl + lane; m < M; m += 32) {
+      const bool std_col = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
+      row[m] = std_col ? Is[roff + m] : 0.0;  // raw (already stored and accumulated by the apply pass)
+    }
+    __syncwarp();
     const int idxw = sc.extrap_width[region];
     const int r0 = g.rstart[region];
-    // non-standard columns that survive the extrapolation (those >= M - idx are overwritten below)
+    // non-standard columns that survive the extrapolation: computed here, never touched by the apply pass
     const int hi = min(M - 1, M - idxw);
     for (int m = g.first_small; m < hi; ++m) {
       const double v = asymptotic_column(g, Js, tau, t, r0, m);
-      if (lane == 0) row[m] = v;
+      if (lane == 0) {
+        row[m] = v;
+        Is[roff + m] = v;
+        if (Sv) Sv[roff + m] = v;
+        if (Ia) Ia[roff + m] += v;
+      }
     }
     __syncwarp();
     if (idxw > 0) {
@@ -622,25 +611,36 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
       const int src0 = (idxw < 2) ? (M - idxw - 2) : (M - idxw - ns);
       const double* __restrict__ W = g.W + g.woff[wclass];
       for (int i = lane; i < idxw; i += 32) {
+        const int m = M - 1 - i;  // sources (< M - idx) and targets (>= M - idx) never overlap
         double v = 0.0;
         for (int k = 0; k < ns; ++k) v += W[i * ns + k] * row[src0 + k];
-        row[M - 1 - i] = v;  // sources (< M - idx) and targets (>= M - idx) never overlap
+        const bool std_col = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
+        Is[roff + m] = v;
+        if (Sv) Sv[roff + m] = v;
+        if (Ia) Ia[roff + m] += std_col ? (v - row[m]) : v;  // standard targets were accumulated raw
       }
+    } else if (lane == 0) {
+      Is[roff + M - 1] = 0.0;  // mu = 0- stays 0 when nothing is extrapolated
+      if (Sv) Sv[roff + M - 1] = 0.0;
     }
     __syncwarp();
   }
 
   if (own_up_zone) {
-    // find-first over raw values: shared memory inside the zone, global memory (final = raw there) beyond
+    const double v0 = Js[roff + M];  // I_n[t, mu = 0+] = J[t, mu = 0+]
+    if (lane == 0) {
+      Is[roff + M] = v0;
+      if (Sv) Sv[roff + M] = v0;
+      if (Ia) Ia[roff + M] += v0;
+    }
+    // find-first over the raw values written by the apply pass
     const int lim = c_hi;  // the search never leaves the owned columns
     int istar = -1;
     for (int base = M + 1; base + 2 <= lim - 1 && istar < 0; base += 32) {
       const int i = base + lane;
       bool hit = false;
       if (i + 2 <= lim - 1) {
-        const double a = (i < hib) ? row[i] : Is[roff + i];
-        const double b = (i + 1 < hib) ? row[i + 1] : Is[roff + i + 1];
-        const double cc = (i + 2 < hib) ? row[i + 2] : Is[roff + i + 2];
+        const double a = Is[roff + i], b = Is[roff + i + 1], cc = Is[roff + i + 2];
         hit = !(fabs((a - b) - (b - cc)) > SOS_BLEND_THRESHOLD);
       }
       const unsigned mask = __ballot_sync(0xffffffffu, hit);
@@ -649,33 +649,19 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
     if (istar < 0) {
       if (lane == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
     } else {
-      const double v0 = row[M];
-      const double v1 = (istar < hib) ? row[istar] : Is[roff + istar];
+      const double v1 = Is[roff + istar];
       const double mus = g.mu[istar];
-      __syncwarp();
+      __syncwarp();  // every lane has read what it needs before anything is overwritten
       for (int m = M + 1 + lane; m < istar; m += 32) {
         const double w = g.mu[m] / mus;
         const double val = (1.0 - w) * v0 + w * v1;
-        if (m < zu) {
-          row[m] = val;
-        } else {
-          // beyond the zone the apply pass already stored and accumulated the raw value: replace it
-          const double old = Is[roff + m];
-          Is[roff + m] = val;
-          if (Sv) Sv[roff + m] = val;
-          if (Ia) Ia[roff + m] += (val - old);
-        }
+        const double old = Is[roff + m];
+        Is[roff + m] = val;
+        if (Sv) Sv[roff + m] = val;
+        if (Ia) Ia[roff + m] += (val - old);
       }
     }
     __syncwarp();
-  }
-
-  // ---- store the zone columns, accumulate them ----
-  for (int m = max(zl, c_lo) + lane; m < min(zu, c_hi); m += 32) {
-    const double v = row[m];
-    Is[roff + m] = v;
-    if (Sv) Sv[roff + m] = v;
-    if (Ia) Ia[roff + m] += v;
   }
 
   // ---- convergence ratios on the TOA / surface rows (whole half-row, read back from global) ----
