@@ -286,10 +286,12 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   // ---- chunks: never straddle a region ----
   int chunk = grid->chunk_rows;
   if (chunk <= 0) {
-    // enough (scenario x chunk x column) threads to fill the chip, but chunks not shorter than 16 rows
+    // enough (scenario x chunk x column) threads to fill the chip
     const long long want = 4LL * p->n_sms * 2048;
     long long c = static_cast<long long>(S) * L * N / want;
-    chunk = static_cast<int>(std::max<long long>(16, std::min<long long>(128, c)));
+    // measured (tools/chunk_sweep.sh): 48-row chunks are the sweet spot for small batches -- shorter chunks
+    // lengthen the serial carry chain more than they help the two scan passes
+    chunk = static_cast<int>(std::max<long long>(48, std::min<long long>(128, c)));
     chunk = std::max(chunk, (L + 47) / 48);  // keep the serial carry chain short
   }
   std::vector<int> cstart, cregion, rowchunk(L);
