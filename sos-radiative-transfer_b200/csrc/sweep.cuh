@@ -66,7 +66,7 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
   const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
 
   if (m < M - 1) {
-    if (fabs(mu) < SOS_MU_THRESHOLD) return;  // windowed / Taylor columns are row-local (finalize)
+    if (fabs(mu) < SOS_MU_THRESHOLD) return;  // windowed / Taylor columns are row-local (sweep_zone_kernel)
     double D = 0.0;
     int t = t0;
     double Jp;
@@ -159,7 +159,7 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// row-level helpers shared by sweep_carry and sweep_finalize (one CTA works on one row in smem)
+// row-level helpers of sweep_carry_kernel (one CTA works on one row in smem)
 // ------------------------------------------------------------------------------------------
 
 // |mu| < MU_THRESHOLD downward column m at layer t (improved_asymptotic_downward_radiance,
