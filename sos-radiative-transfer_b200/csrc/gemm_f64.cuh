@@ -90,6 +90,8 @@ struct GemmParams {
   int nseg[2];
   int n_col_tiles;                   // column tiles this plan computes ...
   int ct0;                           // ... starting at this one (mu-block sharding)
+  int split_passes;                  // 1: the two operand passes of class-1 tiles are SEPARATE tiles that add their
+                                     //    scaled partial into a zeroed J (2 partials: order independent) -- small batches
   int seg_begin, seg_end;            // restrict every group to these segments of its list (row-chunked launches
                                      // that overlap the all-gather of the other chunks); [0, INT_MAX) = all
   int L, N, ld;
@@ -107,7 +109,8 @@ struct TileInfo {
   int valid[SEGS];       // valid rows (0 = empty segment)
   int ct;                // column tile
   int passes;            // 1 or 2
-  int pad[2];
+  int first_pass;        // operand of the first (or only) pass: 0 = A, 1 = B of the group
+  int atomic_out;        // 1: add into J instead of storing
 };
 
 template <int WM, int WN, int MB>
@@ -221,7 +224,11 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
       const int ct = p.ct0 + tile - rt * p.n_col_tiles;
       const int g = restricted ? 0 : find_group(plan, rt);
       const int cls = plan->group_cls[g];
-      const int lt = restricted ? rt + p.seg_begin / C::SEGS : rt - plan->group_tile_start[g];
+      int lt = restricted ? rt + p.seg_begin / C::SEGS : rt - plan->group_tile_start[g];
+      // split class-1 tiles: local tile index = 2 * row tile + pass
+      const bool split = p.split_passes && cls == 1;
+      const int only_pass = split ? (lt & 1) : 0;
+      if (split) lt >>= 1;
       // lanes 0..SEGS-1 own one I segment each, lane SEGS owns the operand tile
       SegRef sr;
       sr.scen = -1; sr.row = 0; sr.valid = 0;
@@ -234,7 +241,8 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
         double coef = 0.0, resc = 0.0;
         if (sr.scen >= 0) {
           const sos_scenario& sc = p.scen[sr.scen];
-          if (cls == 1) { coef = sc.coef_mix_aer; resc = sc.coef_mix_atm / sc.coef_mix_aer; }
+          if (cls == 1 && split) { coef = only_pass ? sc.coef_mix_aer : sc.coef_mix_atm; resc = 1.0; }
+          else if (cls == 1) { coef = sc.coef_mix_aer; resc = sc.coef_mix_atm / sc.coef_mix_aer; }
           else coef = sc.coef_atm;
         }
         info->coef[lane] = coef;
@@ -242,12 +250,12 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
         info->row[lane] = sr.row;
         info->valid[lane] = sr.valid;
       }
-      if (lane == 0) { info->ct = ct; info->passes = cls == 1 ? 2 : 1; }
+      const int passes = (cls == 1 && !split) ? 2 : 1;
+      if (lane == 0) { info->ct = ct; info->passes = passes; info->first_pass = only_pass; info->atomic_out = split ? 1 : 0; }
       __syncwarp();
       ++seq;
-      const int passes = cls == 1 ? 2 : 1;
       for (int pass = 0; pass < passes; ++pass) {
-        const CUtensorMap* mapA = &p.map_A[pass == 0 ? plan->group_phaseA[g] : plan->group_phaseB[g]];
+        const CUtensorMap* mapA = &p.map_A[(pass + only_pass) == 0 ? plan->group_phaseA[g] : plan->group_phaseB[g]];
         int owner = 0;
         for (int ks = 0; ks < ksteps; ++ks) {
           // fused all-gather: the k-range of this step is fetched straight from the GPU that owns those mu
@@ -299,6 +307,7 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
     ++seq;
     const int ct = info->ct;
     const int passes = info->passes;
+    const int atomic_out = info->atomic_out;
 
     double acc[MB][4][2];
 #pragma unroll
@@ -374,7 +383,10 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = col_base + 8 * q;
-          if (c + 1 < p.N) {
+          if (atomic_out) {
+            if (c < p.N) atomicAdd(out + c, coef * acc[i][q][0]);
+            if (c + 1 < p.N) atomicAdd(out + c + 1, coef * acc[i][q][1]);
+          } else if (c + 1 < p.N) {
             *reinterpret_cast<double2*>(out + c) = make_double2(coef * acc[i][q][0], coef * acc[i][q][1]);
           } else if (c < p.N) {
             out[c] = coef * acc[i][q][0];
@@ -399,7 +411,8 @@ struct GroupTable {
 
 __device__ __forceinline__ void plan_tiles_block(const GroupTable& gt, const int* __restrict__ members,
                                                  const ScenState* __restrict__ state, int* __restrict__ active_list,
-                                                 TilePlan* plan, const int nseg0, const int nseg1, const int segs_per_tile) {
+                                                 TilePlan* plan, const int nseg0, const int nseg1, const int segs_per_tile,
+                                                 const int split_passes) {
   // warp w handles groups w, w + nwarps, ...
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   __shared__ int nact[SOS_MAX_GROUPS];
@@ -428,7 +441,7 @@ __device__ __forceinline__ void plan_tiles_block(const GroupTable& gt, const int
       plan->group_phaseA[g] = gt.phaseA[g];
       plan->group_phaseB[g] = gt.phaseB[g];
       const int segs = nact[g] * (gt.cls[g] == 1 ? nseg1 : nseg0);
-      t += (segs + segs_per_tile - 1) / segs_per_tile;
+      t += ((segs + segs_per_tile - 1) / segs_per_tile) * ((split_passes && gt.cls[g] == 1) ? 2 : 1);
     }
     plan->group_tile_start[gt.n_groups] = t;
     plan->n_groups = gt.n_groups;

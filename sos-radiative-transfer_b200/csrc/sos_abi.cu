@@ -89,6 +89,7 @@ struct sos_plan {
   std::vector<sos_scenario> scen_h;
   // GEMM
   int gemm_bm = 0;  // rows per tile
+  int split_passes = 0;  // class-1 operand passes as separate tiles (small batches; see GemmParams)
   sosgemm::GroupTable groups;
   int* d_members = nullptr;      // scenario ids per group (static)
   int* d_active_list = nullptr;  // compacted per group (device-built)
@@ -155,8 +156,16 @@ int dev_upload(sos_plan* p, const T** out, const T* host, size_t count) {
 }
 
 __global__ void plan_tiles_kernel(sosgemm::GroupTable gt, const int* members, const ScenState* state, int* active_list,
-                                  TilePlan* plan, int nseg0, int nseg1, int segs_per_tile) {
-  sosgemm::plan_tiles_block(gt, members, state, active_list, plan, nseg0, nseg1, segs_per_tile);
+                                  TilePlan* plan, int nseg0, int nseg1, int segs_per_tile, int split_passes) {
+  sosgemm::plan_tiles_block(gt, members, state, active_list, plan, nseg0, nseg1, segs_per_tile, split_passes);
+}
+
+// zero the aerosol rows of J of every scenario (split class-1 tiles add their two partials into them)
+__global__ void zero_rows_kernel(double* J, int ld, int L, int r0, int r1, int N) {
+  const int s = blockIdx.z;
+  const int t = r0 + blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < r1 && m < N) J[(static_cast<size_t>(s) * L + t) * ld + m] = 0.0;
 }
 
 cudaEvent_t prof_event(sos_plan* p) {
@@ -197,7 +206,7 @@ int launch_check(sos_plan* p) {
 
 int plan_tiles(sos_plan* p, cudaStream_t st) {
   plan_tiles_kernel<<<1, 256, 0, st>>>(p->groups, p->d_members, p->dev.state, p->d_active_list, p->d_tile_plan,
-                                       p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS);
+                                       p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS, p->split_passes);
   return launch_check(p);
 }
 
@@ -455,6 +464,12 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     TRY(dev_alloc(p, &p->d_order, 1));
     { const int one = 1; SOS_CUDA(cudaMemcpy(p->d_order, &one, sizeof(int), cudaMemcpyHostToDevice)); }
     p->gemm_bm = sosgemm::Cfg<2, 4, 4>::BM;
+    {
+      // few tiles: the two-pass aerosol tiles are the critical path of the launch -> split them
+      const long long segs = static_cast<long long>(S) * (p->nseg[0] + p->nseg[1]);
+      const long long tiles = (segs + 7) / 8 * ((N + 127) / 128);
+      p->split_passes = (grid->n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
+    }
   }
 #undef TRY
   // opt in to the large dynamic shared memory of the kernels used
@@ -699,6 +714,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
   p->gp.active_list = p->d_active_list;
   p->gp.ct0 = g.col0 / 128;
   p->gp.n_col_tiles = (g.col1 + 127) / 128 - p->gp.ct0;
+  p->gp.split_passes = p->split_passes;
   p->gp.seg_begin = seg_begin;
   p->gp.seg_end = seg_end;
   p->gp.L = g.L;
@@ -708,6 +724,13 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
   p->gp.scen = g.scen;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SOS_CUDA(cudaMemsetAsync(p->d_work_counter, 0, sizeof(int), st));
+  if (p->split_passes) {
+    const int r0 = g.rstart[1], r1 = g.rstart[2];
+    dim3 zgrid((g.N + 255) / 256, r1 - r0, g.S);
+    zero_rows_kernel<<<zgrid, 256, 0, st>>>(J_d, g.ld, g.L, r0, r1, g.N);
+    int rz = launch_check(p);
+    if (rz) return rz;
+  }
   ProfSpan span(p, 0, st);
   // 64 x 128 tiles, 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md: best of the four shapes tried)
   sosgemm::jn_gemm_dmma_kernel<2, 4, 4><<<p->n_sms, sosgemm::Cfg<2, 4, 4>::THREADS, sosgemm::Cfg<2, 4, 4>::SMEM, st>>>(p->gp);
