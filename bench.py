@@ -452,7 +452,7 @@ def main():
             "roofline": roofline,
             "wall_s_timed_region": t_wall,
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:   # the CPU baseline leg is an N = 1 item
             units, dt = cpu_port_sample(orders=2)
             line["cpu_baseline"] = {
                 "value": units / dt, "unit": "updates/s", "cores": 1, "kind": "port",

@@ -13,6 +13,12 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # built artefacts are git-ignored: compile libsos_b200.so (nvcc cross-compiles without a GPU) if it is missing
+    lib = os.path.join(ROOT, "sos-radiative-transfer_b200", "libsos_b200.so")
+    if not os.path.isfile(lib):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "sos-radiative-transfer_b200", "csrc")], check=True,
+                       stdout=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")
