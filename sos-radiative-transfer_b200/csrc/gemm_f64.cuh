@@ -17,7 +17,7 @@
 //     hands the tile index to the consumers through the stage ring (heavy two-operand tiles first);
 //   * setmaxnreg moves the producer warpgroup's registers to the consumer warpgroups.
 //
-// Warp tile 64 x 32 = 8 x 4 mma blocks (64 accumulator doubles per thread); fragments:
+// Warp tile = MB x NB mma blocks (shipped: 32 x 32 and 32 x 48); fragments:
 //   A (8x4, row)  lane (g = lane/4, t = lane%4) holds I[r0+g][k0+t]; in the swizzled segment the
 //                 8 rows x 32 B fall on 4 distinct chunk pairs -> 2 wavefronts (the minimum)
 //   B (4x8, col)  lane holds A[k0+t][n0+g]; operand rows are padded to BN+8 doubles by loading a
@@ -113,11 +113,11 @@ struct TileInfo {
   int atomic_out;        // 1: add into J instead of storing
 };
 
-template <int WM, int WN, int MB>
+template <int WM, int WN, int MB, int NB>
 struct Cfg {
-  // warp tile = (8*MB rows) x 32 columns, MB in {4, 8} mma blocks along m
+  // warp tile = (8*MB rows) x (8*NB columns): MB x NB mma blocks
   static constexpr int BM = 8 * MB * WM;
-  static constexpr int BN = 32 * WN;
+  static constexpr int BN = 8 * NB * WN;
   static constexpr int BN_PAD = BN + 8;
   static constexpr int SEGS = BM / SEG_ROWS;
   static constexpr int CONSUMER_WARPS = WM * WN;
@@ -166,10 +166,10 @@ __device__ __forceinline__ int find_group(const TilePlan* plan, int rt) {
   return g;
 }
 
-template <int WM, int WN, int MB>
-__global__ void __launch_bounds__(Cfg<WM, WN, MB>::THREADS, Cfg<WM, WN, MB>::MIN_CTAS)
+template <int WM, int WN, int MB, int NB>
+__global__ void __launch_bounds__(Cfg<WM, WN, MB, NB>::THREADS, Cfg<WM, WN, MB, NB>::MIN_CTAS)
 jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<WM, WN, MB>;
+  using C = Cfg<WM, WN, MB, NB>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: every 8-row segment is one swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -294,7 +294,7 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
   for (int j = 0; j < 4; ++j)
     a_off[j] = static_cast<uint32_t>((warp_m * 8 * MB + g8) * 128 + ((((2 * j + (t4 >> 1)) ^ g8) << 4) | ((t4 & 1) << 3)));
   // B fragment of n-block q, k-slab j: row k = 4 j + t4, col n = warp_n*32 + 8 q + g8
-  const uint32_t b_off = static_cast<uint32_t>(C::A_BYTES + (t4 * C::BN_PAD + warp_n * 32 + g8) * 8);
+  const uint32_t b_off = static_cast<uint32_t>(C::A_BYTES + (t4 * C::BN_PAD + warp_n * 8 * NB + g8) * 8);
 
   int stage = 0;
   uint32_t phase = 0;
@@ -309,11 +309,11 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
     const int passes = info->passes;
     const int atomic_out = info->atomic_out;
 
-    double acc[MB][4][2];
+    double acc[MB][NB][2];
 #pragma unroll
     for (int i = 0; i < MB; ++i)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
+      for (int q = 0; q < NB; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
 
     for (int pass = 0; pass < passes; ++pass) {
       if (pass == 1) {
@@ -322,7 +322,7 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
         for (int i = 0; i < MB; ++i) {
           const double r = info->rescale[warp_m * MB + i];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { acc[i][q][0] *= r; acc[i][q][1] *= r; }
+          for (int q = 0; q < NB; ++q) { acc[i][q][0] *= r; acc[i][q][1] *= r; }
         }
       }
       for (int ks = 0; ks < ksteps; ++ks) {
@@ -331,11 +331,11 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
         const uint32_t sB = sA + b_off;
         if constexpr (MB == 8) {
           // 2 warps per SMSP: prefetch the next k-slab's fragments while this slab's DMMAs issue
-          double fa[2][MB], fb[2][4];
+          double fa[2][MB], fb[2][NB];
 #pragma unroll
           for (int i = 0; i < MB; ++i) fa[0][i] = lds64(sA + a_off[0] + static_cast<uint32_t>(i * 1024));
 #pragma unroll
-          for (int q = 0; q < 4; ++q) fb[0][q] = lds64(sB + static_cast<uint32_t>(8 * q * 8));
+          for (int q = 0; q < NB; ++q) fb[0][q] = lds64(sB + static_cast<uint32_t>(8 * q * 8));
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int cur = j & 1, nxt = cur ^ 1;
@@ -343,27 +343,27 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
               for (int i = 0; i < MB; ++i) fa[nxt][i] = lds64(sA + a_off[j + 1] + static_cast<uint32_t>(i * 1024));
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
+              for (int q = 0; q < NB; ++q)
                 fb[nxt][q] = lds64(sB + static_cast<uint32_t>((4 * (j + 1) * C::BN_PAD + 8 * q) * 8));
             }
 #pragma unroll
             for (int i = 0; i < MB; ++i)
 #pragma unroll
-              for (int q = 0; q < 4; ++q) dmma884(acc[i][q][0], acc[i][q][1], fa[cur][i], fb[cur][q]);
+              for (int q = 0; q < NB; ++q) dmma884(acc[i][q][0], acc[i][q][1], fa[cur][i], fb[cur][q]);
           }
         } else {
           // 4 warps per SMSP hide the fragment-load latency; registers are the scarce resource
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            double fa[MB], fb[4];
+            double fa[MB], fb[NB];
 #pragma unroll
             for (int i = 0; i < MB; ++i) fa[i] = lds64(sA + a_off[j] + static_cast<uint32_t>(i * 1024));
 #pragma unroll
-            for (int q = 0; q < 4; ++q) fb[q] = lds64(sB + static_cast<uint32_t>((4 * j * C::BN_PAD + 8 * q) * 8));
+            for (int q = 0; q < NB; ++q) fb[q] = lds64(sB + static_cast<uint32_t>((4 * j * C::BN_PAD + 8 * q) * 8));
 #pragma unroll
             for (int i = 0; i < MB; ++i)
 #pragma unroll
-              for (int q = 0; q < 4; ++q) dmma884(acc[i][q][0], acc[i][q][1], fa[i], fb[q]);
+              for (int q = 0; q < NB; ++q) dmma884(acc[i][q][0], acc[i][q][1], fa[i], fb[q]);
           }
         }
         __syncwarp();
@@ -373,7 +373,7 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
     }
 
     // ---- epilogue: lane owns J[r][c], J[r][c+1]; a quad writes 64 contiguous bytes ----
-    const int col_base = ct * C::BN + warp_n * 32 + 2 * t4;
+    const int col_base = ct * C::BN + warp_n * 8 * NB + 2 * t4;
 #pragma unroll
     for (int i = 0; i < MB; ++i) {
       const int sg = warp_m * MB + i;
@@ -381,7 +381,7 @@ jn_gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
         const double coef = info->coef[sg];
         double* out = p.J + static_cast<size_t>(info->row[sg] + g8) * p.ld;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NB; ++q) {
           const int c = col_base + 8 * q;
           if (atomic_out) {
             if (c < p.N) atomicAdd(out + c, coef * acc[i][q][0]);

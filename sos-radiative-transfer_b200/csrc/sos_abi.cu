@@ -89,6 +89,7 @@ struct sos_plan {
   std::vector<sos_scenario> scen_h;
   // GEMM
   int gemm_bm = 0;  // rows per tile
+  int gemm_bn = 128;  // columns per tile (128, or 144 when that pads N less and the batch is large)
   int split_passes = 0;  // class-1 operand passes as separate tiles (small batches; see GemmParams)
   sosgemm::GroupTable groups;
   int* d_members = nullptr;      // scenario ids per group (static)
@@ -463,17 +464,29 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     TRY(dev_alloc(p, &p->d_work_counter, 1));
     TRY(dev_alloc(p, &p->d_order, 1));
     { const int one = 1; SOS_CUDA(cudaMemcpy(p->d_order, &one, sizeof(int), cudaMemcpyHostToDevice)); }
-    p->gemm_bm = sosgemm::Cfg<2, 4, 4>::BM;
+    p->gemm_bm = sosgemm::Cfg<2, 4, 4, 4>::BM;
+    {
+      // 128 x 144 tiles (12 consumer warps of 32 x 48) when 144 pads N less than 128 (N = 1002: 1008 vs 1024
+      // issued columns) and the batch still gives every SM several tiles
+      const long long pad128 = (N + 127) / 128 * 128, pad144 = (N + 143) / 144 * 144;
+      const long long segs_all = static_cast<long long>(S) * (p->nseg[0] + p->nseg[1]);
+      const long long tiles144 = (segs_all + 15) / 16 * ((N + 143) / 144);
+      if (pad144 < pad128 && tiles144 >= 8LL * p->n_sms) {
+        p->gemm_bm = sosgemm::Cfg<4, 3, 4, 6>::BM;
+        p->gemm_bn = sosgemm::Cfg<4, 3, 4, 6>::BN;
+      }
+    }
     {
       // few tiles: the two-pass aerosol tiles are the critical path of the launch -> split them
       const long long segs = static_cast<long long>(S) * (p->nseg[0] + p->nseg[1]);
-      const long long tiles = (segs + 7) / 8 * ((N + 127) / 128);
+      const long long tiles = (segs + 7) / 8 * ((N + 127) / 128);  // (small batches always use 64 x 128 tiles)
       p->split_passes = (grid->n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
     }
   }
 #undef TRY
   // opt in to the large dynamic shared memory of the kernels used
-  cudaFuncSetAttribute(sosgemm::jn_gemm_dmma_kernel<2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<2, 4, 4>::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_dmma_kernel<2, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<2, 4, 4, 4>::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_dmma_kernel<4, 3, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::Cfg<4, 3, 4, 6>::SMEM);
   {
     int r2 = plan_tiles(p, nullptr);  // all scenarios active
     if (r2) { sos_plan_destroy(p); return r2; }
@@ -506,6 +519,7 @@ int sos_plan_set_columns(sos_plan* p, int col0, int col1) {
   if (col0 == 0 && col1 == g.N) { g.col0 = 0; g.col1 = g.N; return SOS_OK; }
   // mu-block sharding: only grids without a surface coupling (the coupling mixes mirror columns)
   if (g.surface != SOS_SURFACE_NONE || g.nreg != 1) return SOS_ERR_UNSUPPORTED;
+  if (p->gemm_bn != 128) return SOS_ERR_UNSUPPORTED;  // sharded plans are single-scenario: always 128-column tiles
   if ((col0 % 128) != 0 || (col1 != g.N && (col1 % 128) != 0)) return SOS_ERR_INVALID;
   // the mu -> 0 zones must not straddle a block boundary
   int wmax = 0;
@@ -590,7 +604,7 @@ int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
   if (!p || !A_d || n < 1 || n > SOS_MAX_PHASE || lda < p->N || (lda & 1)) return SOS_ERR_INVALID;
   for (const sos_scenario& sc : p->scen_h)
     if (sc.phase_atm >= n || sc.phase_aer >= n) return SOS_ERR_INVALID;
-  const int bn = sosgemm::Cfg<2, 4, 4>::BN_PAD;  // rows are loaded 8 columns wider than the tile (bank layout)
+  const int bn = p->gemm_bn + 8;  // rows are loaded 8 columns wider than the tile (bank layout)
   for (int i = 0; i < n; ++i) {
     if (!A_d[i] || (reinterpret_cast<uintptr_t>(A_d[i]) & 15)) return SOS_ERR_INVALID;
     int r = encode_2d(&p->gp.map_A[i], A_d[i], p->N, p->N, lda, bn, sosgemm::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -712,8 +726,8 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
   p->gp.plan = p->d_tile_plan;
   p->gp.work_counter = p->d_work_counter;
   p->gp.active_list = p->d_active_list;
-  p->gp.ct0 = g.col0 / 128;
-  p->gp.n_col_tiles = (g.col1 + 127) / 128 - p->gp.ct0;
+  p->gp.ct0 = g.col0 / p->gemm_bn;
+  p->gp.n_col_tiles = (g.col1 + p->gemm_bn - 1) / p->gemm_bn - p->gp.ct0;
   p->gp.split_passes = p->split_passes;
   p->gp.seg_begin = seg_begin;
   p->gp.seg_end = seg_end;
@@ -732,8 +746,11 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     if (rz) return rz;
   }
   ProfSpan span(p, 0, st);
-  // 64 x 128 tiles, 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md: best of the four shapes tried)
-  sosgemm::jn_gemm_dmma_kernel<2, 4, 4><<<p->n_sms, sosgemm::Cfg<2, 4, 4>::THREADS, sosgemm::Cfg<2, 4, 4>::SMEM, st>>>(p->gp);
+  // 64 x 128 tiles with 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md), or 128 x 144 with 12 warps of 32 x 48
+  if (p->gemm_bn == 144)
+    sosgemm::jn_gemm_dmma_kernel<4, 3, 4, 6><<<p->n_sms, sosgemm::Cfg<4, 3, 4, 6>::THREADS, sosgemm::Cfg<4, 3, 4, 6>::SMEM, st>>>(p->gp);
+  else
+    sosgemm::jn_gemm_dmma_kernel<2, 4, 4, 4><<<p->n_sms, sosgemm::Cfg<2, 4, 4, 4>::THREADS, sosgemm::Cfg<2, 4, 4, 4>::SMEM, st>>>(p->gp);
   return launch_check(p);
 }
 

@@ -444,3 +444,20 @@ def test_long_blend_beyond_the_row_zone(sos, so):
     assert ref_idx.max() > M + 140, ref_idx.max()      # the case really leaves the zone
     got = sos.In_NumInt(2, Js, Js, tau, mu, ts, 0.5, None, 1.0, M, 0, 0)
     assert relmax(got, ref) < TOL
+
+
+def test_large_batch_tile_shape_matches_single_solves(sos):
+    """A batch large enough to switch the contraction to its 128 x 144 tile shape (and to pack aerosol
+    rows of many scenarios into shared two-operand tiles) must reproduce single-scenario solves, which use
+    64 x 128 tiles with split operand passes."""
+    base = dict(nb_layers=800, nb_angles=501, atm_phase=("rayleigh", 0.0))
+    scs = []
+    for k in range(30):
+        scs.append(sos.Scenario(mu0=0.2 + 0.025 * k, tauStar_atm=0.124, tauStar_aer=0.01 + 0.015 * k,
+                                alb_aer=0.75 + 0.008 * k, grd_alb=(0.05, 0.15, 0.3)[k % 3],
+                                aer_phase=(("hg", 0.5), ("hg", 0.7))[k % 2], surface="specular", **base))
+    batch = sos.solve_scenarios(scs, quadratures=False)
+    for i in (0, 13, 29):
+        single = sos.solve_scenarios([scs[i]], quadratures=False)[0]
+        assert single.n == batch[i].n
+        assert relmax(batch[i].I, single.I) < 1e-13, i
