@@ -5,6 +5,8 @@ These are the cheap, once-per-plan pieces of the reference that stay on the host
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 # SOS_Aer_global_va.py:5-7
@@ -18,12 +20,19 @@ def mu_grid(nb_angles: int) -> np.ndarray:
     return np.concatenate((np.linspace(-1, 0, nb_angles), np.linspace(0, 1, nb_angles)))
 
 
-def aerosol_rows(z0, z_up, z_down, nb_layers):
-    """Layer indices bounding the aerosol layer (SOS_Aer_main_specular.py:30,39-40)."""
+@functools.lru_cache(maxsize=256)
+def _aerosol_rows_cached(z0, z_up, z_down, nb_layers):
     if z_down > z_up:
         z_down, z_up = z_up, z_down
     z = np.linspace(z0, 0, nb_layers)
+    z.setflags(write=False)  # shared between callers
     return z, int(np.argmin(np.abs(z - z_up))), int(np.argmin(np.abs(z - z_down)))
+
+
+def aerosol_rows(z0, z_up, z_down, nb_layers):
+    """Layer indices bounding the aerosol layer (SOS_Aer_main_specular.py:30,39-40).  Returns
+    (z_profile (read-only), idx_up, idx_down); cached, because a sweep asks thousands of times."""
+    return _aerosol_rows_cached(float(z0), float(z_up), float(z_down), int(nb_layers))
 
 
 def tau_profile(tauStar_atm, tauStar_aer, z0, z_up, z_down, nb_layers):
@@ -99,11 +108,22 @@ def _extrapolation_weights(mu_down: np.ndarray, width: int) -> np.ndarray:
     return W
 
 
+_TABLE_CACHE = {}
+
+
 def extrapolation_tables(mu: np.ndarray, nb_angles: int):
-    """The four W matrices (one per width class) flattened in sos_extrap_layout() order."""
-    mu_down = np.asarray(mu[:nb_angles], dtype=np.float64)
-    parts = []
-    for f in _WIDTH_FACTORS:
-        w = int(f * nb_angles)
-        parts.append(_extrapolation_weights(mu_down, w).ravel())
-    return np.concatenate(parts) if parts else np.zeros(0)
+    """The four W matrices (one per width class) flattened in sos_extrap_layout() order (cached per grid)."""
+    mu_down = np.ascontiguousarray(mu[:nb_angles], dtype=np.float64)
+    key = (int(nb_angles), mu_down.tobytes())
+    hit = _TABLE_CACHE.get(key)
+    if hit is None:
+        parts = []
+        for f in _WIDTH_FACTORS:
+            w = int(f * nb_angles)
+            parts.append(_extrapolation_weights(mu_down, w).ravel())
+        hit = np.concatenate(parts) if parts else np.zeros(0)
+        hit.setflags(write=False)
+        if len(_TABLE_CACHE) > 32:
+            _TABLE_CACHE.clear()
+        _TABLE_CACHE[key] = hit
+    return hit
