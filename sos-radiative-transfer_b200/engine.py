@@ -210,6 +210,8 @@ class SosEngine:
                            "sos_build_contraction")
                 torch.cuda.current_stream(self.device).synchronize()  # Pd may be freed after this
                 if ck is not None:
+                    if len(_OPERANDS) >= 32:   # bounded: ~8 MB per operand at N = 1002
+                        _OPERANDS.pop(next(iter(_OPERANDS)))
                     _OPERANDS[ck] = A
                 self._A.append(A)
             ptrs = (C.c_void_p * len(self._A))(*[a.data_ptr() for a in self._A])
