@@ -16,9 +16,10 @@ closed-form first order + the order loop to In/I < 1e-4 for every scenario.
             coefficients and phase matrices, solve, D2H of the flux / diffusivity / heating-rate
             profiles, order counts and TOA net flux of every scenario (what a forcing sweep returns;
             the reference's SOS_Aer_radiative_forcing returns one float per solve)
-  roofline: dominant kernel = the FP64 source contraction (jn_gemm), timed with CUDA events on the
-            launching stream inside the timed steps; peak = FP64 DMMA/DFMA throughput measured on
-            this GPU in the same run (MEASURED_PEAKS.json has no FP64 entry)
+  roofline: dominant kernel = the FP64 source contraction (jn_gemm_fold / jn_gemm_dmma), timed with CUDA
+            events on the launching stream inside the timed steps; peak = FP64 DMMA/DFMA throughput measured
+            on this GPU in the same run (MEASURED_PEAKS.json has no FP64 entry).  The folded kernel needs half
+            the FLOPs of the general one for the same J; `achieved` counts the FLOPs of the kernel that ran
   cpu_baseline / --impl reference: the NumPy oracle port of the reference algorithm
             (oracle/sos_oracle.py, method="slices") on the host cores, bounded sample.
 """
@@ -251,6 +252,7 @@ def run_thick(args, sos, torch, dist, dev, rank, world, W):
             "config": {"workload": "thick FWC cloud layer (BASELINE configs[3]): one 10000x1024 grid, tau*=30, omega=0.9, "
                                    "to In/I<1e-4", "orders": n, "status": status, "ms_per_order": ms / max(n - 1, 1),
                        "sharding": "none" if world == 1 else "mu blocks of %d columns, contraction reads peer blocks by TMA over NVLink" % (N // world),
+                       "contraction": "folded" if (eng.folded and world == 1) else "general",
                        "l2": "working set 4 x 82 MB fields + operand > 126 MB L2"},
             "clocks": clocks}))
 
@@ -358,7 +360,13 @@ def main():
     # ---------------- roofline of the dominant kernel ----------------
     gemm_ms, gemm_launches = float(ms2[0]), int(sp2[0])
     sweep_ms, sweep_spans = float(ms2[1]), int(sp2[1])
-    flops = 2.0 * units_per_step * args.steps
+    # FLOPs the kernel's algorithm needs: 2*L*N^2 per scenario-order for the general contraction;
+    # the folded contraction (centrosymmetric operands, csrc/gemm_fold.cuh) computes the same J with two M x M
+    # contractions per row = L*N^2 FLOP.  `achieved` counts what the shipped kernel's algorithm needs (no padding,
+    # aerosol rows once), so frac stays a statement about the kernel; `value` keeps the SURVEY 8d unit.
+    folded = bool(eng.folded)
+    flops_general = 2.0 * units_per_step * args.steps
+    flops = flops_general * (0.5 if folded else 1.0)
     achieved = flops / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
     pk = C.c_double()
     lib.sos_fp64_peak(1, 3, C.byref(pk))
@@ -370,21 +378,27 @@ def main():
     # active: one launch of order 2), scaled to the average number of active scenarios per timed launch
     traffic = None
     traffic_note = None
+    tfile = "r01_ncu_fold_traffic.json" if folded else "r01_ncu_gemm_traffic.json"
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", tfile)) as f:
             tj = json.load(f)
         active_per_launch = float(np.sum(n_orders - 1)) * args.steps / max(gemm_launches, 1)
         traffic = tj["dram_bytes_per_active_scenario"] * active_per_launch
-        traffic_note = ("dram__bytes_read+write per launch from profiles/r01_ncu_gemm_traffic.json (%.3e B at %d active "
+        traffic_note = ("dram__bytes_read+write per launch from profiles/%s (%.3e B at %d active "
                         "scenarios; algorithmic %.3e B) scaled to %.1f active scenarios per timed launch"
-                        % (tj["dram_bytes_per_launch"], tj["scenarios"], tj["algorithmic_bytes_per_launch"], active_per_launch))
+                        % (tfile, tj["dram_bytes_per_launch"], tj["scenarios"], tj["algorithmic_bytes_per_launch"], active_per_launch))
     except (OSError, KeyError, ValueError):
         pass
     roofline = {
-        "bound": "tensor", "kernel": "jn_gemm_dmma_kernel (FP64 source contraction, DMMA m8n8k4)",
+        "bound": "tensor",
+        "kernel": ("jn_gemm_fold_kernel (FP64 source contraction folded on the operand's centrosymmetry, DMMA m8n8k4)" if folded
+                   else "jn_gemm_dmma_kernel (FP64 source contraction, DMMA m8n8k4)"),
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "traffic": traffic, "traffic_source": traffic_note,
         "algorithmic_flops_per_launch": flops / max(gemm_launches, 1),
+        "flops_model": ("folded: L*N^2 FLOP per scenario-order (two M x M contractions per row); the general "
+                        "contraction of SURVEY 8d needs 2*L*N^2" if folded else "2*L*N^2 FLOP per scenario-order (SURVEY 8d)"),
+        "general_equivalent_tflops": flops_general / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else None,
         "peak_source": "FP64 DMMA m8n8k4 loop measured on this GPU in this run (sos_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 entry; DFMA loop measured %.1f TFLOP/s" % pk_dfma.value,
         "gemm_ms_per_launch": gemm_ms / max(gemm_launches, 1), "gemm_launches": gemm_launches,
@@ -444,6 +458,7 @@ def main():
                        "orders_per_scenario": [int(n_orders.min()), int(n_orders.max())],
                        "l2": "256 MB flush between timed steps; per-step working set %.0f MB > 126 MB L2" % (3 * S * L * eng.ld * 8 / 1e6),
                        "scenarios_swapped_for_blend_overrun": n_swapped,
+                       "contraction": "folded (centrosymmetric operands, defect %.1e)" % eng.fold_defect if eng.folded else "general",
                        "mie": "HG(0.5/0.7) and FWC stand in for log-normal Mie (miepython absent)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

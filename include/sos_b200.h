@@ -122,6 +122,22 @@ int sos_build_phase(sos_plan* plan, int family, double g, double mu0, const doub
 /* Register the contraction matrices (device, [N][lda] each) the scenarios index. */
 int sos_plan_set_phase(sos_plan* plan, const double* const* A_d, int n_matrices, int lda);
 
+/* Folded contraction (optional, half the multiply-adds).  The operand A[k][m] = w_k/4 P[m][N-1-k] of
+ * SOS_Aer_I1_In.py:73 is centrosymmetric (A[N-1-k][N-1-m] = A[k][m]) whenever P(mu, mu') = P(-mu, -mu') --
+ * true for every builder of SOS_Aer_phase_func.py -- and the mu grid is symmetric (SOS_Aer_main_specular.py:59-61).
+ * Then J[:, j] = u B+ + v B-, J[:, N-1-j] = u B+ - v B- with u, v = I[:, k] +- I[:, N-1-k] and two
+ * M x M operands B+-: the same sum, reassociated (agreement ~1e-14 relative).
+ *   sos_fold_layout     rows / ld of a folded operand for this nb_angles (returns rows*ld, the element count)
+ *   sos_build_folded    F_d [rows][ldf] from A_d; *defect_out (host) = max|A[k][m] - A[N-1-k][N-1-m]| / max|A|.
+ *                       Synchronises the stream.  The caller decides (the Python host enables the fold when every
+ *                       operand's defect is <= 1e-12; F is built from the symmetrised A).
+ *   sos_plan_set_folded register one folded operand per matrix of sos_plan_set_phase (same order); sos_source /
+ *                       sos_solve then use the folded kernel for full-column, single-GPU launches and the general
+ *                       kernel otherwise.  n_matrices = 0 switches it off.  sos_plan_set_phase resets it. */
+int sos_fold_layout(int nb_angles, int* rows, int* ld);
+int sos_build_folded(sos_plan* plan, const double* A_d, int lda, double* F_d, int ldf, double* defect_out, void* stream);
+int sos_plan_set_folded(sos_plan* plan, const double* const* F_d, int n_matrices, int ldf);
+
 /* First order.
  *  n_regions == 3: inlined closed form of SOS_Aer_main_specular.py:104-292; C_h is [S][2][N]:
  *     C_h[s][0][m] = alb_atm*P0_atm[m], C_h[s][1][m] = alb_atm*P0_atm[m]*f_atm + alb_aer*P0_aer[m]*f_aer

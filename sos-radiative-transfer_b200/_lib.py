@@ -74,6 +74,9 @@ SIGNATURES = {
     "sos_build_contraction": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
     "sos_build_phase": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "sos_plan_set_phase": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int]),
+    "sos_fold_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sos_build_folded": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_double), _vp]),
+    "sos_plan_set_folded": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int]),
     "sos_first_order": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source_rows": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),

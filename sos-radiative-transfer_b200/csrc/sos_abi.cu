@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "first_order.cuh"
 #include "gemm_f64.cuh"
+#include "gemm_fold.cuh"
 #include "phase.cuh"
 #include "quadrature.cuh"
 #include "sweep.cuh"
@@ -102,6 +103,11 @@ struct sos_plan {
   sosgemm::GemmParams gp;
   std::map<const void*, CUtensorMap> map_cache;
   bool maps_A_ready = false;
+  std::vector<const double*> A_ptrs;  // operands of sos_plan_set_phase (maps are re-encoded when the tile shape changes)
+  // folded contraction (centrosymmetric operands, gemm_fold.cuh)
+  bool fold = false;
+  sosgemm::FoldParams fp;
+  unsigned long long* d_fold_stats = nullptr;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -279,6 +285,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   p->launches = 0;
   p->scen_h.assign(scen_h, scen_h + S);
   std::memset(&p->gp, 0, sizeof(p->gp));
+  std::memset(&p->fp, 0, sizeof(p->fp));
 
   int widx[4], wns[4], woff[4];
   const int wlen = sos_extrap_layout(M, widx, wns, woff);
@@ -463,6 +470,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     TRY(dev_alloc(p, &p->d_tile_plan, 1));
     TRY(dev_alloc(p, &p->d_work_counter, 1));
     TRY(dev_alloc(p, &p->d_order, 1));
+    TRY(dev_alloc(p, &p->d_fold_stats, 2));
     { const int one = 1; SOS_CUDA(cudaMemcpy(p->d_order, &one, sizeof(int), cudaMemcpyHostToDevice)); }
     p->gemm_bm = sosgemm::Cfg<2, 4, 4, 4>::BM;
     {
@@ -600,18 +608,89 @@ int sos_build_phase(sos_plan* p, int family, double g, double mu0, const double*
   return SOS_OK;
 }
 
+static int encode_A_maps(sos_plan* p) {
+  const int bn = p->gemm_bn + 8;  // rows are loaded 8 columns wider than the tile (bank layout)
+  for (size_t i = 0; i < p->A_ptrs.size(); ++i) {
+    int r = encode_2d(&p->gp.map_A[i], p->A_ptrs[i], p->N, p->N, p->lda, bn, sosgemm::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r) return r;
+  }
+  return SOS_OK;
+}
+
 int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
   if (!p || !A_d || n < 1 || n > SOS_MAX_PHASE || lda < p->N || (lda & 1)) return SOS_ERR_INVALID;
   for (const sos_scenario& sc : p->scen_h)
     if (sc.phase_atm >= n || sc.phase_aer >= n) return SOS_ERR_INVALID;
-  const int bn = p->gemm_bn + 8;  // rows are loaded 8 columns wider than the tile (bank layout)
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n; ++i)
     if (!A_d[i] || (reinterpret_cast<uintptr_t>(A_d[i]) & 15)) return SOS_ERR_INVALID;
-    int r = encode_2d(&p->gp.map_A[i], A_d[i], p->N, p->N, lda, bn, sosgemm::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+  p->A_ptrs.assign(A_d, A_d + n);
+  p->lda = lda;
+  p->fold = false;  // new operands: the folded set (if any) must be given again
+  int r = encode_A_maps(p);
+  if (r) return r;
+  p->maps_A_ready = true;
+  return SOS_OK;
+}
+
+int sos_fold_layout(int nb_angles, int* rows, int* ld) {
+  const int Mh = (nb_angles + 15) / 16 * 16;
+  if (rows) *rows = Mh;       // k rows, padded to the k-step
+  if (ld) *ld = 2 * Mh;       // [B+ | B-], each Mh columns wide
+  return 2 * Mh * Mh;
+}
+
+int sos_build_folded(sos_plan* p, const double* A_d, int lda, double* F_d, int ldf, double* defect_out, void* stream) {
+  if (!p || !A_d || !F_d || !defect_out || lda < p->N) return SOS_ERR_INVALID;
+  int rows = 0, ld = 0;
+  sos_fold_layout(p->dev.M, &rows, &ld);
+  if (ldf != ld) return SOS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SOS_CUDA(cudaMemsetAsync(p->d_fold_stats, 0, 2 * sizeof(unsigned long long), st));
+  dim3 grid((rows + 127) / 128, rows);
+  sosgemm::build_folded_kernel<<<grid, 128, 0, st>>>(A_d, lda, p->N, F_d, ldf, rows, rows, p->d_fold_stats);
+  int r = launch_check(p);
+  if (r) return r;
+  unsigned long long bits[2] = {0, 0};
+  SOS_CUDA(cudaMemcpyAsync(bits, p->d_fold_stats, sizeof(bits), cudaMemcpyDeviceToHost, st));
+  SOS_CUDA(cudaStreamSynchronize(st));
+  double defect, amax;
+  std::memcpy(&defect, &bits[0], 8);
+  std::memcpy(&amax, &bits[1], 8);
+  *defect_out = amax > 0.0 ? defect / amax : 0.0;
+  return SOS_OK;
+}
+
+int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
+  if (!p) return SOS_ERR_INVALID;
+  if (n == 0 || !F_d) { p->fold = false; return SOS_OK; }
+  if (!p->maps_A_ready) return SOS_ERR_STATE;
+  if (n != static_cast<int>(p->A_ptrs.size())) return SOS_ERR_INVALID;
+  int rows = 0, ld = 0;
+  sos_fold_layout(p->dev.M, &rows, &ld);
+  if (ldf != ld) return SOS_ERR_INVALID;
+  using FC = sosgemm::FoldCfg;
+  for (int i = 0; i < n; ++i) {
+    if (!F_d[i] || (reinterpret_cast<uintptr_t>(F_d[i]) & 15)) return SOS_ERR_INVALID;
+    int r = encode_2d(&p->fp.map_F[i], F_d[i], ld, rows, ldf, FC::BN_PAD, sosgemm::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r) return r;
   }
-  p->lda = lda;
-  p->maps_A_ready = true;
+  // the folded kernel and the general fallback (column-sharded or peer launches) share one device tile plan:
+  // 64-row tiles, 128-column general tiles
+  const bool reshape = p->gemm_bm != FC::BM || p->gemm_bn != 128;
+  p->gemm_bm = FC::BM;
+  p->gemm_bn = 128;
+  if (reshape) { int r = encode_A_maps(p); if (r) return r; }
+  const long long segs = static_cast<long long>(p->dev.S) * (p->nseg[0] + p->nseg[1]);
+  const long long tiles = (segs + FC::SEGS - 1) / FC::SEGS * ((p->dev.M + FC::BN - 1) / FC::BN);
+  const int split = (p->grid.n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
+  if (reshape || split != p->split_passes) {
+    p->split_passes = split;
+    int r = plan_tiles(p, nullptr);
+    if (r) return r;
+    SOS_CUDA(cudaDeviceSynchronize());
+  }
+  cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
+  p->fold = true;
   return SOS_OK;
 }
 
@@ -746,6 +825,24 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     if (rz) return rz;
   }
   ProfSpan span(p, 0, st);
+  const bool full_columns = g.col0 == 0 && g.col1 == g.N;
+  if (p->fold && full_columns && !peers && seg_begin == 0 && seg_end == 0x7fffffff) {
+    // centrosymmetric operands: half the DMMA work (gemm_fold.cuh)
+    using FC = sosgemm::FoldCfg;
+    sosgemm::FoldParams& f = p->fp;
+    f.map_I = p->gp.map_I;
+    f.plan = p->d_tile_plan;
+    f.work_counter = p->d_work_counter;
+    f.active_list = p->d_active_list;
+    for (int c = 0; c < 2; ++c) { f.seg_row[c] = p->gp.seg_row[c]; f.seg_valid[c] = p->gp.seg_valid[c]; f.nseg[c] = p->gp.nseg[c]; }
+    f.n_col_tiles = (g.M + FC::BN - 1) / FC::BN;
+    f.split_passes = p->split_passes;
+    f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
+    f.J = J_d;
+    f.scen = g.scen;
+    sosgemm::jn_gemm_fold_kernel<<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
+    return launch_check(p);
+  }
   // 64 x 128 tiles with 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md), or 128 x 144 with 12 warps of 32 x 48
   if (p->gemm_bn == 144)
     sosgemm::jn_gemm_dmma_kernel<4, 3, 4, 6><<<p->n_sms, sosgemm::Cfg<4, 3, 4, 6>::THREADS, sosgemm::Cfg<4, 3, 4, 6>::SMEM, st>>>(p->gp);

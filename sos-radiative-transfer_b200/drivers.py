@@ -116,7 +116,7 @@ class BatchSolver:
     """All scenarios of one group (same L, M, aerosol rows, surface) on one device."""
 
     def __init__(self, scenarios: Sequence[Scenario], device=None, chunk_rows: int = 0, phases: Optional[PhaseCache] = None,
-                 device_phase: bool = True):
+                 device_phase: bool = True, fold: Optional[bool] = None):
         keys = {_group_key(s) for s in scenarios}
         if len(keys) != 1:
             raise ValueError("BatchSolver: scenarios must share nb_layers, nb_angles, aerosol rows and surface")
@@ -130,12 +130,17 @@ class BatchSolver:
         coefs = []
         Ccoef = np.empty((S, 2, self.N))
         mats, mat_index, mat_keys = [], {}, []
-        self.z = None
+        self.z = G.aerosol_rows(scenarios[0].z0, scenarios[0].z_up, scenarios[0].z_down, L)[0]
+        # tau profiles of the whole batch at once: the same arithmetic as grid.tau_profile, element for element
+        # (the group key fixes idx_up / idx_down for every scenario of the batch)
+        rows = np.arange(L)
+        t_atm = np.array([sc.tauStar_atm for sc in scenarios], dtype=np.float64)
+        t_aer = np.array([sc.tauStar_aer for sc in scenarios], dtype=np.float64)
+        tau[:] = rows[None, :] * t_atm[:, None] / (L - 1)
+        inside = (rows >= self.idx_up) & (rows <= self.idx_down)
+        tau[:, inside] += (rows[inside] + 1 - self.idx_up)[None, :] * (t_aer / (self.idx_down + 1 - self.idx_up))[:, None]
+        tau[:, rows > self.idx_down] += t_aer[:, None]
         for i, sc in enumerate(scenarios):
-            z, _, _ = G.aerosol_rows(sc.z0, sc.z_up, sc.z_down, L)
-            self.z = z if self.z is None else self.z
-            zu, zd = (sc.z_up, sc.z_down) if sc.z_up >= sc.z_down else (sc.z_down, sc.z_up)
-            tau[i] = G.tau_profile(sc.tauStar_atm, sc.tauStar_aer, sc.z0, zu, zd, L)
             P0a, Pa, ka = phases.get(sc.atm_phase, M, self.mu, sc.mu0, need_P=not device_phase)
             P0e, Pe, ke = phases.get(sc.aer_phase, M, self.mu, sc.mu0, need_P=not device_phase)
             for k, P in ((ka, Pa), (ke, Pe)):
@@ -161,7 +166,7 @@ class BatchSolver:
         self.Ccoef = Ccoef
         surface = {"specular": _lib.SURFACE_SPECULAR, "lambert": _lib.SURFACE_LAMBERT}[surf]
         self.engine = SosEngine(self.mu, tau, coefs, [0, self.idx_up, self.idx_down + 1, L], surface,
-                                device=device, chunk_rows=chunk_rows)
+                                device=device, chunk_rows=chunk_rows, fold=fold)
         if device_phase:
             # analytic families: the N x N matrix is built on the device (sos_build_phase) unless its
             # contraction operand is already resident; only the cheap P0 vectors were built on the host
@@ -218,14 +223,15 @@ class BatchSolver:
         return out
 
 
-def solve_scenarios(scenarios: Sequence[Scenario], device=None, keep_orders: int = 0, quadratures: bool = True) -> List[DriverResult]:
-    """Solve any mix of scenarios; those sharing a grid are batched together."""
+def solve_scenarios(scenarios: Sequence[Scenario], device=None, keep_orders: int = 0, quadratures: bool = True,
+                    fold: Optional[bool] = None) -> List[DriverResult]:
+    """Solve any mix of scenarios; those sharing a grid are batched together.  fold: see SosEngine."""
     groups: Dict[tuple, List[int]] = {}
     for i, sc in enumerate(scenarios):
         groups.setdefault(_group_key(sc), []).append(i)
     out: List[Optional[DriverResult]] = [None] * len(scenarios)
     for key, idxs in groups.items():
-        bs = BatchSolver([scenarios[i] for i in idxs], device=device)
+        bs = BatchSolver([scenarios[i] for i in idxs], device=device, fold=fold)
         res = bs.solve(keep_orders=keep_orders)
         for i, r in zip(idxs, bs.results(res, quadratures=quadratures, keep_orders=keep_orders)):
             out[i] = r

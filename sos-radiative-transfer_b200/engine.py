@@ -10,6 +10,7 @@ library is missing.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -26,6 +27,8 @@ def _align(n: int, a: int) -> int:
 
 _PINNED = {}
 _OPERANDS = {}  # device-resident contraction operands shared between engines (see SosEngine.set_phase)
+_FOLDED = {}    # their folded counterparts [B+ | B-] and centrosymmetry defects (sos_build_folded)
+FOLD_DEFECT_MAX = 1e-12  # fold only operands that are centrosymmetric to rounding (observed <= 3e-14 for every builder)
 
 
 def _pinned_pair(elems: int):
@@ -66,8 +69,12 @@ class SolveResult:
 
 class SosEngine:
     def __init__(self, mu, tau, scenarios: Sequence[ScenarioCoefficients], region_start: Sequence[int],
-                 surface: int, device: Optional[torch.device] = None, chunk_rows: int = 0):
+                 surface: int, device: Optional[torch.device] = None, chunk_rows: int = 0, fold: Optional[bool] = None):
+        """fold: use the folded contraction (half the multiply-adds) when every operand is centrosymmetric;
+        None = on unless the environment says SOS_B200_FOLD=0."""
         self.lib = _lib.load()
+        self.fold = (os.environ.get("SOS_B200_FOLD", "1") != "0") if fold is None else bool(fold)
+        self.folded = False
         if not torch.cuda.is_available():
             raise _lib.SosError("no CUDA device: the SOS engine has no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -187,6 +194,7 @@ class SosEngine:
         self._A = []
         lda = self.ld
         self.h2d_phase_bytes = 0
+        cks = []
         with torch.cuda.device(self.device):
             for i, P in enumerate(matrices):
                 ck = None
@@ -195,7 +203,9 @@ class SosEngine:
                     hit = _OPERANDS.get(ck)
                     if hit is not None:
                         self._A.append(hit)
+                        cks.append(ck)
                         continue
+                cks.append(ck)
                 if hasattr(P, "build"):
                     Pd = P.build()            # built on the device (drivers._DeviceBuilt)
                 elif isinstance(P, torch.Tensor):
@@ -216,6 +226,34 @@ class SosEngine:
                 self._A.append(A)
             ptrs = (C.c_void_p * len(self._A))(*[a.data_ptr() for a in self._A])
             _lib.check(self.lib.sos_plan_set_phase(self._plan, ptrs, len(self._A), lda), "sos_plan_set_phase")
+            self.folded = False
+            if self.fold:
+                self._set_folded(cks)
+
+    def _set_folded(self, cks):
+        """Build (or fetch) the folded operand of every contraction matrix; enable the folded kernel when all
+        of them are centrosymmetric to rounding (sos_b200.h: sos_build_folded / sos_plan_set_folded)."""
+        rows, ldf = C.c_int(), C.c_int()
+        self.lib.sos_fold_layout(self.M, C.byref(rows), C.byref(ldf))
+        self._F, self.fold_defect = [], 0.0
+        for A, ck in zip(self._A, cks):
+            hit = _FOLDED.get(ck) if ck is not None else None
+            if hit is None:
+                F = torch.empty((rows.value, ldf.value), dtype=torch.float64, device=self.device)
+                defect = C.c_double()
+                _lib.check(self.lib.sos_build_folded(self._plan, A.data_ptr(), self.ld, F.data_ptr(), ldf.value,
+                                                     C.byref(defect), self._stream), "sos_build_folded")
+                hit = (F, defect.value)
+                if ck is not None:
+                    if len(_FOLDED) >= 32:
+                        _FOLDED.pop(next(iter(_FOLDED)))
+                    _FOLDED[ck] = hit
+            self._F.append(hit[0])
+            self.fold_defect = max(self.fold_defect, hit[1])
+        if self.fold_defect <= FOLD_DEFECT_MAX:
+            ptrs = (C.c_void_p * len(self._F))(*[f.data_ptr() for f in self._F])
+            _lib.check(self.lib.sos_plan_set_folded(self._plan, ptrs, len(self._F), ldf.value), "sos_plan_set_folded")
+            self.folded = True
 
     def build_phase_matrix(self, name: str, g: float = 0.5, mu0: Optional[float] = None):
         """P(mu, mu') (and P0(mu, mu0) when mu0 is given) of an analytic family, built ON THE DEVICE
@@ -333,7 +371,8 @@ class SosEngine:
 
     def quadratures(self, I: torch.Tensor, z: Optional[np.ndarray] = None, direct_scale: float = 1.0, heating: bool = True):
         """flux_up, flux_down, net_flux, diffusivity, heating_rate -- each (S, L) on the host."""
-        outs = [torch.zeros((self.S, self.L), dtype=torch.float64, device=self.device) for _ in range(5)]
+        packed = torch.zeros((5, self.S, self.L), dtype=torch.float64, device=self.device)
+        outs = [packed[k] for k in range(5)]
         want_heat = heating and z is not None and self.n_regions == 3
         zc = np.ascontiguousarray(z, dtype=np.float64) if z is not None else None
         with torch.cuda.device(self.device):
@@ -341,6 +380,10 @@ class SosEngine:
                                                 zc.ctypes.data if zc is not None else None,
                                                 outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
                                                 outs[4].data_ptr() if want_heat else None, self._stream), "sos_quadratures")
-        host = [o.cpu().numpy() for o in outs]
+            # one D2H through a cached pinned buffer (five pageable .cpu() calls cost ~1 ms per batch)
+            stage = _pinned_pair(packed.numel())[0][: packed.numel()]
+            stage.copy_(packed.view(-1), non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        host = stage.numpy().reshape(5, self.S, self.L).copy()
         return dict(flux_up=host[0], flux_down=host[1], net_flux=host[2], diffusivity=host[3],
                     heating_rate=host[4] if want_heat else None)

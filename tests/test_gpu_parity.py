@@ -278,9 +278,10 @@ def test_mu_block_sharding_matches_unsharded_single_gpu(sos):
     Cc = np.zeros((1, 2, N))
     Cc[0, 0] = alb * P0
 
-    def one_order(cols=None):
-        eng = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE)
+    def one_order(cols=None, fold=False):
+        eng = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE, fold=fold)
         eng.set_phase([P])
+        assert eng.folded == fold
         if cols is not None:
             eng.set_columns(*cols)
         I1 = eng.first_order(Cc)
@@ -304,6 +305,9 @@ def test_mu_block_sharding_matches_unsharded_single_gpu(sos):
         assert np.array_equal(Ib[:, c0:c1], If[:, c0:c1])
         rmax = np.maximum(rmax, rb)
     assert np.array_equal(rmax, rf)
+    # the folded contraction (default for full-column plans) is the same sum reassociated
+    Jd, Ind, Id, rd = one_order(fold=True)
+    assert relmax(Jd, Jf) < 1e-13 and relmax(Ind, Inf) < 1e-12 and relmax(Id, If) < 1e-13
     # a boundary inside the mu -> 0 zone is refused
     eng = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE)
     with pytest.raises(sos.SosError):
@@ -456,8 +460,57 @@ def test_large_batch_tile_shape_matches_single_solves(sos):
         scs.append(sos.Scenario(mu0=0.2 + 0.025 * k, tauStar_atm=0.124, tauStar_aer=0.01 + 0.015 * k,
                                 alb_aer=0.75 + 0.008 * k, grd_alb=(0.05, 0.15, 0.3)[k % 3],
                                 aer_phase=(("hg", 0.5), ("hg", 0.7))[k % 2], surface="specular", **base))
-    batch = sos.solve_scenarios(scs, quadratures=False)
+    batch = sos.solve_scenarios(scs, quadratures=False, fold=False)
     for i in (0, 13, 29):
-        single = sos.solve_scenarios([scs[i]], quadratures=False)[0]
+        single = sos.solve_scenarios([scs[i]], quadratures=False, fold=False)[0]
         assert single.n == batch[i].n
         assert relmax(batch[i].I, single.I) < 1e-13, i
+    # ... and the folded contraction (centrosymmetric operands: half the multiply-adds) the general one
+    folded = sos.solve_scenarios(scs, quadratures=False)
+    for i in range(len(scs)):
+        assert folded[i].n == batch[i].n
+        assert relmax(folded[i].I, batch[i].I) < 1e-12, i
+
+
+def test_folded_contraction_vs_general_and_asymmetric_operand(sos):
+    """The folded kernel (u = x[k] + x[N-1-k], v = x[k] - x[N-1-k], two M x M operands) against the general one on
+    random rows: odd and even M, ragged sizes, two-operand aerosol rows in packed and split tiles.  An operand that
+    is not centrosymmetric must keep the general kernel."""
+    import torch
+    rng = np.random.default_rng(7)
+    for L, M, S in ((70, 37, 1), (131, 100, 3), (64, 501, 2), (300, 129, 40)):
+        N = 2 * M
+        mu = sos.mu_grid(M)
+        iu, idn = L // 3, L // 3 + 9
+        tau = np.tile(np.linspace(0, 0.7, L), (S, 1))
+        _, Pa = sos.phase_matrices("rayleigh", M, mu, 0.5, 0.0)
+        _, Pe = sos.phase_matrices("hg", M, mu, 0.5, 0.8)
+        w = sos.extrapolation_width(0.7, M)
+        coefs = [sos.ScenarioCoefficients(mu0=0.5, grd_alb=0.1, tauStar_tot=0.7, coef_atm=0.9 + 0.01 * s, coef_mix_atm=0.3 + 0.02 * s,
+                                          coef_mix_aer=0.6 - 0.01 * s, phase_atm=0, phase_aer=1, extrap_width=(w, w, w))
+                 for s in range(S)]
+        x = rng.random((S, L, N)) * np.exp(2.0 * rng.standard_normal((S, L, N)))
+        out = {}
+        for fold in (False, True):
+            eng = sos.SosEngine(mu, tau, coefs, [0, iu, idn + 1, L], sos._lib.SURFACE_SPECULAR, fold=fold)
+            eng.set_phase([Pa, Pe])
+            assert eng.folded == fold
+            if fold:
+                assert eng.fold_defect < 1e-13
+            J = eng.source(eng.to_field(x))
+            torch.cuda.synchronize()
+            out[fold] = eng.to_host(J).reshape(S, L, N)
+            eng.close()
+        assert relelem(out[True], out[False]) < 1e-11, (L, M, S)
+        assert relmax(out[True], out[False]) < 1e-13, (L, M, S)
+    # asymmetric operand: stays on the general kernel
+    L, M = 40, 64
+    mu = sos.mu_grid(M)
+    _, P = sos.phase_matrices("hg", M, mu, 0.5, 0.6)
+    P = P * (1.0 + 1e-6 * rng.random(P.shape))
+    w = sos.extrapolation_width(0.5, M)
+    eng = sos.SosEngine(mu, np.linspace(0, 0.5, L)[None], [sos.ScenarioCoefficients(mu0=0.5, grd_alb=0.0, tauStar_tot=0.5,
+                        coef_atm=1.0, extrap_width=(w, w, w))], [0, L], sos._lib.SURFACE_NONE)
+    eng.set_phase([P])
+    assert not eng.folded and eng.fold_defect > 1e-8
+    eng.close()

@@ -74,7 +74,8 @@ def main():
     s_mean, s_min = timeit(lambda: eng.sweeps(J, out=In, accumulate_into=I), args.reps)
     flops = 2.0 * S * L * N * N
     out = {
-        "S": S, "L": L, "N": N, "gemm_kind": os.environ.get("SOS_GEMM", "dmma"),
+        "S": S, "L": L, "N": N, "gemm_kind": "folded" if eng.folded else "general",
+        "gemm_executed_tflops_mean": flops * (0.5 if eng.folded else 1.0) / g_mean * 1e-9,
         "gemm_ms_mean": g_mean, "gemm_ms_min": g_min, "gemm_tflops_mean": flops / g_mean * 1e-9,
         "gemm_tflops_best": flops / g_min * 1e-9,
         "sweeps_ms_mean": s_mean, "sweeps_ms_min": s_min,
