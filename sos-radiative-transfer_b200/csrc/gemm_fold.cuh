@@ -55,7 +55,7 @@ struct FoldCfg {
   static constexpr int B_BYTES = 2 * B_HALF;
   static constexpr int STAGE_BYTES = ((A_BYTES + B_BYTES + 1023) / 1024) * 1024;
   static constexpr int INFO_SLOTS = NST + 2;
-  static constexpr int SMEM = NST * STAGE_BYTES + 1024 + 2 * NST * 8 + NST * 8 + INFO_SLOTS * static_cast<int>(sizeof(TileInfo<SEGS>));
+  static constexpr int SMEM = NST * STAGE_BYTES + 1024 + 3 * NST * 8 + NST * 8 + INFO_SLOTS * static_cast<int>(sizeof(TileInfo<SEGS>));
 };
 
 __device__ __forceinline__ SegRef seg_lookup_fold(const FoldParams& p, int cls, int nactive, int list_off, int q) {
@@ -70,6 +70,10 @@ __device__ __forceinline__ SegRef seg_lookup_fold(const FoldParams& p, int cls, 
   return r;
 }
 
+// XFORM: the three otherwise idle warps of the producer warpgroup turn every landed stage from (x, mirror x) into
+// (u, v) in place, once per CTA, so that the consumer warps load u and v directly (otherwise each of the WN consumer
+// warps of a row block forms them again while loading its fragments: one DADD per 4 DMMAs on the same FP64 pipe).
+template <bool XFORM>
 __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const __grid_constant__ FoldParams p) {
   using C = FoldCfg;
   constexpr int NST = C::NST, MB = C::MB, NB = C::NB, WN = C::WN;
@@ -77,7 +81,8 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + NST;
-  volatile int* tile_ring = reinterpret_cast<volatile int*>(empty_bar + NST);
+  uint64_t* ready_bar = empty_bar + NST;  // XFORM: u, v of the stage are in place
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(ready_bar + NST);
   using Info = TileInfo<C::SEGS>;
   Info* tile_info = reinterpret_cast<Info*>(const_cast<int*>(tile_ring) + 2 * NST);
 
@@ -88,6 +93,8 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], C::CONSUMER_WARPS);
+      mbar_init(&ready_bar[s], 3);
+      tile_ring[s] = 0;  // the transformer warps look at every stage's slot (only a sentinel is negative)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -102,7 +109,43 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
   if (warp >= C::CONSUMER_WARPS) {
     // ===================== TMA producer warp =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_PRODUCER));
-    if (warp != C::CONSUMER_WARPS) return;
+    if (warp != C::CONSUMER_WARPS) {
+      if constexpr (XFORM) {
+        // ===================== transformer warps: (x, mirror x) -> (u, v) in place =====================
+        // a stage holds SEGS segments x 8 rows x 8 sixteen-byte chunks; chunk c of the direct box (k = 2c, 2c+1)
+        // pairs with chunk 7-c of the mirror box (offsets 15-k: 14-2c, 15-2c)
+        const int t96 = (warp - C::CONSUMER_WARPS - 1) * 32 + lane;
+        int stage = 0;
+        uint32_t phase = 0;
+        while (true) {
+          mbar_wait(&full_bar[stage], phase);
+          if (tile_ring[stage] < 0) {  // sentinel: pass it on
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready_bar[stage]);
+            break;
+          }
+          const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
+#pragma unroll 2
+          for (int idx = t96; idx < C::SEGS * 64; idx += 96) {
+            const int row = (idx >> 3) & 7, c = idx & 7;
+            const uint32_t base = static_cast<uint32_t>((idx >> 6) * 1024 + row * 128);
+            const uint32_t o1 = sA + base + static_cast<uint32_t>((c ^ row) << 4);
+            const uint32_t o2 = sA + static_cast<uint32_t>(C::A_HALF) + base + static_cast<uint32_t>(((7 - c) ^ row) << 4);
+            double x1a, x1b, x2a, x2b;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x1a), "=d"(x1b) : "r"(o1));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x2a), "=d"(x2b) : "r"(o2));
+            // direct k = 2c pairs with mirror offset 15-2c (second of the chunk), k = 2c+1 with 14-2c (first)
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(o1), "d"(x1a + x2b), "d"(x1b + x2a) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(o2), "d"(x1b - x2a), "d"(x1a - x2b) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the next TMA fill overwrites these generic writes
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready_bar[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+      }
+      return;
+    }
     int stage = 0;
     uint32_t phase = 0;
     int seq = 0;
@@ -194,8 +237,10 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
   int stage = 0;
   uint32_t phase = 0;
   int seq = 0;
+  uint64_t* const landed_bar = XFORM ? ready_bar : full_bar;
   while (true) {
-    mbar_wait(&full_bar[stage], phase);
+    if constexpr (XFORM) mbar_wait(&full_bar[stage], phase);  // (already complete: acquires the TMA writes of the operand)
+    mbar_wait(&landed_bar[stage], phase);
     const int tile = tile_ring[stage];
     if (tile < 0) break;
     const Info* info = &tile_info[seq % C::INFO_SLOTS];
@@ -220,7 +265,10 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
         }
       }
       for (int ks = 0; ks < ksteps; ++ks) {
-        if (pass != 0 || ks != 0) mbar_wait(&full_bar[stage], phase);
+        if (pass != 0 || ks != 0) {
+          if constexpr (XFORM) mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&landed_bar[stage], phase);
+        }
         const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
         const uint32_t sB = sA + b_off;
         // one k-slab (4 k values): form u, v while loading the A fragments, then 2 x MB x NB DMMAs
@@ -230,8 +278,8 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
           for (int i = 0; i < MB; ++i) {
             const double x1 = lds64(sA + o1 + static_cast<uint32_t>(i * 1024));
             const double x2 = lds64(sA + o2 + static_cast<uint32_t>(i * 1024));
-            fu[i] = x1 + x2;
-            fv[i] = x1 - x2;
+            if constexpr (XFORM) { fu[i] = x1; fv[i] = x2; }
+            else { fu[i] = x1 + x2; fv[i] = x1 - x2; }
           }
 #pragma unroll
           for (int q = 0; q < NB; ++q) {

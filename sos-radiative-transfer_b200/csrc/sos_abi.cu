@@ -689,7 +689,8 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
     if (r) return r;
     SOS_CUDA(cudaDeviceSynchronize());
   }
-  cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
   p->fold = true;
   return SOS_OK;
 }
@@ -840,7 +841,9 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
     f.J = J_d;
     f.scen = g.scen;
-    sosgemm::jn_gemm_fold_kernel<<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
+    static const bool xform = [] { const char* e = std::getenv("SOS_FOLD_XFORM"); return !(e && e[0] == '0'); }();
+    if (xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
+    else sosgemm::jn_gemm_fold_kernel<false><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     return launch_check(p);
   }
   // 64 x 128 tiles with 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md), or 128 x 144 with 12 warps of 32 x 48
