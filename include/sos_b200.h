@@ -133,7 +133,11 @@ int sos_plan_set_phase(sos_plan* plan, const double* const* A_d, int n_matrices,
  *                       operand's defect is <= 1e-12; F is built from the symmetrised A).
  *   sos_plan_set_folded register one folded operand per matrix of sos_plan_set_phase (same order); sos_source /
  *                       sos_solve then use the folded kernel for full-column, single-GPU launches and the general
- *                       kernel otherwise.  n_matrices = 0 switches it off.  sos_plan_set_phase resets it. */
+ *                       kernel otherwise.  n_matrices = 0 switches it off.  sos_plan_set_phase resets it.
+ *                       For three-region plans it also premixes, per scenario, the two aerosol-row operands
+ *                       c1 F[atm] + c2 F[aer] (SOS_Aer_main_specular.py:321) into one plan-owned operand, so that aerosol
+ *                       tiles need one pass instead of two (S operands of rows*ldf doubles, skipped above 2 GB;
+ *                       environment SOS_FOLD_PREMIX=0 keeps the two-pass tiles). */
 int sos_fold_layout(int nb_angles, int* rows, int* ld);
 int sos_build_folded(sos_plan* plan, const double* A_d, int lda, double* F_d, int ldf, double* defect_out, void* stream);
 int sos_plan_set_folded(sos_plan* plan, const double* const* F_d, int n_matrices, int ldf);

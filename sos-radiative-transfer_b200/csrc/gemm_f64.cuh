@@ -440,8 +440,13 @@ __device__ __forceinline__ void plan_tiles_block(const GroupTable& gt, const int
       plan->group_list_off[g] = gt.member_off[g];
       plan->group_phaseA[g] = gt.phaseA[g];
       plan->group_phaseB[g] = gt.phaseB[g];
-      const int segs = nact[g] * (gt.cls[g] == 1 ? nseg1 : nseg0);
-      t += ((segs + segs_per_tile - 1) / segs_per_tile) * ((split_passes && gt.cls[g] == 1) ? 2 : 1);
+      if (gt.cls[g] == 2) {
+        // premixed aerosol rows (folded kernel): tiles never mix scenarios, each scenario has its own operand
+        t += nact[g] * ((nseg1 + segs_per_tile - 1) / segs_per_tile);
+      } else {
+        const int segs = nact[g] * (gt.cls[g] == 1 ? nseg1 : nseg0);
+        t += ((segs + segs_per_tile - 1) / segs_per_tile) * ((split_passes && gt.cls[g] == 1) ? 2 : 1);
+      }
     }
     plan->group_tile_start[gt.n_groups] = t;
     plan->n_groups = gt.n_groups;

@@ -23,6 +23,7 @@ namespace sosgemm {
 struct FoldParams {
   CUtensorMap map_I;                 // [rows_total][N] (stride ld), box {BK, SEG_ROWS}, 128B swizzle
   CUtensorMap map_F[SOS_MAX_PHASE];  // folded operand [Kp][2*Mh] = [B+ | B-] (stride ldf), box {BN+8, BK}
+  CUtensorMap map_mix;               // premixed aerosol operands [S][Kp][2*Mh]: c1_s F[atm_s] + c2_s F[aer_s] (class 2 groups)
   const TilePlan* plan;
   int* work_counter;
   const int* active_list;
@@ -57,6 +58,13 @@ struct FoldCfg {
   static constexpr int INFO_SLOTS = NST + 2;
   static constexpr int SMEM = NST * STAGE_BYTES + 1024 + 3 * NST * 8 + NST * 8 + INFO_SLOTS * static_cast<int>(sizeof(TileInfo<SEGS>));
 };
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 
 __device__ __forceinline__ SegRef seg_lookup_fold(const FoldParams& p, int cls, int nactive, int list_off, int q) {
   SegRef r;
@@ -171,7 +179,20 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
       if (split) lt >>= 1;
       SegRef sr;
       sr.scen = -1; sr.row = 0; sr.valid = 0;
-      if (lane < C::SEGS) sr = seg_lookup_fold(p, cls, plan->group_nactive[g], plan->group_list_off[g], lt * C::SEGS + lane);
+      int mix_scen = -1;  // class 2: the tile belongs to one scenario and uses that scenario's premixed operand
+      if (cls == 2) {
+        const int tps = (p.nseg[1] + C::SEGS - 1) / C::SEGS;
+        const int rank = lt / tps;
+        mix_scen = p.active_list[plan->group_list_off[g] + rank];
+        const int j = (lt - rank * tps) * C::SEGS + lane;
+        if (lane < C::SEGS && j < p.nseg[1]) {
+          sr.scen = mix_scen;
+          sr.row = mix_scen * p.L + p.seg_row[1][j];
+          sr.valid = p.seg_valid[1][j];
+        }
+      } else if (lane < C::SEGS) {
+        sr = seg_lookup_fold(p, cls, plan->group_nactive[g], plan->group_list_off[g], lt * C::SEGS + lane);
+      }
       const unsigned have = __ballot_sync(0xffffffffu, sr.valid > 0);
       const uint32_t tx = static_cast<uint32_t>(__popc(have)) * (2 * SEG_ROWS * BK * 8) + C::B_BYTES;
       Info* info = &tile_info[seq % C::INFO_SLOTS];
@@ -179,7 +200,8 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
         double coef = 0.0, resc = 0.0;
         if (sr.scen >= 0) {
           const sos_scenario& sc = p.scen[sr.scen];
-          if (cls == 1 && split) { coef = only_pass ? sc.coef_mix_aer : sc.coef_mix_atm; resc = 1.0; }
+          if (cls == 2) coef = 1.0;  // the mixing coefficients are inside the operand
+          else if (cls == 1 && split) { coef = only_pass ? sc.coef_mix_aer : sc.coef_mix_atm; resc = 1.0; }
           else if (cls == 1) { coef = sc.coef_mix_aer; resc = sc.coef_mix_atm / sc.coef_mix_aer; }
           else coef = sc.coef_atm;
         }
@@ -206,8 +228,13 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
             tma_load_2d(dst + lane * (SEG_ROWS * BK * 8), &p.map_I, &full_bar[stage], ks * BK, sr.row);
             tma_load_2d(dst + C::A_HALF + lane * (SEG_ROWS * BK * 8), &p.map_I, &full_bar[stage], p.N - BK - ks * BK, sr.row);
           }
-          if (lane == C::SEGS) tma_load_2d(dst + C::A_BYTES, mapF, &full_bar[stage], ct * C::BN, ks * BK);
-          if (lane == C::SEGS + 1) tma_load_2d(dst + C::A_BYTES + C::B_HALF, mapF, &full_bar[stage], p.Mh + ct * C::BN, ks * BK);
+          if (mix_scen >= 0) {
+            if (lane == C::SEGS) tma_load_3d(dst + C::A_BYTES, &p.map_mix, &full_bar[stage], ct * C::BN, ks * BK, mix_scen);
+            if (lane == C::SEGS + 1) tma_load_3d(dst + C::A_BYTES + C::B_HALF, &p.map_mix, &full_bar[stage], p.Mh + ct * C::BN, ks * BK, mix_scen);
+          } else {
+            if (lane == C::SEGS) tma_load_2d(dst + C::A_BYTES, mapF, &full_bar[stage], ct * C::BN, ks * BK);
+            if (lane == C::SEGS + 1) tma_load_2d(dst + C::A_BYTES + C::B_HALF, mapF, &full_bar[stage], p.Mh + ct * C::BN, ks * BK);
+          }
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
@@ -379,6 +406,21 @@ __global__ void build_folded_kernel(const double* __restrict__ A, int lda, int N
     if (defect > 0.0) atomicMax(&stats[0], static_cast<unsigned long long>(__double_as_longlong(defect)));
     if (amax > 0.0) atomicMax(&stats[1], static_cast<unsigned long long>(__double_as_longlong(amax)));
   }
+}
+
+// Premixed aerosol operands: out[s] = c1_s * F[atm_s] + c2_s * F[aer_s] (c = the two source coefficients of the aerosol rows,
+// SOS_Aer_main_specular.py:321), so that an aerosol-row tile needs ONE operand pass instead of two.
+struct MixSources {
+  const double* F[SOS_MAX_PHASE];
+};
+__global__ void mix_folded_kernel(MixSources src, const sos_scenario* __restrict__ scen, double* __restrict__ out, size_t elems) {
+  const int s = blockIdx.y;
+  const sos_scenario sc = scen[s];
+  const double* __restrict__ Fa = src.F[sc.phase_atm];
+  const double* __restrict__ Fe = src.F[sc.phase_aer];
+  double* __restrict__ o = out + static_cast<size_t>(s) * elems;
+  for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < elems; e += static_cast<size_t>(gridDim.x) * blockDim.x)
+    o[e] = sc.coef_mix_atm * Fa[e] + sc.coef_mix_aer * Fe[e];
 }
 
 }  // namespace sosgemm

@@ -68,6 +68,28 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, 
   return SOS_OK;
 }
 
+// 3D row-major double tensor [slabs][rows][cols] (row stride ld, slab stride rows*ld)
+int encode_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t slabs, uint64_t ld, uint32_t box_cols,
+              uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    g_last_cuda_error = "cuTensorMapEncodeTiled entry point not available";
+    return SOS_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {cols, rows, slabs};
+  cuuint64_t strides[2] = {ld * sizeof(double), rows * ld * sizeof(double)};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = "cuTensorMapEncodeTiled (3D) failed with CUresult " + std::to_string(static_cast<int>(r));
+    return SOS_ERR_CUDA;
+  }
+  return SOS_OK;
+}
+
 }  // namespace
 
 struct sos_plan {
@@ -92,6 +114,7 @@ struct sos_plan {
   int gemm_bm = 0;  // rows per tile
   int gemm_bn = 128;  // columns per tile (128, or 144 when that pads N less and the batch is large)
   int split_passes = 0;  // class-1 operand passes as separate tiles (small batches; see GemmParams)
+  int split_general = 0; // ... as chosen at plan creation for the general kernel
   sosgemm::GroupTable groups;
   int* d_members = nullptr;      // scenario ids per group (static)
   int* d_active_list = nullptr;  // compacted per group (device-built)
@@ -108,6 +131,12 @@ struct sos_plan {
   bool fold = false;
   sosgemm::FoldParams fp;
   unsigned long long* d_fold_stats = nullptr;
+  std::vector<const double*> F_ptrs;
+  // premixed aerosol operands (one per scenario) and the tile-plan tables that go with them
+  bool premix = false;
+  double* d_mix = nullptr;
+  sosgemm::GroupTable groups_premix;
+  int* d_members_premix = nullptr;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -212,8 +241,10 @@ int launch_check(sos_plan* p) {
 }
 
 int plan_tiles(sos_plan* p, cudaStream_t st) {
-  plan_tiles_kernel<<<1, 256, 0, st>>>(p->groups, p->d_members, p->dev.state, p->d_active_list, p->d_tile_plan,
-                                       p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS, p->split_passes);
+  const bool pm = p->fold && p->premix;
+  plan_tiles_kernel<<<1, 256, 0, st>>>(pm ? p->groups_premix : p->groups, pm ? p->d_members_premix : p->d_members, p->dev.state,
+                                       p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS,
+                                       pm ? 0 : p->split_passes);
   return launch_check(p);
 }
 
@@ -489,6 +520,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
       const long long segs = static_cast<long long>(S) * (p->nseg[0] + p->nseg[1]);
       const long long tiles = (segs + 7) / 8 * ((N + 127) / 128);  // (small batches always use 64 x 128 tiles)
       p->split_passes = (grid->n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
+      p->split_general = p->split_passes;
     }
   }
 #undef TRY
@@ -625,10 +657,17 @@ int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
     if (!A_d[i] || (reinterpret_cast<uintptr_t>(A_d[i]) & 15)) return SOS_ERR_INVALID;
   p->A_ptrs.assign(A_d, A_d + n);
   p->lda = lda;
+  const bool was_premix = p->fold && p->premix;
   p->fold = false;  // new operands: the folded set (if any) must be given again
+  p->split_passes = p->split_general;
   int r = encode_A_maps(p);
   if (r) return r;
   p->maps_A_ready = true;
+  if (was_premix) {  // the device tile plan was laid out for per-scenario aerosol tiles
+    r = plan_tiles(p, nullptr);
+    if (r) return r;
+    SOS_CUDA(cudaDeviceSynchronize());
+  }
   return SOS_OK;
 }
 
@@ -662,7 +701,17 @@ int sos_build_folded(sos_plan* p, const double* A_d, int lda, double* F_d, int l
 
 int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   if (!p) return SOS_ERR_INVALID;
-  if (n == 0 || !F_d) { p->fold = false; return SOS_OK; }
+  if (n == 0 || !F_d) {
+    const bool replan = p->fold && p->premix;
+    p->fold = false;
+    p->split_passes = p->split_general;
+    if (replan) {
+      int r = plan_tiles(p, nullptr);
+      if (r) return r;
+      SOS_CUDA(cudaDeviceSynchronize());
+    }
+    return SOS_OK;
+  }
   if (!p->maps_A_ready) return SOS_ERR_STATE;
   if (n != static_cast<int>(p->A_ptrs.size())) return SOS_ERR_INVALID;
   int rows = 0, ld = 0;
@@ -680,10 +729,56 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   p->gemm_bm = FC::BM;
   p->gemm_bn = 128;
   if (reshape) { int r = encode_A_maps(p); if (r) return r; }
+  p->F_ptrs.assign(F_d, F_d + n);
+  const bool was_premix = p->fold && p->premix;
+  // aerosol rows: premix c1 F[atm] + c2 F[aer] per scenario so that their tiles need one operand pass instead of two
+  // (S operands of rows*ldf doubles; above 2 GB the two-pass tiles stay)
+  p->premix = false;
+  {
+    static const bool allow = [] { const char* e = std::getenv("SOS_FOLD_PREMIX"); return !(e && e[0] == '0'); }();
+    const size_t per = static_cast<size_t>(rows) * ldf;
+    const int S = p->dev.S;
+    if (allow && p->grid.n_regions == 3 && per * S * sizeof(double) <= (2ull << 30)) {
+      if (!p->d_mix) { int r = dev_alloc(p, &p->d_mix, per * S); if (r) return r; }
+      sosgemm::MixSources src;
+      for (int i = 0; i < SOS_MAX_PHASE; ++i) src.F[i] = i < n ? F_d[i] : nullptr;
+      dim3 grid(static_cast<unsigned>(std::min<size_t>((per + 255) / 256, 64)), S);
+      sosgemm::mix_folded_kernel<<<grid, 256, 0, nullptr>>>(src, p->dev.scen, p->d_mix, per);
+      int r = launch_check(p);
+      if (r) return r;
+      r = encode_3d(&p->fp.map_mix, p->d_mix, ld, rows, S, ldf, FC::BN_PAD, sosgemm::BK);
+      if (r) return r;
+      if (!p->d_members_premix) {
+        // tile-plan tables: one class-2 group holding every scenario, then the class-0 groups as they are
+        sosgemm::GroupTable& gt = p->groups_premix;
+        std::memset(&gt, 0, sizeof(gt));
+        std::vector<int> flat;
+        gt.cls[0] = 2; gt.phaseA[0] = 0; gt.phaseB[0] = 0; gt.member_off[0] = 0;
+        for (int sidx = 0; sidx < S; ++sidx) flat.push_back(sidx);
+        gt.n_groups = 1;
+        std::vector<int> members_h(p->groups.member_off[p->groups.n_groups]);
+        SOS_CUDA(cudaMemcpy(members_h.data(), p->d_members, members_h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int g = 0; g < p->groups.n_groups; ++g) {
+          if (p->groups.cls[g] != 0) continue;
+          const int ng = gt.n_groups++;
+          gt.cls[ng] = 0; gt.phaseA[ng] = p->groups.phaseA[g]; gt.phaseB[ng] = p->groups.phaseB[g];
+          gt.member_off[ng] = static_cast<int>(flat.size());
+          flat.insert(flat.end(), members_h.begin() + p->groups.member_off[g], members_h.begin() + p->groups.member_off[g + 1]);
+        }
+        gt.member_off[gt.n_groups] = static_cast<int>(flat.size());
+        const int* tmpi = nullptr;
+        r = dev_upload(p, &tmpi, flat.data(), flat.size());
+        if (r) return r;
+        p->d_members_premix = const_cast<int*>(tmpi);
+      }
+      p->premix = true;
+    }
+  }
   const long long segs = static_cast<long long>(p->dev.S) * (p->nseg[0] + p->nseg[1]);
   const long long tiles = (segs + FC::SEGS - 1) / FC::SEGS * ((p->dev.M + FC::BN - 1) / FC::BN);
-  const int split = (p->grid.n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
-  if (reshape || split != p->split_passes) {
+  const int split = (!p->premix && p->grid.n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
+  p->fold = true;
+  if (reshape || split != p->split_passes || p->premix || was_premix) {
     p->split_passes = split;
     int r = plan_tiles(p, nullptr);
     if (r) return r;
@@ -691,7 +786,6 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   }
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
-  p->fold = true;
   return SOS_OK;
 }
 
@@ -846,6 +940,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     else sosgemm::jn_gemm_fold_kernel<false><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     return launch_check(p);
   }
+  if (p->fold && p->premix) return SOS_ERR_UNSUPPORTED;  // the device tile plan is laid out for the folded kernel's per-scenario aerosol tiles
   // 64 x 128 tiles with 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md), or 128 x 144 with 12 warps of 32 x 48
   if (p->gemm_bn == 144)
     sosgemm::jn_gemm_dmma_kernel<4, 3, 4, 6><<<p->n_sms, sosgemm::Cfg<4, 3, 4, 6>::THREADS, sosgemm::Cfg<4, 3, 4, 6>::SMEM, st>>>(p->gp);
