@@ -133,3 +133,32 @@ def test_scenario_defaults_are_the_shipped_literals():
     # SOS_Aer_main_specular.py:23-57
     assert (sc.mu0, sc.z0, sc.z_up, sc.z_down, sc.nb_layers) == (0.5, 120, 25, 17, 800)
     assert (sc.tauStar_atm, sc.tauStar_aer, sc.grd_alb, sc.alb_atm, sc.alb_aer, sc.nb_angles) == (0.104, 0.120, 1, 1.0, 1.0, 501)
+
+
+@pytest.mark.parametrize("name,g,M", [("rayleigh", 0.0, 37), ("hg", 0.8, 64), ("fwc", 0.0, 101)])
+def test_folded_contraction_algebra(name, g, M):
+    """The identity behind csrc/gemm_fold.cuh, restated in NumPy on the oracle's contraction operand: the operand
+    of every reference phase function is centrosymmetric to rounding, and J[:, j], J[:, N-1-j] = u B+ +- v B- with
+    u, v = x[k] +- x[N-1-k] reproduces the full contraction."""
+    mu = so.mu_grid(M)
+    N = 2 * M
+    _, P = sos.phase_matrices(name, M, mu, 0.6, g)
+    A = so.contraction_matrix(P, mu, 0.9)                     # A[k, m], SOS_Aer_I1_In.py:73
+    defect = np.abs(A - A[::-1, ::-1]).max() / np.abs(A).max()
+    assert defect < 1e-12                                     # engine.FOLD_DEFECT_MAX
+    rng = np.random.default_rng(M)
+    x = rng.random((9, N)) * np.exp(2.0 * rng.standard_normal((9, N)))
+    J = x @ A
+    As = 0.5 * (A + A[::-1, ::-1])                            # sos_build_folded symmetrises first
+    mirror = As[:M, ::-1][:, :M]                              # A[k, N-1-j]
+    Bp, Bm = 0.5 * (As[:M, :M] + mirror), 0.5 * (As[:M, :M] - mirror)
+    xr = x[:, ::-1][:, :M]                                    # x[N-1-k]
+    u, v = x[:, :M] + xr, x[:, :M] - xr
+    Jf = np.empty_like(J)
+    Jf[:, :M] = u @ Bp + v @ Bm
+    Jf[:, ::-1][:, :M] = u @ Bp - v @ Bm
+    assert np.max(np.abs(Jf - J) / np.abs(J)) < 1e-12
+    # layout the C ABI promises for the folded operand
+    rows, ld = C.c_int(), C.c_int()
+    n = sos._lib.load().sos_fold_layout(M, C.byref(rows), C.byref(ld))
+    assert rows.value % 16 == 0 and rows.value >= M and ld.value == 2 * rows.value and n == rows.value * ld.value
