@@ -176,7 +176,7 @@ def run_reference(args):
     val = units / (ms * 1e-3)
     sample = (f"{procs} processes x 1 scenario x {orders} order(s) of the NumPy port (method='slices') on a "
               f"{L}x{2 * M_DEFAULT} grid per step; the port vectorises over mu what the reference loops over in Python")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "scattering-order updates/s", "value": val, "unit": "updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -245,7 +245,7 @@ def run_thick(args, sos, torch, dist, dev, rank, world, W):
         dist.barrier()
         peers.close()
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "scattering-order updates/s", "value": units / (ms * 1e-3), "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -257,7 +257,26 @@ def run_thick(args, sos, torch, dist, dev, rank, world, W):
             "clocks": clocks}))
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line, on the process's real stdout (see main: libraries may chat on fd 1)."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: anything a library prints on fd 1 (NCCL prints its version there when
+    # NCCL_DEBUG is set) goes to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -474,7 +493,7 @@ def main():
                 "sample": "1 scenario of the workload, 2 scattering orders at the full 800x1002 grid through the NumPy "
                           "port of the reference algorithm (oracle method='slices', %.1f s); the unmodified reference "
                           "measured 3.0e7 updates/s on one core (BASELINE.md)" % dt}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
