@@ -133,8 +133,10 @@ struct sos_plan {
   unsigned long long* d_fold_stats = nullptr;
   std::vector<const double*> F_ptrs;
   // premixed aerosol operands (one per scenario) and the tile-plan tables that go with them
+  bool fold_xform = true;  // transformer warps form (u, v) once per stage (SOS_FOLD_XFORM=0: every consumer warp does)
   bool premix = false;
   double* d_mix = nullptr;
+  std::vector<int> members_h;  // host copy of d_members
   sosgemm::GroupTable groups_premix;
   int* d_members_premix = nullptr;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
@@ -497,6 +499,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     const int* tmpi = nullptr;
     TRY(dev_upload(p, &tmpi, flat.data(), flat.size()));
     p->d_members = const_cast<int*>(tmpi);
+    p->members_h = flat;
     TRY(dev_alloc(p, &p->d_active_list, flat.size()));
     TRY(dev_alloc(p, &p->d_tile_plan, 1));
     TRY(dev_alloc(p, &p->d_work_counter, 1));
@@ -730,12 +733,14 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   p->gemm_bn = 128;
   if (reshape) { int r = encode_A_maps(p); if (r) return r; }
   p->F_ptrs.assign(F_d, F_d + n);
+  { const char* e = std::getenv("SOS_FOLD_XFORM"); p->fold_xform = !(e && e[0] == '0'); }
   const bool was_premix = p->fold && p->premix;
   // aerosol rows: premix c1 F[atm] + c2 F[aer] per scenario so that their tiles need one operand pass instead of two
   // (S operands of rows*ldf doubles; above 2 GB the two-pass tiles stay)
   p->premix = false;
   {
-    static const bool allow = [] { const char* e = std::getenv("SOS_FOLD_PREMIX"); return !(e && e[0] == '0'); }();
+    const char* env = std::getenv("SOS_FOLD_PREMIX");  // read per call: tests switch it inside one process
+    const bool allow = !(env && env[0] == '0');
     const size_t per = static_cast<size_t>(rows) * ldf;
     const int S = p->dev.S;
     if (allow && p->grid.n_regions == 3 && per * S * sizeof(double) <= (2ull << 30)) {
@@ -756,8 +761,7 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
         gt.cls[0] = 2; gt.phaseA[0] = 0; gt.phaseB[0] = 0; gt.member_off[0] = 0;
         for (int sidx = 0; sidx < S; ++sidx) flat.push_back(sidx);
         gt.n_groups = 1;
-        std::vector<int> members_h(p->groups.member_off[p->groups.n_groups]);
-        SOS_CUDA(cudaMemcpy(members_h.data(), p->d_members, members_h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        const std::vector<int>& members_h = p->members_h;
         for (int g = 0; g < p->groups.n_groups; ++g) {
           if (p->groups.cls[g] != 0) continue;
           const int ng = gt.n_groups++;
@@ -935,8 +939,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
     f.J = J_d;
     f.scen = g.scen;
-    static const bool xform = [] { const char* e = std::getenv("SOS_FOLD_XFORM"); return !(e && e[0] == '0'); }();
-    if (xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
+    if (p->fold_xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     else sosgemm::jn_gemm_fold_kernel<false><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     return launch_check(p);
   }

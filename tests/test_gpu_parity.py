@@ -514,3 +514,39 @@ def test_folded_contraction_vs_general_and_asymmetric_operand(sos):
     eng.set_phase([P])
     assert not eng.folded and eng.fold_defect > 1e-8
     eng.close()
+
+
+def test_folded_kernel_variants_agree(sos, monkeypatch):
+    """The folded contraction's internal variants are the same sums: premixed aerosol operand (one pass) vs two operand
+    passes with a rescaled accumulator, transformer warps vs per-warp u/v -- on packed tiles (S = 20) and on the split
+    tiles of a single scenario."""
+    import torch
+    rng = np.random.default_rng(11)
+    L, M = 120, 165
+    N = 2 * M
+    mu = sos.mu_grid(M)
+    iu, idn = 40, 66                      # 27 aerosol rows: 4 segments, the last one ragged
+    _, Pa = sos.phase_matrices("rayleigh", M, mu, 0.5, 0.0)
+    _, Pe = sos.phase_matrices("hg", M, mu, 0.5, 0.7)
+    w = sos.extrapolation_width(0.7, M)
+    for S in (20, 1):
+        tau = np.tile(np.linspace(0, 0.7, L), (S, 1))
+        coefs = [sos.ScenarioCoefficients(mu0=0.5, grd_alb=0.1, tauStar_tot=0.7, coef_atm=0.9 + 0.004 * s, coef_mix_atm=0.3 + 0.01 * s,
+                                          coef_mix_aer=(0.0 if s == 3 else 0.6 - 0.01 * s), phase_atm=0, phase_aer=1, extrap_width=(w, w, w))
+                 for s in range(S)]
+        x = rng.random((S, L, N)) * np.exp(rng.standard_normal((S, L, N)))
+        out = {}
+        for premix, xform in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
+            monkeypatch.setenv("SOS_FOLD_PREMIX", premix)
+            monkeypatch.setenv("SOS_FOLD_XFORM", xform)
+            eng = sos.SosEngine(mu, tau, coefs, [0, iu, idn + 1, L], sos._lib.SURFACE_SPECULAR, fold=True)
+            eng.set_phase([Pa, Pe])
+            assert eng.folded
+            J = eng.source(eng.to_field(x))
+            torch.cuda.synchronize()
+            out[(premix, xform)] = eng.to_host(J).reshape(S, L, N)
+            eng.close()
+        ref = out[("1", "1")]
+        for key, val in out.items():
+            assert relmax(val, ref) < 1e-13, (S, key)
+            assert relelem(val, ref) < 1e-11, (S, key)
