@@ -111,6 +111,7 @@ struct TileInfo {
   int passes;            // 1 or 2
   int first_pass;        // operand of the first (or only) pass: 0 = A, 1 = B of the group
   int atomic_out;        // 1: add into J instead of storing
+  int ks0, ks1;          // k-steps of this tile (folded kernel with split k: two tiles share an output tile)
 };
 
 template <int WM, int WN, int MB, int NB>

@@ -32,6 +32,8 @@ struct FoldParams {
   int nseg[2];
   int n_col_tiles;   // ceil(M / BN)
   int split_passes;  // see GemmParams
+  int ksplit;        // 1, or 2: every output tile is computed by two tiles (halves of the k range) that add their partial into a
+                     //    zeroed J (exactly two partials per element: order independent) -- launches with fewer tiles than SMs / 2
   int L, N, M, Mh, ld;
   double* J;
   const sos_scenario* scen;
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
   const TilePlan* plan = p.plan;
   const int ksteps = (p.M + BK - 1) / BK;
   const int last_slabs = (p.M - (ksteps - 1) * BK + 3) / 4;  // k-slabs of the last k-step that hold k < M
-  const int n_tiles = plan->n_row_tiles * p.n_col_tiles;
+  const int n_tiles = plan->n_row_tiles * p.n_col_tiles * p.ksplit;
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp >= C::CONSUMER_WARPS) {
@@ -169,8 +171,11 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
         }
         break;
       }
-      const int rt = tile / p.n_col_tiles;
-      const int ct = tile - rt * p.n_col_tiles;
+      const int t2 = tile / p.ksplit;
+      const int kh = tile - t2 * p.ksplit;
+      const int ks0 = kh * ksteps / p.ksplit, ks1 = (kh + 1) * ksteps / p.ksplit;
+      const int rt = t2 / p.n_col_tiles;
+      const int ct = t2 - rt * p.n_col_tiles;
       const int g = find_group(plan, rt);
       const int cls = plan->group_cls[g];
       int lt = rt - plan->group_tile_start[g];
@@ -211,16 +216,19 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
         info->valid[lane] = sr.valid;
       }
       const int passes = (cls == 1 && !split) ? 2 : 1;
-      if (lane == 0) { info->ct = ct; info->passes = passes; info->first_pass = only_pass; info->atomic_out = split ? 1 : 0; }
+      if (lane == 0) {
+        info->ct = ct; info->passes = passes; info->first_pass = only_pass; info->atomic_out = (split || p.ksplit > 1) ? 1 : 0;
+        info->ks0 = ks0; info->ks1 = ks1;
+      }
       __syncwarp();
       ++seq;
       for (int pass = 0; pass < passes; ++pass) {
         const CUtensorMap* mapF = &p.map_F[(pass + only_pass) == 0 ? plan->group_phaseA[g] : plan->group_phaseB[g]];
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int ks = ks0; ks < ks1; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t dst = smem_base + stage * C::STAGE_BYTES;
           if (lane == 0) {
-            if (pass == 0 && ks == 0) tile_ring[stage] = tile;
+            if (pass == 0 && ks == ks0) tile_ring[stage] = tile;
             mbar_expect_tx(&full_bar[stage], tx);
           }
           if (sr.valid > 0) {
@@ -275,6 +283,7 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
     const int ct = info->ct;
     const int passes = info->passes;
     const int atomic_out = info->atomic_out;
+    const int ks0 = info->ks0, ks1 = info->ks1;
 
     double accP[MB][NB][2], accM[MB][NB][2];
 #pragma unroll
@@ -291,8 +300,8 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
           for (int q = 0; q < NB; ++q) { accP[i][q][0] *= r; accP[i][q][1] *= r; accM[i][q][0] *= r; accM[i][q][1] *= r; }
         }
       }
-      for (int ks = 0; ks < ksteps; ++ks) {
-        if (pass != 0 || ks != 0) {
+      for (int ks = ks0; ks < ks1; ++ks) {
+        if (pass != 0 || ks != ks0) {
           if constexpr (XFORM) mbar_wait(&full_bar[stage], phase);
           mbar_wait(&landed_bar[stage], phase);
         }

@@ -133,6 +133,7 @@ struct sos_plan {
   unsigned long long* d_fold_stats = nullptr;
   std::vector<const double*> F_ptrs;
   // premixed aerosol operands (one per scenario) and the tile-plan tables that go with them
+  int fold_ksplit = 1;     // 2: split k for launches with few tiles (single solves), see FoldParams
   bool fold_xform = true;  // transformer warps form (u, v) once per stage (SOS_FOLD_XFORM=0: every consumer warp does)
   bool premix = false;
   double* d_mix = nullptr;
@@ -781,6 +782,12 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   const long long segs = static_cast<long long>(p->dev.S) * (p->nseg[0] + p->nseg[1]);
   const long long tiles = (segs + FC::SEGS - 1) / FC::SEGS * ((p->dev.M + FC::BN - 1) / FC::BN);
   const int split = (!p->premix && p->grid.n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
+  {
+    // single solves: fewer tiles than half the SMs and long k loops -> two tiles per output tile
+    const char* e = std::getenv("SOS_FOLD_KSPLIT");
+    const bool allow = !(e && e[0] == '0');
+    p->fold_ksplit = (allow && 2 * tiles <= p->n_sms && p->dev.M >= 64) ? 2 : 1;
+  }
   p->fold = true;
   if (reshape || split != p->split_passes || p->premix || was_premix) {
     p->split_passes = split;
@@ -916,7 +923,12 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
   p->gp.scen = g.scen;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SOS_CUDA(cudaMemsetAsync(p->d_work_counter, 0, sizeof(int), st));
-  if (p->split_passes) {
+  const bool full_columns = g.col0 == 0 && g.col1 == g.N;
+  const bool use_fold = p->fold && full_columns && !peers && seg_begin == 0 && seg_end == 0x7fffffff;
+  if (use_fold && p->fold_ksplit > 1) {
+    // split-k tiles add two partials per element into a zeroed J
+    SOS_CUDA(cudaMemsetAsync(J_d, 0, static_cast<size_t>(g.S) * g.L * g.ld * sizeof(double), st));
+  } else if (p->split_passes) {
     const int r0 = g.rstart[1], r1 = g.rstart[2];
     dim3 zgrid((g.N + 255) / 256, r1 - r0, g.S);
     zero_rows_kernel<<<zgrid, 256, 0, st>>>(J_d, g.ld, g.L, r0, r1, g.N);
@@ -924,8 +936,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     if (rz) return rz;
   }
   ProfSpan span(p, 0, st);
-  const bool full_columns = g.col0 == 0 && g.col1 == g.N;
-  if (p->fold && full_columns && !peers && seg_begin == 0 && seg_end == 0x7fffffff) {
+  if (use_fold) {
     // centrosymmetric operands: half the DMMA work (gemm_fold.cuh)
     using FC = sosgemm::FoldCfg;
     sosgemm::FoldParams& f = p->fp;
@@ -936,6 +947,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     for (int c = 0; c < 2; ++c) { f.seg_row[c] = p->gp.seg_row[c]; f.seg_valid[c] = p->gp.seg_valid[c]; f.nseg[c] = p->gp.nseg[c]; }
     f.n_col_tiles = (g.M + FC::BN - 1) / FC::BN;
     f.split_passes = p->split_passes;
+    f.ksplit = p->fold_ksplit;
     f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
     f.J = J_d;
     f.scen = g.scen;

@@ -164,9 +164,11 @@ DEFAULT_RUNS = {
 }
 
 
-@pytest.mark.parametrize("tag", list(DEFAULT_RUNS))
-def test_default_grid_vs_golden(sos, golden, tag):
-    """BASELINE configs 1-3 at the reference's 800 x 1002 grid (HG g=0.5 standing in for Mie)."""
+@pytest.mark.parametrize("tag,fold", [(t, "1") for t in DEFAULT_RUNS] + [("eva_spec", "0"), ("wildfire_lamb", "0")])
+def test_default_grid_vs_golden(sos, golden, tag, fold, monkeypatch):
+    """BASELINE configs 1-3 at the reference's 800 x 1002 grid (HG g=0.5 standing in for Mie), through the folded
+    contraction (the default) and, for two of them, through the general kernel (SOS_B200_FOLD=0)."""
+    monkeypatch.setenv("SOS_B200_FOLD", fold)
     d = golden(f"default_{tag}.npz")
     kind, kw = DEFAULT_RUNS[tag]
     n_ref = int(d["n"])

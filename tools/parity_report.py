@@ -15,6 +15,7 @@ RUNS = {
     "wildfire_lamb": ("lambertian", dict(tauStar_atm=0.124, tauStar_aer=0.0075, z_up=15, z_down=14, grd_alb=0.15, alb_aer=0.97)),
     "shipped_spec": ("specular", {}),
 }
+print("contraction:", "general kernel (SOS_B200_FOLD=0)" if os.environ.get("SOS_B200_FOLD") == "0" else "folded kernel (default)")
 for tag, (kind, kw) in RUNS.items():
     d = np.load(os.path.join(ROOT, "tests", "golden", f"default_{tag}.npz"))
     fn = sos.SOS_Aer_main_lambertian if kind == "lambertian" else sos.SOS_Aer_main_specular
