@@ -16,7 +16,7 @@
 namespace sosfirst {
 
 struct Col {
-  double mu, mu0, F0q, Sq, T;
+  double mu, inv_mu, mu0, F0q, Sq, T;  // inv_mu = 1/mu: the two column-dependent exponents per element use a multiply, not a division
   double Cm_atm, Cmir_atm, Cm_mix, Cmir_mix;
   bool down, special;
 };
@@ -47,18 +47,18 @@ __device__ __forceinline__ double i1_value(const Col& c, bool mix, double tt, do
   if (c.down && c.special) {  // |mu + mu0| < 1e-4 (:133-140)
     direct = Cm * c.F0q * e0 * (tt - rk.tau_d) / c.mu0;
   } else {
-    xd = exp((tt - rk.tau_d) / c.mu);
+    xd = exp((tt - rk.tau_d) * c.inv_mu);
     have_xd = true;
     direct = (c.mu0 / (c.mu0 + c.mu)) * Cm * c.F0q * (e0 - rk.ed * xd);
   }
   if (!c.down && c.special) {  // |mu - mu0| < 1e-4 (:225-233)
     surf = Cr * c.Sq * es * (rk.tau_s - tt) / c.mu0;
   } else {
-    surf = (c.mu0 / (c.mu0 - c.mu)) * Cr * c.Sq * (es - rk.esr * exp((tt - rk.tau_s) / c.mu));
+    surf = (c.mu0 / (c.mu0 - c.mu)) * Cr * c.Sq * (es - rk.esr * exp((tt - rk.tau_s) * c.inv_mu));
   }
   double v = direct + surf;
   if (carry != 0.0) {
-    if (!have_xd) xd = exp((tt - rk.tau_d) / c.mu);
+    if (!have_xd) xd = exp((tt - rk.tau_d) * c.inv_mu);
     v = carry * xd + v;
   }
   return v;
@@ -137,6 +137,7 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
   c.mu0 = mu0; c.F0q = F0 * q; c.Sq = S * q; c.T = T;
   if (m < M - 1) {
     c.mu = g.mu[m];
+    c.inv_mu = 1.0 / c.mu;
     c.down = true;
     c.special = fabs(c.mu + mu0) < SOS_MU0_TOLERANCE;
     c.Cm_atm = Catm[m]; c.Cmir_atm = Catm[N - 1 - m];
@@ -157,6 +158,7 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
   Col d;
   d.mu0 = mu0; d.F0q = c.F0q; d.Sq = c.Sq; d.T = T;
   d.mu = g.mu[mir];
+  d.inv_mu = 1.0 / d.mu;
   d.down = true;
   d.special = fabs(d.mu + mu0) < SOS_MU0_TOLERANCE;
   d.Cm_atm = Catm[mir]; d.Cmir_atm = Catm[m];
@@ -170,6 +172,7 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
   }
 
   c.mu = g.mu[m];
+  c.inv_mu = 1.0 / c.mu;
   c.down = false;
   c.special = fabs(c.mu - mu0) < SOS_MU0_TOLERANCE;
   c.Cm_atm = Catm[m]; c.Cmir_atm = Catm[mir];
@@ -212,17 +215,18 @@ first_order_single_kernel(const GridDev g, const double* __restrict__ Cs /*[S][2
   const double k = C / (4.0 * PI);
   const double norm = PI / mu0;  // (:58)
   const double eS = exp(-T / mu0);
+  const double inv_mu = 1.0 / mu, w0 = mu0 / (mu0 + mu);
   for (int t = ta; t < tb; ++t) {
     const double tt = tau[t];
     const double e0 = exp(-tt / mu0);
     double v;
     if (m == M - 1 || m == M) {
-      v = k * (mu0 / (mu0 + mu)) * e0;                                  // (:39,:50)
+      v = k * w0 * e0;                                                  // (:39,:50)
     } else if (m < M - 1) {
       if (fabs(mu + mu0) < SOS_MU0_TOLERANCE) v = k * e0 * tt / mu0;    // (:41-43)
-      else v = (mu0 / (mu0 + mu)) * k * (e0 - exp(tt / mu));            // (:34-37)
+      else v = w0 * k * (e0 - exp(tt * inv_mu));                        // (:34-37)
     } else {
-      v = (mu0 / (mu0 + mu)) * k * (e0 - eS * exp(-(T - tt) / mu));     // (:54-55)
+      v = w0 * k * (e0 - eS * exp(-(T - tt) * inv_mu));                 // (:54-55)
     }
     out[static_cast<size_t>(t) * ld + m] = v * norm;
   }
