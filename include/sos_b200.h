@@ -137,7 +137,9 @@ int sos_plan_set_phase(sos_plan* plan, const double* const* A_d, int n_matrices,
  *                       For three-region plans it also premixes, per scenario, the two aerosol-row operands
  *                       c1 F[atm] + c2 F[aer] (SOS_Aer_main_specular.py:321) into one plan-owned operand, so that aerosol
  *                       tiles need one pass instead of two (S operands of rows*ldf doubles, skipped above 2 GB;
- *                       environment SOS_FOLD_PREMIX=0 keeps the two-pass tiles). */
+ *                       environment SOS_FOLD_PREMIX=0 keeps the two-pass tiles).  Launches with fewer tiles than half the SMs
+ *                       (single solves) split every output tile in two over the k range (two partials added into a
+ *                       zeroed J: order independent; SOS_FOLD_KSPLIT=0 disables it). */
 int sos_fold_layout(int nb_angles, int* rows, int* ld);
 int sos_build_folded(sos_plan* plan, const double* A_d, int lda, double* F_d, int ldf, double* defect_out, void* stream);
 int sos_plan_set_folded(sos_plan* plan, const double* const* F_d, int n_matrices, int ldf);

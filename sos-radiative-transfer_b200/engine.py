@@ -75,6 +75,7 @@ class SosEngine:
         self.lib = _lib.load()
         self.fold = (os.environ.get("SOS_B200_FOLD", "1") != "0") if fold is None else bool(fold)
         self.folded = False
+        self.fold_defect = None   # centrosymmetry defect of the operands (set by set_phase when the fold is considered)
         if not torch.cuda.is_available():
             raise _lib.SosError("no CUDA device: the SOS engine has no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
