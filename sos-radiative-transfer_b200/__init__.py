@@ -11,7 +11,9 @@ the repository root) or with importlib.import_module("sos-radiative-transfer_b20
 from . import _lib
 from ._lib import SosError
 from .grid import mu_grid, tau_profile, extrapolation_width, aerosol_rows
-from .phase import phase_matrices, phase_P, phase_P0
+from .phase import phase_matrices, phase_P, phase_P0, phase_table
+from . import mie
+from .mie import EVA_AEROSOL, WILDFIRE_AEROSOL
 from .engine import SosEngine, ScenarioCoefficients, SolveResult
 from .api import I1_NumInt, Jn_NumInt, In_NumInt, mu_approx_In, clear_cache
 from . import multi_gpu
@@ -21,7 +23,7 @@ from .drivers import (Scenario, DriverResult, BatchSolver, solve_scenarios, SOS_
                       critical_albedo_sweep, EVA, WILDFIRE)
 
 __all__ = [
-    "SosError", "mu_grid", "tau_profile", "extrapolation_width", "aerosol_rows", "phase_matrices", "phase_P", "phase_P0",
+    "SosError", "mu_grid", "tau_profile", "extrapolation_width", "aerosol_rows", "phase_matrices", "phase_P", "phase_P0", "phase_table", "mie", "EVA_AEROSOL", "WILDFIRE_AEROSOL",
     "SosEngine", "ScenarioCoefficients", "SolveResult", "I1_NumInt", "Jn_NumInt", "In_NumInt",
     "mu_approx_In", "clear_cache", "Scenario", "DriverResult", "BatchSolver", "solve_scenarios",
     "MuShardedSolver", "PeerFields", "mu_blocks", "shard_scenarios", "gather_scenario_results", "allgather_columns", "shard_range",

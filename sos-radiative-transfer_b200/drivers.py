@@ -82,7 +82,8 @@ class PhaseCache:
         """(P0, P or None, key).  need_P=False skips the host build of the N x N matrix (the caller builds
         it on the device or already holds the operand)."""
         if isinstance(spec[0], str):
-            name, g = spec[0], float(spec[1])
+            name = spec[0]
+            g = tuple(float(v) for v in spec[1]) if isinstance(spec[1], (tuple, list)) else float(spec[1])
             kP, k0 = (name, g, M), (name, g, M, float(mu0))
             if need_P and kP not in self._P:
                 self._P[kP] = PH.phase_P(name, M, mu, g)

@@ -258,7 +258,7 @@ class SosEngine:
 
     def build_phase_matrix(self, name: str, g: float = 0.5, mu0: Optional[float] = None):
         """P(mu, mu') (and P0(mu, mu0) when mu0 is given) of an analytic family, built ON THE DEVICE
-        (sos_build_phase): 'rayleigh', 'hg', 'fwc', 'iso'.  Returns (P (N, N) tensor, P0 (N,) tensor or None)."""
+        (sos_build_phase): 'rayleigh', 'hg', 'fwc', 'mie_lognormal' (g = (wl, n_re, n_im, r_m, sigma)), 'iso'.  Returns (P (N, N) tensor, P0 (N,) tensor or None)."""
         from . import phase as PH
         N = self.N
         P = torch.empty((N, N), dtype=torch.float64, device=self.device)
@@ -268,21 +268,23 @@ class SosEngine:
             if P0 is not None:
                 P0.fill_(1.0)
             return P, P0
-        fam = {"rayleigh": 0, "hg": 1, "fwc": 2}[name]
+        fam = {"rayleigh": 0, "hg": 1, "fwc": 2, "mie_lognormal": 2}[name]
         phi = np.linspace(0, np.pi, PH.NB_PHI)
         cphi = np.ascontiguousarray(np.cos(0 - phi))
         tx = ty = None
         tn = 0
         if fam == 2:
-            key = ("fwc_table", self.device.index)
+            # tabulated families: FWC cloud, or the log-normal Mie mixture of mie.py (g = its parameter tuple)
+            key = ("phase_table", name, tuple(g) if isinstance(g, (tuple, list)) else None, self.device.index)
             if key not in _OPERANDS:
-                xs, ys = PH._fwc_table()
-                _OPERANDS[key] = (torch.as_tensor(np.ascontiguousarray(xs)).to(self.device),
-                                  torch.as_tensor(np.ascontiguousarray(ys)).to(self.device))
+                xs, ys = PH.phase_table(name, g)
+                _OPERANDS[key] = (torch.as_tensor(np.array(xs, dtype=np.float64)).to(self.device),
+                                  torch.as_tensor(np.array(ys, dtype=np.float64)).to(self.device))
             tx, ty = _OPERANDS[key]
             tn = tx.numel()
+        gval = float(g) if not isinstance(g, (tuple, list)) else 0.0
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.sos_build_phase(self._plan, fam, float(g), float(mu0 if mu0 is not None else 0.5),
+            _lib.check(self.lib.sos_build_phase(self._plan, fam, gval, float(mu0 if mu0 is not None else 0.5),
                                                 phi.ctypes.data, cphi.ctypes.data,
                                                 tx.data_ptr() if tx is not None else None,
                                                 ty.data_ptr() if ty is not None else None, int(tn),

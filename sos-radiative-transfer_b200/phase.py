@@ -6,9 +6,11 @@ matrix symmetric, then every *column* normalised so that trapz(P[:, n], mu) = 4
 (SOS_Aer_phase_func.py:68-292) -- but evaluated as array expressions instead of the reference's
 triple Python loop (89-112 s per matrix at N = 1002 there, well under a second here).
 
-Mie / log-normal Mie (SOS_Aer_phase_func.py:299-753) need `miepython`, which the reference does
-not pin and which is not installed here; callers pass their own P0/P for those (north_star keeps
-Mie coefficients on the host).
+Log-normal Mie aerosols (SOS_Aer_phase_func.py:398-753, the reference's 'eva' / 'wildfire' families) need
+`miepython`, which the reference does not pin and which is not installed here: family 'mie_lognormal' takes
+its tabulated mixture phase function from the host Lorenz-Mie stand-in of mie.py (g = (wavelength, n_re, n_im,
+r_m, sigma), e.g. mie.EVA_AEROSOL) and then goes through the same tabulated builder as the FWC cloud.  Callers
+with their own Mie code still pass (P0, P) arrays.
 """
 from __future__ import annotations
 
@@ -31,6 +33,19 @@ def _fwc_table():
     return _FWC
 
 
+def phase_table(name, g=None):
+    """(cos Theta ascending, values) of a tabulated family: 'fwc', or 'mie_lognormal' with g = (wl, n_re, n_im, r_m, sigma)."""
+    if name == "fwc":
+        return _fwc_table()
+    if name == "mie_lognormal":
+        from . import mie
+        return mie.lognormal_table(*[float(v) for v in g])
+    raise ValueError(f"{name!r} is not a tabulated phase function")
+
+
+TABULATED = ("fwc", "mie_lognormal")
+
+
 def _trapz(y, x, axis=-1):
     y = np.asarray(y)
     d = np.diff(x)
@@ -43,8 +58,8 @@ def _kernel(name, g):
         return lambda c: 0.75 * (1 + c * c)  # SOS_Aer_phase_func.py:97
     if name == "hg":
         return lambda c: (1 - g * g) / ((1 + g * g - 2 * g * c) ** 1.5)  # :158
-    if name == "fwc":
-        xs, ys = _fwc_table()
+    if name in TABULATED:
+        xs, ys = phase_table(name, g)
 
         def interp(c):  # interpolate_fwc_phase, :202-236
             c = np.clip(c, -1, 1)
@@ -98,5 +113,5 @@ def phase_P(name: str, nb_angles: int, mu: np.ndarray, g: float = 0.5, block: in
 
 
 def phase_matrices(name: str, nb_angles: int, mu: np.ndarray, mu0: float, g: float = 0.5):
-    """Return (P0 (N,), P (N, N)) for name in {'iso', 'rayleigh', 'hg', 'fwc'}."""
+    """Return (P0 (N,), P (N, N)) for name in {'iso', 'rayleigh', 'hg', 'fwc', 'mie_lognormal'}."""
     return phase_P0(name, nb_angles, mu, mu0, g), phase_P(name, nb_angles, mu, g)

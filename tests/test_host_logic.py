@@ -162,3 +162,48 @@ def test_folded_contraction_algebra(name, g, M):
     rows, ld = C.c_int(), C.c_int()
     n = sos._lib.load().sos_fold_layout(M, C.byref(rows), C.byref(ld))
     assert rows.value % 16 == 0 and rows.value >= M and ld.value == 2 * rows.value and n == rows.value * ld.value
+
+
+def test_mie_stand_in_against_published_values():
+    """The host Lorenz-Mie series (mie.py, the stand-in for the reference's unpinned miepython) against published
+    numbers: the test sphere of Bohren & Huffman's BHMIE listing (m = 1.55, x = 2 pi 0.525 / 0.6328), Wiscombe's
+    MIEV0 cases m = 1.5 and m = 1.5 - 0.1i at x = 10, the Rayleigh limit, and the 'albedo' normalisation of
+    i_unpolarized that the reference's mixing relies on (SOS_Aer_phase_func.py:419,693)."""
+    M = sos.mie
+    qext, qsca, qback, _ = M.efficiencies(1.55 + 0j, 2 * np.pi * 0.525 / 0.6328)
+    assert abs(qext - 3.10543) < 5e-6 and abs(qsca - 3.10543) < 5e-6 and abs(qback - 2.92534) < 5e-6
+    qext, qsca, _, g = M.efficiencies(1.5 + 0j, 10.0)
+    assert abs(qext - 2.881999) < 2e-6 and abs(qsca - 2.881999) < 2e-6 and abs(g - 0.742913) < 2e-6
+    qext, qsca, _, g = M.efficiencies(1.5 - 0.1j, 10.0)          # either sign of Im m means absorption
+    assert abs(qext - 2.459791) < 2e-6 and abs(qsca - 1.235144) < 2e-6 and abs(g - 0.922350) < 2e-6
+    assert M.efficiencies(1.5 + 0.1j, 10.0)[0] == qext
+    x, m = 0.01, 1.5 + 0j
+    assert abs(M.efficiencies(m, x)[1] / ((8 / 3) * x ** 4 * abs((m * m - 1) / (m * m + 2)) ** 2) - 1) < 1e-4
+    mu_s = np.linspace(-1, 1, 20001)
+    i_ray = M.i_unpolarized(m, x, mu_s)
+    assert np.max(np.abs(i_ray / i_ray[10000] - (1 + mu_s ** 2))) < 2e-4
+    for m, x in ((1.5 + 0j, 10.0), (1.7 + 0.03j, 2.0), (1.44 + 0j, 0.3)):
+        qe, qs, _, g = M.efficiencies(m, x)
+        i = M.i_unpolarized(m, x, mu_s)
+        integral = 2 * np.pi * so.trapz(i, mu_s)
+        assert abs(integral - qs / qe) < 5e-6                   # integral over 4 pi = single-scattering albedo
+        assert abs(2 * np.pi * so.trapz(i * mu_s, mu_s) / integral - g) < 5e-6
+
+
+def test_lognormal_mie_family_goes_through_the_tabulated_builder():
+    """'mie_lognormal' = the reference's log_normal_mie mixture (as coded) as a 6001-point table, then the same
+    azimuth average / normalisation as every other family (trapz(P[:, n], mu) = 4, trapz(P0, mu) = 2)."""
+    xs, ys = sos.phase_table("mie_lognormal", sos.EVA_AEROSOL)
+    assert xs.shape == (6001,) and xs[0] == -1 and xs[-1] == 1 and np.all(ys > 0)
+    assert ys[-1] > 50 * ys[0]                                    # r_m = 0.5 um at 0.55 um: strongly forward peaked
+    xw, yw = sos.phase_table("mie_lognormal", sos.WILDFIRE_AEROSOL)
+    assert 3 < yw[-1] / yw[0] < 30                                # r_m = 0.065 um: much closer to Rayleigh
+    Mg = 41
+    mu = so.mu_grid(Mg)
+    P0, P = sos.phase_matrices("mie_lognormal", Mg, mu, 0.5, sos.EVA_AEROSOL)
+    assert np.allclose([so.trapz(P[:, n], mu) for n in range(2 * Mg)], 4.0, rtol=1e-13)
+    assert abs(so.trapz(P0, mu) - 2.0) < 1e-13
+    assert np.max(np.abs(P - P[::-1, ::-1])) < 1e-12 * np.max(P)  # centrosymmetric like every other family
+    # the physical mixture (weights n(r) r^2 Qsca(x)) is available but is not what the reference computes
+    _, yp = sos.mie.lognormal_table(*sos.EVA_AEROSOL, as_coded=False)
+    assert np.max(np.abs(yp / yp.max() - ys / ys.max())) > 1e-3
