@@ -48,7 +48,8 @@ def make_scenarios(sos, S, rank=0, L=L_DEFAULT, M=M_DEFAULT):
     mu0s = np.linspace(0.1, 1.0, 10)
     oms = np.linspace(0.7, 1.0, 10)
     albs = (0.05, 0.15, 0.3)
-    phases = (("hg", 0.5), ("hg", 0.7), ("fwc", 0.0))
+    # phase-function axis of BASELINE configs[4]: HG / Mie / FWC (Mie = the EVA log-normal mixture from the host stand-in)
+    phases = (("hg", 0.5), ("mie_lognormal", sos.EVA_AEROSOL), ("fwc", 0.0))
     out = []
     for i in range(S):
         k = rank * S + i
@@ -478,7 +479,7 @@ def main():
                        "l2": "256 MB flush between timed steps; per-step working set %.0f MB > 126 MB L2" % (3 * S * L * eng.ld * 8 / 1e6),
                        "scenarios_swapped_for_blend_overrun": n_swapped,
                        "contraction": "folded (centrosymmetric operands, defect %.1e)" % eng.fold_defect if eng.folded else "general",
-                       "mie": "HG(0.5/0.7) and FWC stand in for log-normal Mie (miepython absent)"},
+                       "phase_functions": "HG(0.5) / log-normal Mie mixture (EVA aerosol, host Lorenz-Mie stand-in: miepython absent) / FWC table"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * float(te.item())},
