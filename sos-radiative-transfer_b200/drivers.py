@@ -185,7 +185,9 @@ class BatchSolver:
     def solve(self, keep_orders: int = 0, poll_every: int = 2, max_orders: Optional[int] = None):
         I1 = self.first_order()
         mo = max_orders if max_orders is not None else max(s.max_orders for s in self.scenarios)
-        return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every)
+        # the first order is recomputed by every solve, so its buffer can serve as the loop's I_n field -- unless the caller
+        # wants the per-order fields back (results() then reads I1 as order 1)
+        return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every, consume_I1=(keep_orders == 0))
 
     def results(self, res, quadratures=True, keep_orders=0, fields=True) -> List[DriverResult]:
         """Per-scenario results on the host.  fields=False skips the D2H copy of the radiance fields
@@ -198,7 +200,7 @@ class BatchSolver:
         orders = None
         if keep_orders and res.orders is not None:
             orders = res.orders[:, :, : eng.N].reshape(keep_orders, eng.S, eng.L, eng.N).cpu().numpy()
-        I1 = eng.to_host(self.I1).reshape(eng.S, eng.L, eng.N) if keep_orders else None
+        I1 = eng.to_host(self.I1).reshape(eng.S, eng.L, eng.N) if (keep_orders and res.orders is not None) else None
         out = []
         for i, sc in enumerate(self.scenarios):
             r = DriverResult(I=I[i] if fields else None, n=int(res.n_orders[i]), tau=self.tau[i], mu=self.mu,

@@ -349,16 +349,22 @@ class SosEngine:
         return res
 
     def solve(self, I1: torch.Tensor, max_orders: int = 10000, keep_orders: int = 0, poll_every: int = 1,
-              In: Optional[torch.Tensor] = None, J: Optional[torch.Tensor] = None, I: Optional[torch.Tensor] = None) -> SolveResult:
+              In: Optional[torch.Tensor] = None, J: Optional[torch.Tensor] = None, I: Optional[torch.Tensor] = None,
+              consume_I1: bool = False) -> SolveResult:
         """The order loop of SOS_Aer() (SOS_Aer_main_specular.py:302-458) for the whole batch.
 
-        I1 is not modified.  keep_orders > 0 also returns the first `keep_orders` fields I_n (n >= 2).
+        I1 is not modified unless consume_I1 is set: then its buffer serves as the I_n field of the loop (one field copy
+        less per solve; the caller recomputes the first order before it needs it again).  keep_orders > 0 also returns
+        the first `keep_orders` fields I_n (n >= 2).
         """
         I = self._buf("I") if I is None else I
-        In = self._buf("In") if In is None else In
         J = self._buf("J") if J is None else J
         I.copy_(I1)
-        In.copy_(I1)
+        if consume_I1 and In is None:
+            In = I1
+        else:
+            In = self._buf("In") if In is None else In
+            In.copy_(I1)
         orders = None
         optr = None
         if keep_orders > 0:
