@@ -6,7 +6,7 @@
 
 Workload (BASELINE.json configs[4], the critical-albedo style batch sweep): S independent
 three-region scenarios per GPU on the reference's default grid (800 layers x 1002 mu), spanning
-tau_aer x mu0 x omega_aer x surface albedo x aerosol phase function; every GPU solves its own S
+tau_aer x mu0 x omega_aer x surface albedo x aerosol phase function (HG / log-normal Mie stand-in / FWC); every GPU solves its own S
 scenarios with no data-path collective (scaling: weak).  A "step" is one whole solve of the batch:
 closed-form first order + the order loop to In/I < 1e-4 for every scenario.
 
