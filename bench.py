@@ -435,6 +435,42 @@ def main():
     except OSError:
         roofline["sweeps"]["peak"] = 6650.0
         roofline["sweeps"]["peak_source"] = "fallback"
+    lowrank = [int(r) for r in getattr(eng, "lowrank", [])]
+    if any(lowrank):
+        # Rows whose operand is low rank (Rayleigh: rank 2) no longer go through the DMMA kernel: the contraction is then a
+        # mix of an HBM-bound skinny product (those rows) and the dense folded kernel (aerosol rows), and its FLOP count
+        # against the tensor peak stops meaning anything -- report it by time and in the SURVEY 8d unit only.
+        roofline["kernel"] = ("jn_lowrank_kernel (rows of low-rank operands, ranks %s: HBM bound) + jn_gemm_fold_kernel "
+                              "(aerosol rows: FP64 DMMA)" % lowrank)
+        roofline["flops_model"] = ("general_equivalent_tflops = 2*L*N^2 per scenario-order / time (SURVEY 8d); executed: 4*r*N FLOP per "
+                                   "low-rank row + N^2 per dense folded row")
+        roofline["achieved"] = roofline["frac"] = None
+    if sweep_ms > gemm_ms:
+        # the layer sweeps are now the dominant kernels of a step: they carry the headline roofline (HBM bound)
+        sw = roofline.pop("sweeps")
+        contraction = roofline
+        straffic = None
+        snote = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_sweeps_traffic.json")) as f:
+                tj = json.load(f)
+            active_per_order = float(np.sum(n_orders - 1)) * args.steps / max(sweep_spans, 1)
+            straffic = tj["dram_bytes_per_active_scenario"] * active_per_order
+            snote = ("dram__bytes_read+write of the four sweep kernels per order from profiles/r01_ncu_sweeps_traffic.json (%.3e B at "
+                     "%d active scenarios; algorithmic %.3e B) scaled to %.1f active scenarios per timed order"
+                     % (tj["dram_bytes_per_order"], tj["scenarios"], tj["algorithmic_bytes_per_order"], active_per_order))
+        except (OSError, KeyError, ValueError):
+            pass
+        roofline = {
+            "bound": "hbm",
+            "kernel": "sweep_local + sweep_carry + sweep_apply + sweep_zone (layer sweeps, mu->0 rules, accumulate, convergence ratios)",
+            "achieved": sw["achieved"], "peak": sw.get("peak"), "unit": "GB/s", "frac": sw.get("frac"),
+            "traffic": straffic, "traffic_source": snote,
+            "algorithmic_bytes_per_element": 32, "ms_per_order": sw["ms_per_order"],
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "peak_source" not in sw else sw["peak_source"],
+            "sweeps_share_of_step": sweep_ms / (step_ms * args.steps),
+            "contraction": contraction,
+        }
 
     # ---------------- end to end through the public API (host arrays in, NumPy out) ----------------
     phases = sos.drivers._PHASES  # host-side phase matrices were built during plan creation above
@@ -478,7 +514,7 @@ def main():
                        "orders_per_scenario": [int(n_orders.min()), int(n_orders.max())],
                        "l2": "256 MB flush between timed steps; per-step working set %.0f MB > 126 MB L2" % (3 * S * L * eng.ld * 8 / 1e6),
                        "scenarios_swapped_for_blend_overrun": n_swapped,
-                       "contraction": "folded (centrosymmetric operands, defect %.1e)" % eng.fold_defect if eng.folded else "general",
+                       "contraction": ("folded (centrosymmetric operands, defect %.1e)%s" % (eng.fold_defect, "; low-rank rows (ranks %s)" % [int(r) for r in eng.lowrank] if any(eng.lowrank) else "")) if eng.folded else "general",
                        "phase_functions": "HG(0.5) / log-normal Mie mixture (EVA aerosol, host Lorenz-Mie stand-in: miepython absent) / FWC table"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

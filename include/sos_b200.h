@@ -144,6 +144,17 @@ int sos_fold_layout(int nb_angles, int* rows, int* ld);
 int sos_build_folded(sos_plan* plan, const double* A_d, int lda, double* F_d, int ldf, double* defect_out, void* stream);
 int sos_plan_set_folded(sos_plan* plan, const double* const* F_d, int n_matrices, int ldf);
 
+/* Low-rank operands (optional).  The Rayleigh operand of SOS_Aer_phase_func.py:79-133 is rank 2 and the isotropic one
+ * (:68-76) rank 1, exactly up to rounding; every row outside the aerosol layer uses the molecular operand
+ * (SOS_Aer_main_specular.py:323).  For an operand registered here with rank r in 1..16 and factors A = Us Vt --
+ * Ut_d[i] = (U diag(s))^T and Vt_d[i], both [R][ldr] with R = 4 (r <= 4) or 16 rows, zero beyond r -- the rows that use it
+ * alone are contracted as (I Us) Vt: 2 r N multiply-adds per row instead of N^2, HBM bound.  rank[i] = 0 keeps operand i
+ * dense.  Takes effect with the folded contraction (call before or after sos_plan_set_folded); sos_plan_set_phase
+ * resets it; n_matrices = 0 switches it off.  The caller computes the factors (the Python host: SVD, rank at 1e-13 of
+ * the largest singular value). */
+int sos_plan_set_lowrank(sos_plan* plan, const double* const* Ut_d, const double* const* Vt_d, const int* rank, int n_matrices,
+                         int ldr);
+
 /* First order.
  *  n_regions == 3: inlined closed form of SOS_Aer_main_specular.py:104-292; C_h is [S][2][N]:
  *     C_h[s][0][m] = alb_atm*P0_atm[m], C_h[s][1][m] = alb_atm*P0_atm[m]*f_atm + alb_aer*P0_aer[m]*f_aer

@@ -77,6 +77,7 @@ SIGNATURES = {
     "sos_fold_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sos_build_folded": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_double), _vp]),
     "sos_plan_set_folded": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int]),
+    "sos_plan_set_lowrank": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, C.c_int]),
     "sos_first_order": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source_rows": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),

@@ -441,7 +441,9 @@ __device__ __forceinline__ void plan_tiles_block(const GroupTable& gt, const int
       plan->group_list_off[g] = gt.member_off[g];
       plan->group_phaseA[g] = gt.phaseA[g];
       plan->group_phaseB[g] = gt.phaseB[g];
-      if (gt.cls[g] == 2) {
+      if (gt.cls[g] == 3) {
+        // low-rank operand: these rows are contracted by jn_lowrank_kernel, no dense tiles
+      } else if (gt.cls[g] == 2) {
         // premixed aerosol rows (folded kernel): tiles never mix scenarios, each scenario has its own operand
         t += nact[g] * ((nseg1 + segs_per_tile - 1) / segs_per_tile);
       } else {

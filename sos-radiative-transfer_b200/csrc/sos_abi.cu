@@ -13,6 +13,7 @@
 #include "first_order.cuh"
 #include "gemm_f64.cuh"
 #include "gemm_fold.cuh"
+#include "gemm_lowrank.cuh"
 #include "phase.cuh"
 #include "quadrature.cuh"
 #include "sweep.cuh"
@@ -138,8 +139,15 @@ struct sos_plan {
   bool premix = false;
   double* d_mix = nullptr;
   std::vector<int> members_h;  // host copy of d_members
-  sosgemm::GroupTable groups_premix;
+  sosgemm::GroupTable groups_premix;   // fold-mode tables: class 2 = premixed aerosol rows, class 3 = low-rank operand rows
   int* d_members_premix = nullptr;
+  // low-rank operands (gemm_lowrank.cuh): rank 0 = dense
+  int lowrank_rank[SOS_MAX_PHASE] = {0};
+  const double* lowrank_Ut[SOS_MAX_PHASE] = {nullptr};
+  const double* lowrank_Vt[SOS_MAX_PHASE] = {nullptr};
+  int lowrank_ldr = 0;
+  int n_lowrank_groups = 0;
+  int lowrank_rp = 4;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -244,10 +252,10 @@ int launch_check(sos_plan* p) {
 }
 
 int plan_tiles(sos_plan* p, cudaStream_t st) {
-  const bool pm = p->fold && p->premix;
+  const bool pm = p->fold && p->d_members_premix != nullptr;  // fold-mode tables (build_fold_tables)
   plan_tiles_kernel<<<1, 256, 0, st>>>(pm ? p->groups_premix : p->groups, pm ? p->d_members_premix : p->d_members, p->dev.state,
                                        p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS,
-                                       pm ? 0 : p->split_passes);
+                                       p->split_passes);
   return launch_check(p);
 }
 
@@ -661,8 +669,9 @@ int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
     if (!A_d[i] || (reinterpret_cast<uintptr_t>(A_d[i]) & 15)) return SOS_ERR_INVALID;
   p->A_ptrs.assign(A_d, A_d + n);
   p->lda = lda;
-  const bool was_premix = p->fold && p->premix;
-  p->fold = false;  // new operands: the folded set (if any) must be given again
+  const bool was_premix = p->fold;
+  p->fold = false;  // new operands: the folded set and the low-rank factors (if any) must be given again
+  for (int i = 0; i < SOS_MAX_PHASE; ++i) p->lowrank_rank[i] = 0;
   p->split_passes = p->split_general;
   int r = encode_A_maps(p);
   if (r) return r;
@@ -703,10 +712,102 @@ int sos_build_folded(sos_plan* p, const double* A_d, int lda, double* F_d, int l
   return SOS_OK;
 }
 
+// Fold-mode tile-plan tables: aerosol rows = one class-2 group (premixed operand per scenario) or the class-1 groups of
+// the general plan; every class-0 group whose operand is low rank becomes class 3 (no dense tiles, jn_lowrank_kernel).
+static int build_fold_tables(sos_plan* p) {
+  const int S = p->dev.S;
+  sosgemm::GroupTable& gt = p->groups_premix;
+  std::memset(&gt, 0, sizeof(gt));
+  std::vector<int> flat;
+  const std::vector<int>& members_h = p->members_h;
+  auto copy_group = [&](int g, int cls) {
+    const int ng = gt.n_groups++;
+    gt.cls[ng] = cls; gt.phaseA[ng] = p->groups.phaseA[g]; gt.phaseB[ng] = p->groups.phaseB[g];
+    gt.member_off[ng] = static_cast<int>(flat.size());
+    flat.insert(flat.end(), members_h.begin() + p->groups.member_off[g], members_h.begin() + p->groups.member_off[g + 1]);
+  };
+  if (p->premix) {
+    gt.cls[0] = 2; gt.phaseA[0] = 0; gt.phaseB[0] = 0; gt.member_off[0] = 0;
+    for (int sidx = 0; sidx < S; ++sidx) flat.push_back(sidx);
+    gt.n_groups = 1;
+  } else {
+    for (int g = 0; g < p->groups.n_groups; ++g)
+      if (p->groups.cls[g] == 1) copy_group(g, 1);
+  }
+  p->n_lowrank_groups = 0;
+  p->lowrank_rp = 4;
+  for (int g = 0; g < p->groups.n_groups; ++g) {
+    if (p->groups.cls[g] != 0) continue;
+    const int r = p->lowrank_rank[p->groups.phaseA[g]];
+    copy_group(g, r > 0 ? 3 : 0);
+    if (r > 0) { p->n_lowrank_groups++; if (r > 4) p->lowrank_rp = 16; }
+  }
+  gt.member_off[gt.n_groups] = static_cast<int>(flat.size());
+  if (flat.size() != members_h.size()) return SOS_ERR_STATE;  // (both hold every scenario once per row class)
+  if (!p->d_members_premix) {
+    int r = dev_alloc(p, &p->d_members_premix, flat.size());
+    if (r) return r;
+  }
+  SOS_CUDA(cudaMemcpy(p->d_members_premix, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return SOS_OK;
+}
+
+// dense (DMMA) row tiles of an all-active launch in fold mode, for the small-launch heuristics
+static long long fold_dense_row_tiles(const sos_plan* p) {
+  using FC = sosgemm::FoldCfg;
+  long long rows = 0;
+  for (int g = 0; g < p->groups_premix.n_groups; ++g) {
+    const long long members = p->groups_premix.member_off[g + 1] - p->groups_premix.member_off[g];
+    const int cls = p->groups_premix.cls[g];
+    if (cls == 3) continue;
+    if (cls == 2) rows += members * ((p->nseg[1] + FC::SEGS - 1) / FC::SEGS);
+    else rows += (members * (cls == 1 ? p->nseg[1] : p->nseg[0]) + FC::SEGS - 1) / FC::SEGS;
+  }
+  return rows;
+}
+
+static int refresh_fold_plan(sos_plan* p) {
+  using FC = sosgemm::FoldCfg;
+  int r = build_fold_tables(p);
+  if (r) return r;
+  const long long tiles = fold_dense_row_tiles(p) * ((p->dev.M + FC::BN - 1) / FC::BN);
+  p->split_passes = (!p->premix && p->grid.n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
+  {
+    // single solves: fewer tiles than half the SMs and long k loops -> two tiles per output tile
+    const char* e = std::getenv("SOS_FOLD_KSPLIT");
+    const bool allow = !(e && e[0] == '0');
+    p->fold_ksplit = (allow && 2 * tiles <= p->n_sms && p->dev.M >= 64) ? 2 : 1;
+  }
+  r = plan_tiles(p, nullptr);
+  if (r) return r;
+  SOS_CUDA(cudaDeviceSynchronize());
+  return SOS_OK;
+}
+
+int sos_plan_set_lowrank(sos_plan* p, const double* const* Ut_d, const double* const* Vt_d, const int* rank, int n, int ldr) {
+  if (!p) return SOS_ERR_INVALID;
+  if (n == 0) {
+    for (int i = 0; i < SOS_MAX_PHASE; ++i) p->lowrank_rank[i] = 0;
+  } else {
+    if (!Ut_d || !Vt_d || !rank || !p->maps_A_ready || n != static_cast<int>(p->A_ptrs.size()) || ldr < p->N) return SOS_ERR_INVALID;
+    for (int i = 0; i < n; ++i) {
+      if (rank[i] < 0 || rank[i] > 16) return SOS_ERR_INVALID;
+      if (rank[i] > 0 && (!Ut_d[i] || !Vt_d[i])) return SOS_ERR_INVALID;
+    }
+    for (int i = 0; i < SOS_MAX_PHASE; ++i) {
+      p->lowrank_rank[i] = i < n ? rank[i] : 0;
+      p->lowrank_Ut[i] = i < n ? Ut_d[i] : nullptr;
+      p->lowrank_Vt[i] = i < n ? Vt_d[i] : nullptr;
+    }
+    p->lowrank_ldr = ldr;
+  }
+  return p->fold ? refresh_fold_plan(p) : SOS_OK;
+}
+
 int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   if (!p) return SOS_ERR_INVALID;
   if (n == 0 || !F_d) {
-    const bool replan = p->fold && p->premix;
+    const bool replan = p->fold;
     p->fold = false;
     p->split_passes = p->split_general;
     if (replan) {
@@ -727,7 +828,7 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
     int r = encode_2d(&p->fp.map_F[i], F_d[i], ld, rows, ldf, FC::BN_PAD, sosgemm::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r) return r;
   }
-  // the folded kernel and the general fallback (column-sharded or peer launches) share one device tile plan:
+  // the folded kernel and the general fallback (column-sharded or peer launches) share the tile shape:
   // 64-row tiles, 128-column general tiles
   const bool reshape = p->gemm_bm != FC::BM || p->gemm_bn != 128;
   p->gemm_bm = FC::BM;
@@ -735,7 +836,6 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   if (reshape) { int r = encode_A_maps(p); if (r) return r; }
   p->F_ptrs.assign(F_d, F_d + n);
   { const char* e = std::getenv("SOS_FOLD_XFORM"); p->fold_xform = !(e && e[0] == '0'); }
-  const bool was_premix = p->fold && p->premix;
   // aerosol rows: premix c1 F[atm] + c2 F[aer] per scenario so that their tiles need one operand pass instead of two
   // (S operands of rows*ldf doubles; above 2 GB the two-pass tiles stay)
   p->premix = false;
@@ -754,47 +854,12 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
       if (r) return r;
       r = encode_3d(&p->fp.map_mix, p->d_mix, ld, rows, S, ldf, FC::BN_PAD, sosgemm::BK);
       if (r) return r;
-      if (!p->d_members_premix) {
-        // tile-plan tables: one class-2 group holding every scenario, then the class-0 groups as they are
-        sosgemm::GroupTable& gt = p->groups_premix;
-        std::memset(&gt, 0, sizeof(gt));
-        std::vector<int> flat;
-        gt.cls[0] = 2; gt.phaseA[0] = 0; gt.phaseB[0] = 0; gt.member_off[0] = 0;
-        for (int sidx = 0; sidx < S; ++sidx) flat.push_back(sidx);
-        gt.n_groups = 1;
-        const std::vector<int>& members_h = p->members_h;
-        for (int g = 0; g < p->groups.n_groups; ++g) {
-          if (p->groups.cls[g] != 0) continue;
-          const int ng = gt.n_groups++;
-          gt.cls[ng] = 0; gt.phaseA[ng] = p->groups.phaseA[g]; gt.phaseB[ng] = p->groups.phaseB[g];
-          gt.member_off[ng] = static_cast<int>(flat.size());
-          flat.insert(flat.end(), members_h.begin() + p->groups.member_off[g], members_h.begin() + p->groups.member_off[g + 1]);
-        }
-        gt.member_off[gt.n_groups] = static_cast<int>(flat.size());
-        const int* tmpi = nullptr;
-        r = dev_upload(p, &tmpi, flat.data(), flat.size());
-        if (r) return r;
-        p->d_members_premix = const_cast<int*>(tmpi);
-      }
       p->premix = true;
     }
   }
-  const long long segs = static_cast<long long>(p->dev.S) * (p->nseg[0] + p->nseg[1]);
-  const long long tiles = (segs + FC::SEGS - 1) / FC::SEGS * ((p->dev.M + FC::BN - 1) / FC::BN);
-  const int split = (!p->premix && p->grid.n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
-  {
-    // single solves: fewer tiles than half the SMs and long k loops -> two tiles per output tile
-    const char* e = std::getenv("SOS_FOLD_KSPLIT");
-    const bool allow = !(e && e[0] == '0');
-    p->fold_ksplit = (allow && 2 * tiles <= p->n_sms && p->dev.M >= 64) ? 2 : 1;
-  }
   p->fold = true;
-  if (reshape || split != p->split_passes || p->premix || was_premix) {
-    p->split_passes = split;
-    int r = plan_tiles(p, nullptr);
-    if (r) return r;
-    SOS_CUDA(cudaDeviceSynchronize());
-  }
+  int r = refresh_fold_plan(p);
+  if (r) return r;
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
   return SOS_OK;
@@ -951,11 +1016,27 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
     f.J = J_d;
     f.scen = g.scen;
+    if (p->n_lowrank_groups > 0) {
+      // rows whose operand is low rank (Rayleigh / isotropic): two skinny products, HBM bound (gemm_lowrank.cuh)
+      sosgemm::LowRankParams lr;
+      lr.I = In1_d; lr.J = J_d;
+      for (int i = 0; i < SOS_MAX_PHASE; ++i) { lr.Ut[i] = p->lowrank_Ut[i]; lr.Vt[i] = p->lowrank_Vt[i]; }
+      lr.plan = p->d_tile_plan; lr.active_list = p->d_active_list;
+      lr.seg_row0 = p->gp.seg_row[0]; lr.seg_valid0 = p->gp.seg_valid[0]; lr.nseg0 = p->nseg[0];
+      lr.L = g.L; lr.N = g.N; lr.ld = g.ld; lr.ldr = p->lowrank_ldr;
+      lr.scen = g.scen;
+      const long long units = static_cast<long long>(g.S) * p->nseg[0] * 2;
+      const int blocks = static_cast<int>(std::min<long long>((units + 7) / 8, 8LL * p->n_sms));
+      if (p->lowrank_rp <= 4) sosgemm::jn_lowrank_kernel<4><<<blocks, sosgemm::LR_THREADS, 0, st>>>(lr);
+      else sosgemm::jn_lowrank_kernel<16><<<blocks, sosgemm::LR_THREADS, 0, st>>>(lr);
+      int rl = launch_check(p);
+      if (rl) return rl;
+    }
     if (p->fold_xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     else sosgemm::jn_gemm_fold_kernel<false><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     return launch_check(p);
   }
-  if (p->fold && p->premix) return SOS_ERR_UNSUPPORTED;  // the device tile plan is laid out for the folded kernel's per-scenario aerosol tiles
+  if (p->fold && (p->premix || p->n_lowrank_groups)) return SOS_ERR_UNSUPPORTED;  // the device tile plan has fold-only group classes
   // 64 x 128 tiles with 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md), or 128 x 144 with 12 warps of 32 x 48
   if (p->gemm_bn == 144)
     sosgemm::jn_gemm_dmma_kernel<4, 3, 4, 6><<<p->n_sms, sosgemm::Cfg<4, 3, 4, 6>::THREADS, sosgemm::Cfg<4, 3, 4, 6>::SMEM, st>>>(p->gp);

@@ -29,6 +29,9 @@ _PINNED = {}
 _OPERANDS = {}  # device-resident contraction operands shared between engines (see SosEngine.set_phase)
 _FOLDED = {}    # their folded counterparts [B+ | B-] and centrosymmetry defects (sos_build_folded)
 FOLD_DEFECT_MAX = 1e-12  # fold only operands that are centrosymmetric to rounding (observed <= 3e-14 for every builder)
+_LOWRANK = {}   # low-rank factors (Ut, Vt, rank) of the operands, see SosEngine._lowrank_factors
+LOWRANK_TOL = 1e-13      # numerical rank = singular values above this fraction of the largest
+LOWRANK_MAX = 16         # sos_plan_set_lowrank takes ranks up to 16
 
 
 def _pinned_pair(elems: int):
@@ -75,6 +78,7 @@ class SosEngine:
         self.lib = _lib.load()
         self.fold = (os.environ.get("SOS_B200_FOLD", "1") != "0") if fold is None else bool(fold)
         self.folded = False
+        self.lowrank = []         # numerical rank per operand (0 = dense), set by set_phase in fold mode
         self.fold_defect = None   # centrosymmetry defect of the operands (set by set_phase when the fold is considered)
         if not torch.cuda.is_available():
             raise _lib.SosError("no CUDA device: the SOS engine has no CPU fallback")
@@ -252,9 +256,56 @@ class SosEngine:
             self._F.append(hit[0])
             self.fold_defect = max(self.fold_defect, hit[1])
         if self.fold_defect <= FOLD_DEFECT_MAX:
+            self._set_lowrank(cks)
             ptrs = (C.c_void_p * len(self._F))(*[f.data_ptr() for f in self._F])
             _lib.check(self.lib.sos_plan_set_folded(self._plan, ptrs, len(self._F), ldf.value), "sos_plan_set_folded")
             self.folded = True
+
+    def _lowrank_factors(self, A: torch.Tensor):
+        """(Ut, Vt, rank) with A = (Ut^T)(Vt) to rounding, or (None, None, 0) when the numerical rank exceeds LOWRANK_MAX.
+        The Rayleigh operand of the reference is rank 2, the isotropic one rank 1 (csrc/gemm_lowrank.cuh)."""
+        N = self.N
+        A = A[:, :N]
+        # cheap screen first: the range of A seen through LOWRANK_MAX + 4 random directions
+        gen = torch.Generator(device="cpu").manual_seed(0)
+        probe = torch.randn((N, LOWRANK_MAX + 4), dtype=torch.float64, generator=gen).to(self.device)
+        sv = torch.linalg.svdvals(A @ probe)
+        if int((sv > LOWRANK_TOL * sv[0]).sum()) > LOWRANK_MAX:
+            return None, None, 0
+        U, S, Vh = torch.linalg.svd(A)
+        r = int((S > LOWRANK_TOL * S[0]).sum())
+        if r == 0 or r > LOWRANK_MAX:
+            return None, None, 0
+        R = 4 if r <= 4 else 16
+        Ut = torch.zeros((R, self.ld), dtype=torch.float64, device=self.device)
+        Vt = torch.zeros((R, self.ld), dtype=torch.float64, device=self.device)
+        Ut[:r, :N] = (U[:, :r] * S[:r]).T
+        Vt[:r, :N] = Vh[:r, :]
+        return Ut, Vt, r
+
+    def _set_lowrank(self, cks):
+        """Register the low-rank factors of the operands that have them (sos_plan_set_lowrank); SOS_B200_LOWRANK=0 skips it."""
+        n = len(self._A)
+        self.lowrank = [0] * n
+        if os.environ.get("SOS_B200_LOWRANK", "1") == "0":
+            return
+        self._LR = []
+        for i, (A, ck) in enumerate(zip(self._A, cks)):
+            hit = _LOWRANK.get(ck) if ck is not None else None
+            if hit is None:
+                hit = self._lowrank_factors(A)
+                if ck is not None:
+                    if len(_LOWRANK) >= 32:
+                        _LOWRANK.pop(next(iter(_LOWRANK)))
+                    _LOWRANK[ck] = hit
+            self._LR.append(hit)
+            self.lowrank[i] = hit[2]
+        if not any(self.lowrank):
+            return
+        ut = (C.c_void_p * n)(*[(h[0].data_ptr() if h[2] else None) for h in self._LR])
+        vt = (C.c_void_p * n)(*[(h[1].data_ptr() if h[2] else None) for h in self._LR])
+        rk = (C.c_int * n)(*self.lowrank)
+        _lib.check(self.lib.sos_plan_set_lowrank(self._plan, ut, vt, rk, n, self.ld), "sos_plan_set_lowrank")
 
     def build_phase_matrix(self, name: str, g: float = 0.5, mu0: Optional[float] = None):
         """P(mu, mu') (and P0(mu, mu0) when mu0 is given) of an analytic family, built ON THE DEVICE
@@ -323,6 +374,10 @@ class SosEngine:
 
     def set_columns(self, col0: int, col1: int):
         """Own only the mu columns [col0, col1) (mu-block sharding, see sos_plan_set_columns)."""
+        if (int(col0), int(col1)) != (0, self.N) and self.folded:
+            # column-sharded plans use the general contraction: leave fold mode (its tile plan has fold-only row classes)
+            _lib.check(self.lib.sos_plan_set_folded(self._plan, None, 0, 0), "sos_plan_set_folded")
+            self.folded = False
         _lib.check(self.lib.sos_plan_set_columns(self._plan, int(col0), int(col1)), "sos_plan_set_columns")
         self.col0, self.col1 = int(col0), int(col1)
 

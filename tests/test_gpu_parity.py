@@ -575,3 +575,49 @@ def test_lognormal_mie_aerosol_device_build_and_solve(sos, so):
         ref = _oracle_solve(so, sos, sc, aer=("mie_lognormal", aerosol))
         assert r.n == ref["n"], name
         assert relmax(r.I, ref["I"]) < TOL, name
+
+
+def test_lowrank_operand_rows_match_the_dense_contraction(sos, monkeypatch):
+    """Rayleigh (rank 2) and isotropic (rank 1) operands: the rows that use them alone are contracted as (I Us) Vt by
+    jn_lowrank_kernel; HG stays dense.  Same J as the dense folded kernel on random rows, ragged segments, S = 1 and a batch."""
+    import torch
+    rng = np.random.default_rng(5)
+    for L, M, S, atm in ((131, 100, 3, "rayleigh"), (70, 37, 1, "iso"), (200, 251, 24, "rayleigh")):
+        N = 2 * M
+        mu = sos.mu_grid(M)
+        iu, idn = L // 3, L // 3 + 10
+        tau = np.tile(np.linspace(0, 0.7, L), (S, 1))
+        _, Pa = sos.phase_matrices(atm, M, mu, 0.5, 0.0)
+        _, Pe = sos.phase_matrices("hg", M, mu, 0.5, 0.8)
+        w = sos.extrapolation_width(0.7, M)
+        coefs = [sos.ScenarioCoefficients(mu0=0.5, grd_alb=0.1, tauStar_tot=0.7, coef_atm=0.9 + 0.003 * s, coef_mix_atm=0.3 + 0.01 * s,
+                                          coef_mix_aer=0.6 - 0.01 * s, phase_atm=0, phase_aer=1, extrap_width=(w, w, w))
+                 for s in range(S)]
+        x = rng.random((S, L, N)) * np.exp(rng.standard_normal((S, L, N)))
+        out = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("SOS_B200_LOWRANK", flag)
+            eng = sos.SosEngine(mu, tau, coefs, [0, iu, idn + 1, L], sos._lib.SURFACE_SPECULAR, fold=True)
+            eng.set_phase([Pa, Pe])
+            assert eng.folded
+            assert eng.lowrank == ([2 if atm == "rayleigh" else 1, 0] if flag == "1" else [0, 0])
+            J = eng.source(eng.to_field(x))
+            torch.cuda.synchronize()
+            out[flag] = eng.to_host(J).reshape(S, L, N)
+            eng.close()
+        assert relmax(out["1"], out["0"]) < 1e-13, (L, M, S)
+        assert relelem(out["1"], out["0"]) < 1e-11, (L, M, S)
+    # single homogeneous layer (the Jn_NumInt case): every row is low rank, no dense tile at all
+    L, M = 90, 64
+    mu = sos.mu_grid(M)
+    _, P = sos.phase_matrices("rayleigh", M, mu, 0.5, 0.0)
+    x = rng.random((L, 2 * M))
+    tau = np.linspace(0, 0.5, L)
+    monkeypatch.setenv("SOS_B200_LOWRANK", "1")
+    sos.clear_cache()
+    J1 = sos.Jn_NumInt(2, x, tau, mu, 0.5, 0.5, P, 0.9, M)
+    monkeypatch.setenv("SOS_B200_FOLD", "0")
+    sos.clear_cache()
+    J0 = sos.Jn_NumInt(2, x, tau, mu, 0.5, 0.5, P, 0.9, M)
+    sos.clear_cache()
+    assert relmax(J1, J0) < 1e-13
