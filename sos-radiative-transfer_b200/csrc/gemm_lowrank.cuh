@@ -11,7 +11,7 @@
 //
 // The host decides per operand (engine.py: SVD of A, rank at 1e-13 of the largest singular value, at most 16) and
 // registers the factors with sos_plan_set_lowrank; groups of such operands get class 3 in the fold-mode tile plan
-// (no dense tiles) and are processed here: one warp per 4 rows (half of an 8-row segment), fragments in registers.
+// (no dense tiles) and are processed here: one warp per LR_ROWS rows of an 8-row segment, fragments in registers.
 #pragma once
 #include "gemm_f64.cuh"
 
@@ -31,14 +31,15 @@ struct LowRankParams {
   const sos_scenario* scen;
 };
 
-constexpr int LR_ROWS = 4;      // rows per warp
+constexpr int LR_ROWS = 4;      // rows per warp (2 rows per warp and twice the warps was measured: 0.643 vs 0.615 ms at S = 96)
 constexpr int LR_THREADS = 256;
 
 template <int RP>
 __global__ void __launch_bounds__(LR_THREADS) jn_lowrank_kernel(const LowRankParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TilePlan* plan = p.plan;
-  const int per_scen = p.nseg0 * 2;  // units (half segments) per scenario
+  constexpr int PER_SEG = SEG_ROWS / LR_ROWS;
+  const int per_scen = p.nseg0 * PER_SEG;  // units (LR_ROWS rows of a segment) per scenario
   int total = 0;
   for (int g = 0; g < plan->n_groups; ++g)
     if (plan->group_cls[g] == 3) total += plan->group_nactive[g] * per_scen;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(LR_THREADS) jn_lowrank_kernel(const LowRankPar
     const int v = u - base;
     const int rank = v / per_scen;
     const int w = v - rank * per_scen;
-    const int seg = w >> 1, half = w & 1;
+    const int seg = w / PER_SEG, half = w - seg * PER_SEG;
     const int valid = min(LR_ROWS, p.seg_valid0[seg] - LR_ROWS * half);
     if (valid <= 0) continue;
     const int s = p.active_list[plan->group_list_off[g] + rank];
@@ -72,8 +73,8 @@ __global__ void __launch_bounds__(LR_THREADS) jn_lowrank_kernel(const LowRankPar
     for (int r = 0; r < LR_ROWS; ++r)
 #pragma unroll
       for (int k = 0; k < RP; ++k) acc[r][k] = 0.0;
-#pragma unroll 2
-    for (int m = lane; m < p.N; m += 32) {
+#pragma unroll 4
+    for (int m = lane; m < p.N; m += 32) {  // (16 row loads in flight per warp: the kernel is HBM-latency bound)
       double x[LR_ROWS];
 #pragma unroll
       for (int r = 0; r < LR_ROWS; ++r) x[r] = (r < valid) ? Irow[static_cast<size_t>(r) * p.ld + m] : 0.0;

@@ -1025,7 +1025,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
       lr.seg_row0 = p->gp.seg_row[0]; lr.seg_valid0 = p->gp.seg_valid[0]; lr.nseg0 = p->nseg[0];
       lr.L = g.L; lr.N = g.N; lr.ld = g.ld; lr.ldr = p->lowrank_ldr;
       lr.scen = g.scen;
-      const long long units = static_cast<long long>(g.S) * p->nseg[0] * 2;
+      const long long units = static_cast<long long>(g.S) * p->nseg[0] * (sosgemm::SEG_ROWS / sosgemm::LR_ROWS);
       const int blocks = static_cast<int>(std::min<long long>((units + 7) / 8, 8LL * p->n_sms));
       if (p->lowrank_rp <= 4) sosgemm::jn_lowrank_kernel<4><<<blocks, sosgemm::LR_THREADS, 0, st>>>(lr);
       else sosgemm::jn_lowrank_kernel<16><<<blocks, sosgemm::LR_THREADS, 0, st>>>(lr);
