@@ -16,10 +16,12 @@ closed-form first order + the order loop to In/I < 1e-4 for every scenario.
             coefficients and phase matrices, solve, D2H of the flux / diffusivity / heating-rate
             profiles, order counts and TOA net flux of every scenario (what a forcing sweep returns;
             the reference's SOS_Aer_radiative_forcing returns one float per solve)
-  roofline: dominant kernel = the FP64 source contraction (jn_gemm_fold / jn_gemm_dmma), timed with CUDA
-            events on the launching stream inside the timed steps; peak = FP64 DMMA/DFMA throughput measured
-            on this GPU in the same run (MEASURED_PEAKS.json has no FP64 entry).  The folded kernel needs half
-            the FLOPs of the general one for the same J; `achieved` counts the FLOPs of the kernel that ran
+  roofline: the dominant kernel class of the timed steps (CUDA events on the launching stream inside them): the four
+            layer-sweep kernels (HBM bound, peak = MEASURED_PEAKS.json hbm_gbs) when the molecular rows of the
+            contraction are low rank (Rayleigh: the default workload), with the contraction nested as
+            roofline.contraction; otherwise the FP64 source contraction (jn_gemm_fold / jn_gemm_dmma) against the
+            FP64 DMMA/DFMA throughput measured on this GPU in the same run (MEASURED_PEAKS.json has no FP64 entry),
+            counting the FLOPs of the kernel that ran (the folded kernel needs half of the general one's)
   cpu_baseline / --impl reference: the NumPy oracle port of the reference algorithm
             (oracle/sos_oracle.py, method="slices") on the host cores, bounded sample.
 """
