@@ -207,3 +207,24 @@ def test_lognormal_mie_family_goes_through_the_tabulated_builder():
     # the physical mixture (weights n(r) r^2 Qsca(x)) is available but is not what the reference computes
     _, yp = sos.mie.lognormal_table(*sos.EVA_AEROSOL, as_coded=False)
     assert np.max(np.abs(yp / yp.max() - ys / ys.max())) > 1e-3
+
+
+def test_lowrank_structure_of_the_molecular_operand():
+    """The property behind csrc/gemm_lowrank.cuh, restated in NumPy: the Rayleigh operand of the reference is rank 2
+    (isotropic: 1) to rounding, so (I Us) Vt reproduces I A; HG, FWC and the Mie mixture are not low rank."""
+    M = 101
+    N = 2 * M
+    mu = so.mu_grid(M)
+    rng = np.random.default_rng(3)
+    x = rng.random((7, N)) * np.exp(rng.standard_normal((7, N)))
+    ranks = {}
+    for name, g in (("rayleigh", 0.0), ("iso", 0.0), ("hg", 0.5), ("fwc", 0.0)):
+        _, P = sos.phase_matrices(name, M, mu, 0.5, g)
+        A = so.contraction_matrix(P, mu, 1.0)
+        U, S, Vh = np.linalg.svd(A)
+        r = int((S > 1e-13 * S[0]).sum())            # engine.LOWRANK_TOL
+        ranks[name] = r
+        if r <= 16:                                   # engine.LOWRANK_MAX
+            J = (x @ (U[:, :r] * S[:r])) @ Vh[:r]
+            assert np.max(np.abs(J - x @ A) / np.abs(x @ A)) < 1e-13, name
+    assert ranks["rayleigh"] == 2 and ranks["iso"] == 1 and ranks["hg"] > 16 and ranks["fwc"] > 16
