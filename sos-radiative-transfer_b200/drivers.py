@@ -82,8 +82,8 @@ class PhaseCache:
         """(P0, P or None, key).  need_P=False skips the host build of the N x N matrix (the caller builds
         it on the device or already holds the operand)."""
         if isinstance(spec[0], str):
-            name = spec[0]
-            g = tuple(float(v) for v in spec[1]) if isinstance(spec[1], (tuple, list)) else float(spec[1])
+            name, g = PH.resolve(spec[0], spec[1] if len(spec) > 1 else None)   # 'eva' / 'wildfire' -> the log-normal Mie mixture
+            g = tuple(float(v) for v in g) if isinstance(g, (tuple, list)) else float(g)
             kP, k0 = (name, g, M), (name, g, M, float(mu0))
             if need_P and kP not in self._P:
                 self._P[kP] = PH.phase_P(name, M, mu, g)

@@ -35,6 +35,7 @@ def _fwc_table():
 
 def phase_table(name, g=None):
     """(cos Theta ascending, values) of a tabulated family: 'fwc', or 'mie_lognormal' with g = (wl, n_re, n_im, r_m, sigma)."""
+    name, g = resolve(name, g)
     if name == "fwc":
         return _fwc_table()
     if name == "mie_lognormal":
@@ -44,6 +45,15 @@ def phase_table(name, g=None):
 
 
 TABULATED = ("fwc", "mie_lognormal")
+
+
+def resolve(name, g=None):
+    """The reference's dispatcher names for its two Mie aerosols (phase_func(), SOS_Aer_phase_func.py:12-63: 'eva',
+    'wildfire') -> ('mie_lognormal', parameters); every other family is returned unchanged."""
+    if name in ("eva", "wildfire"):
+        from . import mie
+        return "mie_lognormal", (mie.EVA_AEROSOL if name == "eva" else mie.WILDFIRE_AEROSOL)
+    return name, g
 
 
 def _trapz(y, x, axis=-1):
@@ -78,6 +88,7 @@ def _kernel(name, g):
 
 def phase_P0(name: str, nb_angles: int, mu: np.ndarray, mu0: float, g: float = 0.5) -> np.ndarray:
     """First-order phase function P0(mu, mu0), normalised to trapz(P0, mu) = 2 (:92-105)."""
+    name, g = resolve(name, g)
     N = 2 * nb_angles
     mu = np.asarray(mu, dtype=np.float64)
     if name == "iso":
@@ -94,6 +105,7 @@ def phase_P0(name: str, nb_angles: int, mu: np.ndarray, mu0: float, g: float = 0
 
 def phase_P(name: str, nb_angles: int, mu: np.ndarray, g: float = 0.5, block: int = 128) -> np.ndarray:
     """P(mu, mu'): raw matrix symmetric, then every column normalised to trapz = 4 (:112-131)."""
+    name, g = resolve(name, g)
     N = 2 * nb_angles
     mu = np.asarray(mu, dtype=np.float64)
     if name == "iso":

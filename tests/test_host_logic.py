@@ -228,3 +228,20 @@ def test_lowrank_structure_of_the_molecular_operand():
             J = (x @ (U[:, :r] * S[:r])) @ Vh[:r]
             assert np.max(np.abs(J - x @ A) / np.abs(x @ A)) < 1e-13, name
     assert ranks["rayleigh"] == 2 and ranks["iso"] == 1 and ranks["hg"] > 16 and ranks["fwc"] > 16
+
+
+def test_reference_aerosol_names_resolve_to_the_mie_mixture():
+    """'eva' / 'wildfire' (the names of the reference's phase_func dispatcher) are the log-normal Mie mixtures of mie.py."""
+    from importlib import import_module
+    D = import_module("sos-radiative-transfer_b200.drivers")
+    M = 21
+    mu = so.mu_grid(M)
+    cache = D.PhaseCache()
+    P0a, Pa, ka = cache.get(("eva", 0.0), M, mu, 0.5)
+    P0b, Pb, kb = cache.get(("mie_lognormal", sos.EVA_AEROSOL), M, mu, 0.5)
+    assert ka == kb == ("mie_lognormal", tuple(float(v) for v in sos.EVA_AEROSOL), M)
+    assert np.array_equal(P0a, P0b) and np.array_equal(Pa, Pb)
+    P0w, Pw = sos.phase_matrices("wildfire", M, mu, 0.5)
+    P0x, Px = sos.phase_matrices("mie_lognormal", M, mu, 0.5, sos.WILDFIRE_AEROSOL)
+    assert np.array_equal(P0w, P0x) and np.array_equal(Pw, Px)
+    assert cache.get(("hg", 0.5), M, mu, 0.5)[2] == ("hg", 0.5, M)
