@@ -293,7 +293,10 @@ class SosEngine:
         for i, (A, ck) in enumerate(zip(self._A, cks)):
             hit = _LOWRANK.get(ck) if ck is not None else None
             if hit is None:
-                hit = self._lowrank_factors(A)
+                try:
+                    hit = self._lowrank_factors(A)
+                except RuntimeError:   # a failing SVD must not break the solve: the operand simply stays dense
+                    hit = (None, None, 0)
                 if ck is not None:
                     if len(_LOWRANK) >= 32:
                         _LOWRANK.pop(next(iter(_LOWRANK)))
