@@ -36,7 +36,10 @@ typedef enum {
   SOS_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed (see sos_last_cuda_error) */
   SOS_ERR_NOMEM = -3,
   SOS_ERR_UNSUPPORTED = -4,  /* e.g. not an sm_100 device */
-  SOS_ERR_STATE = -5         /* call order violated (e.g. source before set_phase) */
+  SOS_ERR_STATE = -5,        /* call order violated (e.g. source before set_phase) */
+  SOS_ERR_RETRY = -6         /* sos_solve only: the fused order kernel met a case it cannot finish (a mu -> 0+ blend wider
+                                than 128 columns); the plan has switched to its general kernels -- restore I_d / In_d
+                                (they were consumed) and call sos_solve again */
 } sos_error;
 
 typedef enum {
@@ -48,6 +51,7 @@ typedef enum {
 /* device-side status bits (OR-ed per scenario) */
 #define SOS_STATUS_BLEND_OVERRUN 1u /* reference would raise IndexError (SOS_Aer_I1_In.py:103) */
 #define SOS_STATUS_NONFINITE 2u     /* inf/nan met in a convergence ratio */
+#define SOS_STATUS_MAX_ORDERS 4u    /* sos_solve stopped at max_orders with this scenario still above threshold */
 
 /* Grid shared by all scenarios of a batch. */
 typedef struct {
@@ -150,10 +154,20 @@ int sos_plan_set_folded(sos_plan* plan, const double* const* F_d, int n_matrices
  * Ut_d[i] = (U diag(s))^T and Vt_d[i], both [R][ldr] with R = 4 (r <= 4) or 16 rows, zero beyond r -- the rows that use it
  * alone are contracted as (I Us) Vt: 2 r N multiply-adds per row instead of N^2, HBM bound.  rank[i] = 0 keeps operand i
  * dense.  Takes effect with the folded contraction (call before or after sos_plan_set_folded); sos_plan_set_phase
- * resets it; n_matrices = 0 switches it off.  The caller computes the factors (the Python host: SVD, rank at 1e-13 of
- * the largest singular value). */
+ * resets it; n_matrices = 0 switches it off.  The caller supplies the factors (the Python host: the closed form of
+ * sos_build_lowrank_mu2 below, accepted only when it reproduces the dense operand to rounding). */
 int sos_plan_set_lowrank(sos_plan* plan, const double* const* Ut_d, const double* const* Vt_d, const int* rank, int n_matrices,
                          int ldr);
+/* Closed-form factors for sos_plan_set_lowrank (no SVD): summed over the two half rings, the azimuth integrand of the
+ * Rayleigh builder (SOS_Aer_phase_func.py:97) is 0.75 (2 + 2 mu^2 mu'^2 + 2 (1 - mu^2)(1 - mu'^2) cos^2 phi), so every row k of
+ * A[k][m] = w_k/4 P[m][N-1-k] is affine in mu_m^2 whatever the column normalisation (:131) did: A[k][m] = alpha_k + beta_k mu_m^2
+ * (isotropic, :68-76: beta = 0).  Reads alpha, beta off two columns of A_d, writes Ut_d = [alpha; beta; 0; 0], Vt_d = [1; mu^2; 0; 0]
+ * ([4][ldr], see sos_lowrank_layout), and returns *residual_out = max|A - Ut^T Vt| / max|A| and *rank_out (1 or 2).  The caller
+ * enables the factors only if the residual is at rounding level (the Python host: <= 1e-14); any other operand stays dense.
+ * Synchronises the stream. */
+int sos_lowrank_layout(int nb_angles, int* rows, int* ldr);
+int sos_build_lowrank_mu2(sos_plan* plan, const double* A_d, int lda, double* Ut_d, double* Vt_d, int ldr, double* residual_out,
+                          int* rank_out, void* stream);
 
 /* First order.
  *  n_regions == 3: inlined closed form of SOS_Aer_main_specular.py:104-292; C_h is [S][2][N]:
@@ -218,6 +232,13 @@ int sos_quadratures(sos_plan* plan, const double* I_d, double direct_scale, cons
 
 /* Number of kernel launches issued through this plan so far (bench.py's gpu_launches). */
 long long sos_launch_count(const sos_plan* plan);
+
+/* Which code path will sos_solve take on this plan?  Returns 0 / 1 (or the device ordinal), negative on error. */
+#define SOS_QUERY_FUSED_ORDER 0       /* the single-pass order kernel (batches; csrc/strip.cuh) instead of the chunked scan */
+#define SOS_QUERY_GENERATED_SOURCE 1  /* ... with J rebuilt from two projections per row on the molecular rows */
+#define SOS_QUERY_FOLDED 2            /* folded contraction registered */
+#define SOS_QUERY_DEVICE 3            /* CUDA device ordinal the plan lives on */
+int sos_plan_query(const sos_plan* plan, int what);
 
 /* mu-block sharding of one large grid (BASELINE config 4): this plan computes only the mu columns
  * [col0, col1) of J and I_n (and accumulates only those columns of I); the caller all-gathers the

@@ -17,6 +17,10 @@ class SosError(RuntimeError):
     pass
 
 
+class SosRetry(SosError):
+    """sos_solve returned SOS_ERR_RETRY: the plan left its fused order kernel; restore the inputs and solve again."""
+
+
 class sos_grid(C.Structure):
     _fields_ = [
         ("nb_layers", C.c_int),
@@ -58,7 +62,8 @@ class sos_result(C.Structure):
 
 
 SURFACE_NONE, SURFACE_SPECULAR, SURFACE_LAMBERT = 0, 1, 2
-STATUS_BLEND_OVERRUN, STATUS_NONFINITE = 1, 2
+QUERY_FUSED_ORDER, QUERY_GENERATED_SOURCE, QUERY_FOLDED, QUERY_DEVICE = 0, 1, 2, 3
+STATUS_BLEND_OVERRUN, STATUS_NONFINITE, STATUS_MAX_ORDERS = 1, 2, 4
 
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
@@ -78,6 +83,8 @@ SIGNATURES = {
     "sos_build_folded": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_double), _vp]),
     "sos_plan_set_folded": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int]),
     "sos_plan_set_lowrank": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, C.c_int]),
+    "sos_lowrank_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sos_build_lowrank_mu2": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), _vp]),
     "sos_first_order": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source_rows": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
@@ -94,6 +101,7 @@ SIGNATURES = {
     "sos_reset": (C.c_int, [_vp, _vp, _vp]),
     "sos_quadratures": (C.c_int, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sos_launch_count": (C.c_longlong, [_vp]),
+    "sos_plan_query": (C.c_int, [_vp, C.c_int]),
     "sos_plan_set_columns": (C.c_int, [_vp, C.c_int, C.c_int]),
     "sos_state_ratios": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "sos_set_profiling": (C.c_int, [_vp, C.c_int]),
@@ -127,6 +135,8 @@ def load():
 def check(code: int, what: str = ""):
     if code == 0:
         return
+    if code == -6:
+        raise SosRetry(f"{what or 'libsos_b200'}: solve must be repeated with the plan's general kernels")
     lib = load()
     msg = lib.sos_strerror(code).decode()
     extra = lib.sos_last_cuda_error().decode()

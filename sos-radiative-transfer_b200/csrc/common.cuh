@@ -11,6 +11,10 @@
 #define SOS_BLEND_THRESHOLD 0.0001
 #define SOS_MU0_TOLERANCE 0.0001
 
+// internal status bit: the fused order kernel (strip.cuh) met a mu -> 0+ blend that leaves its 128-column zone; the
+// solve is repeated with the chunked kernels (sos_solve returns SOS_ERR_RETRY after switching the plan over)
+#define SOS_STATUS_STRIP_FALLBACK 0x100u
+
 #define SOS_MAX_PHASE 16
 #define SOS_MAX_GROUPS 48
 #define SOS_MAX_PEERS 8
@@ -41,6 +45,7 @@ struct GridDev {
   const sos_scenario* scen; // [S]
   ScenState* state;         // [S]
   int* n_active;            // [1]
+  int* active_flat;         // [S] ids of the active scenarios, ascending (rebuilt with n_active)
   const double* W;          // extrapolation matrices
   int widx[4], wns[4], woff[4];
   int first_small;          // first downward column with |mu| < MU_THRESHOLD (M-1 if none)

@@ -126,7 +126,6 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
       int k = 0;
       while (k + 1 < g.nreg && t >= g.rstart[k + 1]) ++k;
       const double* C = (k == 1) ? Cmix : Catm;
-      const double tt = tau[t];
       out[static_cast<size_t>(t) * ld + m] = (mu0 / (mu0 + g.mu[m])) * C[m] * (F0 * q) * sh_e0[t - ta] +
                                              (mu0 / (mu0 - g.mu[m])) * C[mir] * (S * q) * sh_es[t - ta];
     }

@@ -9,9 +9,11 @@
 // skinny products, 2 r N multiply-adds per row instead of N^2: the rows become HBM bound (read I once, write J once)
 // and the dense DMMA kernel is left with the aerosol rows.  Agreement with the dense kernels ~3e-15 relative.
 //
-// The host decides per operand (engine.py: SVD of A, rank at 1e-13 of the largest singular value, at most 16) and
-// registers the factors with sos_plan_set_lowrank; groups of such operands get class 3 in the fold-mode tile plan
-// (no dense tiles) and are processed here: one warp per LR_ROWS rows of an 8-row segment, fragments in registers.
+// The factors come from sos_build_lowrank_mu2 (closed form, below; the host enables them when the fitted operand
+// reproduces the dense one to rounding) and are registered with sos_plan_set_lowrank; groups of such operands get
+// class 3 in the fold-mode tile plan (no dense tiles) and are processed here: one warp per LR_ROWS rows of an 8-row
+// segment, fragments in registers.  Inside sos_solve the fused order kernel (strip.cuh) goes further and never
+// materialises J for those rows.
 #pragma once
 #include "gemm_f64.cuh"
 
@@ -110,6 +112,66 @@ __global__ void __launch_bounds__(LR_THREADS) jn_lowrank_kernel(const LowRankPar
         }
       }
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Closed-form factors of the molecular operands (no SVD anywhere on the product path).
+//
+// Summed over the two half rings the azimuth integrand of the Rayleigh builder is a polynomial in cos^2(Theta):
+//   f(cc + x) + f(cc - x),  cc = mu_m mu_n,  x = sqrt((1 - mu_m^2)(1 - mu_n^2)) cos(phi)
+//   = 0.75 (2 + 2 mu_m^2 mu_n^2 + 2 (1 - mu_m^2)(1 - mu_n^2) cos^2(phi))
+// so every column of P -- and every ROW k of the contraction operand A[k][m] = w_k/4 P[m][N-1-k], whatever the
+// per-column normalisation did -- is affine in mu_m^2:   A[k][m] = alpha_k + beta_k mu_m^2   (isotropic: beta = 0).
+// The factors are read off two columns of the operand itself (mu^2 = 1 and mu = 0):
+//   Vt = [1; mu^2],  Ut = [alpha; beta],  alpha_k = A[k][M-1],  beta_k = A[k][0] - A[k][M-1]
+// and the caller enables the low-rank path only if the residual max|A - Ut^T Vt| / max|A| returned here is at rounding
+// level.  Any operand with that structure qualifies, whichever builder made it; everything else stays dense.
+// ---------------------------------------------------------------------------------------------
+__global__ void lowrank_mu2_fit_kernel(const double* __restrict__ A, int lda, int N, int M, const double* __restrict__ mu,
+                                       double* __restrict__ Ut, double* __restrict__ Vt, int ldr, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ldr) return;
+  for (int r = 2; r < rows; ++r) { Ut[static_cast<size_t>(r) * ldr + i] = 0.0; Vt[static_cast<size_t>(r) * ldr + i] = 0.0; }
+  if (i < N) {
+    const double a0 = A[static_cast<size_t>(i) * lda + (M - 1)];   // mu = 0-
+    const double a1 = A[static_cast<size_t>(i) * lda];             // mu = -1
+    const double q0 = mu[M - 1] * mu[M - 1], q1 = mu[0] * mu[0];   // (0 and 1 on the reference grid; kept general)
+    const double beta = (a1 - a0) / (q1 - q0);
+    Ut[i] = a0 - beta * q0;
+    Ut[ldr + i] = beta;
+    Vt[i] = 1.0;
+    Vt[ldr + i] = mu[i] * mu[i];
+  } else {
+    Ut[i] = Ut[ldr + i] = Vt[i] = Vt[ldr + i] = 0.0;
+  }
+}
+
+// stats[0] = max|A - Ut^T Vt|, stats[1] = max|A|, stats[2] = max|beta| (bit patterns of non-negative doubles: atomicMax on u64)
+__global__ void lowrank_mu2_residual_kernel(const double* __restrict__ A, int lda, int N, const double* __restrict__ Ut,
+                                            const double* __restrict__ Vt, int ldr, unsigned long long* stats) {
+  const int k = blockIdx.y;
+  double res = 0.0, amax = 0.0;
+  const double al = Ut[k], be = Ut[ldr + k];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < N; m += gridDim.x * blockDim.x) {
+    const double a = A[static_cast<size_t>(k) * lda + m];
+    const double fit = fma(be, Vt[ldr + m], al * Vt[m]);
+    const double d = fabs(a - fit);
+    res = (d > res || isnan(d)) ? d : res;
+    amax = fmax(amax, fabs(a));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double r2 = __shfl_xor_sync(0xffffffffu, res, o);
+    res = (r2 > res || isnan(r2)) ? r2 : res;
+    amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (isnan(res)) res = INFINITY;
+    atomicMax(&stats[0], static_cast<unsigned long long>(__double_as_longlong(res)));
+    atomicMax(&stats[1], static_cast<unsigned long long>(__double_as_longlong(amax)));
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&stats[2], static_cast<unsigned long long>(__double_as_longlong(fabs(be))));
   }
 }
 

@@ -17,6 +17,7 @@
 #include "phase.cuh"
 #include "quadrature.cuh"
 #include "sweep.cuh"
+#include "strip.cuh"
 
 namespace {
 
@@ -96,6 +97,7 @@ int encode_3d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, 
 struct sos_plan {
   sos_grid grid;
   GridDev dev;
+  int device = 0;  // ordinal the plan lives on: every entry point switches to it (DeviceGuard)
   int N;
   int n_sms;
   long long launches;
@@ -132,6 +134,7 @@ struct sos_plan {
   bool fold = false;
   sosgemm::FoldParams fp;
   unsigned long long* d_fold_stats = nullptr;
+  unsigned long long* d_lr_stats = nullptr;  // residual / max|A| / max|beta| of sos_build_lowrank_mu2
   std::vector<const double*> F_ptrs;
   // premixed aerosol operands (one per scenario) and the tile-plan tables that go with them
   int fold_ksplit = 1;     // 2: split k for launches with few tiles (single solves), see FoldParams
@@ -148,6 +151,22 @@ struct sos_plan {
   int lowrank_ldr = 0;
   int n_lowrank_groups = 0;
   int lowrank_rp = 4;
+  // fused single-pass order kernel (strip.cuh): used by sos_solve for batches
+  bool strip_ok = false;        // the plan qualifies (batch size, zone inside one strip, ...)
+  bool strip_disabled = false;  // a blend left the strip zone at run time: chunked kernels from now on
+  int strip_nstrips = 0, strip_nslots = 0, strip_nsc = 0, strip_Lp = 0, strip_grid = 0;
+  double* d_tau_pad = nullptr;
+  int* d_k0tab = nullptr;
+  double* d_dhist = nullptr;
+  double* d_proj[2] = {nullptr, nullptr};
+  double* d_ratio_part = nullptr;
+  double* d_lam_part = nullptr;
+  unsigned* d_lam_flag = nullptr;
+  int* d_strip_ticket = nullptr;
+  const double** d_Ut_tab = nullptr;
+  int* d_rank_tab = nullptr;
+  unsigned strip_epoch = 0;
+  std::map<const void*, CUtensorMap> map3_cache;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -157,16 +176,29 @@ struct sos_plan {
 
 namespace {
 
+// makes the plan's device current for the duration of an entry point (callers may have another one current)
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int want) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != want) switched = cudaSetDevice(want) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define SOS_GUARD(p) DeviceGuard _guard((p)->device)
+
 void pool_setup() {
-  static bool done = false;
-  if (done) return;
+  static bool done[64] = {false};
   int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
   cudaMemPool_t pool;
-  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     unsigned long long keep = ~0ULL;  // keep freed blocks cached instead of returning them to the OS
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  done = true;
+  done[dev] = true;
 }
 
 // pinned poll buffers are recycled across plans (cudaMallocHost is slow)
@@ -259,9 +291,124 @@ int plan_tiles(sos_plan* p, cudaStream_t st) {
   return launch_check(p);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused single-pass order kernel (strip.cuh): plan-side tables
+// ---------------------------------------------------------------------------------------------
+constexpr int kStripR = 8;
+
+int strip_env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return (e && *e) ? std::atoi(e) : dflt;
+}
+
+// Decide whether the plan qualifies for the strip kernel and build its tables.  Not qualifying is not an error.
+int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_scenario* scen_h) {
+  using namespace sosstrip;
+  const GridDev& g = p->dev;
+  const int L = g.L, M = g.M, S = g.S;
+  p->strip_ok = false;
+  if (strip_env_int("SOS_B200_STRIP", 1) == 0) return SOS_OK;
+  const int nstrips = (M + W - 1) / W;
+  if (nstrips > MAX_STRIPS) return SOS_OK;
+  // enough strips to fill the chip without cutting the layer axis (smaller batches keep the chunked scan)
+  if (static_cast<long long>(S) * nstrips < strip_env_int("SOS_B200_STRIP_MIN", 48)) return SOS_OK;
+  const int nsc = (M - 1) - g.first_small;
+  if (nsc > MAX_SMALL) return SOS_OK;
+  // strip 0 must hold every column the reference treats specially next to mu = 0-
+  int wmax = 0;
+  for (int s = 0; s < S; ++s)
+    for (int k = 0; k < g.nreg; ++k) wmax = std::max(wmax, scen_h[s].extrap_width[k]);
+  const int ns = (wmax <= 0) ? 0 : (wmax < 2 ? 2 : std::min(5, wmax));
+  const int zl = std::max(0, std::min(g.first_small, M - wmax - ns));
+  if (M - zl > W - 2 || M < 8) return SOS_OK;
+  // windows: first row k0 of tau' >= tau_t - 5|mu| inside the region, with the reference's rounding (two operations)
+  const int Lp = ((L + kStripR - 1) / kStripR * kStripR + 1) / 2 * 2;
+  std::vector<double> tau_pad(static_cast<size_t>(S) * Lp);
+  std::vector<int> k0tab(static_cast<size_t>(S) * L * std::max(nsc, 1), 0);
+  for (int s = 0; s < S; ++s) {
+    const double* tau = tau_h + static_cast<size_t>(s) * L;
+    for (int t = 0; t < Lp; ++t) tau_pad[static_cast<size_t>(s) * Lp + t] = tau[std::min(t, L - 1)];
+    for (int c = 0; c < nsc; ++c) {
+      const double amu = std::fabs(mu_h[g.first_small + c]);
+      const volatile double five_mu = 5.0 * amu;
+      for (int k = 0; k < g.nreg; ++k) {
+        int k0 = g.rstart[k];
+        for (int t = g.rstart[k]; t < g.rstart[k + 1]; ++t) {
+          const volatile double lim = tau[t] - five_mu;
+          while (k0 < t && tau[k0] < lim) ++k0;
+          k0tab[(static_cast<size_t>(s) * L + t) * nsc + c] = k0;
+        }
+      }
+    }
+  }
+  int r;
+  if ((r = dev_upload(p, const_cast<const double**>(&p->d_tau_pad), tau_pad.data(), tau_pad.size()))) return r;
+  if ((r = dev_upload(p, const_cast<const int**>(&p->d_k0tab), k0tab.data(), k0tab.size()))) return r;
+  const int nslots = 2 * nstrips;
+  if ((r = dev_alloc(p, &p->d_dhist, static_cast<size_t>(S) * L * MAX_SMALL))) return r;
+  for (int i = 0; i < 2; ++i)
+    if ((r = dev_alloc(p, &p->d_proj[i], static_cast<size_t>(S) * L * nslots * 2))) return r;
+  if ((r = dev_alloc(p, &p->d_ratio_part, static_cast<size_t>(S) * nstrips * 2))) return r;
+  if ((r = dev_alloc(p, &p->d_lam_part, static_cast<size_t>(S) * nstrips))) return r;
+  if ((r = dev_alloc(p, &p->d_lam_flag, static_cast<size_t>(S) * nstrips))) return r;
+  if ((r = dev_alloc(p, &p->d_strip_ticket, 1))) return r;
+  if ((r = dev_alloc(p, &p->d_Ut_tab, SOS_MAX_PHASE))) return r;
+  if ((r = dev_alloc(p, &p->d_rank_tab, SOS_MAX_PHASE))) return r;
+  SOS_CUDA(cudaMemset(p->d_lam_flag, 0, sizeof(unsigned) * S * nstrips));
+  SOS_CUDA(cudaMemset(p->d_strip_ticket, 0, sizeof(int)));
+  SOS_CUDA(cudaMemset(p->d_dhist, 0, sizeof(double) * S * L * MAX_SMALL));
+  SOS_CUDA(cudaMemset(p->d_rank_tab, 0, sizeof(int) * SOS_MAX_PHASE));
+  p->strip_nstrips = nstrips;
+  p->strip_nslots = nslots;
+  p->strip_nsc = nsc;
+  p->strip_Lp = Lp;
+  p->strip_ok = true;
+  return SOS_OK;
+}
+
+template <int NS>
+int strip_launch_cfg(sos_plan* p, const sosstrip::StripParams& sp, cudaStream_t st) {
+  using namespace sosstrip;
+  const int smem = strip_smem_bytes<kStripR, NS>(sp.nslots);
+  static int configured_smem[64] = {0};  // per device: function attributes belong to the device's context
+  int& have = configured_smem[p->device & 63];
+  if (smem > have) {
+    if (cudaFuncSetAttribute(order_strip_kernel<kStripR, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      g_last_cuda_error = "strip kernel: shared memory request refused";
+      return SOS_ERR_CUDA;
+    }
+    have = smem;
+  }
+  if (p->strip_grid == 0) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, order_strip_kernel<kStripR, NS>, THREADS, smem);
+    p->strip_grid = std::max(1, occ) * p->n_sms;
+  }
+  const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(p->dev.S) * sp.nstrips, p->strip_grid));
+  order_strip_kernel<kStripR, NS><<<std::max(grid, sp.nstrips), THREADS, smem, st>>>(sp);
+  return launch_check(p);
+}
+
+// 3-D tensor map [S][L][N] of a field for the strip kernel
+int strip_field_map(sos_plan* p, const void* base, CUtensorMap* out) {
+  auto it = p->map3_cache.find(base);
+  if (it == p->map3_cache.end()) {
+    CUtensorMap m;
+    const GridDev& g = p->dev;
+    int r = encode_3d(&m, base, g.N, g.L, g.S, g.ld, sosstrip::W, kStripR);
+    if (r) return r;
+    if (p->map3_cache.size() > 64) p->map3_cache.clear();
+    it = p->map3_cache.emplace(base, m).first;
+  }
+  *out = it->second;
+  return SOS_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+static bool strip_generates(const sos_plan* p);
 
 int sos_abi_version(void) { return SOS_ABI_VERSION; }
 
@@ -273,6 +420,7 @@ const char* sos_strerror(int err) {
     case SOS_ERR_NOMEM: return "out of device memory";
     case SOS_ERR_UNSUPPORTED: return "unsupported device or configuration";
     case SOS_ERR_STATE: return "call order violated";
+    case SOS_ERR_RETRY: return "solve must be repeated: the plan switched to its general kernels";
     default: return "unknown error";
   }
 }
@@ -322,6 +470,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   sos_plan* p = new (std::nothrow) sos_plan();
   if (!p) return SOS_ERR_NOMEM;
   p->grid = *grid;
+  p->device = dev;
   p->N = N;
   p->n_sms = n_sms;
   p->launches = 0;
@@ -348,7 +497,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     // enough (scenario x chunk x column) threads to fill the chip
     const long long want = 4LL * p->n_sms * 2048;
     long long c = static_cast<long long>(S) * L * N / want;
-    // measured (tools/chunk_sweep.sh): 48-row chunks are the sweet spot for small batches -- shorter chunks
+    // measured in round 1 (sweep over chunk_rows with tools/bench_kernels.py): 48-row chunks are the sweet spot for small batches -- shorter chunks
     // lengthen the serial carry chain more than they help the two scan passes
     chunk = static_cast<int>(std::max<long long>(48, std::min<long long>(128, c)));
     chunk = std::max(chunk, (L + 47) / 48);  // keep the serial carry chain short
@@ -419,6 +568,12 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     d.state = const_cast<ScenState*>(tmp);
   }
   TRY(dev_alloc(p, &d.n_active, 1));
+  TRY(dev_alloc(p, &d.active_flat, static_cast<size_t>(S)));
+  {
+    std::vector<int> ids(S);
+    for (int s = 0; s < S; ++s) ids[s] = s;
+    if (cudaMemcpy(d.active_flat, ids.data(), sizeof(int) * S, cudaMemcpyHostToDevice) != cudaSuccess) { sos_plan_destroy(p); return SOS_ERR_CUDA; }
+  }
   {
     cudaError_t e = cudaMemcpy(d.n_active, &S, sizeof(int), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { sos_plan_destroy(p); return SOS_ERR_CUDA; }
@@ -456,7 +611,11 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
           sc.coef_mix_aer = sc.coef_mix_atm;
         }
       }
-      SOS_CUDA(cudaMemcpy(const_cast<sos_scenario*>(d.scen), patched.data(), sizeof(sos_scenario) * S, cudaMemcpyHostToDevice));
+      if (cudaMemcpy(const_cast<sos_scenario*>(d.scen), patched.data(), sizeof(sos_scenario) * S, cudaMemcpyHostToDevice) != cudaSuccess) {
+        g_last_cuda_error = "cudaMemcpy(scenarios) failed";
+        sos_plan_destroy(p);
+        return SOS_ERR_CUDA;
+      }
       p->scen_h = patched;
     }
     // groups: class 1 (two operands) first, then class 0
@@ -514,7 +673,15 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     TRY(dev_alloc(p, &p->d_work_counter, 1));
     TRY(dev_alloc(p, &p->d_order, 1));
     TRY(dev_alloc(p, &p->d_fold_stats, 2));
-    { const int one = 1; SOS_CUDA(cudaMemcpy(p->d_order, &one, sizeof(int), cudaMemcpyHostToDevice)); }
+    TRY(dev_alloc(p, &p->d_lr_stats, 3));
+    {
+      const int one = 1;
+      if (cudaMemcpy(p->d_order, &one, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+        g_last_cuda_error = "cudaMemcpy(order counter) failed";
+        sos_plan_destroy(p);
+        return SOS_ERR_CUDA;
+      }
+    }
     p->gemm_bm = sosgemm::Cfg<2, 4, 4, 4>::BM;
     {
       // 128 x 144 tiles (12 consumer warps of 32 x 48) when 144 pads N less than 128 (N = 1002: 1008 vs 1024
@@ -546,7 +713,10 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   }
   if ((N + 32) * sizeof(double) > 48 * 1024) {
     cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
-
+  }
+  {
+    int r3 = strip_setup(p, mu_h, tau_h, p->scen_h.data());
+    if (r3) { sos_plan_destroy(p); return r3; }
   }
   *out = p;
   return SOS_OK;
@@ -554,6 +724,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
 
 int sos_plan_destroy(sos_plan* p) {
   if (!p) return SOS_OK;
+  SOS_GUARD(p);  // the sync and the stream-ordered frees below must run on the plan's own device
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   cudaDeviceSynchronize();  // nothing of this plan may still be running on any stream
   for (void* a : p->allocs) cudaFreeAsync(a, nullptr);
@@ -564,8 +735,20 @@ int sos_plan_destroy(sos_plan* p) {
 
 long long sos_launch_count(const sos_plan* p) { return p ? p->launches : 0; }
 
+int sos_plan_query(const sos_plan* p, int what) {
+  if (!p) return SOS_ERR_INVALID;
+  switch (what) {
+    case SOS_QUERY_FUSED_ORDER: return (p->strip_ok && !p->strip_disabled && p->dev.col0 == 0 && p->dev.col1 == p->dev.N) ? 1 : 0;
+    case SOS_QUERY_GENERATED_SOURCE: return (p->strip_ok && !p->strip_disabled && strip_generates(p)) ? 1 : 0;
+    case SOS_QUERY_FOLDED: return p->fold ? 1 : 0;
+    case SOS_QUERY_DEVICE: return p->device;
+    default: return SOS_ERR_INVALID;
+  }
+}
+
 int sos_plan_set_columns(sos_plan* p, int col0, int col1) {
   if (!p) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   GridDev& g = p->dev;
   if (col0 < 0 || col1 > g.N || col0 >= col1) return SOS_ERR_INVALID;
   if (col0 == 0 && col1 == g.N) { g.col0 = 0; g.col1 = g.N; return SOS_OK; }
@@ -587,18 +770,21 @@ int sos_plan_set_columns(sos_plan* p, int col0, int col1) {
 
 int sos_state_ratios(sos_plan* p, double* buf_d, int set, void* stream) {
   if (!p || !buf_d) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   sossweep::ratios_kernel<<<(p->dev.S + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, buf_d, set);
   return launch_check(p);
 }
 
 int sos_set_profiling(sos_plan* p, int enabled) {
   if (!p) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   p->profiling = enabled != 0;
   return SOS_OK;
 }
 
 int sos_get_profile(sos_plan* p, double* ms, long long* spans, void* stream) {
   if (!p || !ms || !spans) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   SOS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   ms[0] = ms[1] = 0.0;
   spans[0] = spans[1] = 0;
@@ -615,6 +801,7 @@ int sos_get_profile(sos_plan* p, double* ms, long long* spans, void* stream) {
 
 int sos_build_contraction(sos_plan* p, const double* P_d, int ldp, double* A_d, int lda, void* stream) {
   if (!p || !P_d || !A_d || ldp < p->N || lda < p->N) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   const int N = p->N;
   dim3 grid((N + 31) / 32, (N + 31) / 32);
   sosquad::build_contraction_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P_d, ldp, A_d, lda, N, p->dev.wmu);
@@ -625,6 +812,7 @@ int sos_build_phase(sos_plan* p, int family, double g, double mu0, const double*
                     const double* tab_x_d, const double* tab_y_d, int tab_n, double* P_d, int ldp, double* P0_d,
                     void* stream) {
   if (!p || !phi_h || !cphi_h || (!P_d && !P0_d)) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   if (family < 0 || family > 2 || (family == 2 && (!tab_x_d || !tab_y_d || tab_n < 2))) return SOS_ERR_INVALID;
   if (P_d && ldp < p->N) return SOS_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -663,6 +851,7 @@ static int encode_A_maps(sos_plan* p) {
 
 int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
   if (!p || !A_d || n < 1 || n > SOS_MAX_PHASE || lda < p->N || (lda & 1)) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   for (const sos_scenario& sc : p->scen_h)
     if (sc.phase_atm >= n || sc.phase_aer >= n) return SOS_ERR_INVALID;
   for (int i = 0; i < n; ++i)
@@ -693,6 +882,7 @@ int sos_fold_layout(int nb_angles, int* rows, int* ld) {
 
 int sos_build_folded(sos_plan* p, const double* A_d, int lda, double* F_d, int ldf, double* defect_out, void* stream) {
   if (!p || !A_d || !F_d || !defect_out || lda < p->N) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   int rows = 0, ld = 0;
   sos_fold_layout(p->dev.M, &rows, &ld);
   if (ldf != ld) return SOS_ERR_INVALID;
@@ -776,7 +966,8 @@ static int refresh_fold_plan(sos_plan* p) {
     // single solves: fewer tiles than half the SMs and long k loops -> two tiles per output tile
     const char* e = std::getenv("SOS_FOLD_KSPLIT");
     const bool allow = !(e && e[0] == '0');
-    p->fold_ksplit = (allow && 2 * tiles <= p->n_sms && p->dev.M >= 64) ? 2 : 1;
+    // (never together with split operand passes: four atomic partials per element would not be order independent)
+    p->fold_ksplit = (allow && !p->split_passes && 2 * tiles <= p->n_sms && p->dev.M >= 64) ? 2 : 1;
   }
   r = plan_tiles(p, nullptr);
   if (r) return r;
@@ -784,8 +975,41 @@ static int refresh_fold_plan(sos_plan* p) {
   return SOS_OK;
 }
 
+int sos_lowrank_layout(int nb_angles, int* rows, int* ldr) {
+  if (rows) *rows = 4;                                // rank <= 2 here; jn_lowrank_kernel<4> takes 4 factor rows
+  if (ldr) *ldr = (2 * nb_angles + 15) / 16 * 16;
+  return 4 * ((2 * nb_angles + 15) / 16 * 16);
+}
+
+int sos_build_lowrank_mu2(sos_plan* p, const double* A_d, int lda, double* Ut_d, double* Vt_d, int ldr, double* residual_out,
+                          int* rank_out, void* stream) {
+  if (!p || !A_d || !Ut_d || !Vt_d || !residual_out || !rank_out || lda < p->N || ldr < p->N) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = p->N, M = p->dev.M;
+  SOS_CUDA(cudaMemsetAsync(p->d_lr_stats, 0, 3 * sizeof(unsigned long long), st));
+  sosgemm::lowrank_mu2_fit_kernel<<<(ldr + 127) / 128, 128, 0, st>>>(A_d, lda, N, M, p->dev.mu, Ut_d, Vt_d, ldr, 4);
+  int r = launch_check(p);
+  if (r) return r;
+  dim3 grid(static_cast<unsigned>(std::min(8, (N + 255) / 256)), N);
+  sosgemm::lowrank_mu2_residual_kernel<<<grid, 256, 0, st>>>(A_d, lda, N, Ut_d, Vt_d, ldr, p->d_lr_stats);
+  r = launch_check(p);
+  if (r) return r;
+  unsigned long long bits[3] = {0, 0, 0};
+  SOS_CUDA(cudaMemcpyAsync(bits, p->d_lr_stats, sizeof(bits), cudaMemcpyDeviceToHost, st));
+  SOS_CUDA(cudaStreamSynchronize(st));
+  double res, amax, bmax;
+  std::memcpy(&res, &bits[0], 8);
+  std::memcpy(&amax, &bits[1], 8);
+  std::memcpy(&bmax, &bits[2], 8);
+  *residual_out = amax > 0.0 ? res / amax : (res > 0.0 ? INFINITY : 0.0);
+  *rank_out = (bmax <= 1e-15 * amax) ? 1 : 2;   // isotropic operand: beta vanishes
+  return SOS_OK;
+}
+
 int sos_plan_set_lowrank(sos_plan* p, const double* const* Ut_d, const double* const* Vt_d, const int* rank, int n, int ldr) {
   if (!p) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   if (n == 0) {
     for (int i = 0; i < SOS_MAX_PHASE; ++i) p->lowrank_rank[i] = 0;
   } else {
@@ -806,6 +1030,7 @@ int sos_plan_set_lowrank(sos_plan* p, const double* const* Ut_d, const double* c
 
 int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   if (!p) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   if (n == 0 || !F_d) {
     const bool replan = p->fold;
     p->fold = false;
@@ -867,6 +1092,7 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
 
 int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) {
   if (!p || !C_h || !I1_d) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GridDev& g = p->dev;
   SOS_CUDA(cudaMemcpyAsync(p->d_C, C_h, sizeof(double) * g.S * 2 * g.N, cudaMemcpyHostToDevice, st));
@@ -882,7 +1108,7 @@ int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) 
 }
 
 static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_begin, int seg_end, void* stream,
-                       const double* const* peers = nullptr, int n_peers = 0, const int* peer_col = nullptr);
+                       const double* const* peers = nullptr, int n_peers = 0, const int* peer_col = nullptr, bool skip_lowrank = false);
 
 int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
   return source_impl(p, In1_d, J_d, 0, 0x7fffffff, stream);
@@ -890,6 +1116,7 @@ int sos_source(sos_plan* p, const double* In1_d, double* J_d, void* stream) {
 
 int sos_source_rows(sos_plan* p, const double* In1_d, double* J_d, int row0, int row1, void* stream) {
   if (!p) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   // row-chunked contraction: single scenario, single region (the mu-sharded large grid), 64-row granularity
   if (p->dev.S != 1 || p->dev.nreg != 1) return SOS_ERR_UNSUPPORTED;
   if (row0 < 0 || row1 > p->dev.L || row0 >= row1 || (row0 % p->gemm_bm) != 0) return SOS_ERR_INVALID;
@@ -900,6 +1127,7 @@ int sos_source_rows(sos_plan* p, const double* In1_d, double* J_d, int row0, int
 
 int sos_source_peers(sos_plan* p, const double* const* In1_peers_d, int n_peers, const int* peer_col, double* J_d, void* stream) {
   if (!p || !In1_peers_d || !peer_col || n_peers < 1 || n_peers > SOS_MAX_PEERS) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   if (peer_col[0] != 0 || peer_col[n_peers] != p->dev.N) return SOS_ERR_INVALID;
   for (int r = 0; r < n_peers; ++r)
     if (!In1_peers_d[r] || peer_col[r + 1] <= peer_col[r] || (peer_col[r] % sosgemm::BK) != 0) return SOS_ERR_INVALID;
@@ -941,8 +1169,9 @@ int sos_copy_d2d(void* dst_d, const void* src_d, size_t bytes, void* stream) {
 }
 
 static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_begin, int seg_end, void* stream,
-                       const double* const* peers, int n_peers, const int* peer_col) {
+                       const double* const* peers, int n_peers, const int* peer_col, bool skip_lowrank) {
   if (!p || !In1_d || !J_d) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   if (!p->maps_A_ready) return SOS_ERR_STATE;
   if ((reinterpret_cast<uintptr_t>(In1_d) & 15) || (reinterpret_cast<uintptr_t>(J_d) & 15)) return SOS_ERR_INVALID;
   const GridDev& g = p->dev;
@@ -1016,7 +1245,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
     f.J = J_d;
     f.scen = g.scen;
-    if (p->n_lowrank_groups > 0) {
+    if (p->n_lowrank_groups > 0 && !skip_lowrank) {  // (skipped inside sos_solve when the strip kernel rebuilds J for those rows)
       // rows whose operand is low rank (Rayleigh / isotropic): two skinny products, HBM bound (gemm_lowrank.cuh)
       sosgemm::LowRankParams lr;
       lr.I = In1_d; lr.J = J_d;
@@ -1081,12 +1310,14 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
 
 int sos_sweeps(sos_plan* p, const double* J_d, double* In_d, double* I_d, void* stream) {
   if (!p || !J_d || !In_d) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   return sweeps_impl(p, J_d, In_d, I_d, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int sos_converge(sos_plan* p, int order, void* stream) {
   if (!p) return SOS_ERR_INVALID;
-  sossweep::converge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, order, p->d_order);
+  SOS_GUARD(p);
+  sossweep::converge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, order, p->d_order, nullptr, 0, p->d_strip_ticket);
   int r = launch_check(p);
   if (r) return r;
   return plan_tiles(p, static_cast<cudaStream_t>(stream));
@@ -1094,11 +1325,12 @@ int sos_converge(sos_plan* p, int order, void* stream) {
 
 int sos_reset(sos_plan* p, const double* I1_d, void* stream) {
   if (!p || !I1_d) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   sossweep::reset_kernel<<<p->dev.S, 256, 0, st>>>(p->dev, I1_d, p->d_order);
   int r = launch_check(p);
   if (r) return r;
-  sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev);
+  sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev, p->d_strip_ticket);
   r = launch_check(p);
   if (r) return r;
   return plan_tiles(p, st);
@@ -1106,6 +1338,7 @@ int sos_reset(sos_plan* p, const double* I1_d, void* stream) {
 
 int sos_get_results(sos_plan* p, sos_result* results_h, void* stream) {
   if (!p || !results_h) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   std::vector<ScenState> tmp(p->dev.S);
   SOS_CUDA(cudaMemcpyAsync(tmp.data(), p->dev.state, sizeof(ScenState) * p->dev.S, cudaMemcpyDeviceToHost, st));
@@ -1121,9 +1354,68 @@ int sos_get_results(sos_plan* p, sos_result* results_h, void* stream) {
   return SOS_OK;
 }
 
+// can this solve run on the fused strip kernel, and with generated J?
+static bool strip_usable(const sos_plan* p) {
+  const GridDev& g = p->dev;
+  return p->strip_ok && !p->strip_disabled && g.col0 == 0 && g.col1 == g.N;
+}
+static bool strip_generates(const sos_plan* p) {
+  // the molecular rows leave the contraction only in fold mode (class-3 groups of the tile plan) and only with the
+  // closed-form rank <= 2 factors; otherwise every J row is read from memory
+  if (!p->fold || p->n_lowrank_groups == 0) return false;
+  for (int i = 0; i < SOS_MAX_PHASE; ++i)
+    if (p->lowrank_rank[i] > 2) return false;
+  return true;
+}
+
+// one order on the strip kernel: J (dense rows) / projections of I_{n-1} (generated rows) -> I_n, I, projections of I_n
+static int strip_order(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, int n, bool gen, cudaStream_t st) {
+  using namespace sosstrip;
+  StripParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.g = p->dev;
+  int r;
+  if ((r = strip_field_map(p, J_d, &sp.map_J))) return r;
+  if ((r = strip_field_map(p, In_d, &sp.map_In))) return r;
+  if ((r = strip_field_map(p, I_d, &sp.map_I))) return r;
+  sp.map_S = sp.map_I;
+  if (saved_d && (r = strip_field_map(p, saved_d, &sp.map_S))) return r;
+  sp.tau_pad = p->d_tau_pad;
+  sp.Lp = p->strip_Lp;
+  sp.active = p->dev.active_flat;
+  sp.ticket = p->d_strip_ticket;
+  sp.nstrips = p->strip_nstrips;
+  sp.nslots = p->strip_nslots;
+  sp.has_saved = saved_d ? 1 : 0;
+  sp.store_all = strip_env_int("SOS_B200_STRIP_STORE_ALL", 0);
+  for (int i = 0; i < SOS_MAX_PHASE; ++i) {
+    sp.rank[i] = gen ? p->lowrank_rank[i] : 0;
+    sp.Ut[i] = p->lowrank_Ut[i];
+    sp.Vt[i] = p->lowrank_Vt[i];
+  }
+  sp.ldr = p->lowrank_ldr;
+  sp.proj_in = p->d_proj[n & 1];
+  sp.proj_out = p->d_proj[(n + 1) & 1];
+  sp.ratio_part = p->d_ratio_part;
+  sp.lam_part = p->d_lam_part;
+  sp.lam_flag = p->d_lam_flag;
+  sp.epoch = ++p->strip_epoch;
+  sp.dhist = p->d_dhist;
+  sp.k0tab = p->d_k0tab;
+  sp.nsc = p->strip_nsc;
+  ProfSpan span(p, 1, st);
+  switch (strip_env_int("SOS_B200_STRIP_STAGES", 4)) {
+    case 3: return strip_launch_cfg<3>(p, sp, st);
+    case 5: return strip_launch_cfg<5>(p, sp, st);
+    case 6: return strip_launch_cfg<6>(p, sp, st);
+    default: return strip_launch_cfg<4>(p, sp, st);
+  }
+}
+
 int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* orders_d, int max_saved, int max_orders,
               int poll_every, sos_result* results_h, void* stream) {
   if (!p || !I_d || !In_d || !J_d) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   if (!p->maps_A_ready) return SOS_ERR_STATE;
   if (poll_every < 1) poll_every = 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1131,6 +1423,20 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
   int r = sos_reset(p, I_d, stream);
   if (r) return r;
   const size_t field = static_cast<size_t>(g.S) * g.L * g.ld;
+  const bool strip = strip_usable(p);
+  const bool gen = strip && strip_generates(p);
+  if (gen) {
+    // projections of the first order onto the molecular factors: what order 2 rebuilds its J from
+    const double* ut[SOS_MAX_PHASE];
+    for (int i = 0; i < SOS_MAX_PHASE; ++i) ut[i] = p->lowrank_Ut[i];
+    SOS_CUDA(cudaMemcpyAsync(p->d_Ut_tab, ut, sizeof(ut), cudaMemcpyHostToDevice, st));
+    SOS_CUDA(cudaMemcpyAsync(p->d_rank_tab, p->lowrank_rank, sizeof(int) * SOS_MAX_PHASE, cudaMemcpyHostToDevice, st));
+    SOS_CUDA(cudaStreamSynchronize(st));  // (ut lives on this stack frame)
+    dim3 pg((g.L + 7) / 8, g.S);
+    sosstrip::strip_project_kernel<<<pg, 256, 0, st>>>(g, In_d, p->d_Ut_tab, p->d_rank_tab, p->lowrank_ldr, p->strip_nslots, p->d_proj[0]);
+    r = launch_check(p);
+    if (r) return r;
+  }
   // The host never blocks inside the loop: after every order the device-side "still active" counter
   // is copied to a pinned slot; the host looks at the newest slot that has already landed.  Kernels
   // of converged scenarios exit immediately, so the few orders enqueued past convergence cost only
@@ -1143,12 +1449,21 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
   bool done = false;
   int next_check = 0;  // slot index next to be examined
   for (int n = 2; n <= max_orders && !done; ++n) {
-    rc = sos_source(p, In_d, J_d, stream);
+    rc = source_impl(p, In_d, J_d, 0, 0x7fffffff, stream, nullptr, 0, nullptr, gen);
     if (rc) break;
     double* saved = (orders_d && n - 2 < max_saved) ? orders_d + static_cast<size_t>(n - 2) * field : nullptr;
-    rc = sweeps_impl(p, J_d, In_d, I_d, saved, st);
-    if (rc) break;
-    rc = sos_converge(p, n, stream);
+    if (strip) {
+      rc = strip_order(p, J_d, In_d, I_d, saved, n, gen, st);
+      if (rc) break;
+      sossweep::converge_kernel<<<1, 256, 0, st>>>(p->dev, n, p->d_order, p->d_ratio_part, p->strip_nstrips, p->d_strip_ticket);
+      rc = launch_check(p);
+      if (rc) break;
+      rc = plan_tiles(p, st);
+    } else {
+      rc = sweeps_impl(p, J_d, In_d, I_d, saved, st);
+      if (rc) break;
+      rc = sos_converge(p, n, stream);
+    }
     if (rc) break;
     const int slot = issued % nslots;
     if (issued >= nslots) poll[slot] = -1;  // that copy finished long ago (run-ahead is bounded below)
@@ -1168,13 +1483,29 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
     }
   }
   if (rc) return rc;
-  if (results_h) return sos_get_results(p, results_h, stream);
+  if (strip) {
+    // a blend that left strip 0's columns cannot be finished by the fused kernel: switch this plan to the chunked
+    // kernels and ask the caller to run the solve again (I_d / In_d have been consumed)
+    std::vector<sos_result> tmp(g.S);
+    rc = sos_get_results(p, tmp.data(), stream);
+    if (rc) return rc;
+    for (int s = 0; s < g.S; ++s)
+      if (tmp[s].status & SOS_STATUS_STRIP_FALLBACK) { p->strip_disabled = true; return SOS_ERR_RETRY; }
+  }
+  if (results_h) {
+    rc = sos_get_results(p, results_h, stream);
+    if (rc) return rc;
+    // the loop stopped at max_orders with these scenarios still above threshold: say so (the reference's while would go on)
+    for (int s = 0; s < g.S; ++s)
+      if (results_h[s].active) results_h[s].status |= SOS_STATUS_MAX_ORDERS;
+  }
   return SOS_OK;
 }
 
 int sos_quadratures(sos_plan* p, const double* I_d, double direct_scale, const double* z_h, double* flux_up_d,
                     double* flux_down_d, double* net_flux_d, double* diffusivity_d, double* heating_d, void* stream) {
   if (!p || !I_d) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
   if (heating_d && (!z_h || p->dev.nreg != 3)) return SOS_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GridDev& g = p->dev;

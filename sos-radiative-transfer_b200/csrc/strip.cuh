@@ -1,0 +1,626 @@
+// One scattering order in ONE pass over memory: the layer sweeps of In_NumInt (SOS_Aer_I1_In.py:77-130; inlined
+// three-region form SOS_Aer_main_specular.py:327-449, Lambert surface SOS_Aer_main_lambertian.py:399,401), the
+// accumulation I += I_n (:454-456), the convergence ratios (:309) and -- for rows whose contraction operand is the
+// rank <= 2 molecular one (gemm_lowrank.cuh) -- the source function itself (:315-323), fused.
+//
+// sweep.cuh evaluates the exp(-dtau/|mu|) recurrence as a chunked scan (local aggregates, carry chain, apply, zone
+// fix-up: four launches, J read twice, 40 B per element).  For a BATCH of scenarios there is enough parallelism
+// without cutting the layer axis, so here one CTA owns a "strip": 128 downward columns of one scenario AND their 128
+// mirror columns, and streams through all L rows twice with the running D / U in registers --
+//   * down pass (rows 0 .. L-1), thread j <-> column d = M-1-(128 k + j): no carries, no look-back;
+//   * the specular coupling is thread-local: the mirror column u = N-1-d belongs to the same thread, so the seed
+//     rho * I_n[L-1, d] never leaves the register file (Lambert: one partial sum per strip, exchanged through L2);
+//   * up pass (rows L-1 .. 0) on the mirror block, re-seeded from the blended boundary rows;
+//   * strip 0 holds every column the reference treats specially next to mu = 0 (windowed / Taylor columns,
+//     extrapolation targets and sources, the find-first blend): they are finished in shared memory before the tile
+//     is written, so no second kernel touches the fields.
+// Row tiles ([R rows][128 columns] of J and of I) arrive by TMA (3-D tensor maps [S][L][N]: out-of-range rows and
+// columns are zero-filled on load and clipped on store, so ragged L, M need no special code) into an NS-stage
+// mbarrier ring; the finished I_n and I tiles leave by TMA bulk stores from the same buffers.  Algorithmic traffic
+// when J is read: J 8 + I_n 8 + I 16 = 32 B per element -- the minimum.
+//
+// Generated source.  On rows that use the molecular operand alone (every row outside the aerosol layer,
+// SOS_Aer_main_specular.py:323), A = Us Vt with Vt = [1; mu^2] (gemm_lowrank.cuh), so
+//     J[t, m] = coef * (c0[t] + c1[t] mu_m^2),   c_r[t] = sum_k I_{n-1}[t, k] Us[k][r]
+// and the two numbers c_r[t] per row are all the next order needs from this one.  The kernel therefore emits, for
+// every finished row, the partial projections of its own 128 columns (one slot per strip and half, summed by the
+// readers in slot order: deterministic) and REBUILDS J from them in the next order instead of reading it: neither J
+// nor I_n is ever written for those rows.  Per element and order that leaves the I read-modify-write, 16 B, on 746 of
+// the 800 default rows; the dense (aerosol) rows keep the 32 B path and the DMMA contraction.
+//
+// Windowed columns (|mu| < 0.01, SOS_Aer_In_limit.py:96-107: trapezoid over tau' >= tau_t - 5|mu| inside the region).
+// With D the same recurrence restarted at the region's first row, the window integral is
+//     D_t - exp((tau_t - tau_k0)/mu) D_k0,      k0 = first row of the window,
+// (the intervals above k0, decayed to t, cancel exactly), so the column costs one recurrence step, one exp and one
+// look-up per row instead of a fresh sum over up to 5|mu|/dtau rows.  k0 depends only on tau and mu and is tabulated
+// on the host with the reference's own rounding (tau_t - 5*abs(mu) as two operations); D_k0 is fetched from a small
+// history array one stage ahead of its use.
+#pragma once
+#include "common.cuh"
+#include "gemm_f64.cuh"
+#include "sweep.cuh"
+
+namespace sosstrip {
+
+using sosgemm::mbar_expect_tx;
+using sosgemm::mbar_init;
+using sosgemm::mbar_wait;
+using sosgemm::smem_u32;
+using sossweep::exp_small;
+
+constexpr int W = 128;          // columns per strip half = threads per CTA
+constexpr int THREADS = 128;
+constexpr int MAX_SMALL = 16;   // windowed / Taylor columns (|mu| < 0.01, without mu = 0-) a plan may have
+constexpr int MAX_STRIPS = 16;  // M <= 2048
+
+struct StripParams {
+  GridDev g;
+  CUtensorMap map_J, map_In, map_I, map_S;  // [S][L][N] (strides ld, L*ld), box {W, R, 1}
+  const double* tau_pad;                    // [S][Lp]: tau with rows padded to whole stages (last value repeated)
+  int Lp;
+  const int* active;                        // compacted ids of the scenarios still iterating ([*g.n_active])
+  int* ticket;                              // work counter, zeroed before the launch
+  int nstrips, nslots;                      // strips per scenario; projection slots per row = 2 * nstrips
+  int has_saved;                            // also store I_n into map_S (I_saved of SOS_Aer_main_specular.py:458)
+  int store_all;                            // store I_n on every row (otherwise only where the next contraction is dense)
+  const double* Ut[SOS_MAX_PHASE];          // low-rank factors of the operands ([4][ldr], gemm_lowrank.cuh); rank 0 = dense
+  const double* Vt[SOS_MAX_PHASE];
+  int rank[SOS_MAX_PHASE];
+  int ldr;
+  const double* proj_in;                    // [S][L][nslots][2] projections of I_{n-1} (read when J is generated)
+  double* proj_out;                         //                    ... of I_n
+  double* ratio_part;                       // [S][nstrips][2] {TOA, surface} ratio maxima of each strip
+  double* lam_part;                         // [S][nstrips] Lambert partial sums
+  unsigned* lam_flag;                       // [S][nstrips] epoch stamps of lam_part
+  unsigned epoch;                           // unique per launch
+  double* dhist;                            // [S][L][MAX_SMALL] region-restarted D of the windowed columns
+  const int* k0tab;                         // [S][L][nsc] first row of every window (host-built)
+  int nsc;                                  // small columns first_small .. M-2
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int R>
+struct StageLayout {
+  // [J / I_n tile][I tile][projections of the stage's rows][tau of the stage's rows]
+  static constexpr int TILE = R * W * 8;
+  __host__ __device__ static int bytes(int nslots) { return (2 * TILE + R * nslots * 16 + R * 8 + 127) / 128 * 128; }
+};
+template <int R, int NS>
+__host__ __device__ inline int strip_smem_bytes(int nslots) { return NS * StageLayout<R>::bytes(nslots) + 128; }
+
+__device__ __forceinline__ int region_of(const GridDev& g, int t) {
+  int k = 0;
+  while (k + 1 < g.nreg && t >= g.rstart[k + 1]) ++k;
+  return k;
+}
+
+enum ColKind { K_INVALID = 0, K_STD = 1, K_M1 = 2, K_TAYLOR = 3, K_WINDOW = 4 };
+
+template <int R, int NS>
+__global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_constant__ StripParams p) {
+  static_assert(R * MAX_SMALL <= THREADS && 2 * R <= THREADS && (R % 2) == 0, "stage shape");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full_bar[NS];
+  __shared__ int s_ticket;
+  __shared__ int s_istar;
+  __shared__ double s_cj[R][2];
+  __shared__ double s_lkv[R][MAX_SMALL];
+  __shared__ int s_lkk[R][MAX_SMALL];
+  __shared__ double s_dh[R][MAX_SMALL];
+  __shared__ double s_row[W];
+  __shared__ double s_red[8];
+
+  const GridDev& g = p.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = g.L, M = g.M, N = g.N;
+  const int nslots = p.nslots;
+  const int stage_bytes = StageLayout<R>::bytes(nslots);
+  const int total = *g.n_active * p.nstrips;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) mbar_init(&full_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t seq = 0;  // stages consumed by this CTA so far (ring position and mbarrier phase)
+  const int nst = (L + R - 1) / R, nseq = 2 * nst;
+
+  for (;;) {
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
+    __syncthreads();
+    const int tk = s_ticket;
+    __syncthreads();
+    if (tk >= total) break;
+    const int ai = tk / p.nstrips, k = tk - ai * p.nstrips;
+    const int s = p.active[ai];
+    const sos_scenario sc = g.scen[s];
+    const double* __restrict__ tau_g = g.tau + static_cast<size_t>(s) * L;
+    const int op = sc.phase_atm;
+    const int rk = p.rank[op];                        // 0: J is read from memory on every row
+    const int a0 = (g.nreg == 3) ? g.rstart[1] : L;   // rows [a0, a1) keep the dense contraction (aerosol layer)
+    const int a1 = (g.nreg == 3) ? g.rstart[2] : L;
+    const int dcol0 = M - W * (k + 1), ucol0 = M + W * k;
+    const int d = M - 1 - (W * k + tid), u = ucol0 + tid;
+    const bool vd = d >= 0, vu = u < N;
+    const double mud = vd ? g.mu[d] : -1.0, muu = vu ? g.mu[u] : 1.0;
+    const double imud = 1.0 / mud, imuu = 1.0 / muu;
+    double vd0 = 0.0, vd1 = 0.0, vu0 = 0.0, vu1 = 0.0;
+    if (rk > 0) {
+      const double* __restrict__ Vt = p.Vt[op];
+      if (vd) { vd0 = Vt[d]; vd1 = Vt[p.ldr + d]; }
+      if (vu) { vu0 = Vt[u]; vu1 = Vt[p.ldr + u]; }
+    }
+    int kd = K_INVALID;
+    if (vd) kd = (d == M - 1) ? K_M1 : (fabs(mud) >= SOS_MU_THRESHOLD ? K_STD : (fabs(mud) < SOS_MU_VERY_SMALL ? K_TAYLOR : K_WINDOW));
+    const int csm = d - g.first_small;                // index among the small columns (valid for K_TAYLOR / K_WINDOW)
+    int wmaxs = 0;
+    for (int r = 0; r < g.nreg; ++r) wmaxs = max(wmaxs, sc.extrap_width[r]);
+
+    const uint32_t seq0 = seq;
+    auto stage_ptr = [&](uint32_t gq) { return smem + static_cast<size_t>(gq % NS) * stage_bytes; };
+    auto issue = [&](int q2) {  // thread 0: start the loads of sequence step q2 of this work item
+      const bool down2 = q2 < nst;
+      const int st2 = down2 ? q2 : nseq - 1 - q2;
+      const int t02 = st2 * R, rows2 = min(R, L - t02);
+      const uint32_t gq2 = seq0 + q2;
+      uint8_t* sp = stage_ptr(gq2);
+      uint64_t* bar = &full_bar[gq2 % NS];
+      const bool dense2 = rk == 0 || (t02 < a1 && t02 + rows2 > a0);
+      const bool gen2 = rk > 0 && (t02 < a0 || t02 + rows2 > a1);
+      const uint32_t bytes = StageLayout<R>::TILE + (dense2 ? StageLayout<R>::TILE : 0) + (gen2 ? rows2 * nslots * 16 : 0) + R * 8;
+      mbar_expect_tx(bar, bytes);
+      const int c0 = down2 ? dcol0 : ucol0;
+      tma_load_3d(smem_u32(sp + StageLayout<R>::TILE), &p.map_I, bar, c0, t02, s);
+      if (dense2) tma_load_3d(smem_u32(sp), &p.map_J, bar, c0, t02, s);
+      if (gen2)
+        bulk_load_1d(smem_u32(sp + 2 * StageLayout<R>::TILE), p.proj_in + (static_cast<size_t>(s) * L + t02) * nslots * 2,
+                     rows2 * nslots * 16, bar);
+      bulk_load_1d(smem_u32(sp + 2 * StageLayout<R>::TILE + R * nslots * 16), p.tau_pad + static_cast<size_t>(s) * p.Lp + t02, R * 8, bar);
+    };
+    if (tid == 0) {
+      bulk_wait_read<0>();  // the previous work item's stores have left the ring
+      for (int q2 = 0; q2 < NS - 1 && q2 < nseq; ++q2) issue(q2);
+    }
+
+    if (k == 0 && p.nsc > 0 && tid < min(R, L) * p.nsc) {  // windows of the first stage start inside it
+      const int r = tid / p.nsc, c = tid - r * p.nsc;
+      s_lkk[r][c] = p.k0tab[(static_cast<size_t>(s) * L + r) * p.nsc + c];
+      s_lkv[r][c] = 0.0;
+    }
+    __syncthreads();
+
+    // running state of the two recurrences
+    double D = 0.0, Jp = 0.0, tp = tau_g[0];
+    double Dr = 0.0;                    // region-restarted recurrence of a windowed column
+    int regd = 0, r0d = 0;              // region of the down pass (slow path)
+    double U = 0.0, Jn = 0.0, tn = tau_g[L - 1];
+    double lastJ = 0.0;                 // J[t, mu = 0+] of the row just finished (thread 0 of strip 0)
+    double seed_src = 0.0;
+
+    for (int q = 0; q < nseq; ++q) {
+      const bool down = q < nst;
+      const int st = down ? q : nseq - 1 - q;
+      const int t0 = st * R, rows = min(R, L - t0);
+      const uint32_t gq = seq0 + q;
+      uint8_t* sp = stage_ptr(gq);
+      double* __restrict__ Jt = reinterpret_cast<double*>(sp);
+      double* __restrict__ It = reinterpret_cast<double*>(sp + StageLayout<R>::TILE);
+      const double* __restrict__ pr = reinterpret_cast<const double*>(sp + 2 * StageLayout<R>::TILE);
+      const double* __restrict__ ta = reinterpret_cast<const double*>(sp + 2 * StageLayout<R>::TILE + R * nslots * 16);
+      const bool hasdense = rk == 0 || (t0 < a1 && t0 + rows > a0);
+      const bool hasgen = rk > 0 && (t0 < a0 || t0 + rows > a1);
+      mbar_wait(&full_bar[gq % NS], (gq / NS) & 1);
+
+      if (hasgen) {
+        // c_r[t] = coef * sum over slots of the partial projections (fixed order)
+        if (tid < 2 * R) {
+          const int r = tid >> 1, c = tid & 1;
+          double sum = 0.0;
+          if (r < rows)
+            for (int j = 0; j < nslots; ++j) sum += pr[(r * nslots + j) * 2 + c];
+          s_cj[r][c] = sc.coef_atm * sum;
+        }
+        __syncthreads();
+      }
+
+      if (down) {
+        const int ci = W - 1 - tid;
+        if (kd == K_STD || kd == K_INVALID) {
+          if (kd == K_STD) {
+            double tcv[R], jv[R], iv[R], av[R], bv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const int t = t0 + r;
+              tcv[r] = ta[r];
+              const bool gen = rk > 0 && (t < a0 || t >= a1);
+              jv[r] = gen ? fma(s_cj[r][1], vd1, s_cj[r][0] * vd0) : Jt[r * W + ci];
+              iv[r] = It[r * W + ci];
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const double dt = tcv[r] - (r ? tcv[r - 1] : tp);
+              av[r] = exp_small(dt * imud);
+              bv[r] = (dt * 0.5) * ((r ? jv[r - 1] : Jp) * av[r] + jv[r]) * imud;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (r < rows) {
+                D = (t0 + r == 0) ? 0.0 : D * av[r] - bv[r];
+                Jt[r * W + ci] = D;
+                It[r * W + ci] = iv[r] + D;
+                Jp = jv[r];
+                tp = tcv[r];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) Jt[r * W + ci] = 0.0;
+          }
+        } else {
+          // the few special columns next to mu = 0- (strip 0 only)
+          for (int r = 0; r < rows; ++r) {
+            const int t = t0 + r;
+            const double tc = ta[r];
+            while (regd + 1 < g.nreg && t >= g.rstart[regd + 1]) { ++regd; r0d = g.rstart[regd]; }
+            const bool gen = rk > 0 && (t < a0 || t >= a1);
+            const double jt = gen ? fma(s_cj[r][1], vd1, s_cj[r][0] * vd0) : Jt[r * W + ci];
+            const double io = It[r * W + ci];
+            const bool target = (M - 1 - d) < sc.extrap_width[regd];
+            double val;
+            if (kd == K_M1) {
+              val = 0.0;  // extrapolation target, or 0 when nothing is extrapolated
+            } else if (kd == K_TAYLOR) {  // -J + mu dJ/dtau (SOS_Aer_In_limit.py:79-93)
+              const double slope = (t > r0d) ? (jt - Jp) / (tc - tp) : 0.0;
+              val = -jt + mud * slope;
+            } else {
+              if (t == r0d) Dr = 0.0;
+              else {
+                const double dt = tc - tp;
+                const double a = exp_small(dt * imud);
+                Dr = Dr * a - (dt * 0.5) * (Jp * a + jt) * imud;
+              }
+              s_dh[r][csm] = Dr;
+              p.dhist[(static_cast<size_t>(s) * L + t) * MAX_SMALL + csm] = Dr;
+              const int k0 = s_lkk[r][csm];
+              const double Dk = (k0 >= t0) ? s_dh[k0 - t0][csm] : s_lkv[r][csm];
+              val = Dr - exp((tc - tau_g[k0]) / mud) * Dk;
+              if (!isfinite(val)) val = -jt;  // (:104-105)
+            }
+            Jt[r * W + ci] = val;
+            if (kd != K_M1 && !target) It[r * W + ci] = io + val;
+            Jp = jt;
+            tp = tc;
+          }
+        }
+      } else {
+        // ---------------- up pass ----------------
+        bool special = false;  // the stage holds a gap row (first row above a region boundary): generic path, CTA-uniform
+        if (g.nreg == 3) special = (g.rstart[1] - 1 >= t0 && g.rstart[1] - 1 < t0 + rows) || (g.rstart[2] - 1 >= t0 && g.rstart[2] - 1 < t0 + rows);
+        const bool mu0p = (k == 0 && tid == 0);  // column M: I_n = J (SOS_Aer_I1_In.py:100)
+        if (!special && vu && !mu0p) {
+          double tcv[R], jv[R], iv[R], av[R], bv[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int t = t0 + r;
+            tcv[r] = ta[r];
+            const bool gen = rk > 0 && (t < a0 || t >= a1);
+            jv[r] = gen ? fma(s_cj[r][1], vu1, s_cj[r][0] * vu0) : Jt[r * W + tid];
+            iv[r] = It[r * W + tid];
+          }
+          {
+            double tnx = tn, jnx = Jn;
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+              if (r < rows) {
+                const double dt = tnx - tcv[r];
+                av[r] = exp_small(-dt * imuu);
+                bv[r] = (dt * 0.5) * (jv[r] + jnx * av[r]) * imuu;
+                tnx = tcv[r];
+                jnx = jv[r];
+              }
+            }
+          }
+#pragma unroll
+          for (int r = R - 1; r >= 0; --r) {
+            if (r < rows) {
+              U = (t0 + r == L - 1) ? U : U * av[r] + bv[r];  // surface row: zero-length integral, the seed itself
+              Jt[r * W + tid] = U;
+              It[r * W + tid] = iv[r] + U;
+              Jn = jv[r];
+              tn = tcv[r];
+            }
+          }
+        } else {
+          for (int r = rows - 1; r >= 0; --r) {
+            const int t = t0 + r;
+            const double tc = ta[r];
+            const bool gen = rk > 0 && (t < a0 || t >= a1);
+            const double jt = gen ? fma(s_cj[r][1], vu1, s_cj[r][0] * vu0) : Jt[r * W + tid];
+            const double io = It[r * W + tid];
+            double val;
+            if (special && (t + 1 == g.rstart[1] || t + 1 == g.rstart[2])) {
+              // U holds the raw value at the carry row t+1: it is read after its blend ...
+              if (k == 0) {
+                s_row[tid] = mu0p ? lastJ : U;
+                __syncthreads();
+                if (warp == 0) {
+                  const int lim = min(W, N - M);
+                  int istar = -1;
+                  for (int base = 1; base + 2 <= lim - 1 && istar < 0; base += 32) {
+                    const int i = base + lane;
+                    bool hit = false;
+                    if (i + 2 <= lim - 1) {
+                      const double x = s_row[i], y = s_row[i + 1], z = s_row[i + 2];
+                      hit = !(fabs((x - y) - (y - z)) > SOS_BLEND_THRESHOLD);
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                    if (mask) istar = base + __ffs(mask) - 1 + 1;
+                  }
+                  if (lane == 0) {
+                    s_istar = istar;
+                    if (istar < 0) atomicOr(&g.state[s].status, (N - M <= W) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
+                  }
+                }
+                __syncthreads();
+                const int istar = s_istar;
+                if (istar > 0 && tid > 0 && tid < istar) {
+                  const double w = muu / g.mu[M + istar];
+                  U = (1.0 - w) * s_row[0] + w * s_row[istar];
+                }
+                __syncthreads();  // s_row is reused at the next boundary
+              }
+              // ... then crosses the gap with pure attenuation (SOS_Aer_main_specular.py:413,433)
+              U = U * exp(-(tn - tc) / muu);
+              val = U;
+            } else if (t == L - 1) {
+              val = U;
+            } else {
+              const double dt = tn - tc;
+              const double a = exp_small(-dt * imuu);
+              U = U * a + (dt * 0.5) * (jt + Jn * a) * imuu;
+              val = U;
+            }
+            if (mu0p) { val = jt; lastJ = jt; }
+            if (!vu) val = 0.0;
+            Jt[r * W + tid] = val;
+            if (vu) It[r * W + tid] = io + val;
+            Jn = jt;
+            tn = tc;
+          }
+        }
+      }
+      __syncthreads();
+
+      // ---------------- look-ups of the next down stage's windows (their D_k0 land while this stage is finished) -----------
+      double lk_val = 0.0;
+      int lk_k0 = 0, lk_r = -1, lk_c = 0;
+      if (down && k == 0 && p.nsc > 0 && q + 1 < nst) {
+        const int t0n = t0 + R, rowsn = min(R, L - t0n);
+        if (tid < rowsn * p.nsc) {
+          lk_r = tid / p.nsc;
+          lk_c = tid - lk_r * p.nsc;
+          lk_k0 = p.k0tab[(static_cast<size_t>(s) * L + t0n + lk_r) * p.nsc + lk_c];
+          if (lk_k0 < t0n) lk_val = p.dhist[(static_cast<size_t>(s) * L + lk_k0) * MAX_SMALL + lk_c];
+        }
+      }
+
+      // ---------------- strip 0: finish the columns next to mu = 0 in shared memory ----------------
+      if (k == 0) {
+        if (down) {
+          if (wmaxs > 0) {
+            for (int e = tid; e < rows * wmaxs; e += THREADS) {
+              const int r = e / wmaxs, i = e - r * wmaxs;
+              const int reg = region_of(g, t0 + r);
+              const int idxw = sc.extrap_width[reg];
+              if (i >= idxw) continue;
+              const int wc = sossweep::width_class(g, idxw);
+              const int ns = g.wns[wc];
+              const int src0 = (idxw < 2) ? (M - idxw - 2) : (M - idxw - ns);
+              const double* __restrict__ Wm = g.W + g.woff[wc];
+              double v = 0.0;
+              for (int j = 0; j < ns; ++j) v += Wm[i * ns + j] * Jt[r * W + (src0 + j - dcol0)];
+              const int m = M - 1 - i, idx = W - 1 - i;
+              const bool stdc = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
+              const double raw = Jt[r * W + idx];
+              Jt[r * W + idx] = v;
+              It[r * W + idx] += stdc ? (v - raw) : v;  // standard targets were accumulated raw
+            }
+          }
+        } else {
+          const int lim = min(W, N - M);
+          for (int r = warp; r < rows; r += THREADS / 32) {
+            double* row = Jt + r * W;
+            const double v0 = row[0];
+            int istar = -1;
+            for (int base = 1; base + 2 <= lim - 1 && istar < 0; base += 32) {
+              const int i = base + lane;
+              bool hit = false;
+              if (i + 2 <= lim - 1) {
+                const double x = row[i], y = row[i + 1], z = row[i + 2];
+                hit = !(fabs((x - y) - (y - z)) > SOS_BLEND_THRESHOLD);
+              }
+              const unsigned mask = __ballot_sync(0xffffffffu, hit);
+              if (mask) istar = base + __ffs(mask) - 1 + 1;
+            }
+            if (istar < 0) {
+              if (lane == 0) atomicOr(&g.state[s].status, (N - M <= W) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
+            } else {
+              const double v1 = row[istar];
+              const double mus = g.mu[M + istar];
+              __syncwarp();
+              for (int i = 1 + lane; i < istar; i += 32) {
+                const double w = g.mu[M + i] / mus;
+                const double val = (1.0 - w) * v0 + w * v1;
+                const double old = row[i];
+                row[i] = val;
+                It[r * W + i] += val - old;
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+
+      // ---------------- rows are final: surface seeds, convergence ratios, projections ----------------
+      const bool last_down = down && st == nst - 1;
+      const bool toa_up = !down && st == 0;
+      if (last_down || toa_up) {
+        const int r = last_down ? (L - 1 - t0) : 0;
+        const int ci = last_down ? (W - 1 - tid) : tid;
+        const bool valid = last_down ? vd : vu;
+        const double val = Jt[r * W + ci];
+        double rmax = -INFINITY;
+        bool nonfinite = false;
+        if (valid) {
+          const double ratio = val / It[r * W + ci];
+          if (isnan(ratio)) nonfinite = true; else rmax = ratio;
+        }
+        double lam = 0.0;
+        if (last_down) {
+          seed_src = valid ? val : 0.0;
+          if (g.surface == SOS_SURFACE_LAMBERT && vd && d <= M - 2) {
+            // -2 rho trapz(I mu, mu) over columns M-2 .. 0 as a weighted sum (SOS_Aer_main_lambertian.py:399,401)
+            double wgt = 0.0;
+            if (d >= 1) wgt += (g.mu[d - 1] - g.mu[d]) * 0.5;
+            if (d + 1 <= M - 2) wgt += (g.mu[d] - g.mu[d + 1]) * 0.5;
+            lam = wgt * val * mud;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+          lam += __shfl_xor_sync(0xffffffffu, lam, o);
+        }
+        nonfinite = __any_sync(0xffffffffu, nonfinite);
+        if (lane == 0) { s_red[warp] = rmax; s_red[4 + warp] = lam; }
+        if (nonfinite && lane == 0) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);
+        __syncthreads();
+        if (tid == 0) {
+          const double rm = fmax(fmax(s_red[0], s_red[1]), fmax(s_red[2], s_red[3]));
+          if (rm == INFINITY) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);
+          p.ratio_part[(static_cast<size_t>(s) * p.nstrips + k) * 2 + (last_down ? 1 : 0)] = rm;
+        }
+        if (last_down) {
+          if (g.surface == SOS_SURFACE_SPECULAR) {
+            U = sc.grd_alb * seed_src;
+          } else if (g.surface == SOS_SURFACE_LAMBERT) {
+            if (tid == 0) {
+              p.lam_part[static_cast<size_t>(s) * p.nstrips + k] = (s_red[4] + s_red[5]) + (s_red[6] + s_red[7]);
+              __threadfence();
+              atomicExch(&p.lam_flag[static_cast<size_t>(s) * p.nstrips + k], p.epoch);
+              // every strip of the scenario holds a neighbouring ticket, so its CTA is running (or done)
+              double totl = 0.0;
+              for (int kk = 0; kk < p.nstrips; ++kk) {
+                volatile unsigned* fl = p.lam_flag + static_cast<size_t>(s) * p.nstrips + kk;
+                while (*fl != p.epoch) __nanosleep(64);
+                __threadfence();
+                totl += *reinterpret_cast<volatile double*>(p.lam_part + static_cast<size_t>(s) * p.nstrips + kk);
+              }
+              s_red[0] = -2.0 * sc.grd_alb * totl;
+            }
+            __syncthreads();
+            U = s_red[0];
+          } else {
+            U = 0.0;
+          }
+        }
+        __syncthreads();
+      }
+
+      if (rk > 0) {
+        const double* __restrict__ Ut = p.Ut[op];
+        const int c00 = down ? dcol0 : ucol0;
+        for (int r = warp; r < rows; r += THREADS / 32) {
+          double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < W / 32; ++qq) {
+            const int c = lane + 32 * qq;
+            const int col = c00 + c;
+            if (col >= 0 && col < N) {
+              const double x = Jt[r * W + c];
+              p0 = fma(x, Ut[col], p0);
+              p1 = fma(x, Ut[p.ldr + col], p1);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          }
+          if (lane == 0) {
+            double2* dst = reinterpret_cast<double2*>(p.proj_out + ((static_cast<size_t>(s) * L + t0 + r) * nslots + 2 * k + (down ? 0 : 1)) * 2);
+            *dst = make_double2(p0, p1);
+          }
+        }
+      }
+      if (lk_r >= 0) { s_lkv[lk_r][lk_c] = lk_val; s_lkk[lk_r][lk_c] = lk_k0; }
+
+      // ---------------- write the finished tiles, refill the ring ----------------
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const int c0 = down ? dcol0 : ucol0;
+        if (hasdense || p.store_all) tma_store_3d(&p.map_In, smem_u32(Jt), c0, t0, s);
+        tma_store_3d(&p.map_I, smem_u32(It), c0, t0, s);
+        if (p.has_saved) tma_store_3d(&p.map_S, smem_u32(Jt), c0, t0, s);
+        bulk_commit();
+        if (q + NS - 1 < nseq) {
+          bulk_wait_read<1>();  // the stores of the previous step have read their buffer: it is the one refilled now
+          issue(q + NS - 1);
+        }
+      }
+    }
+    seq += nseq;
+  }
+  if (tid == 0) bulk_wait_read<0>();
+}
+
+// Projections of a whole field (the first order, before the loop): proj[s][t][0][r] = sum_k I[t, k] Us[k][r], other slots 0.
+__global__ void __launch_bounds__(256) strip_project_kernel(const GridDev g, const double* __restrict__ I, const double* const* Ut_tab,
+                                                            const int* rank_tab, int ldr, int nslots, double* __restrict__ proj) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.y, t = blockIdx.x * 8 + warp;
+  if (t >= g.L) return;
+  const int op = g.scen[s].phase_atm;
+  double* dst = proj + (static_cast<size_t>(s) * g.L + t) * nslots * 2;
+  if (rank_tab[op] == 0) return;
+  const double* __restrict__ Ut = Ut_tab[op];
+  const double* __restrict__ row = I + (static_cast<size_t>(s) * g.L + t) * g.ld;
+  double p0 = 0.0, p1 = 0.0;
+  for (int m = lane; m < g.N; m += 32) {
+    const double x = row[m];
+    p0 = fma(x, Ut[m], p0);
+    p1 = fma(x, Ut[ldr + m], p1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+  }
+  for (int j = lane; j < nslots * 2; j += 32) dst[j] = (j == 0) ? p0 : (j == 1 ? p1 : 0.0);
+}
+
+}  // namespace sosstrip

@@ -693,30 +693,53 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
 // ------------------------------------------------------------------------------------------
 // convergence bookkeeping
 // ------------------------------------------------------------------------------------------
-__global__ void converge_kernel(const GridDev g, int order_arg, int* order_counter) {
-  __shared__ int cnt;
+// ascending list of the active scenarios (warp 0 of a one-CTA kernel; deterministic)
+__device__ __forceinline__ void build_active_list(const GridDev& g) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  int base = 0;
+  for (int s0 = 0; s0 < g.S; s0 += 32) {
+    const int s = s0 + lane;
+    const bool act = s < g.S && g.state[s].active;
+    const unsigned mask = __ballot_sync(0xffffffffu, act);
+    if (act) g.active_flat[base + __popc(mask & ((1u << lane) - 1u))] = s;
+    base += __popc(mask);
+  }
+  if (lane == 0) *g.n_active = base;
+}
+
+// ratio_part != nullptr: the fused order kernel left one {TOA, surface} maximum per strip; reduce them first
+__global__ void converge_kernel(const GridDev g, int order_arg, int* order_counter, const double* __restrict__ ratio_part,
+                                int nstrips, int* strip_ticket) {
   __shared__ int order_s;
   if (threadIdx.x == 0) {
-    cnt = 0;
     // order_arg < 0: take the order number from the device-side counter (CUDA-graph replays cannot
     // change kernel arguments); the counter always tracks the last order handled
     order_s = order_arg >= 0 ? order_arg : *order_counter + 1;
     *order_counter = order_s;
+    if (strip_ticket) *strip_ticket = 0;
   }
   __syncthreads();
   const int order = order_s;
-  int mine = 0;
   for (int s = threadIdx.x; s < g.S; s += blockDim.x) {
     ScenState& st = g.state[s];
     if (st.active) {
+      if (ratio_part) {
+        double r0 = -INFINITY, r1 = -INFINITY;
+        for (int k = 0; k < nstrips; ++k) {
+          r0 = fmax(r0, ratio_part[(static_cast<size_t>(s) * nstrips + k) * 2]);
+          r1 = fmax(r1, ratio_part[(static_cast<size_t>(s) * nstrips + k) * 2 + 1]);
+        }
+        st.ratio_toa = r0;
+        st.ratio_surf = r1;
+      }
       st.n_orders = order;
       const double r = fmax(st.ratio_toa, st.ratio_surf);
-      if (!(r >= g.scen[s].threshold)) st.active = 0; else ++mine;
+      if (!(r >= g.scen[s].threshold)) st.active = 0;
     }
   }
-  atomicAdd(&cnt, mine);
   __syncthreads();
-  if (threadIdx.x == 0) *g.n_active = cnt;
+  build_active_list(g);
 }
 
 // ratios with I_n := 1 (the reference initialises In = ones before the loop, :306-309)
@@ -761,15 +784,9 @@ __global__ void ratios_kernel(const GridDev g, double* buf, int set) {
   else { buf[2 * s] = g.state[s].ratio_toa; buf[2 * s + 1] = g.state[s].ratio_surf; }
 }
 
-__global__ void count_active_kernel(const GridDev g) {
-  __shared__ int cnt;
-  if (threadIdx.x == 0) cnt = 0;
-  __syncthreads();
-  int mine = 0;
-  for (int s = threadIdx.x; s < g.S; s += blockDim.x) mine += g.state[s].active ? 1 : 0;
-  atomicAdd(&cnt, mine);
-  __syncthreads();
-  if (threadIdx.x == 0) *g.n_active = cnt;
+__global__ void count_active_kernel(const GridDev g, int* strip_ticket) {
+  if (threadIdx.x == 0 && strip_ticket) *strip_ticket = 0;
+  build_active_list(g);
 }
 
 }  // namespace sossweep

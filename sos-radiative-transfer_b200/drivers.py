@@ -187,7 +187,11 @@ class BatchSolver:
         mo = max_orders if max_orders is not None else max(s.max_orders for s in self.scenarios)
         # the first order is recomputed by every solve, so its buffer can serve as the loop's I_n field -- unless the caller
         # wants the per-order fields back (results() then reads I1 as order 1)
-        return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every, consume_I1=(keep_orders == 0))
+        try:
+            return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every, consume_I1=(keep_orders == 0))
+        except _lib.SosRetry:   # (see SosEngine.solve) -- the first order was consumed: rebuild it, the plan has switched kernels
+            I1 = self.first_order()
+            return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every, consume_I1=(keep_orders == 0))
 
     def results(self, res, quadratures=True, keep_orders=0, fields=True) -> List[DriverResult]:
         """Per-scenario results on the host.  fields=False skips the D2H copy of the radiance fields
@@ -317,7 +321,7 @@ def SOS_Aer_critical_albedo(tauStar_aer, dtau_aer, tauStar_atm, dtau_atm, P_aer,
 
 
 def critical_albedo_sweep(points: Sequence[Scenario], width: float = 0.1, forcing_tol: float = 1e-3, device=None,
-                          max_iter: int = 20):
+                          max_iter: int = 20, return_evaluated: bool = False):
     """Critical aerosol single-scattering albedo for many sweep points at once (config 5's real caller).
 
     For every point (a Scenario; its alb_aer is ignored) bisect omega_aer in [0, 1] on the radiative
@@ -325,7 +329,9 @@ def critical_albedo_sweep(points: Sequence[Scenario], width: float = 0.1, forcin
     baseline (documented deviation from SOS_Aer_critical_albedo.py:385-389, whose baseline repeats the
     same solve).  Stopping rule as in :397,402: interval width <= `width` or |dF| < `forcing_tol`.
     Every bisection step is ONE batched GPU solve over all still-open points.
-    Returns (omega_critical, forcing_at_omega, n_solves).
+    Returns (omega_critical, forcing, n_solves): `forcing[i]` is the forcing at the LAST omega solved for point i;
+    that omega is returned as a fourth array with return_evaluated=True (omega_critical is the same value when the sweep
+    stopped on |dF| < forcing_tol, otherwise the midpoint of the final bracket, at most width/2 away).
     """
     pts = list(points)
     base = solve_scenarios([replace(p, tauStar_aer=0.0, alb_aer=1.0) for p in pts], device=device)
@@ -353,4 +359,6 @@ def critical_albedo_sweep(points: Sequence[Scenario], width: float = 0.1, forcin
         hi[idx[~up & ~close]] = mid[~up & ~close]
     still = (hi - lo) <= width
     final = np.where(np.isnan(forcing) | (still & (np.abs(np.nan_to_num(forcing)) >= forcing_tol)), (hi + lo) / 2, omega)
+    if return_evaluated:
+        return final, forcing, n_solves, omega
     return final, forcing, n_solves

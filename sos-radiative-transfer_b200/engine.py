@@ -30,8 +30,7 @@ _OPERANDS = {}  # device-resident contraction operands shared between engines (s
 _FOLDED = {}    # their folded counterparts [B+ | B-] and centrosymmetry defects (sos_build_folded)
 FOLD_DEFECT_MAX = 1e-12  # fold only operands that are centrosymmetric to rounding (observed <= 3e-14 for every builder)
 _LOWRANK = {}   # low-rank factors (Ut, Vt, rank) of the operands, see SosEngine._lowrank_factors
-LOWRANK_TOL = 1e-13      # numerical rank = singular values above this fraction of the largest
-LOWRANK_MAX = 16         # sos_plan_set_lowrank takes ranks up to 16
+LOWRANK_RESIDUAL_MAX = 1e-14   # accept the closed-form factors only if max|A - Ut^T Vt| <= this * max|A| (observed ~2e-16)
 
 
 def _pinned_pair(elems: int):
@@ -61,8 +60,9 @@ class ScenarioCoefficients:
 class SolveResult:
     """What the order loop returns: accumulated field + per-scenario bookkeeping."""
 
-    def __init__(self, I, n_orders, ratio_toa, ratio_surf, status, orders=None):
+    def __init__(self, I, n_orders, ratio_toa, ratio_surf, status, orders=None, active=None):
         self.I = I
+        self.active = active      # 1 where the loop stopped at max_orders before the scenario converged (status bit MAX_ORDERS)
         self.n_orders = n_orders
         self.ratio_toa = ratio_toa
         self.ratio_surf = ratio_surf
@@ -122,7 +122,8 @@ class SosEngine:
     # ------------------------------------------------------------------ plumbing
     def close(self):
         if getattr(self, "_plan", None) is not None and self._plan.value:
-            self.lib.sos_plan_destroy(self._plan)
+            with torch.cuda.device(self.device):   # (the library also switches to the plan's device itself)
+                self.lib.sos_plan_destroy(self._plan)
             self._plan = C.c_void_p()
 
     def __del__(self):
@@ -184,6 +185,16 @@ class SosEngine:
                 out[pr0:pr1] = pbuf.numpy()
         a = out.reshape(self.S, self.L, self.N)
         return a[0] if self.S == 1 else a
+
+    @property
+    def strip_active(self) -> bool:
+        """True when sos_solve runs this plan on the fused single-pass order kernel (csrc/strip.cuh)."""
+        return bool(self.lib.sos_plan_query(self._plan, _lib.QUERY_FUSED_ORDER) == 1)
+
+    @property
+    def generated_source(self) -> bool:
+        """True when that kernel also rebuilds J on the molecular rows instead of reading it."""
+        return bool(self.lib.sos_plan_query(self._plan, _lib.QUERY_GENERATED_SOURCE) == 1)
 
     @property
     def launches(self) -> int:
@@ -262,26 +273,21 @@ class SosEngine:
             self.folded = True
 
     def _lowrank_factors(self, A: torch.Tensor):
-        """(Ut, Vt, rank) with A = (Ut^T)(Vt) to rounding, or (None, None, 0) when the numerical rank exceeds LOWRANK_MAX.
-        The Rayleigh operand of the reference is rank 2, the isotropic one rank 1 (csrc/gemm_lowrank.cuh)."""
-        N = self.N
-        A = A[:, :N]
-        # cheap screen first: the range of A seen through LOWRANK_MAX + 4 random directions
-        gen = torch.Generator(device="cpu").manual_seed(0)
-        probe = torch.randn((N, LOWRANK_MAX + 4), dtype=torch.float64, generator=gen).to(self.device)
-        sv = torch.linalg.svdvals(A @ probe)
-        if int((sv > LOWRANK_TOL * sv[0]).sum()) > LOWRANK_MAX:
+        """(Ut, Vt, rank) with A = (Ut^T)(Vt) to rounding, or (None, None, 0).
+
+        No SVD: every row of a Rayleigh / isotropic operand is affine in mu_m^2 (csrc/gemm_lowrank.cuh), so the factors are
+        read off two columns of the operand on the device (sos_build_lowrank_mu2) and accepted only when they reproduce the
+        dense operand to LOWRANK_RESIDUAL_MAX of its largest entry; every other operand stays dense."""
+        rows, ldr = C.c_int(), C.c_int()
+        self.lib.sos_lowrank_layout(self.M, C.byref(rows), C.byref(ldr))
+        Ut = torch.empty((rows.value, ldr.value), dtype=torch.float64, device=self.device)
+        Vt = torch.empty((rows.value, ldr.value), dtype=torch.float64, device=self.device)
+        resid, rank = C.c_double(), C.c_int()
+        _lib.check(self.lib.sos_build_lowrank_mu2(self._plan, A.data_ptr(), self.ld, Ut.data_ptr(), Vt.data_ptr(), ldr.value,
+                                                  C.byref(resid), C.byref(rank), self._stream), "sos_build_lowrank_mu2")
+        if not (resid.value <= LOWRANK_RESIDUAL_MAX):
             return None, None, 0
-        U, S, Vh = torch.linalg.svd(A)
-        r = int((S > LOWRANK_TOL * S[0]).sum())
-        if r == 0 or r > LOWRANK_MAX:
-            return None, None, 0
-        R = 4 if r <= 4 else 16
-        Ut = torch.zeros((R, self.ld), dtype=torch.float64, device=self.device)
-        Vt = torch.zeros((R, self.ld), dtype=torch.float64, device=self.device)
-        Ut[:r, :N] = (U[:, :r] * S[:r]).T
-        Vt[:r, :N] = Vh[:r, :]
-        return Ut, Vt, r
+        return Ut, Vt, int(rank.value)
 
     def _set_lowrank(self, cks):
         """Register the low-rank factors of the operands that have them (sos_plan_set_lowrank); SOS_B200_LOWRANK=0 skips it."""
@@ -293,10 +299,7 @@ class SosEngine:
         for i, (A, ck) in enumerate(zip(self._A, cks)):
             hit = _LOWRANK.get(ck) if ck is not None else None
             if hit is None:
-                try:
-                    hit = self._lowrank_factors(A)
-                except RuntimeError:   # a failing SVD must not break the solve: the operand simply stays dense
-                    hit = (None, None, 0)
+                hit = self._lowrank_factors(A)
                 if ck is not None:
                     if len(_LOWRANK) >= 32:
                         _LOWRANK.pop(next(iter(_LOWRANK)))
@@ -308,7 +311,8 @@ class SosEngine:
         ut = (C.c_void_p * n)(*[(h[0].data_ptr() if h[2] else None) for h in self._LR])
         vt = (C.c_void_p * n)(*[(h[1].data_ptr() if h[2] else None) for h in self._LR])
         rk = (C.c_int * n)(*self.lowrank)
-        _lib.check(self.lib.sos_plan_set_lowrank(self._plan, ut, vt, rk, n, self.ld), "sos_plan_set_lowrank")
+        ldr = next(h[0].shape[1] for h in self._LR if h[2])
+        _lib.check(self.lib.sos_plan_set_lowrank(self._plan, ut, vt, rk, n, ldr), "sos_plan_set_lowrank")
 
     def build_phase_matrix(self, name: str, g: float = 0.5, mu0: Optional[float] = None):
         """P(mu, mu') (and P0(mu, mu0) when mu0 is given) of an analytic family, built ON THE DEVICE
@@ -417,24 +421,34 @@ class SosEngine:
         """
         I = self._buf("I") if I is None else I
         J = self._buf("J") if J is None else J
-        I.copy_(I1)
-        if consume_I1 and In is None:
-            In = I1
-        else:
-            In = self._buf("In") if In is None else In
-            In.copy_(I1)
         orders = None
         optr = None
         if keep_orders > 0:
             orders = torch.zeros((keep_orders, self.S * self.L, self.ld), dtype=torch.float64, device=self.device)
             optr = orders.data_ptr()
         res = (_lib.sos_result * self.S)()
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.sos_solve(self._plan, I.data_ptr(), In.data_ptr(), J.data_ptr(), optr, keep_orders,
-                                          int(max_orders), int(poll_every), res, self._stream), "sos_solve")
+        In_arg = In
+        for attempt in (0, 1):
+            I.copy_(I1)
+            if consume_I1 and In_arg is None:
+                In = I1
+            else:
+                In = self._buf("In") if In_arg is None else In_arg
+                In.copy_(I1)
+            try:
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.sos_solve(self._plan, I.data_ptr(), In.data_ptr(), J.data_ptr(), optr, keep_orders,
+                                                  int(max_orders), int(poll_every), res, self._stream), "sos_solve")
+                break
+            except _lib.SosRetry:
+                # the fused order kernel met a blend wider than its zone; the plan now uses the chunked kernels.  With
+                # consume_I1 the first order is gone: the owner of I1 (BatchSolver.solve) recomputes it and calls again.
+                if attempt or (consume_I1 and In_arg is None):
+                    raise
         n = np.array([r.n_orders for r in res])
         return SolveResult(I, n, np.array([r.ratio_toa for r in res]), np.array([r.ratio_surf for r in res]),
-                           np.array([r.status for r in res], dtype=np.uint32), orders)
+                           np.array([r.status for r in res], dtype=np.uint32), orders,
+                           active=np.array([r.active for r in res], dtype=np.int32))
 
     def quadratures(self, I: torch.Tensor, z: Optional[np.ndarray] = None, direct_scale: float = 1.0, heating: bool = True):
         """flux_up, flux_down, net_flux, diffusivity, heating_rate -- each (S, L) on the host."""

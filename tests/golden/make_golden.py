@@ -8,6 +8,7 @@ Only usable where /root/reference exists (the build container):
     python tests/golden/make_golden.py thick      # ~10 min: thick single-layer FWC
     python tests/golden/make_golden.py forcing    # SOS_Aer_radiative_forcing / critical albedo, small grids
     python tests/golden/make_golden.py fwc_table  # the FWC data table (input data)
+    python tests/golden/make_golden.py fwc3       # ~5 min: FWC cloud as the AEROSOL of the three-region driver
 
 Every array written here is an output of reference code (imported from where it
 lies through oracle/ref_harness.py); no reference source is copied.  Big fields
@@ -316,6 +317,33 @@ def stage_forcing():
     np.savez_compressed(os.path.join(HERE, "forcing.npz"), **rec)
 
 
+def stage_fwc3():
+    """The FWC cloud as the aerosol of the three-region specular driver (what bench.py's workload does with a third of
+    its scenarios), at the corners of the sweep: mu0 = 0.1 / 1.0 (1.0 sits ON the mu grid), omega_aer = 0.7 / 1.0,
+    tau_aer = 0.5 / 0.0075; M = 251 (windowed columns exist: |mu| = 0.004, 0.008), reduced L."""
+    M = 251
+    rec = {}
+    runs = [
+        ("mu01", dict(nb_layers=100, mu0=0.1, tauStar_atm=0.124, tauStar_aer=0.5, grd_alb=0.05, alb_aer=0.7)),
+        ("mu1", dict(nb_layers=100, mu0=1.0, tauStar_atm=0.124, tauStar_aer=0.0075, grd_alb=0.3, alb_aer=1.0)),
+        ("mid", dict(nb_layers=120, mu0=0.6, tauStar_atm=0.124, tauStar_aer=0.12, grd_alb=0.15, alb_aer=0.9)),
+    ]
+    for tag, kw in runs:
+        t0 = time.time()
+        mu0 = kw["mu0"]
+        P0a, Pa = ref_phase("rayleigh", M, mu0)
+        P0f, Pf = ref_phase("fwc", M, mu0)
+        out = rh.run_driver("specular", phase={"atm": (P0a, Pa), "aer": (P0f, Pf)}, nb_angles=M, aer_phase_fun="fwc", **kw)
+        r = _driver_record(out, M, mu0, kw["grd_alb"], row_stride=5)
+        for k, v in r.items():
+            rec[f"{tag}_{k}"] = v
+        rec[f"{tag}_kw"] = np.array(repr(dict(kw, nb_angles=M)))
+        rec[f"{tag}_P0_aer"] = P0f
+        print(tag, "n =", out["n"], f"{time.time() - t0:.1f}s", flush=True)
+    rec["tags"] = np.array([r[0] for r in runs])
+    np.savez_compressed(os.path.join(HERE, "drivers_fwc3.npz"), **rec)
+
+
 def stage_fwc_table():
     fw = rh.load_reference()["fwc_data"]
     out = os.path.join(ROOT, "sos-radiative-transfer_b200", "data")
@@ -339,5 +367,7 @@ if __name__ == "__main__":
         stage_forcing()
     elif stage == "fwc_table":
         stage_fwc_table()
+    elif stage == "fwc3":
+        stage_fwc3()
     else:
         raise SystemExit(f"unknown stage {stage}")

@@ -338,28 +338,7 @@ def test_radiative_forcing_and_critical_albedo(sos, golden):
         crit = sos.SOS_Aer_critical_albedo(c["te"], dtau_aer, c["ta"], dtau_atm, Ph, P0h, Pa, P0a, 1.0, c["rho"], F0, mu, mu0,
                                            M, tau, L, iu, idn, tauStar_tot=c["ta"] + c["te"])
         assert crit == float(d[tag + "_critical"]) == 0.5
-    # corrected sweep: the forcing is monotone in omega_aer, the bisection brackets its sign change
-    pts = [sos.Scenario(nb_layers=80, nb_angles=41, mu0=m, tauStar_atm=0.124, tauStar_aer=t, grd_alb=r,
-                        atm_phase=("rayleigh", 0.0), aer_phase=("hg", 0.6))
-           for m in (0.4, 0.8) for t in (0.05, 0.3) for r in (0.05, 0.3)]
-    omega, forcing, n_solves = sos.critical_albedo_sweep(pts, width=0.05)
-    assert omega.shape == (8,) and np.all((omega > 0) & (omega < 1)) and n_solves >= 16
-    import dataclasses
-
-    def forcing_at(i, w):
-        a = sos.solve_scenarios([dataclasses.replace(pts[i], alb_aer=float(w))])[0].toa_net_flux
-        b = sos.solve_scenarios([dataclasses.replace(pts[i], tauStar_aer=0.0, alb_aer=1.0)])[0].toa_net_flux
-        return a - b
-
-    for i in (0, 5):
-        # the forcing reported by the sweep is the forcing of a stand-alone solve at that omega
-        if np.isfinite(forcing[i]):
-            last = forcing_at(i, omega[i])
-            assert abs(last - forcing[i]) < 1e-10 or abs(forcing_at(i, omega[i]) ) >= 0  # midpoint may have moved on
-        f_lo, f_hi = forcing_at(i, 0.01), forcing_at(i, 0.99)
-        if f_lo * f_hi < 0:  # a sign change exists: the returned omega brackets it within the width
-            a, b = forcing_at(i, max(omega[i] - 0.06, 0.0)), forcing_at(i, min(omega[i] + 0.06, 1.0))
-            assert a * b <= 0 or min(abs(a), abs(b)) < 2e-3
+    # (the corrected batched sweep is checked in test_gpu_workload.py::test_critical_albedo_sweep_reports_the_forcing_it_evaluated)
 
 
 @pytest.mark.parametrize("name,g", [("rayleigh", 0.0), ("hg", 0.5), ("hg", 0.75), ("fwc", 0.0)])

@@ -210,24 +210,30 @@ def test_lognormal_mie_family_goes_through_the_tabulated_builder():
 
 
 def test_lowrank_structure_of_the_molecular_operand():
-    """The property behind csrc/gemm_lowrank.cuh, restated in NumPy: the Rayleigh operand of the reference is rank 2
-    (isotropic: 1) to rounding, so (I Us) Vt reproduces I A; HG, FWC and the Mie mixture are not low rank."""
+    """The property behind csrc/gemm_lowrank.cuh (sos_build_lowrank_mu2), restated in NumPy: every row of the Rayleigh
+    operand of the reference is affine in mu_m^2 (isotropic: constant), so the factors read off two of its columns --
+    alpha = A[:, M-1] (mu = 0), beta = A[:, 0] - A[:, M-1] (mu^2 = 1) -- reproduce it to rounding and (I Us) Vt = I A;
+    HG, FWC and the Mie mixture do not have that structure and must be refused by the residual test."""
     M = 101
     N = 2 * M
     mu = so.mu_grid(M)
     rng = np.random.default_rng(3)
     x = rng.random((7, N)) * np.exp(rng.standard_normal((7, N)))
-    ranks = {}
-    for name, g in (("rayleigh", 0.0), ("iso", 0.0), ("hg", 0.5), ("fwc", 0.0)):
+    resid = {}
+    for name, g in (("rayleigh", 0.0), ("iso", 0.0), ("hg", 0.5), ("hg", 0.05), ("fwc", 0.0)):
         _, P = sos.phase_matrices(name, M, mu, 0.5, g)
         A = so.contraction_matrix(P, mu, 1.0)
-        U, S, Vh = np.linalg.svd(A)
-        r = int((S > 1e-13 * S[0]).sum())            # engine.LOWRANK_TOL
-        ranks[name] = r
-        if r <= 16:                                   # engine.LOWRANK_MAX
-            J = (x @ (U[:, :r] * S[:r])) @ Vh[:r]
+        alpha, beta = A[:, M - 1], A[:, 0] - A[:, M - 1]
+        fit = alpha[:, None] + beta[:, None] * (mu * mu)[None, :]
+        resid[(name, g)] = np.max(np.abs(A - fit)) / np.max(np.abs(A))
+        if name in ("rayleigh", "iso"):
+            J = (x @ np.stack([alpha, beta], 1)) @ np.stack([np.ones(N), mu * mu], 0)
             assert np.max(np.abs(J - x @ A) / np.abs(x @ A)) < 1e-13, name
-    assert ranks["rayleigh"] == 2 and ranks["iso"] == 1 and ranks["hg"] > 16 and ranks["fwc"] > 16
+            assert (np.max(np.abs(beta)) <= 1e-15 * np.max(np.abs(A))) == (name == "iso")
+            assert np.linalg.matrix_rank(A, tol=1e-13 * np.linalg.norm(A, 2)) == (1 if name == "iso" else 2)
+    assert resid[("rayleigh", 0.0)] < 1e-14 and resid[("iso", 0.0)] < 1e-14          # engine.LOWRANK_RESIDUAL_MAX
+    # even a weakly anisotropic HG is refused (the advisor's worry about truncating near-low-rank operands)
+    assert resid[("hg", 0.5)] > 1e-3 and resid[("hg", 0.05)] > 1e-6 and resid[("fwc", 0.0)] > 1e-3
 
 
 def test_reference_aerosol_names_resolve_to_the_mie_mixture():

@@ -107,6 +107,30 @@ def test_n1002_drivers(golden, tag):
     assert relmax(up, d[tag + "_flux_up"]) < TOL and relmax(down, d[tag + "_flux_down"]) < TOL
 
 
+@pytest.mark.parametrize("tag", ["mu01", "mu1", "mid"])
+def test_fwc_aerosol_three_region_driver(golden, tag):
+    """FWC cloud as the AEROSOL of the three-region specular driver (a third of bench.py's scenarios), at the corners
+    of its sweep: mu0 = 0.1 / 1.0 (on the grid), omega_aer = 0.7 / 1.0 -- fixture from the unmodified reference."""
+    d = golden("drivers_fwc3.npz")
+    kw = ast.literal_eval(str(d[tag + "_kw"]))
+    M = kw["nb_angles"]
+    sc = so.Scenario(surface="specular", **kw)
+    mu = so.mu_grid(M)
+    P0a, Pa = _phase("rayleigh", M, mu, sc.mu0)
+    P0f, Pf = _phase("fwc", M, mu, sc.mu0)
+    assert relmax(P0f, d[tag + "_P0_aer"]) < TOL
+    res = so.solve(sc, P0a, Pa, P0f, Pf, method="recurrence", use_gemm=True)
+    assert res["n"] == int(d[tag + "_n"])
+    rows = d[tag + "_rows"]
+    assert relmax(res["I"][rows], d[tag + "_I_rows"]) < TOL
+    assert relmax(res["I"][::5], d[tag + "_I_sub"]) < TOL
+    for j in range(res["n"]):
+        assert relmax(res["I_saved"][j][rows], d[tag + "_order_rows"][j]) < TOL, j
+    F0 = np.pi / sc.mu0
+    up, down = so.flux_up_down(res["I"], mu, M, res["tau"], sc.mu0, F0, sc.grd_alb)
+    assert relmax(up, d[tag + "_flux_up"]) < TOL and relmax(down, d[tag + "_flux_down"]) < TOL
+
+
 def test_default_grid_eva_specular(golden):
     """BASELINE config 3 at the reference's default 800 x 1002 grid (HG g=0.5 Mie stand-in)."""
     d = golden("default_eva_spec.npz")
