@@ -166,7 +166,7 @@ struct sos_plan {
   const double** d_Ut_tab = nullptr;
   int* d_rank_tab = nullptr;
   unsigned strip_epoch = 0;
-  std::map<const void*, CUtensorMap> map3_cache;
+  std::map<const void*, std::pair<CUtensorMap, CUtensorMap>> map3_cache;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -273,10 +273,15 @@ struct ProfSpan {
   }
 };
 
-int launch_check(sos_plan* p) {
+int launch_check(sos_plan* p, const char* what = "kernel") {
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    // SOS_B200_SYNC_DEBUG=1: wait for every kernel so that an asynchronous fault is reported with the kernel's name
+    static const bool sync_debug = [] { const char* v = std::getenv("SOS_B200_SYNC_DEBUG"); return v && v[0] == '1'; }();
+    if (sync_debug) e = cudaDeviceSynchronize();
+  }
   if (e != cudaSuccess) {
-    g_last_cuda_error = std::string("kernel launch: ") + cudaGetErrorString(e);
+    g_last_cuda_error = std::string(what) + " launch: " + cudaGetErrorString(e);
     return SOS_ERR_CUDA;
   }
   p->launches++;
@@ -308,7 +313,8 @@ int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_
   const int L = g.L, M = g.M, S = g.S;
   p->strip_ok = false;
   if (strip_env_int("SOS_B200_STRIP", 1) == 0) return SOS_OK;
-  const int nstrips = (M + W - 1) / W;
+  const int o = M & 1;  // odd M: the strips stop one column short of mu = 0 (TMA boxes must start on even columns)
+  const int nstrips = (M - o + W - 1) / W;
   if (nstrips > MAX_STRIPS) return SOS_OK;
   // enough strips to fill the chip without cutting the layer axis (smaller batches keep the chunked scan)
   if (static_cast<long long>(S) * nstrips < strip_env_int("SOS_B200_STRIP_MIN", 48)) return SOS_OK;
@@ -320,7 +326,7 @@ int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_
     for (int k = 0; k < g.nreg; ++k) wmax = std::max(wmax, scen_h[s].extrap_width[k]);
   const int ns = (wmax <= 0) ? 0 : (wmax < 2 ? 2 : std::min(5, wmax));
   const int zl = std::max(0, std::min(g.first_small, M - wmax - ns));
-  if (M - zl > W - 2 || M < 8) return SOS_OK;
+  if (zl < M - o - W || M < 8) return SOS_OK;
   // windows: first row k0 of tau' >= tau_t - 5|mu| inside the region, with the reference's rounding (two operations)
   const int Lp = ((L + kStripR - 1) / kStripR * kStripR + 1) / 2 * 2;
   std::vector<double> tau_pad(static_cast<size_t>(S) * Lp);
@@ -386,21 +392,27 @@ int strip_launch_cfg(sos_plan* p, const sosstrip::StripParams& sp, cudaStream_t 
   }
   const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(p->dev.S) * sp.nstrips, p->strip_grid));
   order_strip_kernel<kStripR, NS><<<std::max(grid, sp.nstrips), THREADS, smem, st>>>(sp);
-  return launch_check(p);
+  return launch_check(p, "order_strip_kernel");
 }
 
-// 3-D tensor map [S][L][N] of a field for the strip kernel
-int strip_field_map(sos_plan* p, const void* base, CUtensorMap* out) {
+// 3-D tensor maps [S][L][N] of a field for the strip kernel: the whole field, and the field cut off after the columns of
+// the strip at the mu = -1 end (a bulk store must not start at a negative column, so that strip starts at column 0)
+int strip_field_map(sos_plan* p, const void* base, CUtensorMap* out, CUtensorMap* out_lo) {
   auto it = p->map3_cache.find(base);
   if (it == p->map3_cache.end()) {
-    CUtensorMap m;
     const GridDev& g = p->dev;
-    int r = encode_3d(&m, base, g.N, g.L, g.S, g.ld, sosstrip::W, kStripR);
+    const int o = g.M & 1;
+    const int lo_cols = std::max(2, g.M - o - sosstrip::W * (p->strip_nstrips - 1));
+    std::pair<CUtensorMap, CUtensorMap> m;
+    int r = encode_3d(&m.first, base, g.N, g.L, g.S, g.ld, sosstrip::W, kStripR);
+    if (r) return r;
+    r = encode_3d(&m.second, base, lo_cols, g.L, g.S, g.ld, sosstrip::W, kStripR);
     if (r) return r;
     if (p->map3_cache.size() > 64) p->map3_cache.clear();
     it = p->map3_cache.emplace(base, m).first;
   }
-  *out = it->second;
+  *out = it->second.first;
+  *out_lo = it->second.second;
   return SOS_OK;
 }
 
@@ -1263,7 +1275,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     }
     if (p->fold_xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     else sosgemm::jn_gemm_fold_kernel<false><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
-    return launch_check(p);
+    return launch_check(p, "jn_gemm_fold_kernel");
   }
   if (p->fold && (p->premix || p->n_lowrank_groups)) return SOS_ERR_UNSUPPORTED;  // the device tile plan has fold-only group classes
   // 64 x 128 tiles with 8 consumer warps of 32 x 32 (profiles/r01_gemm_variants.md), or 128 x 144 with 12 warps of 32 x 48
@@ -1375,11 +1387,16 @@ static int strip_order(sos_plan* p, const double* J_d, double* In_d, double* I_d
   std::memset(&sp, 0, sizeof(sp));
   sp.g = p->dev;
   int r;
-  if ((r = strip_field_map(p, J_d, &sp.map_J))) return r;
-  if ((r = strip_field_map(p, In_d, &sp.map_In))) return r;
-  if ((r = strip_field_map(p, I_d, &sp.map_I))) return r;
+  if ((r = strip_field_map(p, J_d, &sp.map_J, &sp.lo_J))) return r;
+  if ((r = strip_field_map(p, In_d, &sp.map_In, &sp.lo_In))) return r;
+  if ((r = strip_field_map(p, I_d, &sp.map_I, &sp.lo_I))) return r;
   sp.map_S = sp.map_I;
-  if (saved_d && (r = strip_field_map(p, saved_d, &sp.map_S))) return r;
+  sp.lo_S = sp.lo_I;
+  if (saved_d && (r = strip_field_map(p, saved_d, &sp.map_S, &sp.lo_S))) return r;
+  sp.J = J_d;
+  sp.In = In_d;
+  sp.I = I_d;
+  sp.saved = saved_d;
   sp.tau_pad = p->d_tau_pad;
   sp.Lp = p->strip_Lp;
   sp.active = p->dev.active_flat;
@@ -1434,7 +1451,7 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
     SOS_CUDA(cudaStreamSynchronize(st));  // (ut lives on this stack frame)
     dim3 pg((g.L + 7) / 8, g.S);
     sosstrip::strip_project_kernel<<<pg, 256, 0, st>>>(g, In_d, p->d_Ut_tab, p->d_rank_tab, p->lowrank_ldr, p->strip_nslots, p->d_proj[0]);
-    r = launch_check(p);
+    r = launch_check(p, "strip_project_kernel");
     if (r) return r;
   }
   // The host never blocks inside the loop: after every order the device-side "still active" counter

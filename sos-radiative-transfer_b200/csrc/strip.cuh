@@ -18,6 +18,14 @@
 // columns are zero-filled on load and clipped on store, so ragged L, M need no special code) into an NS-stage
 // mbarrier ring; the finished I_n and I tiles leave by TMA bulk stores from the same buffers.  Algorithmic traffic
 // when J is read: J 8 + I_n 8 + I 16 = 32 B per element -- the minimum.
+// Two hardware rules shape the column layout (measured with tools/tma_probe.cu on B200: both violations raise "illegal
+// instruction"): the first element of a box must sit on a 16-byte boundary -- an EVEN column for doubles -- and a bulk
+// STORE must not start at a negative coordinate (loads may; both may overhang the far edge).  N = 2M is even, so mirror
+// blocks are even-aligned as soon as the down blocks are; for odd M (the reference's 501) the blocks therefore stop
+// one column short of mu = 0 on either side -- d = M-2-(128 k + j), u = M+1+128 k + j -- and the pair of columns
+// mu = 0-/0+ (M-1, M: no recurrence on either, SOS_Aer_I1_In.py:100,124-127) is carried by eight threads of strip 0
+// through plain loads and stores, prefetched one stage ahead.  The strip at the mu = -1 end starts at column 0 and
+// uses tensor maps cut off at its last column instead of a negative start.
 //
 // Generated source.  On rows that use the molecular operand alone (every row outside the aerosol layer,
 // SOS_Aer_main_specular.py:323), A = Us Vt with Vt = [1; mu^2] (gemm_lowrank.cuh), so
@@ -56,6 +64,11 @@ constexpr int MAX_STRIPS = 16;  // M <= 2048
 struct StripParams {
   GridDev g;
   CUtensorMap map_J, map_In, map_I, map_S;  // [S][L][N] (strides ld, L*ld), box {W, R, 1}
+  CUtensorMap lo_J, lo_In, lo_I, lo_S;      // the same fields cut off after the columns of the strip at the mu = -1 end
+  const double* J;                          // raw pointers for the mu = 0 column pair (odd M)
+  double* In;
+  double* I;
+  double* saved;
   const double* tau_pad;                    // [S][Lp]: tau with rows padded to whole stages (last value repeated)
   int Lp;
   const int* active;                        // compacted ids of the scenarios still iterating ([*g.n_active])
@@ -129,15 +142,18 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
   __shared__ double s_lkv[R][MAX_SMALL];
   __shared__ int s_lkk[R][MAX_SMALL];
   __shared__ double s_dh[R][MAX_SMALL];
-  __shared__ double s_row[W];
+  __shared__ double s_row[W + 1];
   __shared__ double s_red[8];
+  __shared__ double s_pI[R], s_pJ[R], s_pV[R];  // mu = 0 column of the current pass (odd M): old I, J (dense rows), I_n
 
   const GridDev& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = g.L, M = g.M, N = g.N;
+  const int o = M & 1;  // odd M: the blocks stop one column short of mu = 0 (see the header)
   const int nslots = p.nslots;
   const int stage_bytes = StageLayout<R>::bytes(nslots);
   const int total = *g.n_active * p.nstrips;
+  const size_t ld = g.ld;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) mbar_init(&full_bar[i], 1);
@@ -147,6 +163,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
 
   uint32_t seq = 0;  // stages consumed by this CTA so far (ring position and mbarrier phase)
   const int nst = (L + R - 1) / R, nseq = 2 * nst;
+  const int side_r = tid - (W - R);  // threads W-R .. W-1 also carry row side_r of the mu = 0 column pair
 
   for (;;) {
     if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
@@ -162,9 +179,11 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
     const int rk = p.rank[op];                        // 0: J is read from memory on every row
     const int a0 = (g.nreg == 3) ? g.rstart[1] : L;   // rows [a0, a1) keep the dense contraction (aerosol layer)
     const int a1 = (g.nreg == 3) ? g.rstart[2] : L;
-    const int dcol0 = M - W * (k + 1), ucol0 = M + W * k;
-    const int d = M - 1 - (W * k + tid), u = ucol0 + tid;
+    const bool lowstrip = M - o - W * (k + 1) < 0;    // the strip at the mu = -1 end: starts at column 0, clipped maps
+    const int dcol0 = lowstrip ? 0 : M - o - W * (k + 1), ucol0 = M + o + W * k;
+    const int d = M - 1 - o - (W * k + tid), u = ucol0 + tid;
     const bool vd = d >= 0, vu = u < N;
+    const int ci = vd ? d - dcol0 : tid;              // tile column of d (W-1-tid except in the low strip, whose idle threads sit past its columns)
     const double mud = vd ? g.mu[d] : -1.0, muu = vu ? g.mu[u] : 1.0;
     const double imud = 1.0 / mud, imuu = 1.0 / muu;
     double vd0 = 0.0, vd1 = 0.0, vu0 = 0.0, vu1 = 0.0;
@@ -178,6 +197,10 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
     const int csm = d - g.first_small;                // index among the small columns (valid for K_TAYLOR / K_WINDOW)
     int wmaxs = 0;
     for (int r = 0; r < g.nreg; ++r) wmaxs = max(wmaxs, sc.extrap_width[r]);
+    const bool side = (o == 1 && k == 0);             // this CTA carries the column pair M-1, M outside its tiles
+    const bool side_thread = side && side_r >= 0;
+    double vM0 = 0.0, vM1 = 0.0;                      // Vt[:, M] (generated J of column M)
+    if (side_thread && rk > 0) { vM0 = p.Vt[op][M]; vM1 = p.Vt[op][p.ldr + M]; }
 
     const uint32_t seq0 = seq;
     auto stage_ptr = [&](uint32_t gq) { return smem + static_cast<size_t>(gq % NS) * stage_bytes; };
@@ -193,8 +216,9 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
       const uint32_t bytes = StageLayout<R>::TILE + (dense2 ? StageLayout<R>::TILE : 0) + (gen2 ? rows2 * nslots * 16 : 0) + R * 8;
       mbar_expect_tx(bar, bytes);
       const int c0 = down2 ? dcol0 : ucol0;
-      tma_load_3d(smem_u32(sp + StageLayout<R>::TILE), &p.map_I, bar, c0, t02, s);
-      if (dense2) tma_load_3d(smem_u32(sp), &p.map_J, bar, c0, t02, s);
+      const bool lo = down2 && lowstrip;
+      tma_load_3d(smem_u32(sp + StageLayout<R>::TILE), lo ? &p.lo_I : &p.map_I, bar, c0, t02, s);
+      if (dense2) tma_load_3d(smem_u32(sp), lo ? &p.lo_J : &p.map_J, bar, c0, t02, s);
       if (gen2)
         bulk_load_1d(smem_u32(sp + 2 * StageLayout<R>::TILE), p.proj_in + (static_cast<size_t>(s) * L + t02) * nslots * 2,
                      rows2 * nslots * 16, bar);
@@ -204,12 +228,12 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
       bulk_wait_read<0>();  // the previous work item's stores have left the ring
       for (int q2 = 0; q2 < NS - 1 && q2 < nseq; ++q2) issue(q2);
     }
-
     if (k == 0 && p.nsc > 0 && tid < min(R, L) * p.nsc) {  // windows of the first stage start inside it
       const int r = tid / p.nsc, c = tid - r * p.nsc;
       s_lkk[r][c] = p.k0tab[(static_cast<size_t>(s) * L + r) * p.nsc + c];
       s_lkv[r][c] = 0.0;
     }
+    if (side_thread && side_r < min(R, L)) s_pI[side_r] = p.I[(static_cast<size_t>(s) * L + side_r) * ld + (M - 1)];
     __syncthreads();
 
     // running state of the two recurrences
@@ -217,7 +241,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
     double Dr = 0.0;                    // region-restarted recurrence of a windowed column
     int regd = 0, r0d = 0;              // region of the down pass (slow path)
     double U = 0.0, Jn = 0.0, tn = tau_g[L - 1];
-    double lastJ = 0.0;                 // J[t, mu = 0+] of the row just finished (thread 0 of strip 0)
+    double lastJ = 0.0;                 // I_n[t, mu = 0+] = J of the last row finished (thread 0 of strip 0)
     double seed_src = 0.0;
 
     for (int q = 0; q < nseq; ++q) {
@@ -234,20 +258,32 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
       const bool hasgen = rk > 0 && (t0 < a0 || t0 + rows > a1);
       mbar_wait(&full_bar[gq % NS], (gq / NS) & 1);
 
-      if (hasgen) {
+      // ---------------- per-row coefficients of the generated source; the mu = 0 column of this pass ----------------
+      if (hasgen && tid < 2 * R) {
         // c_r[t] = coef * sum over slots of the partial projections (fixed order)
-        if (tid < 2 * R) {
-          const int r = tid >> 1, c = tid & 1;
-          double sum = 0.0;
-          if (r < rows)
-            for (int j = 0; j < nslots; ++j) sum += pr[(r * nslots + j) * 2 + c];
-          s_cj[r][c] = sc.coef_atm * sum;
-        }
-        __syncthreads();
+        const int r = tid >> 1, c = tid & 1;
+        double sum = 0.0;
+        if (r < rows)
+          for (int j = 0; j < nslots; ++j) sum += pr[(r * nslots + j) * 2 + c];
+        s_cj[r][c] = sc.coef_atm * sum;
       }
+      if (side_thread && side_r < rows) {
+        double v = 0.0;  // down: column M-1 is an extrapolation target (written by the fix-up below) or stays 0
+        if (!down) {     // up: I_n[t, M] = J[t, M] (SOS_Aer_I1_In.py:100)
+          const int t = t0 + side_r;
+          if (rk > 0 && (t < a0 || t >= a1)) {
+            double c0s = 0.0, c1s = 0.0;
+            for (int j = 0; j < nslots; ++j) { c0s += pr[(side_r * nslots + j) * 2]; c1s += pr[(side_r * nslots + j) * 2 + 1]; }
+            v = fma(sc.coef_atm * c1s, vM1, (sc.coef_atm * c0s) * vM0);
+          } else {
+            v = s_pJ[side_r];
+          }
+        }
+        s_pV[side_r] = v;
+      }
+      if (hasgen || (side && !down)) __syncthreads();
 
       if (down) {
-        const int ci = W - 1 - tid;
         if (kd == K_STD || kd == K_INVALID) {
           if (kd == K_STD) {
             double tcv[R], jv[R], iv[R], av[R], bv[R];
@@ -319,7 +355,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
         // ---------------- up pass ----------------
         bool special = false;  // the stage holds a gap row (first row above a region boundary): generic path, CTA-uniform
         if (g.nreg == 3) special = (g.rstart[1] - 1 >= t0 && g.rstart[1] - 1 < t0 + rows) || (g.rstart[2] - 1 >= t0 && g.rstart[2] - 1 < t0 + rows);
-        const bool mu0p = (k == 0 && tid == 0);  // column M: I_n = J (SOS_Aer_I1_In.py:100)
+        const bool mu0p = (o == 0 && k == 0 && tid == 0);  // column M inside the tile: I_n = J (SOS_Aer_I1_In.py:100)
         if (!special && vu && !mu0p) {
           double tcv[R], jv[R], iv[R], av[R], bv[R];
 #pragma unroll
@@ -364,10 +400,12 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
             if (special && (t + 1 == g.rstart[1] || t + 1 == g.rstart[2])) {
               // U holds the raw value at the carry row t+1: it is read after its blend ...
               if (k == 0) {
-                s_row[tid] = mu0p ? lastJ : U;
+                // s_row[i] = raw I_n[t+1, M+i]
+                if (!mu0p) s_row[tid + o] = U;
+                if (tid == 0) s_row[0] = (o == 0) ? lastJ : ((r + 1 < rows) ? s_pV[r + 1] : lastJ);
                 __syncthreads();
                 if (warp == 0) {
-                  const int lim = min(W, N - M);
+                  const int lim = min(W + o, N - M);
                   int istar = -1;
                   for (int base = 1; base + 2 <= lim - 1 && istar < 0; base += 32) {
                     const int i = base + lane;
@@ -381,12 +419,13 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
                   }
                   if (lane == 0) {
                     s_istar = istar;
-                    if (istar < 0) atomicOr(&g.state[s].status, (N - M <= W) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
+                    if (istar < 0) atomicOr(&g.state[s].status, (N - M <= W + o) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
                   }
                 }
                 __syncthreads();
                 const int istar = s_istar;
-                if (istar > 0 && tid > 0 && tid < istar) {
+                const int ri = tid + o;
+                if (istar > 0 && ri > 0 && ri < istar) {
                   const double w = muu / g.mu[M + istar];
                   U = (1.0 - w) * s_row[0] + w * s_row[istar];
                 }
@@ -411,19 +450,31 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
             tn = tc;
           }
         }
+        if (side && tid == 0) lastJ = s_pV[0];  // the next stage may open with a gap row whose carry row is this stage's first
       }
       __syncthreads();
 
-      // ---------------- look-ups of the next down stage's windows (their D_k0 land while this stage is finished) -----------
+      // ---------------- prefetch for the next step: window look-ups, the mu = 0 column (land while this stage is finished) ----
       double lk_val = 0.0;
       int lk_k0 = 0, lk_r = -1, lk_c = 0;
-      if (down && k == 0 && p.nsc > 0 && q + 1 < nst) {
-        const int t0n = t0 + R, rowsn = min(R, L - t0n);
-        if (tid < rowsn * p.nsc) {
+      double nx_I = 0.0, nx_J = 0.0;
+      bool nx_have = false;
+      if (q + 1 < nseq) {
+        const bool downn = q + 1 < nst;
+        const int stn = downn ? q + 1 : nseq - 2 - q;
+        const int t0n = stn * R, rowsn = min(R, L - t0n);
+        if (downn && k == 0 && p.nsc > 0 && tid < rowsn * p.nsc) {
           lk_r = tid / p.nsc;
           lk_c = tid - lk_r * p.nsc;
           lk_k0 = p.k0tab[(static_cast<size_t>(s) * L + t0n + lk_r) * p.nsc + lk_c];
           if (lk_k0 < t0n) lk_val = p.dhist[(static_cast<size_t>(s) * L + lk_k0) * MAX_SMALL + lk_c];
+        }
+        if (side_thread && side_r < rowsn) {
+          const int t = t0n + side_r;
+          const size_t rowoff = (static_cast<size_t>(s) * L + t) * ld;
+          nx_have = true;
+          nx_I = p.I[rowoff + (downn ? M - 1 : M)];
+          if (!downn && !(rk > 0 && (t < a0 || t >= a1))) nx_J = p.J[rowoff + M];
         }
       }
 
@@ -442,18 +493,22 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
               const double* __restrict__ Wm = g.W + g.woff[wc];
               double v = 0.0;
               for (int j = 0; j < ns; ++j) v += Wm[i * ns + j] * Jt[r * W + (src0 + j - dcol0)];
-              const int m = M - 1 - i, idx = W - 1 - i;
-              const bool stdc = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
-              const double raw = Jt[r * W + idx];
-              Jt[r * W + idx] = v;
-              It[r * W + idx] += stdc ? (v - raw) : v;  // standard targets were accumulated raw
+              const int m = M - 1 - i, idx = m - dcol0;
+              if (idx < W) {
+                const bool stdc = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
+                const double raw = Jt[r * W + idx];
+                Jt[r * W + idx] = v;
+                It[r * W + idx] += stdc ? (v - raw) : v;  // standard targets were accumulated raw
+              } else {
+                s_pV[r] = v;  // column M-1 of an odd grid lives outside the tile
+              }
             }
           }
         } else {
-          const int lim = min(W, N - M);
+          const int lim = min(W + o, N - M);
           for (int r = warp; r < rows; r += THREADS / 32) {
-            double* row = Jt + r * W;
-            const double v0 = row[0];
+            double* row = Jt + r * W - o;  // row[i] = I_n[t, M+i] for i >= o
+            const double v0 = o ? s_pV[r] : row[0];
             int istar = -1;
             for (int base = 1; base + 2 <= lim - 1 && istar < 0; base += 32) {
               const int i = base + lane;
@@ -466,7 +521,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
               if (mask) istar = base + __ffs(mask) - 1 + 1;
             }
             if (istar < 0) {
-              if (lane == 0) atomicOr(&g.state[s].status, (N - M <= W) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
+              if (lane == 0) atomicOr(&g.state[s].status, (N - M <= W + o) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
             } else {
               const double v1 = row[istar];
               const double mus = g.mu[M + istar];
@@ -476,7 +531,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
                 const double val = (1.0 - w) * v0 + w * v1;
                 const double old = row[i];
                 row[i] = val;
-                It[r * W + i] += val - old;
+                It[r * W + i - o] += val - old;
               }
             }
           }
@@ -489,14 +544,18 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
       const bool toa_up = !down && st == 0;
       if (last_down || toa_up) {
         const int r = last_down ? (L - 1 - t0) : 0;
-        const int ci = last_down ? (W - 1 - tid) : tid;
+        const int cix = last_down ? ci : tid;
         const bool valid = last_down ? vd : vu;
-        const double val = Jt[r * W + ci];
+        const double val = Jt[r * W + cix];
         double rmax = -INFINITY;
         bool nonfinite = false;
         if (valid) {
-          const double ratio = val / It[r * W + ci];
+          const double ratio = val / It[r * W + cix];
           if (isnan(ratio)) nonfinite = true; else rmax = ratio;
+        }
+        if (side && tid == 0) {  // the mu = 0 column of this pass takes part in the ratio (SOS_Aer_main_specular.py:309)
+          const double ratio = s_pV[r] / (s_pI[r] + s_pV[r]);
+          if (isnan(ratio)) nonfinite = true; else rmax = fmax(rmax, ratio);
         }
         double lam = 0.0;
         if (last_down) {
@@ -510,9 +569,9 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
           }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-          lam += __shfl_xor_sync(0xffffffffu, lam, o);
+        for (int oo = 16; oo > 0; oo >>= 1) {
+          rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, oo));
+          lam += __shfl_xor_sync(0xffffffffu, lam, oo);
         }
         nonfinite = __any_sync(0xffffffffu, nonfinite);
         if (lane == 0) { s_red[warp] = rmax; s_red[4 + warp] = lam; }
@@ -553,22 +612,29 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
       if (rk > 0) {
         const double* __restrict__ Ut = p.Ut[op];
         const int c00 = down ? dcol0 : ucol0;
+        const int cend = down ? (M - o - W * k) : N;  // the low strip's tile also holds its neighbour's columns: not ours
         for (int r = warp; r < rows; r += THREADS / 32) {
           double p0 = 0.0, p1 = 0.0;
 #pragma unroll
           for (int qq = 0; qq < W / 32; ++qq) {
             const int c = lane + 32 * qq;
             const int col = c00 + c;
-            if (col >= 0 && col < N) {
+            if (col < cend) {
               const double x = Jt[r * W + c];
               p0 = fma(x, Ut[col], p0);
               p1 = fma(x, Ut[p.ldr + col], p1);
             }
           }
+          if (side && lane == 0) {
+            const int pc = down ? M - 1 : M;
+            const double x = s_pV[r];
+            p0 = fma(x, Ut[pc], p0);
+            p1 = fma(x, Ut[p.ldr + pc], p1);
+          }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          for (int oo = 16; oo > 0; oo >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, oo);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, oo);
           }
           if (lane == 0) {
             double2* dst = reinterpret_cast<double2*>(p.proj_out + ((static_cast<size_t>(s) * L + t0 + r) * nslots + 2 * k + (down ? 0 : 1)) * 2);
@@ -576,16 +642,27 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
           }
         }
       }
+      // the mu = 0 column of this pass goes back with plain stores
+      if (side_thread && side_r < rows) {
+        const size_t off = (static_cast<size_t>(s) * L + t0 + side_r) * ld + (down ? M - 1 : M);
+        const double v = s_pV[side_r];
+        if (hasdense || p.store_all) p.In[off] = v;
+        if (p.has_saved) p.saved[off] = v;
+        p.I[off] = s_pI[side_r] + v;
+      }
+      __syncthreads();  // s_pV / s_pI / s_lk* of this stage have been read by everyone
       if (lk_r >= 0) { s_lkv[lk_r][lk_c] = lk_val; s_lkk[lk_r][lk_c] = lk_k0; }
+      if (nx_have) { s_pI[side_r] = nx_I; s_pJ[side_r] = nx_J; }
 
       // ---------------- write the finished tiles, refill the ring ----------------
       fence_async_smem();
       __syncthreads();
       if (tid == 0) {
         const int c0 = down ? dcol0 : ucol0;
-        if (hasdense || p.store_all) tma_store_3d(&p.map_In, smem_u32(Jt), c0, t0, s);
-        tma_store_3d(&p.map_I, smem_u32(It), c0, t0, s);
-        if (p.has_saved) tma_store_3d(&p.map_S, smem_u32(Jt), c0, t0, s);
+        const bool lo = down && lowstrip;
+        if (hasdense || p.store_all) tma_store_3d(lo ? &p.lo_In : &p.map_In, smem_u32(Jt), c0, t0, s);
+        tma_store_3d(lo ? &p.lo_I : &p.map_I, smem_u32(It), c0, t0, s);
+        if (p.has_saved) tma_store_3d(lo ? &p.lo_S : &p.map_S, smem_u32(Jt), c0, t0, s);
         bulk_commit();
         if (q + NS - 1 < nseq) {
           bulk_wait_read<1>();  // the stores of the previous step have read their buffer: it is the one refilled now
