@@ -103,6 +103,13 @@ const char* sos_last_cuda_error(void);
 int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, const double* tau_h,
                     const sos_scenario* scen_h, const double* extrap_W_h, int extrap_W_len);
 int sos_plan_destroy(sos_plan* plan);
+/* Feed an existing plan the NEXT batch of scenarios on the same grid (same L, M, S, regions, surface; phase indices into
+ * the matrices already registered): re-uploads tau and the per-scenario scalars, regroups the scenarios by operand,
+ * re-mixes the per-scenario aerosol operands of the folded contraction and resets the per-scenario state.  What a
+ * sweep driver (SOS_Aer_critical_albedo.py:417-503: one solve per (tau_aer, mu0, albedo) point) calls between batches
+ * instead of destroying and re-creating the plan; device buffers, tensor maps and phase operands stay.  Synchronises
+ * `stream`. */
+int sos_plan_update(sos_plan* plan, const double* tau_h, const sos_scenario* scen_h, void* stream);
 
 /* Extrapolation table layout: for width class c (0..3) the matrix W_c is [idx_c][ns_c] row-major
  * at offset off_c in extrap_W_h, where ns_c = (idx_c<2 ? 2 : min(5, idx_c)) sources

@@ -75,6 +75,7 @@ SIGNATURES = {
     "sos_last_cuda_error": (C.c_char_p, []),
     "sos_plan_create": (C.c_int, [C.POINTER(_vp), C.POINTER(sos_grid), _vp, _vp, C.POINTER(sos_scenario), _vp, C.c_int]),
     "sos_plan_destroy": (C.c_int, [_vp]),
+    "sos_plan_update": (C.c_int, [_vp, _vp, C.POINTER(sos_scenario), _vp]),
     "sos_extrap_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sos_build_contraction": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp]),
     "sos_build_phase": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),

@@ -113,6 +113,7 @@ struct sos_plan {
   double* d_colint = nullptr;  // [N] column integrals of the device phase builder
   int* h_poll = nullptr;     // pinned
   std::vector<sos_scenario> scen_h;
+  std::vector<double> mu_h;
   // GEMM
   int gemm_bm = 0;  // rows per tile
   int gemm_bn = 128;  // columns per tile (128, or 144 when that pads N less and the batch is large)
@@ -154,6 +155,7 @@ struct sos_plan {
   // fused single-pass order kernel (strip.cuh): used by sos_solve for batches
   bool strip_ok = false;        // the plan qualifies (batch size, zone inside one strip, ...)
   bool strip_disabled = false;  // a blend left the strip zone at run time: chunked kernels from now on
+  bool strip_zone_ok = true;    // (sos_plan_update) the new batch's extrapolation widths still fit strip 0
   int strip_nstrips = 0, strip_nslots = 0, strip_nsc = 0, strip_Lp = 0, strip_grid = 0;
   double* d_tau_pad = nullptr;
   int* d_k0tab = nullptr;
@@ -306,31 +308,26 @@ int strip_env_int(const char* name, int dflt) {
   return (e && *e) ? std::atoi(e) : dflt;
 }
 
-// Decide whether the plan qualifies for the strip kernel and build its tables.  Not qualifying is not an error.
-int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_scenario* scen_h) {
-  using namespace sosstrip;
-  const GridDev& g = p->dev;
-  const int L = g.L, M = g.M, S = g.S;
-  p->strip_ok = false;
-  if (strip_env_int("SOS_B200_STRIP", 1) == 0) return SOS_OK;
-  const int o = M & 1;  // odd M: the strips stop one column short of mu = 0 (TMA boxes must start on even columns)
-  const int nstrips = (M - o + W - 1) / W;
-  if (nstrips > MAX_STRIPS) return SOS_OK;
-  // enough strips to fill the chip without cutting the layer axis (smaller batches keep the chunked scan)
-  if (static_cast<long long>(S) * nstrips < strip_env_int("SOS_B200_STRIP_MIN", 48)) return SOS_OK;
-  const int nsc = (M - 1) - g.first_small;
-  if (nsc > MAX_SMALL) return SOS_OK;
-  // strip 0 must hold every column the reference treats specially next to mu = 0-
+int strip_padded_rows(int L) { return ((L + kStripR - 1) / kStripR * kStripR + 1) / 2 * 2; }
+
+// zone test of the strip kernel: strip 0 must hold every column the reference treats specially next to mu = 0-
+bool strip_zone_fits(const GridDev& g, const sos_scenario* scen_h) {
+  const int M = g.M, o = M & 1;
   int wmax = 0;
-  for (int s = 0; s < S; ++s)
+  for (int s = 0; s < g.S; ++s)
     for (int k = 0; k < g.nreg; ++k) wmax = std::max(wmax, scen_h[s].extrap_width[k]);
   const int ns = (wmax <= 0) ? 0 : (wmax < 2 ? 2 : std::min(5, wmax));
   const int zl = std::max(0, std::min(g.first_small, M - wmax - ns));
-  if (zl < M - o - W || M < 8) return SOS_OK;
-  // windows: first row k0 of tau' >= tau_t - 5|mu| inside the region, with the reference's rounding (two operations)
-  const int Lp = ((L + kStripR - 1) / kStripR * kStripR + 1) / 2 * 2;
-  std::vector<double> tau_pad(static_cast<size_t>(S) * Lp);
-  std::vector<int> k0tab(static_cast<size_t>(S) * L * std::max(nsc, 1), 0);
+  return zl >= M - o - sosstrip::W && M >= 8;
+}
+
+// tau padded to whole stages, and the first row k0 of every window tau' >= tau_t - 5|mu| inside its region, with the
+// reference's rounding (two operations, SOS_Aer_In_limit.py:96-100)
+void strip_tables(const GridDev& g, const double* mu_h, const double* tau_h, int nsc, int Lp, std::vector<double>& tau_pad,
+                  std::vector<int>& k0tab) {
+  const int L = g.L, S = g.S;
+  tau_pad.resize(static_cast<size_t>(S) * Lp);
+  k0tab.assign(static_cast<size_t>(S) * L * std::max(nsc, 1), 0);
   for (int s = 0; s < S; ++s) {
     const double* tau = tau_h + static_cast<size_t>(s) * L;
     for (int t = 0; t < Lp; ++t) tau_pad[static_cast<size_t>(s) * Lp + t] = tau[std::min(t, L - 1)];
@@ -347,10 +344,31 @@ int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_
       }
     }
   }
+}
+
+// Decide whether the plan qualifies for the strip kernel and build its tables.  Not qualifying is not an error.
+int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_scenario* scen_h) {
+  using namespace sosstrip;
+  const GridDev& g = p->dev;
+  const int L = g.L, M = g.M, S = g.S;
+  p->strip_ok = false;
+  if (strip_env_int("SOS_B200_STRIP", 1) == 0) return SOS_OK;
+  const int o = M & 1;  // odd M: the strips stop one column short of mu = 0 (TMA boxes must start on even columns)
+  const int nstrips = (M - o + W - 1) / W;
+  if (nstrips > MAX_STRIPS) return SOS_OK;
+  // enough strips to fill the chip without cutting the layer axis (smaller batches keep the chunked scan)
+  if (static_cast<long long>(S) * nstrips < strip_env_int("SOS_B200_STRIP_MIN", 48)) return SOS_OK;
+  const int nsc = (M - 1) - g.first_small;
+  if (nsc > MAX_SMALL) return SOS_OK;
+  if (!strip_zone_fits(g, scen_h)) return SOS_OK;
+  const int Lp = strip_padded_rows(L);
+  std::vector<double> tau_pad;
+  std::vector<int> k0tab;
+  strip_tables(g, mu_h, tau_h, nsc, Lp, tau_pad, k0tab);
   int r;
   if ((r = dev_upload(p, const_cast<const double**>(&p->d_tau_pad), tau_pad.data(), tau_pad.size()))) return r;
   if ((r = dev_upload(p, const_cast<const int**>(&p->d_k0tab), k0tab.data(), k0tab.size()))) return r;
-  const int nslots = 2 * nstrips;
+  const int nslots = 2 * nstrips * sosstrip::PROJ_WARPS;  // one projection slot per strip, half and warp
   if ((r = dev_alloc(p, &p->d_dhist, static_cast<size_t>(S) * L * MAX_SMALL))) return r;
   for (int i = 0; i < 2; ++i)
     if ((r = dev_alloc(p, &p->d_proj[i], static_cast<size_t>(S) * L * nslots * 2))) return r;
@@ -372,6 +390,70 @@ int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_
   return SOS_OK;
 }
 
+// aerosol rows with a vanishing second coefficient: split the first one in two equal halves on the same operand
+// (exact in binary floating point) so that every class-1 tile runs two passes
+void patch_scenarios(const sos_grid& grid, std::vector<sos_scenario>& sc) {
+  if (grid.n_regions != 3) return;
+  for (auto& x : sc) {
+    if (x.coef_mix_aer == 0.0) {
+      x.phase_aer = x.phase_atm;
+      x.coef_mix_atm *= 0.5;
+      x.coef_mix_aer = x.coef_mix_atm;
+    }
+  }
+}
+
+// operand groups of the source contraction: class 1 (aerosol rows, two operands) first, then class 0
+int build_groups(sos_plan* p, const std::vector<sos_scenario>& sc, std::vector<int>& flat) {
+  const int S = static_cast<int>(sc.size());
+  std::vector<std::vector<int>> members;
+  std::memset(&p->groups, 0, sizeof(p->groups));
+  auto add_groups = [&](int cls) -> int {
+    std::map<std::pair<int, int>, int> index;
+    for (int s = 0; s < S; ++s) {
+      const std::pair<int, int> key = cls == 1 ? std::make_pair(sc[s].phase_atm, sc[s].phase_aer) : std::make_pair(sc[s].phase_atm, -1);
+      auto it = index.find(key);
+      if (it == index.end()) {
+        if (p->groups.n_groups >= SOS_MAX_GROUPS) return SOS_ERR_UNSUPPORTED;
+        const int g = p->groups.n_groups++;
+        p->groups.cls[g] = cls;
+        p->groups.phaseA[g] = key.first;
+        p->groups.phaseB[g] = cls == 1 ? key.second : key.first;
+        members.emplace_back();
+        it = index.emplace(key, g).first;
+      }
+      members[it->second].push_back(s);
+    }
+    return SOS_OK;
+  };
+  int r;
+  if (p->grid.n_regions == 3 && (r = add_groups(1))) return r;
+  if ((r = add_groups(0))) return r;
+  flat.clear();
+  for (int g = 0; g < p->groups.n_groups; ++g) {
+    p->groups.member_off[g] = static_cast<int>(flat.size());
+    flat.insert(flat.end(), members[g].begin(), members[g].end());
+  }
+  p->groups.member_off[p->groups.n_groups] = static_cast<int>(flat.size());
+  return SOS_OK;
+}
+
+int validate_scenarios(const sos_grid& grid, const sos_scenario* scen_h) {
+  const int M = grid.nb_angles;
+  int widx[4], wns[4], woff[4];
+  sos_extrap_layout(M, widx, wns, woff);
+  for (int s = 0; s < grid.n_scenarios; ++s) {
+    for (int k = 0; k < grid.n_regions; ++k) {
+      const int w = scen_h[s].extrap_width[k];
+      if (w != widx[0] && w != widx[1] && w != widx[2] && w != widx[3]) return SOS_ERR_INVALID;
+      if (w + 5 > M - 1) return SOS_ERR_INVALID;
+    }
+    if (scen_h[s].phase_atm < 0 || scen_h[s].phase_atm >= SOS_MAX_PHASE || scen_h[s].phase_aer < 0 || scen_h[s].phase_aer >= SOS_MAX_PHASE)
+      return SOS_ERR_INVALID;
+  }
+  return SOS_OK;
+}
+
 template <int NS>
 int strip_launch_cfg(sos_plan* p, const sosstrip::StripParams& sp, cudaStream_t st) {
   using namespace sosstrip;
@@ -387,11 +469,14 @@ int strip_launch_cfg(sos_plan* p, const sosstrip::StripParams& sp, cudaStream_t 
   }
   if (p->strip_grid == 0) {
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, order_strip_kernel<kStripR, NS>, THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, order_strip_kernel<kStripR, NS>, CTA_THREADS, smem);
     p->strip_grid = std::max(1, occ) * p->n_sms;
+    if (strip_env_int("SOS_B200_STRIP_DEBUG", 0))
+      std::fprintf(stderr, "[sos_b200] order_strip_kernel<%d,%d>: %d B dynamic smem, %d CTAs/SM, grid %d, %d strips x %d scenarios\n", kStripR, NS,
+                   smem, occ, p->strip_grid, sp.nstrips, p->dev.S);
   }
   const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(p->dev.S) * sp.nstrips, p->strip_grid));
-  order_strip_kernel<kStripR, NS><<<std::max(grid, sp.nstrips), THREADS, smem, st>>>(sp);
+  order_strip_kernel<kStripR, NS><<<std::max(grid, sp.nstrips), CTA_THREADS, smem, st>>>(sp);
   return launch_check(p, "order_strip_kernel");
 }
 
@@ -421,6 +506,7 @@ int strip_field_map(sos_plan* p, const void* base, CUtensorMap* out, CUtensorMap
 extern "C" {
 
 static bool strip_generates(const sos_plan* p);
+static bool strip_usable(const sos_plan* p);
 
 int sos_abi_version(void) { return SOS_ABI_VERSION; }
 
@@ -487,6 +573,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   p->n_sms = n_sms;
   p->launches = 0;
   p->scen_h.assign(scen_h, scen_h + S);
+  p->mu_h.assign(mu_h, mu_h + N);
   std::memset(&p->gp, 0, sizeof(p->gp));
   std::memset(&p->fp, 0, sizeof(p->fp));
 
@@ -612,17 +699,9 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
 
   // ---- source contraction: operand groups, 8-row segments, device tile plan ----
   {
-    // aerosol rows with a vanishing second coefficient: split the first one in two equal halves on
-    // the same operand (exact in binary floating point) so that every class-1 tile runs two passes
     std::vector<sos_scenario> patched(scen_h, scen_h + S);
+    patch_scenarios(*grid, patched);
     if (grid->n_regions == 3) {
-      for (auto& sc : patched) {
-        if (sc.coef_mix_aer == 0.0) {
-          sc.phase_aer = sc.phase_atm;
-          sc.coef_mix_atm *= 0.5;
-          sc.coef_mix_aer = sc.coef_mix_atm;
-        }
-      }
       if (cudaMemcpy(const_cast<sos_scenario*>(d.scen), patched.data(), sizeof(sos_scenario) * S, cudaMemcpyHostToDevice) != cudaSuccess) {
         g_last_cuda_error = "cudaMemcpy(scenarios) failed";
         sos_plan_destroy(p);
@@ -630,36 +709,8 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
       }
       p->scen_h = patched;
     }
-    // groups: class 1 (two operands) first, then class 0
-    std::vector<std::vector<int>> members;
-    std::memset(&p->groups, 0, sizeof(p->groups));
-    auto add_groups = [&](int cls) -> int {
-      std::map<std::pair<int, int>, int> index;
-      for (int s = 0; s < S; ++s) {
-        const std::pair<int, int> key = cls == 1 ? std::make_pair(patched[s].phase_atm, patched[s].phase_aer)
-                                                 : std::make_pair(patched[s].phase_atm, -1);
-        auto it = index.find(key);
-        if (it == index.end()) {
-          if (p->groups.n_groups >= SOS_MAX_GROUPS) return SOS_ERR_UNSUPPORTED;
-          const int g = p->groups.n_groups++;
-          p->groups.cls[g] = cls;
-          p->groups.phaseA[g] = key.first;
-          p->groups.phaseB[g] = cls == 1 ? key.second : key.first;
-          members.emplace_back();
-          it = index.emplace(key, g).first;
-        }
-        members[it->second].push_back(s);
-      }
-      return SOS_OK;
-    };
-    if (grid->n_regions == 3) TRY(add_groups(1));
-    TRY(add_groups(0));
     std::vector<int> flat;
-    for (int g = 0; g < p->groups.n_groups; ++g) {
-      p->groups.member_off[g] = static_cast<int>(flat.size());
-      flat.insert(flat.end(), members[g].begin(), members[g].end());
-    }
-    p->groups.member_off[p->groups.n_groups] = static_cast<int>(flat.size());
+    TRY(build_groups(p, patched, flat));
     // segments: regions cut into 8-row pieces; class 1 = aerosol region, class 0 = the rest
     std::vector<int> srow[2], sval[2];
     for (int k = 0; k < grid->n_regions; ++k) {
@@ -734,6 +785,59 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   return SOS_OK;
 }
 
+static int refresh_fold_plan(sos_plan* p);
+static int premix_folded(sos_plan* p);
+
+int sos_plan_update(sos_plan* p, const double* tau_h, const sos_scenario* scen_h, void* stream) {
+  if (!p || !tau_h || !scen_h) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
+  const GridDev& g = p->dev;
+  const int S = g.S, L = g.L;
+  if (g.col0 != 0 || g.col1 != g.N) return SOS_ERR_UNSUPPORTED;   // column-sharded plans are created per block
+  int r = validate_scenarios(p->grid, scen_h);
+  if (r) return r;
+  const int n_phase = static_cast<int>(p->A_ptrs.size());
+  for (int s = 0; s < S; ++s)
+    if (p->maps_A_ready && (scen_h[s].phase_atm >= n_phase || scen_h[s].phase_aer >= n_phase)) return SOS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SOS_CUDA(cudaStreamSynchronize(st));  // nothing of the previous batch may still be reading the tables rewritten below
+  std::vector<sos_scenario> patched(scen_h, scen_h + S);
+  patch_scenarios(p->grid, patched);
+  p->scen_h = patched;
+  SOS_CUDA(cudaMemcpyAsync(const_cast<double*>(g.tau), tau_h, sizeof(double) * S * L, cudaMemcpyHostToDevice, st));
+  SOS_CUDA(cudaMemcpyAsync(const_cast<sos_scenario*>(g.scen), patched.data(), sizeof(sos_scenario) * S, cudaMemcpyHostToDevice, st));
+  std::vector<int> flat;
+  if ((r = build_groups(p, patched, flat))) return r;
+  if (flat.size() != p->members_h.size()) return SOS_ERR_STATE;
+  p->members_h = flat;
+  SOS_CUDA(cudaMemcpyAsync(p->d_members, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  std::vector<ScenState> state(S);
+  for (int s = 0; s < S; ++s) { state[s].ratio_toa = 1; state[s].ratio_surf = 1; state[s].n_orders = 1; state[s].active = 1; state[s].status = 0; state[s].pad = 0; }
+  SOS_CUDA(cudaMemcpyAsync(g.state, state.data(), sizeof(ScenState) * S, cudaMemcpyHostToDevice, st));
+  std::vector<double> tau_pad;
+  std::vector<int> k0tab;
+  if (p->strip_ok) {
+    p->strip_zone_ok = strip_zone_fits(g, patched.data());
+    if (p->strip_zone_ok) {
+      strip_tables(g, p->mu_h.data(), tau_h, p->strip_nsc, p->strip_Lp, tau_pad, k0tab);
+      SOS_CUDA(cudaMemcpyAsync(p->d_tau_pad, tau_pad.data(), tau_pad.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      SOS_CUDA(cudaMemcpyAsync(p->d_k0tab, k0tab.data(), k0tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    p->strip_disabled = false;  // a new batch gets the fused kernel again
+  }
+  SOS_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+  sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev, p->d_strip_ticket);
+  if ((r = launch_check(p, "count_active_kernel"))) return r;
+  if (p->fold) {
+    if (p->premix && (r = premix_folded(p))) return r;
+    return refresh_fold_plan(p);
+  }
+  r = plan_tiles(p, st);
+  if (r) return r;
+  SOS_CUDA(cudaStreamSynchronize(st));
+  return SOS_OK;
+}
+
 int sos_plan_destroy(sos_plan* p) {
   if (!p) return SOS_OK;
   SOS_GUARD(p);  // the sync and the stream-ordered frees below must run on the plan's own device
@@ -750,8 +854,8 @@ long long sos_launch_count(const sos_plan* p) { return p ? p->launches : 0; }
 int sos_plan_query(const sos_plan* p, int what) {
   if (!p) return SOS_ERR_INVALID;
   switch (what) {
-    case SOS_QUERY_FUSED_ORDER: return (p->strip_ok && !p->strip_disabled && p->dev.col0 == 0 && p->dev.col1 == p->dev.N) ? 1 : 0;
-    case SOS_QUERY_GENERATED_SOURCE: return (p->strip_ok && !p->strip_disabled && strip_generates(p)) ? 1 : 0;
+    case SOS_QUERY_FUSED_ORDER: return strip_usable(p) ? 1 : 0;
+    case SOS_QUERY_GENERATED_SOURCE: return (strip_usable(p) && strip_generates(p)) ? 1 : 0;
     case SOS_QUERY_FOLDED: return p->fold ? 1 : 0;
     case SOS_QUERY_DEVICE: return p->device;
     default: return SOS_ERR_INVALID;
@@ -1040,6 +1144,19 @@ int sos_plan_set_lowrank(sos_plan* p, const double* const* Ut_d, const double* c
   return p->fold ? refresh_fold_plan(p) : SOS_OK;
 }
 
+// (re)build the per-scenario premixed aerosol operands from the registered folded operands and the current coefficients
+static int premix_folded(sos_plan* p) {
+  int rows = 0, ld = 0;
+  sos_fold_layout(p->dev.M, &rows, &ld);
+  const size_t per = static_cast<size_t>(rows) * ld;
+  const int S = p->dev.S, n = static_cast<int>(p->F_ptrs.size());
+  sosgemm::MixSources src;
+  for (int i = 0; i < SOS_MAX_PHASE; ++i) src.F[i] = i < n ? p->F_ptrs[i] : nullptr;
+  dim3 grid(static_cast<unsigned>(std::min<size_t>((per + 255) / 256, 64)), S);
+  sosgemm::mix_folded_kernel<<<grid, 256, 0, nullptr>>>(src, p->dev.scen, p->d_mix, per);
+  return launch_check(p, "mix_folded_kernel");
+}
+
 int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   if (!p) return SOS_ERR_INVALID;
   SOS_GUARD(p);
@@ -1083,11 +1200,7 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
     const int S = p->dev.S;
     if (allow && p->grid.n_regions == 3 && per * S * sizeof(double) <= (2ull << 30)) {
       if (!p->d_mix) { int r = dev_alloc(p, &p->d_mix, per * S); if (r) return r; }
-      sosgemm::MixSources src;
-      for (int i = 0; i < SOS_MAX_PHASE; ++i) src.F[i] = i < n ? F_d[i] : nullptr;
-      dim3 grid(static_cast<unsigned>(std::min<size_t>((per + 255) / 256, 64)), S);
-      sosgemm::mix_folded_kernel<<<grid, 256, 0, nullptr>>>(src, p->dev.scen, p->d_mix, per);
-      int r = launch_check(p);
+      int r = premix_folded(p);
       if (r) return r;
       r = encode_3d(&p->fp.map_mix, p->d_mix, ld, rows, S, ldf, FC::BN_PAD, sosgemm::BK);
       if (r) return r;
@@ -1369,7 +1482,7 @@ int sos_get_results(sos_plan* p, sos_result* results_h, void* stream) {
 // can this solve run on the fused strip kernel, and with generated J?
 static bool strip_usable(const sos_plan* p) {
   const GridDev& g = p->dev;
-  return p->strip_ok && !p->strip_disabled && g.col0 == 0 && g.col1 == g.N;
+  return p->strip_ok && p->strip_zone_ok && !p->strip_disabled && g.col0 == 0 && g.col1 == g.N;
 }
 static bool strip_generates(const sos_plan* p) {
   // the molecular rows leave the contraction only in fold mode (class-3 groups of the tile plan) and only with the

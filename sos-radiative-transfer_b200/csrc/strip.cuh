@@ -31,8 +31,8 @@
 // SOS_Aer_main_specular.py:323), A = Us Vt with Vt = [1; mu^2] (gemm_lowrank.cuh), so
 //     J[t, m] = coef * (c0[t] + c1[t] mu_m^2),   c_r[t] = sum_k I_{n-1}[t, k] Us[k][r]
 // and the two numbers c_r[t] per row are all the next order needs from this one.  The kernel therefore emits, for
-// every finished row, the partial projections of its own 128 columns (one slot per strip and half, summed by the
-// readers in slot order: deterministic) and REBUILDS J from them in the next order instead of reading it: neither J
+// every finished row, the partial projections of its own columns (one m8n8k4 DMMA chain per warp: one slot per strip,
+// half and warp, summed by the readers in a fixed tree: deterministic) and REBUILDS J from them in the next order instead of reading it: neither J
 // nor I_n is ever written for those rows.  Per element and order that leaves the I read-modify-write, 16 B, on 746 of
 // the 800 default rows; the dense (aerosol) rows keep the 32 B path and the DMMA contraction.
 //
@@ -50,6 +50,7 @@
 
 namespace sosstrip {
 
+using sosgemm::mbar_arrive;
 using sosgemm::mbar_expect_tx;
 using sosgemm::mbar_init;
 using sosgemm::mbar_wait;
@@ -57,9 +58,11 @@ using sosgemm::smem_u32;
 using sossweep::exp_small;
 
 constexpr int W = 128;          // columns per strip half = threads per CTA
-constexpr int THREADS = 128;
+constexpr int THREADS = 128;          // consumer threads: one per column of a strip half
+constexpr int CTA_THREADS = THREADS + 32;  // + one producer warp that owns every TMA operation
 constexpr int MAX_SMALL = 16;   // windowed / Taylor columns (|mu| < 0.01, without mu = 0-) a plan may have
 constexpr int MAX_STRIPS = 16;  // M <= 2048
+constexpr int STRIP_MIN_CTAS = 2;
 
 struct StripParams {
   GridDev g;
@@ -113,6 +116,9 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// barrier over the consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
+
 template <int R>
 struct StageLayout {
   // [J / I_n tile][I tile][projections of the stage's rows][tau of the stage's rows]
@@ -130,15 +136,30 @@ __device__ __forceinline__ int region_of(const GridDev& g, int t) {
 
 enum ColKind { K_INVALID = 0, K_STD = 1, K_M1 = 2, K_TAYLOR = 3, K_WINDOW = 4 };
 
+// exp(x) for |x| <= 2^-10 (x^5/5! < 7e-18 relative): what almost every scan step of a thin atmosphere needs
+constexpr double kTinyArg = 0.0009765625;
+__device__ __forceinline__ double exp_tiny(double x) {
+  double p = sossweep::kExpTaylor[4];
+  p = fma(p, x, sossweep::kExpTaylor[5]);
+  p = fma(p, x, sossweep::kExpTaylor[6]);
+  p = fma(p, x, sossweep::kExpTaylor[7]);
+  return fma(p, x, sossweep::kExpTaylor[7]);
+}
+
+constexpr int PROJ_WARPS = THREADS / 32;  // every warp of a strip half writes its own projection slot
+
 template <int R, int NS>
-__global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_constant__ StripParams p) {
-  static_assert(R * MAX_SMALL <= THREADS && 2 * R <= THREADS && (R % 2) == 0, "stage shape");
+__global__ void __launch_bounds__(CTA_THREADS, STRIP_MIN_CTAS) order_strip_kernel(const __grid_constant__ StripParams p) {
+  static_assert(R == 8, "the projection uses one m8n8k4 tile of rows per stage");
+  static_assert(R * MAX_SMALL <= THREADS && 16 * R <= THREADS, "stage shape");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  __shared__ uint64_t full_bar[NS];
+  __shared__ uint64_t full_bar[NS];   // TMA loads of a stage have landed (producer -> consumers)
+  __shared__ uint64_t ready_bar[NS];  // the stage's tiles are final and fenced (consumers -> producer)
   __shared__ int s_ticket;
   __shared__ int s_istar;
-  __shared__ double s_cj[R][2];
+  __shared__ double s_cj[2][R][2];
+  __shared__ double s_us[2][W][2];  // Us of this strip's down / up columns (0 outside the strip)
   __shared__ double s_lkv[R][MAX_SMALL];
   __shared__ int s_lkk[R][MAX_SMALL];
   __shared__ double s_dh[R][MAX_SMALL];
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
   const size_t ld = g.ld;
 
   if (tid == 0) {
-    for (int i = 0; i < NS; ++i) mbar_init(&full_bar[i], 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&ready_bar[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -181,16 +202,24 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
     const int a1 = (g.nreg == 3) ? g.rstart[2] : L;
     const bool lowstrip = M - o - W * (k + 1) < 0;    // the strip at the mu = -1 end: starts at column 0, clipped maps
     const int dcol0 = lowstrip ? 0 : M - o - W * (k + 1), ucol0 = M + o + W * k;
+    const int dend = M - o - W * k;                   // one past this strip's last downward column
     const int d = M - 1 - o - (W * k + tid), u = ucol0 + tid;
     const bool vd = d >= 0, vu = u < N;
     const int ci = vd ? d - dcol0 : tid;              // tile column of d (W-1-tid except in the low strip, whose idle threads sit past its columns)
     const double mud = vd ? g.mu[d] : -1.0, muu = vu ? g.mu[u] : 1.0;
     const double imud = 1.0 / mud, imuu = 1.0 / muu;
     double vd0 = 0.0, vd1 = 0.0, vu0 = 0.0, vu1 = 0.0;
-    if (rk > 0) {
+    if (rk > 0 && tid < THREADS) {
       const double* __restrict__ Vt = p.Vt[op];
+      const double* __restrict__ Ut = p.Ut[op];
       if (vd) { vd0 = Vt[d]; vd1 = Vt[p.ldr + d]; }
       if (vu) { vu0 = Vt[u]; vu1 = Vt[p.ldr + u]; }
+      // projection operands by TILE column (tid = tile column here)
+      const int cdn = dcol0 + tid, cup = ucol0 + tid;
+      s_us[0][tid][0] = (cdn < dend) ? Ut[cdn] : 0.0;
+      s_us[0][tid][1] = (cdn < dend) ? Ut[p.ldr + cdn] : 0.0;
+      s_us[1][tid][0] = (cup < N) ? Ut[cup] : 0.0;
+      s_us[1][tid][1] = (cup < N) ? Ut[p.ldr + cup] : 0.0;
     }
     int kd = K_INVALID;
     if (vd) kd = (d == M - 1) ? K_M1 : (fabs(mud) >= SOS_MU_THRESHOLD ? K_STD : (fabs(mud) < SOS_MU_VERY_SMALL ? K_TAYLOR : K_WINDOW));
@@ -199,15 +228,21 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
     for (int r = 0; r < g.nreg; ++r) wmaxs = max(wmaxs, sc.extrap_width[r]);
     const bool side = (o == 1 && k == 0);             // this CTA carries the column pair M-1, M outside its tiles
     const bool side_thread = side && side_r >= 0;
-    double vM0 = 0.0, vM1 = 0.0;                      // Vt[:, M] (generated J of column M)
+    double vM0 = 0.0, vM1 = 0.0, uM1a = 0.0, uM1b = 0.0, uMa = 0.0, uMb = 0.0;  // Vt[:, M]; Us[M-1], Us[M]
     if (side_thread && rk > 0) { vM0 = p.Vt[op][M]; vM1 = p.Vt[op][p.ldr + M]; }
+    if (side && rk > 0 && warp == 0) { uM1a = p.Ut[op][M - 1]; uM1b = p.Ut[op][p.ldr + M - 1]; uMa = p.Ut[op][M]; uMb = p.Ut[op][p.ldr + M]; }
 
     const uint32_t seq0 = seq;
     auto stage_ptr = [&](uint32_t gq) { return smem + static_cast<size_t>(gq % NS) * stage_bytes; };
-    auto issue = [&](int q2) {  // thread 0: start the loads of sequence step q2 of this work item
-      const bool down2 = q2 < nst;
+    auto stage_rows = [&](int q2, bool& down2, int& t02, int& rows2) {
+      down2 = q2 < nst;
       const int st2 = down2 ? q2 : nseq - 1 - q2;
-      const int t02 = st2 * R, rows2 = min(R, L - t02);
+      t02 = st2 * R;
+      rows2 = min(R, L - t02);
+    };
+    auto issue = [&](int q2) {  // thread 0: start the loads of sequence step q2 of this work item
+      bool down2; int t02, rows2;
+      stage_rows(q2, down2, t02, rows2);
       const uint32_t gq2 = seq0 + q2;
       uint8_t* sp = stage_ptr(gq2);
       uint64_t* bar = &full_bar[gq2 % NS];
@@ -224,9 +259,54 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
                      rows2 * nslots * 16, bar);
       bulk_load_1d(smem_u32(sp + 2 * StageLayout<R>::TILE + R * nslots * 16), p.tau_pad + static_cast<size_t>(s) * p.Lp + t02, R * 8, bar);
     };
-    if (tid == 0) {
-      bulk_wait_read<0>();  // the previous work item's stores have left the ring
-      for (int q2 = 0; q2 < NS - 1 && q2 < nseq; ++q2) issue(q2);
+    // c_r[t] = coef * (sum over slots of the partial projections), for the rows of sequence step q2, into s_cj[q2 & 1].
+    // All 128 threads: (row, component, eighth of the slots), fixed summation tree -> deterministic.
+    auto coefficients = [&](int q2) {
+      bool down2; int t02, rows2;
+      stage_rows(q2, down2, t02, rows2);
+      if (!(rk > 0 && (t02 < a0 || t02 + rows2 > a1))) return;
+      const uint32_t gq2 = seq0 + q2;
+      mbar_wait(&full_bar[gq2 % NS], (gq2 / NS) & 1);
+      const double* __restrict__ pr2 = reinterpret_cast<const double*>(stage_ptr(gq2) + 2 * StageLayout<R>::TILE);
+      const int r = tid >> 4, c = (tid >> 3) & 1, part = tid & 7;
+      double sum = 0.0;
+      if (r < rows2)
+        for (int j = part; j < nslots; j += 8) sum += pr2[(r * nslots + j) * 2 + c];
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (part == 0) s_cj[q2 & 1][r][c] = sc.coef_atm * sum;
+    };
+    if (tid >= THREADS) {
+      // ===================== producer warp: every TMA load and store of this work item =====================
+      // (a consumer thread that issued them would put the bulk store's shared-memory read latency on the critical path
+      //  of its whole CTA: measured 6.7 us per 8-row stage with thread 0 as issuer)
+      if (tid == THREADS) {
+        bulk_wait_read<0>();  // the previous work item's stores have left the ring
+        for (int q2 = 0; q2 < NS - 1 && q2 < nseq; ++q2) issue(q2);
+        for (int q = 0; q < nseq; ++q) {
+          bool down; int t0, rows;
+          stage_rows(q, down, t0, rows);
+          const uint32_t gq = seq0 + q;
+          uint8_t* sp = stage_ptr(gq);
+          const bool hasdense = rk == 0 || (t0 < a1 && t0 + rows > a0);
+          mbar_wait(&ready_bar[gq % NS], (gq / NS) & 1);
+          const int c0 = down ? dcol0 : ucol0;
+          const bool lo = down && lowstrip;
+          if (hasdense || p.store_all) tma_store_3d(lo ? &p.lo_In : &p.map_In, smem_u32(sp), c0, t0, s);
+          tma_store_3d(lo ? &p.lo_I : &p.map_I, smem_u32(sp + StageLayout<R>::TILE), c0, t0, s);
+          if (p.has_saved) tma_store_3d(lo ? &p.lo_S : &p.map_S, smem_u32(sp), c0, t0, s);
+          bulk_commit();
+          if (q + NS - 1 < nseq) {
+            // the buffer of step q-1 is refilled: its consumers are done (they have signalled step q) and its stores
+            // have read it (at most this step's group is still pending)
+            bulk_wait_read<1>();
+            issue(q + NS - 1);
+          }
+        }
+      }
+      seq += nseq;
+      continue;
     }
     if (k == 0 && p.nsc > 0 && tid < min(R, L) * p.nsc) {  // windows of the first stage start inside it
       const int r = tid / p.nsc, c = tid - r * p.nsc;
@@ -234,7 +314,9 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
       s_lkv[r][c] = 0.0;
     }
     if (side_thread && side_r < min(R, L)) s_pI[side_r] = p.I[(static_cast<size_t>(s) * L + side_r) * ld + (M - 1)];
-    __syncthreads();
+    consumer_sync();   // (thread 0 has issued step 0 before anyone waits for it)
+    coefficients(0);
+    consumer_sync();
 
     // running state of the two recurrences
     double D = 0.0, Jp = 0.0, tp = tau_g[0];
@@ -245,75 +327,77 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
     double seed_src = 0.0;
 
     for (int q = 0; q < nseq; ++q) {
-      const bool down = q < nst;
-      const int st = down ? q : nseq - 1 - q;
-      const int t0 = st * R, rows = min(R, L - t0);
+      bool down; int t0, rows;
+      stage_rows(q, down, t0, rows);
+      const int st = t0 / R;
       const uint32_t gq = seq0 + q;
       uint8_t* sp = stage_ptr(gq);
       double* __restrict__ Jt = reinterpret_cast<double*>(sp);
       double* __restrict__ It = reinterpret_cast<double*>(sp + StageLayout<R>::TILE);
       const double* __restrict__ pr = reinterpret_cast<const double*>(sp + 2 * StageLayout<R>::TILE);
       const double* __restrict__ ta = reinterpret_cast<const double*>(sp + 2 * StageLayout<R>::TILE + R * nslots * 16);
+      const double (*cj)[2] = s_cj[q & 1];
       const bool hasdense = rk == 0 || (t0 < a1 && t0 + rows > a0);
-      const bool hasgen = rk > 0 && (t0 < a0 || t0 + rows > a1);
       mbar_wait(&full_bar[gq % NS], (gq / NS) & 1);
 
-      // ---------------- per-row coefficients of the generated source; the mu = 0 column of this pass ----------------
-      if (hasgen && tid < 2 * R) {
-        // c_r[t] = coef * sum over slots of the partial projections (fixed order)
-        const int r = tid >> 1, c = tid & 1;
-        double sum = 0.0;
-        if (r < rows)
-          for (int j = 0; j < nslots; ++j) sum += pr[(r * nslots + j) * 2 + c];
-        s_cj[r][c] = sc.coef_atm * sum;
-      }
-      if (side_thread && side_r < rows) {
-        double v = 0.0;  // down: column M-1 is an extrapolation target (written by the fix-up below) or stays 0
-        if (!down) {     // up: I_n[t, M] = J[t, M] (SOS_Aer_I1_In.py:100)
-          const int t = t0 + side_r;
-          if (rk > 0 && (t < a0 || t >= a1)) {
-            double c0s = 0.0, c1s = 0.0;
-            for (int j = 0; j < nslots; ++j) { c0s += pr[(side_r * nslots + j) * 2]; c1s += pr[(side_r * nslots + j) * 2 + 1]; }
-            v = fma(sc.coef_atm * c1s, vM1, (sc.coef_atm * c0s) * vM0);
-          } else {
-            v = s_pJ[side_r];
+      // coefficients of the NEXT step's generated source (published by the barrier that ends this step's main loop)
+      if (q + 1 < nseq) coefficients(q + 1);
+
+      // ---------------- strip 0: the mu = 0 column of this pass (odd M) ----------------
+      if (k == 0) {
+        if (side_thread && side_r < rows) {
+          double v = 0.0;  // down: column M-1 is an extrapolation target (written by the fix-up below) or stays 0
+          if (!down) {     // up: I_n[t, M] = J[t, M] (SOS_Aer_I1_In.py:100)
+            const int t = t0 + side_r;
+            v = (rk > 0 && (t < a0 || t >= a1)) ? fma(cj[side_r][1], vM1, cj[side_r][0] * vM0) : s_pJ[side_r];
           }
+          s_pV[side_r] = v;
         }
-        s_pV[side_r] = v;
+        consumer_sync();  // also publishes s_lk* / s_pI / s_pJ written at the end of the previous step
       }
-      if (hasgen || (side && !down)) __syncthreads();
+
+      // tau of the stage's rows; the largest step decides (warp-uniformly) which exp polynomial the scan uses
+      double tcv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) tcv[r] = ta[r];
 
       if (down) {
+        double dtmax = tcv[0] - tp;
+#pragma unroll
+        for (int r = 1; r < R; ++r) dtmax = fmax(dtmax, tcv[r] - tcv[r - 1]);
+        const bool tiny = __all_sync(0xffffffffu, kd != K_STD || dtmax * fabs(imud) <= kTinyArg);
         if (kd == K_STD || kd == K_INVALID) {
           if (kd == K_STD) {
-            double tcv[R], jv[R], iv[R], av[R], bv[R];
+            double jv[R], xv[R], av[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               const int t = t0 + r;
-              tcv[r] = ta[r];
               const bool gen = rk > 0 && (t < a0 || t >= a1);
-              jv[r] = gen ? fma(s_cj[r][1], vd1, s_cj[r][0] * vd0) : Jt[r * W + ci];
-              iv[r] = It[r * W + ci];
+              jv[r] = gen ? fma(cj[r][1], vd1, cj[r][0] * vd0) : Jt[r * W + ci];
+              xv[r] = (tcv[r] - (r ? tcv[r - 1] : tp)) * imud;
+            }
+            if (tiny) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) av[r] = exp_tiny(xv[r]);
+            } else {
+#pragma unroll
+              for (int r = 0; r < R; ++r) av[r] = exp_small(xv[r]);
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const double dt = tcv[r] - (r ? tcv[r - 1] : tp);
-              av[r] = exp_small(dt * imud);
-              bv[r] = (dt * 0.5) * ((r ? jv[r - 1] : Jp) * av[r] + jv[r]) * imud;
-            }
+            for (int r = 0; r < R; ++r) xv[r] = (0.5 * xv[r]) * ((r ? jv[r - 1] : Jp) * av[r] + jv[r]);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               if (r < rows) {
-                D = (t0 + r == 0) ? 0.0 : D * av[r] - bv[r];
+                D = (t0 + r == 0) ? 0.0 : D * av[r] - xv[r];
                 Jt[r * W + ci] = D;
-                It[r * W + ci] = iv[r] + D;
+                It[r * W + ci] += D;
                 Jp = jv[r];
                 tp = tcv[r];
               }
             }
           } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) Jt[r * W + ci] = 0.0;
+            for (int r = 0; r < R; ++r) Jt[r * W + ci] = 0.0;  // idle threads of the low strip: keep the projection's operand finite
           }
         } else {
           // the few special columns next to mu = 0- (strip 0 only)
@@ -322,7 +406,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
             const double tc = ta[r];
             while (regd + 1 < g.nreg && t >= g.rstart[regd + 1]) { ++regd; r0d = g.rstart[regd]; }
             const bool gen = rk > 0 && (t < a0 || t >= a1);
-            const double jt = gen ? fma(s_cj[r][1], vd1, s_cj[r][0] * vd0) : Jt[r * W + ci];
+            const double jt = gen ? fma(cj[r][1], vd1, cj[r][0] * vd0) : Jt[r * W + ci];
             const double io = It[r * W + ci];
             const bool target = (M - 1 - d) < sc.extrap_width[regd];
             double val;
@@ -356,25 +440,44 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
         bool special = false;  // the stage holds a gap row (first row above a region boundary): generic path, CTA-uniform
         if (g.nreg == 3) special = (g.rstart[1] - 1 >= t0 && g.rstart[1] - 1 < t0 + rows) || (g.rstart[2] - 1 >= t0 && g.rstart[2] - 1 < t0 + rows);
         const bool mu0p = (o == 0 && k == 0 && tid == 0);  // column M inside the tile: I_n = J (SOS_Aer_I1_In.py:100)
-        if (!special && vu && !mu0p) {
-          double tcv[R], jv[R], iv[R], av[R], bv[R];
+        const bool fast = !special && vu && !mu0p;
+        double dtmax = tn - tcv[R - 1];  // (tau_pad repeats the last value past row L-1)
+#pragma unroll
+        for (int r = 1; r < R; ++r) dtmax = fmax(dtmax, tcv[r] - tcv[r - 1]);
+        const bool tiny = __all_sync(0xffffffffu, !fast || dtmax * fabs(imuu) <= kTinyArg);
+        if (fast) {
+          double jv[R], xv[R], av[R];
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const int t = t0 + r;
-            tcv[r] = ta[r];
             const bool gen = rk > 0 && (t < a0 || t >= a1);
-            jv[r] = gen ? fma(s_cj[r][1], vu1, s_cj[r][0] * vu0) : Jt[r * W + tid];
-            iv[r] = It[r * W + tid];
+            jv[r] = gen ? fma(cj[r][1], vu1, cj[r][0] * vu0) : Jt[r * W + tid];
           }
           {
-            double tnx = tn, jnx = Jn;
+            double tnx = tn;
 #pragma unroll
             for (int r = R - 1; r >= 0; --r) {
               if (r < rows) {
-                const double dt = tnx - tcv[r];
-                av[r] = exp_small(-dt * imuu);
-                bv[r] = (dt * 0.5) * (jv[r] + jnx * av[r]) * imuu;
+                xv[r] = (tcv[r] - tnx) * imuu;  // = -dt / mu
                 tnx = tcv[r];
+              } else {
+                xv[r] = 0.0;
+              }
+            }
+          }
+          if (tiny) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) av[r] = exp_tiny(xv[r]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) av[r] = exp_small(xv[r]);
+          }
+          {
+            double jnx = Jn;
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+              if (r < rows) {
+                xv[r] = (0.5 * xv[r]) * (jv[r] + jnx * av[r]);  // = -b
                 jnx = jv[r];
               }
             }
@@ -382,19 +485,19 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
 #pragma unroll
           for (int r = R - 1; r >= 0; --r) {
             if (r < rows) {
-              U = (t0 + r == L - 1) ? U : U * av[r] + bv[r];  // surface row: zero-length integral, the seed itself
+              U = (t0 + r == L - 1) ? U : U * av[r] - xv[r];  // surface row: zero-length integral, the seed itself
               Jt[r * W + tid] = U;
-              It[r * W + tid] = iv[r] + U;
-              Jn = jv[r];
-              tn = tcv[r];
+              It[r * W + tid] += U;
             }
           }
+          Jn = jv[0];
+          tn = tcv[0];
         } else {
           for (int r = rows - 1; r >= 0; --r) {
             const int t = t0 + r;
             const double tc = ta[r];
             const bool gen = rk > 0 && (t < a0 || t >= a1);
-            const double jt = gen ? fma(s_cj[r][1], vu1, s_cj[r][0] * vu0) : Jt[r * W + tid];
+            const double jt = gen ? fma(cj[r][1], vu1, cj[r][0] * vu0) : Jt[r * W + tid];
             const double io = It[r * W + tid];
             double val;
             if (special && (t + 1 == g.rstart[1] || t + 1 == g.rstart[2])) {
@@ -403,7 +506,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
                 // s_row[i] = raw I_n[t+1, M+i]
                 if (!mu0p) s_row[tid + o] = U;
                 if (tid == 0) s_row[0] = (o == 0) ? lastJ : ((r + 1 < rows) ? s_pV[r + 1] : lastJ);
-                __syncthreads();
+                consumer_sync();
                 if (warp == 0) {
                   const int lim = min(W + o, N - M);
                   int istar = -1;
@@ -422,14 +525,14 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
                     if (istar < 0) atomicOr(&g.state[s].status, (N - M <= W + o) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
                   }
                 }
-                __syncthreads();
+                consumer_sync();
                 const int istar = s_istar;
                 const int ri = tid + o;
                 if (istar > 0 && ri > 0 && ri < istar) {
                   const double w = muu / g.mu[M + istar];
                   U = (1.0 - w) * s_row[0] + w * s_row[istar];
                 }
-                __syncthreads();  // s_row is reused at the next boundary
+                consumer_sync();  // s_row is reused at the next boundary
               }
               // ... then crosses the gap with pure attenuation (SOS_Aer_main_specular.py:413,433)
               U = U * exp(-(tn - tc) / muu);
@@ -452,34 +555,33 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
         }
         if (side && tid == 0) lastJ = s_pV[0];  // the next stage may open with a gap row whose carry row is this stage's first
       }
-      __syncthreads();
+      if (k != 0) fence_async_smem();  // tiles of the other strips are final here
+      consumer_sync();
+      if (k != 0 && tid == 0) mbar_arrive(&ready_bar[gq % NS]);  // -> producer: store them, refill the ring
 
-      // ---------------- prefetch for the next step: window look-ups, the mu = 0 column (land while this stage is finished) ----
+      // ---------------- strip 0: prefetch for the next step, then finish the columns next to mu = 0 in shared memory -------
       double lk_val = 0.0;
       int lk_k0 = 0, lk_r = -1, lk_c = 0;
       double nx_I = 0.0, nx_J = 0.0;
       bool nx_have = false;
-      if (q + 1 < nseq) {
-        const bool downn = q + 1 < nst;
-        const int stn = downn ? q + 1 : nseq - 2 - q;
-        const int t0n = stn * R, rowsn = min(R, L - t0n);
-        if (downn && k == 0 && p.nsc > 0 && tid < rowsn * p.nsc) {
-          lk_r = tid / p.nsc;
-          lk_c = tid - lk_r * p.nsc;
-          lk_k0 = p.k0tab[(static_cast<size_t>(s) * L + t0n + lk_r) * p.nsc + lk_c];
-          if (lk_k0 < t0n) lk_val = p.dhist[(static_cast<size_t>(s) * L + lk_k0) * MAX_SMALL + lk_c];
-        }
-        if (side_thread && side_r < rowsn) {
-          const int t = t0n + side_r;
-          const size_t rowoff = (static_cast<size_t>(s) * L + t) * ld;
-          nx_have = true;
-          nx_I = p.I[rowoff + (downn ? M - 1 : M)];
-          if (!downn && !(rk > 0 && (t < a0 || t >= a1))) nx_J = p.J[rowoff + M];
-        }
-      }
-
-      // ---------------- strip 0: finish the columns next to mu = 0 in shared memory ----------------
       if (k == 0) {
+        if (q + 1 < nseq) {
+          bool downn; int t0n, rowsn;
+          stage_rows(q + 1, downn, t0n, rowsn);
+          if (downn && p.nsc > 0 && tid < rowsn * p.nsc) {
+            lk_r = tid / p.nsc;
+            lk_c = tid - lk_r * p.nsc;
+            lk_k0 = p.k0tab[(static_cast<size_t>(s) * L + t0n + lk_r) * p.nsc + lk_c];
+            if (lk_k0 < t0n) lk_val = p.dhist[(static_cast<size_t>(s) * L + lk_k0) * MAX_SMALL + lk_c];
+          }
+          if (side_thread && side_r < rowsn) {
+            const int t = t0n + side_r;
+            const size_t rowoff = (static_cast<size_t>(s) * L + t) * ld;
+            nx_have = true;
+            nx_I = p.I[rowoff + (downn ? M - 1 : M)];
+            if (!downn && !(rk > 0 && (t < a0 || t >= a1))) nx_J = p.J[rowoff + M];
+          }
+        }
         if (down) {
           if (wmaxs > 0) {
             for (int e = tid; e < rows * wmaxs; e += THREADS) {
@@ -536,10 +638,12 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
             }
           }
         }
-        __syncthreads();
+        fence_async_smem();
+        consumer_sync();
+        if (tid == 0) mbar_arrive(&ready_bar[gq % NS]);
       }
 
-      // ---------------- rows are final: surface seeds, convergence ratios, projections ----------------
+      // ---------------- rows are final: surface seeds and convergence ratios (two stages per work item) ----------------
       const bool last_down = down && st == nst - 1;
       const bool toa_up = !down && st == 0;
       if (last_down || toa_up) {
@@ -576,7 +680,7 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
         nonfinite = __any_sync(0xffffffffu, nonfinite);
         if (lane == 0) { s_red[warp] = rmax; s_red[4 + warp] = lam; }
         if (nonfinite && lane == 0) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);
-        __syncthreads();
+        consumer_sync();
         if (tid == 0) {
           const double rm = fmax(fmax(s_red[0], s_red[1]), fmax(s_red[2], s_red[3]));
           if (rm == INFINITY) atomicOr(&g.state[s].status, SOS_STATUS_NONFINITE);
@@ -600,79 +704,55 @@ __global__ void __launch_bounds__(THREADS) order_strip_kernel(const __grid_const
               }
               s_red[0] = -2.0 * sc.grd_alb * totl;
             }
-            __syncthreads();
+            consumer_sync();
             U = s_red[0];
           } else {
             U = 0.0;
           }
         }
-        __syncthreads();
+        consumer_sync();
       }
 
+      // ---------------- projections of the finished rows onto the molecular factors: one m8n8k4 DMMA chain per warp ----------
+      // C[row][n] += sum_k I_n[row][32 warp + k] Us[k][n]; lanes with lane % 4 == 0 end up with (n = 0, 1) of row lane / 4
       if (rk > 0) {
-        const double* __restrict__ Ut = p.Ut[op];
-        const int c00 = down ? dcol0 : ucol0;
-        const int cend = down ? (M - o - W * k) : N;  // the low strip's tile also holds its neighbour's columns: not ours
-        for (int r = warp; r < rows; r += THREADS / 32) {
-          double p0 = 0.0, p1 = 0.0;
+        const int half = down ? 0 : 1;
+        const int gq4 = lane >> 2, t4 = lane & 3;
+        double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-          for (int qq = 0; qq < W / 32; ++qq) {
-            const int c = lane + 32 * qq;
-            const int col = c00 + c;
-            if (col < cend) {
-              const double x = Jt[r * W + c];
-              p0 = fma(x, Ut[col], p0);
-              p1 = fma(x, Ut[p.ldr + col], p1);
-            }
-          }
-          if (side && lane == 0) {
-            const int pc = down ? M - 1 : M;
-            const double x = s_pV[r];
-            p0 = fma(x, Ut[pc], p0);
-            p1 = fma(x, Ut[p.ldr + pc], p1);
-          }
-#pragma unroll
-          for (int oo = 16; oo > 0; oo >>= 1) {
-            p0 += __shfl_xor_sync(0xffffffffu, p0, oo);
-            p1 += __shfl_xor_sync(0xffffffffu, p1, oo);
-          }
-          if (lane == 0) {
-            double2* dst = reinterpret_cast<double2*>(p.proj_out + ((static_cast<size_t>(s) * L + t0 + r) * nslots + 2 * k + (down ? 0 : 1)) * 2);
-            *dst = make_double2(p0, p1);
-          }
+        for (int ks = 0; ks < 8; ++ks) {
+          const int col = 32 * warp + 4 * ks + t4;
+          const double a = Jt[gq4 * W + col];
+          const double b = (gq4 < 2) ? s_us[half][col][gq4] : 0.0;
+          sosgemm::dmma884(c0, c1, a, b);
+        }
+        if (side && warp == 0 && t4 == 0) {  // the mu = 0 column of this pass
+          const double x = s_pV[gq4];
+          c0 = fma(x, down ? uM1a : uMa, c0);
+          c1 = fma(x, down ? uM1b : uMb, c1);
+        }
+        if (t4 == 0 && gq4 < rows) {
+          double2* dst = reinterpret_cast<double2*>(p.proj_out + ((static_cast<size_t>(s) * L + t0 + gq4) * nslots + (2 * k + half) * PROJ_WARPS + warp) * 2);
+          *dst = make_double2(c0, c1);
         }
       }
-      // the mu = 0 column of this pass goes back with plain stores
-      if (side_thread && side_r < rows) {
-        const size_t off = (static_cast<size_t>(s) * L + t0 + side_r) * ld + (down ? M - 1 : M);
-        const double v = s_pV[side_r];
-        if (hasdense || p.store_all) p.In[off] = v;
-        if (p.has_saved) p.saved[off] = v;
-        p.I[off] = s_pI[side_r] + v;
-      }
-      __syncthreads();  // s_pV / s_pI / s_lk* of this stage have been read by everyone
-      if (lk_r >= 0) { s_lkv[lk_r][lk_c] = lk_val; s_lkk[lk_r][lk_c] = lk_k0; }
-      if (nx_have) { s_pI[side_r] = nx_I; s_pJ[side_r] = nx_J; }
-
-      // ---------------- write the finished tiles, refill the ring ----------------
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        const int c0 = down ? dcol0 : ucol0;
-        const bool lo = down && lowstrip;
-        if (hasdense || p.store_all) tma_store_3d(lo ? &p.lo_In : &p.map_In, smem_u32(Jt), c0, t0, s);
-        tma_store_3d(lo ? &p.lo_I : &p.map_I, smem_u32(It), c0, t0, s);
-        if (p.has_saved) tma_store_3d(lo ? &p.lo_S : &p.map_S, smem_u32(Jt), c0, t0, s);
-        bulk_commit();
-        if (q + NS - 1 < nseq) {
-          bulk_wait_read<1>();  // the stores of the previous step have read their buffer: it is the one refilled now
-          issue(q + NS - 1);
+      if (k == 0) {
+        // the mu = 0 column of this pass goes back with plain stores
+        if (side_thread && side_r < rows) {
+          const size_t off = (static_cast<size_t>(s) * L + t0 + side_r) * ld + (down ? M - 1 : M);
+          const double v = s_pV[side_r];
+          if (hasdense || p.store_all) p.In[off] = v;
+          if (p.has_saved) p.saved[off] = v;
+          p.I[off] = s_pI[side_r] + v;
         }
+        consumer_sync();  // s_pV / s_pI / s_lk* of this stage have been read by everyone
+        if (lk_r >= 0) { s_lkv[lk_r][lk_c] = lk_val; s_lkk[lk_r][lk_c] = lk_k0; }
+        if (nx_have) { s_pI[side_r] = nx_I; s_pJ[side_r] = nx_J; }
       }
     }
     seq += nseq;
   }
-  if (tid == 0) bulk_wait_read<0>();
+  if (tid == THREADS) bulk_wait_read<0>();
 }
 
 // Projections of a whole field (the first order, before the loop): proj[s][t][0][r] = sum_k I[t, k] Us[k][r], other slots 0.

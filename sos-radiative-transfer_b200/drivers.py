@@ -121,17 +121,30 @@ class BatchSolver:
         keys = {_group_key(s) for s in scenarios}
         if len(keys) != 1:
             raise ValueError("BatchSolver: scenarios must share nb_layers, nb_angles, aerosol rows and surface")
-        self.scenarios = list(scenarios)
-        L, M, self.idx_up, self.idx_down, surf = next(iter(keys))
+        self._key = next(iter(keys))
+        L, M, self.idx_up, self.idx_down, surf = self._key
         self.L, self.M, self.N = L, M, 2 * M
         self.mu = G.mu_grid(M)
-        phases = phases or _PHASES
+        self._phases = phases or _PHASES
+        self._device_phase = device_phase
+        self.z = G.aerosol_rows(scenarios[0].z0, scenarios[0].z_up, scenarios[0].z_down, L)[0]
+        self._mat_index, self._mats, self._mat_keys = {}, [], []
+        coefs = self._prepare(scenarios)
+        surface = {"specular": _lib.SURFACE_SPECULAR, "lambert": _lib.SURFACE_LAMBERT}[surf]
+        self.engine = SosEngine(self.mu, self.tau, coefs, [0, self.idx_up, self.idx_down + 1, L], surface,
+                                device=device, chunk_rows=chunk_rows, fold=fold)
+        self._register_phases()
+        self.I1 = None
+
+    def _prepare(self, scenarios):
+        """Host side of a batch: tau profiles, first-order coefficients, per-scenario scalars; phase functions met for
+        the first time are appended to self._mats (the caller registers them)."""
+        self.scenarios = list(scenarios)
+        L, M = self.L, self.M
         S = len(scenarios)
         tau = np.empty((S, L))
         coefs = []
         Ccoef = np.empty((S, 2, self.N))
-        mats, mat_index, mat_keys = [], {}, []
-        self.z = G.aerosol_rows(scenarios[0].z0, scenarios[0].z_up, scenarios[0].z_down, L)[0]
         # tau profiles of the whole batch at once: the same arithmetic as grid.tau_profile, element for element
         # (the group key fixes idx_up / idx_down for every scenario of the batch)
         rows = np.arange(L)
@@ -141,14 +154,16 @@ class BatchSolver:
         inside = (rows >= self.idx_up) & (rows <= self.idx_down)
         tau[:, inside] += (rows[inside] + 1 - self.idx_up)[None, :] * (t_aer / (self.idx_down + 1 - self.idx_up))[:, None]
         tau[:, rows > self.idx_down] += t_aer[:, None]
+        self._new_mats = 0
         for i, sc in enumerate(scenarios):
-            P0a, Pa, ka = phases.get(sc.atm_phase, M, self.mu, sc.mu0, need_P=not device_phase)
-            P0e, Pe, ke = phases.get(sc.aer_phase, M, self.mu, sc.mu0, need_P=not device_phase)
+            P0a, Pa, ka = self._phases.get(sc.atm_phase, M, self.mu, sc.mu0, need_P=not self._device_phase)
+            P0e, Pe, ke = self._phases.get(sc.aer_phase, M, self.mu, sc.mu0, need_P=not self._device_phase)
             for k, P in ((ka, Pa), (ke, Pe)):
-                if k not in mat_index:
-                    mat_index[k] = len(mats)
-                    mats.append(P)
-                    mat_keys.append(k if k[0] != "array" else None)  # analytic families are immutable: cache on device
+                if k not in self._mat_index:
+                    self._mat_index[k] = len(self._mats)
+                    self._mats.append(P)
+                    self._mat_keys.append(k if k[0] != "array" else None)  # analytic families are immutable: cache on device
+                    self._new_mats += 1
             # global mixing weights (SOS_Aer_main_specular.py:52-53; note dtau_atm = tauStar_atm / L, Q9)
             dtau_aer = sc.tauStar_aer / (self.idx_down + 1 - self.idx_up)
             dtau_atm = sc.tauStar_atm / L
@@ -162,21 +177,33 @@ class BatchSolver:
             coefs.append(ScenarioCoefficients(
                 mu0=sc.mu0, grd_alb=sc.grd_alb, tauStar_tot=sc.tauStar_atm + sc.tauStar_aer,
                 coef_atm=sc.alb_atm, coef_mix_atm=sc.alb_atm * f_atm, coef_mix_aer=sc.alb_aer * f_aer,
-                threshold=sc.threshold, phase_atm=mat_index[ka], phase_aer=mat_index[ke], extrap_width=widths))
+                threshold=sc.threshold, phase_atm=self._mat_index[ka], phase_aer=self._mat_index[ke], extrap_width=widths))
         self.tau = tau
         self.Ccoef = Ccoef
-        surface = {"specular": _lib.SURFACE_SPECULAR, "lambert": _lib.SURFACE_LAMBERT}[surf]
-        self.engine = SosEngine(self.mu, tau, coefs, [0, self.idx_up, self.idx_down + 1, L], surface,
-                                device=device, chunk_rows=chunk_rows, fold=fold)
-        if device_phase:
+        return coefs
+
+    def _register_phases(self):
+        mats = list(self._mats)
+        if self._device_phase:
             # analytic families: the N x N matrix is built on the device (sos_build_phase) unless its
             # contraction operand is already resident; only the cheap P0 vectors were built on the host
-            for i, k in enumerate(mat_keys):
+            for i, k in enumerate(self._mat_keys):
                 if k is not None and mats[i] is None:
-                    name, g = k[0], k[1]
-                    mats[i] = _DeviceBuilt(self.engine, name, g)
-        self.engine.set_phase(mats, keys=mat_keys)
-        self.I1 = None
+                    mats[i] = _DeviceBuilt(self.engine, k[0], k[1])
+        self.engine.set_phase(mats, keys=self._mat_keys)
+
+    def update(self, scenarios: Sequence[Scenario]):
+        """Feed the solver its next batch (same grid group, same number of scenarios): the plan, its device buffers and
+        the registered phase operands are kept (sos_plan_update); only tau, the per-scenario scalars and the first-order
+        coefficients change.  What a parameter sweep calls between batches instead of building a new BatchSolver."""
+        if len(scenarios) != len(self.scenarios) or {_group_key(s) for s in scenarios} != {self._key}:
+            raise ValueError("BatchSolver.update: the next batch must keep the grid group and the batch size")
+        coefs = self._prepare(scenarios)
+        if self._new_mats:
+            if len(self._mats) > 16:
+                raise ValueError("BatchSolver.update: more than 16 phase functions in one plan")
+            self._register_phases()          # a phase function met for the first time: register the larger operand set
+        self.engine.update(self.tau, coefs)
 
     def first_order(self):
         self.I1 = self.engine.first_order(self.Ccoef, out=self.I1)

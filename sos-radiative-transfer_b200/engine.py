@@ -102,6 +102,16 @@ class SosEngine:
         for i in range(4):
             g.region_start[i] = self.region_start[i] if i < len(self.region_start) else 0
         g.surface, g.ld, g.chunk_rows = surface, self.ld, chunk_rows
+        W = np.ascontiguousarray(G.extrapolation_tables(mu, self.M), dtype=np.float64)
+        self._plan = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_plan_create(C.byref(self._plan), C.byref(g), mu.ctypes.data, tau.ctypes.data,
+                                                self._scenario_array(scenarios), W.ctypes.data if W.size else None, int(W.size)),
+                       "sos_plan_create")
+        self._A = []          # device contraction matrices (keep alive)
+        self._bufs = {}
+
+    def _scenario_array(self, scenarios):
         sc = (_lib.sos_scenario * self.S)()
         for i, s in enumerate(scenarios):
             sc[i].mu0, sc[i].grd_alb, sc[i].tauStar_tot = s.mu0, s.grd_alb, s.tauStar_tot
@@ -110,14 +120,21 @@ class SosEngine:
             sc[i].phase_atm, sc[i].phase_aer = s.phase_atm, s.phase_aer
             for k in range(3):
                 sc[i].extrap_width[k] = int(s.extrap_width[k]) if k < len(s.extrap_width) else 0
-        W = np.ascontiguousarray(G.extrapolation_tables(mu, self.M), dtype=np.float64)
-        self._plan = C.c_void_p()
+        return sc
+
+    def update(self, tau, scenarios: Sequence[ScenarioCoefficients]):
+        """The next batch on the same grid (sos_plan_update): new tau profiles and per-scenario scalars, same phase
+        matrices; device buffers, tensor maps and operands are kept."""
+        tau = np.ascontiguousarray(np.atleast_2d(tau), dtype=np.float64)
+        if tau.shape != (self.S, self.L) or len(scenarios) != self.S:
+            raise ValueError("update: the batch must keep its shape (S scenarios x L layers)")
+        n = len(self._A)
+        if any(s.phase_atm >= n or s.phase_aer >= n for s in scenarios):
+            raise ValueError("update: scenario refers to a phase matrix that is not registered")
+        self.tau, self.scenarios = tau, list(scenarios)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.sos_plan_create(C.byref(self._plan), C.byref(g), mu.ctypes.data, tau.ctypes.data,
-                                                sc, W.ctypes.data if W.size else None, int(W.size)),
-                       "sos_plan_create")
-        self._A = []          # device contraction matrices (keep alive)
-        self._bufs = {}
+            _lib.check(self.lib.sos_plan_update(self._plan, tau.ctypes.data, self._scenario_array(scenarios), self._stream),
+                       "sos_plan_update")
 
     # ------------------------------------------------------------------ plumbing
     def close(self):

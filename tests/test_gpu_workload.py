@@ -133,15 +133,15 @@ def _solve_both(sos, scs, monkeypatch, keep=0, **kw):
 
 
 @pytest.mark.parametrize("surface", ["specular", "lambert"])
-@pytest.mark.parametrize("L,M", [(96, 251), (130, 501), (77, 64), (64, 1201), (203, 300)])
+@pytest.mark.parametrize("L,M", [(96, 251), (130, 501), (77, 100), (60, 128), (64, 1201), (203, 300)])
 def test_fused_order_kernel_equals_chunked_scan(sos, so, monkeypatch, surface, L, M):
     """Same batches through csrc/strip.cuh and csrc/sweep.cuh: ragged L (partial last stage) and M (partial strips,
-    one strip only, nine strips), Taylor + windowed columns (M = 1201), all extrapolation widths, dense and generated
+    one strip only, even and odd M, ten strips), Taylor + windowed columns (M = 1201), all extrapolation widths, dense and generated
     source rows, every order compared; one member also against the oracle."""
     aer = (("hg", 0.5), ("fwc", 0.0), ("hg", 0.8))
     scs = [sos.Scenario(nb_layers=L, nb_angles=M, mu0=(0.5, 0.23, 0.9, 1.0)[i % 4], tauStar_atm=(0.124, 0.05, 0.6, 0.3)[i % 4],
-                        tauStar_aer=(0.12, 0.0, 0.9, 2.2)[i % 4], alb_aer=(0.97, 1.0, 0.8, 0.9)[i % 4], alb_atm=(1.0, 1.0, 0.9, 1.0)[i % 4],
-                        grd_alb=(0.15, 0.0, 0.3, 0.8)[i % 4], atm_phase=("rayleigh", 0.0), aer_phase=aer[i % 3], surface=surface)
+                        tauStar_aer=(0.12, 0.0, 0.9, 1.2)[i % 4], alb_aer=(0.97, 1.0, 0.8, 0.85)[i % 4], alb_atm=(1.0, 1.0, 0.9, 1.0)[i % 4],
+                        grd_alb=(0.15, 0.0, 0.3, 0.5)[i % 4], atm_phase=("rayleigh", 0.0), aer_phase=aer[i % 3], surface=surface)
            for i in range(7)]
     keep = 4
     a, b = _solve_both(sos, scs, monkeypatch, keep=keep)
