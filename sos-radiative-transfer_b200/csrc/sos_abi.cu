@@ -17,7 +17,7 @@
 #include "phase.cuh"
 #include "quadrature.cuh"
 #include "sweep.cuh"
-#include "strip.cuh"
+#include "colscan.cuh"
 
 namespace {
 
@@ -152,23 +152,21 @@ struct sos_plan {
   int lowrank_ldr = 0;
   int n_lowrank_groups = 0;
   int lowrank_rp = 4;
-  // fused single-pass order kernel (strip.cuh): used by sos_solve for batches
-  bool strip_ok = false;        // the plan qualifies (batch size, zone inside one strip, ...)
-  bool strip_disabled = false;  // a blend left the strip zone at run time: chunked kernels from now on
-  bool strip_zone_ok = true;    // (sos_plan_update) the new batch's extrapolation widths still fit strip 0
-  int strip_nstrips = 0, strip_nslots = 0, strip_nsc = 0, strip_Lp = 0, strip_grid = 0;
-  double* d_tau_pad = nullptr;
+  // fused single-pass order kernels (colscan.cuh): used by sos_solve for batches
+  bool strip_ok = false;        // the plan qualifies (batch size, small columns, ...)
+  bool strip_disabled = false;  // a blend left the up zone at run time: chunked kernels from now on
+  bool strip_zone_ok = true;    // (sos_plan_update) the new batch still qualifies
+  int col_nbd = 0, col_nbu = 0, col_nslots = 0, col_nsc = 0, col_Lp = 0, col_zlo = 0, col_ue = 0, col_zu_end = 0;
+  double* d_dtd = nullptr;      // [S][Lp] tau[t] - tau[t-1]
+  double* d_dtu = nullptr;      // [S][Lp] tau[t+1] - tau[t]
   int* d_k0tab = nullptr;
   double* d_dhist = nullptr;
-  double* d_proj[2] = {nullptr, nullptr};
-  double* d_ratio_part = nullptr;
-  double* d_lam_part = nullptr;
-  unsigned* d_lam_flag = nullptr;
+  double* d_proj = nullptr;     // [S][L][nslots][2]
+  double* d_cj[2] = {nullptr, nullptr};  // [S][Lp][2] generated-source coefficients, ping-pong over the orders
+  double* d_lam = nullptr;      // [S] Lambert seeds
   int* d_strip_ticket = nullptr;
   const double** d_Ut_tab = nullptr;
   int* d_rank_tab = nullptr;
-  unsigned strip_epoch = 0;
-  std::map<const void*, std::pair<CUtensorMap, CUtensorMap>> map3_cache;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -299,38 +297,40 @@ int plan_tiles(sos_plan* p, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused single-pass order kernel (strip.cuh): plan-side tables
+// fused single-pass order kernels (colscan.cuh): plan-side tables
 // ---------------------------------------------------------------------------------------------
-constexpr int kStripR = 8;
-
 int strip_env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   return (e && *e) ? std::atoi(e) : dflt;
 }
 
-int strip_padded_rows(int L) { return ((L + kStripR - 1) / kStripR * kStripR + 1) / 2 * 2; }
-
-// zone test of the strip kernel: strip 0 must hold every column the reference treats specially next to mu = 0-
-bool strip_zone_fits(const GridDev& g, const sos_scenario* scen_h) {
-  const int M = g.M, o = M & 1;
+// first downward column of the zone: every column the reference treats specially next to mu = 0-, the extrapolation
+// targets and their sources, over all scenarios of the batch; even (16-byte pairs)
+int col_zone_lo(const GridDev& g, const sos_scenario* scen_h) {
+  const int M = g.M;
   int wmax = 0;
   for (int s = 0; s < g.S; ++s)
     for (int k = 0; k < g.nreg; ++k) wmax = std::max(wmax, scen_h[s].extrap_width[k]);
   const int ns = (wmax <= 0) ? 0 : (wmax < 2 ? 2 : std::min(5, wmax));
   const int zl = std::max(0, std::min(g.first_small, M - wmax - ns));
-  return zl >= M - o - sosstrip::W && M >= 8;
+  return zl & ~1;
 }
 
-// tau padded to whole stages, and the first row k0 of every window tau' >= tau_t - 5|mu| inside its region, with the
-// reference's rounding (two operations, SOS_Aer_In_limit.py:96-100)
-void strip_tables(const GridDev& g, const double* mu_h, const double* tau_h, int nsc, int Lp, std::vector<double>& tau_pad,
-                  std::vector<int>& k0tab) {
+// tau differences of the two passes, padded with zeros to whole row groups, and the first row k0 of every window
+// tau' >= tau_t - 5|mu| inside its region, with the reference's rounding (two operations, SOS_Aer_In_limit.py:96-100)
+void col_tables(const GridDev& g, const double* mu_h, const double* tau_h, int nsc, int Lp, std::vector<double>& dtd,
+                std::vector<double>& dtu, std::vector<int>& k0tab) {
   const int L = g.L, S = g.S;
-  tau_pad.resize(static_cast<size_t>(S) * Lp);
+  dtd.assign(static_cast<size_t>(S) * Lp, 0.0);
+  dtu.assign(static_cast<size_t>(S) * Lp, 0.0);
   k0tab.assign(static_cast<size_t>(S) * L * std::max(nsc, 1), 0);
   for (int s = 0; s < S; ++s) {
     const double* tau = tau_h + static_cast<size_t>(s) * L;
-    for (int t = 0; t < Lp; ++t) tau_pad[static_cast<size_t>(s) * Lp + t] = tau[std::min(t, L - 1)];
+    for (int t = 1; t < L; ++t) {
+      const double d = tau[t] - tau[t - 1];
+      dtd[static_cast<size_t>(s) * Lp + t] = d;
+      dtu[static_cast<size_t>(s) * Lp + t - 1] = d;
+    }
     for (int c = 0; c < nsc; ++c) {
       const double amu = std::fabs(mu_h[g.first_small + c]);
       const volatile double five_mu = 5.0 * amu;
@@ -346,46 +346,52 @@ void strip_tables(const GridDev& g, const double* mu_h, const double* tau_h, int
   }
 }
 
-// Decide whether the plan qualifies for the strip kernel and build its tables.  Not qualifying is not an error.
+// Decide whether the plan qualifies for the fused order kernels and build their tables.  Not qualifying is not an error.
 int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_scenario* scen_h) {
-  using namespace sosstrip;
+  using namespace soscol;
   const GridDev& g = p->dev;
-  const int L = g.L, M = g.M, S = g.S;
+  const int L = g.L, M = g.M, N = g.N, S = g.S;
   p->strip_ok = false;
   if (strip_env_int("SOS_B200_STRIP", 1) == 0) return SOS_OK;
-  const int o = M & 1;  // odd M: the strips stop one column short of mu = 0 (TMA boxes must start on even columns)
-  const int nstrips = (M - o + W - 1) / W;
-  if (nstrips > MAX_STRIPS) return SOS_OK;
-  // enough strips to fill the chip without cutting the layer axis (smaller batches keep the chunked scan)
-  if (static_cast<long long>(S) * nstrips < strip_env_int("SOS_B200_STRIP_MIN", 48)) return SOS_OK;
+  if (M < 8 || (g.ld & 1)) return SOS_OK;
+  const int ue = M + (M & 1);                      // first even column above mu = 0+ (16-byte pairs)
+  const int nbd = (M - 1 + BCOLS - 1) / BCOLS;     // downward columns 0 .. M-2
+  const int nbu = (N - ue + BCOLS - 1) / BCOLS;    // upward columns ue .. N-1
+  // enough warps to fill the chip without cutting the layer axis (smaller batches keep the chunked scan)
+  if (static_cast<long long>(S) * nbd < strip_env_int("SOS_B200_STRIP_MIN", 48)) return SOS_OK;
   const int nsc = (M - 1) - g.first_small;
   if (nsc > MAX_SMALL) return SOS_OK;
-  if (!strip_zone_fits(g, scen_h)) return SOS_OK;
-  const int Lp = strip_padded_rows(L);
-  std::vector<double> tau_pad;
+  const int Lp = ((L + RG - 1) / RG + 1) * RG;
+  std::vector<double> dtd, dtu;
   std::vector<int> k0tab;
-  strip_tables(g, mu_h, tau_h, nsc, Lp, tau_pad, k0tab);
+  col_tables(g, mu_h, tau_h, nsc, Lp, dtd, dtu, k0tab);
   int r;
-  if ((r = dev_upload(p, const_cast<const double**>(&p->d_tau_pad), tau_pad.data(), tau_pad.size()))) return r;
+  if ((r = dev_upload(p, const_cast<const double**>(&p->d_dtd), dtd.data(), dtd.size()))) return r;
+  if ((r = dev_upload(p, const_cast<const double**>(&p->d_dtu), dtu.data(), dtu.size()))) return r;
   if ((r = dev_upload(p, const_cast<const int**>(&p->d_k0tab), k0tab.data(), k0tab.size()))) return r;
-  const int nslots = 2 * nstrips * sosstrip::PROJ_WARPS;  // one projection slot per strip, half and warp
+  const int nslots = (nbd + nbu) * WARPS + 1;  // one projection slot per warp of either pass + the down zone's
   if ((r = dev_alloc(p, &p->d_dhist, static_cast<size_t>(S) * L * MAX_SMALL))) return r;
+  if ((r = dev_alloc(p, &p->d_proj, static_cast<size_t>(S) * L * nslots * 2))) return r;
   for (int i = 0; i < 2; ++i)
-    if ((r = dev_alloc(p, &p->d_proj[i], static_cast<size_t>(S) * L * nslots * 2))) return r;
-  if ((r = dev_alloc(p, &p->d_ratio_part, static_cast<size_t>(S) * nstrips * 2))) return r;
-  if ((r = dev_alloc(p, &p->d_lam_part, static_cast<size_t>(S) * nstrips))) return r;
-  if ((r = dev_alloc(p, &p->d_lam_flag, static_cast<size_t>(S) * nstrips))) return r;
+    if ((r = dev_alloc(p, &p->d_cj[i], static_cast<size_t>(S) * Lp * 2))) return r;
+  if ((r = dev_alloc(p, &p->d_lam, static_cast<size_t>(S)))) return r;
   if ((r = dev_alloc(p, &p->d_strip_ticket, 1))) return r;
   if ((r = dev_alloc(p, &p->d_Ut_tab, SOS_MAX_PHASE))) return r;
   if ((r = dev_alloc(p, &p->d_rank_tab, SOS_MAX_PHASE))) return r;
-  SOS_CUDA(cudaMemset(p->d_lam_flag, 0, sizeof(unsigned) * S * nstrips));
   SOS_CUDA(cudaMemset(p->d_strip_ticket, 0, sizeof(int)));
   SOS_CUDA(cudaMemset(p->d_dhist, 0, sizeof(double) * S * L * MAX_SMALL));
+  SOS_CUDA(cudaMemset(p->d_proj, 0, sizeof(double) * S * L * nslots * 2));
+  for (int i = 0; i < 2; ++i) SOS_CUDA(cudaMemset(p->d_cj[i], 0, sizeof(double) * S * Lp * 2));
+  SOS_CUDA(cudaMemset(p->d_lam, 0, sizeof(double) * S));
   SOS_CUDA(cudaMemset(p->d_rank_tab, 0, sizeof(int) * SOS_MAX_PHASE));
-  p->strip_nstrips = nstrips;
-  p->strip_nslots = nslots;
-  p->strip_nsc = nsc;
-  p->strip_Lp = Lp;
+  p->col_nbd = nbd;
+  p->col_nbu = nbu;
+  p->col_nslots = nslots;
+  p->col_nsc = nsc;
+  p->col_Lp = Lp;
+  p->col_ue = ue;
+  p->col_zu_end = std::min(ue + BCOLS, N);
+  p->col_zlo = col_zone_lo(g, scen_h);
   p->strip_ok = true;
   return SOS_OK;
 }
@@ -451,53 +457,6 @@ int validate_scenarios(const sos_grid& grid, const sos_scenario* scen_h) {
     if (scen_h[s].phase_atm < 0 || scen_h[s].phase_atm >= SOS_MAX_PHASE || scen_h[s].phase_aer < 0 || scen_h[s].phase_aer >= SOS_MAX_PHASE)
       return SOS_ERR_INVALID;
   }
-  return SOS_OK;
-}
-
-template <int NS>
-int strip_launch_cfg(sos_plan* p, const sosstrip::StripParams& sp, cudaStream_t st) {
-  using namespace sosstrip;
-  const int smem = strip_smem_bytes<kStripR, NS>(sp.nslots);
-  static int configured_smem[64] = {0};  // per device: function attributes belong to the device's context
-  int& have = configured_smem[p->device & 63];
-  if (smem > have) {
-    if (cudaFuncSetAttribute(order_strip_kernel<kStripR, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-      g_last_cuda_error = "strip kernel: shared memory request refused";
-      return SOS_ERR_CUDA;
-    }
-    have = smem;
-  }
-  if (p->strip_grid == 0) {
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, order_strip_kernel<kStripR, NS>, CTA_THREADS, smem);
-    p->strip_grid = std::max(1, occ) * p->n_sms;
-    if (strip_env_int("SOS_B200_STRIP_DEBUG", 0))
-      std::fprintf(stderr, "[sos_b200] order_strip_kernel<%d,%d>: %d B dynamic smem, %d CTAs/SM, grid %d, %d strips x %d scenarios\n", kStripR, NS,
-                   smem, occ, p->strip_grid, sp.nstrips, p->dev.S);
-  }
-  const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(p->dev.S) * sp.nstrips, p->strip_grid));
-  order_strip_kernel<kStripR, NS><<<std::max(grid, sp.nstrips), CTA_THREADS, smem, st>>>(sp);
-  return launch_check(p, "order_strip_kernel");
-}
-
-// 3-D tensor maps [S][L][N] of a field for the strip kernel: the whole field, and the field cut off after the columns of
-// the strip at the mu = -1 end (a bulk store must not start at a negative column, so that strip starts at column 0)
-int strip_field_map(sos_plan* p, const void* base, CUtensorMap* out, CUtensorMap* out_lo) {
-  auto it = p->map3_cache.find(base);
-  if (it == p->map3_cache.end()) {
-    const GridDev& g = p->dev;
-    const int o = g.M & 1;
-    const int lo_cols = std::max(2, g.M - o - sosstrip::W * (p->strip_nstrips - 1));
-    std::pair<CUtensorMap, CUtensorMap> m;
-    int r = encode_3d(&m.first, base, g.N, g.L, g.S, g.ld, sosstrip::W, kStripR);
-    if (r) return r;
-    r = encode_3d(&m.second, base, lo_cols, g.L, g.S, g.ld, sosstrip::W, kStripR);
-    if (r) return r;
-    if (p->map3_cache.size() > 64) p->map3_cache.clear();
-    it = p->map3_cache.emplace(base, m).first;
-  }
-  *out = it->second.first;
-  *out_lo = it->second.second;
   return SOS_OK;
 }
 
@@ -814,16 +773,16 @@ int sos_plan_update(sos_plan* p, const double* tau_h, const sos_scenario* scen_h
   std::vector<ScenState> state(S);
   for (int s = 0; s < S; ++s) { state[s].ratio_toa = 1; state[s].ratio_surf = 1; state[s].n_orders = 1; state[s].active = 1; state[s].status = 0; state[s].pad = 0; }
   SOS_CUDA(cudaMemcpyAsync(g.state, state.data(), sizeof(ScenState) * S, cudaMemcpyHostToDevice, st));
-  std::vector<double> tau_pad;
+  std::vector<double> dtd, dtu;
   std::vector<int> k0tab;
   if (p->strip_ok) {
-    p->strip_zone_ok = strip_zone_fits(g, patched.data());
-    if (p->strip_zone_ok) {
-      strip_tables(g, p->mu_h.data(), tau_h, p->strip_nsc, p->strip_Lp, tau_pad, k0tab);
-      SOS_CUDA(cudaMemcpyAsync(p->d_tau_pad, tau_pad.data(), tau_pad.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-      SOS_CUDA(cudaMemcpyAsync(p->d_k0tab, k0tab.data(), k0tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    }
-    p->strip_disabled = false;  // a new batch gets the fused kernel again
+    p->strip_zone_ok = true;
+    p->col_zlo = col_zone_lo(g, patched.data());
+    col_tables(g, p->mu_h.data(), tau_h, p->col_nsc, p->col_Lp, dtd, dtu, k0tab);
+    SOS_CUDA(cudaMemcpyAsync(p->d_dtd, dtd.data(), dtd.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SOS_CUDA(cudaMemcpyAsync(p->d_dtu, dtu.data(), dtu.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SOS_CUDA(cudaMemcpyAsync(p->d_k0tab, k0tab.data(), k0tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    p->strip_disabled = false;  // a new batch gets the fused kernels again
   }
   SOS_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
   sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev, p->d_strip_ticket);
@@ -1493,53 +1452,73 @@ static bool strip_generates(const sos_plan* p) {
   return true;
 }
 
-// one order on the strip kernel: J (dense rows) / projections of I_{n-1} (generated rows) -> I_n, I, projections of I_n
+// one order on the fused kernels: J (dense rows) / source coefficients of order n (generated rows) -> I_n, I, the
+// coefficients of order n + 1: down columns, down zone rows (+ surface seeds), up columns, up zone rows
 static int strip_order(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, int n, bool gen, cudaStream_t st) {
-  using namespace sosstrip;
-  StripParams sp;
-  std::memset(&sp, 0, sizeof(sp));
-  sp.g = p->dev;
-  int r;
-  if ((r = strip_field_map(p, J_d, &sp.map_J, &sp.lo_J))) return r;
-  if ((r = strip_field_map(p, In_d, &sp.map_In, &sp.lo_In))) return r;
-  if ((r = strip_field_map(p, I_d, &sp.map_I, &sp.lo_I))) return r;
-  sp.map_S = sp.map_I;
-  sp.lo_S = sp.lo_I;
-  if (saved_d && (r = strip_field_map(p, saved_d, &sp.map_S, &sp.lo_S))) return r;
-  sp.J = J_d;
-  sp.In = In_d;
-  sp.I = I_d;
-  sp.saved = saved_d;
-  sp.tau_pad = p->d_tau_pad;
-  sp.Lp = p->strip_Lp;
-  sp.active = p->dev.active_flat;
-  sp.ticket = p->d_strip_ticket;
-  sp.nstrips = p->strip_nstrips;
-  sp.nslots = p->strip_nslots;
-  sp.has_saved = saved_d ? 1 : 0;
-  sp.store_all = strip_env_int("SOS_B200_STRIP_STORE_ALL", 0);
+  using namespace soscol;
+  const GridDev& g = p->dev;
+  static int configured[64] = {0};  // per device: function attributes belong to the device's context
+  if (!configured[p->device & 63]) {
+    if (cudaFuncSetAttribute(column_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(column_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM) != cudaSuccess) {
+      g_last_cuda_error = "column_scan_kernel: shared memory request refused";
+      return SOS_ERR_CUDA;
+    }
+    configured[p->device & 63] = 1;
+  }
+  ColParams cp;
+  std::memset(&cp, 0, sizeof(cp));
+  cp.g = g;
+  cp.J = J_d; cp.In = In_d; cp.I = I_d; cp.saved = saved_d;
+  cp.cj = p->d_cj[n & 1];
+  cp.Lp = p->col_Lp;
+  cp.proj = p->d_proj;
+  cp.nslots = p->col_nslots;
+  cp.zlo = p->col_zlo;
+  cp.zu_end = p->col_zu_end;
+  cp.gen = gen ? 1 : 0;
+  cp.store_all = strip_env_int("SOS_B200_STRIP_STORE_ALL", 0);
+  ZoneParams zp;
+  std::memset(&zp, 0, sizeof(zp));
   for (int i = 0; i < SOS_MAX_PHASE; ++i) {
-    sp.rank[i] = gen ? p->lowrank_rank[i] : 0;
-    sp.Ut[i] = p->lowrank_Ut[i];
-    sp.Vt[i] = p->lowrank_Vt[i];
+    cp.rank[i] = zp.rank[i] = gen ? p->lowrank_rank[i] : 0;
+    cp.Ut[i] = zp.Ut[i] = p->lowrank_Ut[i];
   }
-  sp.ldr = p->lowrank_ldr;
-  sp.proj_in = p->d_proj[n & 1];
-  sp.proj_out = p->d_proj[(n + 1) & 1];
-  sp.ratio_part = p->d_ratio_part;
-  sp.lam_part = p->d_lam_part;
-  sp.lam_flag = p->d_lam_flag;
-  sp.epoch = ++p->strip_epoch;
-  sp.dhist = p->d_dhist;
-  sp.k0tab = p->d_k0tab;
-  sp.nsc = p->strip_nsc;
+  cp.ldr = zp.ldr = p->lowrank_ldr;
+  cp.dhist = p->d_dhist;
+  cp.lam = p->d_lam;
+  zp.g = g;
+  zp.J = J_d; zp.In = In_d; zp.I = I_d; zp.saved = saved_d;
+  zp.cj_in = p->d_cj[n & 1];
+  zp.cj_out = p->d_cj[(n + 1) & 1];
+  zp.Lp = p->col_Lp;
+  zp.proj = p->d_proj;
+  zp.nslots = p->col_nslots;
+  zp.zone_slot = p->col_nslots - 1;
+  zp.zlo = p->col_zlo;
+  zp.zu_end = p->col_zu_end;
+  zp.gen = cp.gen;
+  zp.dhist = p->d_dhist;
+  zp.k0tab = p->d_k0tab;
+  zp.nsc = p->col_nsc;
+  zp.lam = p->d_lam;
+  zp.zone_buf = g.M - p->col_zlo;
+  const size_t zsmem = static_cast<size_t>(zp.zone_buf) * ZONE_ROWS * sizeof(double);
+  if (zsmem > 200 * 1024) return SOS_ERR_UNSUPPORTED;
+  if (zsmem > 48 * 1024) cudaFuncSetAttribute(zone_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zsmem));
+  const dim3 zgrid((g.L + ZONE_ROWS - 1) / ZONE_ROWS, g.S);
   ProfSpan span(p, 1, st);
-  switch (strip_env_int("SOS_B200_STRIP_STAGES", 4)) {
-    case 3: return strip_launch_cfg<3>(p, sp, st);
-    case 5: return strip_launch_cfg<5>(p, sp, st);
-    case 6: return strip_launch_cfg<6>(p, sp, st);
-    default: return strip_launch_cfg<4>(p, sp, st);
-  }
+  int r;
+  cp.dt = p->d_dtd; cp.nblocks = p->col_nbd; cp.col_first = 0; cp.slot0 = 0;
+  column_scan_kernel<false><<<g.S * p->col_nbd, THREADS, CTA_SMEM, st>>>(cp);
+  if ((r = launch_check(p, "column_scan_kernel<down>"))) return r;
+  zone_rows_kernel<false><<<zgrid, 32 * ZONE_ROWS, zsmem, st>>>(zp);
+  if ((r = launch_check(p, "zone_rows_kernel<down>"))) return r;
+  cp.dt = p->d_dtu; cp.nblocks = p->col_nbu; cp.col_first = p->col_ue; cp.slot0 = p->col_nbd * WARPS;
+  column_scan_kernel<true><<<g.S * p->col_nbu, THREADS, CTA_SMEM, st>>>(cp);
+  if ((r = launch_check(p, "column_scan_kernel<up>"))) return r;
+  zone_rows_kernel<true><<<zgrid, 32 * ZONE_ROWS, 0, st>>>(zp);
+  return launch_check(p, "zone_rows_kernel<up>");
 }
 
 int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* orders_d, int max_saved, int max_orders,
@@ -1563,8 +1542,8 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
     SOS_CUDA(cudaMemcpyAsync(p->d_rank_tab, p->lowrank_rank, sizeof(int) * SOS_MAX_PHASE, cudaMemcpyHostToDevice, st));
     SOS_CUDA(cudaStreamSynchronize(st));  // (ut lives on this stack frame)
     dim3 pg((g.L + 7) / 8, g.S);
-    sosstrip::strip_project_kernel<<<pg, 256, 0, st>>>(g, In_d, p->d_Ut_tab, p->d_rank_tab, p->lowrank_ldr, p->strip_nslots, p->d_proj[0]);
-    r = launch_check(p, "strip_project_kernel");
+    soscol::project_rows_kernel<<<pg, 256, 0, st>>>(g, In_d, p->d_Ut_tab, p->d_rank_tab, p->lowrank_ldr, p->col_Lp, p->d_cj[0]);
+    r = launch_check(p, "project_rows_kernel");
     if (r) return r;
   }
   // The host never blocks inside the loop: after every order the device-side "still active" counter
@@ -1585,7 +1564,7 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
     if (strip) {
       rc = strip_order(p, J_d, In_d, I_d, saved, n, gen, st);
       if (rc) break;
-      sossweep::converge_kernel<<<1, 256, 0, st>>>(p->dev, n, p->d_order, p->d_ratio_part, p->strip_nstrips, p->d_strip_ticket);
+      sossweep::converge_kernel<<<1, 256, 0, st>>>(p->dev, n, p->d_order, nullptr, 0, p->d_strip_ticket);
       rc = launch_check(p);
       if (rc) break;
       rc = plan_tiles(p, st);
