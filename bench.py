@@ -366,8 +366,8 @@ def main():
     clocks = sampler.stop(t_begin, t_end)
     launches = eng.launches - l0
     import ctypes as C
-    ms2 = (C.c_double * 2)()
-    sp2 = (C.c_longlong * 2)()
+    ms2 = (C.c_double * 4)()
+    sp2 = (C.c_longlong * 4)()
     lib.sos_get_profile(eng._plan, ms2, sp2, None)
     lib.sos_set_profiling(eng._plan, 0)
     step_ms = float(np.mean([ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]))

@@ -257,10 +257,13 @@ int sos_plan_set_columns(sos_plan* plan, int col0, int col1);
  * device buffer [S][2]: sharded ranks MAX-all-reduce them between sos_sweeps and sos_converge. */
 int sos_state_ratios(sos_plan* plan, double* buf_d, int set, void* stream);
 
-/* Optional timing of the two kernel classes with CUDA events on the launching stream:
- * class 0 = source contraction (one launch per span), class 1 = layer sweeps (three launches per
- * span).  sos_get_profile synchronises the stream, returns accumulated milliseconds and span counts
- * in ms[2] / spans[2] and clears the accumulators. */
+/* Optional timing of kernel classes with CUDA events on the launching stream:
+ * class 0 = source contraction (all its launches of one order per span), class 1 = layer sweeps (four launches per
+ * span), class 2 = the apply pass of the sweeps alone (the HBM-bound kernel; nested inside class 1), class 3 = the
+ * dense DMMA kernel of the contraction alone (nested inside class 0).  sos_get_profile synchronises the stream,
+ * returns accumulated milliseconds and span counts in ms[SOS_PROFILE_CLASSES] / spans[SOS_PROFILE_CLASSES] and clears
+ * the accumulators. */
+#define SOS_PROFILE_CLASSES 4
 int sos_set_profiling(sos_plan* plan, int enabled);
 int sos_get_profile(sos_plan* plan, double* ms, long long* spans, void* stream);
 

@@ -17,7 +17,6 @@
 #include "phase.cuh"
 #include "quadrature.cuh"
 #include "sweep.cuh"
-#include "colscan.cuh"
 
 namespace {
 
@@ -152,21 +151,13 @@ struct sos_plan {
   int lowrank_ldr = 0;
   int n_lowrank_groups = 0;
   int lowrank_rp = 4;
-  // fused single-pass order kernels (colscan.cuh): used by sos_solve for batches
-  bool strip_ok = false;        // the plan qualifies (batch size, small columns, ...)
-  bool strip_disabled = false;  // a blend left the up zone at run time: chunked kernels from now on
-  bool strip_zone_ok = true;    // (sos_plan_update) the new batch still qualifies
-  int col_nbd = 0, col_nbu = 0, col_nslots = 0, col_nsc = 0, col_Lp = 0, col_zlo = 0, col_ue = 0, col_zu_end = 0;
-  double* d_dtd = nullptr;      // [S][Lp] tau[t] - tau[t-1]
-  double* d_dtu = nullptr;      // [S][Lp] tau[t+1] - tau[t]
-  int* d_k0tab = nullptr;
-  double* d_dhist = nullptr;
+  // generated source inside sos_solve (sweep.cuh: SrcGen): the molecular rows never materialise J or I_n
+  bool strip_ok = false;        // buffers exist (SOS_B200_STRIP=0 disables)
+  bool strip_disabled = false;  // a blend left the zone columns at run time: every row is read / stored from now on
+  int gen_nslots = 0, gen_zlo = 0, gen_zu_end = 0;
   double* d_proj = nullptr;     // [S][L][nslots][2]
-  double* d_cj[2] = {nullptr, nullptr};  // [S][Lp][2] generated-source coefficients, ping-pong over the orders
-  double* d_lam = nullptr;      // [S] Lambert seeds
+  double* d_cj[2] = {nullptr, nullptr};  // [S][L][2] source coefficients, ping-pong over the orders
   int* d_strip_ticket = nullptr;
-  const double** d_Ut_tab = nullptr;
-  int* d_rank_tab = nullptr;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -297,7 +288,7 @@ int plan_tiles(sos_plan* p, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused single-pass order kernels (colscan.cuh): plan-side tables
+// generated source (sweep.cuh: SrcGen): plan-side buffers
 // ---------------------------------------------------------------------------------------------
 int strip_env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
@@ -305,93 +296,34 @@ int strip_env_int(const char* name, int dflt) {
 }
 
 // first downward column of the zone: every column the reference treats specially next to mu = 0-, the extrapolation
-// targets and their sources, over all scenarios of the batch; even (16-byte pairs)
-int col_zone_lo(const GridDev& g, const sos_scenario* scen_h) {
+// targets and their sources, over all scenarios of the batch
+int gen_zone_lo(const GridDev& g, const sos_scenario* scen_h) {
   const int M = g.M;
   int wmax = 0;
   for (int s = 0; s < g.S; ++s)
     for (int k = 0; k < g.nreg; ++k) wmax = std::max(wmax, scen_h[s].extrap_width[k]);
   const int ns = (wmax <= 0) ? 0 : (wmax < 2 ? 2 : std::min(5, wmax));
-  const int zl = std::max(0, std::min(g.first_small, M - wmax - ns));
-  return zl & ~1;
+  return std::max(0, std::min(g.first_small, M - wmax - ns));
 }
 
-// tau differences of the two passes, padded with zeros to whole row groups, and the first row k0 of every window
-// tau' >= tau_t - 5|mu| inside its region, with the reference's rounding (two operations, SOS_Aer_In_limit.py:96-100)
-void col_tables(const GridDev& g, const double* mu_h, const double* tau_h, int nsc, int Lp, std::vector<double>& dtd,
-                std::vector<double>& dtu, std::vector<int>& k0tab) {
-  const int L = g.L, S = g.S;
-  dtd.assign(static_cast<size_t>(S) * Lp, 0.0);
-  dtu.assign(static_cast<size_t>(S) * Lp, 0.0);
-  k0tab.assign(static_cast<size_t>(S) * L * std::max(nsc, 1), 0);
-  for (int s = 0; s < S; ++s) {
-    const double* tau = tau_h + static_cast<size_t>(s) * L;
-    for (int t = 1; t < L; ++t) {
-      const double d = tau[t] - tau[t - 1];
-      dtd[static_cast<size_t>(s) * Lp + t] = d;
-      dtu[static_cast<size_t>(s) * Lp + t - 1] = d;
-    }
-    for (int c = 0; c < nsc; ++c) {
-      const double amu = std::fabs(mu_h[g.first_small + c]);
-      const volatile double five_mu = 5.0 * amu;
-      for (int k = 0; k < g.nreg; ++k) {
-        int k0 = g.rstart[k];
-        for (int t = g.rstart[k]; t < g.rstart[k + 1]; ++t) {
-          const volatile double lim = tau[t] - five_mu;
-          while (k0 < t && tau[k0] < lim) ++k0;
-          k0tab[(static_cast<size_t>(s) * L + t) * nsc + c] = k0;
-        }
-      }
-    }
-  }
-}
+constexpr int kGenUpZone = 128;  // upward columns next to mu = 0+ whose raw I_n is kept for the find-first blend
 
-// Decide whether the plan qualifies for the fused order kernels and build their tables.  Not qualifying is not an error.
-int strip_setup(sos_plan* p, const double* mu_h, const double* tau_h, const sos_scenario* scen_h) {
-  using namespace soscol;
+int strip_setup(sos_plan* p, const sos_scenario* scen_h) {
   const GridDev& g = p->dev;
   const int L = g.L, M = g.M, N = g.N, S = g.S;
   p->strip_ok = false;
   if (strip_env_int("SOS_B200_STRIP", 1) == 0) return SOS_OK;
-  if (M < 8 || (g.ld & 1)) return SOS_OK;
-  const int ue = M + (M & 1);                      // first even column above mu = 0+ (16-byte pairs)
-  const int nbd = (M - 1 + BCOLS - 1) / BCOLS;     // downward columns 0 .. M-2
-  const int nbu = (N - ue + BCOLS - 1) / BCOLS;    // upward columns ue .. N-1
-  // enough warps to fill the chip without cutting the layer axis (smaller batches keep the chunked scan)
-  if (static_cast<long long>(S) * nbd < strip_env_int("SOS_B200_STRIP_MIN", 48)) return SOS_OK;
-  const int nsc = (M - 1) - g.first_small;
-  if (nsc > MAX_SMALL) return SOS_OK;
-  const int Lp = ((L + RG - 1) / RG + 1) * RG;
-  std::vector<double> dtd, dtu;
-  std::vector<int> k0tab;
-  col_tables(g, mu_h, tau_h, nsc, Lp, dtd, dtu, k0tab);
+  const int T = sossweep::LOCAL_THREADS;
+  const int nslots = ((M - 1 + T - 1) / T + (N - M - 1 + T - 1) / T) * (T / 32);  // one per warp of the apply pass
   int r;
-  if ((r = dev_upload(p, const_cast<const double**>(&p->d_dtd), dtd.data(), dtd.size()))) return r;
-  if ((r = dev_upload(p, const_cast<const double**>(&p->d_dtu), dtu.data(), dtu.size()))) return r;
-  if ((r = dev_upload(p, const_cast<const int**>(&p->d_k0tab), k0tab.data(), k0tab.size()))) return r;
-  const int nslots = (nbd + nbu) * WARPS + 1;  // one projection slot per warp of either pass + the down zone's
-  if ((r = dev_alloc(p, &p->d_dhist, static_cast<size_t>(S) * L * MAX_SMALL))) return r;
   if ((r = dev_alloc(p, &p->d_proj, static_cast<size_t>(S) * L * nslots * 2))) return r;
   for (int i = 0; i < 2; ++i)
-    if ((r = dev_alloc(p, &p->d_cj[i], static_cast<size_t>(S) * Lp * 2))) return r;
-  if ((r = dev_alloc(p, &p->d_lam, static_cast<size_t>(S)))) return r;
-  if ((r = dev_alloc(p, &p->d_strip_ticket, 1))) return r;
-  if ((r = dev_alloc(p, &p->d_Ut_tab, SOS_MAX_PHASE))) return r;
-  if ((r = dev_alloc(p, &p->d_rank_tab, SOS_MAX_PHASE))) return r;
-  SOS_CUDA(cudaMemset(p->d_strip_ticket, 0, sizeof(int)));
-  SOS_CUDA(cudaMemset(p->d_dhist, 0, sizeof(double) * S * L * MAX_SMALL));
+    if ((r = dev_alloc(p, &p->d_cj[i], static_cast<size_t>(S) * L * 2))) return r;
   SOS_CUDA(cudaMemset(p->d_proj, 0, sizeof(double) * S * L * nslots * 2));
-  for (int i = 0; i < 2; ++i) SOS_CUDA(cudaMemset(p->d_cj[i], 0, sizeof(double) * S * Lp * 2));
-  SOS_CUDA(cudaMemset(p->d_lam, 0, sizeof(double) * S));
-  SOS_CUDA(cudaMemset(p->d_rank_tab, 0, sizeof(int) * SOS_MAX_PHASE));
-  p->col_nbd = nbd;
-  p->col_nbu = nbu;
-  p->col_nslots = nslots;
-  p->col_nsc = nsc;
-  p->col_Lp = Lp;
-  p->col_ue = ue;
-  p->col_zu_end = std::min(ue + BCOLS, N);
-  p->col_zlo = col_zone_lo(g, scen_h);
+  for (int i = 0; i < 2; ++i) SOS_CUDA(cudaMemset(p->d_cj[i], 0, sizeof(double) * S * L * 2));
+  p->gen_nslots = nslots;
+  p->gen_zu_end = std::min(M + 1 + kGenUpZone, N);
+  p->gen_zlo = gen_zone_lo(g, scen_h);
   p->strip_ok = true;
   return SOS_OK;
 }
@@ -737,7 +669,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
   }
   {
-    int r3 = strip_setup(p, mu_h, tau_h, p->scen_h.data());
+    int r3 = strip_setup(p, p->scen_h.data());
     if (r3) { sos_plan_destroy(p); return r3; }
   }
   *out = p;
@@ -773,16 +705,9 @@ int sos_plan_update(sos_plan* p, const double* tau_h, const sos_scenario* scen_h
   std::vector<ScenState> state(S);
   for (int s = 0; s < S; ++s) { state[s].ratio_toa = 1; state[s].ratio_surf = 1; state[s].n_orders = 1; state[s].active = 1; state[s].status = 0; state[s].pad = 0; }
   SOS_CUDA(cudaMemcpyAsync(g.state, state.data(), sizeof(ScenState) * S, cudaMemcpyHostToDevice, st));
-  std::vector<double> dtd, dtu;
-  std::vector<int> k0tab;
   if (p->strip_ok) {
-    p->strip_zone_ok = true;
-    p->col_zlo = col_zone_lo(g, patched.data());
-    col_tables(g, p->mu_h.data(), tau_h, p->col_nsc, p->col_Lp, dtd, dtu, k0tab);
-    SOS_CUDA(cudaMemcpyAsync(p->d_dtd, dtd.data(), dtd.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    SOS_CUDA(cudaMemcpyAsync(p->d_dtu, dtu.data(), dtu.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    SOS_CUDA(cudaMemcpyAsync(p->d_k0tab, k0tab.data(), k0tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    p->strip_disabled = false;  // a new batch gets the fused kernels again
+    p->gen_zlo = gen_zone_lo(g, patched.data());
+    p->strip_disabled = false;  // a new batch gets the generated source again
   }
   SOS_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
   sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev, p->d_strip_ticket);
@@ -861,11 +786,11 @@ int sos_get_profile(sos_plan* p, double* ms, long long* spans, void* stream) {
   if (!p || !ms || !spans) return SOS_ERR_INVALID;
   SOS_GUARD(p);
   SOS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-  ms[0] = ms[1] = 0.0;
-  spans[0] = spans[1] = 0;
+  for (int i = 0; i < SOS_PROFILE_CLASSES; ++i) { ms[i] = 0.0; spans[i] = 0; }
   for (auto& sp : p->ev_spans) {
     float t = 0.f;
     SOS_CUDA(cudaEventElapsedTime(&t, sp.second.first, sp.second.second));
+    if (sp.first < 0 || sp.first >= SOS_PROFILE_CLASSES) continue;
     ms[sp.first] += t;
     spans[sp.first] += 1;
   }
@@ -1345,6 +1270,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
       int rl = launch_check(p);
       if (rl) return rl;
     }
+    ProfSpan dense_span(p, 3, st);
     if (p->fold_xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     else sosgemm::jn_gemm_fold_kernel<false><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     return launch_check(p, "jn_gemm_fold_kernel");
@@ -1358,35 +1284,65 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
   return launch_check(p);
 }
 
-static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st) {
+// SrcGen of order n (n < 0: every J row is read from memory, every I_n row stored)
+static sossweep::SrcGen source_gen(const sos_plan* p, int n) {
+  sossweep::SrcGen sg;
+  std::memset(&sg, 0, sizeof(sg));
+  sg.zu_end = p->dev.N;
+  if (n < 0) return sg;
+  sg.cj = p->d_cj[n & 1];
+  sg.cj_out = p->d_cj[(n + 1) & 1];
+  sg.Lp = p->dev.L;
+  sg.proj = p->d_proj;
+  sg.nslots = p->gen_nslots;
+  sg.zlo = p->gen_zlo;
+  sg.zu_end = p->gen_zu_end;
+  sg.store_all = strip_env_int("SOS_B200_STRIP_STORE_ALL", 0);
+  sg.ldr = p->lowrank_ldr;
+  for (int i = 0; i < SOS_MAX_PHASE; ++i) {
+    sg.rank[i] = p->lowrank_rank[i];
+    sg.Ut[i] = p->lowrank_Ut[i];
+  }
+  return sg;
+}
+
+static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st, int gen_order = -1) {
   const GridDev& g = p->dev;
+  const sossweep::SrcGen sg = source_gen(p, gen_order);
   ProfSpan span(p, 1, st);
-  dim3 cgrid((g.N + sossweep::LOCAL_THREADS - 1) / sossweep::LOCAL_THREADS, g.nchunks, g.S);
+  const int T = sossweep::LOCAL_THREADS;
+  dim3 cgrid((g.M - 1 + T - 1) / T + (g.N - g.M - 1 + T - 1) / T, g.nchunks, g.S);
   {
-    sossweep::sweep_local_kernel<<<cgrid, sossweep::LOCAL_THREADS, 0, st>>>(g, J_d, p->d_aggD, p->d_aggU);
-    int r = launch_check(p);
+    sossweep::sweep_local_kernel<<<cgrid, T, 0, st>>>(g, sg, J_d, p->d_aggD, p->d_aggU);
+    int r = launch_check(p, "sweep_local_kernel");
     if (r) return r;
   }
   {
     const size_t smem = (g.N + 32) * sizeof(double);
-    sossweep::sweep_carry_kernel<<<g.S, sossweep::CARRY_THREADS, smem, st>>>(g, J_d, p->d_aggD, p->d_aggU, p->d_carryD, p->d_carryU);
-    int r = launch_check(p);
+    sossweep::sweep_carry_kernel<<<g.S, sossweep::CARRY_THREADS, smem, st>>>(g, sg, J_d, p->d_aggD, p->d_aggU, p->d_carryD, p->d_carryU);
+    int r = launch_check(p, "sweep_carry_kernel");
     if (r) return r;
   }
   {
-    sossweep::sweep_apply_kernel<<<cgrid, sossweep::LOCAL_THREADS, 0, st>>>(g, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
-    int r = launch_check(p);
+    ProfSpan apply_span(p, 2, st);
+    sossweep::sweep_apply_kernel<<<cgrid, T, 0, st>>>(g, sg, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
+    int r = launch_check(p, "sweep_apply_kernel");
     if (r) return r;
   }
   {
-    // per-warp buffer of the raw downward values next to mu = 0-: the widest extrapolation class (0.06 M) + 5
-    // sources, or all non-standard columns, whichever is more
+    // per-warp buffer of the downward values next to mu = 0-: the widest extrapolation class (0.06 M) + 5
+    // sources, or all non-standard columns, whichever is more (with a generated source: the plan-wide zone)
     const int down = std::max(g.M - g.first_small, g.widx[3] + 6) + 1;
-    const int zone_buf = std::min(g.M, down);
+    int zone_buf = std::min(g.M, down);
+    if (gen_order >= 0) zone_buf = std::max(zone_buf, g.M - p->gen_zlo);
     const size_t smem = static_cast<size_t>(zone_buf) * sossweep::ZONE_ROWS * sizeof(double);
+    if (smem > 48 * 1024) {
+      if (smem > 200 * 1024) return SOS_ERR_UNSUPPORTED;
+      cudaFuncSetAttribute(sossweep::sweep_zone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    }
     dim3 grid((g.L + sossweep::ZONE_ROWS - 1) / sossweep::ZONE_ROWS, g.S);
-    sossweep::sweep_zone_kernel<<<grid, 32 * sossweep::ZONE_ROWS, smem, st>>>(g, J_d, In_d, I_d, saved_d, zone_buf);
-    int r = launch_check(p);
+    sossweep::sweep_zone_kernel<<<grid, 32 * sossweep::ZONE_ROWS, smem, st>>>(g, sg, J_d, In_d, I_d, saved_d, zone_buf);
+    int r = launch_check(p, "sweep_zone_kernel");
     if (r) return r;
   }
   return SOS_OK;
@@ -1441,7 +1397,7 @@ int sos_get_results(sos_plan* p, sos_result* results_h, void* stream) {
 // can this solve run on the fused strip kernel, and with generated J?
 static bool strip_usable(const sos_plan* p) {
   const GridDev& g = p->dev;
-  return p->strip_ok && p->strip_zone_ok && !p->strip_disabled && g.col0 == 0 && g.col1 == g.N;
+  return p->strip_ok && !p->strip_disabled && g.col0 == 0 && g.col1 == g.N;
 }
 static bool strip_generates(const sos_plan* p) {
   // the molecular rows leave the contraction only in fold mode (class-3 groups of the tile plan) and only with the
@@ -1450,75 +1406,6 @@ static bool strip_generates(const sos_plan* p) {
   for (int i = 0; i < SOS_MAX_PHASE; ++i)
     if (p->lowrank_rank[i] > 2) return false;
   return true;
-}
-
-// one order on the fused kernels: J (dense rows) / source coefficients of order n (generated rows) -> I_n, I, the
-// coefficients of order n + 1: down columns, down zone rows (+ surface seeds), up columns, up zone rows
-static int strip_order(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, int n, bool gen, cudaStream_t st) {
-  using namespace soscol;
-  const GridDev& g = p->dev;
-  static int configured[64] = {0};  // per device: function attributes belong to the device's context
-  if (!configured[p->device & 63]) {
-    if (cudaFuncSetAttribute(column_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(column_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM) != cudaSuccess) {
-      g_last_cuda_error = "column_scan_kernel: shared memory request refused";
-      return SOS_ERR_CUDA;
-    }
-    configured[p->device & 63] = 1;
-  }
-  ColParams cp;
-  std::memset(&cp, 0, sizeof(cp));
-  cp.g = g;
-  cp.J = J_d; cp.In = In_d; cp.I = I_d; cp.saved = saved_d;
-  cp.cj = p->d_cj[n & 1];
-  cp.Lp = p->col_Lp;
-  cp.proj = p->d_proj;
-  cp.nslots = p->col_nslots;
-  cp.zlo = p->col_zlo;
-  cp.zu_end = p->col_zu_end;
-  cp.gen = gen ? 1 : 0;
-  cp.store_all = strip_env_int("SOS_B200_STRIP_STORE_ALL", 0);
-  ZoneParams zp;
-  std::memset(&zp, 0, sizeof(zp));
-  for (int i = 0; i < SOS_MAX_PHASE; ++i) {
-    cp.rank[i] = zp.rank[i] = gen ? p->lowrank_rank[i] : 0;
-    cp.Ut[i] = zp.Ut[i] = p->lowrank_Ut[i];
-  }
-  cp.ldr = zp.ldr = p->lowrank_ldr;
-  cp.dhist = p->d_dhist;
-  cp.lam = p->d_lam;
-  zp.g = g;
-  zp.J = J_d; zp.In = In_d; zp.I = I_d; zp.saved = saved_d;
-  zp.cj_in = p->d_cj[n & 1];
-  zp.cj_out = p->d_cj[(n + 1) & 1];
-  zp.Lp = p->col_Lp;
-  zp.proj = p->d_proj;
-  zp.nslots = p->col_nslots;
-  zp.zone_slot = p->col_nslots - 1;
-  zp.zlo = p->col_zlo;
-  zp.zu_end = p->col_zu_end;
-  zp.gen = cp.gen;
-  zp.dhist = p->d_dhist;
-  zp.k0tab = p->d_k0tab;
-  zp.nsc = p->col_nsc;
-  zp.lam = p->d_lam;
-  zp.zone_buf = g.M - p->col_zlo;
-  const size_t zsmem = static_cast<size_t>(zp.zone_buf) * ZONE_ROWS * sizeof(double);
-  if (zsmem > 200 * 1024) return SOS_ERR_UNSUPPORTED;
-  if (zsmem > 48 * 1024) cudaFuncSetAttribute(zone_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zsmem));
-  const dim3 zgrid((g.L + ZONE_ROWS - 1) / ZONE_ROWS, g.S);
-  ProfSpan span(p, 1, st);
-  int r;
-  cp.dt = p->d_dtd; cp.nblocks = p->col_nbd; cp.col_first = 0; cp.slot0 = 0;
-  column_scan_kernel<false><<<g.S * p->col_nbd, THREADS, CTA_SMEM, st>>>(cp);
-  if ((r = launch_check(p, "column_scan_kernel<down>"))) return r;
-  zone_rows_kernel<false><<<zgrid, 32 * ZONE_ROWS, zsmem, st>>>(zp);
-  if ((r = launch_check(p, "zone_rows_kernel<down>"))) return r;
-  cp.dt = p->d_dtu; cp.nblocks = p->col_nbu; cp.col_first = p->col_ue; cp.slot0 = p->col_nbd * WARPS;
-  column_scan_kernel<true><<<g.S * p->col_nbu, THREADS, CTA_SMEM, st>>>(cp);
-  if ((r = launch_check(p, "column_scan_kernel<up>"))) return r;
-  zone_rows_kernel<true><<<zgrid, 32 * ZONE_ROWS, 0, st>>>(zp);
-  return launch_check(p, "zone_rows_kernel<up>");
 }
 
 int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* orders_d, int max_saved, int max_orders,
@@ -1532,17 +1419,11 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
   int r = sos_reset(p, I_d, stream);
   if (r) return r;
   const size_t field = static_cast<size_t>(g.S) * g.L * g.ld;
-  const bool strip = strip_usable(p);
-  const bool gen = strip && strip_generates(p);
+  const bool gen = strip_usable(p) && strip_generates(p);
   if (gen) {
     // projections of the first order onto the molecular factors: what order 2 rebuilds its J from
-    const double* ut[SOS_MAX_PHASE];
-    for (int i = 0; i < SOS_MAX_PHASE; ++i) ut[i] = p->lowrank_Ut[i];
-    SOS_CUDA(cudaMemcpyAsync(p->d_Ut_tab, ut, sizeof(ut), cudaMemcpyHostToDevice, st));
-    SOS_CUDA(cudaMemcpyAsync(p->d_rank_tab, p->lowrank_rank, sizeof(int) * SOS_MAX_PHASE, cudaMemcpyHostToDevice, st));
-    SOS_CUDA(cudaStreamSynchronize(st));  // (ut lives on this stack frame)
     dim3 pg((g.L + 7) / 8, g.S);
-    soscol::project_rows_kernel<<<pg, 256, 0, st>>>(g, In_d, p->d_Ut_tab, p->d_rank_tab, p->lowrank_ldr, p->col_Lp, p->d_cj[0]);
+    sossweep::project_rows_kernel<<<pg, 256, 0, st>>>(g, source_gen(p, 2), In_d, p->d_cj[0]);
     r = launch_check(p, "project_rows_kernel");
     if (r) return r;
   }
@@ -1561,18 +1442,9 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
     rc = source_impl(p, In_d, J_d, 0, 0x7fffffff, stream, nullptr, 0, nullptr, gen);
     if (rc) break;
     double* saved = (orders_d && n - 2 < max_saved) ? orders_d + static_cast<size_t>(n - 2) * field : nullptr;
-    if (strip) {
-      rc = strip_order(p, J_d, In_d, I_d, saved, n, gen, st);
-      if (rc) break;
-      sossweep::converge_kernel<<<1, 256, 0, st>>>(p->dev, n, p->d_order, nullptr, 0, p->d_strip_ticket);
-      rc = launch_check(p);
-      if (rc) break;
-      rc = plan_tiles(p, st);
-    } else {
-      rc = sweeps_impl(p, J_d, In_d, I_d, saved, st);
-      if (rc) break;
-      rc = sos_converge(p, n, stream);
-    }
+    rc = sweeps_impl(p, J_d, In_d, I_d, saved, st, gen ? n : -1);
+    if (rc) break;
+    rc = sos_converge(p, n, stream);
     if (rc) break;
     const int slot = issued % nslots;
     if (issued >= nslots) poll[slot] = -1;  // that copy finished long ago (run-ahead is bounded below)
@@ -1592,9 +1464,9 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
     }
   }
   if (rc) return rc;
-  if (strip) {
-    // a blend that left strip 0's columns cannot be finished by the fused kernel: switch this plan to the chunked
-    // kernels and ask the caller to run the solve again (I_d / In_d have been consumed)
+  if (gen) {
+    // a blend that left the columns whose raw I_n is kept cannot be finished: switch this plan to stored sources
+    // and ask the caller to run the solve again (I_d / In_d have been consumed)
     std::vector<sos_result> tmp(g.S);
     rc = sos_get_results(p, tmp.data(), stream);
     if (rc) return rc;

@@ -19,10 +19,86 @@
 //                    extrapolation (:113-141, a fixed linear map W), the find-first second-difference
 //                    blend (SOS_Aer_I1_In.py:101-108) and the convergence ratios of :309.
 //   Traffic: J 8 (pass 1) + J 8 + I_n 8 + I 16 (pass 3) = 40 B per element (32 B is the algorithmic minimum).
+//
+// Generated source.  On rows that use the molecular operand alone (every row outside the aerosol layer,
+// SOS_Aer_main_specular.py:323) the contraction operand is A = Us Vt with Vt = [1; mu^2] (gemm_lowrank.cuh), so
+//     J[t, m] = c0[t] + c1[t] mu_m^2,     c_r[t] = coef * sum_k I_{n-1}[t, k] Us[k][r]
+// and the two numbers c_r[t] per row are all the next order needs from this one.  Inside sos_solve the sweeps therefore
+// REBUILD J from c on those rows instead of reading it (SrcGen / SrcAt below), sweep_apply_kernel emits the partial
+// projections of the I_n it produces (one slot per warp and row; butterfly transpose-reduce, a fixed tree: deterministic)
+// and sweep_zone_kernel adds the columns it finishes, sums the slots and writes the next order's c.  On those rows
+// neither J nor I_n touches memory (I_n is kept only where something reads it: the aerosol rows for the dense
+// contraction, the columns next to mu = 0 for the zone kernel, the TOA / surface rows for the ratios and the surface
+// coupling): per element and order that leaves the read-modify-write of I, 16 B, on 746 of the 800 default rows; the
+// local pass of those rows reads nothing at all.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace sossweep {
+
+struct SrcGen {
+  const double* cj;        // [S][Lp][2] source coefficients of this order; nullptr: every J row is read from memory
+  double* cj_out;          // ... of the next order (written by sweep_zone_kernel)
+  int Lp;
+  double* proj;            // [S][L][nslots][2] partial projections of I_n (one slot per warp of sweep_apply_kernel)
+  int nslots;
+  int zlo, zu_end;         // columns the zone kernel reads raw: downward m >= zlo, upward m < zu_end (I_n stored there on
+                           // every row; left out of the apply pass's projections, projected by the zone kernel)
+  int store_all;           // store I_n everywhere (debugging aid)
+  int ldr;
+  int rank[SOS_MAX_PHASE];
+  const double* Ut[SOS_MAX_PHASE];
+};
+
+// J[t, m] of one scenario: read, or rebuilt on the molecular rows
+struct SrcAt {
+  const double* Js;
+  const double2* cj2;
+  int ld, a0, a1;
+  bool gen;
+  __device__ __forceinline__ SrcAt(const GridDev& g, const SrcGen& sg, const double* J, int s)
+      : Js(J + static_cast<size_t>(s) * g.L * g.ld), cj2(nullptr), ld(g.ld), a0(g.nreg == 3 ? g.rstart[1] : g.L),
+        a1(g.nreg == 3 ? g.rstart[2] : g.L), gen(sg.cj != nullptr && sg.rank[g.scen[s].phase_atm] > 0) {
+    if (gen) cj2 = reinterpret_cast<const double2*>(sg.cj) + static_cast<size_t>(s) * sg.Lp;
+  }
+  __device__ __forceinline__ bool gen_row(int t) const { return gen && (t < a0 || t >= a1); }
+  __device__ __forceinline__ double operator()(int t, int m, double mu) const {
+    if (gen_row(t)) {
+      const double2 c = cj2[t];
+      return fma(c.y, mu * mu, c.x);
+    }
+    return Js[static_cast<size_t>(t) * ld + m];
+  }
+};
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// v[0..7] of every lane -> the sum over the warp of v[lane >> 2], in every lane (fixed tree: deterministic)
+__device__ __forceinline__ double transpose_reduce8(double (&v)[8], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double keep = h16 ? v[i + 4] : v[i], send = h16 ? v[i] : v[i + 4];
+    v[i] = keep + shfl_xor_d(send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double keep = h8 ? v[i + 2] : v[i], send = h8 ? v[i] : v[i + 2];
+    v[i] = keep + shfl_xor_d(send, 8);
+  }
+  {
+    const double keep = h4 ? v[1] : v[0], send = h4 ? v[0] : v[1];
+    v[0] = keep + shfl_xor_d(send, 4);
+  }
+  v[0] += shfl_xor_d(v[0], 2);
+  v[0] += shfl_xor_d(v[0], 1);
+  return v[0];
+}
+
+// column of a (block, thread) of the two scan passes: blocks [0, nbd) hold the downward columns 0 .. M-2, the others
+// the upward columns M+1 .. N-1, so that no warp mixes the two directions (its rows run together: warp collectives)
+__device__ __forceinline__ int scan_blocks_down(int M, int threads) { return (M - 1 + threads - 1) / threads; }
 
 // exp(x) for the attenuation factors a_t = exp(-dtau/|mu|): almost every argument is tiny (dtau ~ 1e-4 ..
 // 3e-3 per layer), where a degree-8 Taylor polynomial is exact to < 1e-19 relative (|x| <= 2^-5:
@@ -46,6 +122,33 @@ __device__ __forceinline__ double exp_small(double x) {
   return exp(x);
 }
 
+// exp(x) for |x| <= 2^-10 (x^5/5! < 7e-18 relative): what almost every scan step of a thin atmosphere needs
+constexpr double kTinyArg = 0.0009765625;
+__device__ __forceinline__ double exp_tiny(double x) {
+  double p = kExpTaylor[4];
+  p = fma(p, x, kExpTaylor[5]);
+  p = fma(p, x, kExpTaylor[6]);
+  p = fma(p, x, kExpTaylor[7]);
+  return fma(p, x, kExpTaylor[7]);
+}
+// the polynomial branch of exp_small alone (|x| <= 2^-5 guaranteed by the caller)
+__device__ __forceinline__ double exp_poly8(double x) {
+  double p = kExpTaylor[0];
+  p = fma(p, x, kExpTaylor[1]);
+  p = fma(p, x, kExpTaylor[2]);
+  p = fma(p, x, kExpTaylor[3]);
+  p = fma(p, x, kExpTaylor[4]);
+  p = fma(p, x, kExpTaylor[5]);
+  p = fma(p, x, kExpTaylor[6]);
+  p = fma(p, x, kExpTaylor[7]);
+  return fma(p, x, kExpTaylor[7]);
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 constexpr int LOCAL_THREADS = 128;
 constexpr int LOCAL_UNROLL = 4;  // (8 rows in flight was measured: lower occupancy, 0.756 vs 0.744 ms per order at S = 96)
 constexpr int ROW_THREADS = 256;
@@ -55,106 +158,196 @@ constexpr int CARRY_THREADS = 1024;
 // 1. chunk-local recurrences
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LOCAL_THREADS)
-sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ aggD, double* __restrict__ aggU) {
+sweep_local_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, double* __restrict__ aggD, double* __restrict__ aggU) {
   const int s = blockIdx.z;
   if (!g.state[s].active) return;
   const int c = blockIdx.y;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= g.N || m < g.col0 || m >= g.col1) return;
-  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
   const int L = g.L, M = g.M, ld = g.ld;
+  const int nbd = scan_blocks_down(M, LOCAL_THREADS);
+  const bool up = static_cast<int>(blockIdx.x) >= nbd;
+  const int m = up ? M + 1 + (blockIdx.x - nbd) * LOCAL_THREADS + threadIdx.x : blockIdx.x * LOCAL_THREADS + threadIdx.x;
+  if (up ? (m >= g.N) : (m >= M - 1)) return;
+  if (m < g.col0 || m >= g.col1) return;
+  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
-  const double* __restrict__ Js = J + static_cast<size_t>(s) * L * ld;
+  const SrcAt src(g, sg, J, s);
+  const double* __restrict__ Js = src.Js;
   const double mu = g.mu[m];
   const double imu = 1.0 / mu;  // one division per thread; the scan steps multiply
+  const double q = mu * mu;
   const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
+  const bool cg = src.gen_row(t0);  // chunks never straddle a region: the whole chunk is rebuilt, or read
+  // J of a row of THIS chunk (one kind of row); rows outside go through src()
+  auto jrow = [&](auto gen_tag, int t) -> double {
+    if (decltype(gen_tag)::value) {
+      const double2 cc = src.cj2[t];
+      return fma(cc.y, q, cc.x);
+    }
+    return Js[static_cast<size_t>(t) * ld + m];
+  };
 
-  if (m < M - 1) {
+  if (!up) {
     if (fabs(mu) < SOS_MU_THRESHOLD) return;  // windowed / Taylor columns are row-local (sweep_zone_kernel)
     double D = 0.0;
     int t = t0;
     double Jp;
     if (t == 0) {
-      Jp = Js[m];
+      Jp = src(0, m, mu);
       t = 1;
     } else {
-      Jp = Js[static_cast<size_t>(t - 1) * ld + m];
+      Jp = src(t - 1, m, mu);
     }
     double tp = tau[t - 1 < 0 ? 0 : t - 1];
-    // LOCAL_UNROLL independent loads / exps in flight, one dependent DFMA chain
-    for (; t + LOCAL_UNROLL - 1 < t1; t += LOCAL_UNROLL) {
-      double tc[LOCAL_UNROLL], jv[LOCAL_UNROLL], a[LOCAL_UNROLL], b[LOCAL_UNROLL];
+    auto body = [&](auto gen_tag) {
+      // LOCAL_UNROLL independent loads / exps in flight, one dependent DFMA chain
+      for (; t + LOCAL_UNROLL - 1 < t1; t += LOCAL_UNROLL) {
+        double tc[LOCAL_UNROLL], jv[LOCAL_UNROLL], a[LOCAL_UNROLL], b[LOCAL_UNROLL];
 #pragma unroll
-      for (int u = 0; u < LOCAL_UNROLL; ++u) {
-        tc[u] = tau[t + u];
-        jv[u] = Js[static_cast<size_t>(t + u) * ld + m];
+        for (int u = 0; u < LOCAL_UNROLL; ++u) {
+          tc[u] = tau[t + u];
+          jv[u] = jrow(gen_tag, t + u);
+        }
+#pragma unroll
+        for (int u = 0; u < LOCAL_UNROLL; ++u) {
+          const double d = tc[u] - (u ? tc[u - 1] : tp);
+          a[u] = exp_small(d * imu);
+          b[u] = (d * 0.5) * ((u ? jv[u - 1] : Jp) * a[u] + jv[u]) * imu;
+        }
+#pragma unroll
+        for (int u = 0; u < LOCAL_UNROLL; ++u) D = D * a[u] - b[u];
+        Jp = jv[LOCAL_UNROLL - 1];
+        tp = tc[LOCAL_UNROLL - 1];
       }
-#pragma unroll
-      for (int u = 0; u < LOCAL_UNROLL; ++u) {
-        const double d = tc[u] - (u ? tc[u - 1] : tp);
-        a[u] = exp_small(d * imu);
-        b[u] = (d * 0.5) * ((u ? jv[u - 1] : Jp) * a[u] + jv[u]) * imu;
+      for (; t < t1; ++t) {
+        const double tc = tau[t];
+        const double jc = jrow(gen_tag, t);
+        const double d = tc - tp;
+        const double a = exp_small(d * imu);
+        D = D * a - (d * 0.5) * (Jp * a + jc) * imu;
+        Jp = jc;
+        tp = tc;
       }
+    };
+    if (cg) {
+      // rebuilt source: nothing is read but tau and the two coefficients of each row; 4 rows per step, the short
+      // polynomial where every step of the group is tiny (x = dtau / mu is the same sign-definite exponent everywhere)
+      const double2* __restrict__ pc = src.cj2 + t;
+      const double* __restrict__ pt = tau + t;
+      const double ximax = fabs(imu);
+      for (; t + 3 < t1; t += 4, pc += 4, pt += 4) {
+        double tc[4], jv[4], x[4], a[4];
 #pragma unroll
-      for (int u = 0; u < LOCAL_UNROLL; ++u) D = D * a[u] - b[u];
-      Jp = jv[LOCAL_UNROLL - 1];
-      tp = tc[LOCAL_UNROLL - 1];
-    }
-    for (; t < t1; ++t) {
-      const double tc = tau[t];
-      const double jc = Js[static_cast<size_t>(t) * ld + m];
-      const double d = tc - tp;
-      const double a = exp_small(d * imu);
-      D = D * a - (d * 0.5) * (Jp * a + jc) * imu;
-      Jp = jc;
-      tp = tc;
+        for (int u = 0; u < 4; ++u) {
+          tc[u] = pt[u];
+          const double2 cc = pc[u];
+          jv[u] = fma(cc.y, q, cc.x);
+        }
+        double dmax = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double d = tc[u] - (u ? tc[u - 1] : tp);
+          dmax = fmax(dmax, d);
+          x[u] = d * imu;
+        }
+        if (dmax * ximax <= kTinyArg) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = exp_tiny(x[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = exp_small(x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) D = fma(D, a[u], -(0.5 * x[u]) * fma(u ? jv[u - 1] : Jp, a[u], jv[u]));
+        Jp = jv[3];
+        tp = tc[3];
+      }
+      body(std::true_type{});
+    } else {
+      body(std::false_type{});
     }
     aggD[agg] = D;
-  } else if (m > M) {
+  } else {
     double U = 0.0;
     int t = t1 - 1;
     double Jn, tn;
     if (t == L - 1) {
-      Jn = Js[static_cast<size_t>(t) * ld + m];
+      Jn = src(t, m, mu);
       tn = tau[t];
       --t;
     } else {
-      Jn = Js[static_cast<size_t>(t + 1) * ld + m];
+      Jn = src(t + 1, m, mu);
       tn = tau[t + 1];
       // chunk ends at a region boundary: the slice stops one row short of the carry row
       // (SOS_Aer_main_specular.py:413,433) -> pure attenuation, no source on this step
       if (g.chunk_region[c + 1] != g.chunk_region[c]) {
-        Jn = Js[static_cast<size_t>(t) * ld + m];
+        Jn = src(t, m, mu);
         tn = tau[t];
         --t;
       }
     }
-    for (; t - (LOCAL_UNROLL - 1) >= t0; t -= LOCAL_UNROLL) {
-      double tc[LOCAL_UNROLL], jv[LOCAL_UNROLL], a[LOCAL_UNROLL], b[LOCAL_UNROLL];
+    auto body = [&](auto gen_tag) {
+      for (; t - (LOCAL_UNROLL - 1) >= t0; t -= LOCAL_UNROLL) {
+        double tc[LOCAL_UNROLL], jv[LOCAL_UNROLL], a[LOCAL_UNROLL], b[LOCAL_UNROLL];
 #pragma unroll
-      for (int u = 0; u < LOCAL_UNROLL; ++u) {
-        tc[u] = tau[t - u];
-        jv[u] = Js[static_cast<size_t>(t - u) * ld + m];
+        for (int u = 0; u < LOCAL_UNROLL; ++u) {
+          tc[u] = tau[t - u];
+          jv[u] = jrow(gen_tag, t - u);
+        }
+#pragma unroll
+        for (int u = 0; u < LOCAL_UNROLL; ++u) {
+          const double d = (u ? tc[u - 1] : tn) - tc[u];
+          a[u] = exp_small(-d * imu);
+          b[u] = (d * 0.5) * (jv[u] + (u ? jv[u - 1] : Jn) * a[u]) * imu;
+        }
+#pragma unroll
+        for (int u = 0; u < LOCAL_UNROLL; ++u) U = U * a[u] + b[u];
+        Jn = jv[LOCAL_UNROLL - 1];
+        tn = tc[LOCAL_UNROLL - 1];
       }
-#pragma unroll
-      for (int u = 0; u < LOCAL_UNROLL; ++u) {
-        const double d = (u ? tc[u - 1] : tn) - tc[u];
-        a[u] = exp_small(-d * imu);
-        b[u] = (d * 0.5) * (jv[u] + (u ? jv[u - 1] : Jn) * a[u]) * imu;
+      for (; t >= t0; --t) {
+        const double tc = tau[t];
+        const double jc = jrow(gen_tag, t);
+        const double d = tn - tc;
+        const double a = exp_small(-d * imu);
+        U = U * a + (d * 0.5) * (jc + Jn * a) * imu;
+        Jn = jc;
+        tn = tc;
       }
+    };
+    if (cg) {
+      const double2* __restrict__ pc = src.cj2 + t;
+      const double* __restrict__ pt = tau + t;
+      const double ximax = fabs(imu);
+      for (; t - 3 >= t0; t -= 4, pc -= 4, pt -= 4) {
+        double tc[4], jv[4], x[4], a[4];
 #pragma unroll
-      for (int u = 0; u < LOCAL_UNROLL; ++u) U = U * a[u] + b[u];
-      Jn = jv[LOCAL_UNROLL - 1];
-      tn = tc[LOCAL_UNROLL - 1];
-    }
-    for (; t >= t0; --t) {
-      const double tc = tau[t];
-      const double jc = Js[static_cast<size_t>(t) * ld + m];
-      const double d = tn - tc;
-      const double a = exp_small(-d * imu);
-      U = U * a + (d * 0.5) * (jc + Jn * a) * imu;
-      Jn = jc;
-      tn = tc;
+        for (int u = 0; u < 4; ++u) {
+          tc[u] = pt[-u];
+          const double2 cc = pc[-u];
+          jv[u] = fma(cc.y, q, cc.x);
+        }
+        double dmax = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double d = (u ? tc[u - 1] : tn) - tc[u];
+          dmax = fmax(dmax, d);
+          x[u] = -d * imu;
+        }
+        if (dmax * ximax <= kTinyArg) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = exp_tiny(x[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = exp_small(x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) U = fma(U, a[u], -(0.5 * x[u]) * fma(u ? jv[u - 1] : Jn, a[u], jv[u]));
+        Jn = jv[3];
+        tn = tc[3];
+      }
+      body(std::true_type{});
+    } else {
+      body(std::false_type{});
     }
     aggU[agg] = U;
   }
@@ -166,15 +359,14 @@ sweep_local_kernel(const GridDev g, const double* __restrict__ J, double* __rest
 
 // |mu| < MU_THRESHOLD downward column m at layer t (improved_asymptotic_downward_radiance,
 // SOS_Aer_In_limit.py:70-109).  One warp per call; every lane returns the value.
-__device__ __forceinline__ double asymptotic_column(const GridDev& g, const double* __restrict__ Js,
+__device__ __forceinline__ double asymptotic_column(const GridDev& g, const SrcAt& src,
                                                     const double* __restrict__ tau, int t, int r0, int m) {
   const int lane = threadIdx.x & 31;
-  const int ld = g.ld;
   const double mu = g.mu[m];
-  const double jt = Js[static_cast<size_t>(t) * ld + m];
+  const double jt = src(t, m, mu);
   if (fabs(mu) < SOS_MU_VERY_SMALL) {  // Taylor: -J + mu dJ/dtau (:79-93)
     double slope = 0.0;
-    if (t > r0) slope = (jt - Js[static_cast<size_t>(t - 1) * ld + m]) / (tau[t] - tau[t - 1]);
+    if (t > r0) slope = (jt - src(t - 1, m, mu)) / (tau[t] - tau[t - 1]);
     return -jt + mu * slope;
   }
   // windowed trapezoid over tau' >= tau_t - 5|mu| inside the region slice (:96-107)
@@ -190,8 +382,8 @@ __device__ __forceinline__ double asymptotic_column(const GridDev& g, const doub
   bool bad = false;
   // interval k..k+1 handled by lane (k-k0)%32; fixed order -> deterministic
   for (int k = k0 + lane; k < t; k += 32) {
-    const double f0 = Js[static_cast<size_t>(k) * ld + m] * exp((tt - tau[k]) / mu);
-    const double f1 = Js[static_cast<size_t>(k + 1) * ld + m] * exp((tt - tau[k + 1]) / mu);
+    const double f0 = src(k, m, mu) * exp((tt - tau[k]) / mu);
+    const double f1 = src(k + 1, m, mu) * exp((tt - tau[k + 1]) / mu);
     bad |= !isfinite(f0) || !isfinite(f1);
     sum += (tau[k + 1] - tau[k]) * (f1 + f0) * 0.5;
   }
@@ -206,7 +398,7 @@ __device__ __forceinline__ double asymptotic_column(const GridDev& g, const doub
 // Complete the downward half of a row held in smem `row[0..M-1]`:
 // windowed/Taylor columns that survive the extrapolation, then the extrapolation itself.
 // Must be called by all threads of the CTA; contains __syncthreads.
-__device__ __forceinline__ void finish_down_row(const GridDev& g, double* row, const double* __restrict__ Js,
+__device__ __forceinline__ void finish_down_row(const GridDev& g, double* row, const SrcAt& src,
                                                 const double* __restrict__ tau, int t, int region, int idx_width,
                                                 int wclass) {
   const int M = g.M;
@@ -215,7 +407,7 @@ __device__ __forceinline__ void finish_down_row(const GridDev& g, double* row, c
   // columns first_small .. M-2 are non-standard; those >= M - idx are overwritten below -> skip them
   const int hi = min(M - 1, M - idx_width);
   for (int m = g.first_small + warp; m < hi; m += nwarps) {
-    const double v = asymptotic_column(g, Js, tau, t, r0, m);
+    const double v = asymptotic_column(g, src, tau, t, r0, m);
     if (lane == 0) row[m] = v;
   }
   __syncthreads();
@@ -290,15 +482,15 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /*[32]*/) 
 // 2. carry chain (one CTA per scenario)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CARRY_THREADS)
-sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* __restrict__ aggD,
+sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, const double* __restrict__ aggD,
                    const double* __restrict__ aggU, double* __restrict__ carryD, double* __restrict__ carryU) {
   extern __shared__ double sm_row[];  // [N] + scratch[32]
   __shared__ int found;
   const int s = blockIdx.x;
   if (!g.state[s].active) return;
-  const int L = g.L, M = g.M, N = g.N, ld = g.ld, nch = g.nchunks;
+  const int L = g.L, M = g.M, N = g.N, nch = g.nchunks;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
-  const double* __restrict__ Js = J + static_cast<size_t>(s) * L * ld;
+  const SrcAt src(g, sg, J, s);
   const sos_scenario sc = g.scen[s];
   double* row = sm_row;
   double* scratch = sm_row + N;
@@ -343,7 +535,7 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
   const int last_region = g.nreg - 1;
   if (g.surface != SOS_SURFACE_NONE) {
     const int idxw = sc.extrap_width[last_region];
-    finish_down_row(g, row, Js, tau, L - 1, last_region, idxw, width_class(g, idxw));
+    finish_down_row(g, row, src, tau, L - 1, last_region, idxw, width_class(g, idxw));
   }
   double lambert = 0.0;
   if (g.surface == SOS_SURFACE_LAMBERT) {
@@ -398,7 +590,7 @@ sweep_carry_kernel(const GridDev g, const double* __restrict__ J, const double* 
     }
     if (ce > 0 && g.chunk_region[ce - 1] != g.chunk_region[ce]) {
       // row chunk_start[ce] is the carry row of the region above and is read after its blend (A.7)
-      if (threadIdx.x == 0) row[M] = Js[static_cast<size_t>(g.chunk_start[ce]) * ld + M];
+      if (threadIdx.x == 0) row[M] = src(g.chunk_start[ce], M, g.mu[M]);
       __syncthreads();
       if (!blend_up_row(g, row, &found) && threadIdx.x == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
     }
@@ -421,139 +613,303 @@ __device__ __forceinline__ int zone_lo(const GridDev& g, const sos_scenario& sc)
 
 // Second sweep pass: the same recurrences as sweep_local_kernel, now started from the TRUE carry of the
 // chunk, writing the final I_n and accumulating I += I_n in the same pass (J 8 + I_n 8 + I 16 bytes per
-// element).  The few columns next to mu = 0 that the reference post-processes are corrected afterwards by
-// sweep_zone_kernel (it replaces the raw value in I_n and adds the difference to I).
+// element; 16 where the source is rebuilt and I_n is not kept).  The few columns next to mu = 0 that the reference
+// post-processes are corrected afterwards by sweep_zone_kernel (it replaces the raw value in I_n and adds the
+// difference to I).  Every lane of a warp runs the same rows (lanes without a column compute on zeros and store
+// nothing), so the projections of a group of four rows are reduced with one butterfly.
 __global__ void __launch_bounds__(LOCAL_THREADS)
-sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
+sweep_apply_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, double* __restrict__ In,
                    const double* __restrict__ carryD, const double* __restrict__ carryU,
                    double* __restrict__ I, double* __restrict__ saved) {
   const int s = blockIdx.z;
   if (!g.state[s].active) return;
   const int c = blockIdx.y;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= g.N || m < g.col0 || m >= g.col1) return;
-  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
   const int L = g.L, M = g.M, ld = g.ld;
+  const int lane = threadIdx.x & 31;
+  const int nbd = scan_blocks_down(M, LOCAL_THREADS);
+  const bool up = static_cast<int>(blockIdx.x) >= nbd;
+  const int m = up ? M + 1 + (blockIdx.x - nbd) * LOCAL_THREADS + threadIdx.x : blockIdx.x * LOCAL_THREADS + threadIdx.x;
+  const bool in_range = up ? (m < g.N) : (m < M - 1);
+  const double mu_raw = in_range ? g.mu[m] : (up ? 1.0 : -1.0);
+  // windowed / Taylor columns are row-local (sweep_zone_kernel); mu-block plans own [col0, col1)
+  const bool valid = in_range && (up || fabs(mu_raw) >= SOS_MU_THRESHOLD) && m >= g.col0 && m < g.col1;
+  if (!__any_sync(0xffffffffu, valid)) return;
+  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
   const size_t fbase = static_cast<size_t>(s) * L * ld;
-  const double* __restrict__ Js = J + fbase;
+  const SrcAt src(g, sg, J, s);
+  const double* __restrict__ Js = src.Js;
   double* __restrict__ Is = In + fbase;
   double* __restrict__ Ia = I ? I + fbase : nullptr;
   double* __restrict__ Sv = saved ? saved + fbase : nullptr;
-  const double mu = g.mu[m];
+  const double mu = valid ? mu_raw : (up ? 1.0 : -1.0);
   const double imu = 1.0 / mu;  // one division per thread; the scan steps multiply
-  const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + m;
+  const double q = mu * mu;
+  const double ximax = warp_max_d(fabs(imu));  // the short exp polynomial is chosen per warp (uniform branch)
+  const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + (valid ? m : 0);
+  const bool cg = src.gen_row(t0);  // the whole chunk is rebuilt, or read
+  const bool zonecol = up ? (m < sg.zu_end) : (m >= sg.zlo);
+  const bool keep_in = !cg || zonecol || sg.store_all;  // I_n of this column is read by someone on every row
+  const int op = g.scen[s].phase_atm;
+  const double us0 = (cg && valid && !zonecol) ? sg.Ut[op][m] : 0.0;
+  const double us1 = (cg && valid && !zonecol) ? sg.Ut[op][sg.ldr + m] : 0.0;
+  double* const projs = cg ? sg.proj + ((fbase / ld) * sg.nslots + blockIdx.x * (LOCAL_THREADS / 32) + (threadIdx.x >> 5)) * 2 : nullptr;
+  const int forced = up ? 0 : L - 1;  // the row whose I_n everybody stores: ratios, surface coupling
 
-// store I_n (and I_saved); accumulate with the I value that was prefetched together with J
-#define SOS_EMIT(T_, V_, IOLD_)                                      \
-  do {                                                               \
-    const size_t o_ = static_cast<size_t>(T_) * ld + m;              \
-    const double v_ = (V_);                                          \
-    Is[o_] = v_;                                                     \
-    if (Sv) Sv[o_] = v_;                                             \
-    if (Ia) Ia[o_] = (IOLD_) + v_;                                   \
-  } while (0)
-#define SOS_IOLD(T_) (Ia ? Ia[static_cast<size_t>(T_) * ld + m] : 0.0)
+  auto jrow = [&](auto gen_tag, int t) -> double {
+    if (decltype(gen_tag)::value) {
+      const double2 cc = src.cj2[t];
+      return fma(cc.y, q, cc.x);
+    }
+    return valid ? Js[static_cast<size_t>(t) * ld + m] : 0.0;
+  };
+  auto jany = [&](int t) -> double { return (valid || src.gen_row(t)) ? src(t, valid ? m : 0, mu) : 0.0; };
+  // store I_n (and I_saved); accumulate with the I value that was prefetched together with J
+  auto emit = [&](int t, double v, double iold) {
+    if (valid) {
+      const size_t o = static_cast<size_t>(t) * ld + m;
+      if (keep_in || t == forced) Is[o] = v;
+      if (Sv) Sv[o] = v;
+      if (Ia) Ia[o] = iold + v;
+    }
+  };
+  auto iold = [&](int t) -> double { return (Ia && valid) ? Ia[static_cast<size_t>(t) * ld + m] : 0.0; };
+  // projections of one row (tail rows and the rows outside the unrolled loop): plain butterfly
+  auto project1 = [&](int t, double v) {
+    if (!cg) return;
+    double p0 = v * us0, p1 = v * us1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { p0 += shfl_xor_d(p0, o); p1 += shfl_xor_d(p1, o); }
+    if (lane == 0) *reinterpret_cast<double2*>(projs + static_cast<size_t>(t) * sg.nslots * 2) = make_double2(p0, p1);
+  };
+  // ... of four rows t, t + step, ...: transpose-reduce
+  auto project4 = [&](int t, int step, double v0, double v1, double v2, double v3) {
+    if (!cg) return;
+    double v[8] = {v0 * us0, v1 * us0, v2 * us0, v3 * us0, v0 * us1, v1 * us1, v2 * us1, v3 * us1};
+    const double tot = transpose_reduce8(v, lane);
+    const int idx = lane >> 2;
+    if ((lane & 3) == 0) projs[static_cast<size_t>(t + step * (idx & 3)) * sg.nslots * 2 + (idx >> 2)] = tot;
+  };
 
-  if (m < M - 1) {
-    if (fabs(mu) < SOS_MU_THRESHOLD) return;
-    double D = (t0 > 0) ? carryD[agg] : 0.0;
+  if (!up) {
+    double D = (t0 > 0 && valid) ? carryD[agg] : 0.0;
     int t = t0;
     double Jp;
     if (t == 0) {
-      Jp = Js[m];
-      SOS_EMIT(0, 0.0, SOS_IOLD(0));
+      Jp = jany(0);
+      emit(0, 0.0, iold(0));
+      project1(0, 0.0);
       t = 1;
     } else {
-      Jp = Js[static_cast<size_t>(t - 1) * ld + m];
+      Jp = jany(t - 1);
     }
     double tp = tau[t - 1 < 0 ? 0 : t - 1];
-    for (; t + 3 < t1; t += 4) {
-      const double tc0 = tau[t], tc1 = tau[t + 1], tc2 = tau[t + 2], tc3 = tau[t + 3];
-      const double j0 = Js[static_cast<size_t>(t) * ld + m];
-      const double j1 = Js[static_cast<size_t>(t + 1) * ld + m];
-      const double j2 = Js[static_cast<size_t>(t + 2) * ld + m];
-      const double j3 = Js[static_cast<size_t>(t + 3) * ld + m];
-      const double i0 = SOS_IOLD(t), i1 = SOS_IOLD(t + 1), i2 = SOS_IOLD(t + 2), i3 = SOS_IOLD(t + 3);
-      const double d0 = tc0 - tp, d1 = tc1 - tc0, d2 = tc2 - tc1, d3 = tc3 - tc2;
-      const double a0 = exp_small(d0 * imu), a1 = exp_small(d1 * imu), a2 = exp_small(d2 * imu), a3 = exp_small(d3 * imu);
-      const double b0 = (d0 * 0.5) * (Jp * a0 + j0) * imu;
-      const double b1 = (d1 * 0.5) * (j0 * a1 + j1) * imu;
-      const double b2 = (d2 * 0.5) * (j1 * a2 + j2) * imu;
-      const double b3 = (d3 * 0.5) * (j2 * a3 + j3) * imu;
-      D = D * a0 - b0; SOS_EMIT(t, D, i0);
-      D = D * a1 - b1; SOS_EMIT(t + 1, D, i1);
-      D = D * a2 - b2; SOS_EMIT(t + 2, D, i2);
-      D = D * a3 - b3; SOS_EMIT(t + 3, D, i3);
-      Jp = j3;
-      tp = tc3;
+    auto body = [&](auto gen_tag) {
+      for (; t + 3 < t1; t += 4) {
+        const double tc0 = tau[t], tc1 = tau[t + 1], tc2 = tau[t + 2], tc3 = tau[t + 3];
+        const double j0 = jrow(gen_tag, t), j1 = jrow(gen_tag, t + 1), j2 = jrow(gen_tag, t + 2), j3 = jrow(gen_tag, t + 3);
+        const double i0 = iold(t), i1 = iold(t + 1), i2 = iold(t + 2), i3 = iold(t + 3);
+        const double d0 = tc0 - tp, d1 = tc1 - tc0, d2 = tc2 - tc1, d3 = tc3 - tc2;
+        const double a0 = exp_small(d0 * imu), a1 = exp_small(d1 * imu), a2 = exp_small(d2 * imu), a3 = exp_small(d3 * imu);
+        const double b0 = (d0 * 0.5) * (Jp * a0 + j0) * imu;
+        const double b1 = (d1 * 0.5) * (j0 * a1 + j1) * imu;
+        const double b2 = (d2 * 0.5) * (j1 * a2 + j2) * imu;
+        const double b3 = (d3 * 0.5) * (j2 * a3 + j3) * imu;
+        const double D0 = D * a0 - b0, D1 = D0 * a1 - b1, D2 = D1 * a2 - b2, D3 = D2 * a3 - b3;
+        emit(t, D0, i0);
+        emit(t + 1, D1, i1);
+        emit(t + 2, D2, i2);
+        emit(t + 3, D3, i3);
+        project4(t, 1, D0, D1, D2, D3);
+        D = D3;
+        Jp = j3;
+        tp = tc3;
+      }
+      for (; t < t1; ++t) {
+        const double tc = tau[t];
+        const double jc = jrow(gen_tag, t);
+        const double io = iold(t);
+        const double d = tc - tp;
+        const double a = exp_small(d * imu);
+        D = D * a - (d * 0.5) * (Jp * a + jc) * imu;
+        emit(t, D, io);
+        project1(t, D);
+        Jp = jc;
+        tp = tc;
+      }
+    };
+    if (cg) {
+      // rebuilt source: running pointers, the short polynomial where every step of the group is tiny; the surface row
+      // (I_n stored in every column) is left to the tail loop
+      const int tend = (t1 == L) ? t1 - 1 : t1;
+      const double2* __restrict__ pc = src.cj2 + t;
+      const double* __restrict__ pt = tau + t;
+      double* pI = Ia + static_cast<size_t>(t) * ld + (valid ? m : 0);
+      const ptrdiff_t dIn = Is - Ia, dSv = Sv ? Sv - Ia : 0;
+      const size_t pstep = static_cast<size_t>(sg.nslots) * 2;
+      double* pp = projs + static_cast<size_t>(t) * pstep + (lane >> 4) + ((lane >> 2) & 3) * pstep;
+      const bool writer = (lane & 3) == 0;
+      for (; t + 3 < tend; t += 4, pc += 4, pt += 4, pI += 4 * static_cast<size_t>(ld), pp += 4 * pstep) {
+        double tc[4], jv[4], iv[4], x[4], a[4], Dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          tc[u] = pt[u];
+          const double2 cc = pc[u];
+          jv[u] = fma(cc.y, q, cc.x);
+          iv[u] = valid ? pI[static_cast<size_t>(u) * ld] : 0.0;
+        }
+        double dmax = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double d = tc[u] - (u ? tc[u - 1] : tp);
+          dmax = fmax(dmax, d);
+          x[u] = d * imu;
+        }
+        if (dmax * ximax <= kTinyArg) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = exp_tiny(x[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = exp_small(x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          D = fma(D, a[u], -(0.5 * x[u]) * fma(u ? jv[u - 1] : Jp, a[u], jv[u]));
+          Dv[u] = D;
+        }
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            double* o = pI + static_cast<size_t>(u) * ld;
+            *o = iv[u] + Dv[u];
+            if (keep_in) o[dIn] = Dv[u];
+            if (Sv) o[dSv] = Dv[u];
+          }
+        }
+        double v[8] = {Dv[0] * us0, Dv[1] * us0, Dv[2] * us0, Dv[3] * us0, Dv[0] * us1, Dv[1] * us1, Dv[2] * us1, Dv[3] * us1};
+        const double tot = transpose_reduce8(v, lane);
+        if (writer) *pp = tot;
+        Jp = jv[3];
+        tp = tc[3];
+      }
+      body(std::true_type{});
+    } else {
+      body(std::false_type{});
     }
-    for (; t < t1; ++t) {
-      const double tc = tau[t];
-      const double jc = Js[static_cast<size_t>(t) * ld + m];
-      const double io = SOS_IOLD(t);
-      const double d = tc - tp;
-      const double a = exp_small(d * imu);
-      D = D * a - (d * 0.5) * (Jp * a + jc) * imu;
-      SOS_EMIT(t, D, io);
-      Jp = jc;
-      tp = tc;
-    }
-  } else if (m > M) {
-    double U = carryU[agg];  // value at the carry row (t1, or the surface seed for the last chunk)
+  } else {
+    double U = valid ? carryU[agg] : 0.0;  // value at the carry row (t1, or the surface seed for the last chunk)
     int t = t1 - 1;
     double Jn, tn;
     if (t == L - 1) {
-      Jn = Js[static_cast<size_t>(t) * ld + m];
+      Jn = jany(t);
       tn = tau[t];
-      SOS_EMIT(t, U, SOS_IOLD(t));  // zero-length integral: the surface row is the seed itself
+      emit(t, U, iold(t));  // zero-length integral: the surface row is the seed itself
+      project1(t, U);
       --t;
     } else {
-      Jn = Js[static_cast<size_t>(t + 1) * ld + m];
+      Jn = jany(t + 1);
       tn = tau[t + 1];
       if (g.chunk_region[c + 1] != g.chunk_region[c]) {  // carry gap: pure attenuation on this step
         const double tc = tau[t];
         U = U * exp(-(tn - tc) / mu);
-        SOS_EMIT(t, U, SOS_IOLD(t));
-        Jn = Js[static_cast<size_t>(t) * ld + m];
+        emit(t, U, iold(t));
+        project1(t, U);
+        Jn = jany(t);
         tn = tc;
         --t;
       }
     }
-    for (; t - 3 >= t0; t -= 4) {
-      const double tc0 = tau[t], tc1 = tau[t - 1], tc2 = tau[t - 2], tc3 = tau[t - 3];
-      const double j0 = Js[static_cast<size_t>(t) * ld + m];
-      const double j1 = Js[static_cast<size_t>(t - 1) * ld + m];
-      const double j2 = Js[static_cast<size_t>(t - 2) * ld + m];
-      const double j3 = Js[static_cast<size_t>(t - 3) * ld + m];
-      const double i0 = SOS_IOLD(t), i1 = SOS_IOLD(t - 1), i2 = SOS_IOLD(t - 2), i3 = SOS_IOLD(t - 3);
-      const double d0 = tn - tc0, d1 = tc0 - tc1, d2 = tc1 - tc2, d3 = tc2 - tc3;
-      const double a0 = exp_small(-d0 * imu), a1 = exp_small(-d1 * imu), a2 = exp_small(-d2 * imu), a3 = exp_small(-d3 * imu);
-      const double b0 = (d0 * 0.5) * (j0 + Jn * a0) * imu;
-      const double b1 = (d1 * 0.5) * (j1 + j0 * a1) * imu;
-      const double b2 = (d2 * 0.5) * (j2 + j1 * a2) * imu;
-      const double b3 = (d3 * 0.5) * (j3 + j2 * a3) * imu;
-      U = U * a0 + b0; SOS_EMIT(t, U, i0);
-      U = U * a1 + b1; SOS_EMIT(t - 1, U, i1);
-      U = U * a2 + b2; SOS_EMIT(t - 2, U, i2);
-      U = U * a3 + b3; SOS_EMIT(t - 3, U, i3);
-      Jn = j3;
-      tn = tc3;
-    }
-    for (; t >= t0; --t) {
-      const double tc = tau[t];
-      const double jc = Js[static_cast<size_t>(t) * ld + m];
-      const double io = SOS_IOLD(t);
-      const double d = tn - tc;
-      const double a = exp_small(-d * imu);
-      U = U * a + (d * 0.5) * (jc + Jn * a) * imu;
-      SOS_EMIT(t, U, io);
-      Jn = jc;
-      tn = tc;
+    auto body = [&](auto gen_tag) {
+      for (; t - 3 >= t0; t -= 4) {
+        const double tc0 = tau[t], tc1 = tau[t - 1], tc2 = tau[t - 2], tc3 = tau[t - 3];
+        const double j0 = jrow(gen_tag, t), j1 = jrow(gen_tag, t - 1), j2 = jrow(gen_tag, t - 2), j3 = jrow(gen_tag, t - 3);
+        const double i0 = iold(t), i1 = iold(t - 1), i2 = iold(t - 2), i3 = iold(t - 3);
+        const double d0 = tn - tc0, d1 = tc0 - tc1, d2 = tc1 - tc2, d3 = tc2 - tc3;
+        const double a0 = exp_small(-d0 * imu), a1 = exp_small(-d1 * imu), a2 = exp_small(-d2 * imu), a3 = exp_small(-d3 * imu);
+        const double b0 = (d0 * 0.5) * (j0 + Jn * a0) * imu;
+        const double b1 = (d1 * 0.5) * (j1 + j0 * a1) * imu;
+        const double b2 = (d2 * 0.5) * (j2 + j1 * a2) * imu;
+        const double b3 = (d3 * 0.5) * (j3 + j2 * a3) * imu;
+        const double U0 = U * a0 + b0, U1 = U0 * a1 + b1, U2 = U1 * a2 + b2, U3 = U2 * a3 + b3;
+        emit(t, U0, i0);
+        emit(t - 1, U1, i1);
+        emit(t - 2, U2, i2);
+        emit(t - 3, U3, i3);
+        project4(t, -1, U0, U1, U2, U3);
+        U = U3;
+        Jn = j3;
+        tn = tc3;
+      }
+      for (; t >= t0; --t) {
+        const double tc = tau[t];
+        const double jc = jrow(gen_tag, t);
+        const double io = iold(t);
+        const double d = tn - tc;
+        const double a = exp_small(-d * imu);
+        U = U * a + (d * 0.5) * (jc + Jn * a) * imu;
+        emit(t, U, io);
+        project1(t, U);
+        Jn = jc;
+        tn = tc;
+      }
+    };
+    if (cg) {
+      const int tbeg = (t0 == 0) ? 1 : t0;  // the TOA row (I_n stored in every column) is left to the tail loop
+      const double2* __restrict__ pc = src.cj2 + t;
+      const double* __restrict__ pt = tau + t;
+      double* pI = Ia + static_cast<size_t>(t) * ld + (valid ? m : 0);
+      const ptrdiff_t dIn = Is - Ia, dSv = Sv ? Sv - Ia : 0;
+      const size_t pstep = static_cast<size_t>(sg.nslots) * 2;
+      double* pp = projs + static_cast<size_t>(t) * pstep + (lane >> 4) - ((lane >> 2) & 3) * pstep;
+      const bool writer = (lane & 3) == 0;
+      for (; t - 3 >= tbeg; t -= 4, pc -= 4, pt -= 4, pI -= 4 * static_cast<size_t>(ld), pp -= 4 * pstep) {
+        double tc[4], jv[4], iv[4], x[4], a[4], Uv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          tc[u] = pt[-u];
+          const double2 cc = pc[-u];
+          jv[u] = fma(cc.y, q, cc.x);
+          iv[u] = valid ? *(pI - static_cast<size_t>(u) * ld) : 0.0;
+        }
+        double dmax = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double d = (u ? tc[u - 1] : tn) - tc[u];
+          dmax = fmax(dmax, d);
+          x[u] = -d * imu;
+        }
+        if (dmax * ximax <= kTinyArg) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = exp_tiny(x[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = exp_small(x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          U = fma(U, a[u], -(0.5 * x[u]) * fma(u ? jv[u - 1] : Jn, a[u], jv[u]));
+          Uv[u] = U;
+        }
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            double* o = pI - static_cast<size_t>(u) * ld;
+            *o = iv[u] + Uv[u];
+            if (keep_in) o[dIn] = Uv[u];
+            if (Sv) o[dSv] = Uv[u];
+          }
+        }
+        double v[8] = {Uv[0] * us0, Uv[1] * us0, Uv[2] * us0, Uv[3] * us0, Uv[0] * us1, Uv[1] * us1, Uv[2] * us1, Uv[3] * us1};
+        const double tot = transpose_reduce8(v, lane);
+        if (writer) *pp = tot;
+        Jn = jv[3];
+        tn = tc[3];
+      }
+      body(std::true_type{});
+    } else {
+      body(std::false_type{});
     }
   }
-#undef SOS_IOLD
-#undef SOS_EMIT
 }
 
 // Row-wise post-processing of the columns next to mu = 0: windowed / Taylor columns
@@ -561,20 +917,21 @@ sweep_apply_kernel(const GridDev g, const double* __restrict__ J, double* __rest
 // the find-first second-difference blend (:101-108) and, on the TOA / surface rows, the convergence
 // ratios of SOS_Aer_main_specular.py:309.  ONE WARP per (layer, scenario): it reads the ~40 raw values
 // it needs, rewrites only the columns that change and corrects I by (new - raw) for those the apply
-// pass had already accumulated.
+// pass had already accumulated.  With a generated source it also finishes the next order's coefficients of its row:
+// projections of the zone columns (final values) + the apply pass's slots.
 constexpr int ZONE_ROWS = 8;
 
 __global__ void __launch_bounds__(32 * ZONE_ROWS)  // (forcing 6 or 8 CTAs per SM spills and is slower: 0.755 vs 0.744 ms per order)
-sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restrict__ In,
+sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, double* __restrict__ In,
                   double* __restrict__ I, double* __restrict__ saved, int zone_buf) {
-  extern __shared__ double sm_zone[];  // ZONE_ROWS x zone_buf: raw downward values of columns [zl, M)
+  extern __shared__ double sm_zone[];  // ZONE_ROWS x zone_buf: downward values of columns [zl, M)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.y, t = blockIdx.x * ZONE_ROWS + warp;
   const int L = g.L, M = g.M, ld = g.ld;
   if (t >= L || !g.state[s].active) return;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
   const size_t fbase = static_cast<size_t>(s) * L * ld;
-  const double* __restrict__ Js = J + fbase;
+  const SrcAt src(g, sg, J, s);
   double* __restrict__ Is = In + fbase;
   double* __restrict__ Ia = I ? I + fbase : nullptr;
   double* __restrict__ Sv = saved ? saved + fbase : nullptr;
@@ -584,9 +941,13 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
   const int c_lo = g.col0, c_hi = g.col1;
   const bool own_down_zone = (c_lo < M && c_hi >= M);
   const bool own_up_zone = (c_lo <= M && c_hi > M + 1);
+  const bool project = src.gen_row(t);  // this row's I_n feeds a rebuilt source: finish its coefficients
+  const double* __restrict__ Ut = sg.Ut[sc.phase_atm];
+  double p0 = 0.0, p1 = 0.0;
 
   if (own_down_zone) {
-    const int zl = zone_lo(g, sc);
+    // with a generated source the zone is the plan-wide one (the apply pass left those columns out of its projections)
+    const int zl = src.gen ? sg.zlo : zone_lo(g, sc);
     double* row = sm_zone + static_cast<size_t>(warp) * zone_buf - zl;  // row[m] valid for m in [zl, M)
     for (int m = zl + lane; m < M; m += 32) {
       const bool std_col = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
@@ -598,7 +959,7 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
     // non-standard columns that survive the extrapolation: computed here, never touched by the apply pass
     const int hi = min(M - 1, M - idxw);
     for (int m = g.first_small; m < hi; ++m) {
-      const double v = asymptotic_column(g, Js, tau, t, r0, m);
+      const double v = asymptotic_column(g, src, tau, t, r0, m);
       if (lane == 0) {
         row[m] = v;
         Is[roff + m] = v;
@@ -617,26 +978,35 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
         double v = 0.0;
         for (int k = 0; k < ns; ++k) v += W[i * ns + k] * row[src0 + k];
         const bool std_col = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
+        const double raw = row[m];
+        row[m] = v;
         Is[roff + m] = v;
         if (Sv) Sv[roff + m] = v;
-        if (Ia) Ia[roff + m] += std_col ? (v - row[m]) : v;  // standard targets were accumulated raw
+        if (Ia) Ia[roff + m] += std_col ? (v - raw) : v;  // standard targets were accumulated raw
       }
     } else if (lane == 0) {
+      row[M - 1] = 0.0;
       Is[roff + M - 1] = 0.0;  // mu = 0- stays 0 when nothing is extrapolated
       if (Sv) Sv[roff + M - 1] = 0.0;
     }
     __syncwarp();
+    if (project) {
+      for (int m = zl + lane; m < M; m += 32) {
+        p0 = fma(row[m], Ut[m], p0);
+        p1 = fma(row[m], Ut[sg.ldr + m], p1);
+      }
+    }
   }
 
   if (own_up_zone) {
-    const double v0 = Js[roff + M];  // I_n[t, mu = 0+] = J[t, mu = 0+]
+    const double v0 = src(t, M, g.mu[M]);  // I_n[t, mu = 0+] = J[t, mu = 0+]
     if (lane == 0) {
       Is[roff + M] = v0;
       if (Sv) Sv[roff + M] = v0;
       if (Ia) Ia[roff + M] += v0;
     }
-    // find-first over the raw values written by the apply pass
-    const int lim = c_hi;  // the search never leaves the owned columns
+    // find-first over the raw values written by the apply pass (with a generated source they exist up to zu_end)
+    const int lim = src.gen ? min(c_hi, sg.zu_end) : c_hi;  // the search never leaves the owned columns
     int istar = -1;
     for (int base = M + 1; base + 2 <= lim - 1 && istar < 0; base += 32) {
       const int i = base + lane;
@@ -649,7 +1019,7 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
       if (mask) istar = base + __ffs(mask) - 1 + 1;
     }
     if (istar < 0) {
-      if (lane == 0) atomicOr(&g.state[s].status, SOS_STATUS_BLEND_OVERRUN);
+      if (lane == 0) atomicOr(&g.state[s].status, (lim >= g.N) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
     } else {
       const double v1 = Is[roff + istar];
       const double mus = g.mu[istar];
@@ -664,6 +1034,23 @@ sweep_zone_kernel(const GridDev g, const double* __restrict__ J, double* __restr
       }
     }
     __syncwarp();
+  }
+
+  if (project) {
+    // the next order's source coefficients of this row: zone columns (final values) + the apply pass's slots
+    __threadfence_block();
+    __syncwarp();
+    for (int m = M + lane; m < min(sg.zu_end, g.N); m += 32) {
+      const double v = Is[roff + m];
+      p0 = fma(v, Ut[m], p0);
+      p1 = fma(v, Ut[sg.ldr + m], p1);
+    }
+    const double* __restrict__ pr = sg.proj + (fbase / ld + t) * sg.nslots * 2;
+    for (int j = lane; j < sg.nslots; j += 32) { p0 += pr[2 * j]; p1 += pr[2 * j + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { p0 += shfl_xor_d(p0, o); p1 += shfl_xor_d(p1, o); }
+    if (lane == 0)
+      *reinterpret_cast<double2*>(sg.cj_out + (static_cast<size_t>(s) * sg.Lp + t) * 2) = make_double2(sc.coef_atm * p0, sc.coef_atm * p1);
   }
 
   // ---- convergence ratios on the TOA / surface rows (whole half-row, read back from global) ----
@@ -782,6 +1169,30 @@ __global__ void ratios_kernel(const GridDev g, double* buf, int set) {
   if (s >= g.S) return;
   if (set) { g.state[s].ratio_toa = buf[2 * s]; g.state[s].ratio_surf = buf[2 * s + 1]; }
   else { buf[2 * s] = g.state[s].ratio_toa; buf[2 * s + 1] = g.state[s].ratio_surf; }
+}
+
+// Source coefficients of a whole field (the first order, before the loop): cj[s][t][r] = coef * sum_k I[t, k] Us[k][r]
+__global__ void __launch_bounds__(256) project_rows_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ I, double* __restrict__ cj) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.y, t = blockIdx.x * 8 + warp;
+  if (t >= g.L) return;
+  const int op = g.scen[s].phase_atm;
+  if (sg.rank[op] == 0) return;
+  const double* __restrict__ Ut = sg.Ut[op];
+  const double* __restrict__ row = I + (static_cast<size_t>(s) * g.L + t) * g.ld;
+  double p0 = 0.0, p1 = 0.0;
+  for (int m = lane; m < g.N; m += 32) {
+    const double x = row[m];
+    p0 = fma(x, Ut[m], p0);
+    p1 = fma(x, Ut[sg.ldr + m], p1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    p0 += shfl_xor_d(p0, o);
+    p1 += shfl_xor_d(p1, o);
+  }
+  const double coef = g.scen[s].coef_atm;
+  if (lane == 0) *reinterpret_cast<double2*>(cj + (static_cast<size_t>(s) * sg.Lp + t) * 2) = make_double2(coef * p0, coef * p1);
 }
 
 __global__ void count_active_kernel(const GridDev g, int* strip_ticket) {

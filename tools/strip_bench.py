@@ -29,11 +29,11 @@ for _ in range(reps):
     res = bs.solve(poll_every=2)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    ms2 = (C.c_double * 2)()
-    sp2 = (C.c_longlong * 2)()
+    ms2 = (C.c_double * 4)()
+    sp2 = (C.c_longlong * 4)()
     lib.sos_get_profile(eng._plan, ms2, sp2, None)
     lib.sos_set_profiling(eng._plan, 0)
     elems = norders * 800 * 1002
-    print(f"solve {dt * 1e3:.2f} ms | contraction {ms2[0]:.2f} ms / {sp2[0]} launches | sweeps {ms2[1]:.2f} ms / {sp2[1]} launches "
+    print(f"solve {dt * 1e3:.2f} ms | contraction {ms2[0]:.2f} ms / {sp2[0]} launches (dense {ms2[3]:.2f}) | sweeps {ms2[1]:.2f} ms / {sp2[1]} launches (apply {ms2[2]:.2f}) "
           f"| sweeps: {32 * elems / (ms2[1] * 1e-3) * 1e-9:.0f} GB/s at 32 B/elem, {elems / (ms2[1] * 1e-3) * 1e-9:.1f} Gelem/s "
           f"| orders {int(res.n_orders.min())}..{int(res.n_orders.max())}", flush=True)
