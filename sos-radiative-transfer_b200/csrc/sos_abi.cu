@@ -313,8 +313,9 @@ int strip_setup(sos_plan* p, const sos_scenario* scen_h) {
   const int L = g.L, M = g.M, N = g.N, S = g.S;
   p->strip_ok = false;
   if (strip_env_int("SOS_B200_STRIP", 1) == 0) return SOS_OK;
-  const int T = sossweep::LOCAL_THREADS;
-  const int nslots = ((M - 1 + T - 1) / T + (N - M - 1 + T - 1) / T) * (T / 32);  // one per warp of the apply pass
+  // one projection slot per warp of the apply pass: two columns per thread on grids with odd M (sweep_apply2_kernel)
+  const int T = (M & 1) ? 2 * sossweep::APPLY2_THREADS : sossweep::LOCAL_THREADS;
+  const int nslots = ((M - 1 + T - 1) / T + (N - M - 1 + T - 1) / T) * 4;
   int r;
   if ((r = dev_alloc(p, &p->d_proj, static_cast<size_t>(S) * L * nslots * 2))) return r;
   for (int i = 0; i < 2; ++i)
@@ -1325,7 +1326,14 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
   }
   {
     ProfSpan apply_span(p, 2, st);
-    sossweep::sweep_apply_kernel<<<cgrid, T, 0, st>>>(g, sg, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
+    if ((g.M & 1) && g.col0 == 0 && g.col1 == g.N && I_d) {
+      // odd M: every column pair is 16-byte aligned and inside one half -> two columns per thread
+      const int T2 = 2 * sossweep::APPLY2_THREADS;
+      dim3 grid2((g.M - 1 + T2 - 1) / T2 + (g.N - g.M - 1 + T2 - 1) / T2, g.nchunks, g.S);
+      sossweep::sweep_apply2_kernel<<<grid2, sossweep::APPLY2_THREADS, 0, st>>>(g, sg, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
+    } else {
+      sossweep::sweep_apply_kernel<<<cgrid, T, 0, st>>>(g, sg, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
+    }
     int r = launch_check(p, "sweep_apply_kernel");
     if (r) return r;
   }

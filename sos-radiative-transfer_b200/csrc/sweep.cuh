@@ -149,6 +149,16 @@ __device__ __forceinline__ double warp_max_d(double v) {
   return v;
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 constexpr int LOCAL_THREADS = 128;
 constexpr int LOCAL_UNROLL = 4;  // (8 rows in flight was measured: lower occupancy, 0.756 vs 0.744 ms per order at S = 96)
 constexpr int ROW_THREADS = 256;
@@ -645,7 +655,6 @@ sweep_apply_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
   const double mu = valid ? mu_raw : (up ? 1.0 : -1.0);
   const double imu = 1.0 / mu;  // one division per thread; the scan steps multiply
   const double q = mu * mu;
-  const double ximax = warp_max_d(fabs(imu));  // the short exp polynomial is chosen per warp (uniform branch)
   const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * g.N + (valid ? m : 0);
   const bool cg = src.gen_row(t0);  // the whole chunk is rebuilt, or read
   const bool zonecol = up ? (m < sg.zu_end) : (m >= sg.zlo);
@@ -738,64 +747,7 @@ sweep_apply_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
         tp = tc;
       }
     };
-    if (cg) {
-      // rebuilt source: running pointers, the short polynomial where every step of the group is tiny; the surface row
-      // (I_n stored in every column) is left to the tail loop
-      const int tend = (t1 == L) ? t1 - 1 : t1;
-      const double2* __restrict__ pc = src.cj2 + t;
-      const double* __restrict__ pt = tau + t;
-      double* pI = Ia + static_cast<size_t>(t) * ld + (valid ? m : 0);
-      const ptrdiff_t dIn = Is - Ia, dSv = Sv ? Sv - Ia : 0;
-      const size_t pstep = static_cast<size_t>(sg.nslots) * 2;
-      double* pp = projs + static_cast<size_t>(t) * pstep + (lane >> 4) + ((lane >> 2) & 3) * pstep;
-      const bool writer = (lane & 3) == 0;
-      for (; t + 3 < tend; t += 4, pc += 4, pt += 4, pI += 4 * static_cast<size_t>(ld), pp += 4 * pstep) {
-        double tc[4], jv[4], iv[4], x[4], a[4], Dv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          tc[u] = pt[u];
-          const double2 cc = pc[u];
-          jv[u] = fma(cc.y, q, cc.x);
-          iv[u] = valid ? pI[static_cast<size_t>(u) * ld] : 0.0;
-        }
-        double dmax = 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const double d = tc[u] - (u ? tc[u - 1] : tp);
-          dmax = fmax(dmax, d);
-          x[u] = d * imu;
-        }
-        if (dmax * ximax <= kTinyArg) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = exp_tiny(x[u]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = exp_small(x[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          D = fma(D, a[u], -(0.5 * x[u]) * fma(u ? jv[u - 1] : Jp, a[u], jv[u]));
-          Dv[u] = D;
-        }
-        if (valid) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            double* o = pI + static_cast<size_t>(u) * ld;
-            *o = iv[u] + Dv[u];
-            if (keep_in) o[dIn] = Dv[u];
-            if (Sv) o[dSv] = Dv[u];
-          }
-        }
-        double v[8] = {Dv[0] * us0, Dv[1] * us0, Dv[2] * us0, Dv[3] * us0, Dv[0] * us1, Dv[1] * us1, Dv[2] * us1, Dv[3] * us1};
-        const double tot = transpose_reduce8(v, lane);
-        if (writer) *pp = tot;
-        Jp = jv[3];
-        tp = tc[3];
-      }
-      body(std::true_type{});
-    } else {
-      body(std::false_type{});
-    }
+    if (cg) body(std::true_type{}); else body(std::false_type{});
   } else {
     double U = valid ? carryU[agg] : 0.0;  // value at the carry row (t1, or the surface seed for the last chunk)
     int t = t1 - 1;
@@ -853,62 +805,299 @@ sweep_apply_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
         tn = tc;
       }
     };
-    if (cg) {
-      const int tbeg = (t0 == 0) ? 1 : t0;  // the TOA row (I_n stored in every column) is left to the tail loop
-      const double2* __restrict__ pc = src.cj2 + t;
-      const double* __restrict__ pt = tau + t;
-      double* pI = Ia + static_cast<size_t>(t) * ld + (valid ? m : 0);
-      const ptrdiff_t dIn = Is - Ia, dSv = Sv ? Sv - Ia : 0;
-      const size_t pstep = static_cast<size_t>(sg.nslots) * 2;
-      double* pp = projs + static_cast<size_t>(t) * pstep + (lane >> 4) - ((lane >> 2) & 3) * pstep;
-      const bool writer = (lane & 3) == 0;
-      for (; t - 3 >= tbeg; t -= 4, pc -= 4, pt -= 4, pI -= 4 * static_cast<size_t>(ld), pp -= 4 * pstep) {
-        double tc[4], jv[4], iv[4], x[4], a[4], Uv[4];
+    if (cg) body(std::true_type{}); else body(std::false_type{});
+  }
+}
+
+// The apply pass with TWO adjacent columns per thread (16-byte accesses: 2 KB per row and CTA, half the per-row
+// overhead per element) for grids with an odd number of angles per half (the reference's: the first upward column
+// M + 1 is then even, so every pair is 16-byte aligned and lies inside one half).  Same recurrences, same outputs;
+// the projections of a group of four rows are reduced through a small per-warp buffer in shared memory.
+constexpr int APPLY2_THREADS = 128;
+constexpr int APPLY2_RING = 4;   // groups of four rows in the I ring: three in flight (12 rows, 24 KB per CTA) + the one consumed
+constexpr int APPLY2_STAGE = 160;  // longest chunk whose per-row scalars are staged in shared memory
+constexpr int PROJ_STRIDE = 34;  // doubles per row of the per-warp buffer (16-byte aligned rows, conflict-free 128-bit reads)
+
+// v[0..7] of every lane -> the sum over the warp of v[lane >> 2], in the four lanes of quad lane >> 2 (fixed order)
+__device__ __forceinline__ double quad_reduce8(double* buf, const double (&v)[8], int lane) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          tc[u] = pt[-u];
-          const double2 cc = pc[-u];
-          jv[u] = fma(cc.y, q, cc.x);
-          iv[u] = valid ? *(pI - static_cast<size_t>(u) * ld) : 0.0;
-        }
-        double dmax = 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const double d = (u ? tc[u - 1] : tn) - tc[u];
-          dmax = fmax(dmax, d);
-          x[u] = -d * imu;
-        }
-        if (dmax * ximax <= kTinyArg) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = exp_tiny(x[u]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = exp_small(x[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          U = fma(U, a[u], -(0.5 * x[u]) * fma(u ? jv[u - 1] : Jn, a[u], jv[u]));
-          Uv[u] = U;
-        }
-        if (valid) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            double* o = pI - static_cast<size_t>(u) * ld;
-            *o = iv[u] + Uv[u];
-            if (keep_in) o[dIn] = Uv[u];
-            if (Sv) o[dSv] = Uv[u];
-          }
-        }
-        double v[8] = {Uv[0] * us0, Uv[1] * us0, Uv[2] * us0, Uv[3] * us0, Uv[0] * us1, Uv[1] * us1, Uv[2] * us1, Uv[3] * us1};
-        const double tot = transpose_reduce8(v, lane);
-        if (writer) *pp = tot;
-        Jn = jv[3];
-        tn = tc[3];
-      }
-      body(std::true_type{});
-    } else {
-      body(std::false_type{});
+  for (int i = 0; i < 8; ++i) buf[i * PROJ_STRIDE + lane] = v[i];
+  __syncwarp();
+  const double2* row = reinterpret_cast<const double2*>(buf + (lane >> 2) * PROJ_STRIDE + (lane & 3) * 8);
+  const double2 a = row[0], b = row[1], c = row[2], d = row[3];
+  double sum = ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
+  sum += shfl_xor_d(sum, 1);
+  sum += shfl_xor_d(sum, 2);
+  __syncwarp();
+  return sum;
+}
+
+__global__ void __launch_bounds__(APPLY2_THREADS, 4)
+sweep_apply2_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, double* __restrict__ In,
+                    const double* __restrict__ carryD, const double* __restrict__ carryU,
+                    double* __restrict__ I, double* __restrict__ saved) {
+  __shared__ __align__(16) double s_proj[APPLY2_THREADS / 32][8 * PROJ_STRIDE];
+  __shared__ __align__(16) double2 s_ring[APPLY2_RING * 4 * APPLY2_THREADS];
+  __shared__ __align__(16) double2 s_cj[APPLY2_STAGE];
+  __shared__ double s_tau[APPLY2_STAGE];
+  const int s = blockIdx.z;
+  if (!g.state[s].active) return;
+  const int c = blockIdx.y;
+  const int L = g.L, M = g.M, N = g.N, ld = g.ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nbd = ((M - 1) / 2 + APPLY2_THREADS - 1) / APPLY2_THREADS;
+  const bool up = static_cast<int>(blockIdx.x) >= nbd;
+  const int m0 = (up ? M + 1 : 0) + 2 * ((up ? blockIdx.x - nbd : blockIdx.x) * APPLY2_THREADS + threadIdx.x);
+  const bool live = up ? (m0 < N) : (m0 < M - 1);
+  const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
+  const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
+  const size_t fbase = static_cast<size_t>(s) * L * ld;
+  const SrcAt src(g, sg, J, s);
+  const bool cg = src.gen_row(t0);  // the whole chunk is rebuilt, or read
+  // the per-row scalars of the chunk (tau, source coefficients) go to shared memory once: read row by row from global
+  // they cost an exposed L2 round trip per step of the main loop
+  const bool staged = t1 - t0 <= APPLY2_STAGE;
+  if (staged) {
+    for (int i = threadIdx.x; i < t1 - t0; i += APPLY2_THREADS) {
+      s_tau[i] = tau[t0 + i];
+      if (cg) s_cj[i] = src.cj2[t0 + i];
     }
+    __syncthreads();
+  }
+  const int op = g.scen[s].phase_atm;
+  const size_t agg = (static_cast<size_t>(s) * g.nchunks + c) * N;
+  bool stdc[2], anyzone = false;
+  double mu[2], imu[2], q[2], us0[2], us1[2], X[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int m = m0 + k;
+    mu[k] = live ? g.mu[m] : (up ? 1.0 : -1.0);
+    stdc[k] = live && (up || fabs(mu[k]) >= SOS_MU_THRESHOLD);  // windowed / Taylor columns are row-local (sweep_zone_kernel)
+    // columns without a recurrence get a zero exponent: a = 1, b = 0, their X stays 0 and I is written back unchanged
+    imu[k] = stdc[k] ? 1.0 / mu[k] : 0.0;
+    q[k] = mu[k] * mu[k];
+    const bool zonecol = up ? (m < sg.zu_end) : (m >= sg.zlo);
+    anyzone |= zonecol;
+    const bool projected = cg && stdc[k] && !zonecol;
+    us0[k] = projected ? sg.Ut[op][m] : 0.0;
+    us1[k] = projected ? sg.Ut[op][sg.ldr + m] : 0.0;
+    X[k] = 0.0;
+    if (stdc[k]) X[k] = up ? carryU[agg + m] : (t0 > 0 ? carryD[agg + m] : 0.0);
+  }
+  const bool act = stdc[0] || stdc[1];                   // this thread stores
+  if (!__any_sync(0xffffffffu, act)) return;
+  const bool keep_in = !cg || anyzone || sg.store_all;   // I_n of this pair is read by someone on every row
+  const int forced = up ? 0 : L - 1;                     // the row whose I_n everybody stores: ratios, surface coupling
+  const double ximax = warp_max_d(fmax(fabs(imu[0]), fabs(imu[1])));  // the exp polynomial is chosen per warp
+  const int ldv = ld / 2;
+  double2* const Iv = reinterpret_cast<double2*>(I + fbase + (act ? m0 : 0));
+  double2* const Nv = reinterpret_cast<double2*>(In + fbase + (act ? m0 : 0));
+  double2* const Sv = saved ? reinterpret_cast<double2*>(saved + fbase + (act ? m0 : 0)) : nullptr;
+  const double2* const Jv = reinterpret_cast<const double2*>(src.Js + (act ? m0 : 0));
+  const size_t pstep = static_cast<size_t>(sg.nslots) * 2;
+  double* const projs = cg ? sg.proj + ((fbase / ld) * sg.nslots + blockIdx.x * (APPLY2_THREADS / 32) + warp) * 2 : nullptr;
+  double* const pbuf = s_proj[warp];
+  const double sgn = up ? -1.0 : 1.0;  // x = sgn * dtau / mu is the (negative) exponent of the attenuation in either direction
+
+  // J[t, m0 + k] of any row (rows of this chunk and the one next to it)
+  auto jpair = [&](int t, double (&j)[2]) {
+    if (src.gen_row(t)) {
+      const double2 cc = src.cj2[t];
+      j[0] = fma(cc.y, q[0], cc.x);
+      j[1] = fma(cc.y, q[1], cc.x);
+    } else if (act) {
+      const double2 jv = Jv[static_cast<size_t>(t) * ldv];
+      j[0] = jv.x;
+      j[1] = jv.y;
+    } else {
+      j[0] = j[1] = 0.0;
+    }
+  };
+  auto emit = [&](int t, const double (&v)[2]) {
+    if (act) {
+      const size_t o = static_cast<size_t>(t) * ldv;
+      const double2 iv = Iv[o];
+      Iv[o] = make_double2(iv.x + v[0], iv.y + v[1]);
+      if (keep_in || t == forced) Nv[o] = make_double2(v[0], v[1]);
+      if (Sv) Sv[o] = make_double2(v[0], v[1]);
+    }
+  };
+  auto project1 = [&](int t, const double (&v)[2]) {
+    if (!cg) return;
+    double p0 = fma(v[1], us0[1], v[0] * us0[0]), p1 = fma(v[1], us1[1], v[0] * us1[0]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { p0 += shfl_xor_d(p0, o); p1 += shfl_xor_d(p1, o); }
+    if (lane == 0) *reinterpret_cast<double2*>(projs + static_cast<size_t>(t) * pstep) = make_double2(p0, p1);
+  };
+  // one row of the recurrence: d = |tau step|, jn = J of the row processed before
+  auto step1 = [&](int t, double d, double (&jn)[2]) {
+    double j[2], v[2];
+    jpair(t, j);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double x = sgn * d * imu[k];
+      const double a = exp_small(x);
+      X[k] = fma(X[k], a, -(0.5 * x) * fma(jn[k], a, j[k]));
+      v[k] = stdc[k] ? X[k] : 0.0;
+      jn[k] = j[k];
+    }
+    emit(t, v);
+    project1(t, v);
+  };
+
+  double jn[2];
+  int t;
+  double tn;  // tau of the row processed before
+  if (!up) {
+    t = t0;
+    if (t == 0) {
+      jpair(0, jn);
+      const double z[2] = {0.0, 0.0};
+      emit(0, z);
+      project1(0, z);
+      t = 1;
+    } else {
+      jpair(t - 1, jn);
+    }
+    tn = tau[t - 1 < 0 ? 0 : t - 1];
+  } else {
+    t = t1 - 1;
+    if (t == L - 1) {
+      jpair(t, jn);
+      tn = tau[t];
+      const double v[2] = {stdc[0] ? X[0] : 0.0, stdc[1] ? X[1] : 0.0};
+      emit(t, v);  // zero-length integral: the surface row is the seed itself
+      project1(t, v);
+      --t;
+    } else {
+      jpair(t + 1, jn);
+      tn = tau[t + 1];
+      if (g.chunk_region[c + 1] != g.chunk_region[c]) {  // carry gap: pure attenuation on this step
+        const double tc = tau[t];
+        double v[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          X[k] = X[k] * exp(-(tn - tc) / mu[k]);
+          v[k] = stdc[k] ? X[k] : 0.0;
+        }
+        emit(t, v);
+        project1(t, v);
+        jpair(t, jn);
+        tn = tc;
+        --t;
+      }
+    }
+  }
+
+  // ---- four rows per step; the I rows of the next three steps are already on their way into this thread's private
+  //      slots of a shared-memory ring (cp.async: no registers held, no barrier needed) ----
+  const int dir = up ? -1 : 1;
+  auto main_loop = [&](auto gen_tag) {
+    constexpr bool GEN = decltype(gen_tag)::value;
+    double2* const ring = s_ring + threadIdx.x;  // slot (g, u) of this thread: ring[(g * 4 + u) * APPLY2_THREADS]
+    const ptrdiff_t rstep = static_cast<ptrdiff_t>(dir) * ldv;  // one row, in double2 units
+    const double2* pf = Iv + static_cast<size_t>(t) * ldv;      // first row of the next group to prefetch
+    int pf_t = t, pf_g = 0;
+    auto prefetch = [&]() {
+      if (up ? (pf_t - 3 >= t0) : (pf_t + 3 < t1)) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cp_async16(ring + (pf_g * 4 + u) * APPLY2_THREADS, pf + u * rstep);
+        pf += 4 * rstep;
+        pf_t += 4 * dir;
+      }
+      cp_async_commit();
+      pf_g = (pf_g + 1 == APPLY2_RING) ? 0 : pf_g + 1;
+    };
+#pragma unroll
+    for (int i = 0; i < APPLY2_RING - 1; ++i) prefetch();
+    int cg_slot = 0;
+    double2* po = Iv + static_cast<size_t>(t) * ldv;            // row t of I (I_n / I_saved at fixed offsets from it)
+    const ptrdiff_t dN = Nv - Iv, dS = Sv ? Sv - Iv : 0;
+    const double2* pj = Jv + static_cast<size_t>(t) * ldv;
+    const double2* pc = GEN ? (staged ? s_cj + (t - t0) : src.cj2 + t) : nullptr;
+    const double* pt = staged ? s_tau + (t - t0) : tau + t;
+    double* pp = GEN ? projs + static_cast<size_t>(t) * pstep + (lane >> 4) + static_cast<ptrdiff_t>(dir) * ((lane >> 2) & 3) * static_cast<ptrdiff_t>(pstep) : nullptr;
+    while (up ? (t - 3 >= t0) : (t + 3 < t1)) {
+      double tc[4], j[4][2], x[4][2], a[4][2], v[4][2];
+      double2 iv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        tc[u] = pt[dir * u];
+        if (GEN) {
+          const double2 cc = pc[dir * u];
+          j[u][0] = fma(cc.y, q[0], cc.x);
+          j[u][1] = fma(cc.y, q[1], cc.x);
+        } else {
+          const double2 jv = pj[u * rstep];
+          j[u][0] = jv.x;
+          j[u][1] = jv.y;
+        }
+      }
+      double dmax = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double d = up ? ((u ? tc[u - 1] : tn) - tc[u]) : (tc[u] - (u ? tc[u - 1] : tn));
+        dmax = fmax(dmax, d);
+        x[u][0] = sgn * d * imu[0];
+        x[u][1] = sgn * d * imu[1];
+      }
+      if (dmax * ximax <= kTinyArg) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u][0] = exp_tiny(x[u][0]); a[u][1] = exp_tiny(x[u][1]); }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u][0] = exp_small(x[u][0]); a[u][1] = exp_small(x[u][1]); }
+      }
+      // (columns without a recurrence have x = 0: a = 1, b = 0, X stays 0 -- no select needed)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          X[k] = fma(X[k], a[u][k], -(0.5 * x[u][k]) * fma(u ? j[u - 1][k] : jn[k], a[u][k], j[u][k]));
+          v[u][k] = X[k];
+        }
+      cp_async_wait<APPLY2_RING - 2>();  // this group's I rows have landed
+#pragma unroll
+      for (int u = 0; u < 4; ++u) iv[u] = ring[(cg_slot * 4 + u) * APPLY2_THREADS];
+      prefetch();  // refills the slot consumed in the previous step
+      if (act) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          double2* o = po + u * rstep;
+          *o = make_double2(iv[u].x + v[u][0], iv[u].y + v[u][1]);
+          if (!GEN || keep_in || t + dir * u == forced) o[dN] = make_double2(v[u][0], v[u][1]);
+          if (Sv) o[dS] = make_double2(v[u][0], v[u][1]);
+        }
+      }
+      if (GEN) {
+        double pv[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          pv[u] = fma(v[u][1], us0[1], v[u][0] * us0[0]);
+          pv[4 + u] = fma(v[u][1], us1[1], v[u][0] * us1[0]);
+        }
+        const double tot = quad_reduce8(pbuf, pv, lane);
+        if ((lane & 3) == 0) *pp = tot;
+        pp += 4 * static_cast<ptrdiff_t>(dir) * static_cast<ptrdiff_t>(pstep);
+        pc += 4 * dir;
+      }
+      jn[0] = j[3][0];
+      jn[1] = j[3][1];
+      tn = tc[3];
+      t += 4 * dir;
+      po += 4 * rstep;
+      pj += 4 * rstep;
+      pt += 4 * dir;
+      cg_slot = (cg_slot + 1 == APPLY2_RING) ? 0 : cg_slot + 1;
+    }
+    cp_async_wait<0>();
+  };
+  if (cg) main_loop(std::true_type{}); else main_loop(std::false_type{});
+  // ---- tail rows ----
+  for (; up ? (t >= t0) : (t < t1); t += dir) {
+    const double tc = tau[t];
+    step1(t, up ? tn - tc : tc - tn, jn);
+    tn = tc;
   }
 }
 

@@ -97,6 +97,28 @@ class PhaseCache:
 _PHASES = PhaseCache()
 
 
+def clear_caches(disk: bool = False):
+    """Forget everything the process keeps between solves: host phase tables, device-resident contraction operands and
+    their folded / low-rank companions, the drop-in API's engines (what a cold start pays for again; bench.py's
+    e2e_cold).  disk=True also removes the parameter-keyed Mie tables from mie.cache_dir()."""
+    from . import api, engine as E, mie
+    global _PHASES
+    _PHASES._P.clear()
+    _PHASES._P0.clear()
+    api.clear_cache()
+    for d in (E._OPERANDS, E._FOLDED, E._LOWRANK):
+        d.clear()
+    mie.lognormal_table.cache_clear()
+    if disk:
+        import glob
+        import os
+        for f in glob.glob(os.path.join(mie.cache_dir(), "mie_lognormal_*.npy")):
+            try:
+                os.remove(f)
+            except OSError:
+                pass
+
+
 class _DeviceBuilt:
     """Placeholder for a phase matrix that SosEngine.set_phase builds on the device when (and only
     when) the operand cache misses."""

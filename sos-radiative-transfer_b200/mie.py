@@ -26,9 +26,12 @@ interpolate_fwc_phase (:202-236) and mixing commutes with it.
 from __future__ import annotations
 
 import functools
+import hashlib
+import os
 
 import numpy as np
 
+CACHE_VERSION = 1                     # bump when the table's definition changes
 N_ANGLES_TABLE = 6001                 # compute_P, SOS_Aer_phase_func.py:685
 RADII = (0.01, 10.0, 100)             # list_radius = linspace(0.01, 10, 100) micrometres, :404-405
 
@@ -95,18 +98,59 @@ def i_unpolarized(m: complex, x: float, mu) -> np.ndarray:
     return (np.abs(S1) ** 2 + np.abs(S2) ** 2) / 2.0 / (np.pi * x ** 2 * qext)
 
 
+def cache_dir() -> str:
+    """Directory of the parameter-keyed table cache: $SOS_B200_CACHE, else ~/.cache/sos_b200."""
+    return os.environ.get("SOS_B200_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "sos_b200")
+
+
+def _table_path(wl, n_re, n_im, r_m, sig, as_coded) -> str:
+    # Every parameter the table depends on is in the file name (the reference keys its .npy cache in the working
+    # directory on nb_angles and a few scenario numbers only, so stale tables survive a change of refractive index:
+    # SOS_Aer_global_va.py:17-83, SOS_Aer_phase_func.py:24-33 -- Q16), plus a format version.
+    key = repr((CACHE_VERSION, float(wl), float(n_re), float(abs(n_im)), float(r_m), float(sig), bool(as_coded), RADII, N_ANGLES_TABLE))
+    return os.path.join(cache_dir(), "mie_lognormal_" + hashlib.sha1(key.encode()).hexdigest()[:20] + ".npy")
+
+
 @functools.lru_cache(maxsize=8)
 def lognormal_table(wl: float, n_re: float, n_im: float, r_m: float, sig: float, as_coded: bool = True):
     """(cos Theta grid (6001,), mixture phase function on it) of a log-normal population of spheres.
 
     SOS_Aer_phase_func.py:404-421 (radii, n(r), Qsca weights), :684-694 (per-radius phase functions), :713-753
     (mixture = trapz over the radius of n(r) Qsca(r) p_r).  The overall scale is irrelevant: P0 and every column of P
-    are normalised afterwards (:131)."""
+    are normalised afterwards (:131).
+
+    The table is cached in memory (per process) and on disk as a .npy file keyed on every parameter (cache_dir();
+    SOS_B200_CACHE=off disables the disk cache): the Lorenz-Mie series over 200 radii x 6001 angles takes seconds."""
+    mu_s = np.linspace(-1.0, 1.0, N_ANGLES_TABLE)
+    mu_s.setflags(write=False)
+    path = None if os.environ.get("SOS_B200_CACHE", "") == "off" else _table_path(wl, n_re, n_im, r_m, sig, as_coded)
+    if path and os.path.exists(path):
+        try:
+            mix = np.load(path)
+            if mix.shape == (N_ANGLES_TABLE,) and mix.dtype == np.float64 and np.all(np.isfinite(mix)):
+                mix.setflags(write=False)
+                return mu_s, mix
+        except (OSError, ValueError):
+            pass  # unreadable file: rebuild and overwrite
+    mix = _lognormal_mixture(wl, n_re, n_im, r_m, sig, as_coded, mu_s)
+    mix.setflags(write=False)
+    if path:
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            tmp = path + ".%d.tmp" % os.getpid()
+            with open(tmp, "wb") as f:
+                np.save(f, mix)
+            os.replace(tmp, path)   # atomic: concurrent ranks may build the same table
+        except OSError:
+            pass  # read-only location: the in-memory cache still works
+    return mu_s, mix
+
+
+def _lognormal_mixture(wl, n_re, n_im, r_m, sig, as_coded, mu_s):
     m = complex(n_re, abs(n_im))
     radii = np.linspace(*RADII)
     n_r = (1.0 / radii) * np.exp(-((np.log(radii) - np.log(r_m)) ** 2) / (2.0 * np.log(sig) ** 2))
     x_list = 2.0 * np.pi * radii / wl
-    mu_s = np.linspace(-1.0, 1.0, N_ANGLES_TABLE)
     table = np.zeros((len(radii), N_ANGLES_TABLE))
     weight = np.empty(len(radii))
     for i, x in enumerate(x_list):
@@ -115,10 +159,7 @@ def lognormal_table(wl: float, n_re: float, n_im: float, r_m: float, sig: float,
         else:
             weight[i] = n_r[i] * radii[i] ** 2 * efficiencies(m, x)[1]
         table[i] = i_unpolarized(m, x, mu_s)
-    mix = _trapz_rows(weight[:, None] * table, radii)
-    mix.setflags(write=False)
-    mu_s.setflags(write=False)
-    return mu_s, mix
+    return _trapz_rows(weight[:, None] * table, radii)
 
 
 def _trapz_rows(y, x):
