@@ -45,7 +45,11 @@ typedef enum {
 typedef enum {
   SOS_SURFACE_NONE = 0,      /* single homogeneous layer: In_NumInt (SOS_Aer_I1_In.py:77-130) */
   SOS_SURFACE_SPECULAR = 1,  /* SOS_Aer_main_specular.py:397,399 */
-  SOS_SURFACE_LAMBERT = 2    /* Lambert-as-coded: SOS_Aer_main_lambertian.py:399,401 */
+  SOS_SURFACE_LAMBERT = 2,   /* Lambert-as-coded: SOS_Aer_main_lambertian.py:399,401 */
+  SOS_SURFACE_LAMBERT_README = 3  /* the n >= 2 Lambert coupling as the README states it (README.md:215): isotropic upward
+                                     radiance -2 rho int_{-1}^{0} I_n(tau*, mu') mu' dmu' > 0 over the WHOLE downward half
+                                     (the shipped code has the opposite sign and drops [-h, 0]: Q5).  A separate, named
+                                     physics mode: validated by invariants, not by parity with the reference. */
 } sos_surface;
 
 /* device-side status bits (OR-ed per scenario) */
@@ -241,8 +245,9 @@ int sos_quadratures(sos_plan* plan, const double* I_d, double direct_scale, cons
 long long sos_launch_count(const sos_plan* plan);
 
 /* Which code path will sos_solve take on this plan?  Returns 0 / 1 (or the device ordinal), negative on error. */
-#define SOS_QUERY_FUSED_ORDER 0       /* the single-pass order kernel (batches; csrc/strip.cuh) instead of the chunked scan */
-#define SOS_QUERY_GENERATED_SOURCE 1  /* ... with J rebuilt from two projections per row on the molecular rows */
+#define SOS_QUERY_FUSED_ORDER 0       /* sos_solve may rebuild sources inside the sweeps (buffers exist, nothing disabled it) */
+#define SOS_QUERY_GENERATED_SOURCE 1  /* ... and does: J is rebuilt from two projections per row on the molecular rows
+                                         (csrc/sweep.cuh: SrcGen) instead of being written by a contraction and read back */
 #define SOS_QUERY_FOLDED 2            /* folded contraction registered */
 #define SOS_QUERY_DEVICE 3            /* CUDA device ordinal the plan lives on */
 int sos_plan_query(const sos_plan* plan, int what);

@@ -300,6 +300,9 @@ def order_sweeps(lay: Layout, J: np.ndarray, method="slices", blend_index_out=No
     elif lay.surface == "lambert":
         cols = np.arange(M - 2, -1, -1)
         seed = np.full(M - 1, -2 * lay.grd_alb * trapz(out[last, cols] * mu[cols], mu[cols]))
+    elif lay.surface == "lambert_readme":
+        # README.md:215 (not the shipped code): -2 rho int_{-1}^{0} I mu dmu, ascending abscissa, whole downward half
+        seed = np.full(M - 1, -2 * lay.grd_alb * trapz(out[last, :M] * mu[:M], mu[:M]))
     else:
         seed = np.zeros(M - 1)
 

@@ -11,8 +11,9 @@
 #define SOS_BLEND_THRESHOLD 0.0001
 #define SOS_MU0_TOLERANCE 0.0001
 
-// internal status bit: the fused order kernel (strip.cuh) met a mu -> 0+ blend that leaves its 128-column zone; the
-// solve is repeated with the chunked kernels (sos_solve returns SOS_ERR_RETRY after switching the plan over)
+// internal status bit: with a generated source (sweep.cuh: SrcGen) only the first 128 upward columns keep their raw I_n;
+// a mu -> 0+ blend that reaches further cannot be finished, and the solve is repeated with every row stored (sos_solve
+// returns SOS_ERR_RETRY after switching the plan over)
 #define SOS_STATUS_STRIP_FALLBACK 0x100u
 
 #define SOS_MAX_PHASE 16

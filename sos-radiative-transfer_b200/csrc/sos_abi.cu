@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a tool is attached
+
 #include "common.cuh"
 #include "first_order.cuh"
 #include "gemm_f64.cuh"
@@ -152,12 +154,11 @@ struct sos_plan {
   int n_lowrank_groups = 0;
   int lowrank_rp = 4;
   // generated source inside sos_solve (sweep.cuh: SrcGen): the molecular rows never materialise J or I_n
-  bool strip_ok = false;        // buffers exist (SOS_B200_STRIP=0 disables)
-  bool strip_disabled = false;  // a blend left the zone columns at run time: every row is read / stored from now on
+  bool gen_ok = false;        // buffers exist (SOS_B200_GENSRC=0 disables)
+  bool gen_disabled = false;  // a blend left the zone columns at run time: every row is read / stored from now on
   int gen_nslots = 0, gen_zlo = 0, gen_zu_end = 0;
   double* d_proj = nullptr;     // [S][L][nslots][2]
   double* d_cj[2] = {nullptr, nullptr};  // [S][L][2] source coefficients, ping-pong over the orders
-  int* d_strip_ticket = nullptr;
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -247,6 +248,12 @@ cudaEvent_t prof_event(sos_plan* p) {
   return p->ev_pool[p->ev_used++];
 }
 
+// NVTX range around a kernel class / a phase of the solve (visible in Nsight Systems / ncu --nvtx)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct ProfSpan {
   sos_plan* p;
   int cls;
@@ -290,7 +297,7 @@ int plan_tiles(sos_plan* p, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // generated source (sweep.cuh: SrcGen): plan-side buffers
 // ---------------------------------------------------------------------------------------------
-int strip_env_int(const char* name, int dflt) {
+int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   return (e && *e) ? std::atoi(e) : dflt;
 }
@@ -308,11 +315,11 @@ int gen_zone_lo(const GridDev& g, const sos_scenario* scen_h) {
 
 constexpr int kGenUpZone = 128;  // upward columns next to mu = 0+ whose raw I_n is kept for the find-first blend
 
-int strip_setup(sos_plan* p, const sos_scenario* scen_h) {
+int gen_setup(sos_plan* p, const sos_scenario* scen_h) {
   const GridDev& g = p->dev;
   const int L = g.L, M = g.M, N = g.N, S = g.S;
-  p->strip_ok = false;
-  if (strip_env_int("SOS_B200_STRIP", 1) == 0) return SOS_OK;
+  p->gen_ok = false;
+  if (env_int("SOS_B200_GENSRC", 1) == 0) return SOS_OK;
   // one projection slot per warp of the apply pass: two columns per thread on grids with odd M (sweep_apply2_kernel)
   const int T = (M & 1) ? 2 * sossweep::APPLY2_THREADS : sossweep::LOCAL_THREADS;
   const int nslots = ((M - 1 + T - 1) / T + (N - M - 1 + T - 1) / T) * 4;
@@ -325,7 +332,7 @@ int strip_setup(sos_plan* p, const sos_scenario* scen_h) {
   p->gen_nslots = nslots;
   p->gen_zu_end = std::min(M + 1 + kGenUpZone, N);
   p->gen_zlo = gen_zone_lo(g, scen_h);
-  p->strip_ok = true;
+  p->gen_ok = true;
   return SOS_OK;
 }
 
@@ -397,8 +404,8 @@ int validate_scenarios(const sos_grid& grid, const sos_scenario* scen_h) {
 
 extern "C" {
 
-static bool strip_generates(const sos_plan* p);
-static bool strip_usable(const sos_plan* p);
+static bool gen_applies(const sos_plan* p);
+static bool gen_usable(const sos_plan* p);
 
 int sos_abi_version(void) { return SOS_ABI_VERSION; }
 
@@ -442,7 +449,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     if (grid->region_start[k + 1] <= grid->region_start[k]) return SOS_ERR_INVALID;
   if (grid->n_regions == 3 && (grid->region_start[1] < 2 || grid->region_start[2] < grid->region_start[1] + 1))
     return SOS_ERR_INVALID;
-  if (grid->surface < 0 || grid->surface > 2) return SOS_ERR_INVALID;
+  if (grid->surface < 0 || grid->surface > 3) return SOS_ERR_INVALID;
 
   int dev = 0;
   SOS_CUDA(cudaGetDevice(&dev));
@@ -670,7 +677,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
   }
   {
-    int r3 = strip_setup(p, p->scen_h.data());
+    int r3 = gen_setup(p, p->scen_h.data());
     if (r3) { sos_plan_destroy(p); return r3; }
   }
   *out = p;
@@ -706,12 +713,12 @@ int sos_plan_update(sos_plan* p, const double* tau_h, const sos_scenario* scen_h
   std::vector<ScenState> state(S);
   for (int s = 0; s < S; ++s) { state[s].ratio_toa = 1; state[s].ratio_surf = 1; state[s].n_orders = 1; state[s].active = 1; state[s].status = 0; state[s].pad = 0; }
   SOS_CUDA(cudaMemcpyAsync(g.state, state.data(), sizeof(ScenState) * S, cudaMemcpyHostToDevice, st));
-  if (p->strip_ok) {
+  if (p->gen_ok) {
     p->gen_zlo = gen_zone_lo(g, patched.data());
-    p->strip_disabled = false;  // a new batch gets the generated source again
+    p->gen_disabled = false;  // a new batch gets the generated source again
   }
   SOS_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
-  sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev, p->d_strip_ticket);
+  sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev);
   if ((r = launch_check(p, "count_active_kernel"))) return r;
   if (p->fold) {
     if (p->premix && (r = premix_folded(p))) return r;
@@ -739,8 +746,8 @@ long long sos_launch_count(const sos_plan* p) { return p ? p->launches : 0; }
 int sos_plan_query(const sos_plan* p, int what) {
   if (!p) return SOS_ERR_INVALID;
   switch (what) {
-    case SOS_QUERY_FUSED_ORDER: return strip_usable(p) ? 1 : 0;
-    case SOS_QUERY_GENERATED_SOURCE: return (strip_usable(p) && strip_generates(p)) ? 1 : 0;
+    case SOS_QUERY_FUSED_ORDER: return gen_usable(p) ? 1 : 0;
+    case SOS_QUERY_GENERATED_SOURCE: return (gen_usable(p) && gen_applies(p)) ? 1 : 0;
     case SOS_QUERY_FOLDED: return p->fold ? 1 : 0;
     case SOS_QUERY_DEVICE: return p->device;
     default: return SOS_ERR_INVALID;
@@ -1103,6 +1110,7 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
 int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) {
   if (!p || !C_h || !I1_d) return SOS_ERR_INVALID;
   SOS_GUARD(p);
+  NvtxRange nvtx("sos:first_order");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GridDev& g = p->dev;
   SOS_CUDA(cudaMemcpyAsync(p->d_C, C_h, sizeof(double) * g.S * 2 * g.N, cudaMemcpyHostToDevice, st));
@@ -1180,6 +1188,7 @@ int sos_copy_d2d(void* dst_d, const void* src_d, size_t bytes, void* stream) {
 
 static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_begin, int seg_end, void* stream,
                        const double* const* peers, int n_peers, const int* peer_col, bool skip_lowrank) {
+  NvtxRange nvtx("sos:source_contraction");
   if (!p || !In1_d || !J_d) return SOS_ERR_INVALID;
   SOS_GUARD(p);
   if (!p->maps_A_ready) return SOS_ERR_STATE;
@@ -1298,7 +1307,7 @@ static sossweep::SrcGen source_gen(const sos_plan* p, int n) {
   sg.nslots = p->gen_nslots;
   sg.zlo = p->gen_zlo;
   sg.zu_end = p->gen_zu_end;
-  sg.store_all = strip_env_int("SOS_B200_STRIP_STORE_ALL", 0);
+  sg.store_all = env_int("SOS_B200_GENSRC_STORE_ALL", 0);
   sg.ldr = p->lowrank_ldr;
   for (int i = 0; i < SOS_MAX_PHASE; ++i) {
     sg.rank[i] = p->lowrank_rank[i];
@@ -1310,6 +1319,7 @@ static sossweep::SrcGen source_gen(const sos_plan* p, int n) {
 static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st, int gen_order = -1) {
   const GridDev& g = p->dev;
   const sossweep::SrcGen sg = source_gen(p, gen_order);
+  NvtxRange nvtx("sos:layer_sweeps");
   ProfSpan span(p, 1, st);
   const int T = sossweep::LOCAL_THREADS;
   dim3 cgrid((g.M - 1 + T - 1) / T + (g.N - g.M - 1 + T - 1) / T, g.nchunks, g.S);
@@ -1343,7 +1353,7 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     const int down = std::max(g.M - g.first_small, g.widx[3] + 6) + 1;
     int zone_buf = std::min(g.M, down);
     if (gen_order >= 0) zone_buf = std::max(zone_buf, g.M - p->gen_zlo);
-    const size_t smem = static_cast<size_t>(zone_buf) * sossweep::ZONE_ROWS * sizeof(double);
+    const size_t smem = static_cast<size_t>(zone_buf + sossweep::ZONE_UP + 4) * sossweep::ZONE_ROWS * sizeof(double);
     if (smem > 48 * 1024) {
       if (smem > 200 * 1024) return SOS_ERR_UNSUPPORTED;
       cudaFuncSetAttribute(sossweep::sweep_zone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1365,7 +1375,7 @@ int sos_sweeps(sos_plan* p, const double* J_d, double* In_d, double* I_d, void* 
 int sos_converge(sos_plan* p, int order, void* stream) {
   if (!p) return SOS_ERR_INVALID;
   SOS_GUARD(p);
-  sossweep::converge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, order, p->d_order, nullptr, 0, p->d_strip_ticket);
+  sossweep::converge_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, order, p->d_order);
   int r = launch_check(p);
   if (r) return r;
   return plan_tiles(p, static_cast<cudaStream_t>(stream));
@@ -1378,7 +1388,7 @@ int sos_reset(sos_plan* p, const double* I1_d, void* stream) {
   sossweep::reset_kernel<<<p->dev.S, 256, 0, st>>>(p->dev, I1_d, p->d_order);
   int r = launch_check(p);
   if (r) return r;
-  sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev, p->d_strip_ticket);
+  sossweep::count_active_kernel<<<1, 256, 0, st>>>(p->dev);
   r = launch_check(p);
   if (r) return r;
   return plan_tiles(p, st);
@@ -1403,11 +1413,11 @@ int sos_get_results(sos_plan* p, sos_result* results_h, void* stream) {
 }
 
 // can this solve run on the fused strip kernel, and with generated J?
-static bool strip_usable(const sos_plan* p) {
+static bool gen_usable(const sos_plan* p) {
   const GridDev& g = p->dev;
-  return p->strip_ok && !p->strip_disabled && g.col0 == 0 && g.col1 == g.N;
+  return p->gen_ok && !p->gen_disabled && g.col0 == 0 && g.col1 == g.N;
 }
-static bool strip_generates(const sos_plan* p) {
+static bool gen_applies(const sos_plan* p) {
   // the molecular rows leave the contraction only in fold mode (class-3 groups of the tile plan) and only with the
   // closed-form rank <= 2 factors; otherwise every J row is read from memory
   if (!p->fold || p->n_lowrank_groups == 0) return false;
@@ -1420,6 +1430,7 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
               int poll_every, sos_result* results_h, void* stream) {
   if (!p || !I_d || !In_d || !J_d) return SOS_ERR_INVALID;
   SOS_GUARD(p);
+  NvtxRange nvtx("sos:solve");
   if (!p->maps_A_ready) return SOS_ERR_STATE;
   if (poll_every < 1) poll_every = 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1427,7 +1438,7 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
   int r = sos_reset(p, I_d, stream);
   if (r) return r;
   const size_t field = static_cast<size_t>(g.S) * g.L * g.ld;
-  const bool gen = strip_usable(p) && strip_generates(p);
+  const bool gen = gen_usable(p) && gen_applies(p);
   if (gen) {
     // projections of the first order onto the molecular factors: what order 2 rebuilds its J from
     dim3 pg((g.L + 7) / 8, g.S);
@@ -1479,7 +1490,7 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
     rc = sos_get_results(p, tmp.data(), stream);
     if (rc) return rc;
     for (int s = 0; s < g.S; ++s)
-      if (tmp[s].status & SOS_STATUS_STRIP_FALLBACK) { p->strip_disabled = true; return SOS_ERR_RETRY; }
+      if (tmp[s].status & SOS_STATUS_STRIP_FALLBACK) { p->gen_disabled = true; return SOS_ERR_RETRY; }
   }
   if (results_h) {
     rc = sos_get_results(p, results_h, stream);
@@ -1495,6 +1506,7 @@ int sos_quadratures(sos_plan* p, const double* I_d, double direct_scale, const d
                     double* flux_down_d, double* net_flux_d, double* diffusivity_d, double* heating_d, void* stream) {
   if (!p || !I_d) return SOS_ERR_INVALID;
   SOS_GUARD(p);
+  NvtxRange nvtx("sos:quadratures");
   if (heating_d && (!z_h || p->dev.nreg != 3)) return SOS_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GridDev& g = p->dev;

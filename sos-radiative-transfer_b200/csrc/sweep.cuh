@@ -556,12 +556,20 @@ sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
       part += (g.mu[c1] - g.mu[c0]) * (row[c1] * g.mu[c1] + row[c0] * g.mu[c0]) * 0.5;
     }
     lambert = -2.0 * sc.grd_alb * block_sum(part, scratch);
+  } else if (g.surface == SOS_SURFACE_LAMBERT_README) {
+    // README.md:215: -2 rho int_{-1}^{0} I mu dmu with the abscissa ascending and the interval next to mu = 0 included
+    double part = 0.0;
+    for (int c0 = threadIdx.x; c0 < M - 1; c0 += blockDim.x) {
+      const int c1 = c0 + 1;
+      part += (g.mu[c1] - g.mu[c0]) * (row[c1] * g.mu[c1] + row[c0] * g.mu[c0]) * 0.5;
+    }
+    lambert = -2.0 * sc.grd_alb * block_sum(part, scratch);
   }
   // seeds into the upper half of the row buffer
   for (int m = M + 1 + threadIdx.x; m < N; m += blockDim.x) {
     double seed = 0.0;
     if (g.surface == SOS_SURFACE_SPECULAR) seed = sc.grd_alb * row[N - 1 - m];
-    else if (g.surface == SOS_SURFACE_LAMBERT) seed = lambert;
+    else if (g.surface == SOS_SURFACE_LAMBERT || g.surface == SOS_SURFACE_LAMBERT_README) seed = lambert;
     row[m] = seed;
   }
   __syncthreads();
@@ -1109,11 +1117,16 @@ sweep_apply2_kernel(const GridDev g, const SrcGen sg, const double* __restrict__
 // pass had already accumulated.  With a generated source it also finishes the next order's coefficients of its row:
 // projections of the zone columns (final values) + the apply pass's slots.
 constexpr int ZONE_ROWS = 8;
+constexpr int ZONE_UP = 128;  // upward columns next to mu = 0+ fetched eagerly for the blend search
 
-__global__ void __launch_bounds__(32 * ZONE_ROWS)  // (forcing 6 or 8 CTAs per SM spills and is slower: 0.755 vs 0.744 ms per order)
+// One global round trip per row: everything the row needs (raw values on both sides of mu = 0, the projection slots) is
+// fetched up front into registers / a per-warp shared-memory row, the fix-ups run on shared memory, and I is corrected
+// with fire-and-forget reductions (red.global.add: each element is touched by exactly one lane, so the result does not
+// depend on timing) instead of read-modify-write round trips.
+__global__ void __launch_bounds__(32 * ZONE_ROWS, 4)
 sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, double* __restrict__ In,
                   double* __restrict__ I, double* __restrict__ saved, int zone_buf) {
-  extern __shared__ double sm_zone[];  // ZONE_ROWS x zone_buf: downward values of columns [zl, M)
+  extern __shared__ double sm_zone[];  // per warp: zone_buf downward values of columns [zl, M), then ZONE_UP + 4 upward ones
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.y, t = blockIdx.x * ZONE_ROWS + warp;
   const int L = g.L, M = g.M, ld = g.ld;
@@ -1125,24 +1138,46 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
   double* __restrict__ Ia = I ? I + fbase : nullptr;
   double* __restrict__ Sv = saved ? saved + fbase : nullptr;
   const sos_scenario sc = g.scen[s];
-  const int region = g.chunk_region[g.row_chunk[t]];
+  int region = 0;
+  while (region + 1 < g.nreg && t >= g.rstart[region + 1]) ++region;
   const size_t roff = static_cast<size_t>(t) * ld;
   const int c_lo = g.col0, c_hi = g.col1;
   const bool own_down_zone = (c_lo < M && c_hi >= M);
   const bool own_up_zone = (c_lo <= M && c_hi > M + 1);
   const bool project = src.gen_row(t);  // this row's I_n feeds a rebuilt source: finish its coefficients
   const double* __restrict__ Ut = sg.Ut[sc.phase_atm];
-  double p0 = 0.0, p1 = 0.0;
+  double* row_dn = sm_zone + static_cast<size_t>(warp) * (zone_buf + ZONE_UP + 4);
+  double* row_up = row_dn + zone_buf;  // row_up[i] = I_n[t, M + i]
+  // with a generated source the zone is the plan-wide one (the apply pass left those columns out of its projections)
+  const int zl = src.gen ? sg.zlo : zone_lo(g, sc);
+  const int lim = src.gen ? min(c_hi, sg.zu_end) : c_hi;  // the blend search never leaves the owned / stored columns
+  const int eager = min(lim, M + 1 + ZONE_UP);            // ... and its first columns are fetched with everything else
 
+  // ---------------- one round of loads ----------------
   if (own_down_zone) {
-    // with a generated source the zone is the plan-wide one (the apply pass left those columns out of its projections)
-    const int zl = src.gen ? sg.zlo : zone_lo(g, sc);
-    double* row = sm_zone + static_cast<size_t>(warp) * zone_buf - zl;  // row[m] valid for m in [zl, M)
     for (int m = zl + lane; m < M; m += 32) {
       const bool std_col = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
-      row[m] = std_col ? Is[roff + m] : 0.0;  // raw (already stored and accumulated by the apply pass)
+      row_dn[m - zl] = std_col ? Is[roff + m] : 0.0;  // raw (already stored and accumulated by the apply pass)
     }
-    __syncwarp();
+  }
+  double v0 = 0.0;
+  if (own_up_zone) {
+    for (int m = M + 1 + lane; m < eager; m += 32) row_up[m - M] = Is[roff + m];
+    v0 = src(t, M, g.mu[M]);  // I_n[t, mu = 0+] = J[t, mu = 0+]
+  }
+  double p0 = 0.0, p1 = 0.0;  // projections: the apply pass's slots first
+  if (project) {
+    const double2* __restrict__ pr = reinterpret_cast<const double2*>(sg.proj + (fbase / ld + t) * sg.nslots * 2);
+    for (int j = lane; j < sg.nslots; j += 32) {
+      const double2 v = pr[j];
+      p0 += v.x;
+      p1 += v.y;
+    }
+  }
+  __syncwarp();
+
+  if (own_down_zone) {
+    double* row = row_dn - zl;  // row[m] valid for m in [zl, M)
     const int idxw = sc.extrap_width[region];
     const int r0 = g.rstart[region];
     // non-standard columns that survive the extrapolation: computed here, never touched by the apply pass
@@ -1153,7 +1188,7 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
         row[m] = v;
         Is[roff + m] = v;
         if (Sv) Sv[roff + m] = v;
-        if (Ia) Ia[roff + m] += v;
+        if (Ia) atomicAdd(&Ia[roff + m], v);
       }
     }
     __syncwarp();
@@ -1171,7 +1206,7 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
         row[m] = v;
         Is[roff + m] = v;
         if (Sv) Sv[roff + m] = v;
-        if (Ia) Ia[roff + m] += std_col ? (v - raw) : v;  // standard targets were accumulated raw
+        if (Ia) atomicAdd(&Ia[roff + m], std_col ? (v - raw) : v);  // standard targets were accumulated raw
       }
     } else if (lane == 0) {
       row[M - 1] = 0.0;
@@ -1188,54 +1223,65 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
   }
 
   if (own_up_zone) {
-    const double v0 = src(t, M, g.mu[M]);  // I_n[t, mu = 0+] = J[t, mu = 0+]
     if (lane == 0) {
+      row_up[0] = v0;
       Is[roff + M] = v0;
       if (Sv) Sv[roff + M] = v0;
-      if (Ia) Ia[roff + M] += v0;
+      if (Ia) atomicAdd(&Ia[roff + M], v0);
     }
-    // find-first over the raw values written by the apply pass (with a generated source they exist up to zu_end)
-    const int lim = src.gen ? min(c_hi, sg.zu_end) : c_hi;  // the search never leaves the owned columns
+    __syncwarp();
+    // find-first over the raw values written by the apply pass: the eager window in shared memory, then (rare) on
     int istar = -1;
-    for (int base = M + 1; base + 2 <= lim - 1 && istar < 0; base += 32) {
+    int base = M + 1;
+    for (; base + 2 <= eager - 1 && istar < 0; base += 32) {
       const int i = base + lane;
       bool hit = false;
-      if (i + 2 <= lim - 1) {
-        const double a = Is[roff + i], b = Is[roff + i + 1], cc = Is[roff + i + 2];
+      if (i + 2 <= eager - 1) {
+        const double a = row_up[i - M], b = row_up[i + 1 - M], cc = row_up[i + 2 - M];
         hit = !(fabs((a - b) - (b - cc)) > SOS_BLEND_THRESHOLD);
       }
       const unsigned mask = __ballot_sync(0xffffffffu, hit);
       if (mask) istar = base + __ffs(mask) - 1 + 1;
     }
+    if (istar < 0 && eager < lim) {
+      // (the triples that straddle the end of the eager window are examined again from global memory)
+      for (base = max(M + 1, eager - 2 - 31); base + 2 <= lim - 1 && istar < 0; base += 32) {
+        const int i = base + lane;
+        bool hit = false;
+        if (i + 2 <= lim - 1 && i + 2 >= eager) {
+          const double a = Is[roff + i], b = Is[roff + i + 1], cc = Is[roff + i + 2];
+          hit = !(fabs((a - b) - (b - cc)) > SOS_BLEND_THRESHOLD);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) istar = base + __ffs(mask) - 1 + 1;
+      }
+    }
     if (istar < 0) {
       if (lane == 0) atomicOr(&g.state[s].status, (lim >= g.N) ? SOS_STATUS_BLEND_OVERRUN : SOS_STATUS_STRIP_FALLBACK);
     } else {
-      const double v1 = Is[roff + istar];
+      const double v1 = (istar < eager) ? row_up[istar - M] : Is[roff + istar];
       const double mus = g.mu[istar];
       __syncwarp();  // every lane has read what it needs before anything is overwritten
       for (int m = M + 1 + lane; m < istar; m += 32) {
         const double w = g.mu[m] / mus;
         const double val = (1.0 - w) * v0 + w * v1;
-        const double old = Is[roff + m];
+        const double old = (m < eager) ? row_up[m - M] : Is[roff + m];
+        if (m < eager) row_up[m - M] = val;
         Is[roff + m] = val;
         if (Sv) Sv[roff + m] = val;
-        if (Ia) Ia[roff + m] += (val - old);
+        if (Ia) atomicAdd(&Ia[roff + m], val - old);
       }
     }
     __syncwarp();
   }
 
   if (project) {
-    // the next order's source coefficients of this row: zone columns (final values) + the apply pass's slots
-    __threadfence_block();
-    __syncwarp();
+    // the next order's source coefficients of this row: + the zone columns (final values: all inside the eager window)
     for (int m = M + lane; m < min(sg.zu_end, g.N); m += 32) {
-      const double v = Is[roff + m];
+      const double v = row_up[m - M];
       p0 = fma(v, Ut[m], p0);
       p1 = fma(v, Ut[sg.ldr + m], p1);
     }
-    const double* __restrict__ pr = sg.proj + (fbase / ld + t) * sg.nslots * 2;
-    for (int j = lane; j < sg.nslots; j += 32) { p0 += pr[2 * j]; p1 += pr[2 * j + 1]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { p0 += shfl_xor_d(p0, o); p1 += shfl_xor_d(p1, o); }
     if (lane == 0)
@@ -1245,14 +1291,14 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
   // ---- convergence ratios on the TOA / surface rows (whole half-row, read back from global) ----
   const bool toa = (t == 0), surf = (t == L - 1);
   if (Ia && (toa || surf)) {
-    __threadfence_block();
+    __threadfence();  // this warp's own reductions into I have landed before it reads the row back
     __syncwarp();
     double rmax = -INFINITY;
     bool nonfinite = false;
     const int a0 = toa ? max(M, c_lo) : c_lo;
     const int a1 = toa ? c_hi : min(M, c_hi);
     for (int m = a0 + lane; m < a1; m += 32) {
-      const double r = Is[roff + m] / Ia[roff + m];
+      const double r = Is[roff + m] / __ldcg(&Ia[roff + m]);
       if (isnan(r)) nonfinite = true; else rmax = fmax(rmax, r);
     }
 #pragma unroll
@@ -1284,31 +1330,19 @@ __device__ __forceinline__ void build_active_list(const GridDev& g) {
   if (lane == 0) *g.n_active = base;
 }
 
-// ratio_part != nullptr: the fused order kernel left one {TOA, surface} maximum per strip; reduce them first
-__global__ void converge_kernel(const GridDev g, int order_arg, int* order_counter, const double* __restrict__ ratio_part,
-                                int nstrips, int* strip_ticket) {
+__global__ void converge_kernel(const GridDev g, int order_arg, int* order_counter) {
   __shared__ int order_s;
   if (threadIdx.x == 0) {
     // order_arg < 0: take the order number from the device-side counter (CUDA-graph replays cannot
     // change kernel arguments); the counter always tracks the last order handled
     order_s = order_arg >= 0 ? order_arg : *order_counter + 1;
     *order_counter = order_s;
-    if (strip_ticket) *strip_ticket = 0;
   }
   __syncthreads();
   const int order = order_s;
   for (int s = threadIdx.x; s < g.S; s += blockDim.x) {
     ScenState& st = g.state[s];
     if (st.active) {
-      if (ratio_part) {
-        double r0 = -INFINITY, r1 = -INFINITY;
-        for (int k = 0; k < nstrips; ++k) {
-          r0 = fmax(r0, ratio_part[(static_cast<size_t>(s) * nstrips + k) * 2]);
-          r1 = fmax(r1, ratio_part[(static_cast<size_t>(s) * nstrips + k) * 2 + 1]);
-        }
-        st.ratio_toa = r0;
-        st.ratio_surf = r1;
-      }
       st.n_orders = order;
       const double r = fmax(st.ratio_toa, st.ratio_surf);
       if (!(r >= g.scen[s].threshold)) st.active = 0;
@@ -1384,9 +1418,6 @@ __global__ void __launch_bounds__(256) project_rows_kernel(const GridDev g, cons
   if (lane == 0) *reinterpret_cast<double2*>(cj + (static_cast<size_t>(s) * sg.Lp + t) * 2) = make_double2(coef * p0, coef * p1);
 }
 
-__global__ void count_active_kernel(const GridDev g, int* strip_ticket) {
-  if (threadIdx.x == 0 && strip_ticket) *strip_ticket = 0;
-  build_active_list(g);
-}
+__global__ void count_active_kernel(const GridDev g) { build_active_list(g); }
 
 }  // namespace sossweep

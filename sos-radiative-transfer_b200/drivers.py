@@ -41,7 +41,9 @@ class Scenario:
     # the shipped default is the log-normal Mie 'eva' aerosol, which needs miepython; pass explicit
     # (P0, P) arrays for Mie, or an analytic stand-in such as ("hg", 0.5)
     aer_phase: PhaseSpec = ("hg", 0.5)
-    surface: str = "specular"  # 'specular' | 'lambert' (Lambert-as-coded, SURVEY.md 8c "repair A")
+    # 'specular' | 'lambert' (Lambert-as-coded, SURVEY.md 8c "repair A") | 'lambert_readme' (the n >= 2 coupling with the
+    # README's sign and integration range, README.md:215; first order as in the other two: a named physics mode, not parity)
+    surface: str = "specular"
     threshold: float = 1e-4
     max_orders: int = 10000
 
@@ -152,7 +154,8 @@ class BatchSolver:
         self.z = G.aerosol_rows(scenarios[0].z0, scenarios[0].z_up, scenarios[0].z_down, L)[0]
         self._mat_index, self._mats, self._mat_keys = {}, [], []
         coefs = self._prepare(scenarios)
-        surface = {"specular": _lib.SURFACE_SPECULAR, "lambert": _lib.SURFACE_LAMBERT}[surf]
+        surface = {"specular": _lib.SURFACE_SPECULAR, "lambert": _lib.SURFACE_LAMBERT,
+                   "lambert_readme": _lib.SURFACE_LAMBERT_README}[surf]
         self.engine = SosEngine(self.mu, self.tau, coefs, [0, self.idx_up, self.idx_down + 1, L], surface,
                                 device=device, chunk_rows=chunk_rows, fold=fold)
         self._register_phases()
@@ -279,6 +282,33 @@ class BatchSolver:
         return out
 
 
+MAX_PHASES_PER_PLAN, MAX_GROUPS_PER_PLAN = 16, 48   # SOS_MAX_PHASE / SOS_MAX_GROUPS of the C ABI (csrc/common.cuh)
+
+
+def _phase_id(spec):
+    return spec if isinstance(spec[0], str) else ("array", id(spec[1]))
+
+
+def split_for_plan_limits(scenarios: Sequence[Scenario], idxs: Sequence[int]) -> List[List[int]]:
+    """Cut one grid group into sub-batches a plan accepts: at most 16 distinct phase matrices and 48 (atm, aer) operand
+    pairs each (a phase sweep over more than 16 HG asymmetry factors, or per-scenario Mie arrays, would otherwise be
+    refused by sos_plan_create).  Order inside the group is kept."""
+    out, cur, phases, pairs = [], [], set(), set()
+    for i in idxs:
+        sc = scenarios[i]
+        pa, pe = _phase_id(sc.atm_phase), _phase_id(sc.aer_phase)
+        new_phases = phases | {pa, pe}
+        new_pairs = pairs | {(pa, pe), (pa, None)}
+        if cur and (len(new_phases) > MAX_PHASES_PER_PLAN or len(new_pairs) > MAX_GROUPS_PER_PLAN):
+            out.append(cur)
+            cur, new_phases, new_pairs = [], {pa, pe}, {(pa, pe), (pa, None)}
+        cur.append(i)
+        phases, pairs = new_phases, new_pairs
+    if cur:
+        out.append(cur)
+    return out
+
+
 def solve_scenarios(scenarios: Sequence[Scenario], device=None, keep_orders: int = 0, quadratures: bool = True,
                     fold: Optional[bool] = None) -> List[DriverResult]:
     """Solve any mix of scenarios; those sharing a grid are batched together.  fold: see SosEngine."""
@@ -286,7 +316,8 @@ def solve_scenarios(scenarios: Sequence[Scenario], device=None, keep_orders: int
     for i, sc in enumerate(scenarios):
         groups.setdefault(_group_key(sc), []).append(i)
     out: List[Optional[DriverResult]] = [None] * len(scenarios)
-    for key, idxs in groups.items():
+    batches = [b for idxs in groups.values() for b in split_for_plan_limits(scenarios, idxs)]
+    for idxs in batches:
         bs = BatchSolver([scenarios[i] for i in idxs], device=device, fold=fold)
         res = bs.solve(keep_orders=keep_orders)
         for i, r in zip(idxs, bs.results(res, quadratures=quadratures, keep_orders=keep_orders)):

@@ -204,13 +204,15 @@ class SosEngine:
         return a[0] if self.S == 1 else a
 
     @property
-    def strip_active(self) -> bool:
-        """True when sos_solve runs this plan on the fused single-pass order kernel (csrc/strip.cuh)."""
+    def gensrc_enabled(self) -> bool:
+        """True when sos_solve may rebuild sources inside the sweeps on this plan (SOS_B200_GENSRC=0 disables it; a blend
+        wider than the columns kept raw disables it for the plan at run time)."""
         return bool(self.lib.sos_plan_query(self._plan, _lib.QUERY_FUSED_ORDER) == 1)
 
     @property
     def generated_source(self) -> bool:
-        """True when that kernel also rebuilds J on the molecular rows instead of reading it."""
+        """True when sos_solve rebuilds J on the molecular rows from two projections per row instead of writing and reading
+        it (csrc/sweep.cuh: SrcGen): needs the folded contraction and rank <= 2 molecular operands."""
         return bool(self.lib.sos_plan_query(self._plan, _lib.QUERY_GENERATED_SOURCE) == 1)
 
     @property
@@ -458,7 +460,7 @@ class SosEngine:
                                                   int(max_orders), int(poll_every), res, self._stream), "sos_solve")
                 break
             except _lib.SosRetry:
-                # the fused order kernel met a blend wider than its zone; the plan now uses the chunked kernels.  With
+                # a blend reached past the columns whose raw I_n is kept; the plan now stores every row.  With
                 # consume_I1 the first order is gone: the owner of I1 (BatchSolver.solve) recomputes it and calls again.
                 if attempt or (consume_I1 and In_arg is None):
                     raise

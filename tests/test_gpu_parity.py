@@ -6,6 +6,7 @@ and heating rates, same scattering order at convergence.  Metric (h
 max|delta| / max|ref| per field, plus elementwise relative error where |ref| > 1e-6 max|ref|.
 """
 import ast
+import dataclasses
 
 import numpy as np
 import pytest
@@ -136,6 +137,76 @@ def test_small_drivers_vs_golden(sos, golden, kind, tag):
     # heating rate = difference of nearly equal fluxes / dz: compare against the flux scale
     scale = np.max(np.abs(d[key + "_flux_down"])) / abs(r.z_profile[1] - r.z_profile[0]) / (1.225 * 1004)
     assert np.max(np.abs(r.heating_rate - d[key + "_heating_rate"])) < TOL * scale
+
+
+def test_more_than_sixteen_phase_functions_in_one_call(sos):
+    """A phase sweep over 20 HG asymmetry factors on one grid (a plan holds 16 operands): solved in sub-batches, every
+    member equal to its stand-alone solve."""
+    scs = [sos.Scenario(nb_layers=96, nb_angles=101, tauStar_atm=0.124, tauStar_aer=0.12, grd_alb=0.15, alb_aer=0.97,
+                        aer_phase=("hg", 0.2 + 0.03 * i)) for i in range(20)]
+    out = sos.solve_scenarios(scs)
+    for i in (0, 7, 16, 19):
+        one = sos.solve_scenarios([scs[i]])[0]
+        assert out[i].n == one.n and relmax(out[i].I, one.I) < 1e-12, i
+
+
+def test_lambert_readme_mode_invariants_and_oracle(sos, so):
+    """surface="lambert_readme": the n >= 2 Lambert coupling as README.md:215 states it (a named physics mode, SURVEY 8c;
+    the shipped code has the opposite sign and drops [-h, 0], Q5).  Validated by invariants -- the surface returns the
+    fraction rho of every order's downward irradiance, isotropically and with a positive radiance -- and against the
+    oracle's restatement of the same formula."""
+    kw = dict(nb_layers=120, nb_angles=101, mu0=0.6, tauStar_atm=0.3, tauStar_aer=0.4, alb_aer=0.95, grd_alb=0.4)
+    sc = sos.Scenario(atm_phase=("rayleigh", 0.0), aer_phase=("hg", 0.6), surface="lambert_readme", **kw)
+    r = sos.solve_scenarios([sc], keep_orders=6)[0]
+    M, mu, L = sc.nb_angles, r.mu, sc.nb_layers
+    for n in range(1, min(6, r.n)):                      # orders 2 ..
+        In = r.I_saved[n]
+        down = -so.trapz(In[L - 1, :M] * mu[:M], mu[:M])              # downward irradiance of this order at the surface (> 0)
+        seed = In[L - 1, M + 40:]                                      # away from the mu -> 0+ blend: the raw surface radiance
+        assert down > 0 and np.all(seed > 0)
+        assert np.max(np.abs(seed - seed[0])) < 1e-13 * abs(seed[0])   # isotropic
+        assert abs(seed[0] - 2 * sc.grd_alb * down) < 1e-12 * abs(seed[0])   # R = 2 rho F_down  <=>  F_up = rho F_down
+        up = so.trapz(In[L - 1, M:] * mu[M:], mu[M:])
+        assert abs(up - sc.grd_alb * down) < 2e-2 * up                 # (the blend next to mu = 0+ reshapes a few columns)
+    # as coded, the same scenario has the opposite sign (Q5)
+    rc = sos.solve_scenarios([dataclasses.replace(sc, surface="lambert")], keep_orders=2)[0]
+    assert np.all(rc.I_saved[1][L - 1, M + 40:] < 0)
+    # the oracle's restatement of the README formula
+    P0a, Pa = sos.phase_matrices("rayleigh", M, mu, sc.mu0, 0.0)
+    P0e, Pe = sos.phase_matrices("hg", M, mu, sc.mu0, 0.6)
+    ref = so.solve(so.Scenario(surface="lambert_readme", **kw), P0a, Pa, P0e, Pe, method="recurrence", use_gemm=True)
+    assert r.n == ref["n"] and relmax(r.I, ref["I"]) < TOL
+
+
+def test_graphe_shim_reproduces_the_reference_curves(sos, so, golden):
+    """The reference's output layer with its own signatures (sos.graphe_*, SOS_Aer_graphe.py:6,37,68,118,152): the curves
+    the unmodified reference computed inside its graphe_* functions (captured by make_golden.py), reproduced from the
+    golden radiance field through the device quadratures; per-order diffusivity against the NumPy formula."""
+    d = golden("drivers_small.npz")
+    key = "specular_thick"
+    kw = ast.literal_eval(str(d[key + "_kw"]))
+    r = _run_driver(sos, "specular", kw, keep=3)
+    I, mu, z, tau = d[key + "_I"], r.mu, r.z_profile, d[key + "_tau"]
+    L, M = I.shape[0], I.shape[1] // 2
+    mu0, alb = kw.get("mu0", 0.5), kw.get("grd_alb", 0.0)
+    F0 = np.pi / mu0
+    assert relmax(sos.graphe_diffusivity(I, mu, z, L, "hg"), d[key + "_diffusivity"]) < TOL
+    assert relmax(sos.graphe_flux(I, mu, z, L, M, tau, mu0, F0, alb, "hg"), d[key + "_net_flux"]) < TOL
+    up, down = sos.graphe_flux_up_down(I, mu, z, L, M, tau, mu0, F0, alb, "hg")
+    assert relmax(up, d[key + "_flux_up"]) < TOL and relmax(down, d[key + "_flux_down"]) < TOL
+    hr = sos.graphe_heating_rate(I, mu, z, L, M, r.idx_up, r.idx_down, F0, mu0, tau, alb, "hg")
+    scale = np.max(np.abs(d[key + "_flux_down"])) / abs(z[1] - z[0]) / (1.225 * 1004)
+    assert np.max(np.abs(hr - d[key + "_heating_rate"])) < TOL * scale
+    # another F0 only rescales the direct terms (the reference passes F0 explicitly)
+    up2, down2 = sos.graphe_flux_up_down(I, mu, z, L, M, tau, mu0, 2.0 * F0, alb, "hg")
+    assert relmax(down2 - down, -F0 * np.exp(-tau / mu0)) < 1e-9
+    # per-order diffusivity, all saved orders in one launch
+    dif = sos.graphe_successive_dif(r.I_saved, mu, z, L, M, "hg")
+    assert dif.shape == (len(r.I_saved), L)
+    for j, In in enumerate(r.I_saved):
+        assert relmax(dif[j], so.diffusivity(In, mu)) < TOL, j
+    with pytest.raises(ValueError):
+        sos.graphe_successive_dif([I[:-1]], mu, z, L, M, "hg")
 
 
 @pytest.mark.parametrize("tag", ["eva_spec", "eva_lamb", "thin_spec", "mixed_spec", "tau2_lamb"])

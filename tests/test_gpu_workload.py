@@ -1,10 +1,12 @@
-"""GPU parity of what bench.py actually times, and of the two sweep implementations against each other.
+"""GPU parity of what bench.py actually times, and of the order loop with and without the generated source.
 
 * the benchmarked workload itself (bench.make_scenarios: Rayleigh atmosphere + HG / log-normal-Mie / FWC aerosols in
   the three-region specular driver at 800 x 1002, mu0 in [0.1, 1], omega_aer in [0.7, 1]) against the oracle;
 * the FWC cloud as the aerosol of the three-region driver against a fixture produced by the unmodified reference;
-* the fused single-pass order kernel (csrc/strip.cuh: one pass, generated J on the molecular rows) against the chunked
-  four-kernel scan (csrc/sweep.cuh) on the same batches, all surfaces, ragged sizes, Taylor / windowed columns.
+* sos_solve with the generated source (csrc/sweep.cuh SrcGen: J rebuilt from two projections per row on the molecular rows,
+  I_n kept only where something reads it, two-column apply pass on odd grids) against the same solve with every J row
+  written by the contraction kernels and read back (SOS_B200_GENSRC=0), on the same batches: all surfaces, ragged sizes,
+  even and odd M, Taylor / windowed columns, single solves.
 
 Tolerance 1e-10 relative (BASELINE.json north_star), same order counts.
 """
@@ -61,13 +63,13 @@ def stratified_subset(scen):
 
 
 def test_benchmarked_workload_vs_oracle(sos, so, monkeypatch):
-    """bench.py's 96-scenario batch, solved exactly as bench.py solves it (one BatchSolver, fused order kernel), against
+    """bench.py's 96-scenario batch, solved exactly as bench.py solves it (one BatchSolver, generated source), against
     the oracle on a stratified dozen of its members: radiances, order counts, fluxes, diffusivity, heating rate, TOA
-    net flux.  Then the whole batch again through the chunked kernels: same orders, same fields."""
+    net flux.  Then the whole batch again with every source row stored: same orders, same fields."""
     import bench
     scen = bench.make_scenarios(sos, 96)
     bs = sos.BatchSolver(scen)
-    assert bs.engine.strip_active, "the benchmarked batch must run on the fused order kernel"
+    assert bs.engine.gensrc_enabled, "the benchmarked batch must run with the generated source"
     res = bs.solve(poll_every=2)
     assert not np.any(res.status), res.status
     out = bs.results(res, quadratures=True, fields=True)
@@ -91,10 +93,10 @@ def test_benchmarked_workload_vs_oracle(sos, so, monkeypatch):
         assert np.max(np.abs(got.heating_rate - hr)) < TOL * scale, i
         toa = so.toa_net_flux(ref["I"], mu, M, ref["tau"], sc.mu0, F0, sc.grd_alb)
         assert abs(got.toa_net_flux - toa) < TOL * abs(toa), i
-    # the chunked scan (what small batches and single solves use) must tell the same story for all 96
-    monkeypatch.setenv("SOS_B200_STRIP", "0")
+    # the same batch with every source row written and read back must tell the same story for all 96
+    monkeypatch.setenv("SOS_B200_GENSRC", "0")
     bs2 = sos.BatchSolver(scen)
-    assert not bs2.engine.strip_active
+    assert not bs2.engine.gensrc_enabled
     res2 = bs2.solve(poll_every=2)
     out2 = bs2.results(res2, quadratures=False, fields=True)
     bs2.engine.close()
@@ -122,10 +124,9 @@ def test_fwc_aerosol_three_region_vs_golden(sos, golden, tag):
 def _solve_both(sos, scs, monkeypatch, keep=0, **kw):
     outs = {}
     for flag in ("1", "0"):
-        monkeypatch.setenv("SOS_B200_STRIP", flag)
-        monkeypatch.setenv("SOS_B200_STRIP_MIN", "1")
+        monkeypatch.setenv("SOS_B200_GENSRC", flag)
         bs = sos.BatchSolver(scs, **kw)
-        assert bs.engine.strip_active == (flag == "1"), flag
+        assert bs.engine.gensrc_enabled == (flag == "1"), flag
         res = bs.solve(keep_orders=keep)
         outs[flag] = bs.results(res, quadratures=True, keep_orders=keep)
         bs.engine.close()
@@ -134,9 +135,9 @@ def _solve_both(sos, scs, monkeypatch, keep=0, **kw):
 
 @pytest.mark.parametrize("surface", ["specular", "lambert"])
 @pytest.mark.parametrize("L,M", [(96, 251), (130, 501), (77, 100), (60, 128), (64, 1201), (203, 300)])
-def test_fused_order_kernel_equals_chunked_scan(sos, so, monkeypatch, surface, L, M):
-    """Same batches through csrc/strip.cuh and csrc/sweep.cuh: ragged L (partial last stage) and M (partial strips,
-    one strip only, even and odd M, ten strips), Taylor + windowed columns (M = 1201), all extrapolation widths, dense and generated
+def test_generated_source_equals_stored_source(sos, so, monkeypatch, surface, L, M):
+    """Same batches with and without the generated source: ragged L and M (odd M: two-column apply pass, even M: the
+    scalar one; partial column blocks), Taylor + windowed columns (M = 1201), all extrapolation widths, dense and rebuilt
     source rows, every order compared; one member also against the oracle."""
     aer = (("hg", 0.5), ("fwc", 0.0), ("hg", 0.8))
     scs = [sos.Scenario(nb_layers=L, nb_angles=M, mu0=(0.5, 0.23, 0.9, 1.0)[i % 4], tauStar_atm=(0.124, 0.05, 0.6, 0.3)[i % 4],
@@ -155,7 +156,18 @@ def test_fused_order_kernel_equals_chunked_scan(sos, so, monkeypatch, surface, L
     assert a[2].n == ref["n"] and relmax(a[2].I, ref["I"]) < TOL
 
 
-def test_fused_order_kernel_dense_atmosphere_and_single_layer(sos, so, monkeypatch):
+def test_generated_source_single_solve_default_grid(sos, so, monkeypatch):
+    """One scenario alone (the reference's own use: configs 1-3) runs with the generated source too: EVA specular on the
+    default 800 x 1002 grid against the stored-source solve and the oracle."""
+    sc = sos.Scenario(nb_layers=800, nb_angles=501, mu0=0.5, tauStar_atm=0.124, tauStar_aer=0.12, alb_aer=0.97, grd_alb=0.15,
+                      atm_phase=("rayleigh", 0.0), aer_phase=("hg", 0.5), surface="specular")
+    a, b = _solve_both(sos, [sc], monkeypatch)
+    assert a[0].n == b[0].n and relmax(a[0].I, b[0].I) < 1e-12
+    ref, _ = _oracle(so, sos, sc)
+    assert a[0].n == ref["n"] and relmax(a[0].I, ref["I"]) < TOL
+
+
+def test_generated_source_dense_atmosphere_and_single_layer(sos, so, monkeypatch):
     """No low-rank operand at all (HG atmosphere: every J row is read, 32 B per element), and the single-layer grid
     (one region, no surface) with a Rayleigh operand (every row generated, no dense tile at all)."""
     scs = [sos.Scenario(nb_layers=120, nb_angles=251, mu0=0.4 + 0.1 * i, tauStar_atm=0.2, tauStar_aer=0.1 * i, alb_aer=0.9, grd_alb=0.2,
@@ -173,14 +185,13 @@ def test_fused_order_kernel_dense_atmosphere_and_single_layer(sos, so, monkeypat
     tau = np.stack([np.linspace(0, t, L) for t in ts])
     out = {}
     for flag in ("1", "0"):
-        monkeypatch.setenv("SOS_B200_STRIP", flag)
-        monkeypatch.setenv("SOS_B200_STRIP_MIN", "1")
+        monkeypatch.setenv("SOS_B200_GENSRC", flag)
         P0, P = sos.phase_matrices("rayleigh", M, mu, 0.6, 0.0)
         coefs = [sos.ScenarioCoefficients(mu0=0.6, grd_alb=0.0, tauStar_tot=float(t), coef_atm=0.95,
                                           extrap_width=(sos.extrapolation_width(float(t), M),) * 3) for t in ts]
         eng = sos.SosEngine(mu, tau, coefs, [0, L], sos._lib.SURFACE_NONE)
         eng.set_phase([P])
-        assert eng.strip_active == (flag == "1")
+        assert eng.gensrc_enabled == (flag == "1")
         Cc = np.zeros((S, 2, N))
         Cc[:, 0] = 0.95 * P0
         I1 = eng.first_order(Cc)
@@ -206,10 +217,10 @@ def test_fused_order_kernel_dense_atmosphere_and_single_layer(sos, so, monkeypat
     assert relmax(out["1"][0][k], I) < TOL
 
 
-def test_wide_blend_falls_back_to_the_chunked_scan(sos, monkeypatch):
-    """A source large enough to push the find-first blend past the 128 columns the fused kernel keeps next to mu = 0+
-    (the threshold of SOS_Aer_I1_In.py:103 is absolute): the plan must notice, switch to the chunked kernels and return
-    their result."""
+def test_wide_blend_falls_back_to_stored_sources(sos, monkeypatch):
+    """A source large enough to push the find-first blend past the 128 upward columns whose raw I_n is kept next to
+    mu = 0+ (the threshold of SOS_Aer_I1_In.py:103 is absolute): the plan must notice, switch to stored sources and
+    return their result."""
     import torch
     L, M, S = 48, 801, 8
     N = 2 * M
@@ -219,8 +230,7 @@ def test_wide_blend_falls_back_to_the_chunked_scan(sos, monkeypatch):
     w = sos.extrapolation_width(0.3, M)
     out = {}
     for flag in ("1", "0"):
-        monkeypatch.setenv("SOS_B200_STRIP", flag)
-        monkeypatch.setenv("SOS_B200_STRIP_MIN", "1")
+        monkeypatch.setenv("SOS_B200_GENSRC", flag)
         coefs = [sos.ScenarioCoefficients(mu0=0.5, grd_alb=0.0, tauStar_tot=0.3, coef_atm=1.0, extrap_width=(w, w, w)) for _ in range(S)]
         eng = sos.SosEngine(mu, tau, coefs, [0, L], sos._lib.SURFACE_NONE)
         eng.set_phase([P])
@@ -229,9 +239,9 @@ def test_wide_blend_falls_back_to_the_chunked_scan(sos, monkeypatch):
         I1 = eng.first_order(Cc)
         res = eng.solve(I1, max_orders=4)
         torch.cuda.synchronize()
-        out[flag] = (eng.to_host(res.I), res.n_orders.copy(), eng.strip_active)
+        out[flag] = (eng.to_host(res.I), res.n_orders.copy(), eng.gensrc_enabled)
         eng.close()
-    assert out["1"][2] is False, "the wide blend should have switched the plan to the chunked kernels"
+    assert out["1"][2] is False, "the wide blend should have switched the plan to stored sources"
     assert np.array_equal(out["1"][1], out["0"][1])
     assert relmax(out["1"][0], out["0"][0]) < 1e-13
 

@@ -251,3 +251,61 @@ def test_reference_aerosol_names_resolve_to_the_mie_mixture():
     P0x, Px = sos.phase_matrices("mie_lognormal", M, mu, 0.5, sos.WILDFIRE_AEROSOL)
     assert np.array_equal(P0w, P0x) and np.array_equal(Pw, Px)
     assert cache.get(("hg", 0.5), M, mu, 0.5)[2] == ("hg", 0.5, M)
+
+
+def test_mie_table_disk_cache_is_keyed_on_every_parameter(tmp_path, monkeypatch):
+    """The log-normal Mie table cache (the reference keys its .npy cache on nb_angles and a few scenario
+    numbers only, SOS_Aer_global_va.py:17-83): one file per parameter set, identical values on reload, a changed
+    refractive index never picks up a stale file, SOS_B200_CACHE=off writes nothing."""
+    import sos_b200 as sos
+    monkeypatch.setenv("SOS_B200_CACHE", str(tmp_path))
+    sos.mie.lognormal_table.cache_clear()
+    p = (0.55, 1.44, 0.0, 0.2, 1.3)
+    mu_a, a = sos.mie.lognormal_table(*p)
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 1 and files[0].startswith("mie_lognormal_") and files[0].endswith(".npy")
+    sos.mie.lognormal_table.cache_clear()
+    _, b = sos.mie.lognormal_table(*p)            # from disk
+    assert np.array_equal(a, b) and len(os.listdir(tmp_path)) == 1
+    sos.mie.lognormal_table.cache_clear()
+    _, c = sos.mie.lognormal_table(0.55, 1.50, 0.0, 0.2, 1.3)
+    assert len(os.listdir(tmp_path)) == 2 and not np.array_equal(a, c)
+    # a corrupt file is rebuilt, not trusted
+    path = os.path.join(tmp_path, files[0])
+    with open(path, "wb") as f:
+        f.write(b"not a npy file")
+    sos.mie.lognormal_table.cache_clear()
+    _, d = sos.mie.lognormal_table(*p)
+    assert np.array_equal(a, d)
+    sos.clear_caches(disk=True)
+    assert os.listdir(tmp_path) == []
+    monkeypatch.setenv("SOS_B200_CACHE", "off")
+    sos.mie.lognormal_table(*p)
+    assert os.listdir(tmp_path) == []
+    sos.mie.lognormal_table.cache_clear()
+
+
+def test_bench_arms_share_one_config():
+    """The driver compares the `config` objects of the two bench arms: both come from bench.workload_config."""
+    import ast as _ast
+    import bench
+    cfg = bench.workload_config(96)
+    assert cfg["workload"] == bench.WORKLOAD and cfg["layers"] == 800 and cfg["mu_columns"] == 1002
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = _ast.parse(src)
+    uses = [n for n in _ast.walk(tree) if isinstance(n, _ast.Call) and getattr(n.func, "id", "") == "workload_config"]
+    assert len(uses) >= 2   # reference arm and our arm
+    assert '"config": {"workload"' not in src.split("def thick_record")[0].split("def run_reference")[1].split("def ")[0]
+
+
+def test_phase_sweeps_are_split_to_the_plan_limits():
+    """More than 16 phase functions on one grid: solve_scenarios cuts the group into sub-batches a plan accepts."""
+    from sos_b200 import drivers as D
+    scs = [sos.Scenario(nb_layers=40, nb_angles=21, aer_phase=("hg", 0.3 + 0.02 * i)) for i in range(40)]
+    parts = D.split_for_plan_limits(scs, list(range(40)))
+    assert [i for p in parts for i in p] == list(range(40))
+    for p in parts:
+        specs = {scs[i].atm_phase for i in p} | {scs[i].aer_phase for i in p}
+        assert len(specs) <= D.MAX_PHASES_PER_PLAN
+    assert len(parts) == 3     # 1 atmosphere + 15 aerosols per plan
+    assert D.split_for_plan_limits(scs[:5], [0, 1, 2, 3, 4]) == [[0, 1, 2, 3, 4]]
