@@ -392,7 +392,6 @@ def main():
     units_per_step = int(np.sum(res.n_orders - 1)) * L * N * N
     n_orders = res.n_orders.copy()
     barrier()
-    lib.sos_set_profiling(eng._plan, 1)
     l0 = eng.launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
     barrier()
@@ -408,11 +407,23 @@ def main():
     t_wall = t_end - t_wall
     clocks = sampler.stop(t_begin, t_end)
     launches = eng.launches - l0
+    # per-kernel times: the SAME K steps once more with CUDA-event spans around every kernel class (on the launching
+    # stream).  The spans cost a few percent and switch the order loop from graph replays to single launches, so the
+    # headline pass above runs without them; step_ms_spans reports what this pass took.
     import ctypes as C
+    lib.sos_set_profiling(eng._plan, 1)
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        ev2[2 * k].record()
+        step_resident()
+        ev2[2 * k + 1].record()
+    barrier()
     ms4 = (C.c_double * 4)()
     sp4 = (C.c_longlong * 4)()
     lib.sos_get_profile(eng._plan, ms4, sp4, None)
     lib.sos_set_profiling(eng._plan, 0)
+    step_ms_spans = float(np.mean([ev2[2 * k].elapsed_time(ev2[2 * k + 1]) for k in range(args.steps)]))
     step_ms = float(np.mean([ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]))
     t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
     u = torch.tensor([float(units_per_step)], dtype=torch.float64, device=dev)
@@ -480,13 +491,13 @@ def main():
         "peak_source": "FP64 DMMA m8n8k4 loop measured on this GPU in this run (sos_fp64_peak); MEASURED_PEAKS.json has no FP64 "
                        "entry; DFMA loop measured %.1f TFLOP/s" % pk_dfma.value,
         "ms_per_launch": d_ms / max(dense_launches or gemm_launches, 1), "launches": dense_launches or gemm_launches,
-        "share_of_step": gemm_ms / (step_ms * args.steps),
+        "share_of_step": gemm_ms / (step_ms_spans * args.steps),
     }
     sweeps_class = {
         "kernels": "sweep_local + sweep_carry + sweep_apply2 + sweep_zone", "ms_per_order": sweep_ms / max(sweep_spans, 1),
         "achieved": sweep_class_bytes / (sweep_ms * 1e-3) * 1e-9 if sweep_ms > 0 else None, "unit": "GB/s",
         "frac": (sweep_class_bytes / (sweep_ms * 1e-3) * 1e-9 / hbm_peak) if sweep_ms > 0 else None,
-        "share_of_step": sweep_ms / (step_ms * args.steps),
+        "share_of_step": sweep_ms / (step_ms_spans * args.steps),
         "note": "the local pass (chunk aggregates) reads nothing on the rebuilt rows: it is FP64-pipe work, not traffic",
     }
     if apply_ms >= d_ms or not dense_launches:
@@ -499,7 +510,9 @@ def main():
             "algorithmic_bytes_per_element": {"rows with a rebuilt source": 16, "aerosol rows": 32},
             "algorithmic_bytes_per_launch": apply_bytes / max(apply_launches, 1),
             "ms_per_launch": apply_ms / max(apply_launches, 1), "launches": apply_launches,
-            "share_of_step": apply_ms / (step_ms * args.steps), "peak_source": hbm_src,
+            "share_of_step": apply_ms / (step_ms_spans * args.steps), "peak_source": hbm_src,
+            "timing": "CUDA-event spans on the launching stream in a second pass of the same %d steps (%.2f ms per step with spans; the "
+                      "headline pass runs without them, as CUDA-graph replays of two orders each)" % (args.steps, step_ms_spans),
             "sweeps_class": sweeps_class, "contraction": contraction,
         }
     else:

@@ -159,6 +159,14 @@ struct sos_plan {
   int gen_nslots = 0, gen_zlo = 0, gen_zu_end = 0;
   double* d_proj = nullptr;     // [S][L][nslots][2]
   double* d_cj[2] = {nullptr, nullptr};  // [S][L][2] source coefficients, ping-pong over the orders
+  // CUDA graph of two consecutive orders (even + odd: the source coefficients ping-pong), replayed by sos_solve
+  struct OrderGraph {
+    const void* I; const void* In; const void* J; bool gen; cudaGraphExec_t exec; long long launches;
+    sosgemm::GemmParams gp; sosgemm::FoldParams fp; int zlo, zu_end;   // what the captured launches baked in (see order_graph)
+  };
+  std::vector<OrderGraph> graphs;
+  cudaStream_t cap_stream = nullptr;   // capture needs a non-legacy stream; replays go to the caller's stream
+  cudaEvent_t graph_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -292,6 +300,13 @@ int plan_tiles(sos_plan* p, cudaStream_t st) {
                                        p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS,
                                        p->split_passes);
   return launch_check(p);
+}
+
+// instantiated order graphs bake in kernel arguments (operand pointers, zone columns, tile shapes): anything that changes
+// the plan's tables drops them
+void drop_graphs(sos_plan* p) {
+  for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
+  p->graphs.clear();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -591,7 +606,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     if (e == cudaSuccess) {
       auto& fl = pinned_free_list();
       if (!fl.empty()) { p->h_poll = fl.back(); fl.pop_back(); }
-      else e = cudaMallocHost(reinterpret_cast<void**>(&p->h_poll), kPollSlots * sizeof(int));
+      else e = cudaMallocHost(reinterpret_cast<void**>(&p->h_poll), (kPollSlots + 1) * sizeof(int));  // (+1: the order graph's slot)
     }
     if (e != cudaSuccess) { g_last_cuda_error = cudaGetErrorString(e); sos_plan_destroy(p); return SOS_ERR_CUDA; }
   }
@@ -735,6 +750,9 @@ int sos_plan_destroy(sos_plan* p) {
   SOS_GUARD(p);  // the sync and the stream-ordered frees below must run on the plan's own device
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   cudaDeviceSynchronize();  // nothing of this plan may still be running on any stream
+  drop_graphs(p);
+  for (cudaEvent_t& e : p->graph_ev) if (e) cudaEventDestroy(e);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   for (void* a : p->allocs) cudaFreeAsync(a, nullptr);
   if (p->h_poll) pinned_free_list().push_back(p->h_poll);
   delete p;
@@ -757,6 +775,7 @@ int sos_plan_query(const sos_plan* p, int what) {
 int sos_plan_set_columns(sos_plan* p, int col0, int col1) {
   if (!p) return SOS_ERR_INVALID;
   SOS_GUARD(p);
+  drop_graphs(p);
   GridDev& g = p->dev;
   if (col0 < 0 || col1 > g.N || col0 >= col1) return SOS_ERR_INVALID;
   if (col0 == 0 && col1 == g.N) { g.col0 = 0; g.col1 = g.N; return SOS_OK; }
@@ -786,6 +805,7 @@ int sos_state_ratios(sos_plan* p, double* buf_d, int set, void* stream) {
 int sos_set_profiling(sos_plan* p, int enabled) {
   if (!p) return SOS_ERR_INVALID;
   SOS_GUARD(p);
+  drop_graphs(p);
   p->profiling = enabled != 0;
   return SOS_OK;
 }
@@ -860,6 +880,7 @@ static int encode_A_maps(sos_plan* p) {
 int sos_plan_set_phase(sos_plan* p, const double* const* A_d, int n, int lda) {
   if (!p || !A_d || n < 1 || n > SOS_MAX_PHASE || lda < p->N || (lda & 1)) return SOS_ERR_INVALID;
   SOS_GUARD(p);
+  drop_graphs(p);
   for (const sos_scenario& sc : p->scen_h)
     if (sc.phase_atm >= n || sc.phase_aer >= n) return SOS_ERR_INVALID;
   for (int i = 0; i < n; ++i)
@@ -1018,6 +1039,7 @@ int sos_build_lowrank_mu2(sos_plan* p, const double* A_d, int lda, double* Ut_d,
 int sos_plan_set_lowrank(sos_plan* p, const double* const* Ut_d, const double* const* Vt_d, const int* rank, int n, int ldr) {
   if (!p) return SOS_ERR_INVALID;
   SOS_GUARD(p);
+  drop_graphs(p);
   if (n == 0) {
     for (int i = 0; i < SOS_MAX_PHASE; ++i) p->lowrank_rank[i] = 0;
   } else {
@@ -1052,6 +1074,7 @@ static int premix_folded(sos_plan* p) {
 int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   if (!p) return SOS_ERR_INVALID;
   SOS_GUARD(p);
+  drop_graphs(p);
   if (n == 0 || !F_d) {
     const bool replan = p->fold;
     p->fold = false;
@@ -1426,6 +1449,65 @@ static bool gen_applies(const sos_plan* p) {
   return true;
 }
 
+// one scattering order: source (dense rows) -> sweeps -> convergence bookkeeping -> tile plan of the next contraction
+static int order_body(sos_plan* p, double* I_d, double* In_d, double* J_d, double* saved, int n, bool gen, cudaStream_t st,
+                      bool device_order) {
+  int rc = source_impl(p, In_d, J_d, 0, 0x7fffffff, st, nullptr, 0, nullptr, gen);
+  if (rc) return rc;
+  rc = sweeps_impl(p, J_d, In_d, I_d, saved, st, gen ? n : -1);
+  if (rc) return rc;
+  // (inside a graph the order number comes from the device-side counter: replays cannot change kernel arguments)
+  sossweep::converge_kernel<<<1, 256, 0, st>>>(p->dev, device_order ? -1 : n, p->d_order);
+  rc = launch_check(p, "converge_kernel");
+  if (rc) return rc;
+  return plan_tiles(p, st);
+}
+
+// The order loop is launch-latency bound for small batches (a single default-grid solve: ~45 us of kernels per order
+// behind ~10 launches) and keeps one host thread per GPU busy for large ones.  Two consecutive orders (even + odd: the
+// source coefficients ping-pong between two buffers) are captured once per (plan, field buffers) into a CUDA graph and
+// replayed; every kernel takes what changes from device memory (active list, tile plan, order counter) and exits at once
+// when nothing is active, so replays past convergence cost only their launch.  Returns nullptr when the order body
+// cannot be captured (the caller then launches kernel by kernel).
+static sos_plan::OrderGraph* order_graph(sos_plan* p, double* I_d, double* In_d, double* J_d, bool gen) {
+  for (auto& g : p->graphs) {
+    if (g.I == I_d && g.In == In_d && g.J == J_d && g.gen == gen) {
+      if (std::memcmp(&g.gp, &p->gp, sizeof(p->gp)) == 0 && std::memcmp(&g.fp, &p->fp, sizeof(p->fp)) == 0 && g.zlo == p->gen_zlo &&
+          g.zu_end == p->gen_zu_end)
+        return &g;
+      drop_graphs(p);   // the plan's tables have changed since the capture
+      break;
+    }
+  }
+  if (!p->cap_stream && cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  for (auto& e : p->graph_ev)
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  const long long l0 = p->launches;
+  if (cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  int rc = order_body(p, I_d, In_d, J_d, nullptr, 2, gen, p->cap_stream, true);
+  if (!rc) rc = order_body(p, I_d, In_d, J_d, nullptr, 3, gen, p->cap_stream, true);
+  if (!rc && cudaMemcpyAsync(p->h_poll + kPollSlots, p->dev.n_active, sizeof(int), cudaMemcpyDeviceToHost, p->cap_stream) != cudaSuccess) rc = SOS_ERR_CUDA;
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ee = cudaStreamEndCapture(p->cap_stream, &graph);
+  const long long per_replay = p->launches - l0;
+  p->launches = l0;
+  if (rc || ee != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return nullptr;
+  }
+  sos_plan::OrderGraph og;
+  og.I = I_d; og.In = In_d; og.J = J_d; og.gen = gen; og.launches = per_replay;
+  std::memcpy(&og.gp, &p->gp, sizeof(p->gp));
+  std::memcpy(&og.fp, &p->fp, sizeof(p->fp));
+  og.zlo = p->gen_zlo; og.zu_end = p->gen_zu_end;
+  if (cudaGraphInstantiate(&og.exec, graph, 0) != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return nullptr; }
+  cudaGraphDestroy(graph);
+  if (p->graphs.size() >= 4) drop_graphs(p);
+  p->graphs.push_back(og);
+  return &p->graphs.back();
+}
+
 int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* orders_d, int max_saved, int max_orders,
               int poll_every, sos_result* results_h, void* stream) {
   if (!p || !I_d || !In_d || !J_d) return SOS_ERR_INVALID;
@@ -1457,13 +1539,33 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
   int issued = 0;
   bool done = false;
   int next_check = 0;  // slot index next to be examined
-  for (int n = 2; n <= max_orders && !done; ++n) {
-    rc = source_impl(p, In_d, J_d, 0, 0x7fffffff, stream, nullptr, 0, nullptr, gen);
-    if (rc) break;
+  int n = 2;
+  // ---- graph replays, two orders each (not while saving per-order fields, timing kernel classes or debugging launches) ----
+  const bool graphs_on = env_int("SOS_B200_GRAPH", 1) != 0 && env_int("SOS_B200_SYNC_DEBUG", 0) == 0;
+  if (graphs_on && !orders_d && !p->profiling && max_orders >= 3) {
+    sos_plan::OrderGraph* og = order_graph(p, I_d, In_d, J_d, gen);
+    if (og) {
+      volatile int* gslot = p->h_poll + kPollSlots;
+      *gslot = -1;
+      int k = 0;
+      while (!done && n + 1 <= max_orders) {
+        if (k >= 3) cudaEventSynchronize(p->graph_ev[(k - 3) & 3]);   // run-ahead: at most three replays (six orders)
+        if (*gslot == 0) { done = true; break; }
+        if (cudaGraphLaunch(og->exec, st) != cudaSuccess) { g_last_cuda_error = "cudaGraphLaunch failed"; return SOS_ERR_CUDA; }
+        cudaEventRecord(p->graph_ev[k & 3], st);
+        p->launches += og->launches;
+        ++k;
+        n += 2;
+      }
+      if (!done && n <= max_orders) {   // an odd remainder up to max_orders: know first whether it is needed at all
+        cudaStreamSynchronize(st);
+        if (*gslot == 0) done = true;
+      }
+    }
+  }
+  for (; n <= max_orders && !done; ++n) {
     double* saved = (orders_d && n - 2 < max_saved) ? orders_d + static_cast<size_t>(n - 2) * field : nullptr;
-    rc = sweeps_impl(p, J_d, In_d, I_d, saved, st, gen ? n : -1);
-    if (rc) break;
-    rc = sos_converge(p, n, stream);
+    rc = order_body(p, I_d, In_d, J_d, saved, n, gen, st, false);
     if (rc) break;
     const int slot = issued % nslots;
     if (issued >= nslots) poll[slot] = -1;  // that copy finished long ago (run-ahead is bounded below)

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--slabs", type=int, default=1)
     ap.add_argument("--p2p", action="store_true", help="fused all-gather: contraction reads peer memory over NVLink")
+    ap.add_argument("--ref-general", action="store_true", help="--check against the unsharded solve with the GENERAL contraction kernel "
+                    "(what the sharded plans run): the two must then agree bit for bit; the default reference uses the folded kernel")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -85,9 +87,10 @@ def main():
     if args.check:
         I_sh = I[:, :N].cpu().numpy()
         if rank == 0:
-            ref = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE, device=dev)
+            ref = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE, device=dev, fold=False if args.ref_general else None)
             ref.set_phase([P])
             r = ref.solve(ref.first_order(Cc), max_orders=args.orders + 1)
+            out["reference_contraction"] = "folded" if ref.folded else "general"
             I_ref = r.I[:, :N].cpu().numpy()
             out["max_rel_dev_vs_unsharded"] = float(np.max(np.abs(I_sh - I_ref)) / np.max(np.abs(I_ref)))
             out["orders_unsharded"] = int(r.n_orders[0]) - 1
