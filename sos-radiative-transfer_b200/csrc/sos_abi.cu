@@ -113,6 +113,9 @@ struct sos_plan {
   double* d_z = nullptr;     // [L]
   double* d_colint = nullptr;  // [N] column integrals of the device phase builder
   int* h_poll = nullptr;     // pinned
+  double* h_C[2] = {nullptr, nullptr};        // pinned staging of the first-order coefficients (sos_first_order never blocks)
+  cudaEvent_t h_C_ev[2] = {nullptr, nullptr};
+  int h_C_next = 0;
   std::vector<sos_scenario> scen_h;
   std::vector<double> mu_h;
   // GEMM
@@ -207,6 +210,12 @@ std::vector<int*>& pinned_free_list() {
   return v;
 }
 constexpr int kPollSlots = 4096;
+
+// ... and so are the staging buffers of the first-order coefficients, by size
+std::vector<std::pair<size_t, double*>>& pinned_coef_free_list() {
+  static std::vector<std::pair<size_t, double*>> v;
+  return v;
+}
 
 template <typename T>
 int dev_alloc(sos_plan* p, T** out, size_t count) {
@@ -506,6 +515,7 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
 
   // ---- chunks: never straddle a region ----
   int chunk = grid->chunk_rows;
+  if (chunk <= 0) chunk = env_int("SOS_B200_CHUNK_ROWS", 0);  // (experiments; 0 = choose)
   if (chunk <= 0) {
     // enough (scenario x chunk x column) threads to fill the chip
     const long long want = 4LL * p->n_sms * 2048;
@@ -521,8 +531,9 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     const int len = r1 - r0;
     const int nck = (len + chunk - 1) / chunk;
     for (int i = 0; i < nck; ++i) {
-      // balanced split
-      const int a = r0 + static_cast<int>(static_cast<long long>(len) * i / nck);
+      // balanced split, chunk lengths in whole groups of four rows (the scan passes run four rows per step: only the
+      // chunk that ends its region is left with a remainder for the row-by-row tail)
+      const int a = r0 + static_cast<int>(static_cast<long long>(len) * i / nck) / 4 * 4;
       cstart.push_back(a);
       cregion.push_back(k);
     }
@@ -751,6 +762,14 @@ int sos_plan_destroy(sos_plan* p) {
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   cudaDeviceSynchronize();  // nothing of this plan may still be running on any stream
   drop_graphs(p);
+  for (int k = 0; k < 2; ++k) {
+    if (p->h_C[k]) {
+      auto& fl = pinned_coef_free_list();
+      if (fl.size() < 8) fl.push_back({sizeof(double) * p->dev.S * 2 * p->dev.N, p->h_C[k]});
+      else cudaFreeHost(p->h_C[k]);
+    }
+    if (p->h_C_ev[k]) cudaEventDestroy(p->h_C_ev[k]);
+  }
   for (cudaEvent_t& e : p->graph_ev) if (e) cudaEventDestroy(e);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   for (void* a : p->allocs) cudaFreeAsync(a, nullptr);
@@ -1136,9 +1155,25 @@ int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) 
   NvtxRange nvtx("sos:first_order");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GridDev& g = p->dev;
-  SOS_CUDA(cudaMemcpyAsync(p->d_C, C_h, sizeof(double) * g.S * 2 * g.N, cudaMemcpyHostToDevice, st));
-  // C_h may be pageable: make sure the copy has consumed it before we return
-  SOS_CUDA(cudaStreamSynchronize(st));
+  {
+    // C_h belongs to the caller (and may be pageable): it is copied into one of two pinned staging buffers owned by the
+    // plan, so the H2D copy is truly asynchronous and the call returns without waiting for the stream
+    const size_t bytes = sizeof(double) * g.S * 2 * g.N;
+    const int k = p->h_C_next;
+    p->h_C_next ^= 1;
+    if (!p->h_C[k]) {
+      auto& fl = pinned_coef_free_list();
+      for (size_t i = 0; i < fl.size() && !p->h_C[k]; ++i)
+        if (fl[i].first == bytes) { p->h_C[k] = fl[i].second; fl.erase(fl.begin() + i); }
+      if (!p->h_C[k]) SOS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_C[k]), bytes));
+      SOS_CUDA(cudaEventCreateWithFlags(&p->h_C_ev[k], cudaEventDisableTiming));
+    } else {
+      SOS_CUDA(cudaEventSynchronize(p->h_C_ev[k]));  // the copy issued two calls ago has left this buffer
+    }
+    std::memcpy(p->h_C[k], C_h, bytes);
+    SOS_CUDA(cudaMemcpyAsync(p->d_C, p->h_C[k], bytes, cudaMemcpyHostToDevice, st));
+    SOS_CUDA(cudaEventRecord(p->h_C_ev[k], st));
+  }
   const int rows_per_block = 32;
   dim3 grid((g.N + 127) / 128, (g.L + rows_per_block - 1) / rows_per_block, g.S);
   if (g.nreg == 3)
