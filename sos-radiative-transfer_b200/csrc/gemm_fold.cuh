@@ -32,7 +32,7 @@ struct FoldParams {
   int nseg[2];
   int n_col_tiles;   // ceil(M / BN)
   int split_passes;  // see GemmParams
-  int ksplit;        // 1, or 2: every output tile is computed by two tiles (halves of the k range) that add their partial into a
+  int ksplit;        // 0: chosen per launch on the device (1 or 2; J rows zeroed by the caller); 1, or 2: every output tile is computed by two tiles (halves of the k range) that add their partial into a
                      //    zeroed J (exactly two partials per element: order independent) -- launches with fewer tiles than SMs / 2
   int L, N, M, Mh, ld;
   double* J;
@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
   const TilePlan* plan = p.plan;
   const int ksteps = (p.M + BK - 1) / BK;
   const int last_slabs = (p.M - (ksteps - 1) * BK + 3) / 4;  // k-slabs of the last k-step that hold k < M
-  const int n_tiles = plan->n_row_tiles * p.n_col_tiles * p.ksplit;
+  // ksplit == 0: decided per launch from the device-built tile plan -- when the output tiles would leave more than half
+  // of the CTAs idle (few scenarios still iterating), every tile is computed as two halves of the k range
+  const int ksplit = p.ksplit > 0 ? p.ksplit : ((2 * plan->n_row_tiles * p.n_col_tiles <= static_cast<int>(gridDim.x) && p.M >= 64) ? 2 : 1);
+  const int n_tiles = plan->n_row_tiles * p.n_col_tiles * ksplit;
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp >= C::CONSUMER_WARPS) {
@@ -171,9 +174,9 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
         }
         break;
       }
-      const int t2 = tile / p.ksplit;
-      const int kh = tile - t2 * p.ksplit;
-      const int ks0 = kh * ksteps / p.ksplit, ks1 = (kh + 1) * ksteps / p.ksplit;
+      const int t2 = tile / ksplit;
+      const int kh = tile - t2 * ksplit;
+      const int ks0 = kh * ksteps / ksplit, ks1 = (kh + 1) * ksteps / ksplit;
       const int rt = t2 / p.n_col_tiles;
       const int ct = t2 - rt * p.n_col_tiles;
       const int g = find_group(plan, rt);
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
       }
       const int passes = (cls == 1 && !split) ? 2 : 1;
       if (lane == 0) {
-        info->ct = ct; info->passes = passes; info->first_pass = only_pass; info->atomic_out = (split || p.ksplit > 1) ? 1 : 0;
+        info->ct = ct; info->passes = passes; info->first_pass = only_pass; info->atomic_out = (split || ksplit > 1) ? 1 : 0;
         info->ks0 = ks0; info->ks1 = ks1;
       }
       __syncwarp();

@@ -1296,10 +1296,14 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
   SOS_CUDA(cudaMemsetAsync(p->d_work_counter, 0, sizeof(int), st));
   const bool full_columns = g.col0 == 0 && g.col1 == g.N;
   const bool use_fold = p->fold && full_columns && !peers && seg_begin == 0 && seg_end == 0x7fffffff;
+  // inside sos_solve with a generated source only the aerosol rows have dense tiles: the kernel then decides per launch,
+  // from the device-built tile plan, whether to split k (few scenarios still iterating) -- their J rows start from zero
+  const bool dyn_ksplit = use_fold && skip_lowrank && p->fold_ksplit == 1 && !p->split_passes && g.nreg == 3 && g.M >= 64 &&
+                          env_int("SOS_B200_DYN_KSPLIT", 1) != 0;
   if (use_fold && p->fold_ksplit > 1) {
     // split-k tiles add two partials per element into a zeroed J
     SOS_CUDA(cudaMemsetAsync(J_d, 0, static_cast<size_t>(g.S) * g.L * g.ld * sizeof(double), st));
-  } else if (p->split_passes) {
+  } else if (p->split_passes || dyn_ksplit) {
     const int r0 = g.rstart[1], r1 = g.rstart[2];
     dim3 zgrid((g.N + 255) / 256, r1 - r0, g.S);
     zero_rows_kernel<<<zgrid, 256, 0, st>>>(J_d, g.ld, g.L, r0, r1, g.N);
@@ -1318,7 +1322,7 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     for (int c = 0; c < 2; ++c) { f.seg_row[c] = p->gp.seg_row[c]; f.seg_valid[c] = p->gp.seg_valid[c]; f.nseg[c] = p->gp.nseg[c]; }
     f.n_col_tiles = (g.M + FC::BN - 1) / FC::BN;
     f.split_passes = p->split_passes;
-    f.ksplit = p->fold_ksplit;
+    f.ksplit = dyn_ksplit ? 0 : p->fold_ksplit;
     f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
     f.J = J_d;
     f.scen = g.scen;
