@@ -7,6 +7,8 @@ package raises.  Build the library with `python -c "import __graft_entry__ as g;
 from __future__ import annotations
 
 import ctypes as C
+
+import numpy as np
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -48,6 +50,13 @@ class sos_scenario(C.Structure):
         ("extrap_width", C.c_int * 3),
         ("reserved", C.c_int),
     ]
+
+
+# the same 80 bytes as a NumPy record: whole batches are marshalled without a Python loop (engine.scenario_table)
+SCENARIO_DTYPE = np.dtype([("mu0", "f8"), ("grd_alb", "f8"), ("tauStar_tot", "f8"), ("coef_atm", "f8"), ("coef_mix_atm", "f8"),
+                           ("coef_mix_aer", "f8"), ("threshold", "f8"), ("phase_atm", "i4"), ("phase_aer", "i4"),
+                           ("extrap_width", "i4", 3), ("reserved", "i4")])
+assert SCENARIO_DTYPE.itemsize == C.sizeof(sos_scenario)
 
 
 class sos_result(C.Structure):

@@ -256,6 +256,14 @@ __global__ void zero_rows_kernel(double* J, int ld, int L, int r0, int r1, int N
   if (t < r1 && m < N) J[(static_cast<size_t>(s) * L + t) * ld + m] = 0.0;
 }
 
+// ... of the scenarios that are still iterating only, sixteen bytes per store (the per-order form used with split-k chosen on the device)
+__global__ void __launch_bounds__(256) zero_active_rows_kernel(double* J, int ld, int L, int r0, const ScenState* state) {
+  const int s = blockIdx.y;
+  if (!state[s].active) return;
+  double2* row = reinterpret_cast<double2*>(J + (static_cast<size_t>(s) * L + r0 + blockIdx.x) * ld);
+  for (int i = threadIdx.x; i < ld / 2; i += 256) row[i] = make_double2(0.0, 0.0);
+}
+
 cudaEvent_t prof_event(sos_plan* p) {
   if (p->ev_used == p->ev_pool.size()) {
     cudaEvent_t e;
@@ -1174,7 +1182,7 @@ int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) 
     SOS_CUDA(cudaMemcpyAsync(p->d_C, p->h_C[k], bytes, cudaMemcpyHostToDevice, st));
     SOS_CUDA(cudaEventRecord(p->h_C_ev[k], st));
   }
-  const int rows_per_block = 32;
+  const int rows_per_block = std::min(64, std::max(8, env_int("SOS_B200_FO_ROWS", 64)));  // (the kernel stages 64 rows at most)
   dim3 grid((g.N + 127) / 128, (g.L + rows_per_block - 1) / rows_per_block, g.S);
   if (g.nreg == 3)
     sosfirst::first_order_regions_kernel<<<grid, 128, 0, st>>>(g, p->d_C, I1_d, rows_per_block);
@@ -1303,7 +1311,11 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
   if (use_fold && p->fold_ksplit > 1) {
     // split-k tiles add two partials per element into a zeroed J
     SOS_CUDA(cudaMemsetAsync(J_d, 0, static_cast<size_t>(g.S) * g.L * g.ld * sizeof(double), st));
-  } else if (p->split_passes || dyn_ksplit) {
+  } else if (dyn_ksplit) {
+    zero_active_rows_kernel<<<dim3(g.rstart[2] - g.rstart[1], g.S), 256, 0, st>>>(J_d, g.ld, g.L, g.rstart[1], g.state);
+    int rz = launch_check(p, "zero_active_rows_kernel");
+    if (rz) return rz;
+  } else if (p->split_passes) {
     const int r0 = g.rstart[1], r1 = g.rstart[2];
     dim3 zgrid((g.N + 255) / 256, r1 - r0, g.S);
     zero_rows_kernel<<<zgrid, 256, 0, st>>>(J_d, g.ld, g.L, r0, r1, g.N);

@@ -167,9 +167,11 @@ class BatchSolver:
         self.scenarios = list(scenarios)
         L, M = self.L, self.M
         S = len(scenarios)
-        tau = np.empty((S, L))
-        coefs = []
-        Ccoef = np.empty((S, 2, self.N))
+        # batch-sized host buffers are kept between batches (BatchSolver.update): fresh ones cost page faults every time
+        bufs = getattr(self, "_host_bufs", None)
+        if bufs is None or bufs[0].shape != (S, L):
+            bufs = self._host_bufs = (np.empty((S, L)), np.empty((S, 2, self.N)), np.empty((S, self.N)), np.empty((S, self.N)))
+        tau, Ccoef = bufs[0], bufs[1]
         # tau profiles of the whole batch at once: the same arithmetic as grid.tau_profile, element for element
         # (the group key fixes idx_up / idx_down for every scenario of the batch)
         rows = np.arange(L)
@@ -180,29 +182,50 @@ class BatchSolver:
         tau[:, inside] += (rows[inside] + 1 - self.idx_up)[None, :] * (t_aer / (self.idx_down + 1 - self.idx_up))[:, None]
         tau[:, rows > self.idx_down] += t_aer[:, None]
         self._new_mats = 0
+        # phase tables: one look-up per DISTINCT (phase, mu0) of the batch, then everything below is array arithmetic
+        P0A, P0E = bufs[2], bufs[3]
+        idx_atm = np.empty(S, dtype=np.int32)
+        idx_aer = np.empty(S, dtype=np.int32)
+        seen = {}
         for i, sc in enumerate(scenarios):
-            P0a, Pa, ka = self._phases.get(sc.atm_phase, M, self.mu, sc.mu0, need_P=not self._device_phase)
-            P0e, Pe, ke = self._phases.get(sc.aer_phase, M, self.mu, sc.mu0, need_P=not self._device_phase)
-            for k, P in ((ka, Pa), (ke, Pe)):
-                if k not in self._mat_index:
-                    self._mat_index[k] = len(self._mats)
-                    self._mats.append(P)
-                    self._mat_keys.append(k if k[0] != "array" else None)  # analytic families are immutable: cache on device
-                    self._new_mats += 1
-            # global mixing weights (SOS_Aer_main_specular.py:52-53; note dtau_atm = tauStar_atm / L, Q9)
-            dtau_aer = sc.tauStar_aer / (self.idx_down + 1 - self.idx_up)
-            dtau_atm = sc.tauStar_atm / L
-            f_atm = dtau_atm / (dtau_atm + dtau_aer)
-            f_aer = dtau_aer / (dtau_atm + dtau_aer)
-            Ccoef[i, 0] = sc.alb_atm * P0a
-            Ccoef[i, 1] = sc.alb_atm * P0a * f_atm + sc.alb_aer * P0e * f_aer
-            widths = (G.extrapolation_width(float(tau[i, self.idx_up - 1]), M),
-                      G.extrapolation_width(float(tau[i, self.idx_down]), M),
-                      G.extrapolation_width(float(tau[i, self.idx_down]), M))
-            coefs.append(ScenarioCoefficients(
-                mu0=sc.mu0, grd_alb=sc.grd_alb, tauStar_tot=sc.tauStar_atm + sc.tauStar_aer,
-                coef_atm=sc.alb_atm, coef_mix_atm=sc.alb_atm * f_atm, coef_mix_aer=sc.alb_aer * f_aer,
-                threshold=sc.threshold, phase_atm=self._mat_index[ka], phase_aer=self._mat_index[ke], extrap_width=widths))
+            for spec, P0dst, idst in ((sc.atm_phase, P0A, idx_atm), (sc.aer_phase, P0E, idx_aer)):
+                key = (spec if isinstance(spec[0], str) else id(spec[1]), sc.mu0)
+                hit = seen.get(key)
+                if hit is None:
+                    P0, P, k = self._phases.get(spec, M, self.mu, sc.mu0, need_P=not self._device_phase)
+                    if k not in self._mat_index:
+                        self._mat_index[k] = len(self._mats)
+                        self._mats.append(P)
+                        self._mat_keys.append(k if k[0] != "array" else None)  # analytic families are immutable: cache on device
+                        self._new_mats += 1
+                    hit = seen[key] = (P0, self._mat_index[k])
+                P0dst[i] = hit[0]
+                idst[i] = hit[1]
+        alb_atm = np.array([sc.alb_atm for sc in scenarios], dtype=np.float64)
+        alb_aer = np.array([sc.alb_aer for sc in scenarios], dtype=np.float64)
+        # global mixing weights (SOS_Aer_main_specular.py:52-53; note dtau_atm = tauStar_atm / L, Q9)
+        dtau_aer = t_aer / (self.idx_down + 1 - self.idx_up)
+        dtau_atm = t_atm / L
+        f_atm = dtau_atm / (dtau_atm + dtau_aer)
+        f_aer = dtau_aer / (dtau_atm + dtau_aer)
+        # (in place: same operations in the same order as the scalar formulas, without batch-sized temporaries)
+        np.multiply(P0A, alb_atm[:, None], out=Ccoef[:, 0])
+        np.multiply(Ccoef[:, 0], f_atm[:, None], out=Ccoef[:, 1])
+        np.multiply(P0E, alb_aer[:, None], out=P0E)
+        np.multiply(P0E, f_aer[:, None], out=P0E)
+        np.add(Ccoef[:, 1], P0E, out=Ccoef[:, 1])
+        coefs = np.zeros(S, dtype=_lib.SCENARIO_DTYPE)
+        coefs["mu0"] = [sc.mu0 for sc in scenarios]
+        coefs["grd_alb"] = [sc.grd_alb for sc in scenarios]
+        coefs["tauStar_tot"] = t_atm + t_aer
+        coefs["coef_atm"] = alb_atm
+        coefs["coef_mix_atm"] = alb_atm * f_atm
+        coefs["coef_mix_aer"] = alb_aer * f_aer
+        coefs["threshold"] = [sc.threshold for sc in scenarios]
+        coefs["phase_atm"] = idx_atm
+        coefs["phase_aer"] = idx_aer
+        coefs["extrap_width"][:, 0] = G.extrapolation_widths(tau[:, self.idx_up - 1], M)
+        coefs["extrap_width"][:, 1] = coefs["extrap_width"][:, 2] = G.extrapolation_widths(tau[:, self.idx_down], M)
         self.tau = tau
         self.Ccoef = Ccoef
         return coefs
@@ -257,22 +280,27 @@ class BatchSolver:
         if keep_orders and res.orders is not None:
             orders = res.orders[:, :, : eng.N].reshape(keep_orders, eng.S, eng.L, eng.N).cpu().numpy()
         I1 = eng.to_host(self.I1).reshape(eng.S, eng.L, eng.N) if (keep_orders and res.orders is not None) else None
+        toa = None
+        if q is not None:
+            # TOA net flux with the F0/(4 pi) direct scaling (SOS_Aer_critical_albedo.py:377-382): same quadrature sums, direct
+            # terms rescaled from F0 to F0/(4 pi) -- for the whole batch at once
+            mu0 = np.array([sc.mu0 for sc in self.scenarios], dtype=np.float64)
+            alb = np.array([sc.grd_alb for sc in self.scenarios], dtype=np.float64)
+            k = (np.pi / mu0) * (1.0 - 1.0 / (4 * np.pi))
+            t0, tl = self.tau[:, 0], self.tau[:, -1]
+            fd = q["flux_down"][:, 0] + k * np.exp(-t0 / mu0)
+            fu = q["flux_up"][:, 0] - k * alb * np.exp(-(2 * tl - t0) / mu0)
+            toa = -fd - fu
+        tau_out = self.tau.copy()   # (self.tau is a buffer reused by the next update())
         out = []
         for i, sc in enumerate(self.scenarios):
-            r = DriverResult(I=I[i] if fields else None, n=int(res.n_orders[i]), tau=self.tau[i], mu=self.mu,
+            r = DriverResult(I=I[i] if fields else None, n=int(res.n_orders[i]), tau=tau_out[i], mu=self.mu,
                              z_profile=self.z, idx_up=self.idx_up, idx_down=self.idx_down,
                              ratio=float(max(res.ratio_toa[i], res.ratio_surf[i])), status=int(res.status[i]))
             if q is not None:
                 r.flux_up, r.flux_down, r.net_flux = q["flux_up"][i], q["flux_down"][i], q["net_flux"][i]
                 r.diffusivity, r.heating_rate = q["diffusivity"][i], q["heating_rate"][i]
-                # TOA net flux with the F0/(4 pi) direct scaling (SOS_Aer_critical_albedo.py:377-382):
-                # same quadrature sums, direct terms rescaled from F0 to F0/(4 pi)
-                F0 = np.pi / sc.mu0
-                k = F0 * (1.0 - 1.0 / (4 * np.pi))
-                t0, tl = self.tau[i][0], self.tau[i][-1]
-                fd = r.flux_down[0] + k * np.exp(-t0 / sc.mu0)
-                fu = r.flux_up[0] - k * sc.grd_alb * np.exp(-(2 * tl - t0) / sc.mu0)
-                r.toa_net_flux = float(-fd - fu)
+                r.toa_net_flux = float(toa[i])
             if orders is not None:
                 r.I_saved = [I1[i]] + [orders[k, i] for k in range(min(keep_orders, r.n - 1))]
             if r.status & _lib.STATUS_BLEND_OVERRUN:

@@ -95,7 +95,7 @@ class SosEngine:
         self.n_regions = len(region_start) - 1
         self.region_start = list(region_start)
         self.surface = surface
-        self.scenarios = list(scenarios)
+        self.scenarios = scenarios
 
         g = _lib.sos_grid()
         g.nb_layers, g.nb_angles, g.n_scenarios, g.n_regions = self.L, self.M, self.S, self.n_regions
@@ -112,6 +112,13 @@ class SosEngine:
         self._bufs = {}
 
     def _scenario_array(self, scenarios):
+        """ctypes view of the per-scenario records: a list of ScenarioCoefficients, or a NumPy record array of
+        _lib.SCENARIO_DTYPE (what BatchSolver builds for a whole batch at once)."""
+        if isinstance(scenarios, np.ndarray):
+            if scenarios.dtype != _lib.SCENARIO_DTYPE or scenarios.shape != (self.S,):
+                raise ValueError("scenario table: expected %d records of _lib.SCENARIO_DTYPE" % self.S)
+            self._scen_keepalive = np.ascontiguousarray(scenarios)
+            return C.cast(self._scen_keepalive.ctypes.data, C.POINTER(_lib.sos_scenario))
         sc = (_lib.sos_scenario * self.S)()
         for i, s in enumerate(scenarios):
             sc[i].mu0, sc[i].grd_alb, sc[i].tauStar_tot = s.mu0, s.grd_alb, s.tauStar_tot
@@ -129,9 +136,13 @@ class SosEngine:
         if tau.shape != (self.S, self.L) or len(scenarios) != self.S:
             raise ValueError("update: the batch must keep its shape (S scenarios x L layers)")
         n = len(self._A)
-        if any(s.phase_atm >= n or s.phase_aer >= n for s in scenarios):
+        if isinstance(scenarios, np.ndarray):
+            bad = bool(np.any(scenarios["phase_atm"] >= n) or np.any(scenarios["phase_aer"] >= n))
+        else:
+            bad = any(s.phase_atm >= n or s.phase_aer >= n for s in scenarios)
+        if bad:
             raise ValueError("update: scenario refers to a phase matrix that is not registered")
-        self.tau, self.scenarios = tau, list(scenarios)
+        self.tau, self.scenarios = tau, scenarios
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sos_plan_update(self._plan, tau.ctypes.data, self._scenario_array(scenarios), self._stream),
                        "sos_plan_update")

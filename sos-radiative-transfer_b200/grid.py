@@ -77,6 +77,13 @@ def extrapolation_width(tau_ref: float, nb_angles: int) -> int:
     return int(f * nb_angles)
 
 
+def extrapolation_widths(tau_ref, nb_angles: int) -> np.ndarray:
+    """extrapolation_width for an array of reference optical depths (same thresholds, same truncation)."""
+    t = np.asarray(tau_ref, dtype=np.float64)
+    f = np.select([t <= 0.0625, t <= 1, t < 4], _WIDTH_FACTORS[:3], default=_WIDTH_FACTORS[3])
+    return np.array([int(x * nb_angles) for x in f], dtype=np.int32)
+
+
 def _extrapolation_weights(mu_down: np.ndarray, width: int) -> np.ndarray:
     """Weights W[i, j] with target column M-1-i = sum_j W[i,j] * source column j.
 
