@@ -22,6 +22,8 @@
 #ifndef SOS_B200_H
 #define SOS_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -258,6 +260,23 @@ int sos_plan_query(const sos_plan* plan, int what);
  * N); only grids without surface coupling (n_regions == 1, SOS_SURFACE_NONE) can be sharded, and a
  * block boundary must not cut the mu -> 0 zones (SOS_ERR_UNSUPPORTED otherwise). */
 int sos_plan_set_columns(sos_plan* plan, int col0, int col1);
+/* Layer-block sharding of one large grid over the GPUs of a node (BASELINE configs[3]; the order loop it splits is
+ * SOS_Aer_main_specular.py:302-458 on the single-layer operators SOS_Aer_I1_In.py:62-130).  Rank r of n_ranks owns a
+ * contiguous block of scan chunks = layers [*row0_out, *row1_out): its source contraction and sweeps touch only those rows
+ * (the contraction a few halo rows more), every field keeps the full [L][ld] layout.  Per order the ranks exchange, by
+ * stores into each other's memory over NVLink (no host round trip, no NCCL call on the data path):
+ *   - the chunk aggregates of the scan (N doubles per chunk and direction), after which every rank runs the same carry
+ *     chain over the same numbers as the unsharded solve: results are bit-identical to it;
+ *   - the I_n rows next to a block boundary that the neighbour reads as halos, and the two convergence ratios.
+ * mailbox_peers_d[q] / In_peers_d[q]: rank q's mailbox (sos_layer_mailbox_bytes() bytes, 128-byte aligned, zeroed once at
+ * allocation) and I_n field as mapped into THIS process (sos_ipc_alloc / sos_ipc_open; entry `rank` = this rank's own
+ * buffers).  Afterwards sos_solve(plan, I_d, In_peers_d[rank], J_d, ...) runs the sharded order loop: every rank must call
+ * it with the same max_orders, I_d and In_d holding the first order on ALL rows; on exit the rank's rows of I_d are final.
+ * Only single-scenario, single-region plans without surface coupling, all mu columns.  n_ranks <= 1 restores the whole grid. */
+int sos_layer_mailbox_bytes(const sos_plan* plan, size_t* bytes);
+int sos_plan_set_layers(sos_plan* plan, int rank, int n_ranks, void* const* mailbox_peers_d, double* const* In_peers_d,
+                        int* row0_out, int* row1_out);
+
 /* Copy the per-scenario convergence ratios {ratio_toa, ratio_surf} to (set = 0) or from (set = 1) a
  * device buffer [S][2]: sharded ranks MAX-all-reduce them between sos_sweeps and sos_converge. */
 int sos_state_ratios(sos_plan* plan, double* buf_d, int set, void* stream);

@@ -20,7 +20,7 @@ from . import multi_gpu
 from . import graphe
 from .graphe import (graphe_diffusivity, graphe_flux, graphe_heating_rate, graphe_successive_dif, graphe_flux_up_down,
                      successive_diffusivity)
-from .multi_gpu import PeerFields, MuShardedSolver, mu_blocks, shard_scenarios, gather_scenario_results, allgather_columns, shard_range
+from .multi_gpu import PeerFields, PeerBuffers, LayerShardedSolver, MuShardedSolver, mu_blocks, shard_scenarios, gather_scenario_results, allgather_columns, shard_range
 from .drivers import (Scenario, DriverResult, BatchSolver, solve_scenarios, SOS_Aer_main_specular,
                       SOS_Aer_main_lambertian, SOS_Aer_radiative_forcing, SOS_Aer_critical_albedo,
                       critical_albedo_sweep, EVA, WILDFIRE, clear_caches)
@@ -29,7 +29,7 @@ __all__ = [
     "SosError", "mu_grid", "tau_profile", "extrapolation_width", "aerosol_rows", "phase_matrices", "phase_P", "phase_P0", "phase_table", "mie", "EVA_AEROSOL", "WILDFIRE_AEROSOL",
     "SosEngine", "ScenarioCoefficients", "SolveResult", "I1_NumInt", "Jn_NumInt", "In_NumInt",
     "mu_approx_In", "clear_cache", "Scenario", "DriverResult", "BatchSolver", "solve_scenarios",
-    "MuShardedSolver", "PeerFields", "mu_blocks", "shard_scenarios", "gather_scenario_results", "allgather_columns", "shard_range",
+    "MuShardedSolver", "LayerShardedSolver", "PeerFields", "PeerBuffers", "mu_blocks", "shard_scenarios", "gather_scenario_results", "allgather_columns", "shard_range",
     "SOS_Aer_main_specular", "SOS_Aer_main_lambertian", "SOS_Aer_radiative_forcing", "SOS_Aer_critical_albedo", "critical_albedo_sweep", "EVA", "WILDFIRE", "clear_caches",
     "graphe", "graphe_diffusivity", "graphe_flux", "graphe_heating_rate", "graphe_successive_dif", "graphe_flux_up_down", "successive_diffusivity",
 ]

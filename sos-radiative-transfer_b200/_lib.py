@@ -113,6 +113,8 @@ SIGNATURES = {
     "sos_launch_count": (C.c_longlong, [_vp]),
     "sos_plan_query": (C.c_int, [_vp, C.c_int]),
     "sos_plan_set_columns": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "sos_layer_mailbox_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
+    "sos_plan_set_layers": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sos_state_ratios": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "sos_set_profiling": (C.c_int, [_vp, C.c_int]),
     "sos_get_profile": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), _vp]),

@@ -15,6 +15,8 @@
 // a mu -> 0+ blend that reaches further cannot be finished, and the solve is repeated with every row stored (sos_solve
 // returns SOS_ERR_RETRY after switching the plan over)
 #define SOS_STATUS_STRIP_FALLBACK 0x100u
+// internal status bit: a layer-sharded rank waited more than a few seconds for a peer's flag (layer_shard.cuh)
+#define SOS_STATUS_PEER_TIMEOUT 0x200u
 
 #define SOS_MAX_PHASE 16
 #define SOS_MAX_GROUPS 48
@@ -51,6 +53,8 @@ struct GridDev {
   int widx[4], wns[4], woff[4];
   int first_small;          // first downward column with |mu| < MU_THRESHOLD (M-1 if none)
   int col0, col1;           // mu columns this plan owns (mu-block sharding); [0, N) by default
+  int row0, row1;           // layers this plan owns (layer-block sharding, layer_shard.cuh); [0, L) by default
+  int c_lo, c_hi;           // ... = the scan chunks [c_lo, c_hi); [0, nchunks) by default
 };
 
 // Row-tile layout of the source contraction, rebuilt on the device whenever the set of active

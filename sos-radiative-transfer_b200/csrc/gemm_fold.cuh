@@ -34,6 +34,7 @@ struct FoldParams {
   int split_passes;  // see GemmParams
   int ksplit;        // 0: chosen per launch on the device (1 or 2; J rows zeroed by the caller); 1, or 2: every output tile is computed by two tiles (halves of the k range) that add their partial into a
                      //    zeroed J (exactly two partials per element: order independent) -- launches with fewer tiles than SMs / 2
+  int seg_begin, seg_end;  // row-restricted launch (one single-region group: layer-sharded plans): only the segments [seg_begin, seg_end)
   int L, N, M, Mh, ld;
   double* J;
   const sos_scenario* scen;
@@ -115,8 +116,12 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
   const int last_slabs = (p.M - (ksteps - 1) * BK + 3) / 4;  // k-slabs of the last k-step that hold k < M
   // ksplit == 0: decided per launch from the device-built tile plan -- when the output tiles would leave more than half
   // of the CTAs idle (few scenarios still iterating), every tile is computed as two halves of the k range
-  const int ksplit = p.ksplit > 0 ? p.ksplit : ((2 * plan->n_row_tiles * p.n_col_tiles <= static_cast<int>(gridDim.x) && p.M >= 64) ? 2 : 1);
-  const int n_tiles = plan->n_row_tiles * p.n_col_tiles * ksplit;
+  // row-restricted launch: tiles cover the segments [seg_begin, seg_end) of the (single) group's list
+  const bool restricted = p.seg_begin > 0 || p.seg_end != 0x7fffffff;
+  const int seg_stop = restricted ? min(p.seg_end, plan->group_nactive[0] * p.nseg[plan->group_cls[0]]) : 0;
+  const int n_row_tiles = restricted ? max(0, (seg_stop - p.seg_begin + C::SEGS - 1) / C::SEGS) : plan->n_row_tiles;
+  const int ksplit = p.ksplit > 0 ? p.ksplit : ((2 * n_row_tiles * p.n_col_tiles <= static_cast<int>(gridDim.x) && p.M >= 64) ? 2 : 1);
+  const int n_tiles = n_row_tiles * p.n_col_tiles * ksplit;
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp >= C::CONSUMER_WARPS) {
@@ -179,9 +184,9 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
       const int ks0 = kh * ksteps / ksplit, ks1 = (kh + 1) * ksteps / ksplit;
       const int rt = t2 / p.n_col_tiles;
       const int ct = t2 - rt * p.n_col_tiles;
-      const int g = find_group(plan, rt);
+      const int g = restricted ? 0 : find_group(plan, rt);
       const int cls = plan->group_cls[g];
-      int lt = rt - plan->group_tile_start[g];
+      int lt = restricted ? rt : rt - plan->group_tile_start[g];
       const bool split = p.split_passes && cls == 1;
       const int only_pass = split ? (lt & 1) : 0;
       if (split) lt >>= 1;
@@ -199,7 +204,8 @@ __global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const
           sr.valid = p.seg_valid[1][j];
         }
       } else if (lane < C::SEGS) {
-        sr = seg_lookup_fold(p, cls, plan->group_nactive[g], plan->group_list_off[g], lt * C::SEGS + lane);
+        const int q = (restricted ? p.seg_begin : 0) + lt * C::SEGS + lane;
+        if (!restricted || q < seg_stop) sr = seg_lookup_fold(p, cls, plan->group_nactive[g], plan->group_list_off[g], q);
       }
       const unsigned have = __ballot_sync(0xffffffffu, sr.valid > 0);
       const uint32_t tx = static_cast<uint32_t>(__popc(have)) * (2 * SEG_ROWS * BK * 8) + C::B_BYTES;

@@ -16,6 +16,7 @@
 #include "gemm_f64.cuh"
 #include "gemm_fold.cuh"
 #include "gemm_lowrank.cuh"
+#include "layer_shard.cuh"
 #include "phase.cuh"
 #include "quadrature.cuh"
 #include "sweep.cuh"
@@ -170,6 +171,11 @@ struct sos_plan {
   std::vector<OrderGraph> graphs;
   cudaStream_t cap_stream = nullptr;   // capture needs a non-legacy stream; replays go to the caller's stream
   cudaEvent_t graph_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // layer-block sharding over the GPUs of a node (layer_shard.cuh); n <= 1: off
+  soslayer::LayerPeers layers;
+  double* own_aggD = nullptr;   // the plan's own aggregate tables (d_aggD / d_aggU point into the mailbox while sharded)
+  double* own_aggU = nullptr;
+  int layer_seg_begin = 0, layer_seg_end = 0x7fffffff;  // segments of the rows whose J this rank needs (own rows + halos)
   // optional per-kernel-class timing with CUDA events (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -576,6 +582,11 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   d.first_small = first_small;
   d.col0 = 0;
   d.col1 = N;
+  d.row0 = 0;
+  d.row1 = L;
+  d.c_lo = 0;
+  d.c_hi = nch;
+  std::memset(&p->layers, 0, sizeof(p->layers));
   for (int c = 0; c < 4; ++c) { d.widx[c] = widx[c]; d.wns[c] = wns[c]; d.woff[c] = woff[c]; }
 
   int r = SOS_OK;
@@ -613,6 +624,8 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
   const size_t nagg = static_cast<size_t>(S) * nch * N;
   TRY(dev_alloc(p, &p->d_aggD, nagg));
   TRY(dev_alloc(p, &p->d_aggU, nagg));
+  p->own_aggD = p->d_aggD;
+  p->own_aggU = p->d_aggU;
   TRY(dev_alloc(p, &p->d_carryD, nagg));
   TRY(dev_alloc(p, &p->d_carryU, nagg));
   TRY(dev_alloc(p, &p->d_C, static_cast<size_t>(S) * 2 * N));
@@ -819,6 +832,74 @@ int sos_plan_set_columns(sos_plan* p, int col0, int col1) {
   if (cuts_down || cuts_up) return SOS_ERR_UNSUPPORTED;
   g.col0 = col0;
   g.col1 = col1;
+  return SOS_OK;
+}
+
+int sos_layer_mailbox_bytes(const sos_plan* p, size_t* bytes) {
+  if (!p || !bytes) return SOS_ERR_INVALID;
+  *bytes = soslayer::mailbox_layout(nullptr, p->dev.nchunks, p->dev.N, nullptr);
+  return SOS_OK;
+}
+
+int sos_plan_set_layers(sos_plan* p, int rank, int n_ranks, void* const* mailbox_peers_d, double* const* In_peers_d, int* row0_out,
+                        int* row1_out) {
+  if (!p) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
+  drop_graphs(p);
+  GridDev& g = p->dev;
+  if (n_ranks <= 1) {  // back to the whole grid
+    std::memset(&p->layers, 0, sizeof(p->layers));
+    p->d_aggD = p->own_aggD;
+    p->d_aggU = p->own_aggU;
+    g.row0 = 0; g.row1 = g.L; g.c_lo = 0; g.c_hi = g.nchunks;
+    p->layer_seg_begin = 0; p->layer_seg_end = 0x7fffffff;
+    if (row0_out) *row0_out = 0;
+    if (row1_out) *row1_out = g.L;
+    return SOS_OK;
+  }
+  if (!mailbox_peers_d || !In_peers_d || rank < 0 || rank >= n_ranks || n_ranks > SOS_MAX_PEERS) return SOS_ERR_INVALID;
+  // one scenario, one region, no surface coupling (the single-layer operator of SOS_Aer_I1_In.py:77-130), all columns
+  if (g.S != 1 || g.nreg != 1 || g.surface != SOS_SURFACE_NONE || g.col0 != 0 || g.col1 != g.N) return SOS_ERR_UNSUPPORTED;
+  if (g.nchunks < n_ranks) return SOS_ERR_UNSUPPORTED;
+  for (int r = 0; r < n_ranks; ++r)
+    if (!mailbox_peers_d[r] || !In_peers_d[r] || (reinterpret_cast<uintptr_t>(mailbox_peers_d[r]) & 127)) return SOS_ERR_INVALID;
+  std::vector<int> cstart(g.nchunks + 1);
+  std::vector<double> tau(g.L);
+  SOS_CUDA(cudaMemcpy(cstart.data(), g.chunk_start, sizeof(int) * (g.nchunks + 1), cudaMemcpyDeviceToHost));
+  SOS_CUDA(cudaMemcpy(tau.data(), g.tau, sizeof(double) * g.L, cudaMemcpyDeviceToHost));
+  auto first_chunk = [&](int r) { return static_cast<int>(static_cast<long long>(g.nchunks) * r / n_ranks); };
+  // rows above `a` whose J the sweeps of the block starting at `a` read: the previous row (first trapezoid of the downward
+  // recurrence, Taylor slope of the |mu| < 0.001 columns) and the window tau' >= tau - 5 |mu|, |mu| < 0.01, of
+  // SOS_Aer_In_limit.py:96-107
+  auto halo_above = [&](int a) {
+    if (a == 0) return 0;
+    int h = 1;
+    while (a - h > 0 && tau[a - h] >= tau[a] - 5.0 * SOS_MU_THRESHOLD) ++h;
+    return std::min(a, h + 1);
+  };
+  soslayer::LayerPeers& lp = p->layers;
+  std::memset(&lp, 0, sizeof(lp));
+  lp.rank = rank;
+  lp.n = n_ranks;
+  for (int r = 0; r < n_ranks; ++r) {
+    soslayer::mailbox_layout(mailbox_peers_d[r], g.nchunks, g.N, &lp.box[r]);
+    lp.In[r] = In_peers_d[r];
+  }
+  g.c_lo = first_chunk(rank);
+  g.c_hi = first_chunk(rank + 1);
+  g.row0 = cstart[g.c_lo];
+  g.row1 = cstart[g.c_hi];
+  lp.halo_above = halo_above(g.row0);
+  lp.next_halo_above = rank + 1 < n_ranks ? halo_above(g.row1) : 0;
+  // the chunk-local pass writes, and the carry chain reads, the aggregate tables inside the mailbox (peers write theirs there)
+  p->d_aggD = lp.box[rank].aggD;
+  p->d_aggU = lp.box[rank].aggU;
+  // J is needed on the rows [row0 - halo, row1] (the upward recurrence reads one row below the block); whole 64-row tiles
+  const int tile_segs = p->gemm_bm / sosgemm::SEG_ROWS;
+  p->layer_seg_begin = (g.row0 - lp.halo_above) / sosgemm::SEG_ROWS / tile_segs * tile_segs;
+  p->layer_seg_end = (std::min(g.L, g.row1 + 1) + sosgemm::SEG_ROWS - 1) / sosgemm::SEG_ROWS;
+  if (row0_out) *row0_out = g.row0;
+  if (row1_out) *row1_out = g.row1;
   return SOS_OK;
 }
 
@@ -1303,7 +1384,9 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SOS_CUDA(cudaMemsetAsync(p->d_work_counter, 0, sizeof(int), st));
   const bool full_columns = g.col0 == 0 && g.col1 == g.N;
-  const bool use_fold = p->fold && full_columns && !peers && seg_begin == 0 && seg_end == 0x7fffffff;
+  const bool layered = p->layers.n > 1;
+  if (layered && seg_begin == 0 && seg_end == 0x7fffffff) { seg_begin = p->layer_seg_begin; seg_end = p->layer_seg_end; p->gp.seg_begin = seg_begin; p->gp.seg_end = seg_end; }
+  const bool use_fold = p->fold && full_columns && !peers && (layered || (seg_begin == 0 && seg_end == 0x7fffffff));
   // inside sos_solve with a generated source only the aerosol rows have dense tiles: the kernel then decides per launch,
   // from the device-built tile plan, whether to split k (few scenarios still iterating) -- their J rows start from zero
   const bool dyn_ksplit = use_fold && skip_lowrank && p->fold_ksplit == 1 && !p->split_passes && g.nreg == 3 && g.M >= 64 &&
@@ -1335,6 +1418,8 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     f.n_col_tiles = (g.M + FC::BN - 1) / FC::BN;
     f.split_passes = p->split_passes;
     f.ksplit = dyn_ksplit ? 0 : p->fold_ksplit;
+    f.seg_begin = seg_begin;
+    f.seg_end = seg_end;
     f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
     f.J = J_d;
     f.scen = g.scen;
@@ -1390,16 +1475,32 @@ static sossweep::SrcGen source_gen(const sos_plan* p, int n) {
   return sg;
 }
 
+// layer-sharded plans: one exchange with the peers (layer_shard.cuh) -- stores into peer memory + flags, then the wait
+static int layer_exchange(sos_plan* p, int phase, cudaStream_t st) {
+  static const unsigned long long timeout_ns = static_cast<unsigned long long>(std::max(1, env_int("SOS_B200_PEER_TIMEOUT_MS", 4000))) * 1000000ull;
+  soslayer::layer_push_kernel<<<p->layers.n, soslayer::PUSH_THREADS, 0, st>>>(p->dev, p->layers, phase);
+  int r = launch_check(p, "layer_push_kernel");
+  if (r) return r;
+  soslayer::layer_wait_kernel<<<1, 32, 0, st>>>(p->dev, p->layers, phase, timeout_ns);
+  return launch_check(p, "layer_wait_kernel");
+}
+
 static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st, int gen_order = -1) {
   const GridDev& g = p->dev;
   const sossweep::SrcGen sg = source_gen(p, gen_order);
   NvtxRange nvtx("sos:layer_sweeps");
   ProfSpan span(p, 1, st);
   const int T = sossweep::LOCAL_THREADS;
-  dim3 cgrid((g.M - 1 + T - 1) / T + (g.N - g.M - 1 + T - 1) / T, g.nchunks, g.S);
+  dim3 cgrid((g.M - 1 + T - 1) / T + (g.N - g.M - 1 + T - 1) / T, g.c_hi - g.c_lo, g.S);
+  const bool layered = p->layers.n > 1;
+  if (layered && In_d != p->layers.In[p->layers.rank]) return SOS_ERR_INVALID;  // the neighbours write their halo rows into the registered field
   {
     sossweep::sweep_local_kernel<<<cgrid, T, 0, st>>>(g, sg, J_d, p->d_aggD, p->d_aggU);
     int r = launch_check(p, "sweep_local_kernel");
+    if (r) return r;
+  }
+  if (layered) {  // chunk aggregates -> the ranks that chain through them; wait for the ones this rank chains through
+    int r = layer_exchange(p, 0, st);
     if (r) return r;
   }
   {
@@ -1413,7 +1514,7 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     if ((g.M & 1) && g.col0 == 0 && g.col1 == g.N && I_d) {
       // odd M: every column pair is 16-byte aligned and inside one half -> two columns per thread
       const int T2 = 2 * sossweep::APPLY2_THREADS;
-      dim3 grid2((g.M - 1 + T2 - 1) / T2 + (g.N - g.M - 1 + T2 - 1) / T2, g.nchunks, g.S);
+      dim3 grid2((g.M - 1 + T2 - 1) / T2 + (g.N - g.M - 1 + T2 - 1) / T2, g.c_hi - g.c_lo, g.S);
       sossweep::sweep_apply2_kernel<<<grid2, sossweep::APPLY2_THREADS, 0, st>>>(g, sg, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
     } else {
       sossweep::sweep_apply_kernel<<<cgrid, T, 0, st>>>(g, sg, J_d, In_d, p->d_carryD, p->d_carryU, I_d, saved_d);
@@ -1432,11 +1533,12 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
       if (smem > 200 * 1024) return SOS_ERR_UNSUPPORTED;
       cudaFuncSetAttribute(sossweep::sweep_zone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     }
-    dim3 grid((g.L + sossweep::ZONE_ROWS - 1) / sossweep::ZONE_ROWS, g.S);
+    dim3 grid((g.row1 - g.row0 + sossweep::ZONE_ROWS - 1) / sossweep::ZONE_ROWS, g.S);
     sossweep::sweep_zone_kernel<<<grid, 32 * sossweep::ZONE_ROWS, smem, st>>>(g, sg, J_d, In_d, I_d, saved_d, zone_buf);
     int r = launch_check(p, "sweep_zone_kernel");
     if (r) return r;
   }
+  if (layered) return layer_exchange(p, 1, st);  // halo rows of I_n -> the neighbours, convergence ratios -> everybody
   return SOS_OK;
 }
 
@@ -1571,7 +1673,8 @@ int sos_solve(sos_plan* p, double* I_d, double* In_d, double* J_d, double* order
   int r = sos_reset(p, I_d, stream);
   if (r) return r;
   const size_t field = static_cast<size_t>(g.S) * g.L * g.ld;
-  const bool gen = gen_usable(p) && gen_applies(p);
+  const bool gen = gen_usable(p) && gen_applies(p) && p->layers.n <= 1;
+  if (p->layers.n > 1 && orders_d) return SOS_ERR_UNSUPPORTED;
   if (gen) {
     // projections of the first order onto the molecular factors: what order 2 rebuilds its J from
     dim3 pg((g.L + 7) / 8, g.S);

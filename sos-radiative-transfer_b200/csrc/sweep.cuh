@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(LOCAL_THREADS)
 sweep_local_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, double* __restrict__ aggD, double* __restrict__ aggU) {
   const int s = blockIdx.z;
   if (!g.state[s].active) return;
-  const int c = blockIdx.y;
+  const int c = g.c_lo + blockIdx.y;  // (layer-sharded plans own the chunks [c_lo, c_hi))
   const int L = g.L, M = g.M, ld = g.ld;
   const int nbd = scan_blocks_down(M, LOCAL_THREADS);
   const bool up = static_cast<int>(blockIdx.x) >= nbd;
@@ -641,7 +641,7 @@ sweep_apply_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
                    double* __restrict__ I, double* __restrict__ saved) {
   const int s = blockIdx.z;
   if (!g.state[s].active) return;
-  const int c = blockIdx.y;
+  const int c = g.c_lo + blockIdx.y;  // (layer-sharded plans own the chunks [c_lo, c_hi))
   const int L = g.L, M = g.M, ld = g.ld;
   const int lane = threadIdx.x & 31;
   const int nbd = scan_blocks_down(M, LOCAL_THREADS);
@@ -850,7 +850,7 @@ sweep_apply2_kernel(const GridDev g, const SrcGen sg, const double* __restrict__
   __shared__ double s_tau[APPLY2_STAGE];
   const int s = blockIdx.z;
   if (!g.state[s].active) return;
-  const int c = blockIdx.y;
+  const int c = g.c_lo + blockIdx.y;  // (layer-sharded plans own the chunks [c_lo, c_hi))
   const int L = g.L, M = g.M, N = g.N, ld = g.ld;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nbd = ((M - 1) / 2 + APPLY2_THREADS - 1) / APPLY2_THREADS;
@@ -1128,9 +1128,9 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
                   double* __restrict__ I, double* __restrict__ saved, int zone_buf) {
   extern __shared__ double sm_zone[];  // per warp: zone_buf downward values of columns [zl, M), then ZONE_UP + 4 upward ones
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.y, t = blockIdx.x * ZONE_ROWS + warp;
+  const int s = blockIdx.y, t = g.row0 + blockIdx.x * ZONE_ROWS + warp;  // (layer-sharded plans own the rows [row0, row1))
   const int L = g.L, M = g.M, ld = g.ld;
-  if (t >= L || !g.state[s].active) return;
+  if (t >= g.row1 || !g.state[s].active) return;
   const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
   const size_t fbase = static_cast<size_t>(s) * L * ld;
   const SrcAt src(g, sg, J, s);

@@ -418,6 +418,21 @@ class SosEngine:
         _lib.check(self.lib.sos_plan_set_columns(self._plan, int(col0), int(col1)), "sos_plan_set_columns")
         self.col0, self.col1 = int(col0), int(col1)
 
+    def layer_mailbox_bytes(self) -> int:
+        n = C.c_size_t()
+        _lib.check(self.lib.sos_layer_mailbox_bytes(self._plan, C.byref(n)), "sos_layer_mailbox_bytes")
+        return int(n.value)
+
+    def set_layers(self, rank: int, world: int, mailbox_ptrs=None, In_ptrs=None):
+        """Own only a block of layers (layer-block sharding, see sos_plan_set_layers); returns its rows [row0, row1).
+        mailbox_ptrs / In_ptrs: ctypes arrays of `world` device pointers (every rank's buffers as mapped here)."""
+        r0, r1 = C.c_int(), C.c_int()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_plan_set_layers(self._plan, int(rank), int(world), mailbox_ptrs, In_ptrs, C.byref(r0), C.byref(r1)),
+                       "sos_plan_set_layers")
+        self.row0, self.row1 = int(r0.value), int(r1.value)
+        return self.row0, self.row1
+
     def ratios(self, buf: Optional[torch.Tensor] = None, set: bool = False) -> torch.Tensor:
         """Device tensor (S, 2) of {ratio_toa, ratio_surf}; set=True writes `buf` back into the plan."""
         if buf is None:

@@ -170,6 +170,127 @@ class PeerFields:
         self.local = []
 
 
+class PeerBuffers:
+    """Device buffers of the given sizes on every rank, each mapped into every rank's address space with CUDA IPC.
+    ptrs[b][r] = buffer b of rank r as a device pointer valid in THIS process."""
+
+    def __init__(self, sizes: Sequence[int], device, rank: int, world: int, group=None):
+        import ctypes as C
+        from . import _lib
+        self.lib, self.C = _lib.load(), C
+        self.rank, self.world, self.sizes = rank, world, [int(n) for n in sizes]
+        self.local, handles, self._opened = [], [], []
+        with torch.cuda.device(device):
+            for nbytes in self.sizes:
+                ptr = C.c_void_p()
+                h = C.create_string_buffer(64)
+                _lib.check(self.lib.sos_ipc_alloc(nbytes, C.byref(ptr), h), "sos_ipc_alloc")   # (zero-filled)
+                self.local.append(RawField(ptr.value, nbytes))
+                handles.append(h.raw)
+            everyone = [handles]
+            if world > 1:
+                everyone = [None] * world
+                dist.all_gather_object(everyone, handles, group=group)
+            self.ptrs = []
+            for b in range(len(self.sizes)):
+                row = []
+                for r in range(world):
+                    if r == rank:
+                        row.append(self.local[b].ptr)
+                    else:
+                        ptr = C.c_void_p()
+                        _lib.check(self.lib.sos_ipc_open(everyone[r][b], C.byref(ptr)), "sos_ipc_open")
+                        self._opened.append(ptr.value)
+                        row.append(ptr.value)
+                self.ptrs.append(row)
+
+    def ptr_array(self, b: int):
+        return (self.C.c_void_p * self.world)(*self.ptrs[b])
+
+    def close(self):
+        for p in self._opened:
+            self.lib.sos_ipc_close(self.C.c_void_p(p))
+        self._opened = []
+        for f in self.local:
+            self.lib.sos_ipc_free(self.C.c_void_p(f.ptr))
+        self.local = []
+
+
+class LayerShardedSolver:
+    """Order loop of one large single-layer grid sharded by LAYER blocks (BASELINE configs[3]).
+
+    Rank r owns a contiguous block of scan chunks.  The source contraction is row-local (no communication); per order the
+    ranks exchange the chunk aggregates of the scan and the halo rows next to a block boundary by stores into each other's
+    memory over NVLink, issued from kernels inside the CUDA-graphed order loop of sos_solve (csrc/layer_shard.cuh) -- no NCCL
+    call and no host round trip per order.  The result is bit-identical to the unsharded solve of a plan with the same scan
+    chunks.  NCCL carries only the rendezvous and the final gather of the row blocks of I."""
+
+    def __init__(self, engine, rank: int, world: int, group=None):
+        self.eng, self.rank, self.world, self.group = engine, rank, world, group
+        nfield = engine.S * engine.L * engine.ld * 8
+        self.bufs = PeerBuffers([engine.layer_mailbox_bytes(), nfield], engine.device, rank, world, group)
+        self.In = self.bufs.local[1]
+        row0, row1 = engine.set_layers(rank, world, self.bufs.ptr_array(0), self.bufs.ptr_array(1))
+        rows = [(row0, row1)]
+        if world > 1:
+            rows = [None] * world
+            dist.all_gather_object(rows, (row0, row1), group=group)
+        self.rows = rows
+        self._I = None
+        self._stage = None
+        if world > 1:
+            torch.cuda.synchronize(engine.device)
+            dist.barrier(group=group)      # every rank's mailbox is zeroed and mapped before anybody writes into it
+
+    def solve(self, I1: torch.Tensor, max_orders: int = 10000, gather: bool = True):
+        """I1: the first order on ALL rows (every rank computes it: closed form, SOS_Aer_I1_In.py:13-58).  Returns (I, results);
+        with gather=True every rank ends with the full field, otherwise only its own rows of I are final."""
+        import ctypes as C
+        from . import _lib
+        eng = self.eng
+        if self._I is None:
+            self._I = torch.empty_like(I1)
+            self._J = eng.new_field(zero=True)
+        I, J = self._I, self._J
+        I.copy_(I1)
+        res = (_lib.sos_result * eng.S)()
+        with torch.cuda.device(eng.device):
+            _lib.check(eng.lib.sos_copy_d2d(C.c_void_p(self.In.ptr), C.c_void_p(I1.data_ptr()), self.In.nbytes, eng._stream), "sos_copy_d2d")
+            _lib.check(eng.lib.sos_solve(eng._plan, I.data_ptr(), C.c_void_p(self.In.ptr), J.data_ptr(), None, 0, int(max_orders), 1, res,
+                                         eng._stream), "sos_solve")
+        if gather and self.world > 1:
+            self.gather_rows(I)
+        return I, res
+
+    def gather_rows(self, field: torch.Tensor) -> None:
+        """In place: every rank contributes its own rows of `field` and receives everybody else's."""
+        L, ld = self.eng.L, self.eng.ld
+        width = max(b - a for a, b in self.rows)
+        if self._stage is None:
+            self._stage = (torch.zeros((width, ld), dtype=field.dtype, device=field.device),
+                           torch.empty((self.world, width, ld), dtype=field.dtype, device=field.device))
+        send, recv = self._stage
+        a, b = self.rows[self.rank]
+        f2 = field.view(-1, ld)[:L]
+        send[: b - a].copy_(f2[a:b])
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+        else:   # gloo (CPU tests, or several ranks sharing one GPU): through host memory
+            parts = [torch.empty((width, ld), dtype=field.dtype) for _ in range(self.world)]
+            dist.all_gather(parts, send.cpu(), group=self.group)
+            recv.copy_(torch.stack(parts))
+        for r, (a, b) in enumerate(self.rows):
+            if r != self.rank:
+                f2[a:b].copy_(recv[r, : b - a])
+
+    def close(self):
+        torch.cuda.synchronize(self.eng.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.eng.set_layers(0, 1)
+        self.bufs.close()
+
+
 class MuShardedSolver:
     """Order loop of one large single-layer grid sharded by mu blocks (config 4)."""
 

@@ -47,3 +47,32 @@ def test_mu_sharded_solve_on_two_gpus_equals_unsharded(p2p, ref_general):
         assert rec["reference_contraction"] == "general" and rec["max_rel_dev_vs_unsharded"] == 0.0, rec
     else:
         assert rec["max_rel_dev_vs_unsharded"] < 1e-12, rec
+
+
+@pytest.mark.parametrize("case", [
+    # (layers, angles, tau*, order cap, chunk rows): thick (the widest extrapolation class, no surviving windowed column),
+    # thin (windowed |mu| < 0.01 columns survive: tau-window halos of hundreds of rows across the block boundary)
+    (1500, 256, 6.0, 13, 64),
+    (1200, 512, 0.05, 300, 48),
+])
+def test_layer_sharded_solve_is_bit_identical_to_unsharded(case):
+    """Layer-block sharding (csrc/layer_shard.cuh): two ranks exchange chunk aggregates, halo rows and ratios by stores into
+    each other's memory from inside the CUDA-graphed order loop.  With fewer than two GPUs the two ranks share GPU 0
+    (time-sliced: slow, but the same code path), so the driver's one-GPU run covers it too."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    L, M, tau, cap, chunk = case
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29631 + (L % 7)), os.path.join(ROOT, "tools", "layer_shard_check.py"),
+           "--layers", str(L), "--angles", str(M), "--tau", str(tau), "--orders", str(cap), "--chunk-rows", str(chunk), "--repeat", "1", "--check"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    rec = json.loads(line)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "layer_shard_2rank_L%d_M%d.json" % (L, M)), "w") as f:
+        f.write(line + "\n")
+    assert rec["world"] == 2 and rec["status"] == 0, rec
+    assert rec["orders"] == rec["orders_unsharded"], rec
+    assert rec["bit_identical"] and rec["max_rel_dev_vs_unsharded"] == 0.0, rec
