@@ -211,22 +211,32 @@ def thick_record(args, sos, torch, dist, dev, rank, world, W, steps):
     tau = np.linspace(0, tau_star, L)
     w = sos.extrapolation_width(tau_star, M)
     coef = [sos.ScenarioCoefficients(mu0=mu0, grd_alb=0.0, tauStar_tot=tau_star, coef_atm=alb, extrap_width=(w, w, w))]
-    eng = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE, device=dev)
+    # N > 1: layer blocks (the default) or mu blocks; the sharded plan and its one-GPU reference use the same scan chunks
+    chunk_rows = args.thick_chunk_rows if world > 1 else 0
+    eng = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE, device=dev, chunk_rows=chunk_rows)
     phase = "fwc"
     P, _ = eng.build_phase_matrix(phase)                      # built on the device
     eng.set_phase([P])
     Cc = np.zeros((1, 2, N))
     Cc[0, 0] = alb * sos.phase_P0(phase, M, mu, mu0)
     I1 = eng.first_order(Cc)
-    blocks = sos.mu_blocks(N, M, world, M - w - 5)
-    solver = sos.MuShardedSolver(eng, blocks, rank)
-    peers = sos.PeerFields(eng, rank, world) if world > 1 else None
+    layered = world > 1 and args.thick_sharding == "layers"
+    solver = peers = None
+    if layered:
+        solver = sos.LayerShardedSolver(eng, rank, world)
+    elif world > 1:
+        blocks = sos.mu_blocks(N, M, world, M - w - 5)
+        solver = sos.MuShardedSolver(eng, blocks, rank)
+        peers = sos.PeerFields(eng, rank, world)
 
     def step():
         if world == 1:
             r = eng.solve(I1, max_orders=args.thick_orders, poll_every=8)
             return int(r.n_orders[0]), int(r.status[0])
-        I, res = solver.solve_p2p(I1, peers, max_orders=args.thick_orders)
+        if layered:
+            I, res = solver.solve(I1, max_orders=args.thick_orders)   # (incl. the final gather of the row blocks of I)
+        else:
+            I, res = solver.solve_p2p(I1, peers, max_orders=args.thick_orders)
         return int(res[0].n_orders), int(res[0].status)
 
     for _ in range(W):
@@ -253,10 +263,20 @@ def thick_record(args, sos, torch, dist, dev, rank, world, W, steps):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    # the same solve unsharded on one GPU (rank 0), for the speed-up: a fresh engine with the folded contraction
+    # the same solve unsharded on one GPU (rank 0), for the speed-up: a fresh engine with the folded contraction and the
+    # library's own choice of scan chunks (its best one-GPU configuration)
     ms1 = None
+    sharded_I = None
     if world > 1:
         if rank == 0:
+            if layered:
+                sharded_I = solver._I.clone()   # (the gathered field of the last timed solve)
+                # ... and, for the parity statement, the unsharded solve of a plan with the sharded plan's chunks: bit-identical
+                chk = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE, device=dev, chunk_rows=chunk_rows)
+                chk.set_phase([P])
+                rc = chk.solve(chk.first_order(Cc), max_orders=args.thick_orders, poll_every=8)
+                bit_identical = bool(torch.equal(rc.I.view(-1, chk.ld)[:L, :N], sharded_I.view(-1, eng.ld)[:L, :N]))
+                chk.close()
             ref = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE, device=dev)
             ref.set_phase([P])
             J1 = ref.first_order(Cc)
@@ -276,6 +296,8 @@ def thick_record(args, sos, torch, dist, dev, rank, world, W, steps):
         dist.barrier()
         peers.close()
     eng_folded = bool(eng.folded)
+    if layered:
+        solver.close()
     eng.close()
     if rank != 0:
         return None
@@ -285,13 +307,18 @@ def thick_record(args, sos, torch, dist, dev, rank, world, W, steps):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "thick FWC cloud layer (BASELINE configs[3]): one 10000x1024 grid, tau*=30, omega=0.9, "
                                "to In/I<1e-4", "orders": n, "status": status, "ms_per_order": ms / max(n - 1, 1),
-                   "sharding": "none" if world == 1 else "mu blocks of %d columns, contraction reads peer blocks by TMA over NVLink" % (N // world),
-                   "contraction": "folded" if (eng_folded and world == 1) else "general",
+                   "sharding": "none" if world == 1 else (
+                       "layer blocks of %d rows; chunk aggregates, halo rows and ratios exchanged by peer-memory stores + flags inside the "
+                       "graphed order loop (no NCCL on the data path); %d-row scan chunks" % (L // world, chunk_rows) if layered else
+                       "mu blocks of %d columns, contraction reads peer blocks by TMA over NVLink" % (N // world)),
+                   "contraction": "folded" if (eng_folded and (world == 1 or layered)) else "general",
                    "l2": "working set 4 x 82 MB fields + operand > 126 MB L2"},
         "clocks": clocks}
     if ms1 is not None:
         rec["one_gpu_ms"] = ms1
         rec["speedup_vs_1gpu"] = ms1 / ms
+    if layered:
+        rec["bit_identical_to_unsharded_same_chunks"] = bit_identical
     return rec
 
 
@@ -332,6 +359,8 @@ def main():
     ap.add_argument("--workload", default="sweep", choices=["sweep", "thick"],
                     help="sweep (default): BASELINE configs[4] batch; thick: configs[3], one 10000x1024 grid, mu-sharded for N>1")
     ap.add_argument("--thick-orders", type=int, default=300, help="order cap of the thick workload")
+    ap.add_argument("--thick-sharding", default="layers", choices=["layers", "mu"], help="N > 1: how the one large grid is split over the GPUs")
+    ap.add_argument("--thick-chunk-rows", type=int, default=64, help="N > 1, layer blocks: rows per scan chunk of the sharded plan")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false", help="N > 1: skip the mu-sharded thick-cloud record")
     ap.add_argument("--full-sweep", type=int, default=9984, help="solves of the full configs[4] sweep reported as full_sweep (0: skip)")
     args = ap.parse_args()
@@ -589,7 +618,8 @@ def main():
             if rec is not None:
                 secondary = {"workload": rec["config"]["workload"], "scaling": "strong", "ms": rec["ms_per_step"], "orders": rec["config"]["orders"],
                              "updates_per_s": rec["value"], "one_gpu_ms": rec.get("one_gpu_ms"), "speedup_vs_1gpu": rec.get("speedup_vs_1gpu"),
-                             "sharding": rec["config"]["sharding"], "status": rec["config"]["status"]}
+                             "sharding": rec["config"]["sharding"], "status": rec["config"]["status"],
+                             "bit_identical_to_unsharded_same_chunks": rec.get("bit_identical_to_unsharded_same_chunks")}
         except Exception as e:   # the headline line must not depend on the secondary workload
             secondary = {"workload": "thick FWC cloud layer (BASELINE configs[3])", "error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 

@@ -15,10 +15,10 @@
 //
 // Both exchanges are plain stores into peer memory (CUDA IPC mappings over NVLink / NVSwitch) issued by the kernels below,
 // followed by a system-scope fence and one flag per (phase, sender) in the receiver's mailbox; the receiver spins on its own
-// memory.  No NCCL call and no host round trip per order: 16 KB-class messages are latency, not bandwidth.  Flags carry a
-// monotonically increasing epoch kept on the device, so the kernels can be replayed from a CUDA graph; once the solve has
-// converged (identical state on every rank: the ratios are the same bits everywhere) both kernels return at once, so ranks
-// may run ahead by different numbers of no-op orders without ever waiting for each other.
+// memory (inside the kernel that consumes the data).  No NCCL call and no host round trip per order: 16 KB-class messages
+// are latency, not bandwidth.  Flags carry a monotonically increasing epoch kept on the device, so the kernels can be replayed
+// from a CUDA graph; once the solve has converged (identical state on every rank: the ratios are the same bits everywhere)
+// every kernel returns at once, so ranks may run ahead by different numbers of no-op orders without waiting for each other.
 #pragma once
 #include "common.cuh"
 
@@ -63,7 +63,21 @@ __device__ __forceinline__ void copy16(double* dst, const double* src, size_t n_
   // both sides are 16-byte aligned (rows of ld doubles, ld even; aggregate rows of N = 2M doubles)
   double2* d = reinterpret_cast<double2*>(dst);
   const double2* s = reinterpret_cast<const double2*>(src);
-  for (size_t i = threadIdx.x; i < n_doubles / 2; i += blockDim.x) d[i] = s[i];
+  // eight independent 16-byte loads per thread in flight, then the (posted) stores: the copy is latency, not bandwidth
+  const size_t n = n_doubles / 2, step = static_cast<size_t>(blockDim.x) * 8;
+  for (size_t i0 = threadIdx.x; i0 < n; i0 += step) {
+    double2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const size_t i = i0 + static_cast<size_t>(u) * blockDim.x;
+      if (i < n) v[u] = s[i];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const size_t i = i0 + static_cast<size_t>(u) * blockDim.x;
+      if (i < n) d[i] = v[u];
+    }
+  }
 }
 
 // One CTA per receiving rank q.  phase 0 (after the chunk-local pass): this rank's chunk aggregates.  phase 1 (after the
@@ -73,7 +87,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) layer_push_kernel(const GridDev 
   const int q = blockIdx.x, me = lp.rank;
   const Mailbox& mine = lp.box[me];
   const Mailbox& theirs = lp.box[q];
-  const unsigned long long e = mine.epoch[phase] + 1;  // (advanced by layer_wait_kernel, later on this stream)
+  const unsigned long long e = mine.epoch[phase] + 1;  // (advanced by order_end_kernel, later on this stream)
   const int N = g.N;
   if (phase == 0) {
     if (q != me) {
@@ -96,51 +110,25 @@ __global__ void __launch_bounds__(PUSH_THREADS) layer_push_kernel(const GridDev 
     }
   }
   if (q == me) return;
-  __threadfence_system();  // every thread: its stores into the peer are visible system-wide before the flag
   __syncthreads();
   if (threadIdx.x == 0) {
-    *reinterpret_cast<volatile unsigned long long*>(theirs.flags + phase * SOS_MAX_PEERS + me) = e;
+    // the barrier orders the CTA's stores before this thread; its system-scope fence (cumulative) then orders them before the flag
     __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(theirs.flags + phase * SOS_MAX_PEERS + me) = e;
   }
 }
 
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// One warp: lane q waits until rank q's flag of this phase has reached the next epoch, then the epoch advances.  After
-// phase 1 the two ratios that arrived become this rank's convergence state.  A peer that does not show up within
-// `timeout_ns` (a crashed rank) raises a status bit instead of hanging the GPU.
-__global__ void layer_wait_kernel(const GridDev g, const LayerPeers lp, int phase, unsigned long long timeout_ns) {
-  if (!g.state[0].active) return;
-  const int lane = threadIdx.x, me = lp.rank;
-  const Mailbox& mine = lp.box[me];
-  const unsigned long long e = mine.epoch[phase] + 1;
-  bool late = false;
-  if (lane < lp.n && lane != me) {
-    const volatile unsigned long long* f = mine.flags + phase * SOS_MAX_PEERS + lane;
-    const unsigned long long t0 = global_timer_ns();
-    while (*f < e) {
-      if (global_timer_ns() - t0 > timeout_ns) { late = true; break; }
-      __nanosleep(100);
-    }
-  }
-  __threadfence_system();
-  late = __any_sync(0xffffffffu, late);
-  if (lane == 0) {
-    if (late) {  // give up: every later kernel of the solve returns at once, the host sees "nothing active" and the status bit
-      atomicOr(&g.state[0].status, SOS_STATUS_PEER_TIMEOUT | SOS_STATUS_NONFINITE);
-      g.state[0].active = 0;
-      *g.n_active = 0;
-    }
-    if (phase == 1) {
-      g.state[0].ratio_toa = *reinterpret_cast<volatile double*>(mine.ratios);
-      g.state[0].ratio_surf = *reinterpret_cast<volatile double*>(mine.ratios + 1);
-    }
-    mine.epoch[phase] = e;
-  }
+// The waits live in the kernels that consume what arrived: sweep_carry_cols_kernel (sweep.cuh) waits for the peers'
+// aggregates (phase 0), order_end_kernel (sos_abi.cu) for the halo rows and ratios (phase 1); the latter then takes the two
+// ratios over as this rank's convergence state and advances both epochs (one exchange of each phase per order).
+inline LayerWait wait_for(const LayerPeers& lp, int phase, unsigned long long timeout_ns) {
+  LayerWait w;
+  w.flags = lp.n > 1 ? lp.box[lp.rank].flags + phase * SOS_MAX_PEERS : nullptr;
+  w.epoch = lp.n > 1 ? lp.box[lp.rank].epoch + phase : nullptr;
+  w.n = lp.n;
+  w.me = lp.rank;
+  w.timeout_ns = timeout_ns;
+  return w;
 }
 
 }  // namespace soslayer

@@ -254,6 +254,35 @@ __global__ void plan_tiles_kernel(sosgemm::GroupTable gt, const int* members, co
   sosgemm::plan_tiles_block(gt, members, state, active_list, plan, nseg0, nseg1, segs_per_tile, split_passes);
 }
 
+// End of one scattering order in ONE launch: convergence bookkeeping (SOS_Aer_main_specular.py:309) + the tile plan of the
+// next contraction.  Layer-sharded plans first wait here for the peers' halo rows and ratios (layer_shard.cuh), take the two
+// ratios that arrived over as their own and advance the exchange epochs.
+__global__ void __launch_bounds__(256)
+order_end_kernel(const GridDev g, int order_arg, int* order_counter, sosgemm::GroupTable gt, const int* members, int* active_list,
+                 TilePlan* plan, int nseg0, int nseg1, int segs_per_tile, int split_passes, const LayerWait lw,
+                 const double* ratios_in, unsigned long long* epochs) {
+  if (lw.flags) {
+    if (g.state[0].active && threadIdx.x < 32) {
+      const bool late = layer_wait_warp(lw);
+      if (threadIdx.x == 0) {
+        if (late) {  // give up: every later kernel of the solve returns at once; the host sees "nothing active" and the status bit
+          atomicOr(&g.state[0].status, SOS_STATUS_PEER_TIMEOUT | SOS_STATUS_NONFINITE);
+          g.state[0].active = 0;
+        } else {
+          g.state[0].ratio_toa = *reinterpret_cast<const volatile double*>(ratios_in);
+          g.state[0].ratio_surf = *reinterpret_cast<const volatile double*>(ratios_in + 1);
+        }
+        epochs[0] += 1;
+        epochs[1] += 1;
+      }
+    }
+    __syncthreads();
+  }
+  sossweep::converge_block(g, order_arg, order_counter);
+  __syncthreads();
+  sosgemm::plan_tiles_block(gt, members, g.state, active_list, plan, nseg0, nseg1, segs_per_tile, split_passes);
+}
+
 // zero the aerosol rows of J of every scenario (split class-1 tiles add their two partials into them)
 __global__ void zero_rows_kernel(double* J, int ld, int L, int r0, int r1, int N) {
   const int s = blockIdx.z;
@@ -1475,17 +1504,39 @@ static sossweep::SrcGen source_gen(const sos_plan* p, int n) {
   return sg;
 }
 
-// layer-sharded plans: one exchange with the peers (layer_shard.cuh) -- stores into peer memory + flags, then the wait
-static int layer_exchange(sos_plan* p, int phase, cudaStream_t st) {
-  static const unsigned long long timeout_ns = static_cast<unsigned long long>(std::max(1, env_int("SOS_B200_PEER_TIMEOUT_MS", 4000))) * 1000000ull;
+// layer-sharded plans: this rank's half of an exchange with the peers (layer_shard.cuh) -- stores into peer memory + flags; the
+// kernel that consumes what the peers send waits for their flags (phase 0: the carry chain, phase 1: order_end_kernel)
+static int layer_push(sos_plan* p, int phase, cudaStream_t st) {
   soslayer::layer_push_kernel<<<p->layers.n, soslayer::PUSH_THREADS, 0, st>>>(p->dev, p->layers, phase);
-  int r = launch_check(p, "layer_push_kernel");
-  if (r) return r;
-  soslayer::layer_wait_kernel<<<1, 32, 0, st>>>(p->dev, p->layers, phase, timeout_ns);
-  return launch_check(p, "layer_wait_kernel");
+  return launch_check(p, "layer_push_kernel");
+}
+static unsigned long long peer_timeout_ns() {
+  // (0: do not wait at all -- one rank profiled alone, its results are meaningless)
+  static const unsigned long long ns = static_cast<unsigned long long>(std::max(0, env_int("SOS_B200_PEER_TIMEOUT_MS", 4000))) * 1000000ull;
+  return ns;
 }
 
-static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st, int gen_order = -1) {
+// convergence bookkeeping of the order just accumulated + tile plan of the next contraction (one launch)
+static int order_end(sos_plan* p, int order_arg, cudaStream_t st) {
+  const bool pm = p->fold && p->d_members_premix != nullptr;  // fold-mode tables (build_fold_tables)
+  const bool layered = p->layers.n > 1;
+  LayerWait lw;
+  std::memset(&lw, 0, sizeof(lw));
+  const double* ratios = nullptr;
+  unsigned long long* epochs = nullptr;
+  if (layered) {
+    lw = soslayer::wait_for(p->layers, 1, peer_timeout_ns());
+    ratios = p->layers.box[p->layers.rank].ratios;
+    epochs = p->layers.box[p->layers.rank].epoch;
+  }
+  order_end_kernel<<<1, 256, 0, st>>>(p->dev, order_arg, p->d_order, pm ? p->groups_premix : p->groups, pm ? p->d_members_premix : p->d_members,
+                                      p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS, p->split_passes, lw,
+                                      ratios, epochs);
+  return launch_check(p, "order_end_kernel");
+}
+
+static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d, double* saved_d, cudaStream_t st, int gen_order = -1,
+                       bool in_order_loop = false) {
   const GridDev& g = p->dev;
   const sossweep::SrcGen sg = source_gen(p, gen_order);
   NvtxRange nvtx("sos:layer_sweeps");
@@ -1493,17 +1544,30 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
   const int T = sossweep::LOCAL_THREADS;
   dim3 cgrid((g.M - 1 + T - 1) / T + (g.N - g.M - 1 + T - 1) / T, g.c_hi - g.c_lo, g.S);
   const bool layered = p->layers.n > 1;
+  if (layered && !in_order_loop) return SOS_ERR_UNSUPPORTED;  // sharded plans run whole orders only (sos_solve): the exchange ends in order_end_kernel
   if (layered && In_d != p->layers.In[p->layers.rank]) return SOS_ERR_INVALID;  // the neighbours write their halo rows into the registered field
   {
     sossweep::sweep_local_kernel<<<cgrid, T, 0, st>>>(g, sg, J_d, p->d_aggD, p->d_aggU);
     int r = launch_check(p, "sweep_local_kernel");
     if (r) return r;
   }
-  if (layered) {  // chunk aggregates -> the ranks that chain through them; wait for the ones this rank chains through
-    int r = layer_exchange(p, 0, st);
+  if (layered) {  // chunk aggregates -> the ranks that chain through them
+    int r = layer_push(p, 0, st);
     if (r) return r;
   }
-  {
+  if (g.nreg == 1 && g.surface == SOS_SURFACE_NONE) {
+    // nothing couples the columns: one thread per column, small CTAs all over the chip (sharded plans wait for the peers' aggregates here)
+    LayerWait lw;
+    std::memset(&lw, 0, sizeof(lw));
+    if (layered) lw = soslayer::wait_for(p->layers, 0, peer_timeout_ns());
+    const int T3 = sossweep::CARRY_COLS;
+    const size_t smem = 2 * static_cast<size_t>(g.nchunks + 1) * sizeof(double);
+    if (smem > 30 * 1024) return SOS_ERR_UNSUPPORTED;
+    sossweep::sweep_carry_cols_kernel<<<dim3((g.N + T3 - 1) / T3, g.S), T3 * sossweep::CARRY_GROUPS, smem, st>>>(g, p->d_aggD, p->d_aggU, p->d_carryD,
+                                                                                                           p->d_carryU, lw);
+    int r = launch_check(p, "sweep_carry_cols_kernel");
+    if (r) return r;
+  } else {
     const size_t smem = (g.N + 32) * sizeof(double);
     sossweep::sweep_carry_kernel<<<g.S, sossweep::CARRY_THREADS, smem, st>>>(g, sg, J_d, p->d_aggD, p->d_aggU, p->d_carryD, p->d_carryU);
     int r = launch_check(p, "sweep_carry_kernel");
@@ -1538,7 +1602,7 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     int r = launch_check(p, "sweep_zone_kernel");
     if (r) return r;
   }
-  if (layered) return layer_exchange(p, 1, st);  // halo rows of I_n -> the neighbours, convergence ratios -> everybody
+  if (layered) return layer_push(p, 1, st);  // halo rows of I_n -> the neighbours, convergence ratios -> everybody
   return SOS_OK;
 }
 
@@ -1607,13 +1671,10 @@ static int order_body(sos_plan* p, double* I_d, double* In_d, double* J_d, doubl
                       bool device_order) {
   int rc = source_impl(p, In_d, J_d, 0, 0x7fffffff, st, nullptr, 0, nullptr, gen);
   if (rc) return rc;
-  rc = sweeps_impl(p, J_d, In_d, I_d, saved, st, gen ? n : -1);
+  rc = sweeps_impl(p, J_d, In_d, I_d, saved, st, gen ? n : -1, true);
   if (rc) return rc;
   // (inside a graph the order number comes from the device-side counter: replays cannot change kernel arguments)
-  sossweep::converge_kernel<<<1, 256, 0, st>>>(p->dev, device_order ? -1 : n, p->d_order);
-  rc = launch_check(p, "converge_kernel");
-  if (rc) return rc;
-  return plan_tiles(p, st);
+  return order_end(p, device_order ? -1 : n, st);
 }
 
 // The order loop is launch-latency bound for small batches (a single default-grid solve: ~45 us of kernels per order

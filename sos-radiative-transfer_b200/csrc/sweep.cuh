@@ -616,6 +616,112 @@ sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
   }
 }
 
+// The carry chain of a single-region grid without surface coupling (the single-layer operator In_NumInt,
+// SOS_Aer_I1_In.py:77-130): no row-level work couples the columns, so every column chains on its own.  With many chunks
+// (one large grid: 10 000 layers = hundreds of chunks) a serial chain per column is the critical path of the sweeps, so the
+// chain itself is a two-level scan: a CTA owns 32 columns, thread (g, col) owns a group of consecutive chunks of its
+// column (in chain order: top-down for the downward half, bottom-up for the upward one).  It composes its group into one
+// affine map carry_out = B + P carry_in (all loads of the group in flight at once), the 32 maps of a column are chained
+// through shared memory by one thread (32 FMAs), and every thread re-chains its group from the true incoming carry.  A
+// fixed order of operations: deterministic, and the same for sharded and unsharded plans.  Layer-sharded plans wait
+// here for the peers' aggregates (layer_shard.cuh) -- every CTA looks at the flags itself.
+constexpr int CARRY_COLS = 32;     // columns per CTA (one 256-byte line of an aggregate row)
+constexpr int CARRY_GROUPS = 32;   // chunk groups per column
+__global__ void __launch_bounds__(CARRY_COLS * CARRY_GROUPS)
+sweep_carry_cols_kernel(const GridDev g, const double* __restrict__ aggD, const double* __restrict__ aggU,
+                        double* __restrict__ carryD, double* __restrict__ carryU, const LayerWait lw) {
+  extern __shared__ double sm_tb[];  // [nch + 1] tau at the last row before each chunk (down), [nch + 1] at its first row (up)
+  __shared__ double sP[CARRY_GROUPS][CARRY_COLS + 1], sB[CARRY_GROUPS][CARRY_COLS + 1];
+  const int s = blockIdx.y;
+  if (!g.state[s].active) return;
+  const int L = g.L, M = g.M, N = g.N, nch = g.nchunks;
+  const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
+  double* td = sm_tb;
+  double* tu = sm_tb + nch + 1;
+  for (int c = threadIdx.x; c <= nch; c += blockDim.x) {
+    const int t0 = g.chunk_start[c];
+    td[c] = tau[t0 > 0 ? t0 - 1 : 0];
+    tu[c] = tau[t0 < L ? t0 : L - 1];
+  }
+  if (lw.flags && threadIdx.x < 32) {
+    if (layer_wait_warp(lw) && threadIdx.x == 0) {
+      atomicOr(&g.state[s].status, SOS_STATUS_PEER_TIMEOUT | SOS_STATUS_NONFINITE);
+      g.state[s].active = 0;
+    }
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & (CARRY_COLS - 1), ty = threadIdx.x / CARRY_COLS;
+  const int m = blockIdx.x * CARRY_COLS + tx;
+  const bool up = m > M;
+  // windowed / Taylor columns are row-local (sweep_zone_kernel); mu = 0 has no recurrence
+  const bool live = m < N && m >= g.col0 && m < g.col1 && m != M - 1 && m != M && (up || fabs(g.mu[m]) >= SOS_MU_THRESHOLD);
+  const double imu = live ? 1.0 / g.mu[m] : 0.0;
+  const double* __restrict__ agg = up ? aggU : aggD;
+  double* __restrict__ carry = up ? carryU : carryD;
+  const size_t base = static_cast<size_t>(s) * nch * N + (live ? m : 0);
+  const int k = (nch + CARRY_GROUPS - 1) / CARRY_GROUPS;
+  const int j0 = ty * k, j1 = min(nch, j0 + k);   // this thread's positions in chain order
+  // chunk at chain position j, and the attenuation of a carry across it
+  auto chunk_of = [&](int j) { return up ? nch - 1 - j : j; };
+  auto decay = [&](int c) -> double {
+    if (up) return exp(-(tu[c + 1] - tu[c]) * imu);
+    return c > 0 ? exp((td[c + 1] - td[c]) * imu) : 0.0;  // (nothing enters the first chunk from above)
+  };
+  double P = 1.0, B = 0.0;
+  if (live) {
+    for (int jb = j0; jb < j1; jb += 8) {
+      double ag[8], ex[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = jb + u;
+        ag[u] = j < j1 ? agg[base + static_cast<size_t>(chunk_of(j)) * N] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ex[u] = (jb + u < j1) ? decay(chunk_of(jb + u)) : 1.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (jb + u < j1) {
+          B = fma(B, ex[u], ag[u]);
+          P *= ex[u];
+        }
+      }
+    }
+  }
+  sP[ty][tx] = P;
+  sB[ty][tx] = B;
+  __syncthreads();
+  if (ty == 0) {
+    // incoming carry of every group of this column (nothing enters the chain: TOA above, no surface coupling below)
+    double cin = 0.0;
+#pragma unroll 8
+    for (int q = 0; q < CARRY_GROUPS; ++q) {
+      const double p = sP[q][tx], b = sB[q][tx];
+      sB[q][tx] = cin;
+      cin = fma(cin, p, b);
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  double cc = sB[ty][tx];
+  for (int jb = j0; jb < j1; jb += 8) {
+    double ag[8], ex[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = jb + u;
+      ag[u] = j < j1 ? agg[base + static_cast<size_t>(chunk_of(j)) * N] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ex[u] = (jb + u < j1) ? decay(chunk_of(jb + u)) : 1.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (jb + u < j1) {
+        carry[base + static_cast<size_t>(chunk_of(jb + u)) * N] = cc;  // value entering the chunk (down: at the row above it, up: at the row below it)
+        cc = fma(cc, ex[u], ag[u]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // 3. apply the carries (chunk x column threads) and finish the mu -> 0 zone (row CTAs)
 // ------------------------------------------------------------------------------------------
@@ -1330,7 +1436,8 @@ __device__ __forceinline__ void build_active_list(const GridDev& g) {
   if (lane == 0) *g.n_active = base;
 }
 
-__global__ void converge_kernel(const GridDev g, int order_arg, int* order_counter) {
+// (a device function: the order loop runs it inside order_end_kernel, sos_abi.cu, together with the tile plan)
+__device__ __forceinline__ void converge_block(const GridDev& g, int order_arg, int* order_counter) {
   __shared__ int order_s;
   if (threadIdx.x == 0) {
     // order_arg < 0: take the order number from the device-side counter (CUDA-graph replays cannot
@@ -1351,6 +1458,8 @@ __global__ void converge_kernel(const GridDev g, int order_arg, int* order_count
   __syncthreads();
   build_active_list(g);
 }
+
+__global__ void converge_kernel(const GridDev g, int order_arg, int* order_counter) { converge_block(g, order_arg, order_counter); }
 
 // ratios with I_n := 1 (the reference initialises In = ones before the loop, :306-309)
 __global__ void reset_kernel(const GridDev g, const double* __restrict__ I1, int* order_counter) {

@@ -225,12 +225,19 @@ class LayerShardedSolver:
     call and no host round trip per order.  The result is bit-identical to the unsharded solve of a plan with the same scan
     chunks.  NCCL carries only the rendezvous and the final gather of the row blocks of I."""
 
-    def __init__(self, engine, rank: int, world: int, group=None):
+    def __init__(self, engine, rank: int, world: int, group=None, emulate=None):
+        """emulate=(rank, world): ONE process plays one rank of a larger job with its own buffers standing in for the peers'
+        (profiling a rank's kernels under ncu with SOS_B200_PEER_TIMEOUT_MS=0; the numbers it computes are meaningless)."""
         self.eng, self.rank, self.world, self.group = engine, rank, world, group
         nfield = engine.S * engine.L * engine.ld * 8
         self.bufs = PeerBuffers([engine.layer_mailbox_bytes(), nfield], engine.device, rank, world, group)
         self.In = self.bufs.local[1]
-        row0, row1 = engine.set_layers(rank, world, self.bufs.ptr_array(0), self.bufs.ptr_array(1))
+        if emulate is not None:
+            import ctypes as C
+            er, ew = emulate
+            row0, row1 = engine.set_layers(er, ew, (C.c_void_p * ew)(*[self.bufs.local[0].ptr] * ew), (C.c_void_p * ew)(*[self.In.ptr] * ew))
+        else:
+            row0, row1 = engine.set_layers(rank, world, self.bufs.ptr_array(0), self.bufs.ptr_array(1))
         rows = [(row0, row1)]
         if world > 1:
             rows = [None] * world

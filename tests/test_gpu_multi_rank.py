@@ -52,7 +52,7 @@ def test_mu_sharded_solve_on_two_gpus_equals_unsharded(p2p, ref_general):
 @pytest.mark.parametrize("case", [
     # (layers, angles, tau*, order cap, chunk rows): thick (the widest extrapolation class, no surviving windowed column),
     # thin (windowed |mu| < 0.01 columns survive: tau-window halos of hundreds of rows across the block boundary)
-    (1500, 256, 6.0, 13, 64),
+    (1500, 256, 6.0, 300, 64),
     (1200, 512, 0.05, 300, 48),
 ])
 def test_layer_sharded_solve_is_bit_identical_to_unsharded(case):

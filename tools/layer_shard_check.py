@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=0, help="rows per scan chunk (0: the library's choice); the unsharded reference uses the same")
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--emulate", default="", help="R/W: one process runs the kernels of rank R of W alone (set SOS_B200_PEER_TIMEOUT_MS=0); for ncu")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -59,7 +60,7 @@ def main():
     eng = sos.SosEngine(mu, tau[None], coef, [0, L], sos._lib.SURFACE_NONE, device=dev, chunk_rows=args.chunk_rows)
     eng.set_phase([P])
     I1 = eng.first_order(Cc)
-    solver = sos.LayerShardedSolver(eng, rank, world)
+    solver = sos.LayerShardedSolver(eng, rank, world, emulate=tuple(int(x) for x in args.emulate.split("/")) if args.emulate else None)
 
     for _ in range(2):
         solver.solve(I1, max_orders=args.orders)
