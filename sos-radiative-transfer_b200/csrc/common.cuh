@@ -57,36 +57,10 @@ struct GridDev {
   int c_lo, c_hi;           // ... = the scan chunks [c_lo, c_hi); [0, nchunks) by default
 };
 
-// Layer-sharded plans (layer_shard.cuh): what a kernel needs to wait for the peers' flags of one exchange phase.
-// flags == nullptr: nothing to wait for.
-struct LayerWait {
-  const unsigned long long* flags;  // [SOS_MAX_PEERS] this rank's flags of the phase, written by the peers
-  const unsigned long long* epoch;  // [1] exchanges of the phase completed so far; the peers' flags must reach epoch + 1
-  int n, me;
-  unsigned long long timeout_ns;    // 0: do not wait (one rank profiled alone)
-};
-
 __device__ __forceinline__ unsigned long long sos_global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
-}
-
-// called by one full warp; returns true (in every lane) if a peer did not show up in time
-__device__ __forceinline__ bool layer_wait_warp(const LayerWait& w) {
-  const int lane = threadIdx.x & 31;
-  bool late = false;
-  if (w.flags && lane < w.n && lane != w.me && w.timeout_ns > 0) {
-    const unsigned long long e = *w.epoch + 1;
-    const volatile unsigned long long* f = w.flags + lane;
-    const unsigned long long t0 = sos_global_timer_ns();
-    while (*f < e) {
-      if (sos_global_timer_ns() - t0 > w.timeout_ns) { late = true; break; }
-      __nanosleep(64);
-    }
-  }
-  __threadfence_system();
-  return __any_sync(0xffffffffu, late);
 }
 
 // Row-tile layout of the source contraction, rebuilt on the device whenever the set of active

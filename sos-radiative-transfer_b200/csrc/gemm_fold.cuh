@@ -40,8 +40,12 @@ struct FoldParams {
   const sos_scenario* scen;
 };
 
-struct FoldCfg {
-  static constexpr int WM = 2, WN = 4, MB = 4, NB = 4;
+// MB_ = 8-row blocks per consumer warp: 4 -> 64-row tiles (the default), 3 -> 48-row tiles.  One tile per SM is ~70 us of DMMA
+// work at M = 512, so a launch with few tiles (one large grid, or a layer block of it) is quantised in whole tiles per SM:
+// the host picks the shape with the fewer (waves x rows per tile), see source_impl.
+template <int MB_>
+struct FoldCfgT {
+  static constexpr int WM = 2, WN = 4, MB = MB_, NB = 4;
   static constexpr int NST = 4;
   static constexpr int BM = 8 * MB * WM;    // 64 rows
   static constexpr int BN = 8 * NB * WN;    // 128 folded columns j (-> J columns j and N-1-j)
@@ -61,6 +65,7 @@ struct FoldCfg {
   static constexpr int INFO_SLOTS = NST + 2;
   static constexpr int SMEM = NST * STAGE_BYTES + 1024 + 3 * NST * 8 + NST * 8 + INFO_SLOTS * static_cast<int>(sizeof(TileInfo<SEGS>));
 };
+using FoldCfg = FoldCfgT<4>;
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -84,9 +89,9 @@ __device__ __forceinline__ SegRef seg_lookup_fold(const FoldParams& p, int cls, 
 // XFORM: the three otherwise idle warps of the producer warpgroup turn every landed stage from (x, mirror x) into
 // (u, v) in place, once per CTA, so that the consumer warps load u and v directly (otherwise each of the WN consumer
 // warps of a row block forms them again while loading its fragments: one DADD per 4 DMMAs on the same FP64 pipe).
-template <bool XFORM>
-__global__ void __launch_bounds__(FoldCfg::THREADS, 1) jn_gemm_fold_kernel(const __grid_constant__ FoldParams p) {
-  using C = FoldCfg;
+template <bool XFORM, int MBT = 4>
+__global__ void __launch_bounds__(FoldCfgT<MBT>::THREADS, 1) jn_gemm_fold_kernel(const __grid_constant__ FoldParams p) {
+  using C = FoldCfgT<MBT>;
   constexpr int NST = C::NST, MB = C::MB, NB = C::NB, WN = C::WN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

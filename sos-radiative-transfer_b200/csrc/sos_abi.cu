@@ -257,23 +257,21 @@ __global__ void plan_tiles_kernel(sosgemm::GroupTable gt, const int* members, co
 // End of one scattering order in ONE launch: convergence bookkeeping (SOS_Aer_main_specular.py:309) + the tile plan of the
 // next contraction.  Layer-sharded plans first wait here for the peers' halo rows and ratios (layer_shard.cuh), take the two
 // ratios that arrived over as their own and advance the exchange epochs.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 order_end_kernel(const GridDev g, int order_arg, int* order_counter, sosgemm::GroupTable gt, const int* members, int* active_list,
-                 TilePlan* plan, int nseg0, int nseg1, int segs_per_tile, int split_passes, const LayerWait lw,
-                 const double* ratios_in, unsigned long long* epochs) {
-  if (lw.flags) {
-    if (g.state[0].active && threadIdx.x < 32) {
-      const bool late = layer_wait_warp(lw);
+                 TilePlan* plan, int nseg0, int nseg1, int segs_per_tile, int split_passes, const soslayer::LayerPeers lp) {
+  if (lp.n > 1) {
+    if (g.state[0].active) {   // (uniform: nobody has touched the state yet)
+      const bool late = soslayer::exchange_halos(g, lp);
       if (threadIdx.x == 0) {
         if (late) {  // give up: every later kernel of the solve returns at once; the host sees "nothing active" and the status bit
           atomicOr(&g.state[0].status, SOS_STATUS_PEER_TIMEOUT | SOS_STATUS_NONFINITE);
           g.state[0].active = 0;
         } else {
+          const double* ratios_in = lp.box[lp.rank].ratios;
           g.state[0].ratio_toa = *reinterpret_cast<const volatile double*>(ratios_in);
           g.state[0].ratio_surf = *reinterpret_cast<const volatile double*>(ratios_in + 1);
         }
-        epochs[0] += 1;
-        epochs[1] += 1;
       }
     }
     __syncthreads();
@@ -566,7 +564,10 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     // measured in round 1 (sweep over chunk_rows with tools/bench_kernels.py): 48-row chunks are the sweet spot for small batches -- shorter chunks
     // lengthen the serial carry chain more than they help the two scan passes
     chunk = static_cast<int>(std::max<long long>(48, std::min<long long>(128, c)));
-    chunk = std::max(chunk, (L + 47) / 48);  // keep the serial carry chain short
+    if (grid->n_regions == 1 && grid->surface == SOS_SURFACE_NONE)
+      chunk = std::max(chunk, (L + 1023) / 1024);  // the carry chain is a two-level scan per column (sweep_carry_cols_kernel): short chunks cost nothing there
+    else
+      chunk = std::max(chunk, (L + 47) / 48);  // keep the serial carry chain short
   }
   std::vector<int> cstart, cregion, rowchunk(L);
   for (int k = 0; k < grid->n_regions; ++k) {
@@ -889,7 +890,7 @@ int sos_plan_set_layers(sos_plan* p, int rank, int n_ranks, void* const* mailbox
   if (!mailbox_peers_d || !In_peers_d || rank < 0 || rank >= n_ranks || n_ranks > SOS_MAX_PEERS) return SOS_ERR_INVALID;
   // one scenario, one region, no surface coupling (the single-layer operator of SOS_Aer_I1_In.py:77-130), all columns
   if (g.S != 1 || g.nreg != 1 || g.surface != SOS_SURFACE_NONE || g.col0 != 0 || g.col1 != g.N) return SOS_ERR_UNSUPPORTED;
-  if (g.nchunks < n_ranks) return SOS_ERR_UNSUPPORTED;
+  if (g.nchunks < n_ranks || (g.N + soslayer::COL_GROUP - 1) / soslayer::COL_GROUP > soslayer::MAX_GROUPS) return SOS_ERR_UNSUPPORTED;
   for (int r = 0; r < n_ranks; ++r)
     if (!mailbox_peers_d[r] || !In_peers_d[r] || (reinterpret_cast<uintptr_t>(mailbox_peers_d[r]) & 127)) return SOS_ERR_INVALID;
   std::vector<int> cstart(g.nchunks + 1);
@@ -910,6 +911,8 @@ int sos_plan_set_layers(sos_plan* p, int rank, int n_ranks, void* const* mailbox
   std::memset(&lp, 0, sizeof(lp));
   lp.rank = rank;
   lp.n = n_ranks;
+  // (SOS_B200_PEER_TIMEOUT_MS=0: never wait -- one rank profiled alone, its results are meaningless)
+  lp.timeout_ns = static_cast<unsigned long long>(std::max(0, env_int("SOS_B200_PEER_TIMEOUT_MS", 4000))) * 1000000ull;
   for (int r = 0; r < n_ranks; ++r) {
     soslayer::mailbox_layout(mailbox_peers_d[r], g.nchunks, g.N, &lp.box[r]);
     lp.In[r] = In_peers_d[r];
@@ -1264,6 +1267,7 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   if (r) return r;
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::FoldCfgT<3>::SMEM);
   return SOS_OK;
 }
 
@@ -1449,6 +1453,19 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     f.ksplit = dyn_ksplit ? 0 : p->fold_ksplit;
     f.seg_begin = seg_begin;
     f.seg_end = seg_end;
+    // One grid (a single scenario, one region: one operand group): the kernel lays its tiles out itself over the segment range,
+    // so the tile height is free.  A tile is ~70 us of DMMA work per SM at M = 512 and a launch is whole tiles per SM: take the
+    // 48-row shape when (waves x rows per tile) is smaller -- 10 000 rows: 6 x 48 instead of 5 x 64; a layer block of 1 269: 1 x 48.
+    bool rows48 = false;
+    if (g.S == 1 && g.nreg == 1 && p->fold_xform && f.ksplit == 1 && env_int("SOS_FOLD_ROWS48", 1) != 0) {
+      if (f.seg_end == 0x7fffffff) { f.seg_begin = 0; f.seg_end = p->nseg[0]; }
+      const long long segs = std::min(f.seg_end, p->nseg[0]) - f.seg_begin;
+      auto cost = [&](int segs_per_tile) {
+        const long long tiles = (segs + segs_per_tile - 1) / segs_per_tile * f.n_col_tiles;
+        return (tiles + p->n_sms - 1) / p->n_sms * segs_per_tile;
+      };
+      rows48 = cost(6) < cost(8);
+    }
     f.L = g.L; f.N = g.N; f.M = g.M; f.Mh = (g.M + 15) / 16 * 16; f.ld = g.ld;
     f.J = J_d;
     f.scen = g.scen;
@@ -1469,7 +1486,8 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
       if (rl) return rl;
     }
     ProfSpan dense_span(p, 3, st);
-    if (p->fold_xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
+    if (rows48) sosgemm::jn_gemm_fold_kernel<true, 3><<<p->n_sms, sosgemm::FoldCfgT<3>::THREADS, sosgemm::FoldCfgT<3>::SMEM, st>>>(f);
+    else if (p->fold_xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     else sosgemm::jn_gemm_fold_kernel<false><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     return launch_check(p, "jn_gemm_fold_kernel");
   }
@@ -1504,34 +1522,13 @@ static sossweep::SrcGen source_gen(const sos_plan* p, int n) {
   return sg;
 }
 
-// layer-sharded plans: this rank's half of an exchange with the peers (layer_shard.cuh) -- stores into peer memory + flags; the
-// kernel that consumes what the peers send waits for their flags (phase 0: the carry chain, phase 1: order_end_kernel)
-static int layer_push(sos_plan* p, int phase, cudaStream_t st) {
-  soslayer::layer_push_kernel<<<p->layers.n, soslayer::PUSH_THREADS, 0, st>>>(p->dev, p->layers, phase);
-  return launch_check(p, "layer_push_kernel");
-}
-static unsigned long long peer_timeout_ns() {
-  // (0: do not wait at all -- one rank profiled alone, its results are meaningless)
-  static const unsigned long long ns = static_cast<unsigned long long>(std::max(0, env_int("SOS_B200_PEER_TIMEOUT_MS", 4000))) * 1000000ull;
-  return ns;
-}
-
 // convergence bookkeeping of the order just accumulated + tile plan of the next contraction (one launch)
 static int order_end(sos_plan* p, int order_arg, cudaStream_t st) {
   const bool pm = p->fold && p->d_members_premix != nullptr;  // fold-mode tables (build_fold_tables)
-  const bool layered = p->layers.n > 1;
-  LayerWait lw;
-  std::memset(&lw, 0, sizeof(lw));
-  const double* ratios = nullptr;
-  unsigned long long* epochs = nullptr;
-  if (layered) {
-    lw = soslayer::wait_for(p->layers, 1, peer_timeout_ns());
-    ratios = p->layers.box[p->layers.rank].ratios;
-    epochs = p->layers.box[p->layers.rank].epoch;
-  }
-  order_end_kernel<<<1, 256, 0, st>>>(p->dev, order_arg, p->d_order, pm ? p->groups_premix : p->groups, pm ? p->d_members_premix : p->d_members,
-                                      p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS, p->split_passes, lw,
-                                      ratios, epochs);
+  // (sharded plans: the CTA also copies the halo rows to the neighbours -- more threads, more loads in flight)
+  order_end_kernel<<<1, p->layers.n > 1 ? 1024 : 256, 0, st>>>(p->dev, order_arg, p->d_order, pm ? p->groups_premix : p->groups,
+                                                               pm ? p->d_members_premix : p->d_members, p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1],
+                                                               p->gemm_bm / sosgemm::SEG_ROWS, p->split_passes, p->layers);
   return launch_check(p, "order_end_kernel");
 }
 
@@ -1551,20 +1548,14 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     int r = launch_check(p, "sweep_local_kernel");
     if (r) return r;
   }
-  if (layered) {  // chunk aggregates -> the ranks that chain through them
-    int r = layer_push(p, 0, st);
-    if (r) return r;
-  }
   if (g.nreg == 1 && g.surface == SOS_SURFACE_NONE) {
-    // nothing couples the columns: one thread per column, small CTAs all over the chip (sharded plans wait for the peers' aggregates here)
-    LayerWait lw;
-    std::memset(&lw, 0, sizeof(lw));
-    if (layered) lw = soslayer::wait_for(p->layers, 0, peer_timeout_ns());
+    // nothing couples the columns: a two-level scan per column, 32 columns per CTA (sharded plans exchange their chunk
+    // aggregates with the peers inside this kernel)
     const int T3 = sossweep::CARRY_COLS;
     const size_t smem = 2 * static_cast<size_t>(g.nchunks + 1) * sizeof(double);
     if (smem > 30 * 1024) return SOS_ERR_UNSUPPORTED;
     sossweep::sweep_carry_cols_kernel<<<dim3((g.N + T3 - 1) / T3, g.S), T3 * sossweep::CARRY_GROUPS, smem, st>>>(g, p->d_aggD, p->d_aggU, p->d_carryD,
-                                                                                                           p->d_carryU, lw);
+                                                                                                           p->d_carryU, p->layers);
     int r = launch_check(p, "sweep_carry_cols_kernel");
     if (r) return r;
   } else {
@@ -1602,8 +1593,7 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     int r = launch_check(p, "sweep_zone_kernel");
     if (r) return r;
   }
-  if (layered) return layer_push(p, 1, st);  // halo rows of I_n -> the neighbours, convergence ratios -> everybody
-  return SOS_OK;
+  return SOS_OK;  // (sharded plans: halo rows and ratios travel in order_end_kernel)
 }
 
 int sos_sweeps(sos_plan* p, const double* J_d, double* In_d, double* I_d, void* stream) {

@@ -34,6 +34,7 @@
 #pragma once
 #include <type_traits>
 #include "common.cuh"
+#include "layer_shard.cuh"
 
 namespace sossweep {
 
@@ -623,13 +624,13 @@ sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
 // column (in chain order: top-down for the downward half, bottom-up for the upward one).  It composes its group into one
 // affine map carry_out = B + P carry_in (all loads of the group in flight at once), the 32 maps of a column are chained
 // through shared memory by one thread (32 FMAs), and every thread re-chains its group from the true incoming carry.  A
-// fixed order of operations: deterministic, and the same for sharded and unsharded plans.  Layer-sharded plans wait
-// here for the peers' aggregates (layer_shard.cuh) -- every CTA looks at the flags itself.
-constexpr int CARRY_COLS = 32;     // columns per CTA (one 256-byte line of an aggregate row)
+// fixed order of operations: deterministic, and the same for sharded and unsharded plans.  Layer-sharded plans exchange
+// their aggregates with the peers here, column group by column group (layer_shard.cuh: exchange_aggregates).
+constexpr int CARRY_COLS = soslayer::COL_GROUP;  // columns per CTA (one 256-byte line of an aggregate row)
 constexpr int CARRY_GROUPS = 32;   // chunk groups per column
 __global__ void __launch_bounds__(CARRY_COLS * CARRY_GROUPS)
 sweep_carry_cols_kernel(const GridDev g, const double* __restrict__ aggD, const double* __restrict__ aggU,
-                        double* __restrict__ carryD, double* __restrict__ carryU, const LayerWait lw) {
+                        double* __restrict__ carryD, double* __restrict__ carryU, const soslayer::LayerPeers lp) {
   extern __shared__ double sm_tb[];  // [nch + 1] tau at the last row before each chunk (down), [nch + 1] at its first row (up)
   __shared__ double sP[CARRY_GROUPS][CARRY_COLS + 1], sB[CARRY_GROUPS][CARRY_COLS + 1];
   const int s = blockIdx.y;
@@ -643,11 +644,9 @@ sweep_carry_cols_kernel(const GridDev g, const double* __restrict__ aggD, const 
     td[c] = tau[t0 > 0 ? t0 - 1 : 0];
     tu[c] = tau[t0 < L ? t0 : L - 1];
   }
-  if (lw.flags && threadIdx.x < 32) {
-    if (layer_wait_warp(lw) && threadIdx.x == 0) {
-      atomicOr(&g.state[s].status, SOS_STATUS_PEER_TIMEOUT | SOS_STATUS_NONFINITE);
-      g.state[s].active = 0;
-    }
+  if (lp.n > 1) {
+    // (aggD / aggU are this rank's tables inside its mailbox; the peers' CTAs of the same column group write theirs into them)
+    if (soslayer::exchange_aggregates(g, lp, blockIdx.x) && threadIdx.x == 0) atomicOr(&g.state[s].status, SOS_STATUS_PEER_TIMEOUT | SOS_STATUS_NONFINITE);
   }
   __syncthreads();
   const int tx = threadIdx.x & (CARRY_COLS - 1), ty = threadIdx.x / CARRY_COLS;
