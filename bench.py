@@ -203,8 +203,10 @@ def run_reference(args):
 
 def thick_record(args, sos, torch, dist, dev, rank, world, W, steps):
     """BASELINE configs[3]: optically thick FWC cloud layer (tau* = 30, omega = 0.9) on ONE large grid
-    (10 000 layers x 1024 mu), run to In/I < 1e-4; for N > 1 the grid is sharded by mu blocks and the
-    contraction reads the peers' I_n blocks by TMA over NVLink (strong scaling).  Returns the record (rank 0) or None."""
+    (10 000 layers x 1024 mu), run to In/I < 1e-4; for N > 1 the grid is sharded by layer blocks (the ranks exchange scan
+    aggregates, halo rows and ratios by stores into each other's memory from inside the graphed order loop; --thick-sharding
+    mu: by mu blocks, the contraction reading the peers' I_n blocks by TMA over NVLink) -- strong scaling, with the one-GPU
+    time of the same solve measured in the same run.  Returns the record (rank 0) or None."""
     L, M, tau_star, mu0, alb = 10000, 512, 30.0, 0.5, 0.9
     N = 2 * M
     mu = sos.mu_grid(M)

@@ -119,13 +119,17 @@ __global__ void __launch_bounds__(FoldCfgT<MBT>::THREADS, 1) jn_gemm_fold_kernel
   const TilePlan* plan = p.plan;
   const int ksteps = (p.M + BK - 1) / BK;
   const int last_slabs = (p.M - (ksteps - 1) * BK + 3) / 4;  // k-slabs of the last k-step that hold k < M
-  // ksplit == 0: decided per launch from the device-built tile plan -- when the output tiles would leave more than half
-  // of the CTAs idle (few scenarios still iterating), every tile is computed as two halves of the k range
   // row-restricted launch: tiles cover the segments [seg_begin, seg_end) of the (single) group's list
   const bool restricted = p.seg_begin > 0 || p.seg_end != 0x7fffffff;
   const int seg_stop = restricted ? min(p.seg_end, plan->group_nactive[0] * p.nseg[plan->group_cls[0]]) : 0;
   const int n_row_tiles = restricted ? max(0, (seg_stop - p.seg_begin + C::SEGS - 1) / C::SEGS) : plan->n_row_tiles;
-  const int ksplit = p.ksplit > 0 ? p.ksplit : ((2 * n_row_tiles * p.n_col_tiles <= static_cast<int>(gridDim.x) && p.M >= 64) ? 2 : 1);
+  // ksplit == 0: a launch is whole tiles per CTA, so halving the tiles pays whenever it saves half a wave: with T output tiles on
+  // G CTAs, ceil(2T / G) half-tiles per CTA against 2 ceil(T / G) (T = 156 on 148: 3 instead of 4 half-tile times)
+  int ksplit = p.ksplit;
+  if (ksplit == 0) {
+    const int T = n_row_tiles * p.n_col_tiles, G = static_cast<int>(gridDim.x);
+    ksplit = (T > 0 && p.M >= 64 && (2 * T + G - 1) / G < 2 * ((T + G - 1) / G)) ? 2 : 1;
+  }
   const int n_tiles = n_row_tiles * p.n_col_tiles * ksplit;
   const uint32_t smem_base = smem_u32(smem);
 

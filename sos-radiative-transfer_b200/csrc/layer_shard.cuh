@@ -16,7 +16,7 @@
 // Both exchanges are FUSED into the kernels that consume what arrives: plain stores into peer memory (CUDA IPC mappings over
 // NVLink / NVSwitch), one system-scope fence, one flag per sender in the receiver's mailbox, and the receiver spins on its
 // own memory.
-//   phase 0  sweep_carry_cols_kernel (sweep.cuh): CTA b owns 32 mu columns; it pushes its columns of this rank's aggregates to
+//   phase 0  sweep_carry_cols_kernel (sweep.cuh): CTA b owns 16 mu columns; it pushes its columns of this rank's aggregates to
 //            the peers, raises flag (sender, b) there and waits for the peers' flags b only -- no rank-wide barrier, the
 //            column groups of the carry chain proceed independently.
 //   phase 1  order_end_kernel (sos_abi.cu): one CTA pushes the halo rows and ratios, raises its flag at every peer, waits for
@@ -31,8 +31,8 @@
 
 namespace soslayer {
 
-constexpr int COL_GROUP = 32;    // mu columns per CTA of the carry chain = per phase-0 flag
-constexpr int MAX_GROUPS = 128;  // N <= 4096
+constexpr int COL_GROUP = 16;    // mu columns per CTA of the carry chain = per phase-0 flag
+constexpr int MAX_GROUPS = 256;  // N <= 4096
 
 struct Mailbox {
   double* aggD;               // [nchunks][N]

@@ -1549,7 +1549,7 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     if (r) return r;
   }
   if (g.nreg == 1 && g.surface == SOS_SURFACE_NONE) {
-    // nothing couples the columns: a two-level scan per column, 32 columns per CTA (sharded plans exchange their chunk
+    // nothing couples the columns: a two-level scan per column, 16 columns per CTA (sharded plans exchange their chunk
     // aggregates with the peers inside this kernel)
     const int T3 = sossweep::CARRY_COLS;
     const size_t smem = 2 * static_cast<size_t>(g.nchunks + 1) * sizeof(double);

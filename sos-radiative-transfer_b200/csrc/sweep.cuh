@@ -620,13 +620,13 @@ sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
 // The carry chain of a single-region grid without surface coupling (the single-layer operator In_NumInt,
 // SOS_Aer_I1_In.py:77-130): no row-level work couples the columns, so every column chains on its own.  With many chunks
 // (one large grid: 10 000 layers = hundreds of chunks) a serial chain per column is the critical path of the sweeps, so the
-// chain itself is a two-level scan: a CTA owns 32 columns, thread (g, col) owns a group of consecutive chunks of its
+// chain itself is a two-level scan: a CTA owns 16 columns, thread (g, col) owns a group of consecutive chunks of its
 // column (in chain order: top-down for the downward half, bottom-up for the upward one).  It composes its group into one
 // affine map carry_out = B + P carry_in (all loads of the group in flight at once), the 32 maps of a column are chained
 // through shared memory by one thread (32 FMAs), and every thread re-chains its group from the true incoming carry.  A
 // fixed order of operations: deterministic, and the same for sharded and unsharded plans.  Layer-sharded plans exchange
 // their aggregates with the peers here, column group by column group (layer_shard.cuh: exchange_aggregates).
-constexpr int CARRY_COLS = soslayer::COL_GROUP;  // columns per CTA (one 256-byte line of an aggregate row)
+constexpr int CARRY_COLS = soslayer::COL_GROUP;  // columns per CTA (one 128-byte line of an aggregate row)
 constexpr int CARRY_GROUPS = 32;   // chunk groups per column
 __global__ void __launch_bounds__(CARRY_COLS * CARRY_GROUPS)
 sweep_carry_cols_kernel(const GridDev g, const double* __restrict__ aggD, const double* __restrict__ aggU,
@@ -666,7 +666,11 @@ sweep_carry_cols_kernel(const GridDev g, const double* __restrict__ aggD, const 
     if (up) return exp(-(tu[c + 1] - tu[c]) * imu);
     return c > 0 ? exp((td[c + 1] - td[c]) * imu) : 0.0;  // (nothing enters the first chunk from above)
   };
+  // (groups of up to eight chunks keep their aggregates and decay factors in registers between the two passes)
   double P = 1.0, B = 0.0;
+  double ag0[8], ex0[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { ag0[u] = 0.0; ex0[u] = 1.0; }
   if (live) {
     for (int jb = j0; jb < j1; jb += 8) {
       double ag[8], ex[8];
@@ -683,6 +687,7 @@ sweep_carry_cols_kernel(const GridDev g, const double* __restrict__ aggD, const 
           B = fma(B, ex[u], ag[u]);
           P *= ex[u];
         }
+        if (jb == j0) { ag0[u] = ag[u]; ex0[u] = ex[u]; }
       }
     }
   }
@@ -704,13 +709,18 @@ sweep_carry_cols_kernel(const GridDev g, const double* __restrict__ aggD, const 
   double cc = sB[ty][tx];
   for (int jb = j0; jb < j1; jb += 8) {
     double ag[8], ex[8];
+    if (jb == j0) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = jb + u;
-      ag[u] = j < j1 ? agg[base + static_cast<size_t>(chunk_of(j)) * N] : 0.0;
+      for (int u = 0; u < 8; ++u) { ag[u] = ag0[u]; ex[u] = ex0[u]; }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = jb + u;
+        ag[u] = j < j1 ? agg[base + static_cast<size_t>(chunk_of(j)) * N] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ex[u] = (jb + u < j1) ? decay(chunk_of(jb + u)) : 1.0;
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) ex[u] = (jb + u < j1) ? decay(chunk_of(jb + u)) : 1.0;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (jb + u < j1) {
