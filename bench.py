@@ -280,7 +280,7 @@ def thick_record(args, sos, torch, dist, dev, rank, world, W, steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(dev)
             e0.record()
-            ref.solve(ref.first_order(Cc), max_orders=args.thick_orders, poll_every=8)
+            ref.solve(J1, max_orders=args.thick_orders, poll_every=8)   # (as in the sharded step: the first order is computed outside)
             e1.record()
             torch.cuda.synchronize(dev)
             ms1 = float(e0.elapsed_time(e1))
@@ -457,6 +457,13 @@ def main():
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
     step_ms_max, units_all = float(t.item()), float(u.item())
     value = units_all / (step_ms_max * 1e-3)
+    # every rank's own step time and work (the ranks solve DIFFERENT batches of the sweep: the slowest one sets the time)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([step_ms, float(units_per_step) / (L * (2 * M) ** 2)], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]), 4) for x in allr], "scenario_orders_per_step": [int(round(float(x[1]))) for x in allr]}
 
     # ---------------- roofline of the dominant kernel ----------------
     ms = [float(x) for x in ms4]
@@ -646,6 +653,8 @@ def main():
         }
         if full is not None:
             line["full_sweep"] = full
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if secondary is not None:
             line["secondary"] = secondary
         if not args.no_cpu and world == 1:   # the CPU baseline leg is an N = 1 item

@@ -32,7 +32,7 @@ struct FoldParams {
   int nseg[2];
   int n_col_tiles;   // ceil(M / BN)
   int split_passes;  // see GemmParams
-  int ksplit;        // 0: chosen per launch on the device (1 or 2; J rows zeroed by the caller); 1, or 2: every output tile is computed by two tiles (halves of the k range) that add their partial into a
+  int ksplit;        // 0: chosen per launch on the device (J rows zeroed by the caller; see the kernel); 1, or 2: every output tile is computed by two tiles (halves of the k range) that add their partial into a
                      //    zeroed J (exactly two partials per element: order independent) -- launches with fewer tiles than SMs / 2
   int seg_begin, seg_end;  // row-restricted launch (one single-region group: layer-sharded plans): only the segments [seg_begin, seg_end)
   int L, N, M, Mh, ld;
@@ -125,10 +125,16 @@ __global__ void __launch_bounds__(FoldCfgT<MBT>::THREADS, 1) jn_gemm_fold_kernel
   const int n_row_tiles = restricted ? max(0, (seg_stop - p.seg_begin + C::SEGS - 1) / C::SEGS) : plan->n_row_tiles;
   // ksplit == 0: a launch is whole tiles per CTA, so halving the tiles pays whenever it saves half a wave: with T output tiles on
   // G CTAs, ceil(2T / G) half-tiles per CTA against 2 ceil(T / G) (T = 156 on 148: 3 instead of 4 half-tile times)
+  // With at least one output tile per CTA the launch is not cut into tiles at all ("stream-k"): the T x ksteps k-steps of
+  // the launch are dealt to the CTAs as equal contiguous ranges, a range covers the tail of one tile, some whole tiles and
+  // the head of another.  A range is at least one tile long, so no tile is shared by more than two CTAs: its two partials are
+  // added into the zeroed J (order independent), whole tiles are stored.  T = 384 tiles on 148 CTAs: 2.6 tile times instead of 3.
   int ksplit = p.ksplit;
+  bool streamk = false;
   if (ksplit == 0) {
     const int T = n_row_tiles * p.n_col_tiles, G = static_cast<int>(gridDim.x);
-    ksplit = (T > 0 && p.M >= 64 && (2 * T + G - 1) / G < 2 * ((T + G - 1) / G)) ? 2 : 1;
+    streamk = T >= G && !p.split_passes;
+    ksplit = (!streamk && T > 0 && p.M >= 64 && (2 * T + G - 1) / G < 2 * ((T + G - 1) / G)) ? 2 : 1;
   }
   const int n_tiles = n_row_tiles * p.n_col_tiles * ksplit;
   const uint32_t smem_base = smem_u32(smem);
@@ -176,10 +182,17 @@ __global__ void __launch_bounds__(FoldCfgT<MBT>::THREADS, 1) jn_gemm_fold_kernel
     int stage = 0;
     uint32_t phase = 0;
     int seq = 0;
+    // stream-k: this CTA's range of the launch's k-steps
+    const long long all_steps = static_cast<long long>(n_tiles) * ksteps;
+    long long pos = streamk ? all_steps * blockIdx.x / gridDim.x : 0;
+    const long long pos_end = streamk ? all_steps * (blockIdx.x + 1) / gridDim.x : 0;
     while (true) {
       int tile = 0;
-      if (lane == 0) tile = atomicAdd(p.work_counter, 1);
-      tile = __shfl_sync(0xffffffffu, tile, 0);
+      if (streamk) tile = pos < pos_end ? static_cast<int>(pos / ksteps) : n_tiles;
+      else {
+        if (lane == 0) tile = atomicAdd(p.work_counter, 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+      }
       if (tile >= n_tiles) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
@@ -190,7 +203,12 @@ __global__ void __launch_bounds__(FoldCfgT<MBT>::THREADS, 1) jn_gemm_fold_kernel
       }
       const int t2 = tile / ksplit;
       const int kh = tile - t2 * ksplit;
-      const int ks0 = kh * ksteps / ksplit, ks1 = (kh + 1) * ksteps / ksplit;
+      int ks0 = kh * ksteps / ksplit, ks1 = (kh + 1) * ksteps / ksplit;
+      if (streamk) {
+        ks0 = static_cast<int>(pos - static_cast<long long>(tile) * ksteps);
+        ks1 = static_cast<int>(min(static_cast<long long>(ksteps), pos_end - static_cast<long long>(tile) * ksteps));
+        pos += ks1 - ks0;
+      }
       const int rt = t2 / p.n_col_tiles;
       const int ct = t2 - rt * p.n_col_tiles;
       const int g = restricted ? 0 : find_group(plan, rt);
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(FoldCfgT<MBT>::THREADS, 1) jn_gemm_fold_kernel
       }
       const int passes = (cls == 1 && !split) ? 2 : 1;
       if (lane == 0) {
-        info->ct = ct; info->passes = passes; info->first_pass = only_pass; info->atomic_out = (split || ksplit > 1) ? 1 : 0;
+        info->ct = ct; info->passes = passes; info->first_pass = only_pass; info->atomic_out = (split || ksplit > 1 || ks1 - ks0 < ksteps) ? 1 : 0;
         info->ks0 = ks0; info->ks1 = ks1;
       }
       __syncwarp();
