@@ -1,5 +1,6 @@
 """world_size-2 gloo tests of the multi-GPU host logic (no GPU): partitioning helpers, the column
-all-gather used by mu-block sharding, the result gather used by scenario sharding."""
+all-gather used by mu-block sharding, the row gather used by layer-block sharding, the result gather used by scenario
+sharding."""
 import os
 import socket
 
@@ -32,6 +33,20 @@ def _worker(rank, world, port, N, M, rows):
         mine[:, c0:c1] = full[:, c0:c1]
         sos.allgather_columns(mine, blocks, rank)
         assert torch.equal(mine[:, :N], full[:, :N]), "column all-gather did not rebuild the field"
+        # ---- layer-block sharding: the final gather of the (uneven) row blocks of I ----
+        class _Eng:   # what LayerShardedSolver.gather_rows needs of an engine
+            L, ld = 3 * rows + 5, (N + 15) // 16 * 16
+        cut = _Eng.L // 2 - 3
+        solver = object.__new__(sos.LayerShardedSolver)
+        solver.eng, solver.rank, solver.world, solver.group = _Eng, rank, world, None
+        solver.rows = [(0, cut), (cut, _Eng.L)]
+        solver._stage = None
+        whole = torch.arange(_Eng.L * _Eng.ld, dtype=torch.float64).reshape(_Eng.L, _Eng.ld)
+        part = torch.full_like(whole, -7.0)
+        a, b = solver.rows[rank]
+        part[a:b] = whole[a:b]
+        solver.gather_rows(part)
+        assert torch.equal(part, whole), "row gather did not rebuild the field"
         # ---- convergence ratios: MAX all-reduce ----
         r = torch.tensor([[0.1 * (rank + 1), 0.5 - 0.1 * rank]], dtype=torch.float64)
         dist.all_reduce(r, op=dist.ReduceOp.MAX)
