@@ -40,12 +40,14 @@ struct FoldParams {
   const sos_scenario* scen;
 };
 
-// MB_ = 8-row blocks per consumer warp: 4 -> 64-row tiles (the default), 3 -> 48-row tiles.  One tile per SM is ~70 us of DMMA
-// work at M = 512, so a launch with few tiles (one large grid, or a layer block of it) is quantised in whole tiles per SM:
-// the host picks the shape with the fewer (waves x rows per tile), see source_impl.
-template <int MB_>
+// Tile shapes: WM x WN consumer warps, each MB x NB blocks of 8 x 8: <4, 2, 4, 4> = 64 x 128 (the default), <3, 2, 4, 4> = 48 x 128,
+// <7, 1, 8, 2> = 56 x 128.  One tile per SM is ~70 us of DMMA work at M = 512, so a launch with few tiles (one large grid, or
+// a layer block of it) is quantised in whole tiles per SM: the host picks the 48-row shape when (waves x rows per tile) is
+// smaller, see source_impl; and an aerosol layer of 54 rows (7 segments per scenario) fills a 56-row tile exactly where a
+// 64-row tile issues an eighth of its DMMAs on nothing.
+template <int MB_, int WM_ = 2, int WN_ = 4, int NB_ = 4>
 struct FoldCfgT {
-  static constexpr int WM = 2, WN = 4, MB = MB_, NB = 4;
+  static constexpr int WM = WM_, WN = WN_, MB = MB_, NB = NB_;
   static constexpr int NST = 4;
   static constexpr int BM = 8 * MB * WM;    // 64 rows
   static constexpr int BN = 8 * NB * WN;    // 128 folded columns j (-> J columns j and N-1-j)
@@ -89,9 +91,10 @@ __device__ __forceinline__ SegRef seg_lookup_fold(const FoldParams& p, int cls, 
 // XFORM: the three otherwise idle warps of the producer warpgroup turn every landed stage from (x, mirror x) into
 // (u, v) in place, once per CTA, so that the consumer warps load u and v directly (otherwise each of the WN consumer
 // warps of a row block forms them again while loading its fragments: one DADD per 4 DMMAs on the same FP64 pipe).
-template <bool XFORM, int MBT = 4>
-__global__ void __launch_bounds__(FoldCfgT<MBT>::THREADS, 1) jn_gemm_fold_kernel(const __grid_constant__ FoldParams p) {
-  using C = FoldCfgT<MBT>;
+template <bool XFORM, int MBT = 4, int WMT = 2, int WNT = 4, int NBT = 4>
+__global__ void __launch_bounds__(FoldCfgT<MBT, WMT, WNT, NBT>::THREADS, 1) jn_gemm_fold_kernel(const __grid_constant__ FoldParams p) {
+  using C = FoldCfgT<MBT, WMT, WNT, NBT>;
+  static_assert(C::BN == 128 && C::CONSUMER_WARPS == 8, "operand boxes and the warp roles assume 128 folded columns and eight consumer warps");
   constexpr int NST = C::NST, MB = C::MB, NB = C::NB, WN = C::WN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -143,6 +143,7 @@ struct sos_plan {
   unsigned long long* d_lr_stats = nullptr;  // residual / max|A| / max|beta| of sos_build_lowrank_mu2
   std::vector<const double*> F_ptrs;
   // premixed aerosol operands (one per scenario) and the tile-plan tables that go with them
+  int fold_segs = 8;       // 8-row segments per tile of the folded kernel: 8 (64-row tiles), or 7 when every dense tile is an aerosol layer of 7 segments
   int fold_ksplit = 1;     // 2: split k for launches with few tiles (single solves), see FoldParams
   bool fold_xform = true;  // transformer warps form (u, v) once per stage (SOS_FOLD_XFORM=0: every consumer warp does)
   bool premix = false;
@@ -347,7 +348,7 @@ int launch_check(sos_plan* p, const char* what = "kernel") {
 int plan_tiles(sos_plan* p, cudaStream_t st) {
   const bool pm = p->fold && p->d_members_premix != nullptr;  // fold-mode tables (build_fold_tables)
   plan_tiles_kernel<<<1, 256, 0, st>>>(pm ? p->groups_premix : p->groups, pm ? p->d_members_premix : p->d_members, p->dev.state,
-                                       p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1], p->gemm_bm / sosgemm::SEG_ROWS,
+                                       p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1], p->fold ? p->fold_segs : p->gemm_bm / sosgemm::SEG_ROWS,
                                        p->split_passes);
   return launch_check(p);
 }
@@ -1113,14 +1114,14 @@ static int build_fold_tables(sos_plan* p) {
 
 // dense (DMMA) row tiles of an all-active launch in fold mode, for the small-launch heuristics
 static long long fold_dense_row_tiles(const sos_plan* p) {
-  using FC = sosgemm::FoldCfg;
+  struct FC { int SEGS; } fc{p->fold_segs};
   long long rows = 0;
   for (int g = 0; g < p->groups_premix.n_groups; ++g) {
     const long long members = p->groups_premix.member_off[g + 1] - p->groups_premix.member_off[g];
     const int cls = p->groups_premix.cls[g];
     if (cls == 3) continue;
-    if (cls == 2) rows += members * ((p->nseg[1] + FC::SEGS - 1) / FC::SEGS);
-    else rows += (members * (cls == 1 ? p->nseg[1] : p->nseg[0]) + FC::SEGS - 1) / FC::SEGS;
+    if (cls == 2) rows += members * ((p->nseg[1] + fc.SEGS - 1) / fc.SEGS);
+    else rows += (members * (cls == 1 ? p->nseg[1] : p->nseg[0]) + fc.SEGS - 1) / fc.SEGS;
   }
   return rows;
 }
@@ -1129,6 +1130,16 @@ static int refresh_fold_plan(sos_plan* p) {
   using FC = sosgemm::FoldCfg;
   int r = build_fold_tables(p);
   if (r) return r;
+  {
+    // every dense tile is the aerosol layer of one scenario (premixed operand; the other rows are low rank): a layer of 7 segments
+    // (54 rows on the default grid) fills a 56-row tile exactly
+    bool only_aerosol = p->premix && p->fold_xform && p->groups_premix.n_groups > 0;
+    for (int g = 0; g < p->groups_premix.n_groups; ++g)
+      if (p->groups_premix.cls[g] != 2 && p->groups_premix.cls[g] != 3) only_aerosol = false;
+    const int segs = (only_aerosol && p->nseg[1] % 7 == 0 && env_int("SOS_FOLD_ROWS56", 1) != 0) ? 7 : 8;
+    if (segs != p->fold_segs) drop_graphs(p);  // (captured order graphs hold the kernel of the other tile shape)
+    p->fold_segs = segs;
+  }
   const long long tiles = fold_dense_row_tiles(p) * ((p->dev.M + FC::BN - 1) / FC::BN);
   p->split_passes = (!p->premix && p->grid.n_regions == 3 && tiles < 2LL * p->n_sms) ? 1 : 0;
   {
@@ -1268,6 +1279,7 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC::SMEM);
   cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::FoldCfgT<3>::SMEM);
+  cudaFuncSetAttribute(sosgemm::jn_gemm_fold_kernel<true, 7, 1, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sosgemm::FoldCfgT<7, 1, 8, 2>::SMEM);
   return SOS_OK;
 }
 
@@ -1457,6 +1469,8 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     // so the tile height is free.  A tile is ~70 us of DMMA work per SM at M = 512 and a launch is whole tiles per SM: take the
     // 48-row shape when (waves x rows per tile) is smaller -- 10 000 rows: 6 x 48 instead of 5 x 64; a layer block of 1 269: 1 x 48.
     bool rows48 = false;
+    const bool restricted_launch = f.seg_begin > 0 || f.seg_end != 0x7fffffff;
+    if (p->fold_segs != 8 && restricted_launch) return SOS_ERR_UNSUPPORTED;  // (the device tile plan counts 56-row tiles)
     if (g.S == 1 && g.nreg == 1 && p->fold_xform && f.ksplit == 1 && env_int("SOS_FOLD_ROWS48", 1) != 0) {
       if (f.seg_end == 0x7fffffff) { f.seg_begin = 0; f.seg_end = p->nseg[0]; }
       const long long segs = std::min(f.seg_end, p->nseg[0]) - f.seg_begin;
@@ -1487,6 +1501,8 @@ static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_be
     }
     ProfSpan dense_span(p, 3, st);
     if (rows48) sosgemm::jn_gemm_fold_kernel<true, 3><<<p->n_sms, sosgemm::FoldCfgT<3>::THREADS, sosgemm::FoldCfgT<3>::SMEM, st>>>(f);
+    else if (p->fold_segs == 7 && !restricted_launch)
+      sosgemm::jn_gemm_fold_kernel<true, 7, 1, 8, 2><<<p->n_sms, sosgemm::FoldCfgT<7, 1, 8, 2>::THREADS, sosgemm::FoldCfgT<7, 1, 8, 2>::SMEM, st>>>(f);
     else if (p->fold_xform) sosgemm::jn_gemm_fold_kernel<true><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     else sosgemm::jn_gemm_fold_kernel<false><<<p->n_sms, FC::THREADS, FC::SMEM, st>>>(f);
     return launch_check(p, "jn_gemm_fold_kernel");
@@ -1528,7 +1544,7 @@ static int order_end(sos_plan* p, int order_arg, cudaStream_t st) {
   // (sharded plans: the CTA also copies the halo rows to the neighbours -- more threads, more loads in flight)
   order_end_kernel<<<1, p->layers.n > 1 ? 1024 : 256, 0, st>>>(p->dev, order_arg, p->d_order, pm ? p->groups_premix : p->groups,
                                                                pm ? p->d_members_premix : p->d_members, p->d_active_list, p->d_tile_plan, p->nseg[0], p->nseg[1],
-                                                               p->gemm_bm / sosgemm::SEG_ROWS, p->split_passes, p->layers);
+                                                               p->fold ? p->fold_segs : p->gemm_bm / sosgemm::SEG_ROWS, p->split_passes, p->layers);
   return launch_check(p, "order_end_kernel");
 }
 
