@@ -12,7 +12,7 @@ import numpy as np
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsos_b200.so")
+LIB_PATH = os.environ.get("SOS_B200_LIB") or os.path.join(_HERE, "libsos_b200.so")   # (SOS_B200_LIB: an experimental build of the same ABI)
 
 
 class SosError(RuntimeError):

@@ -937,7 +937,13 @@ sweep_apply_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
 // M + 1 is then even, so every pair is 16-byte aligned and lies inside one half).  Same recurrences, same outputs;
 // the projections of a group of four rows are reduced through a small per-warp buffer in shared memory.
 constexpr int APPLY2_THREADS = 128;
-constexpr int APPLY2_RING = 4;   // groups of four rows in the I ring: three in flight (12 rows, 24 KB per CTA) + the one consumed
+#ifndef SOS_APPLY2_RING
+#define SOS_APPLY2_RING 4
+#endif
+#ifndef SOS_APPLY2_MINB
+#define SOS_APPLY2_MINB 4
+#endif
+constexpr int APPLY2_RING = SOS_APPLY2_RING;   // groups of four rows in the I ring: three in flight (12 rows, 24 KB per CTA) + the one consumed
 constexpr int APPLY2_STAGE = 160;  // longest chunk whose per-row scalars are staged in shared memory
 constexpr int PROJ_STRIDE = 34;  // doubles per row of the per-warp buffer (16-byte aligned rows, conflict-free 128-bit reads)
 
@@ -955,7 +961,7 @@ __device__ __forceinline__ double quad_reduce8(double* buf, const double (&v)[8]
   return sum;
 }
 
-__global__ void __launch_bounds__(APPLY2_THREADS, 4)
+__global__ void __launch_bounds__(APPLY2_THREADS, SOS_APPLY2_MINB)
 sweep_apply2_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, double* __restrict__ In,
                     const double* __restrict__ carryD, const double* __restrict__ carryU,
                     double* __restrict__ I, double* __restrict__ saved) {
