@@ -771,6 +771,7 @@ int sos_plan_update(sos_plan* p, const double* tau_h, const sos_scenario* scen_h
   const GridDev& g = p->dev;
   const int S = g.S, L = g.L;
   if (g.col0 != 0 || g.col1 != g.N) return SOS_ERR_UNSUPPORTED;   // column-sharded plans are created per block
+  if (p->layers.n > 1) return SOS_ERR_UNSUPPORTED;                 // layer blocks and their halos were laid out for the old tau: set the layers again afterwards
   int r = validate_scenarios(p->grid, scen_h);
   if (r) return r;
   const int n_phase = static_cast<int>(p->A_ptrs.size());

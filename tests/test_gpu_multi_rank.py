@@ -50,10 +50,12 @@ def test_mu_sharded_solve_on_two_gpus_equals_unsharded(p2p, ref_general):
 
 
 @pytest.mark.parametrize("case", [
-    # (layers, angles, tau*, order cap, chunk rows): thick (the widest extrapolation class, no surviving windowed column),
-    # thin (windowed |mu| < 0.01 columns survive: tau-window halos of hundreds of rows across the block boundary)
-    (1500, 256, 6.0, 300, 64),
-    (1200, 512, 0.05, 300, 48),
+    # (layers, angles, tau*, order cap, chunk rows, folded contraction): thick (the widest extrapolation class, no surviving
+    # windowed column), thin (windowed |mu| < 0.01 columns survive: tau-window halos of hundreds of rows across the block
+    # boundary), and the general (unfolded) contraction kernel on its row-restricted path
+    (1500, 256, 6.0, 300, 64, True),
+    (1200, 512, 0.05, 300, 48, True),
+    (1100, 128, 2.0, 300, 0, False),
 ])
 def test_layer_sharded_solve_is_bit_identical_to_unsharded(case):
     """Layer-block sharding (csrc/layer_shard.cuh): two ranks exchange chunk aggregates, halo rows and ratios by stores into
@@ -62,14 +64,16 @@ def test_layer_sharded_solve_is_bit_identical_to_unsharded(case):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
-    L, M, tau, cap, chunk = case
+    L, M, tau, cap, chunk, fold = case
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(29631 + (L % 7)), os.path.join(ROOT, "tools", "layer_shard_check.py"),
            "--layers", str(L), "--angles", str(M), "--tau", str(tau), "--orders", str(cap), "--chunk-rows", str(chunk), "--repeat", "1", "--check"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    env = dict(os.environ, SOS_B200_FOLD="1" if fold else "0")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
     rec = json.loads(line)
+    assert rec["folded"] == fold, rec
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "layer_shard_2rank_L%d_M%d.json" % (L, M)), "w") as f:
         f.write(line + "\n")
