@@ -756,8 +756,8 @@ int sos_plan_create(sos_plan** out, const sos_grid* grid, const double* mu_h, co
     if (r2) { sos_plan_destroy(p); return r2; }
     cudaDeviceSynchronize();
   }
-  if ((N + 32) * sizeof(double) > 48 * 1024) {
-    cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32) * sizeof(double));
+  if ((N + 32 + 2 * (nch + 1)) * sizeof(double) > 48 * 1024) {
+    cudaFuncSetAttribute(sossweep::sweep_carry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (N + 32 + 2 * (nch + 1)) * sizeof(double));
   }
   {
     int r3 = gen_setup(p, p->scen_h.data());
@@ -1581,7 +1581,7 @@ static int sweeps_impl(sos_plan* p, const double* J_d, double* In_d, double* I_d
     int r = launch_check(p, "sweep_carry_cols_kernel");
     if (r) return r;
   } else {
-    const size_t smem = (g.N + 32) * sizeof(double);
+    const size_t smem = (g.N + 32 + 2 * (g.nchunks + 1)) * sizeof(double);
     sossweep::sweep_carry_kernel<<<g.S, sossweep::CARRY_THREADS, smem, st>>>(g, sg, J_d, p->d_aggD, p->d_aggU, p->d_carryD, p->d_carryU);
     int r = launch_check(p, "sweep_carry_kernel");
     if (r) return r;

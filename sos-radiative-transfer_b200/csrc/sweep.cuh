@@ -495,7 +495,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch /*[32]*/) 
 __global__ void __launch_bounds__(CARRY_THREADS)
 sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, const double* __restrict__ aggD,
                    const double* __restrict__ aggU, double* __restrict__ carryD, double* __restrict__ carryU) {
-  extern __shared__ double sm_row[];  // [N] + scratch[32]
+  extern __shared__ double sm_row[];  // [N] + scratch[32] + tau at the chunk boundaries: [nch + 1] (down), [nch + 1] (up)
   __shared__ int found;
   const int s = blockIdx.x;
   if (!g.state[s].active) return;
@@ -505,6 +505,16 @@ sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
   const sos_scenario sc = g.scen[s];
   double* row = sm_row;
   double* scratch = sm_row + N;
+  // the decay of a carry across chunk c needs tau at the chunk boundaries: staged once (read through chunk_start -> tau inside
+  // the chains they are two dependent loads in front of every batch of exps)
+  double* td = scratch + 32;      // td[c] = tau at the last row before chunk c
+  double* tu = td + nch + 1;      // tu[c] = tau at the first row of chunk c (tu[nch] = tau at the surface row)
+  for (int c = threadIdx.x; c <= nch; c += blockDim.x) {
+    const int t0 = g.chunk_start[c];
+    td[c] = tau[t0 > 0 ? t0 - 1 : 0];
+    tu[c] = tau[t0 < L ? t0 : L - 1];
+  }
+  __syncthreads();
   const size_t base = static_cast<size_t>(s) * nch * N;
 
   // ---- down: chain the standard columns through the chunks ----
@@ -523,8 +533,7 @@ sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
           ex[u] = 0.0;
           if (c < nch) {
             ag[u] = aggD[base + static_cast<size_t>(c) * N + m];
-            const int t0 = g.chunk_start[c], t1 = g.chunk_start[c + 1];
-            if (t0 > 0) ex[u] = exp((tau[t1 - 1] - tau[t0 - 1]) / mu);
+            if (c > 0) ex[u] = exp((td[c + 1] - td[c]) / mu);
           }
         }
 #pragma unroll
@@ -591,9 +600,8 @@ sweep_carry_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
         ag[u] = 0.0;
         ex[u] = 0.0;
         if (cc >= ce) {
-          const int t0 = g.chunk_start[cc], t1 = g.chunk_start[cc + 1];
           ag[u] = aggU[base + static_cast<size_t>(cc) * N + m];
-          ex[u] = exp(-(tau[(t1 == L) ? L - 1 : t1] - tau[t0]) / mu);
+          ex[u] = exp(-(tu[cc + 1] - tu[cc]) / mu);
         }
       }
       double cu = row[m];
