@@ -187,6 +187,10 @@ int sos_build_lowrank_mu2(sos_plan* plan, const double* A_d, int lda, double* Ut
  *     C_h[s][0][m] = alb_atm*P0_atm[m], C_h[s][1][m] = alb_atm*P0_atm[m]*f_atm + alb_aer*P0_aer[m]*f_aer
  *  n_regions == 1: I1_NumInt (SOS_Aer_I1_In.py:13-58); C_h[s][0][m] = alb*P0[m] ([S][2][N], plane 1 unused) */
 int sos_first_order(sos_plan* plan, const double* C_h, double* I1_d, void* stream);
+/* ... the same, every value stored twice: I1_d and I1_copy_d (the field the order loop accumulates into: sos_solve starts
+ * from I = I_1, SOS_Aer_main_specular.py:302-304), which saves the device-to-device copy of the field in front of every
+ * solve.  I1_copy_d may be NULL (= sos_first_order). */
+int sos_first_order2(sos_plan* plan, const double* C_h, double* I1_d, double* I1_copy_d, void* stream);
 
 /* Jn_NumInt (SOS_Aer_I1_In.py:62-74) / SOS_Aer_main_specular.py:315-323 as one FP64 GEMM. */
 int sos_source(sos_plan* plan, const double* In1_d, double* J_d, void* stream);

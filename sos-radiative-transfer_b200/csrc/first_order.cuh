@@ -91,6 +91,7 @@ __device__ double down_carry(const GridDev& g, const Col& c, const double* __res
 
 __global__ void __launch_bounds__(128)
 first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][2][N]*/, double* __restrict__ I1,
+                           double* __restrict__ I1_copy /*second destination (the accumulator I of the order loop) or nullptr*/,
                            int rows_per_block) {
   const int s = blockIdx.z;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,6 +101,12 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
   const double* __restrict__ Catm = Cs + static_cast<size_t>(s) * 2 * N;
   const double* __restrict__ Cmix = Catm + N;
   double* __restrict__ out = I1 + static_cast<size_t>(s) * L * ld;
+  double* __restrict__ out2 = I1_copy ? I1_copy + static_cast<size_t>(s) * L * ld : nullptr;
+  auto put = [&](int t, int col, double v) {
+    const size_t at = static_cast<size_t>(t) * ld + col;
+    out[at] = v;
+    if (out2) out2[at] = v;
+  };
   const int ta = blockIdx.y * rows_per_block;
   const int tb = min(L, ta + rows_per_block);
   const double PI = 3.14159265358979323846;
@@ -126,8 +133,7 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
       int k = 0;
       while (k + 1 < g.nreg && t >= g.rstart[k + 1]) ++k;
       const double* C = (k == 1) ? Cmix : Catm;
-      out[static_cast<size_t>(t) * ld + m] = (mu0 / (mu0 + g.mu[m])) * C[m] * (F0 * q) * sh_e0[t - ta] +
-                                             (mu0 / (mu0 - g.mu[m])) * C[mir] * (S * q) * sh_es[t - ta];
+      put(t, m, (mu0 / (mu0 + g.mu[m])) * C[m] * (F0 * q) * sh_e0[t - ta] + (mu0 / (mu0 - g.mu[m])) * C[mir] * (S * q) * sh_es[t - ta]);
     }
     return;
   }
@@ -147,7 +153,7 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
     for (int t = ta; t < tb; ++t) {
       const int k = region_of(g, t);
       if (k != kcur) { kcur = k; carry = down_carry(g, c, tau, k, T); rk = down_region(g, tau, k, T, mu0); }
-      out[static_cast<size_t>(t) * ld + m] = i1_value(c, k == 1, tau[t], sh_e0[t - ta], sh_es[t - ta], carry, rk);
+      put(t, m, i1_value(c, k == 1, tau[t], sh_e0[t - ta], sh_es[t - ta], carry, rk));
     }
     return;
   }
@@ -191,14 +197,14 @@ first_order_regions_kernel(const GridDev g, const double* __restrict__ Cs /*[S][
   }
   for (int t = ta; t < tb; ++t) {
     const int k = region_of(g, t);
-    out[static_cast<size_t>(t) * ld + m] = i1_value(c, k == 1, tau[t], sh_e0[t - ta], sh_es[t - ta], carry_k[k], rks[k]);
+    put(t, m, i1_value(c, k == 1, tau[t], sh_e0[t - ta], sh_es[t - ta], carry_k[k], rks[k]));
   }
 }
 
 // I1_NumInt (SOS_Aer_I1_In.py:13-58): one homogeneous layer above a black surface
 __global__ void __launch_bounds__(128)
 first_order_single_kernel(const GridDev g, const double* __restrict__ Cs /*[S][2][N], plane 0 = alb*P0*/,
-                          double* __restrict__ I1, int rows_per_block) {
+                          double* __restrict__ I1, double* __restrict__ I1_copy, int rows_per_block) {
   const int s = blockIdx.z;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= g.N) return;
@@ -207,6 +213,7 @@ first_order_single_kernel(const GridDev g, const double* __restrict__ Cs /*[S][2
   const sos_scenario sc = g.scen[s];
   const double C = Cs[static_cast<size_t>(s) * 2 * N + m];
   double* __restrict__ out = I1 + static_cast<size_t>(s) * L * ld;
+  double* __restrict__ out2 = I1_copy ? I1_copy + static_cast<size_t>(s) * L * ld : nullptr;
   const int ta = blockIdx.y * rows_per_block;
   const int tb = min(L, ta + rows_per_block);
   const double PI = 3.14159265358979323846;
@@ -228,6 +235,7 @@ first_order_single_kernel(const GridDev g, const double* __restrict__ Cs /*[S][2
       v = w0 * k * (e0 - eS * exp(-(T - tt) * inv_mu));                 // (:54-55)
     }
     out[static_cast<size_t>(t) * ld + m] = v * norm;
+    if (out2) out2[static_cast<size_t>(t) * ld + m] = v * norm;
   }
 }
 

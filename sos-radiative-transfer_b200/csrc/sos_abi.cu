@@ -1290,7 +1290,11 @@ int sos_plan_set_folded(sos_plan* p, const double* const* F_d, int n, int ldf) {
 }
 
 int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) {
-  if (!p || !C_h || !I1_d) return SOS_ERR_INVALID;
+  return sos_first_order2(p, C_h, I1_d, nullptr, stream);
+}
+
+int sos_first_order2(sos_plan* p, const double* C_h, double* I1_d, double* I1_copy_d, void* stream) {
+  if (!p || !C_h || !I1_d || I1_copy_d == I1_d) return SOS_ERR_INVALID;
   SOS_GUARD(p);
   NvtxRange nvtx("sos:first_order");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1317,9 +1321,9 @@ int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) 
   const int rows_per_block = std::min(64, std::max(8, env_int("SOS_B200_FO_ROWS", 64)));  // (the kernel stages 64 rows at most)
   dim3 grid((g.N + 127) / 128, (g.L + rows_per_block - 1) / rows_per_block, g.S);
   if (g.nreg == 3)
-    sosfirst::first_order_regions_kernel<<<grid, 128, 0, st>>>(g, p->d_C, I1_d, rows_per_block);
+    sosfirst::first_order_regions_kernel<<<grid, 128, 0, st>>>(g, p->d_C, I1_d, I1_copy_d, rows_per_block);
   else
-    sosfirst::first_order_single_kernel<<<grid, 128, 0, st>>>(g, p->d_C, I1_d, rows_per_block);
+    sosfirst::first_order_single_kernel<<<grid, 128, 0, st>>>(g, p->d_C, I1_d, I1_copy_d, rows_per_block);
   return launch_check(p);
 }
 
@@ -1535,6 +1539,7 @@ static sossweep::SrcGen source_gen(const sos_plan* p, int n) {
   sg.nslots = p->gen_nslots;
   sg.zlo = p->gen_zlo;
   sg.zu_end = p->gen_zu_end;
+  sg.zu_proj = std::min(p->dev.M + 1 + sossweep::ZONE_UP, p->dev.N);
   sg.store_all = env_int("SOS_B200_GENSRC_STORE_ALL", 0);
   sg.ldr = p->lowrank_ldr;
   for (int i = 0; i < SOS_MAX_PHASE; ++i) {

@@ -44,8 +44,10 @@ struct SrcGen {
   int Lp;
   double* proj;            // [S][L][nslots][2] partial projections of I_n (one slot per warp of sweep_apply_kernel)
   int nslots;
-  int zlo, zu_end;         // columns the zone kernel reads raw: downward m >= zlo, upward m < zu_end (I_n stored there on
-                           // every row; left out of the apply pass's projections, projected by the zone kernel)
+  int zlo, zu_end;         // columns the zone kernel may read raw: downward m >= zlo, upward m < zu_end (I_n stored there on every row)
+  int zu_proj;             // ... upward m < zu_proj (<= zu_end) and downward m >= zlo are left out of the apply pass's projections
+                           // and projected by the zone kernel with their final values; a blend that reaches past zu_proj corrects
+                           // the raw projection of the apply pass by (final - raw)
   int store_all;           // store I_n everywhere (debugging aid)
   int ldr;
   int rank[SOS_MAX_PHASE];
@@ -791,9 +793,10 @@ sweep_apply_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ 
   const bool zonecol = up ? (m < sg.zu_end) : (m >= sg.zlo);
   const bool keep_in = !cg || zonecol || sg.store_all;  // I_n of this column is read by someone on every row
   const int op = g.scen[s].phase_atm;
-  const double us0 = (cg && valid && !zonecol) ? sg.Ut[op][m] : 0.0;
-  const double us1 = (cg && valid && !zonecol) ? sg.Ut[op][sg.ldr + m] : 0.0;
-  double* const projs = cg ? sg.proj + ((fbase / ld) * sg.nslots + blockIdx.x * (LOCAL_THREADS / 32) + (threadIdx.x >> 5)) * 2 : nullptr;
+  const bool zoneproj = up ? (m < sg.zu_proj) : (m >= sg.zlo);  // projected by the zone kernel (final values)
+  const double us0 = (cg && valid && !zoneproj) ? sg.Ut[op][m] : 0.0;
+  const double us1 = (cg && valid && !zoneproj) ? sg.Ut[op][sg.ldr + m] : 0.0;
+  double* const projs = cg ? sg.proj + (static_cast<size_t>(s) * L * sg.nslots + blockIdx.x * (LOCAL_THREADS / 32) + (threadIdx.x >> 5)) * 2 : nullptr;
   const int forced = up ? 0 : L - 1;  // the row whose I_n everybody stores: ratios, surface coupling
 
   auto jrow = [&](auto gen_tag, int t) -> double {
@@ -1015,7 +1018,7 @@ sweep_apply2_kernel(const GridDev g, const SrcGen sg, const double* __restrict__
     q[k] = mu[k] * mu[k];
     const bool zonecol = up ? (m < sg.zu_end) : (m >= sg.zlo);
     anyzone |= zonecol;
-    const bool projected = cg && stdc[k] && !zonecol;
+    const bool projected = cg && stdc[k] && !(up ? (m < sg.zu_proj) : (m >= sg.zlo));  // the others: zone kernel, final values
     us0[k] = projected ? sg.Ut[op][m] : 0.0;
     us1[k] = projected ? sg.Ut[op][sg.ldr + m] : 0.0;
     X[k] = 0.0;
@@ -1032,7 +1035,7 @@ sweep_apply2_kernel(const GridDev g, const SrcGen sg, const double* __restrict__
   double2* const Sv = saved ? reinterpret_cast<double2*>(saved + fbase + (act ? m0 : 0)) : nullptr;
   const double2* const Jv = reinterpret_cast<const double2*>(src.Js + (act ? m0 : 0));
   const size_t pstep = static_cast<size_t>(sg.nslots) * 2;
-  double* const projs = cg ? sg.proj + ((fbase / ld) * sg.nslots + blockIdx.x * (APPLY2_THREADS / 32) + warp) * 2 : nullptr;
+  double* const projs = cg ? sg.proj + (static_cast<size_t>(s) * L * sg.nslots + blockIdx.x * (APPLY2_THREADS / 32) + warp) * 2 : nullptr;
   double* const pbuf = s_proj[warp];
   const double sgn = up ? -1.0 : 1.0;  // x = sgn * dtau / mu is the (negative) exponent of the attenuation in either direction
 
@@ -1246,12 +1249,21 @@ sweep_apply2_kernel(const GridDev g, const SrcGen sg, const double* __restrict__
 // pass had already accumulated.  With a generated source it also finishes the next order's coefficients of its row:
 // projections of the zone columns (final values) + the apply pass's slots.
 constexpr int ZONE_ROWS = 8;
-constexpr int ZONE_UP = 128;  // upward columns next to mu = 0+ fetched eagerly for the blend search
+#ifndef SOS_ZONE_UP
+#define SOS_ZONE_UP 32
+#endif
+constexpr int ZONE_UP = SOS_ZONE_UP;  // upward columns next to mu = 0+ fetched eagerly for the blend search (and projected here)
 
-// One global round trip per row: everything the row needs (raw values on both sides of mu = 0, the projection slots) is
-// fetched up front into registers / a per-warp shared-memory row, the fix-ups run on shared memory, and I is corrected
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+
+// Two rounds of loads per row: (1) the active flag together with the scenario's words, (2) everything the row needs
+// (raw values on both sides of mu = 0 as asynchronous copies into a per-warp shared-memory row, the projection slots)
+// -- the addresses of round 2 depend on kernel parameters only.  The fix-ups run on shared memory, and I is corrected
 // with fire-and-forget reductions (red.global.add: each element is touched by exactly one lane, so the result does not
-// depend on timing) instead of read-modify-write round trips.
+// depend on timing) instead of read-modify-write round trips.  A blend that reaches past the eager window (a few per
+// cent of the rows) continues from global memory.
 __global__ void __launch_bounds__(32 * ZONE_ROWS, 4)
 sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J, double* __restrict__ In,
                   double* __restrict__ I, double* __restrict__ saved, int zone_buf) {
@@ -1259,55 +1271,65 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.y, t = g.row0 + blockIdx.x * ZONE_ROWS + warp;  // (layer-sharded plans own the rows [row0, row1))
   const int L = g.L, M = g.M, ld = g.ld;
-  if (t >= g.row1 || !g.state[s].active) return;
-  const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
+  if (t >= g.row1) return;
+  // ---- round 1 ----
+  const sos_scenario* __restrict__ scp = g.scen + s;
+  const int active = g.state[s].active;
+  const int op = scp->phase_atm;
+  int region = 0;
+  while (region + 1 < g.nreg && t >= g.rstart[region + 1]) ++region;
+  const int idxw = scp->extrap_width[region];
+  const double coef_atm = scp->coef_atm;
+  if (!active) return;
   const size_t fbase = static_cast<size_t>(s) * L * ld;
-  const SrcAt src(g, sg, J, s);
   double* __restrict__ Is = In + fbase;
   double* __restrict__ Ia = I ? I + fbase : nullptr;
   double* __restrict__ Sv = saved ? saved + fbase : nullptr;
-  const sos_scenario sc = g.scen[s];
-  int region = 0;
-  while (region + 1 < g.nreg && t >= g.rstart[region + 1]) ++region;
   const size_t roff = static_cast<size_t>(t) * ld;
   const int c_lo = g.col0, c_hi = g.col1;
   const bool own_down_zone = (c_lo < M && c_hi >= M);
   const bool own_up_zone = (c_lo <= M && c_hi > M + 1);
-  const bool project = src.gen_row(t);  // this row's I_n feeds a rebuilt source: finish its coefficients
-  const double* __restrict__ Ut = sg.Ut[sc.phase_atm];
   double* row_dn = sm_zone + static_cast<size_t>(warp) * (zone_buf + ZONE_UP + 4);
   double* row_up = row_dn + zone_buf;  // row_up[i] = I_n[t, M + i]
-  // with a generated source the zone is the plan-wide one (the apply pass left those columns out of its projections)
-  const int zl = src.gen ? sg.zlo : zone_lo(g, sc);
-  const int lim = src.gen ? min(c_hi, sg.zu_end) : c_hi;  // the blend search never leaves the owned / stored columns
-  const int eager = min(lim, M + 1 + ZONE_UP);            // ... and its first columns are fetched with everything else
+  // with a generated source the zone is the plan-wide one (the apply pass left those columns out of its projections); it
+  // contains the zone of every scenario, also of those whose source is not rebuilt
+  const bool plan_gen = sg.cj != nullptr;
+  const int zl = plan_gen ? sg.zlo : zone_lo(g, *scp);
+  const int eager = min(c_hi, M + 1 + ZONE_UP);  // (rows of a rebuilt source store I_n up to zu_end >= M + 1 + ZONE_UP)
 
-  // ---------------- one round of loads ----------------
+  // ---- round 2: every load of the row in flight at once ----
   if (own_down_zone) {
+    const int nstd = min(M - 1, g.first_small);  // standard columns: raw values stored and accumulated by the apply pass
     for (int m = zl + lane; m < M; m += 32) {
-      const bool std_col = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
-      row_dn[m - zl] = std_col ? Is[roff + m] : 0.0;  // raw (already stored and accumulated by the apply pass)
+      if (m < nstd) cp_async8(&row_dn[m - zl], &Is[roff + m]);
+      else row_dn[m - zl] = 0.0;
     }
   }
+  if (own_up_zone)
+    for (int m = M + 1 + lane; m < eager; m += 32) cp_async8(&row_up[m - M], &Is[roff + m]);
+  cp_async_commit();
+  const SrcAt src(g, sg, J, s);
+  const double* __restrict__ tau = g.tau + static_cast<size_t>(s) * L;
+  const bool project = src.gen_row(t);  // this row's I_n feeds a rebuilt source: finish its coefficients
+  const double* __restrict__ Ut = sg.Ut[op];
+  const int lim = src.gen ? min(c_hi, sg.zu_end) : c_hi;  // the blend search never leaves the owned / stored columns
+  const int pend = min(sg.zu_proj, g.N);                  // upward columns < pend are projected here, the others by the apply pass
   double v0 = 0.0;
-  if (own_up_zone) {
-    for (int m = M + 1 + lane; m < eager; m += 32) row_up[m - M] = Is[roff + m];
-    v0 = src(t, M, g.mu[M]);  // I_n[t, mu = 0+] = J[t, mu = 0+]
-  }
+  if (own_up_zone) v0 = src(t, M, g.mu[M]);  // I_n[t, mu = 0+] = J[t, mu = 0+]
   double p0 = 0.0, p1 = 0.0;  // projections: the apply pass's slots first
   if (project) {
-    const double2* __restrict__ pr = reinterpret_cast<const double2*>(sg.proj + (fbase / ld + t) * sg.nslots * 2);
+    const double2* __restrict__ pr = reinterpret_cast<const double2*>(sg.proj + (static_cast<size_t>(s) * L + t) * sg.nslots * 2);
     for (int j = lane; j < sg.nslots; j += 32) {
       const double2 v = pr[j];
       p0 += v.x;
       p1 += v.y;
     }
   }
+  cp_async_wait<0>();
   __syncwarp();
 
   if (own_down_zone) {
     double* row = row_dn - zl;  // row[m] valid for m in [zl, M)
-    const int idxw = sc.extrap_width[region];
     const int r0 = g.rstart[region];
     // non-standard columns that survive the extrapolation: computed here, never touched by the apply pass
     const int hi = min(M - 1, M - idxw);
@@ -1330,7 +1352,7 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
         const int m = M - 1 - i;  // sources (< M - idx) and targets (>= M - idx) never overlap
         double v = 0.0;
         for (int k = 0; k < ns; ++k) v += W[i * ns + k] * row[src0 + k];
-        const bool std_col = (m < M - 1) && fabs(g.mu[m]) >= SOS_MU_THRESHOLD;
+        const bool std_col = m < min(M - 1, g.first_small);
         const double raw = row[m];
         row[m] = v;
         Is[roff + m] = v;
@@ -1399,6 +1421,10 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
         Is[roff + m] = val;
         if (Sv) Sv[roff + m] = val;
         if (Ia) atomicAdd(&Ia[roff + m], val - old);
+        if (project && m >= pend) {  // past the columns projected below: the apply pass projected the raw value
+          p0 = fma(val - old, Ut[m], p0);
+          p1 = fma(val - old, Ut[sg.ldr + m], p1);
+        }
       }
     }
     __syncwarp();
@@ -1406,7 +1432,7 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
 
   if (project) {
     // the next order's source coefficients of this row: + the zone columns (final values: all inside the eager window)
-    for (int m = M + lane; m < min(sg.zu_end, g.N); m += 32) {
+    for (int m = M + lane; m < min(pend, eager); m += 32) {
       const double v = row_up[m - M];
       p0 = fma(v, Ut[m], p0);
       p1 = fma(v, Ut[sg.ldr + m], p1);
@@ -1414,7 +1440,7 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { p0 += shfl_xor_d(p0, o); p1 += shfl_xor_d(p1, o); }
     if (lane == 0)
-      *reinterpret_cast<double2*>(sg.cj_out + (static_cast<size_t>(s) * sg.Lp + t) * 2) = make_double2(sc.coef_atm * p0, sc.coef_atm * p1);
+      *reinterpret_cast<double2*>(sg.cj_out + (static_cast<size_t>(s) * sg.Lp + t) * 2) = make_double2(coef_atm * p0, coef_atm * p1);
   }
 
   // ---- convergence ratios on the TOA / surface rows (whole half-row, read back from global) ----
@@ -1536,10 +1562,29 @@ __global__ void __launch_bounds__(256) project_rows_kernel(const GridDev g, cons
   const double* __restrict__ Ut = sg.Ut[op];
   const double* __restrict__ row = I + (static_cast<size_t>(s) * g.L + t) * g.ld;
   double p0 = 0.0, p1 = 0.0;
-  for (int m = lane; m < g.N; m += 32) {
-    const double x = row[m];
-    p0 = fma(x, Ut[m], p0);
-    p1 = fma(x, Ut[sg.ldr + m], p1);
+  if (((g.ld | sg.ldr) & 1) == 0 && ((reinterpret_cast<uintptr_t>(I) | reinterpret_cast<uintptr_t>(Ut)) & 15) == 0) {
+    // rows and factor rows start on 16-byte boundaries: two columns per load
+    const double2* __restrict__ row2 = reinterpret_cast<const double2*>(row);
+    const double2* __restrict__ u0 = reinterpret_cast<const double2*>(Ut);
+    const double2* __restrict__ u1 = reinterpret_cast<const double2*>(Ut + sg.ldr);
+    const int n2 = g.N >> 1;
+#pragma unroll 4
+    for (int j = lane; j < n2; j += 32) {
+      const double2 x = row2[j], a = u0[j], b = u1[j];
+      p0 = fma(x.x, a.x, p0); p0 = fma(x.y, a.y, p0);
+      p1 = fma(x.x, b.x, p1); p1 = fma(x.y, b.y, p1);
+    }
+    if ((g.N & 1) && lane == 0) {
+      const int m = g.N - 1;
+      p0 = fma(row[m], Ut[m], p0);
+      p1 = fma(row[m], Ut[sg.ldr + m], p1);
+    }
+  } else {
+    for (int m = lane; m < g.N; m += 32) {
+      const double x = row[m];
+      p0 = fma(x, Ut[m], p0);
+      p1 = fma(x, Ut[sg.ldr + m], p1);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

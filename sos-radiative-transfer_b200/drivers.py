@@ -253,20 +253,24 @@ class BatchSolver:
             self._register_phases()          # a phase function met for the first time: register the larger operand set
         self.engine.update(self.tau, coefs)
 
-    def first_order(self):
-        self.I1 = self.engine.first_order(self.Ccoef, out=self.I1)
+    def first_order(self, also_into=None):
+        self.I1 = self.engine.first_order(self.Ccoef, out=self.I1, also_into=also_into)
         return self.I1
 
     def solve(self, keep_orders: int = 0, poll_every: int = 2, max_orders: Optional[int] = None):
-        I1 = self.first_order()
+        # the first-order kernel stores its values twice: into I1 and into the field the loop accumulates into (I = I_1 + ...),
+        # which is one device-to-device field copy less per solve
+        acc = self.engine._buf("I")
+        I1 = self.first_order(also_into=acc)
         mo = max_orders if max_orders is not None else max(s.max_orders for s in self.scenarios)
         # the first order is recomputed by every solve, so its buffer can serve as the loop's I_n field -- unless the caller
         # wants the per-order fields back (results() then reads I1 as order 1)
+        kw = dict(max_orders=mo, keep_orders=keep_orders, poll_every=poll_every, consume_I1=(keep_orders == 0), I=acc, I_holds_I1=True)
         try:
-            return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every, consume_I1=(keep_orders == 0))
+            return self.engine.solve(I1, **kw)
         except _lib.SosRetry:   # (see SosEngine.solve) -- the first order was consumed: rebuild it, the plan has switched kernels
-            I1 = self.first_order()
-            return self.engine.solve(I1, max_orders=mo, keep_orders=keep_orders, poll_every=poll_every, consume_I1=(keep_orders == 0))
+            I1 = self.first_order(also_into=acc)
+            return self.engine.solve(I1, **kw)
 
     def results(self, res, quadratures=True, keep_orders=0, fields=True) -> List[DriverResult]:
         """Per-scenario results on the host.  fields=False skips the D2H copy of the radiance fields

@@ -381,12 +381,15 @@ class SosEngine:
         return P, P0
 
     # ------------------------------------------------------------------ operators
-    def first_order(self, C_coef: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """C_coef: (S, 2, N) -- see sos_first_order in sos_b200.h."""
+    def first_order(self, C_coef: np.ndarray, out: Optional[torch.Tensor] = None, also_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """C_coef: (S, 2, N) -- see sos_first_order in sos_b200.h.  also_into: a second field that receives the same values
+        (the accumulator of the order loop: solve(..., I=also_into, I_holds_I1=True) then skips its field copy)."""
         Cc = np.ascontiguousarray(C_coef, dtype=np.float64).reshape(self.S, 2, self.N)
         out = self.new_field(zero=True) if out is None else out
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.sos_first_order(self._plan, Cc.ctypes.data, out.data_ptr(), self._stream), "sos_first_order")
+            _lib.check(self.lib.sos_first_order2(self._plan, Cc.ctypes.data, out.data_ptr(),
+                                                 also_into.data_ptr() if also_into is not None else None, self._stream),
+                       "sos_first_order")
         return out
 
     def source(self, In1: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -457,12 +460,12 @@ class SosEngine:
 
     def solve(self, I1: torch.Tensor, max_orders: int = 10000, keep_orders: int = 0, poll_every: int = 1,
               In: Optional[torch.Tensor] = None, J: Optional[torch.Tensor] = None, I: Optional[torch.Tensor] = None,
-              consume_I1: bool = False) -> SolveResult:
+              consume_I1: bool = False, I_holds_I1: bool = False) -> SolveResult:
         """The order loop of SOS_Aer() (SOS_Aer_main_specular.py:302-458) for the whole batch.
 
         I1 is not modified unless consume_I1 is set: then its buffer serves as the I_n field of the loop (one field copy
         less per solve; the caller recomputes the first order before it needs it again).  keep_orders > 0 also returns
-        the first `keep_orders` fields I_n (n >= 2).
+        the first `keep_orders` fields I_n (n >= 2).  I_holds_I1: the accumulator I already holds I1 (first_order(also_into=I)).
         """
         I = self._buf("I") if I is None else I
         J = self._buf("J") if J is None else J
@@ -474,7 +477,8 @@ class SosEngine:
         res = (_lib.sos_result * self.S)()
         In_arg = In
         for attempt in (0, 1):
-            I.copy_(I1)
+            if not (I_holds_I1 and attempt == 0):
+                I.copy_(I1)
             if consume_I1 and In_arg is None:
                 In = I1
             else:
