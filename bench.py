@@ -562,7 +562,9 @@ def main():
         bs_e2e.update(scen)                            # host: tau / coefficients of the batch; H2D
         r = bs_e2e.solve(poll_every=2)
         out = bs_e2e.results(r, quadratures=True, fields=False)   # D2H: flux/diffusivity/heating profiles, n, TOA net flux
-        h2d = bs_e2e.tau.nbytes + bs_e2e.Ccoef.nbytes + 80 * len(scen)
+        # what actually crosses PCIe: tau, the scenario records, and the first-order inputs (table of distinct solar phase
+        # vectors + rows + weights: the coefficient planes are assembled on the device, sos_first_order_tab)
+        h2d = bs_e2e.tau.nbytes + 80 * len(scen) + bs_e2e.P0tab.nbytes + bs_e2e.P0idx.nbytes + bs_e2e.P0w.nbytes
         d2h = sum(5 * o.flux_up.nbytes for o in out) + 40 * len(out)
         return out
 

@@ -191,6 +191,16 @@ int sos_first_order(sos_plan* plan, const double* C_h, double* I1_d, void* strea
  * from I = I_1, SOS_Aer_main_specular.py:302-304), which saves the device-to-device copy of the field in front of every
  * solve.  I1_copy_d may be NULL (= sos_first_order). */
 int sos_first_order2(sos_plan* plan, const double* C_h, double* I1_d, double* I1_copy_d, void* stream);
+/* ... the same with the coefficient planes assembled on the device from what a sweep driver actually holds: a table of
+ * the distinct solar phase vectors P0tab_h [n_tab][N] of the batch (one row per (phase function, mu0):
+ * SOS_Aer_phase_func.py:68-292), per scenario the two rows it uses idx_h [S][2] = (atmosphere, aerosol) and the weights
+ * w_h [S][4] = (alb_atm, f_atm, alb_aer, f_aer) (SOS_Aer_main_specular.py:52-53):
+ *     C[s][0][m] = P0tab[ia][m]*w0,   C[s][1][m] = (P0tab[ia][m]*w0)*w1 + (P0tab[ie][m]*w2)*w3
+ * with every product and the sum rounded separately, i.e. bit for bit the planes sos_first_order takes (n_regions == 1:
+ * w = (alb, 0, 0, 0)).  Saves the host the per-element arithmetic on [S][2][N] and the copy of it.  n_tab*N + 5*S must not
+ * exceed 2*S*N (SOS_ERR_UNSUPPORTED otherwise: use sos_first_order2). */
+int sos_first_order_tab(sos_plan* plan, const double* P0tab_h, int n_tab, const int* idx_h, const double* w_h, double* I1_d,
+                        double* I1_copy_d, void* stream);
 
 /* Jn_NumInt (SOS_Aer_I1_In.py:62-74) / SOS_Aer_main_specular.py:315-323 as one FP64 GEMM. */
 int sos_source(sos_plan* plan, const double* In1_d, double* J_d, void* stream);

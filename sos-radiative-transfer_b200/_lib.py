@@ -97,6 +97,7 @@ SIGNATURES = {
     "sos_build_lowrank_mu2": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), _vp]),
     "sos_first_order": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_first_order2": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "sos_first_order_tab": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "sos_source": (C.c_int, [_vp, _vp, _vp, _vp]),
     "sos_source_rows": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "sos_source_peers": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.POINTER(C.c_int), _vp, _vp]),

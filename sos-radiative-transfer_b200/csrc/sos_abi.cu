@@ -110,6 +110,7 @@ struct sos_plan {
   double* d_carryD = nullptr;
   double* d_carryU = nullptr;
   double* d_C = nullptr;     // [S][2][N] first-order coefficients
+  double* d_Ctab = nullptr;  // sos_first_order_tab: the uploaded table, weights and indices the coefficients are assembled from
   double* d_sums = nullptr;  // [S][L][3]
   double* d_z = nullptr;     // [L]
   double* d_colint = nullptr;  // [N] column integrals of the device phase builder
@@ -1293,31 +1294,29 @@ int sos_first_order(sos_plan* p, const double* C_h, double* I1_d, void* stream) 
   return sos_first_order2(p, C_h, I1_d, nullptr, stream);
 }
 
-int sos_first_order2(sos_plan* p, const double* C_h, double* I1_d, double* I1_copy_d, void* stream) {
-  if (!p || !C_h || !I1_d || I1_copy_d == I1_d) return SOS_ERR_INVALID;
-  SOS_GUARD(p);
-  NvtxRange nvtx("sos:first_order");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// The caller's host arrays (possibly pageable) are copied into one of two pinned staging buffers owned by the plan, so the
+// H2D copy is truly asynchronous and the first-order entry points return without waiting for the stream.  Returns the buffer.
+static int first_order_stage(sos_plan* p, double** buf, cudaEvent_t* ev) {
   const GridDev& g = p->dev;
-  {
-    // C_h belongs to the caller (and may be pageable): it is copied into one of two pinned staging buffers owned by the
-    // plan, so the H2D copy is truly asynchronous and the call returns without waiting for the stream
-    const size_t bytes = sizeof(double) * g.S * 2 * g.N;
-    const int k = p->h_C_next;
-    p->h_C_next ^= 1;
-    if (!p->h_C[k]) {
-      auto& fl = pinned_coef_free_list();
-      for (size_t i = 0; i < fl.size() && !p->h_C[k]; ++i)
-        if (fl[i].first == bytes) { p->h_C[k] = fl[i].second; fl.erase(fl.begin() + i); }
-      if (!p->h_C[k]) SOS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_C[k]), bytes));
-      SOS_CUDA(cudaEventCreateWithFlags(&p->h_C_ev[k], cudaEventDisableTiming));
-    } else {
-      SOS_CUDA(cudaEventSynchronize(p->h_C_ev[k]));  // the copy issued two calls ago has left this buffer
-    }
-    std::memcpy(p->h_C[k], C_h, bytes);
-    SOS_CUDA(cudaMemcpyAsync(p->d_C, p->h_C[k], bytes, cudaMemcpyHostToDevice, st));
-    SOS_CUDA(cudaEventRecord(p->h_C_ev[k], st));
+  const size_t bytes = sizeof(double) * g.S * 2 * g.N;
+  const int k = p->h_C_next;
+  p->h_C_next ^= 1;
+  if (!p->h_C[k]) {
+    auto& fl = pinned_coef_free_list();
+    for (size_t i = 0; i < fl.size() && !p->h_C[k]; ++i)
+      if (fl[i].first == bytes) { p->h_C[k] = fl[i].second; fl.erase(fl.begin() + i); }
+    if (!p->h_C[k]) SOS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_C[k]), bytes));
+    SOS_CUDA(cudaEventCreateWithFlags(&p->h_C_ev[k], cudaEventDisableTiming));
+  } else {
+    SOS_CUDA(cudaEventSynchronize(p->h_C_ev[k]));  // the copy issued two calls ago has left this buffer
   }
+  *buf = p->h_C[k];
+  *ev = p->h_C_ev[k];
+  return SOS_OK;
+}
+
+static int first_order_launch(sos_plan* p, double* I1_d, double* I1_copy_d, cudaStream_t st) {
+  const GridDev& g = p->dev;
   const int rows_per_block = std::min(64, std::max(8, env_int("SOS_B200_FO_ROWS", 64)));  // (the kernel stages 64 rows at most)
   dim3 grid((g.N + 127) / 128, (g.L + rows_per_block - 1) / rows_per_block, g.S);
   if (g.nreg == 3)
@@ -1325,6 +1324,71 @@ int sos_first_order2(sos_plan* p, const double* C_h, double* I1_d, double* I1_co
   else
     sosfirst::first_order_single_kernel<<<grid, 128, 0, st>>>(g, p->d_C, I1_d, I1_copy_d, rows_per_block);
   return launch_check(p);
+}
+
+int sos_first_order2(sos_plan* p, const double* C_h, double* I1_d, double* I1_copy_d, void* stream) {
+  if (!p || !C_h || !I1_d || I1_copy_d == I1_d) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
+  NvtxRange nvtx("sos:first_order");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GridDev& g = p->dev;
+  const size_t bytes = sizeof(double) * g.S * 2 * g.N;
+  double* buf;
+  cudaEvent_t ev;
+  int r = first_order_stage(p, &buf, &ev);
+  if (r) return r;
+  std::memcpy(buf, C_h, bytes);
+  SOS_CUDA(cudaMemcpyAsync(p->d_C, buf, bytes, cudaMemcpyHostToDevice, st));
+  SOS_CUDA(cudaEventRecord(ev, st));
+  return first_order_launch(p, I1_d, I1_copy_d, st);
+}
+
+// C[s][0][m] = P0[ia][m] * w0,  C[s][1][m] = (P0[ia][m] * w0) * w1 + (P0[ie][m] * w2) * w3 -- every product and the sum rounded
+// separately (no contraction into FMAs): the same bits as the host arithmetic the reference does on its P0 vectors
+__global__ void __launch_bounds__(256)
+first_order_coef_kernel(const double* __restrict__ tab, const double* __restrict__ w, const int* __restrict__ idx, double* __restrict__ C, int N) {
+  const int s = blockIdx.y, m = blockIdx.x * 256 + threadIdx.x;
+  if (m >= N) return;
+  const int ia = idx[2 * s], ie = idx[2 * s + 1];
+  const double c0 = __dmul_rn(tab[static_cast<size_t>(ia) * N + m], w[4 * s]);
+  const double e = __dmul_rn(__dmul_rn(tab[static_cast<size_t>(ie) * N + m], w[4 * s + 2]), w[4 * s + 3]);
+  C[(static_cast<size_t>(s) * 2) * N + m] = c0;
+  C[(static_cast<size_t>(s) * 2 + 1) * N + m] = __dadd_rn(__dmul_rn(c0, w[4 * s + 1]), e);
+}
+
+int sos_first_order_tab(sos_plan* p, const double* P0tab_h, int n_tab, const int* idx_h, const double* w_h, double* I1_d,
+                        double* I1_copy_d, void* stream) {
+  if (!p || !P0tab_h || !idx_h || !w_h || !I1_d || I1_copy_d == I1_d || n_tab < 1) return SOS_ERR_INVALID;
+  SOS_GUARD(p);
+  NvtxRange nvtx("sos:first_order");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GridDev& g = p->dev;
+  const size_t S = g.S, N = g.N;
+  // staging layout (doubles): [n_tab][N] table | [S][4] weights | [S][2] indices (ints); it must fit the [S][2][N] staging buffer
+  const size_t tab_d = static_cast<size_t>(n_tab) * N, all_d = tab_d + 4 * S + S;
+  if (all_d > S * 2 * N) return SOS_ERR_UNSUPPORTED;
+  for (size_t i = 0; i < 2 * S; ++i)
+    if (idx_h[i] < 0 || idx_h[i] >= n_tab) return SOS_ERR_INVALID;
+  if (!p->d_Ctab) {
+    int r = dev_alloc(p, &p->d_Ctab, S * 2 * N);
+    if (r) return r;
+    SOS_CUDA(cudaStreamSynchronize(nullptr));  // (the pool allocates on the legacy default stream; once per plan)
+  }
+  double* buf;
+  cudaEvent_t ev;
+  int r = first_order_stage(p, &buf, &ev);
+  if (r) return r;
+  std::memcpy(buf, P0tab_h, sizeof(double) * tab_d);
+  std::memcpy(buf + tab_d, w_h, sizeof(double) * 4 * S);
+  std::memcpy(buf + tab_d + 4 * S, idx_h, sizeof(int) * 2 * S);
+  SOS_CUDA(cudaMemcpyAsync(p->d_Ctab, buf, sizeof(double) * all_d, cudaMemcpyHostToDevice, st));
+  SOS_CUDA(cudaEventRecord(ev, st));
+  dim3 cg(static_cast<unsigned>((N + 255) / 256), static_cast<unsigned>(S));
+  first_order_coef_kernel<<<cg, 256, 0, st>>>(p->d_Ctab, p->d_Ctab + tab_d, reinterpret_cast<const int*>(p->d_Ctab + tab_d + 4 * S), p->d_C,
+                                              static_cast<int>(N));
+  r = launch_check(p, "first_order_coef_kernel");
+  if (r) return r;
+  return first_order_launch(p, I1_d, I1_copy_d, st);
 }
 
 static int source_impl(sos_plan* p, const double* In1_d, double* J_d, int seg_begin, int seg_end, void* stream,

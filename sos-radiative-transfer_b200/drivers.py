@@ -162,33 +162,34 @@ class BatchSolver:
         self.I1 = None
 
     def _prepare(self, scenarios):
-        """Host side of a batch: tau profiles, first-order coefficients, per-scenario scalars; phase functions met for
-        the first time are appended to self._mats (the caller registers them)."""
+        """Host side of a batch: tau profiles, per-scenario scalars, the table of distinct solar phase vectors with the rows
+        and weights each scenario's first-order coefficients are made of (assembled on the device); phase functions met for the
+        first time are appended to self._mats (the caller registers them)."""
         self.scenarios = list(scenarios)
         L, M = self.L, self.M
         S = len(scenarios)
         # batch-sized host buffers are kept between batches (BatchSolver.update): fresh ones cost page faults every time
         bufs = getattr(self, "_host_bufs", None)
         if bufs is None or bufs[0].shape != (S, L):
-            bufs = self._host_bufs = (np.empty((S, L)), np.empty((S, 2, self.N)), np.empty((S, self.N)), np.empty((S, self.N)))
-        tau, Ccoef = bufs[0], bufs[1]
+            bufs = self._host_bufs = (np.empty((S, L)), np.arange(L, dtype=np.float64), np.arange(L))
+        tau, rows_f, rows = bufs
         # tau profiles of the whole batch at once: the same arithmetic as grid.tau_profile, element for element
-        # (the group key fixes idx_up / idx_down for every scenario of the batch)
-        rows = np.arange(L)
+        # (the group key fixes idx_up / idx_down for every scenario of the batch; int -> float conversion is exact)
         t_atm = np.array([sc.tauStar_atm for sc in scenarios], dtype=np.float64)
         t_aer = np.array([sc.tauStar_aer for sc in scenarios], dtype=np.float64)
-        tau[:] = rows[None, :] * t_atm[:, None] / (L - 1)
-        inside = (rows >= self.idx_up) & (rows <= self.idx_down)
-        tau[:, inside] += (rows[inside] + 1 - self.idx_up)[None, :] * (t_aer / (self.idx_down + 1 - self.idx_up))[:, None]
-        tau[:, rows > self.idx_down] += t_aer[:, None]
+        iu, idn = self.idx_up, self.idx_down
+        np.multiply(rows_f[None, :], t_atm[:, None], out=tau)
+        np.divide(tau, L - 1, out=tau)
+        tau[:, iu:idn + 1] += (rows[iu:idn + 1] + 1 - iu)[None, :] * (t_aer / (idn + 1 - iu))[:, None]
+        tau[:, idn + 1:] += t_aer[:, None]
         self._new_mats = 0
-        # phase tables: one look-up per DISTINCT (phase, mu0) of the batch, then everything below is array arithmetic
-        P0A, P0E = bufs[2], bufs[3]
-        idx_atm = np.empty(S, dtype=np.int32)
-        idx_aer = np.empty(S, dtype=np.int32)
+        # phase tables: one look-up per DISTINCT (phase, mu0) of the batch; a scenario refers to rows of the table
+        tab_rows = []
+        p0_idx = np.empty((S, 2), dtype=np.int32)
+        mat_idx = np.empty((S, 2), dtype=np.int32)
         seen = {}
         for i, sc in enumerate(scenarios):
-            for spec, P0dst, idst in ((sc.atm_phase, P0A, idx_atm), (sc.aer_phase, P0E, idx_aer)):
+            for j, spec in enumerate((sc.atm_phase, sc.aer_phase)):
                 key = (spec if isinstance(spec[0], str) else id(spec[1]), sc.mu0)
                 hit = seen.get(key)
                 if hit is None:
@@ -198,22 +199,27 @@ class BatchSolver:
                         self._mats.append(P)
                         self._mat_keys.append(k if k[0] != "array" else None)  # analytic families are immutable: cache on device
                         self._new_mats += 1
-                    hit = seen[key] = (P0, self._mat_index[k])
-                P0dst[i] = hit[0]
-                idst[i] = hit[1]
+                    hit = seen[key] = (len(tab_rows), self._mat_index[k])
+                    tab_rows.append(P0)
+                p0_idx[i, j] = hit[0]
+                mat_idx[i, j] = hit[1]
+        tab = getattr(self, "_tab_buf", None)
+        if tab is None or tab.shape[0] < len(tab_rows):
+            tab = self._tab_buf = np.empty((max(len(tab_rows), 16), self.N))
+        for r, P0 in enumerate(tab_rows):
+            tab[r] = P0
         alb_atm = np.array([sc.alb_atm for sc in scenarios], dtype=np.float64)
         alb_aer = np.array([sc.alb_aer for sc in scenarios], dtype=np.float64)
         # global mixing weights (SOS_Aer_main_specular.py:52-53; note dtau_atm = tauStar_atm / L, Q9)
-        dtau_aer = t_aer / (self.idx_down + 1 - self.idx_up)
+        dtau_aer = t_aer / (idn + 1 - iu)
         dtau_atm = t_atm / L
         f_atm = dtau_atm / (dtau_atm + dtau_aer)
         f_aer = dtau_aer / (dtau_atm + dtau_aer)
-        # (in place: same operations in the same order as the scalar formulas, without batch-sized temporaries)
-        np.multiply(P0A, alb_atm[:, None], out=Ccoef[:, 0])
-        np.multiply(Ccoef[:, 0], f_atm[:, None], out=Ccoef[:, 1])
-        np.multiply(P0E, alb_aer[:, None], out=P0E)
-        np.multiply(P0E, f_aer[:, None], out=P0E)
-        np.add(Ccoef[:, 1], P0E, out=Ccoef[:, 1])
+        # first-order coefficient planes C0 = P0_atm * alb_atm, C1 = C0 * f_atm + (P0_aer * alb_aer) * f_aer: the device assembles
+        # them from the table (sos_first_order_tab, same operations in the same order); Ccoef does it on the host when asked
+        self.P0tab = tab[: len(tab_rows)]
+        self.P0idx = p0_idx
+        self.P0w = np.stack([alb_atm, f_atm, alb_aer, f_aer], axis=1)
         coefs = np.zeros(S, dtype=_lib.SCENARIO_DTYPE)
         coefs["mu0"] = [sc.mu0 for sc in scenarios]
         coefs["grd_alb"] = [sc.grd_alb for sc in scenarios]
@@ -222,13 +228,22 @@ class BatchSolver:
         coefs["coef_mix_atm"] = alb_atm * f_atm
         coefs["coef_mix_aer"] = alb_aer * f_aer
         coefs["threshold"] = [sc.threshold for sc in scenarios]
-        coefs["phase_atm"] = idx_atm
-        coefs["phase_aer"] = idx_aer
-        coefs["extrap_width"][:, 0] = G.extrapolation_widths(tau[:, self.idx_up - 1], M)
-        coefs["extrap_width"][:, 1] = coefs["extrap_width"][:, 2] = G.extrapolation_widths(tau[:, self.idx_down], M)
+        coefs["phase_atm"] = mat_idx[:, 0]
+        coefs["phase_aer"] = mat_idx[:, 1]
+        coefs["extrap_width"][:, 0] = G.extrapolation_widths(tau[:, iu - 1], M)
+        coefs["extrap_width"][:, 1] = coefs["extrap_width"][:, 2] = G.extrapolation_widths(tau[:, idn], M)
         self.tau = tau
-        self.Ccoef = Ccoef
         return coefs
+
+    @property
+    def Ccoef(self) -> np.ndarray:
+        """The (S, 2, N) first-order coefficient planes of the batch, assembled on the host (sos_first_order's input)."""
+        w = self.P0w
+        C = np.empty((len(self.scenarios), 2, self.N))
+        np.multiply(self.P0tab[self.P0idx[:, 0]], w[:, 0:1], out=C[:, 0])
+        np.multiply(C[:, 0], w[:, 1:2], out=C[:, 1])
+        C[:, 1] += (self.P0tab[self.P0idx[:, 1]] * w[:, 2:3]) * w[:, 3:4]
+        return C
 
     def _register_phases(self):
         mats = list(self._mats)
@@ -254,7 +269,10 @@ class BatchSolver:
         self.engine.update(self.tau, coefs)
 
     def first_order(self, also_into=None):
-        self.I1 = self.engine.first_order(self.Ccoef, out=self.I1, also_into=also_into)
+        if SosEngine.table_fits(self.P0tab.shape[0], len(self.scenarios), self.N):
+            self.I1 = self.engine.first_order_from_table(self.P0tab, self.P0idx, self.P0w, out=self.I1, also_into=also_into)
+        else:   # (a single scenario with two phase functions: nothing to save, the planes go up as they are)
+            self.I1 = self.engine.first_order(self.Ccoef, out=self.I1, also_into=also_into)
         return self.I1
 
     def solve(self, keep_orders: int = 0, poll_every: int = 2, max_orders: Optional[int] = None):

@@ -392,6 +392,26 @@ class SosEngine:
                        "sos_first_order")
         return out
 
+    def first_order_from_table(self, P0tab: np.ndarray, idx: np.ndarray, weights: np.ndarray, out: Optional[torch.Tensor] = None,
+                               also_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """First order with the (S, 2, N) coefficient planes assembled on the device (sos_first_order_tab): P0tab (K, N) =
+        the distinct solar phase vectors of the batch, idx (S, 2) int32 = rows used by (atmosphere, aerosol), weights (S, 4) =
+        (alb_atm, f_atm, alb_aer, f_aer).  Same bits as first_order() on the host-assembled planes."""
+        tab = np.ascontiguousarray(P0tab, dtype=np.float64).reshape(-1, self.N)
+        ix = np.ascontiguousarray(idx, dtype=np.int32).reshape(self.S, 2)
+        w = np.ascontiguousarray(weights, dtype=np.float64).reshape(self.S, 4)
+        out = self.new_field(zero=True) if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sos_first_order_tab(self._plan, tab.ctypes.data, int(tab.shape[0]), ix.ctypes.data, w.ctypes.data,
+                                                    out.data_ptr(), also_into.data_ptr() if also_into is not None else None,
+                                                    self._stream), "sos_first_order_tab")
+        return out
+
+    @staticmethod
+    def table_fits(n_tab: int, S: int, N: int) -> bool:
+        """sos_first_order_tab's staging constraint (include/sos_b200.h)."""
+        return n_tab * N + 5 * S <= 2 * S * N
+
     def source(self, In1: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         out = self.new_field(zero=True) if out is None else out
         with torch.cuda.device(self.device):

@@ -309,3 +309,36 @@ def test_phase_sweeps_are_split_to_the_plan_limits():
         assert len(specs) <= D.MAX_PHASES_PER_PLAN
     assert len(parts) == 3     # 1 atmosphere + 15 aerosols per plan
     assert D.split_for_plan_limits(scs[:5], [0, 1, 2, 3, 4]) == [[0, 1, 2, 3, 4]]
+
+
+def test_batch_preparation_matches_the_per_scenario_formulas():
+    """BatchSolver._prepare (host side of a batch: no device needed): batched tau profiles == grid.tau_profile row by row,
+    and the table / rows / weights handed to sos_first_order_tab reproduce the first-order coefficient planes of
+    SOS_Aer_main_specular.py:52-53,104-292 (C0 = alb_atm P0_atm, C1 = C0 f_atm + alb_aer P0_aer f_aer) bit for bit."""
+    import bench
+    drivers = import_module("sos_b200").drivers
+    scen = bench.make_scenarios(sos, 24, rank=1, L=120, M=41)
+    bs = object.__new__(sos.BatchSolver)
+    bs._key = drivers._group_key(scen[0])
+    L, M, bs.idx_up, bs.idx_down, _ = bs._key
+    bs.L, bs.M, bs.N = L, M, 2 * M
+    bs.mu = sos.grid.mu_grid(M)
+    bs._phases = drivers.PhaseCache()
+    bs._device_phase = False
+    bs._mat_index, bs._mats, bs._mat_keys = {}, [], []
+    for _ in range(2):                       # the second pass reuses the host buffers of the first
+        coefs = bs._prepare(scen)
+    C = bs.Ccoef
+    assert bs.P0tab.shape[0] < 2 * len(scen) and sos.engine.SosEngine.table_fits(bs.P0tab.shape[0], len(scen), bs.N)
+    for i, sc in enumerate(scen):
+        tau = sos.grid.tau_profile(sc.tauStar_atm, sc.tauStar_aer, sc.z0, sc.z_up, sc.z_down, L)
+        assert np.array_equal(bs.tau[i], tau)
+        P0a, _ = sos.phase_matrices(sc.atm_phase[0], M, bs.mu, sc.mu0, sc.atm_phase[1])
+        P0e, _ = sos.phase_matrices(sc.aer_phase[0], M, bs.mu, sc.mu0, sc.aer_phase[1])
+        dtau_aer = sc.tauStar_aer / (bs.idx_down + 1 - bs.idx_up)
+        dtau_atm = sc.tauStar_atm / L
+        f_atm, f_aer = dtau_atm / (dtau_atm + dtau_aer), dtau_aer / (dtau_atm + dtau_aer)
+        assert np.array_equal(C[i, 0], P0a * sc.alb_atm)
+        assert np.array_equal(C[i, 1], (P0a * sc.alb_atm) * f_atm + (P0e * sc.alb_aer) * f_aer)
+        assert coefs["tauStar_tot"][i] == sc.tauStar_atm + sc.tauStar_aer
+        assert np.array_equal(bs.P0tab[bs.P0idx[i, 0]], P0a) and np.array_equal(bs.P0tab[bs.P0idx[i, 1]], P0e)
