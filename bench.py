@@ -54,8 +54,23 @@ def workload_config(S):
             "phase_functions": PHASES_NOTE, "convergence": "In/I < 1e-4 at TOA and surface (every scenario to its own order)"}
 
 
-def make_scenarios(sos, S, rank=0, L=L_DEFAULT, M=M_DEFAULT):
-    """Deterministic sweep tau_aer x mu0 x omega_aer x albedo x phase."""
+def cost_proxy(sc):
+    """Orders to convergence grow with the aerosol optical depth x single-scattering albedo and with the ground albedo."""
+    return sc.tauStar_aer * sc.alb_aer + 0.2 * sc.grd_alb
+
+
+def make_scenarios(sos, S, rank=0, L=L_DEFAULT, M=M_DEFAULT, world=1):
+    """Deterministic sweep tau_aer x mu0 x omega_aer x albedo x phase.
+
+    world == 1: members rank*S .. rank*S + S - 1 of the sweep.  world > 1 (bench.py --gpus N): the job's world*S members
+    (0 .. world*S - 1) sorted by the cost proxy and dealt in serpentine rounds, so that every rank solves a batch of the same
+    make-up (the step time of the job is the slowest rank's) -- how the full sweep is dealt, too."""
+    if world > 1:
+        job = make_scenarios(sos, world * S, 0, L, M)
+        order = sorted(range(world * S), key=lambda i: (-cost_proxy(job[i]), i))
+        # serpentine: rounds run 0 .. world-1, then world-1 .. 0 (no rank always gets the costliest member of a round)
+        mine = [order[r * world + (rank if r % 2 == 0 else world - 1 - rank)] for r in range(S)]
+        return [job[i] for i in mine]
     taus = np.linspace(0.0075, 0.5, 10)
     mu0s = np.linspace(0.1, 1.0, 10)
     oms = np.linspace(0.7, 1.0, 10)
@@ -384,7 +399,7 @@ def main():
     S, L, M = args.scenarios, L_DEFAULT, M_DEFAULT
     N = 2 * M
 
-    scen = make_scenarios(sos, S, rank)
+    scen = make_scenarios(sos, S, rank, world=world)
     bs = sos.BatchSolver(scen, device=dev)       # plan + phase operands resident
     # scenarios on which the reference itself would die with IndexError (blend-search overrun, Q11)
     # are not valid workload members: swap their aerosol phase function for HG(0.7) once, up front
@@ -637,6 +652,9 @@ def main():
             "details": {"orders_per_scenario": [int(n_orders.min()), int(n_orders.max())], "scenario_orders_per_step": int(np.sum(n_orders - 1)),
                         "l2": "256 MB flush between timed steps; per-step working set %.0f MB > 126 MB L2" % (3 * S * L * eng.ld * 8 / 1e6),
                         "scenarios_swapped_for_blend_overrun": n_swapped,
+                        "dealing": ("members 0..%d of the sweep" % (S - 1)) if world == 1 else
+                                   ("members 0..%d of the sweep sorted by the cost proxy tau_aer*omega_aer + 0.2*albedo and dealt in serpentine rounds "
+                                    "to the %d ranks (every rank a batch of the same make-up; no data-path collective)" % (world * S - 1, world)),
                         "contraction": ("folded (centrosymmetric operands, defect %.1e)" % eng.fold_defect) if folded else "general",
                         "generated_source": generated,
                         "low_rank_operands": [int(r) for r in getattr(eng, "lowrank", [])]},
@@ -678,7 +696,7 @@ def run_full_sweep(args, sos, torch, dist, dev, rank, world, S):
     plan per rank (BatchSolver.update).  Host work (tau profiles, coefficients, results) is inside the timed region."""
     total = args.full_sweep
     allsc = make_scenarios(sos, total, 0)
-    order = sorted(range(total), key=lambda i: -(allsc[i].tauStar_aer * allsc[i].alb_aer + 0.2 * allsc[i].grd_alb))
+    order = sorted(range(total), key=lambda i: -cost_proxy(allsc[i]))
     batches = [order[i:i + S] for i in range(0, total - total % S, S)]          # whole batches only
     mine = batches[rank::world]
     bs = sos.BatchSolver([allsc[i] for i in mine[0]], device=dev)
