@@ -1250,9 +1250,10 @@ sweep_apply2_kernel(const GridDev g, const SrcGen sg, const double* __restrict__
 // projections of the zone columns (final values) + the apply pass's slots.
 constexpr int ZONE_ROWS = 8;
 #ifndef SOS_ZONE_UP
-#define SOS_ZONE_UP 32
+#define SOS_ZONE_UP 31
 #endif
-constexpr int ZONE_UP = SOS_ZONE_UP;  // upward columns next to mu = 0+ fetched eagerly for the blend search (and projected here)
+constexpr int ZONE_UP = SOS_ZONE_UP;  // upward columns next to mu = 0+ fetched eagerly for the blend search (and projected here): with
+                                      // column M itself one warp-wide step of every loop over them
 
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
@@ -1276,8 +1277,8 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
   const sos_scenario* __restrict__ scp = g.scen + s;
   const int active = g.state[s].active;
   const int op = scp->phase_atm;
-  int region = 0;
-  while (region + 1 < g.nreg && t >= g.rstart[region + 1]) ++region;
+  // (at most three regions: rstart[nreg] = L)
+  const int region = (g.nreg > 1 && t >= g.rstart[1] ? 1 : 0) + (g.nreg > 2 && t >= g.rstart[2] ? 1 : 0);
   const int idxw = scp->extrap_width[region];
   const double coef_atm = scp->coef_atm;
   if (!active) return;
@@ -1351,7 +1352,17 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
       for (int i = lane; i < idxw; i += 32) {
         const int m = M - 1 - i;  // sources (< M - idx) and targets (>= M - idx) never overlap
         double v = 0.0;
-        for (int k = 0; k < ns; ++k) v += W[i * ns + k] * row[src0 + k];
+        if (ns == 5) {  // (every width >= 5: the parabola through five columns; same operations in the same order)
+          const double* __restrict__ w5 = W + i * 5;
+          const double* r5 = row + src0;
+          v = fma(w5[0], r5[0], v);
+          v = fma(w5[1], r5[1], v);
+          v = fma(w5[2], r5[2], v);
+          v = fma(w5[3], r5[3], v);
+          v = fma(w5[4], r5[4], v);
+        } else {
+          for (int k = 0; k < ns; ++k) v = fma(W[i * ns + k], row[src0 + k], v);
+        }
         const bool std_col = m < min(M - 1, g.first_small);
         const double raw = row[m];
         row[m] = v;
@@ -1437,10 +1448,15 @@ sweep_zone_kernel(const GridDev g, const SrcGen sg, const double* __restrict__ J
       p0 = fma(v, Ut[m], p0);
       p1 = fma(v, Ut[sg.ldr + m], p1);
     }
+    // both sums with one butterfly: the lower half warp finishes p0, the upper one p1 (fixed tree: deterministic)
+    const bool upper = lane >= 16;
+    double mine = upper ? p1 : p0;
+    mine += shfl_xor_d(upper ? p0 : p1, 16);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { p0 += shfl_xor_d(p0, o); p1 += shfl_xor_d(p1, o); }
+    for (int o = 8; o > 0; o >>= 1) mine += shfl_xor_d(mine, o);
+    const double other = __shfl_sync(0xffffffffu, mine, 16);
     if (lane == 0)
-      *reinterpret_cast<double2*>(sg.cj_out + (static_cast<size_t>(s) * sg.Lp + t) * 2) = make_double2(coef_atm * p0, coef_atm * p1);
+      *reinterpret_cast<double2*>(sg.cj_out + (static_cast<size_t>(s) * sg.Lp + t) * 2) = make_double2(coef_atm * mine, coef_atm * other);
   }
 
   // ---- convergence ratios on the TOA / surface rows (whole half-row, read back from global) ----
