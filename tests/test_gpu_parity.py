@@ -671,3 +671,31 @@ def test_lowrank_operand_rows_match_the_dense_contraction(sos, monkeypatch):
     J0 = sos.Jn_NumInt(2, x, tau, mu, 0.5, 0.5, P, 0.9, M)
     sos.clear_cache()
     assert relmax(J1, J0) < 1e-13
+
+
+@pytest.mark.parametrize("surface", ["specular", "lambert"])
+def test_first_order_entry_points_agree_bit_for_bit(sos, surface):
+    """sos_first_order_tab (coefficient planes assembled on the device from the table of distinct solar phase vectors) and
+    sos_first_order2 (planes assembled on the host, SOS_Aer_main_specular.py:52-53) produce the same bits, and the second
+    destination of the first order (the accumulator of the order loop) holds the same field."""
+    import torch
+    scen = [sos.Scenario(nb_layers=90, nb_angles=75, tauStar_atm=0.124, tauStar_aer=0.03 + 0.05 * i, mu0=(0.2, 0.5, 0.9)[i % 3],
+                         alb_aer=0.8 + 0.02 * i, grd_alb=0.1 * (i % 4), atm_phase=("rayleigh", 0.0),
+                         aer_phase=(("hg", 0.5), ("hg", 0.7), ("fwc", 0.0))[i % 3], surface=surface) for i in range(9)]
+    bs = sos.BatchSolver(scen)
+    eng = bs.engine
+    assert eng.table_fits(bs.P0tab.shape[0], len(scen), eng.N) and bs.P0tab.shape[0] < 2 * len(scen)
+    acc = eng.new_field(zero=True)
+    a = bs.first_order(also_into=acc).clone()
+    b = eng.first_order(bs.Ccoef)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert torch.equal(acc[:, : eng.N], a[:, : eng.N])
+    # a single scenario with two phase functions does not fit the table's staging: the planes go up as they are
+    one = sos.BatchSolver(scen[:1])
+    assert not one.engine.table_fits(one.P0tab.shape[0], 1, one.engine.N)
+    r1 = one.results(one.solve(), quadratures=False)[0]
+    rb = bs.results(bs.solve(), quadratures=False)[0]
+    assert r1.n == rb.n and relmax(r1.I, rb.I) < 1e-12
+    one.engine.close()
+    bs.engine.close()
