@@ -59,18 +59,28 @@ def cost_proxy(sc):
     return sc.tauStar_aer * sc.alb_aer + 0.2 * sc.grd_alb
 
 
+def job_deal(sos, S, world, L=L_DEFAULT, M=M_DEFAULT, cost=None):
+    """The world*S members (0 .. world*S - 1) of the sweep a multi-GPU job solves, and who solves which: members sorted by
+    cost (the proxy, or `cost[i]` = measured orders to convergence with the proxy as the tie-break) and dealt in serpentine
+    rounds -- 0 .. world-1, then world-1 .. 0, so that no rank always gets the costliest member of a round.  Every rank gets
+    a batch of the same make-up: the step time of the job is the slowest rank's.  Returns (job, [members of rank r])."""
+    job = make_scenarios(sos, world * S, 0, L, M)
+    if cost is None:
+        key = lambda i: (-cost_proxy(job[i]), i)
+    else:
+        key = lambda i: (-cost[i], -cost_proxy(job[i]), i)
+    order = sorted(range(world * S), key=key)
+    return job, [[order[r * world + (rank if r % 2 == 0 else world - 1 - rank)] for r in range(S)] for rank in range(world)]
+
+
 def make_scenarios(sos, S, rank=0, L=L_DEFAULT, M=M_DEFAULT, world=1):
     """Deterministic sweep tau_aer x mu0 x omega_aer x albedo x phase.
 
-    world == 1: members rank*S .. rank*S + S - 1 of the sweep.  world > 1 (bench.py --gpus N): the job's world*S members
-    (0 .. world*S - 1) sorted by the cost proxy and dealt in serpentine rounds, so that every rank solves a batch of the same
-    make-up (the step time of the job is the slowest rank's) -- how the full sweep is dealt, too."""
+    world == 1: members rank*S .. rank*S + S - 1 of the sweep.  world > 1 (bench.py --gpus N): rank's share of the job's
+    world*S members, see job_deal -- how the full sweep is dealt, too."""
     if world > 1:
-        job = make_scenarios(sos, world * S, 0, L, M)
-        order = sorted(range(world * S), key=lambda i: (-cost_proxy(job[i]), i))
-        # serpentine: rounds run 0 .. world-1, then world-1 .. 0 (no rank always gets the costliest member of a round)
-        mine = [order[r * world + (rank if r % 2 == 0 else world - 1 - rank)] for r in range(S)]
-        return [job[i] for i in mine]
+        job, deals = job_deal(sos, S, world, L, M)
+        return [job[i] for i in deals[rank]]
     taus = np.linspace(0.0075, 0.5, 10)
     mu0s = np.linspace(0.1, 1.0, 10)
     oms = np.linspace(0.7, 1.0, 10)
@@ -403,7 +413,25 @@ def main():
     bs = sos.BatchSolver(scen, device=dev)       # plan + phase operands resident
     # scenarios on which the reference itself would die with IndexError (blend-search overrun, Q11)
     # are not valid workload members: swap their aerosol phase function for HG(0.7) once, up front
-    st = bs.solve(poll_every=2).status
+    res0 = bs.solve(poll_every=2)
+    st = res0.status
+    dealt_by = "the cost proxy tau_aer*omega_aer + 0.2*albedo"
+    if world > 1:
+        # second deal, by measured cost: the orders to convergence of this pilot solve (every rank learns every member's)
+        job, deals = job_deal(sos, S, world)
+        loc = torch.tensor(np.stack([np.asarray(res0.n_orders, dtype=np.int64), (st & 1).astype(np.int64)]), device=dev)
+        got = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(got, loc)
+        n_of, overrun = np.zeros(world * S, dtype=np.int64), np.zeros(world * S, dtype=np.int64)
+        for r in range(world):
+            g = got[r].cpu().numpy()
+            n_of[deals[r]], overrun[deals[r]] = g[0], g[1]
+        _, deals = job_deal(sos, S, world, cost=n_of)
+        scen = [job[i] for i in deals[rank]]
+        st = overrun[deals[rank]]
+        bs.engine.close()
+        bs = sos.BatchSolver(scen, device=dev)
+        dealt_by = "their orders to convergence (measured by a pilot solve of the first deal, which went by the cost proxy tau_aer*omega_aer + 0.2*albedo)"
     n_swapped = int(np.sum((st & 1) != 0))
     if n_swapped:
         import dataclasses
@@ -653,8 +681,8 @@ def main():
                         "l2": "256 MB flush between timed steps; per-step working set %.0f MB > 126 MB L2" % (3 * S * L * eng.ld * 8 / 1e6),
                         "scenarios_swapped_for_blend_overrun": n_swapped,
                         "dealing": ("members 0..%d of the sweep" % (S - 1)) if world == 1 else
-                                   ("members 0..%d of the sweep sorted by the cost proxy tau_aer*omega_aer + 0.2*albedo and dealt in serpentine rounds "
-                                    "to the %d ranks (every rank a batch of the same make-up; no data-path collective)" % (world * S - 1, world)),
+                                   ("members 0..%d of the sweep sorted by %s and dealt in serpentine rounds to the %d ranks (every rank a batch "
+                                    "of the same make-up; no data-path collective)" % (world * S - 1, dealt_by, world)),
                         "contraction": ("folded (centrosymmetric operands, defect %.1e)" % eng.fold_defect) if folded else "general",
                         "generated_source": generated,
                         "low_rank_operands": [int(r) for r in getattr(eng, "lowrank", [])]},

@@ -357,3 +357,11 @@ def test_bench_deals_the_job_evenly_over_the_ranks():
     means = [np.mean([bench.cost_proxy(sc) for sc in b]) for b in dealt]
     assert (max(means) - min(means)) / np.mean(means) < 0.01
     assert [key(sc) for sc in bench.make_scenarios(sos, S, 0, world=1)] == [key(sc) for sc in job[:S]]
+    # the second deal of bench.py goes by measured orders to convergence: every rank gets the same distribution of them
+    rng = np.random.default_rng(5)
+    n_of = rng.integers(7, 24, size=world * S)
+    job2, deals = bench.job_deal(sos, S, world, cost=n_of)
+    assert sorted(i for d in deals for i in d) == list(range(world * S)) and [key(sc) for sc in job2] == [key(sc) for sc in job]
+    hist = [np.bincount(n_of[d], minlength=24) for d in deals]
+    assert max(np.abs(h - hist[0]).max() for h in hist) <= 2
+    assert max(int(n_of[d].sum()) for d in deals) - min(int(n_of[d].sum()) for d in deals) <= 16
