@@ -314,20 +314,28 @@ class BatchSolver:
             fu = q["flux_up"][:, 0] - k * alb * np.exp(-(2 * tl - t0) / mu0)
             toa = -fd - fu
         tau_out = self.tau.copy()   # (self.tau is a buffer reused by the next update())
+        if np.any(res.status & _lib.STATUS_BLEND_OVERRUN):
+            raise IndexError("mu->0 blend search ran off the row (reference: IndexError, "
+                             "SOS_Aer_main_specular.py:404)")
+        # per-scenario records: NumPy scalars and rows are unpacked once for the whole batch (a sweep calls this per batch)
+        n_l = [int(v) for v in res.n_orders]
+        ratio_l = np.maximum(res.ratio_toa, res.ratio_surf).tolist()
+        status_l = res.status.tolist()
+        tau_l = list(tau_out)
+        I_l = list(I) if fields else [None] * len(n_l)
+        if q is not None:
+            fu, fd, nf, df = list(q["flux_up"]), list(q["flux_down"]), list(q["net_flux"]), list(q["diffusivity"])
+            hr = list(q["heating_rate"]) if q["heating_rate"] is not None else [None] * len(n_l)
+            toa_l = toa.tolist()
         out = []
-        for i, sc in enumerate(self.scenarios):
-            r = DriverResult(I=I[i] if fields else None, n=int(res.n_orders[i]), tau=tau_out[i], mu=self.mu,
-                             z_profile=self.z, idx_up=self.idx_up, idx_down=self.idx_down,
-                             ratio=float(max(res.ratio_toa[i], res.ratio_surf[i])), status=int(res.status[i]))
+        for i in range(len(self.scenarios)):
+            r = DriverResult(I=I_l[i], n=n_l[i], tau=tau_l[i], mu=self.mu, z_profile=self.z, idx_up=self.idx_up,
+                             idx_down=self.idx_down, ratio=ratio_l[i], status=status_l[i])
             if q is not None:
-                r.flux_up, r.flux_down, r.net_flux = q["flux_up"][i], q["flux_down"][i], q["net_flux"][i]
-                r.diffusivity, r.heating_rate = q["diffusivity"][i], q["heating_rate"][i]
-                r.toa_net_flux = float(toa[i])
+                r.flux_up, r.flux_down, r.net_flux, r.diffusivity, r.heating_rate = fu[i], fd[i], nf[i], df[i], hr[i]
+                r.toa_net_flux = toa_l[i]
             if orders is not None:
                 r.I_saved = [I1[i]] + [orders[k, i] for k in range(min(keep_orders, r.n - 1))]
-            if r.status & _lib.STATUS_BLEND_OVERRUN:
-                raise IndexError("mu->0 blend search ran off the row (reference: IndexError, "
-                                 "SOS_Aer_main_specular.py:404)")
             out.append(r)
         return out
 
