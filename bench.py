@@ -7,15 +7,18 @@
 Workload (BASELINE.json configs[4], the critical-albedo style batch sweep): S independent
 three-region scenarios per GPU on the reference's default grid (800 layers x 1002 mu), spanning
 tau_aer x mu0 x omega_aer x surface albedo x aerosol phase function (HG / log-normal Mie stand-in / FWC); every GPU solves its own S
-scenarios with no data-path collective (scaling: weak).  A "step" is one whole solve of the batch:
+scenarios with no data-path collective (scaling: weak).  With N GPUs the job is members 0 .. N*S-1 of the sweep, dealt so that
+every rank gets a batch of the same make-up (job_deal: sorted by cost, serpentine rounds; first by a cost proxy, then by the
+orders to convergence a pilot solve measured -- the line's details.dealing says so).  A "step" is one whole solve of the batch:
 closed-form first order + the order loop to In/I < 1e-4 for every scenario.
 
   metric  = sum over scenarios and orders n >= 2 of L*N^2  /  time     
   value   : inputs already resident in HBM (plan, phase operands, coefficients uploaded before)
-  e2e     : the public API call with HOST arrays in / NumPy out per step: plan creation, H2D of tau,
-            coefficients and phase matrices, solve, D2H of the flux / diffusivity / heating-rate
-            profiles, order counts and TOA net flux of every scenario (what a forcing sweep returns;
-            the reference's SOS_Aer_radiative_forcing returns one float per solve)
+  e2e     : the public API call with HOST scenario values in / NumPy out per step on a resident plan: BatchSolver.update
+            (tau profiles, per-scenario records, the table of solar phase vectors the device assembles the first-order
+            coefficients from: H2D), solve, D2H of the flux / diffusivity / heating-rate profiles, order counts and TOA
+            net flux of every scenario (what a forcing sweep returns; the reference's SOS_Aer_radiative_forcing returns one
+            float per solve).  new_plan_per_batch_ms / cold_ms: the same with a new plan per batch / from a cold process
   roofline: the dominant kernel of the timed steps, timed with CUDA events on the launching stream inside them.  With a
             Rayleigh atmosphere (the default workload) that is the apply pass of the layer sweeps (sweep_apply2_kernel: HBM
             bound, peak = MEASURED_PEAKS.json hbm_gbs): the molecular rows rebuild their source from two coefficients per

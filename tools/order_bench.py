@@ -1,5 +1,5 @@
 """Time the order loop of bench.py's batch (no e2e, no CPU leg): per-class CUDA-event times of one solve.
-Usage: python tools/strip_bench.py [S] [repeats]   (env SOS_B200_GENSRC=0 for the chunked scan)"""
+Usage: python tools/order_bench.py [S] [repeats]   (env SOS_B200_GENSRC=0 for the chunked scan)"""
 import ctypes as C
 import os
 import sys
@@ -19,7 +19,7 @@ scen = bench.make_scenarios(sos, S)
 bs = sos.BatchSolver(scen)
 eng = bs.engine
 lib = sos._lib.load()
-print("strip", eng.gensrc_enabled, "generated", eng.generated_source, flush=True)
+print("gensrc", eng.gensrc_enabled, "generated", eng.generated_source, flush=True)
 res = bs.solve(poll_every=2)
 torch.cuda.synchronize()
 norders = int(np.sum(res.n_orders - 1))
