@@ -185,15 +185,15 @@ class BatchSolver:
         self._new_mats = 0
         # phase tables: one look-up per DISTINCT (phase, mu0) of the batch; a scenario refers to rows of the table
         tab_rows = []
-        p0_idx = np.empty((S, 2), dtype=np.int32)
-        mat_idx = np.empty((S, 2), dtype=np.int32)
+        hits = []          # (table row, operand index) of atmosphere and aerosol, scenario after scenario
         seen = {}
-        for i, sc in enumerate(scenarios):
-            for j, spec in enumerate((sc.atm_phase, sc.aer_phase)):
-                key = (spec if isinstance(spec[0], str) else id(spec[1]), sc.mu0)
+        for sc in scenarios:
+            mu0 = sc.mu0
+            for spec in (sc.atm_phase, sc.aer_phase):
+                key = (spec if isinstance(spec[0], str) else id(spec[1]), mu0)
                 hit = seen.get(key)
                 if hit is None:
-                    P0, P, k = self._phases.get(spec, M, self.mu, sc.mu0, need_P=not self._device_phase)
+                    P0, P, k = self._phases.get(spec, M, self.mu, mu0, need_P=not self._device_phase)
                     if k not in self._mat_index:
                         self._mat_index[k] = len(self._mats)
                         self._mats.append(P)
@@ -201,8 +201,9 @@ class BatchSolver:
                         self._new_mats += 1
                     hit = seen[key] = (len(tab_rows), self._mat_index[k])
                     tab_rows.append(P0)
-                p0_idx[i, j] = hit[0]
-                mat_idx[i, j] = hit[1]
+                hits.append(hit)
+        both = np.array(hits, dtype=np.int32).reshape(S, 2, 2)
+        p0_idx, mat_idx = np.ascontiguousarray(both[:, :, 0]), both[:, :, 1]
         tab = getattr(self, "_tab_buf", None)
         if tab is None or tab.shape[0] < len(tab_rows):
             tab = self._tab_buf = np.empty((max(len(tab_rows), 16), self.N))

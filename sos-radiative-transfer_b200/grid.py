@@ -81,7 +81,7 @@ def extrapolation_widths(tau_ref, nb_angles: int) -> np.ndarray:
     """extrapolation_width for an array of reference optical depths (same thresholds, same truncation)."""
     t = np.asarray(tau_ref, dtype=np.float64)
     f = np.select([t <= 0.0625, t <= 1, t < 4], _WIDTH_FACTORS[:3], default=_WIDTH_FACTORS[3])
-    return np.array([int(x * nb_angles) for x in f], dtype=np.int32)
+    return (f * nb_angles).astype(np.int32)   # (positive products: the same truncation as int(f * nb_angles))
 
 
 def _extrapolation_weights(mu_down: np.ndarray, width: int) -> np.ndarray:
