@@ -342,6 +342,17 @@ def test_batch_preparation_matches_the_per_scenario_formulas():
         assert np.array_equal(C[i, 1], (P0a * sc.alb_atm) * f_atm + (P0e * sc.alb_aer) * f_aer)
         assert coefs["tauStar_tot"][i] == sc.tauStar_atm + sc.tauStar_aer
         assert np.array_equal(bs.P0tab[bs.P0idx[i, 0]], P0a) and np.array_equal(bs.P0tab[bs.P0idx[i, 1]], P0e)
+        # widths of the mu -> 0- extrapolation per region (SOS_Aer_main_specular.py:342-345) and the operands of the scenario
+        assert coefs["extrap_width"][i, 0] == sos.extrapolation_width(float(tau[bs.idx_up - 1]), M)
+        assert coefs["extrap_width"][i, 1] == coefs["extrap_width"][i, 2] == sos.extrapolation_width(float(tau[bs.idx_down]), M)
+        for spec, col in ((sc.atm_phase, "phase_atm"), (sc.aer_phase, "phase_aer")):
+            assert bs._mat_keys[coefs[col][i]][0] == spec[0]
+        assert coefs["mu0"][i] == sc.mu0 and coefs["grd_alb"][i] == sc.grd_alb and coefs["coef_atm"][i] == sc.alb_atm
+        assert coefs["coef_mix_atm"][i] == sc.alb_atm * f_atm and coefs["coef_mix_aer"][i] == sc.alb_aer * f_aer
+    # every width class the thresholds distinguish, scalar vs batched
+    for M_ in (21, 101, 501, 1201):
+        ts = np.array([0.0, 0.01, 0.0625, 0.0626, 0.5, 1.0, 1.0001, 3.99, 4.0, 30.0])
+        assert [int(w) for w in sos.grid.extrapolation_widths(ts, M_)] == [sos.extrapolation_width(float(t_), M_) for t_ in ts]
 
 
 def test_bench_deals_the_job_evenly_over_the_ranks():
