@@ -76,6 +76,23 @@ def job_deal(sos, S, world, L=L_DEFAULT, M=M_DEFAULT, cost=None):
     return job, [[order[r * world + (rank if r % 2 == 0 else world - 1 - rank)] for r in range(S)] for rank in range(world)]
 
 
+def redeal_by_orders(sos, S, world, rank, n_orders, overrun, dist, torch, dev, L=L_DEFAULT, M=M_DEFAULT):
+    """Second deal of a multi-GPU job, by measured cost: `n_orders` / `overrun` are this rank's per-scenario orders to
+    convergence and blend-overrun bits from a pilot solve of the FIRST deal (job_deal by the proxy).  One all-gather of
+    2*S integers per rank tells every rank every member's count; all ranks then compute the same second deal.  Returns
+    (this rank's scenarios, their overrun bits)."""
+    job, deals = job_deal(sos, S, world, L, M)
+    loc = torch.tensor(np.stack([np.asarray(n_orders, dtype=np.int64), np.asarray(overrun, dtype=np.int64)]), device=dev)
+    got = [torch.empty_like(loc) for _ in range(world)]
+    dist.all_gather(got, loc)
+    n_of, ov = np.zeros(world * S, dtype=np.int64), np.zeros(world * S, dtype=np.int64)
+    for r in range(world):
+        g = got[r].cpu().numpy()
+        n_of[deals[r]], ov[deals[r]] = g[0], g[1]
+    _, deals = job_deal(sos, S, world, L, M, cost=n_of)
+    return [job[i] for i in deals[rank]], ov[deals[rank]]
+
+
 def make_scenarios(sos, S, rank=0, L=L_DEFAULT, M=M_DEFAULT, world=1):
     """Deterministic sweep tau_aer x mu0 x omega_aer x albedo x phase.
 
@@ -421,17 +438,7 @@ def main():
     dealt_by = "the cost proxy tau_aer*omega_aer + 0.2*albedo"
     if world > 1:
         # second deal, by measured cost: the orders to convergence of this pilot solve (every rank learns every member's)
-        job, deals = job_deal(sos, S, world)
-        loc = torch.tensor(np.stack([np.asarray(res0.n_orders, dtype=np.int64), (st & 1).astype(np.int64)]), device=dev)
-        got = [torch.empty_like(loc) for _ in range(world)]
-        dist.all_gather(got, loc)
-        n_of, overrun = np.zeros(world * S, dtype=np.int64), np.zeros(world * S, dtype=np.int64)
-        for r in range(world):
-            g = got[r].cpu().numpy()
-            n_of[deals[r]], overrun[deals[r]] = g[0], g[1]
-        _, deals = job_deal(sos, S, world, cost=n_of)
-        scen = [job[i] for i in deals[rank]]
-        st = overrun[deals[rank]]
+        scen, st = redeal_by_orders(sos, S, world, rank, res0.n_orders, st & 1, dist, torch, dev)
         bs.engine.close()
         bs = sos.BatchSolver(scen, device=dev)
         dealt_by = "their orders to convergence (measured by a pilot solve of the first deal, which went by the cost proxy tau_aer*omega_aer + 0.2*albedo)"

@@ -61,6 +61,21 @@ def _worker(rank, world, port, N, M, rows):
             assert [o[2] for o in out] == [i % world for i in range(len(scen))]
         else:
             assert out is None
+        # ---- bench.py's second deal of a multi-GPU job: every rank reports the orders to convergence of its members of the
+        #      first deal, every rank computes the same second deal (same make-up of order counts on every rank) ----
+        import bench
+        S = 12
+        job, deals = bench.job_deal(sos, S, world, 40, 21)
+        truth = np.array([7 + (5 * i) % 11 for i in range(world * S)])          # "measured" orders of the job's members
+        mine, ov = bench.redeal_by_orders(sos, S, world, rank, truth[deals[rank]], np.zeros(S, dtype=np.int64), dist, torch,
+                                          torch.device("cpu"), 40, 21)
+        _, want = bench.job_deal(sos, S, world, 40, 21, cost=truth)
+        key = lambda sc: (sc.tauStar_aer, sc.mu0, sc.alb_aer, sc.grd_alb, sc.aer_phase[0])
+        assert [key(sc) for sc in mine] == [key(job[i]) for i in want[rank]] and not ov.any()
+        tot = torch.tensor([int(truth[want[rank]].sum())])
+        both = [torch.empty_like(tot) for _ in range(world)]
+        dist.all_gather(both, tot)
+        assert abs(int(both[0]) - int(both[1])) <= 4, "the second deal left the ranks with different work"
     finally:
         dist.destroy_process_group()
 
